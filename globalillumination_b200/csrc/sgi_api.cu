@@ -1,0 +1,363 @@
+// sgi_api.cu — the C ABI of include/shadowgi.h: context lifecycle, uploads, pass orchestration, readback.
+// The passes replace the reference's per-frame free functions (ShadowMapping/src/main.cpp:350-414,
+// SoftShadowMapping/src/main.cpp:756-811,925-1022, ShadowVolumes/src/main.cpp:120-206); see the header for
+// the entry-point -> reference mapping.  There is no CPU fallback: without a CUDA device sgi_create fails.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "sgi_internal.cuh"
+
+static int ensure_buf(sgi_ctx* ctx, int which, size_t bytes) {
+  if (ctx->buf[which] && ctx->buf_bytes[which] == bytes) return SGI_OK;
+  if (ctx->buf[which]) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->buf[which]); ctx->buf[which] = nullptr; }
+  ctx->buf_bytes[which] = 0;
+  if (bytes == 0) return SGI_OK;
+  cudaError_t e = cudaMalloc(&ctx->buf[which], bytes);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SGI_ERR_NOMEM; }
+  ctx->buf_bytes[which] = bytes;
+  return SGI_OK;
+}
+
+// ---- timing ring ---------------------------------------------------------------------------------------------
+int sgi_timing_drain(sgi_ctx* ctx) {
+  for (int p = 0; p < SGI_PASS_COUNT_; p++) {
+    for (int k = 0; k < ctx->ev_n[p]; k++) {
+      float ms = 0.f;
+      cudaEventSynchronize(ctx->ev[p][k][1]);
+      if (cudaEventElapsedTime(&ms, ctx->ev[p][k][0], ctx->ev[p][k][1]) == cudaSuccess) { ctx->pass_ms[p] += ms; ctx->pass_calls[p]++; }
+    }
+    ctx->ev_n[p] = 0;
+  }
+  return SGI_OK;
+}
+int sgi_timing_begin(sgi_ctx* ctx, int pass) {
+  if (!ctx->timing) return -1;
+  if (ctx->ev_n[pass] >= SGI_EV_RING) sgi_timing_drain(ctx);
+  int slot = ctx->ev_n[pass];
+  cudaEventRecord(ctx->ev[pass][slot][0], ctx->stream);
+  return slot;
+}
+void sgi_timing_end(sgi_ctx* ctx, int pass, int slot) {
+  if (slot < 0) return;
+  cudaEventRecord(ctx->ev[pass][slot][1], ctx->stream);
+  ctx->ev_n[pass] = slot + 1;
+}
+
+static int check_overflow(sgi_ctx* ctx) {
+  if (!ctx->overflow_pending || !ctx->h_flags) return SGI_OK;
+  ctx->overflow_pending = false;
+  if (ctx->h_flags[0]) {
+    ctx->h_flags[0] = 0;
+    ctx->gbuffer_valid = false; ctx->shadow_map_valid = false;
+    ctx->err = "tile list overflow: the lists were re-sized, run the frame again";
+    return SGI_ERR_OVERFLOW;       // sgi_raster_run grows d_pairs from h_flags[1] on the next call
+  }
+  return SGI_OK;
+}
+
+extern "C" {
+
+const char* sgi_version(void) { return "shadowgi-b200 0.1 (sm_100a)"; }
+
+void sgi_default_params(sgi_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->technique = SGI_TECH_HARD;
+  p->shadow_map_width = p->shadow_map_height = 2048;   // ShadowMapping/src/main.cpp:90-91
+  p->shadow_intensity = 0.25f;                         // :877
+  p->kernel_order = 7;                                 // Filter order, :859
+  p->penumbra_size = 1;                                // :871
+  p->blocker_search_size = 7;                          // SoftShadowMapping/src/main.cpp:1611
+  p->kernel_size = 15;                                 // :1612
+  p->light_source_radius = 8;                          // :1598,1613 (16/2)
+  p->max_search = 16;                                  // ShadowMapping/src/main.cpp:869
+  p->depth_threshold = 0.0f;
+  p->z_near = 1; p->z_far = 1000;
+  p->polygon_offset_factor = 4.0f; p->polygon_offset_units = 20.0f;   // :246
+  p->sv_depth_func = SGI_DEPTH_LEQUAL;
+  p->sv_infinity = 100;                                // ShadowVolumes/src/main.cpp:469
+}
+
+int sgi_create(sgi_ctx** out, int device) {
+  if (!out) return SGI_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return SGI_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return SGI_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return SGI_ERR_CUDA;
+  sgi_ctx* ctx = new (std::nothrow) sgi_ctx();
+  if (!ctx) return SGI_ERR_NOMEM;
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
+  ctx->stream = ctx->own_stream;
+  sgi_default_params(&ctx->params);
+  for (int p = 0; p < SGI_PASS_COUNT_; p++) {
+    ctx->ev_n[p] = 0; ctx->pass_ms[p] = 0; ctx->pass_calls[p] = 0;
+    for (int k = 0; k < SGI_EV_RING; k++) { ctx->ev[p][k][0] = nullptr; ctx->ev[p][k][1] = nullptr; }
+  }
+  ctx->light_pos[0] = ctx->light_pos[1] = ctx->light_pos[2] = 0.f;
+  *out = ctx;
+  return SGI_OK;
+}
+
+int sgi_destroy(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
+  void* ptrs[] = {ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->d_light_trans, ctx->d_rec, ctx->d_attr, ctx->d_ovf_base, ctx->d_counters,
+                  ctx->d_tile_cnt, ctx->d_tile_off, ctx->d_tile_fill, ctx->d_pairs, ctx->d_scan_tmp};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);
+  for (int p = 0; p < SGI_PASS_COUNT_; p++)
+    for (int k = 0; k < SGI_EV_RING; k++) { if (ctx->ev[p][k][0]) cudaEventDestroy(ctx->ev[p][k][0]); if (ctx->ev[p][k][1]) cudaEventDestroy(ctx->ev[p][k][1]); }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return SGI_OK;
+}
+
+int sgi_set_stream(sgi_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SGI_OK;
+}
+
+int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, const int32_t* idx, int32_t T) {
+  if (!ctx || V < 0 || T < 0 || (V > 0 && (!xyz || !nrm)) || (T > 0 && !idx)) { if (ctx) ctx->err = "sgi_set_mesh: bad arguments"; return SGI_ERR_INVALID; }
+  for (int64_t k = 0; k < (int64_t)T * 3; k++)
+    if (idx[k] < 0 || idx[k] >= V) { ctx->err = "sgi_set_mesh: index out of range"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (V != ctx->V) {
+    if (ctx->d_xyz) cudaFree(ctx->d_xyz);
+    if (ctx->d_nrm) cudaFree(ctx->d_nrm);
+    ctx->d_xyz = ctx->d_nrm = nullptr;
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_xyz, (size_t)(V > 0 ? V : 1) * 12));
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_nrm, (size_t)(V > 0 ? V : 1) * 12));
+  }
+  if (T != ctx->T) {
+    if (ctx->d_idx) cudaFree(ctx->d_idx);
+    ctx->d_idx = nullptr;
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_idx, (size_t)(T > 0 ? T : 1) * 12));
+  }
+  ctx->V = V; ctx->T = T;
+  if (V > 0) {
+    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
+    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm, nrm, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (T > 0) SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_idx, idx, (size_t)T * 12, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->gbuffer_valid = ctx->shadow_map_valid = false;
+  return SGI_OK;
+}
+
+int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const float nm[9], int32_t W, int32_t H) {
+  if (!ctx || !mvp || !mv || !nm || W <= 0 || H <= 0 || W > 32767 || H > 32767) { if (ctx) ctx->err = "sgi_set_camera: bad arguments"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  memcpy(ctx->cam_mvp, mvp, 64); memcpy(ctx->cam_mv, mv, 64); memcpy(ctx->cam_nm, nm, 36);
+  int rc;
+  size_t px = (size_t)W * H;
+  if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_POS, px * 16))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_NRM, px * 16))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_CAM_DEPTH, px * 4))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_VISIBILITY, px * 4))) return rc;
+  if (W != ctx->W || H != ctx->H) {
+    SGI_CUDA(ctx, cudaMemsetAsync(ctx->buf[SGI_BUF_VISIBILITY], 0, px * 4, ctx->stream));
+    ctx->sized[SGI_MODE_GBUFFER] = ctx->sized[SGI_MODE_SVCOUNT] = false;
+  }
+  ctx->W = W; ctx->H = H; ctx->has_camera = true; ctx->gbuffer_valid = false;
+  return SGI_OK;
+}
+
+int sgi_set_lights(sgi_ctx* ctx, int32_t N, const float* light_mvp, const float* light_mvp_b, const float lpos[3], int32_t SW, int32_t SH) {
+  if (!ctx || N <= 0 || N > SGI_MAX_LIGHTS || !light_mvp || !light_mvp_b || !lpos || SW <= 0 || SH <= 0 || SW > 32767 || SH > 32767) {
+    if (ctx) ctx->err = "sgi_set_lights: bad arguments";
+    return SGI_ERR_INVALID;
+  }
+  cudaSetDevice(ctx->device);
+  int rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SHADOW_MAP, (size_t)N * SW * SH * 4))) return rc;
+  if (N != ctx->N) {
+    free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);
+    ctx->h_light_mvp = (float*)malloc((size_t)N * 64); ctx->h_light_mvp_b = (float*)malloc((size_t)N * 64);
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_light_trans) cudaFree(ctx->d_light_trans);
+    ctx->d_light_trans = nullptr;
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_light_trans, (size_t)N * 16));
+  }
+  if (SW != ctx->SW || SH != ctx->SH) ctx->sized[SGI_MODE_DEPTH] = false;
+  ctx->N = N; ctx->SW = SW; ctx->SH = SH;
+  memcpy(ctx->h_light_mvp, light_mvp, (size_t)N * 64);
+  memcpy(ctx->h_light_mvp_b, light_mvp_b, (size_t)N * 64);
+  memcpy(ctx->light_pos, lpos, 12);
+  // lightMVPTrans[i] = column 3 of bias*lightMVP_i (SoftShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:187-190)
+  float* tmp = (float*)malloc((size_t)N * 16);
+  for (int i = 0; i < N; i++) memcpy(tmp + 4 * i, light_mvp_b + 16 * (size_t)i + 12, 16);
+  cudaError_t e = cudaMemcpyAsync(ctx->d_light_trans, tmp, (size_t)N * 16, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // tmp is pageable and freed below
+  free(tmp);
+  if (e != cudaSuccess) { ctx->err = std::string("light upload: ") + cudaGetErrorString(e); return SGI_ERR_CUDA; }
+  ctx->shadow_map_valid = false;
+  return SGI_OK;
+}
+
+int sgi_set_params(sgi_ctx* ctx, const sgi_params* p) {
+  if (!ctx || !p) return SGI_ERR_INVALID;
+  if (p->technique < 0 || p->technique > SGI_TECH_MULTI_HARD) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
+  if (p->kernel_order <= 0 || p->blocker_search_size <= 0 || p->kernel_size <= 0 || p->max_search < 0 || p->max_search > 4096) {
+    ctx->err = "sgi_set_params: kernel sizes must be positive";
+    return SGI_ERR_INVALID;
+  }
+  int n1 = sgi_host_pcf_offsets(p->kernel_order, p->penumbra_size, 0, ctx->pcf_off, SGI_MAX_PCF_TAPS);
+  int n2 = sgi_host_pcf_offsets(p->kernel_order, p->penumbra_size, 1, ctx->rpcf_off, SGI_MAX_PCF_TAPS);
+  if (n1 < 0 || n2 < 0) { ctx->err = "sgi_set_params: more than 64 PCF taps per axis"; return SGI_ERR_INVALID; }
+  ctx->pcf_n = n1; ctx->rpcf_n = n2;
+  ctx->params = *p;
+  ctx->has_params = true;
+  return SGI_OK;
+}
+
+int sgi_render_shadow_map(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  if (!ctx->d_idx || ctx->N <= 0) { ctx->err = "sgi_render_shadow_map: set mesh and lights first"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP);
+  for (int l = 0; l < ctx->N; l++) {
+    SgiRasterJob job;
+    memset(&job, 0, sizeof(job));
+    job.mode = SGI_MODE_DEPTH;
+    job.xyz = ctx->d_xyz; job.nrm = ctx->d_nrm; job.idx = ctx->d_idx; job.T = ctx->T;
+    memcpy(job.mvp, ctx->h_light_mvp + 16 * (size_t)l, 64);
+    job.W = ctx->SW; job.H = ctx->SH;
+    job.use_offset = 1; job.factor = ctx->params.polygon_offset_factor; job.units = ctx->params.polygon_offset_units;
+    job.depth = (float*)ctx->buf[SGI_BUF_SHADOW_MAP] + (size_t)l * ctx->SW * ctx->SH;
+    int rc = sgi_raster_run(ctx, job);
+    if (rc) return rc;
+  }
+  sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot);
+  ctx->shadow_map_valid = true;
+  return SGI_OK;
+}
+
+int sgi_render_gbuffer(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  if (!ctx->d_idx || !ctx->has_camera) { ctx->err = "sgi_render_gbuffer: set mesh and camera first"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER);
+  SgiRasterJob job;
+  memset(&job, 0, sizeof(job));
+  job.mode = SGI_MODE_GBUFFER;
+  job.xyz = ctx->d_xyz; job.nrm = ctx->d_nrm; job.idx = ctx->d_idx; job.T = ctx->T;
+  memcpy(job.mvp, ctx->cam_mvp, 64);
+  job.W = ctx->W; job.H = ctx->H;
+  job.depth = (float*)ctx->buf[SGI_BUF_CAM_DEPTH];
+  job.pos4 = (float4*)ctx->buf[SGI_BUF_GBUF_POS]; job.nrm4 = (float4*)ctx->buf[SGI_BUF_GBUF_NRM];
+  job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
+  int rc = sgi_raster_run(ctx, job);
+  if (rc) return rc;
+  sgi_timing_end(ctx, SGI_PASS_GBUFFER, slot);
+  ctx->gbuffer_valid = true;
+  return SGI_OK;
+}
+
+int sgi_compute_visibility(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  if (!ctx->gbuffer_valid || !ctx->shadow_map_valid) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY);
+  int rc = sgi_shadow_run(ctx);
+  if (rc) return rc;
+  sgi_timing_end(ctx, SGI_PASS_VISIBILITY, slot);
+  return SGI_OK;
+}
+
+int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
+  if (!ctx || !light_pos) return SGI_ERR_INVALID;
+  if (!ctx->gbuffer_valid) { ctx->err = "sgi_compute_shadow_volume: render the G-buffer (depth pre-pass) first"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int rc;
+  size_t px = (size_t)ctx->W * ctx->H;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SV_COUNT, px * 4))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SV_STENCIL, px))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_XYZ, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_IDX, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
+  int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_VOLUME);
+  if ((rc = sgi_sv_extrude_run(ctx, light_pos, (float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ], (int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]))) return rc;
+  SgiRasterJob job;
+  memset(&job, 0, sizeof(job));
+  job.mode = SGI_MODE_SVCOUNT;
+  job.xyz = (const float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ]; job.nrm = nullptr;
+  job.idx = (const int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]; job.T = ctx->T * 6;
+  memcpy(job.mvp, ctx->cam_mvp, 64);
+  job.W = ctx->W; job.H = ctx->H;
+  job.scene_depth = (const float*)ctx->buf[SGI_BUF_CAM_DEPTH]; job.depth_func = ctx->params.sv_depth_func;
+  job.count = (int32_t*)ctx->buf[SGI_BUF_SV_COUNT]; job.stencil = (uint8_t*)ctx->buf[SGI_BUF_SV_STENCIL];
+  job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
+  if ((rc = sgi_raster_run(ctx, job))) return rc;
+  sgi_timing_end(ctx, SGI_PASS_SHADOW_VOLUME, slot);
+  return SGI_OK;
+}
+
+int sgi_synchronize(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->timing) sgi_timing_drain(ctx);
+  return check_overflow(ctx);
+}
+
+int sgi_read(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes) {
+  if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dst) return SGI_ERR_INVALID;
+  if (!ctx->buf[which] || bytes > ctx->buf_bytes[which]) { ctx->err = "sgi_read: buffer not produced yet or size too large"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_overflow(ctx);
+}
+
+int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** dptr, size_t* bytes) {
+  if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dptr) return SGI_ERR_INVALID;
+  *dptr = ctx->buf[which];
+  if (bytes) *bytes = ctx->buf_bytes[which];
+  return ctx->buf[which] ? SGI_OK : SGI_ERR_INVALID;
+}
+
+int sgi_enable_timing(sgi_ctx* ctx, int32_t on) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (on && !ctx->ev[0][0][0]) {
+    for (int p = 0; p < SGI_PASS_COUNT_; p++)
+      for (int k = 0; k < SGI_EV_RING; k++) {
+        SGI_CUDA(ctx, cudaEventCreate(&ctx->ev[p][k][0]));
+        SGI_CUDA(ctx, cudaEventCreate(&ctx->ev[p][k][1]));
+      }
+  }
+  if (!on && ctx->timing) { cudaStreamSynchronize(ctx->stream); sgi_timing_drain(ctx); }
+  ctx->timing = on != 0;
+  return SGI_OK;
+}
+
+int sgi_pass_time_ms(sgi_ctx* ctx, int32_t pass, double* total_ms, int64_t* calls) {
+  if (!ctx || pass < 0 || pass >= SGI_PASS_COUNT_) return SGI_ERR_INVALID;
+  if (total_ms) *total_ms = ctx->pass_ms[pass];
+  if (calls) *calls = ctx->pass_calls[pass];
+  return SGI_OK;
+}
+
+int sgi_reset_timing(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  if (ctx->timing) { cudaStreamSynchronize(ctx->stream); sgi_timing_drain(ctx); }
+  for (int p = 0; p < SGI_PASS_COUNT_; p++) { ctx->pass_ms[p] = 0; ctx->pass_calls[p] = 0; }
+  return SGI_OK;
+}
+
+int sgi_kernel_launches(sgi_ctx* ctx, int64_t* launches) {
+  if (!ctx || !launches) return SGI_ERR_INVALID;
+  *launches = ctx->launches;
+  return SGI_OK;
+}
+
+const char* sgi_last_error(sgi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+}  // extern "C"

@@ -1,0 +1,644 @@
+// sgi_raster.cu — tile-binned triangle rasteriser for sm_100a (K1 light-view depth, K2 camera G-buffer,
+// K4 shadow-volume counting).  Replaces the fixed-function GL raster behind
+//   renderShadowMap()   ShadowMapping/src/main.cpp:350-361   (Scene.vert:11-20, glPolygonOffset :246)
+//   renderGBuffer()     ShadowMapping/src/main.cpp:363-372   (GBuffer.vert:12-23, GBuffer.frag:32-38)
+//   stencil pass        ShadowVolumes/src/main.cpp:154-172   (INCR_WRAP/DECR_WRAP on z-pass)
+//
+// Pipeline (all on one stream, no host round trip):
+//   k_setup      1 thread / source triangle: transform, clip (near/far + 16x guard band), snap to 1/256 px,
+//                integer edge set-up, depth plane, polygon offset -> 64-byte SgiRec (+ attribute record)
+//   k_bin<0>     1 warp / record: count the 64x64 tiles the triangle really overlaps
+//   cub scan     exclusive sum of the per-tile counts
+//   k_bin<1>     same walk, writes record ids into the per-tile lists
+//   k_tile<MODE> 1 CTA / tile: the tile lives in shared memory (u32 depth, u64 depth|prim key or i32 count);
+//                triangles are expanded into bbox "candidates" that are spread evenly over the 256 threads
+//                (block prefix sum + binary search), so a floor triangle covering the tile and a 2-pixel
+//                triangle cost the same per candidate; shared-memory atomics resolve visibility; the tile
+//                is written to HBM exactly once, coalesced (the clear is fused: no separate memset pass).
+//
+// HBM traffic per pass = geometry once + every output texel once; depth never bounces
+// through global atomics.  Numerics follow DESIGN.md §3 to the bit (-fmad=false).
+#include <cub/cub.cuh>
+#include "sgi_internal.cuh"
+
+namespace {
+
+struct CV { float x, y, z, w, b0, b1, b2; };
+
+__device__ __forceinline__ float plane_dist(const CV& v, int p) {
+  switch (p) {
+    case 0: return v.w + v.z;
+    case 1: return v.w - v.z;
+    case 2: return SGI_GUARD * v.w + v.x;
+    case 3: return SGI_GUARD * v.w - v.x;
+    case 4: return SGI_GUARD * v.w + v.y;
+    default: return SGI_GUARD * v.w - v.y;
+  }
+}
+
+// a inside, b outside; always evaluated inside -> outside so shared edges clip identically
+__device__ __forceinline__ CV clip_lerp(const CV& a, const CV& b, float da, float db) {
+  float t = da / (da - db);
+  CV r;
+  r.x = a.x + t * (b.x - a.x);
+  r.y = a.y + t * (b.y - a.y);
+  r.z = a.z + t * (b.z - a.z);
+  r.w = a.w + t * (b.w - a.w);
+  r.b0 = a.b0 + t * (b.b0 - a.b0);
+  r.b1 = a.b1 + t * (b.b1 - a.b1);
+  r.b2 = a.b2 + t * (b.b2 - a.b2);
+  return r;
+}
+
+__device__ int clip_polygon(CV* poly, int n) {
+  CV tmp[10];
+  float d[10];
+  for (int p = 0; p < 6; p++) {
+    bool any_out = false;
+    for (int i = 0; i < n; i++) { d[i] = plane_dist(poly[i], p); if (!(d[i] >= 0.0f)) any_out = true; }
+    if (!any_out) continue;
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      int j = (i + 1 == n) ? 0 : i + 1;
+      bool in_i = d[i] >= 0.0f, in_j = d[j] >= 0.0f;
+      if (in_i) {
+        tmp[m++] = poly[i];
+        if (!in_j) tmp[m++] = clip_lerp(poly[i], poly[j], d[i], d[j]);
+      } else if (in_j) {
+        tmp[m++] = clip_lerp(poly[j], poly[i], d[j], d[i]);
+      }
+    }
+    n = m;
+    if (n < 3) return 0;
+    for (int i = 0; i < n; i++) poly[i] = tmp[i];
+  }
+  return n;
+}
+
+__device__ __forceinline__ CV xform(const float* __restrict__ m, float x, float y, float z) {
+  CV o;
+  o.x = ((m[0] * x + m[4] * y) + m[8] * z) + m[12];
+  o.y = ((m[1] * x + m[5] * y) + m[9] * z) + m[13];
+  o.z = ((m[2] * x + m[6] * y) + m[10] * z) + m[14];
+  o.w = ((m[3] * x + m[7] * y) + m[11] * z) + m[15];
+  return o;
+}
+
+struct SetupArgs {
+  const float* xyz; const int32_t* idx; int T;
+  float mvp[16];
+  int W, H;
+  int use_offset; float factor, units;
+  SgiRec* rec; SgiRecAttr* attr; int32_t* ovf_base; int32_t* counters;
+};
+
+__device__ __forceinline__ void invalidate(SgiRec* r) {
+  SgiRec z;
+  z.X0 = z.Y0 = z.X1 = z.Y1 = z.X2 = z.Y2 = 0;
+  z.z0 = z.dz1 = z.dz2 = z.ia = z.zoff = 0.0f;
+  z.prim_front = -1;
+  z.px0 = z.py0 = 1; z.px1 = z.py1 = 0;
+  z.pad0 = z.pad1 = 0;
+  *r = z;
+}
+
+__global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T) return;
+  a.ovf_base[t] = -1;
+  int i0 = a.idx[3 * t], i1 = a.idx[3 * t + 1], i2 = a.idx[3 * t + 2];
+  CV poly[10];
+  poly[0] = xform(a.mvp, a.xyz[3 * (size_t)i0], a.xyz[3 * (size_t)i0 + 1], a.xyz[3 * (size_t)i0 + 2]);
+  poly[1] = xform(a.mvp, a.xyz[3 * (size_t)i1], a.xyz[3 * (size_t)i1 + 1], a.xyz[3 * (size_t)i1 + 2]);
+  poly[2] = xform(a.mvp, a.xyz[3 * (size_t)i2], a.xyz[3 * (size_t)i2 + 1], a.xyz[3 * (size_t)i2 + 2]);
+  poly[0].b0 = 1; poly[0].b1 = 0; poly[0].b2 = 0;
+  poly[1].b0 = 0; poly[1].b1 = 1; poly[1].b2 = 0;
+  poly[2].b0 = 0; poly[2].b1 = 0; poly[2].b2 = 1;
+  {  // trivial reject against the true frustum
+    int o0 = 0, o1 = 0, o2 = 0, o3 = 0, o4 = 0, o5 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const CV& v = poly[k];
+      if (!(v.w + v.z >= 0.0f)) o0++;
+      if (!(v.w - v.z >= 0.0f)) o1++;
+      if (!(v.w + v.x >= 0.0f)) o2++;
+      if (!(v.w - v.x >= 0.0f)) o3++;
+      if (!(v.w + v.y >= 0.0f)) o4++;
+      if (!(v.w - v.y >= 0.0f)) o5++;
+    }
+    if (o0 == 3 || o1 == 3 || o2 == 3 || o3 == 3 || o4 == 3 || o5 == 3) { invalidate(&a.rec[t]); return; }
+  }
+  int n = clip_polygon(poly, 3);
+  if (n < 3) { invalidate(&a.rec[t]); return; }
+  float hw = (float)a.W * 0.5f, hh = (float)a.H * 0.5f;
+  int32_t X[10], Y[10];
+  float Z[10], IW[10];
+  for (int k = 0; k < n; k++) {
+    float nx = poly[k].x / poly[k].w, ny = poly[k].y / poly[k].w, nz = poly[k].z / poly[k].w;
+    float xw = nx * hw + hw, yw = ny * hh + hh;
+    Z[k] = nz * 0.5f + 0.5f;
+    IW[k] = 1.0f / poly[k].w;
+    float sx = xw * (float)SGI_SUBPIX, sy = yw * (float)SGI_SUBPIX;
+    if (!(fabsf(sx) < 1.0e9f) || !(fabsf(sy) < 1.0e9f) || !(fabsf(Z[k]) < 1.0e9f)) { invalidate(&a.rec[t]); return; }
+    X[k] = __float2int_rn(sx);
+    Y[k] = __float2int_rn(sy);
+  }
+  int base = -1;
+  if (n > 3) {
+    base = a.T + atomicAdd(&a.counters[0], n - 3);
+    a.ovf_base[t] = base;
+  }
+  for (int f = 1; f + 1 < n; f++) {
+    int slot = (f == 1) ? t : base + (f - 2);
+    int id0 = 0, id1 = f, id2 = f + 1;
+    long long area2 = (long long)(X[id1] - X[id0]) * (long long)(Y[id2] - Y[id0]) -
+                      (long long)(X[id2] - X[id0]) * (long long)(Y[id1] - Y[id0]);
+    if (area2 == 0) { invalidate(&a.rec[slot]); continue; }
+    int front = area2 > 0;
+    if (area2 < 0) { int s = id1; id1 = id2; id2 = s; area2 = -area2; }
+    SgiRec r;
+    r.X0 = X[id0]; r.Y0 = Y[id0]; r.X1 = X[id1]; r.Y1 = Y[id1]; r.X2 = X[id2]; r.Y2 = Y[id2];
+    int mnx = min(r.X0, min(r.X1, r.X2)), mxx = max(r.X0, max(r.X1, r.X2));
+    int mny = min(r.Y0, min(r.Y1, r.Y2)), mxy = max(r.Y0, max(r.Y1, r.Y2));
+    r.ia = 1.0f / (float)area2;
+    r.z0 = Z[id0]; r.dz1 = Z[id1] - Z[id0]; r.dz2 = Z[id2] - Z[id0];
+    r.zoff = 0.0f;
+    if (a.use_offset) {
+      double dY1 = (double)(r.Y1 - r.Y0), dY2 = (double)(r.Y2 - r.Y0);
+      double dX1 = (double)(r.X1 - r.X0), dX2 = (double)(r.X2 - r.X0);
+      double nx = __dsub_rn(__dmul_rn((double)r.dz1, dY2), __dmul_rn((double)r.dz2, dY1));
+      double ny = __dsub_rn(__dmul_rn((double)r.dz2, dX1), __dmul_rn((double)r.dz1, dX2));
+      double dzdx = __dmul_rn(__ddiv_rn(nx, (double)area2), (double)SGI_SUBPIX);
+      double dzdy = __dmul_rn(__ddiv_rn(ny, (double)area2), (double)SGI_SUBPIX);
+      float m = (float)fmax(fabs(dzdx), fabs(dzdy));
+      float zmax = fmaxf(Z[id0], fmaxf(Z[id1], Z[id2]));
+      float rr = 0.0f;
+      if (zmax > 0.0f) {
+        int eb = (int)((__float_as_uint(zmax) >> 23) & 255u);
+        if (eb > 23 && eb < 255) rr = __uint_as_float((uint32_t)(eb - 23) << 23);
+      }
+      r.zoff = a.factor * m + a.units * rr;
+    }
+    int px0 = (mnx - SGI_SUBPIX / 2 + (SGI_SUBPIX - 1)) >> 8, px1 = (mxx - SGI_SUBPIX / 2) >> 8;
+    int py0 = (mny - SGI_SUBPIX / 2 + (SGI_SUBPIX - 1)) >> 8, py1 = (mxy - SGI_SUBPIX / 2) >> 8;
+    px0 = max(px0, 0); py0 = max(py0, 0); px1 = min(px1, a.W - 1); py1 = min(py1, a.H - 1);
+    if (px0 > px1 || py0 > py1) { invalidate(&a.rec[slot]); continue; }
+    r.px0 = (int16_t)px0; r.py0 = (int16_t)py0; r.px1 = (int16_t)px1; r.py1 = (int16_t)py1;
+    r.prim_front = ((t * 8 + (f - 1)) << 1) | front;
+    r.pad0 = r.pad1 = 0;
+    a.rec[slot] = r;
+    if (a.attr) {
+      SgiRecAttr q;
+      const int ids[3] = {id0, id1, id2};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        q.iw[k] = IW[ids[k]];
+        q.bary[3 * k + 0] = poly[ids[k]].b0; q.bary[3 * k + 1] = poly[ids[k]].b1; q.bary[3 * k + 2] = poly[ids[k]].b2;
+      }
+      a.attr[slot] = q;
+    }
+  }
+}
+
+// ---- binning -------------------------------------------------------------------------------------------------
+struct BinArgs {
+  const SgiRec* rec; const int32_t* counters; int T;
+  int tiles_x, tiles_y, tx0, ty0, tx1, ty1;     // tile grid and the inclusive tile range of the job rectangle
+  int32_t* tile_cnt; const int32_t* tile_off; int32_t* tile_fill; int32_t* pairs; long long pair_cap;
+  int32_t* flags;                                // counters[1] = overflow flag
+};
+
+// conservative triangle / tile overlap: for each edge evaluate at the tile corner that maximises it
+__device__ __forceinline__ bool tile_overlaps(const SgiRec& r, int tx, int ty, int W, int H) {
+  long long cx0 = (long long)(tx << SGI_TILE_LOG2) * SGI_SUBPIX + SGI_SUBPIX / 2;
+  long long cy0 = (long long)(ty << SGI_TILE_LOG2) * SGI_SUBPIX + SGI_SUBPIX / 2;
+  long long cx1 = cx0 + (long long)(SGI_TILE - 1) * SGI_SUBPIX, cy1 = cy0 + (long long)(SGI_TILE - 1) * SGI_SUBPIX;
+  const int XA[3] = {r.X1, r.X2, r.X0}, YA[3] = {r.Y1, r.Y2, r.Y0};
+  const int XB[3] = {r.X2, r.X0, r.X1}, YB[3] = {r.Y2, r.Y0, r.Y1};
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    long long dx = (long long)XB[e] - XA[e], dy = (long long)YB[e] - YA[e];
+    long long px = (dy < 0) ? cx1 : cx0;      // coefficient of px is -dy
+    long long py = (dx > 0) ? cy1 : cy0;      // coefficient of py is  dx
+    long long v = dx * (py - YA[e]) - dy * (px - XA[e]);
+    if (v < 0) return false;
+  }
+  return true;
+}
+
+template <int FILL>
+__global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
+  int lane = threadIdx.x & 31;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int nrec = a.T + a.counters[0];
+  for (int slot = warp; slot < nrec; slot += nwarps) {
+    SgiRec r = a.rec[slot];
+    if (r.prim_front < 0) continue;
+    int bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0), bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1);
+    int by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
+    if (bx0 > bx1 || by0 > by1) continue;
+    int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
+    bool single = (nt == 1);
+    for (int k = lane; k < nt; k += 32) {
+      int ty = by0 + k / bw, tx = bx0 + k % bw;
+      if (!single && !tile_overlaps(r, tx, ty, W, H)) continue;
+      int tile = ty * a.tiles_x + tx;
+      if (!FILL) {
+        atomicAdd(&a.tile_cnt[tile], 1);
+      } else {
+        long long pos = (long long)a.tile_off[tile] + atomicAdd(&a.tile_fill[tile], 1);
+        if (pos < a.pair_cap) a.pairs[pos] = slot;
+        else a.flags[1] = 1;
+      }
+    }
+  }
+}
+
+// h_flags is mapped pinned host memory: [0] sticky "a list overflowed", [1] largest list size ever wanted
+__global__ void k_publish_total(const int32_t* tile_off, int n_tiles, int32_t* counters, volatile int32_t* h_flags) {
+  int total = tile_off[n_tiles];
+  counters[2] = total;
+  if (total > h_flags[1]) h_flags[1] = total;
+}
+__global__ void k_publish_flag(const int32_t* counters, volatile int32_t* h_flags) { if (counters[1]) h_flags[0] = 1; }
+
+// ---- per-tile rasterisation ----------------------------------------------------------------------------------
+struct TileArgs {
+  const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
+  const int32_t* tile_off; const int32_t* pairs; long long pair_cap;
+  int tiles_x, tx0, ty0;
+  int W, H, rx0, ry0, rx1, ry1;
+  const float* xyz; const float* nrm; const int32_t* idx;
+  float* depth; float4* pos4; float4* nrm4;
+  const float* scene_depth; int depth_func; int32_t* count; uint8_t* stencil;
+};
+
+#define ONE_BITS 0x3F800000u
+
+struct TriSmem {
+  int X0[SGI_TILE_THREADS], Y0[SGI_TILE_THREADS], X1[SGI_TILE_THREADS], Y1[SGI_TILE_THREADS], X2[SGI_TILE_THREADS], Y2[SGI_TILE_THREADS];
+  float z0[SGI_TILE_THREADS], dz1[SGI_TILE_THREADS], dz2[SGI_TILE_THREADS], ia[SGI_TILE_THREADS], zoff[SGI_TILE_THREADS];
+  int meta[SGI_TILE_THREADS];      // prim_front
+  int box[SGI_TILE_THREADS];       // lx0 | ly0<<8 | w<<16 (tile-local bbox origin and width)
+  int prefix[SGI_TILE_THREADS + 1];
+};
+
+__device__ __forceinline__ bool edge_in(long long e, int dx, int dy) {
+  return e > 0 || (e == 0 && (dy < 0 || (dy == 0 && dx < 0)));
+}
+
+// coverage + the three edge values of pixel centre (px,py) [pixels]
+__device__ __forceinline__ bool cover(int X0, int Y0, int X1, int Y1, int X2, int Y2, int px, int py, long long& E0,
+                                      long long& E1, long long& E2) {
+  int PX = px * SGI_SUBPIX + SGI_SUBPIX / 2, PY = py * SGI_SUBPIX + SGI_SUBPIX / 2;
+  int dx0 = X2 - X1, dy0 = Y2 - Y1;      // edge 0: v1 -> v2 (opposite v0)
+  int dx1 = X0 - X2, dy1 = Y0 - Y2;      // edge 1: v2 -> v0
+  int dx2 = X1 - X0, dy2 = Y1 - Y0;      // edge 2: v0 -> v1
+  E0 = (long long)dx0 * (long long)(PY - Y1) - (long long)dy0 * (long long)(PX - X1);
+  if (!edge_in(E0, dx0, dy0)) return false;
+  E1 = (long long)dx1 * (long long)(PY - Y2) - (long long)dy1 * (long long)(PX - X2);
+  if (!edge_in(E1, dx1, dy1)) return false;
+  E2 = (long long)dx2 * (long long)(PY - Y0) - (long long)dy2 * (long long)(PX - X0);
+  return edge_in(E2, dx2, dy2);
+}
+
+__device__ __forceinline__ float frag_z(float z0, float dz1, float dz2, float ia, float zoff, long long E1, long long E2) {
+  float b1 = (float)E1 * ia, b2 = (float)E2 * ia;
+  float z = (z0 + b1 * dz1) + b2 * dz2;
+  z = z + zoff;
+  if (!(z >= 0.0f)) z = 0.0f;
+  if (z > 1.0f) z = 1.0f;
+  return z;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: tile payload | (SV: scene depth) | TriSmem
+  unsigned int* zt = reinterpret_cast<unsigned int*>(smem_raw);
+  unsigned long long* kt = reinterpret_cast<unsigned long long*>(smem_raw);
+  int* ct = reinterpret_cast<int*>(smem_raw);
+  constexpr int NPIX = SGI_TILE * SGI_TILE;
+  constexpr size_t PAYLOAD = (MODE == SGI_MODE_GBUFFER) ? NPIX * 8 : NPIX * 4;
+  float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
+  TriSmem& ts = *reinterpret_cast<TriSmem*>(smem_raw + PAYLOAD + (MODE == SGI_MODE_SVCOUNT ? NPIX * 4 : 0));
+
+  const int tid = threadIdx.x;
+  const int tx = a.tx0 + blockIdx.x, ty = a.ty0 + blockIdx.y;
+  const int tile = ty * a.tiles_x + tx;
+  const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
+
+  for (int p = tid; p < NPIX; p += SGI_TILE_THREADS) {
+    if (MODE == SGI_MODE_DEPTH) zt[p] = ONE_BITS;
+    else if (MODE == SGI_MODE_GBUFFER) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
+    else {
+      ct[p] = 0;
+      int x = ox + (p & (SGI_TILE - 1)), y = oy + (p >> SGI_TILE_LOG2);
+      sd[p] = (x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
+    }
+  }
+  long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
+  if (end > a.pair_cap) end = a.pair_cap;
+  if (beg > end) beg = end;
+  __syncthreads();
+
+  typedef cub::BlockScan<int, SGI_TILE_THREADS> BlockScan;
+  __shared__ typename BlockScan::TempStorage scan_tmp;
+
+  for (long long base = beg; base < end; base += SGI_TILE_THREADS) {
+    int ncand = 0;
+    if (base + tid < end) {
+      const SgiRec* rp = &a.rec[a.pairs[base + tid]];
+      uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+      uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+      uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rp) + 2);
+      uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rp) + 3);
+      ts.X0[tid] = (int)q0.x; ts.Y0[tid] = (int)q0.y; ts.X1[tid] = (int)q0.z; ts.Y1[tid] = (int)q0.w;
+      ts.X2[tid] = (int)q1.x; ts.Y2[tid] = (int)q1.y;
+      ts.z0[tid] = __uint_as_float(q1.z); ts.dz1[tid] = __uint_as_float(q1.w);
+      ts.dz2[tid] = __uint_as_float(q2.x); ts.ia[tid] = __uint_as_float(q2.y); ts.zoff[tid] = __uint_as_float(q2.z);
+      ts.meta[tid] = (int)q2.w;
+      int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
+      int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
+      int lx0 = max(px0, ox) - ox, ly0 = max(py0, oy) - oy;
+      int lx1 = min(px1, ox + SGI_TILE - 1) - ox, ly1 = min(py1, oy + SGI_TILE - 1) - oy;
+      int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
+      if (w > 0 && h > 0) ncand = w * h; else w = 1;
+      ts.box[tid] = lx0 | (ly0 << 8) | (w << 16);
+    }
+    int excl, total;
+    BlockScan(scan_tmp).ExclusiveSum(ncand, excl, total);
+    ts.prefix[tid] = excl;
+    if (tid == 0) ts.prefix[SGI_TILE_THREADS] = total;
+    __syncthreads();
+
+    for (int c = tid; c < total; c += SGI_TILE_THREADS) {
+      // upper_bound over prefix[0..256): last k with prefix[k] <= c
+      int lo = 0, hi = SGI_TILE_THREADS;
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        int mid = (lo + hi) >> 1;
+        if (ts.prefix[mid] <= c) lo = mid; else hi = mid;
+      }
+      int k = lo;
+      int local = c - ts.prefix[k];
+      int box = ts.box[k];
+      int w = box >> 16;
+      int jj = local / w, ii = local - jj * w;
+      int lx = (box & 0xFF) + ii, ly = ((box >> 8) & 0xFF) + jj;
+      long long E0, E1, E2;
+      if (!cover(ts.X0[k], ts.Y0[k], ts.X1[k], ts.Y1[k], ts.X2[k], ts.Y2[k], ox + lx, oy + ly, E0, E1, E2)) continue;
+      float z = frag_z(ts.z0[k], ts.dz1[k], ts.dz2[k], ts.ia[k], ts.zoff[k], E1, E2);
+      int p = (ly << SGI_TILE_LOG2) + lx;
+      if (MODE == SGI_MODE_DEPTH) {
+        atomicMin(&zt[p], __float_as_uint(z));
+      } else if (MODE == SGI_MODE_GBUFFER) {
+        if (z < 1.0f) {
+          unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)(ts.meta[k] >> 1);
+          atomicMin(&kt[p], key);
+        }
+      } else {
+        float d = sd[p];
+        bool pass = (a.depth_func == SGI_DEPTH_LESS) ? (z < d) : (z <= d);
+        if (pass) atomicAdd(&ct[p], (ts.meta[k] & 1) ? 1 : -1);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write the tile to HBM exactly once ------------------------------------------------------------------
+  for (int p = tid; p < NPIX; p += SGI_TILE_THREADS) {
+    int lx = p & (SGI_TILE - 1), ly = p >> SGI_TILE_LOG2;
+    int x = ox + lx, y = oy + ly;
+    if (x < a.rx0 || x >= a.rx1 || y < a.ry0 || y >= a.ry1) continue;
+    size_t o = (size_t)y * a.W + x;
+    if (MODE == SGI_MODE_DEPTH) {
+      a.depth[o] = __uint_as_float(zt[p]);
+    } else if (MODE == SGI_MODE_SVCOUNT) {
+      int c = ct[p];
+      a.count[o] = c;
+      a.stencil[o] = (uint8_t)((unsigned int)c & 255u);
+    } else {
+      unsigned long long key = kt[p];
+      unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
+      if (lo32 == 0xFFFFFFFFu) {
+        a.depth[o] = 1.0f;
+        a.pos4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
+        a.nrm4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
+        continue;
+      }
+      int prim = (int)lo32, t = prim >> 3, sub = prim & 7;
+      int slot = (sub == 0) ? t : a.ovf_base[t] + sub - 1;
+      SgiRec r = a.rec[slot];
+      SgiRecAttr q = a.attr[slot];
+      long long E0, E1, E2;
+      cover(r.X0, r.Y0, r.X1, r.Y1, r.X2, r.Y2, x, y, E0, E1, E2);
+      int i0 = a.idx[3 * (size_t)t], i1 = a.idx[3 * (size_t)t + 1], i2 = a.idx[3 * (size_t)t + 2];
+      float q0 = ((float)E0 * r.ia) * q.iw[0];
+      float q1 = ((float)E1 * r.ia) * q.iw[1];
+      float q2 = ((float)E2 * r.ia) * q.iw[2];
+      float qs = (q0 + q1) + q2;
+      float outv[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const float* src = (c < 3) ? a.xyz : a.nrm;
+        int cc = (c < 3) ? c : c - 3;
+        float s0 = src[3 * (size_t)i0 + cc], s1 = src[3 * (size_t)i1 + cc], s2 = src[3 * (size_t)i2 + cc];
+        float A0 = (q.bary[0] * s0 + q.bary[1] * s1) + q.bary[2] * s2;
+        float A1 = (q.bary[3] * s0 + q.bary[4] * s1) + q.bary[5] * s2;
+        float A2 = (q.bary[6] * s0 + q.bary[7] * s1) + q.bary[8] * s2;
+        outv[c] = ((q0 * A0 + q1 * A1) + q2 * A2) / qs;
+      }
+      a.depth[o] = __uint_as_float((unsigned int)(key >> 32));
+      a.pos4[o] = make_float4(outv[0], outv[1], outv[2], 1.0f);
+      a.nrm4[o] = make_float4(outv[3], outv[4], outv[5], (r.prim_front & 1) ? 1.0f : 0.0f);
+    }
+  }
+}
+
+template <int MODE>
+constexpr size_t tile_smem_bytes() {
+  return (size_t)SGI_TILE * SGI_TILE * (MODE == SGI_MODE_GBUFFER ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? SGI_TILE * SGI_TILE * 4 : 0) +
+         sizeof(TriSmem);
+}
+
+// ---- shadow-volume extrusion: ShadowVolumes/src/ShadowVolume.cpp:116-195 -----------------------------------------
+__global__ void __launch_bounds__(128) k_sv_extrude(const float* __restrict__ xyz, const float* __restrict__ nrm,
+                                                    const int32_t* __restrict__ idx, int T, float lx, float ly, float lz,
+                                                    int infinity, float* __restrict__ pxyz, int32_t* __restrict__ pidx) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float L[3] = {lx, ly, lz};
+  int v[3] = {idx[3 * t], idx[3 * t + 1], idx[3 * t + 2]};
+  float* q = pxyz + (size_t)t * 18;
+  float n[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float p = xyz[3 * (size_t)v[k] + a];
+      q[k * 3 + a] = p;
+      q[(3 + k) * 3 + a] = (p - L[a]) * (float)infinity;           // :39-41 / :140-142
+    }
+    s = nrm[3 * (size_t)v[0] + a] + nrm[3 * (size_t)v[1] + a] + nrm[3 * (size_t)v[2] + a];
+    n[a] = s / 3.0f;
+  }
+  float d = n[0] * L[0] + n[1] * L[1] + n[2] * L[2];
+  // index order flips on dot(avg normal, light POSITION) >= 0  (:61 / :162)
+  const int ordA[18] = {1, 0, 3, 1, 3, 4, 2, 1, 4, 2, 4, 5, 0, 2, 5, 0, 5, 3};
+  const int ordB[18] = {4, 3, 0, 4, 0, 1, 5, 4, 1, 5, 1, 2, 3, 5, 2, 3, 2, 0};
+#pragma unroll
+  for (int k = 0; k < 18; k++) pidx[(size_t)t * 18 + k] = t * 6 + ((d >= 0.0f) ? ordA[k] : ordB[k]);
+}
+
+}  // namespace
+
+// ================================================ host side =====================================================
+static int grow(sgi_ctx* ctx, void** p, size_t bytes) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SGI_ERR_NOMEM; }
+  return SGI_OK;
+}
+
+int sgi_raster_reserve(sgi_ctx* ctx, int max_tris, int W, int H) {
+  int rc;
+  if (max_tris > ctx->rec_cap_tris) {
+    size_t n = (size_t)max_tris * 7 + 16;
+    if ((rc = grow(ctx, (void**)&ctx->d_rec, n * sizeof(SgiRec)))) return rc;
+    if ((rc = grow(ctx, (void**)&ctx->d_attr, n * sizeof(SgiRecAttr)))) return rc;
+    if ((rc = grow(ctx, (void**)&ctx->d_ovf_base, (size_t)max_tris * 4 + 16))) return rc;
+    ctx->rec_cap_tris = max_tris;
+  }
+  if (!ctx->d_counters) {
+    if ((rc = grow(ctx, (void**)&ctx->d_counters, 64))) return rc;
+    SGI_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 64, cudaHostAllocMapped));
+    ctx->h_flags[0] = ctx->h_flags[1] = 0;
+  }
+  int tiles = ((W + SGI_TILE - 1) >> SGI_TILE_LOG2) * ((H + SGI_TILE - 1) >> SGI_TILE_LOG2);
+  if (tiles + 1 > ctx->tile_cap) {
+    if ((rc = grow(ctx, (void**)&ctx->d_tile_cnt, (size_t)(tiles + 1) * 4))) return rc;
+    if ((rc = grow(ctx, (void**)&ctx->d_tile_off, (size_t)(tiles + 1) * 4))) return rc;
+    if ((rc = grow(ctx, (void**)&ctx->d_tile_fill, (size_t)(tiles + 1) * 4))) return rc;
+    ctx->tile_cap = tiles + 1;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_tile_cnt, ctx->d_tile_off, tiles + 1, ctx->stream);
+    if (tmp > ctx->scan_tmp_bytes) {
+      if ((rc = grow(ctx, &ctx->d_scan_tmp, tmp + 256))) return rc;
+      ctx->scan_tmp_bytes = tmp + 256;
+    }
+  }
+  if (ctx->pair_cap == 0) {
+    long long want = (long long)max_tris * 4 + (long long)tiles * 8 + (1 << 20);
+    if ((rc = grow(ctx, (void**)&ctx->d_pairs, (size_t)want * 4))) return rc;
+    ctx->pair_cap = want;
+  }
+  return SGI_OK;
+}
+
+template <int MODE>
+static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
+  static bool configured = false;
+  constexpr size_t smem = tile_smem_bytes<MODE>();
+  if (!configured) {
+    SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_tile<MODE><<<grid, SGI_TILE_THREADS, smem, ctx->stream>>>(ta);
+  ctx->launches++;
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
+}
+
+int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
+  int rc = sgi_raster_reserve(ctx, job.T, job.W, job.H);
+  if (rc) return rc;
+  // a previous frame asked for more list space than we had: grow before running again
+  if (ctx->h_flags[1] > 0 && (long long)ctx->h_flags[1] + 1024 > ctx->pair_cap) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    long long want = (long long)ctx->h_flags[1] * 3 / 2 + (1 << 16);
+    if ((rc = grow(ctx, (void**)&ctx->d_pairs, (size_t)want * 4))) return rc;
+    ctx->pair_cap = want;
+  }
+  cudaStream_t st = ctx->stream;
+  const int tiles_x = (job.W + SGI_TILE - 1) >> SGI_TILE_LOG2, tiles_y = (job.H + SGI_TILE - 1) >> SGI_TILE_LOG2;
+  const int n_tiles = tiles_x * tiles_y;
+  int rx0 = job.rx0, ry0 = job.ry0, rx1 = job.rx1, ry1 = job.ry1;
+  if (rx1 <= rx0 || ry1 <= ry0) { rx0 = 0; ry0 = 0; rx1 = job.W; ry1 = job.H; }
+  rx0 = rx0 < 0 ? 0 : rx0; ry0 = ry0 < 0 ? 0 : ry0; rx1 = rx1 > job.W ? job.W : rx1; ry1 = ry1 > job.H ? job.H : ry1;
+  const int tx0 = rx0 >> SGI_TILE_LOG2, ty0 = ry0 >> SGI_TILE_LOG2;
+  const int tx1 = (rx1 - 1) >> SGI_TILE_LOG2, ty1 = (ry1 - 1) >> SGI_TILE_LOG2;
+
+  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 16, st));
+  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_cnt, 0, (size_t)(n_tiles + 1) * 4, st));
+  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_fill, 0, (size_t)(n_tiles + 1) * 4, st));
+
+  SetupArgs sa;
+  sa.xyz = job.xyz; sa.idx = job.idx; sa.T = job.T;
+  for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
+  sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
+  sa.rec = ctx->d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? ctx->d_attr : nullptr;
+  sa.ovf_base = ctx->d_ovf_base; sa.counters = ctx->d_counters;
+  if (job.T > 0) {
+    k_setup<<<(job.T + 127) / 128, 128, 0, st>>>(sa);
+    ctx->launches++;
+  }
+
+  BinArgs ba;
+  ba.rec = ctx->d_rec; ba.counters = ctx->d_counters; ba.T = job.T;
+  ba.tiles_x = tiles_x; ba.tiles_y = tiles_y; ba.tx0 = tx0; ba.ty0 = ty0; ba.tx1 = tx1; ba.ty1 = ty1;
+  ba.tile_cnt = ctx->d_tile_cnt; ba.tile_off = ctx->d_tile_off; ba.tile_fill = ctx->d_tile_fill;
+  ba.pairs = ctx->d_pairs; ba.pair_cap = ctx->pair_cap; ba.flags = ctx->d_counters;
+  int bin_blocks = (job.T + 7) / 8;                 // 8 warps per CTA, one record per warp per trip
+  if (bin_blocks > 148 * 16) bin_blocks = 148 * 16;
+  if (bin_blocks < 1) bin_blocks = 1;
+  k_bin<0><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
+  ctx->launches++;
+  size_t tmp = ctx->scan_tmp_bytes;
+  SGI_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, tmp, ctx->d_tile_cnt, ctx->d_tile_off, n_tiles + 1, st));
+  ctx->launches += 1;
+  k_publish_total<<<1, 1, 0, st>>>(ctx->d_tile_off, n_tiles, ctx->d_counters, ctx->h_flags);
+  ctx->launches++;
+  if (!ctx->sized[job.mode]) {
+    // first pass of this kind on this context: size the tile lists from the real count (one sync, once)
+    SGI_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->sized[job.mode] = true;
+    if ((long long)ctx->h_flags[1] > ctx->pair_cap) {
+      long long want = (long long)ctx->h_flags[1] * 3 / 2 + (1 << 16);
+      if ((rc = grow(ctx, (void**)&ctx->d_pairs, (size_t)want * 4))) return rc;
+      ctx->pair_cap = want;
+      ba.pairs = ctx->d_pairs; ba.pair_cap = ctx->pair_cap;
+    }
+  }
+  k_bin<1><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
+  ctx->launches++;
+  k_publish_flag<<<1, 1, 0, st>>>(ctx->d_counters, ctx->h_flags);
+  ctx->launches++;
+  ctx->overflow_pending = true;
+
+  TileArgs ta;
+  ta.rec = ctx->d_rec; ta.attr = ctx->d_attr; ta.ovf_base = ctx->d_ovf_base;
+  ta.tile_off = ctx->d_tile_off; ta.pairs = ctx->d_pairs; ta.pair_cap = ctx->pair_cap;
+  ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
+  ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
+  ta.xyz = job.xyz; ta.nrm = job.nrm; ta.idx = job.idx;
+  ta.depth = job.depth; ta.pos4 = job.pos4; ta.nrm4 = job.nrm4;
+  ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
+  dim3 grid(tx1 - tx0 + 1, ty1 - ty0 + 1);
+  if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid);
+  else if (job.mode == SGI_MODE_GBUFFER) rc = launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid);
+  else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid);
+  return rc;
+}
+
+int sgi_sv_extrude_run(sgi_ctx* ctx, const float light[3], float* prism_xyz, int32_t* prism_idx) {
+  if (ctx->T <= 0) return SGI_OK;
+  k_sv_extrude<<<(ctx->T + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->T, light[0], light[1],
+                                                             light[2], ctx->params.sv_infinity, prism_xyz, prism_idx);
+  ctx->launches++;
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
+}

@@ -1,0 +1,506 @@
+// sgi_shadow.cu — per-pixel shadow test / filter kernels for sm_100a (K3a-d, K5).  One thread per screen
+// pixel reads the G-buffer (2 x 128-bit loads), projects into light space and evaluates the technique the
+// reference's full-screen fragment program would:
+//   hard, PCF            ShadowMapping/Shaders/Shadow.frag:86-116,222-273
+//   PCSS                 SoftShadowMapping/Shaders/SoftShadow/PlausibleSoftShadow.frag:33-49,166-194,365-398,556-563,605-633
+//   RBSM / RPCF / RSMSS  ShadowMapping/Shaders/RBSM/{NonConservativeSMSR,ConservativeSMSR,FilteredRBSM}.frag
+//   many-light           SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag:52-133
+// Shadow-map taps are GL_NEAREST + CLAMP_TO_BORDER(0): texel = floor(coord*size) (MyGLTextureViewer.cpp:3-28).
+// fp32 in source order, -fmad=false: results are bit-identical to oracle/ (DESIGN.md §3).
+#include "sgi_internal.cuh"
+
+namespace {
+
+struct VisArgs {
+  sgi_params p;
+  float mv[16], nm[9], lpos[3];
+  float lmvp[16];
+  const float4* pos4; const float4* nrm4; float* vis;
+  int W, H, rx0, ry0, rx1, ry1;
+  const float* sm; int SW, SH; float fw, fh;
+  float sx, sy;
+  float pcf_off[SGI_MAX_PCF_TAPS]; int pcf_n;
+  float rpcf_off[SGI_MAX_PCF_TAPS]; int rpcf_n;
+  const float4* trans; int N; size_t layer;
+};
+
+struct Smap { const float* __restrict__ d; int w, h; float fw, fh; };
+
+__device__ __forceinline__ float sm_fetch(const Smap& s, float u, float v) {
+  float fi = floorf(u * s.fw), fj = floorf(v * s.fh);
+  if (!(fi >= 0.0f && fi < s.fw && fj >= 0.0f && fj < s.fh)) return 0.0f;
+  return __ldg(&s.d[(size_t)(int)fj * s.w + (int)fi]);
+}
+__device__ __forceinline__ float g_mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float g_max(float a, float b) { return a < b ? b : a; }
+__device__ __forceinline__ float g_min(float a, float b) { return b < a ? b : a; }
+__device__ __forceinline__ float g_fract(float x) { return x - floorf(x); }
+
+__device__ __forceinline__ float4 mat4_mul(const float* __restrict__ m, float4 v) {
+  float4 r;
+  r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
+  r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
+  r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * v.w;
+  r.w = ((m[3] * v.x + m[7] * v.y) + m[11] * v.z) + m[15] * v.w;
+  return r;
+}
+
+// Shadow.frag:222-238
+__device__ __forceinline__ float pre_evaluation(const VisArgs& a, float4 vertex, float4 normal) {
+  float4 ev = mat4_mul(a.mv, vertex);
+  float n0 = (a.nm[0] * normal.x + a.nm[3] * normal.y) + a.nm[6] * normal.z;
+  float n1 = (a.nm[1] * normal.x + a.nm[4] * normal.y) + a.nm[7] * normal.z;
+  float n2 = (a.nm[2] * normal.x + a.nm[5] * normal.y) + a.nm[8] * normal.z;
+  float inv = 1.0f / sqrtf((n0 * n0 + n1 * n1) + n2 * n2);
+  n0 = n0 * inv; n1 = n1 * inv; n2 = n2 * inv;
+  float d0 = a.lpos[0] - ev.x, d1 = a.lpos[1] - ev.y, d2 = a.lpos[2] - ev.z;
+  float invl = 1.0f / sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
+  float L0 = d0 * invl, L1 = d1 * invl, L2 = d2 * invl;
+  if (!(normal.w != 0.0f)) { n0 *= -1.0f; n1 *= -1.0f; n2 *= -1.0f; }
+  float dt = (n0 * L0 + n1 * L1) + n2 * L2;
+  return (g_max(dt, 0.0f) == 0.0f) ? a.p.shadow_intensity : 1.0f;
+}
+
+// ---- Shadow.frag:86-116 (tap offsets precomputed on the host with the same fp32 loop) ----
+__device__ float pcf(const VisArgs& a, const Smap& s, float4 c) {
+  float incrWidth = 1.0f / (float)a.SW, incrHeight = 1.0f / (float)a.SH;
+  float illum = 0.0f;
+  int n = a.pcf_n;
+  if (n <= 0) return 1.0f;
+  for (int iw = 0; iw < n; iw++) {
+    float u = c.x + a.pcf_off[iw] * incrWidth;
+    for (int ih = 0; ih < n; ih++) {
+      float dfl = sm_fetch(s, u, c.y + a.pcf_off[ih] * incrHeight);
+      if (c.z <= dfl) illum += 1.0f; else illum += a.p.shadow_intensity;
+    }
+  }
+  return illum / (float)(n * n);
+}
+
+// ---- PlausibleSoftShadow.frag:166-194, 365-374, 376-398 ----
+__device__ float pcss(const VisArgs& a, const Smap& s, float4 c) {
+  const sgi_params& p = a.p;
+  float averageDepth = 0.0f;
+  int numberOfBlockers = 0;
+  float bsw;
+  if ((float)a.SW <= 1024.0f) bsw = (float)p.light_source_radius / (float)a.SW;
+  else bsw = (float)p.light_source_radius / 1024.0f;
+  float filterWidth = ((float)p.blocker_search_size - 1.0f) * 0.5f;
+  for (int h = (int)(-filterWidth); (float)h <= filterWidth; h++) {
+    float v = c.y + ((float)h * bsw) / filterWidth;
+    for (int w = (int)(-filterWidth); (float)w <= filterWidth; w++) {
+      float u = c.x + ((float)w * bsw) / filterWidth;
+      float dfl = sm_fetch(s, u, v);
+      if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+    }
+  }
+  if (numberOfBlockers == 0) averageDepth = 1.0f;
+  else averageDepth = averageDepth / (float)numberOfBlockers;
+  float penumbraWidth;
+  if (averageDepth < 0.99f) penumbraWidth = 0.0f;
+  else {
+    float pw = ((c.z - averageDepth) / averageDepth) * (float)p.light_source_radius;
+    penumbraWidth = ((float)p.z_near * pw) / c.z;
+  }
+  float illum = 0.0f;
+  float stepSize = 2.0f * penumbraWidth / (float)p.kernel_size;
+  float fw2 = ((float)p.kernel_size - 1.0f) * 0.5f;
+  if (stepSize <= 0.0f || stepSize >= 1.0f) return 1.0f;
+  for (int h = (int)(-fw2); (float)h <= fw2; h++) {
+    float v = c.y + ((float)h * penumbraWidth) / fw2;
+    for (int w = (int)(-fw2); (float)w <= fw2; w++) {
+      float u = c.x + ((float)w * penumbraWidth) / fw2;
+      float dfl = sm_fetch(s, u, v);
+      if (c.z <= dfl) illum += 1.0f; else illum += p.shadow_intensity;
+    }
+  }
+  return illum / (float)(p.kernel_size * p.kernel_size);
+}
+
+// ================================ RBSM ===========================================================
+struct Rb {
+  const Smap& s; float sx, sy; float thr; int max_search; float si; int filtered; float SWf, SHf;
+  float newDepth;
+};
+
+// NonConservativeSMSR.frag:23-54 / ConservativeSMSR.frag:23-48 (same fetch sequence)
+__device__ __forceinline__ void getdisc4(Rb& r, float4 c, float dir[4]) {
+  c.x -= r.sx;
+  dir[0] = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+  c.x += 2.0f * r.sx;
+  dir[1] = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+  c.x -= r.sx;
+  c.y += r.sy;
+  dir[2] = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+  c.y -= 2.0f * r.sy;
+  dir[3] = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+}
+
+// NonConservativeSMSR.frag:56-94
+__device__ bool nc_getdisc_f(Rb& r, float4 c, float dx, float dy, float discType) {
+  if (dx == 0.0f) {
+    c.x -= r.sx;
+    float left = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+    if (fabsf(left - discType) == 0.0f) return true;
+    c.x += 2.0f * r.sx;
+    float right = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+    if (fabsf(right - discType) == 0.0f) return true;
+    c.x -= r.sx;
+  }
+  if (dy == 0.0f) {
+    c.y += r.sy;
+    float bottom = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+    if (fabsf(bottom - discType) == 0.0f) return true;
+    c.y -= 2.0f * r.sy;
+    float top = (c.z <= sm_fetch(r.s, c.x, c.y)) ? 1.0f : 0.0f;
+    if (fabsf(top - discType) == 0.0f) return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool nc_side(Rb& r, float4& c, float ux, float uy, float discB) {
+  float dfl = sm_fetch(r.s, ux, uy);
+  if (discB == 1.0f) {
+    if (fabsf(c.z - dfl) < r.thr) { c.z -= r.thr; r.newDepth = c.z; }
+  }
+  float side = (c.z <= dfl) ? 1.0f : 0.0f;
+  return fabsf(side - discB) == 0.0f;
+}
+
+// NonConservativeSMSR.frag:96-178
+__device__ bool nc_getdisc_v(Rb& r, float4 c, float dx, float dy, float dr, float dg, float db) {
+  float relx = c.x, rely = c.y;
+  r.newDepth = c.z;
+  if (dx == 0.0f) {
+    if (dr == 0.5f || dr == 0.75f) { relx = c.x - r.sx; if (nc_side(r, c, relx, rely, db)) return true; }
+    if (dr == 0.75f || dr == 0.25f) { relx = c.x + r.sx; if (nc_side(r, c, relx, rely, db)) return true; }
+  }
+  if (dy == 0.0f) {
+    if (dg == 0.5f || dg == 0.75f) { rely = c.y + r.sy; if (nc_side(r, c, relx, rely, db)) return true; }
+    if (dg == 0.75f || dg == 0.25f) { rely = c.y - r.sy; if (nc_side(r, c, relx, rely, db)) return true; }
+  }
+  return false;
+}
+
+// NonConservativeSMSR.frag:180-232
+__device__ float nc_disc_length(Rb& r, float dr, float dg, float db, float4 c, float dx, float dy, float subCoord) {
+  float foundEdgeEnd = 0.0f, dist = 0.0f;
+  float stx = dx * r.sx, sty = dy * r.sy;
+  c.x += stx; c.y += sty;
+  for (int it = 0; it < r.max_search; it++) {
+    float dfl = sm_fetch(r.s, c.x, c.y);
+    if (db == 0.0f)
+      if (fabsf(c.z - dfl) < r.thr) c.z -= r.thr;
+    float center = (c.z <= dfl) ? 1.0f : 0.0f;
+    if (fabsf(center - db) == 0.0f) {
+      foundEdgeEnd = nc_getdisc_f(r, c, 0.0f, 0.0f, db) ? 1.0f : 0.0f;
+      break;
+    } else {
+      if (!nc_getdisc_v(r, c, dx, dy, dr, dg, db)) break;
+    }
+    dist += 1.0f;
+    c.x += stx; c.y += sty;
+    if (db == 1.0f) c.z = r.newDepth;
+  }
+  return g_mix(-(dist + (1.0f - subCoord)), dist + (1.0f - subCoord), foundEdgeEnd);
+}
+
+// :234-243 (FilteredRBSM.frag:241)
+__device__ __forceinline__ float nc_rel_pos(const Rb& r, float ax, float ay, float shadow) {
+  float T = 1.0f;
+  if (ax < 0.0f && ay < 0.0f) T = 0.0f;
+  if (ax > 0.0f && ay > 0.0f) T = -2.0f;
+  float edgeLength = g_min(fabsf(ax) + fabsf(ay), (float)r.max_search);
+  float lead = r.filtered ? T : g_max(T, 2.0f * shadow - 1.0f);
+  return (lead * fabsf(g_max(T * ax, T * ay))) / edgeLength;
+}
+
+// :266-274 / FilteredRBSM.frag:266-272
+__device__ __forceinline__ float nc_revectorize(const Rb& r, float rx, float ry, float shadow) {
+  if (r.filtered) {
+    if (rx * ry < 0.0f) return (1.0f - shadow) + (2.0f * shadow - 1.0f) * g_max(rx, ry);
+    else if (rx * ry == 0.0f) return shadow;
+    else {
+      float v = (1.0f - shadow) + (2.0f * shadow - 1.0f) * (rx + ry);
+      return g_min(g_max(v, 0.0f), 1.0f);
+    }
+  }
+  if ((rx * ry == 2.0f * shadow) ||
+      ((fabsf(rx) * fabsf(ry) > 0.0f) && ((1.0f - shadow) + (2.0f * shadow - 1.0f) * (fabsf(rx) + fabsf(ry)) < 0.5f)))
+    return 0.0f;
+  return 1.0f;
+}
+
+// :276-286
+__device__ __forceinline__ void nc_compute_disc(Rb& r, float4 c, float dfl, float& dr, float& dg, float& db) {
+  float center = (c.z <= dfl) ? 1.0f : 0.0f;
+  float dir[4];
+  getdisc4(r, c, dir);
+  float d0 = fabsf(dir[0] - center), d1 = fabsf(dir[1] - center), d2 = fabsf(dir[2] - center), d3 = fabsf(dir[3] - center);
+  dr = (2.0f * d0 + d1) / 4.0f;
+  dg = (2.0f * d2 + d3) / 4.0f;
+  db = 1.0f - center;
+}
+
+__device__ void nc_rel(Rb& r, float4 c, float dr, float dg, float db, float subx, float suby, float shadow, float& rx, float& ry) {
+  float left = nc_disc_length(r, dr, dg, db, c, -1.0f, 0.0f, (1.0f - subx));
+  float right = nc_disc_length(r, dr, dg, db, c, 1.0f, 0.0f, subx);
+  float down = nc_disc_length(r, dr, dg, db, c, 0.0f, -1.0f, (1.0f - suby));
+  float up = nc_disc_length(r, dr, dg, db, c, 0.0f, 1.0f, suby);
+  rx = nc_rel_pos(r, left, right, shadow);
+  ry = nc_rel_pos(r, down, up, shadow);
+}
+
+// :288-304
+__device__ float nc_smsr(Rb& r, float4 c) {
+  float dfl = sm_fetch(r.s, c.x, c.y);
+  float dr, dg, db;
+  nc_compute_disc(r, c, dfl, dr, dg, db);
+  float subx = g_fract(c.x * r.SWf), suby = g_fract(c.y * r.SHf);
+  float shadow = (c.z <= dfl) ? 1.0f : 0.0f;
+  if (dr > 0.0f || dg > 0.0f) {
+    if (dr == 0.75f && dg == 0.75f) return g_mix(1.0f - shadow, 1.0f, r.si);
+    float rx, ry;
+    nc_rel(r, c, dr, dg, db, subx, suby, shadow, rx, ry);
+    return g_mix(nc_revectorize(r, rx, ry, shadow), 1.0f, r.si);
+  }
+  return g_mix(shadow, 1.0f, r.si);
+}
+
+// :306-349
+__device__ float nc_rpcf(Rb& r, const VisArgs& a, float4 c) {
+  float incrWidth = 1.0f / (float)a.SW, incrHeight = 1.0f / (float)a.SH;
+  float illum = 0.0f;
+  int n = a.rpcf_n;
+  if (n <= 0) return 1.0f;
+  for (int iw = 0; iw < n; iw++)
+    for (int ih = 0; ih < n; ih++) {
+      float4 sc = make_float4(c.x + a.rpcf_off[iw] * incrWidth, c.y + a.rpcf_off[ih] * incrHeight, c.z, c.w);
+      float dfl = sm_fetch(r.s, sc.x, sc.y);
+      float shadow = (sc.z <= dfl) ? 1.0f : 0.0f;
+      float dr, dg, db;
+      nc_compute_disc(r, sc, dfl, dr, dg, db);
+      if (dr > 0.0f || dg > 0.0f) {
+        float subx = g_fract(sc.x * r.SWf), suby = g_fract(sc.y * r.SHf);
+        float rx, ry;
+        nc_rel(r, sc, dr, dg, db, subx, suby, shadow, rx, ry);
+        illum += g_mix(nc_revectorize(r, rx, ry, shadow), 1.0f, r.si);
+      } else {
+        illum += g_mix(shadow, 1.0f, r.si);
+      }
+    }
+  return illum / (float)(n * n);
+}
+
+// ---- conservative: ConservativeSMSR.frag ----
+__device__ __forceinline__ void cs_disc(Rb& r, float4 c, float d[4]) {
+  float dir[4];
+  getdisc4(r, c, dir);
+#pragma unroll
+  for (int k = 0; k < 4; k++) d[k] = fabsf(dir[k] - 1.0f);
+}
+
+// :50-86
+__device__ float cs_rel_distance(Rb& r, float4 t, float dx, float dy, float cc) {
+  float foundSilhouetteEnd = 0.0f, distance = 0.0f;
+  float stx = dx * r.sx, sty = dy * r.sy;
+  t.x += stx; t.y += sty;
+  for (int it = 0; it < r.max_search; it++) {
+    float dfl = sm_fetch(r.s, t.x, t.y);
+    if (fabsf(t.z - dfl) < r.thr) t.z -= r.thr;
+    float center = (t.z <= dfl) ? 1.0f : 0.0f;
+    if (!(center != 0.0f)) { foundSilhouetteEnd = 1.0f; break; }
+    else {
+      float d[4];
+      cs_disc(r, t, d);
+      if ((d[0] + d[1] + d[2] + d[3]) == 0.0f) break;
+    }
+    distance += 1.0f;
+    t.x += stx; t.y += sty;
+  }
+  distance = distance + (1.0f - cc);
+  return g_mix(-distance, distance, foundSilhouetteEnd);
+}
+
+// :99-108
+__device__ __forceinline__ float cs_norm(const Rb& r, float ax, float ay) {
+  float T = 1.0f;
+  if (ax < 0.0f && ay < 0.0f) T = 0.0f;
+  if (ax > 0.0f && ay > 0.0f) T = -2.0f;
+  float length = g_min(fabsf(ax) + fabsf(ay), (float)r.max_search);
+  return fabsf(g_max(T * ax, T * ay)) / length;
+}
+
+// :88-97,110-126
+__device__ float cs_revec(Rb& r, float4 sc, float cx, float cy) {
+  float dl = cs_rel_distance(r, sc, -1.0f, 0.0f, (1.0f - cx));
+  float dr = cs_rel_distance(r, sc, 1.0f, 0.0f, cx);
+  float db = cs_rel_distance(r, sc, 0.0f, -1.0f, (1.0f - cy));
+  float dt = cs_rel_distance(r, sc, 0.0f, 1.0f, cy);
+  float rx = cs_norm(r, dl, dr), ry = cs_norm(r, db, dt);
+  if ((rx * ry > 0.0f) && (1.0f - rx > ry)) return r.si;
+  return 1.0f;
+}
+
+// :128-144
+__device__ float cs_smsr(Rb& r, float4 c) {
+  float dfl = sm_fetch(r.s, c.x, c.y);
+  float shadow = (c.z <= dfl) ? 1.0f : 0.0f;
+  if (shadow == 0.0f) return r.si;
+  float d[4];
+  cs_disc(r, c, d);
+  if ((d[0] + d[1] + d[2] + d[3]) == 0.0f) return 1.0f;
+  else if ((d[0] + d[1]) == 2.0f || (d[2] + d[3]) == 2.0f) return r.si;
+  float cx = g_fract(c.x * r.SWf), cy = g_fract(c.y * r.SHf);
+  return cs_revec(r, c, cx, cy);
+}
+
+// :146-198
+__device__ float cs_rpcf(Rb& r, const VisArgs& a, float4 c) {
+  float incrWidth = 1.0f / (float)a.SW, incrHeight = 1.0f / (float)a.SH;
+  float illum = 0.0f;
+  int n = a.rpcf_n;
+  if (n <= 0) return 1.0f;
+  for (int iw = 0; iw < n; iw++)
+    for (int ih = 0; ih < n; ih++) {
+      float u = c.x + a.rpcf_off[iw] * incrWidth, v = c.y + a.rpcf_off[ih] * incrHeight;
+      float dfl = sm_fetch(r.s, u, v);
+      float shadow = (c.z <= dfl) ? 1.0f : r.si;
+      if (shadow == 1.0f) {
+        float4 sc = make_float4(u, v, c.z, c.w);
+        float d[4];
+        cs_disc(r, sc, d);
+        if (d[0] == 0.0f && d[1] == 0.0f) illum += 1.0f;
+        else {
+          float subx = g_fract(sc.x * r.SWf), suby = g_fract(sc.y * r.SHf);
+          illum += cs_revec(r, sc, subx, suby);
+        }
+      } else illum += r.si;
+    }
+  return illum / (float)(n * n);
+}
+
+// ================================ kernels ========================================================
+template <int TECH>
+__global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
+  int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.rx1 || y >= a.ry1) return;
+  size_t o = (size_t)y * a.W + x;
+  float4 vertex = __ldg(&a.pos4[o]);
+  if (vertex.x == 0.0f) return;                                   // discard (Shadow.frag:244): output keeps 0
+  float4 normal = __ldg(&a.nrm4[o]);
+  float4 sc = mat4_mul(a.lmvp, vertex);
+  float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+  float shadow = pre_evaluation(a, vertex, normal);
+  Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
+  if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS) {
+    if (sc.w > 0.0f && shadow == 1.0f) {
+      if (TECH == SGI_TECH_HARD) shadow = (c.z <= sm_fetch(s, c.x, c.y)) ? 1.0f : a.p.shadow_intensity;
+      else if (TECH == SGI_TECH_PCF) shadow = pcf(a, s, c);
+      else shadow = pcss(a, s, c);
+    }
+  } else if (shadow == 1.0f) {
+    Rb r = {s, a.sx, a.sy, a.p.depth_threshold, a.p.max_search, a.p.shadow_intensity, TECH == SGI_TECH_RSMSS, a.fw, a.fh, 0.0f};
+    if (TECH == SGI_TECH_RBSM_NONCONS) shadow = nc_smsr(r, c);
+    else if (TECH == SGI_TECH_RBSM_CONS) shadow = cs_smsr(r, c);
+    else if (TECH == SGI_TECH_RPCF_NONCONS || TECH == SGI_TECH_RSMSS) shadow = nc_rpcf(r, a, c);
+    else if (TECH == SGI_TECH_RPCF_CONS) shadow = cs_rpcf(r, a, c);
+  }
+  a.vis[o] = shadow;
+}
+
+// AccurateSoftShadow.frag:52-133, monteCarlo branch
+__global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
+  int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.rx1 || y >= a.ry1) return;
+  size_t o = (size_t)y * a.W + x;
+  float4 vertex = __ldg(&a.pos4[o]);
+  if (vertex.x == 0.0f) return;
+  const float* m = a.lmvp;
+  float cx = m[0] * vertex.x + m[4] * vertex.y + m[8] * vertex.z;
+  float cy = m[1] * vertex.x + m[5] * vertex.y + m[9] * vertex.z;
+  float cz = m[2] * vertex.x + m[6] * vertex.y + m[10] * vertex.z;
+  float cw = m[3] * vertex.x + m[7] * vertex.y + m[11] * vertex.z;
+  float accShadow = 0.0f, count = 0.0f;
+  const float accFactor = 1.0f;
+  for (int l = 0; l < a.N; l++) {
+    float4 t = __ldg(&a.trans[l]);
+    float sx = cx + t.x, sy = cy + t.y, sz = cz + t.z, sw = cw + t.w;
+    sx = sx / sw; sy = sy / sw; sz = sz / sw;
+    Smap s = {a.sm + a.layer * l, a.SW, a.SH, a.fw, a.fh};
+    float dfl = sm_fetch(s, sx, sy);
+    accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
+    count += accFactor;
+  }
+  a.vis[o] = accShadow / count;
+}
+
+__global__ void k_clear_rect(float* vis, int W, int rx0, int ry0, int rx1, int ry1) {
+  int x = rx0 + blockIdx.x * blockDim.x + threadIdx.x, y = ry0 + blockIdx.y;
+  if (x < rx1 && y < ry1) vis[(size_t)y * W + x] = 0.0f;
+}
+
+}  // namespace
+
+int sgi_host_pcf_offsets(int kernel_order, int penumbra_size, int inclusive, float* out, int cap) {
+  // Shadow.frag:93-98 / NonConservativeSMSR.frag:313-319, evaluated in fp32 exactly as the shader's float loop
+  volatile float offset = (float)penumbra_size;
+  volatile float stepSize = 2 * offset / (float)kernel_order;
+  int n = 0;
+  if (!(stepSize > 0.0f)) return 0;
+  for (volatile float w = -offset; inclusive ? (w <= offset) : (w < offset); w = w + stepSize) {
+    if (n >= cap) return -1;
+    out[n++] = w;
+  }
+  return n;
+}
+
+int sgi_shadow_run(sgi_ctx* ctx) {
+  VisArgs a;
+  a.p = ctx->params;
+  for (int k = 0; k < 16; k++) a.mv[k] = ctx->cam_mv[k];
+  for (int k = 0; k < 9; k++) a.nm[k] = ctx->cam_nm[k];
+  for (int k = 0; k < 3; k++) a.lpos[k] = ctx->light_pos[k];
+  const bool multi = ctx->params.technique == SGI_TECH_MULTI_HARD;
+  const float* lm = ctx->h_light_mvp_b + (multi ? (size_t)(ctx->N - 1) * 16 : 0);
+  for (int k = 0; k < 16; k++) a.lmvp[k] = lm[k];
+  a.pos4 = (const float4*)ctx->buf[SGI_BUF_GBUF_POS];
+  a.nrm4 = (const float4*)ctx->buf[SGI_BUF_GBUF_NRM];
+  a.vis = (float*)ctx->buf[SGI_BUF_VISIBILITY];
+  a.W = ctx->W; a.H = ctx->H;
+  a.rx0 = ctx->params.rect_x0; a.ry0 = ctx->params.rect_y0; a.rx1 = ctx->params.rect_x1; a.ry1 = ctx->params.rect_y1;
+  if (a.rx1 <= a.rx0 || a.ry1 <= a.ry0) { a.rx0 = 0; a.ry0 = 0; a.rx1 = ctx->W; a.ry1 = ctx->H; }
+  a.rx0 = a.rx0 < 0 ? 0 : a.rx0; a.ry0 = a.ry0 < 0 ? 0 : a.ry0;
+  a.rx1 = a.rx1 > ctx->W ? ctx->W : a.rx1; a.ry1 = a.ry1 > ctx->H ? ctx->H : a.ry1;
+  a.sm = (const float*)ctx->buf[SGI_BUF_SHADOW_MAP];
+  a.SW = ctx->SW; a.SH = ctx->SH; a.fw = (float)ctx->SW; a.fh = (float)ctx->SH;
+  a.sx = (float)(1.0 / ctx->SW); a.sy = (float)(1.0 / ctx->SH);      // MyGLGeometryViewer.cpp:238
+  a.pcf_n = ctx->pcf_n; a.rpcf_n = ctx->rpcf_n;
+  for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
+  a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
+
+  int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
+  if (rw <= 0 || rh <= 0) return SGI_OK;
+  cudaStream_t st = ctx->stream;
+  // the reference clears the target to 0 before the full-screen pass (main.cpp:403-405); discarded pixels keep it
+  k_clear_rect<<<dim3((rw + 255) / 256, rh), 256, 0, st>>>(a.vis, a.W, a.rx0, a.ry0, a.rx1, a.ry1);
+  ctx->launches++;
+  dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
+  int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL);
+  switch (ctx->params.technique) {
+    case SGI_TECH_HARD: k_visibility<SGI_TECH_HARD><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_PCF: k_visibility<SGI_TECH_PCF><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_PCSS: k_visibility<SGI_TECH_PCSS><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RBSM_NONCONS: k_visibility<SGI_TECH_RBSM_NONCONS><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RBSM_CONS: k_visibility<SGI_TECH_RBSM_CONS><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RPCF_NONCONS: k_visibility<SGI_TECH_RPCF_NONCONS><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RPCF_CONS: k_visibility<SGI_TECH_RPCF_CONS><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RSMSS: k_visibility<SGI_TECH_RSMSS><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_MULTI_HARD: k_visibility_multi<<<grid, block, 0, st>>>(a); break;
+    default: ctx->err = "unknown technique"; return SGI_ERR_INVALID;
+  }
+  ctx->launches++;
+  sgi_timing_end(ctx, SGI_PASS_VIS_KERNEL, tslot);
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
+}

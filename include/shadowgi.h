@@ -1,0 +1,166 @@
+/*
+ * shadowgi.h — C ABI of the B200-native shadow hot path (libshadowgi.so).
+ *
+ * Drop-in boundary: the reference (MarcioCerqueira/GlobalIllumination) has no plugin API; the seam is
+ * the set of free functions its display() calls once per frame plus the ShadowParams block they share.
+ * Each entry point below names the reference interface it replaces (paths relative to the reference
+ * root).  The only C ABI precedent in the reference is the EDT module
+ * (ShadowMapping/include/EDT/pba2D.h:51-56: init / compute / deinit on caller-owned device memory);
+ * this keeps that shape with an opaque per-GPU context and error codes instead of global state.
+ *
+ * Conventions
+ *   - every function returns SGI_OK (0) or a negative sgi_status; it never exits or throws;
+ *     sgi_last_error(ctx) gives the message of the last failure on that context;
+ *   - host input pointers are borrowed for the duration of the call and copied to the device;
+ *   - outputs live in device memory owned by the context (HBM-resident between passes);
+ *     sgi_read copies one to a host buffer, sgi_device_ptr lends the device pointer;
+ *   - one CUDA stream per context; all passes are asynchronous on it, sgi_read / sgi_synchronize block;
+ *   - matrices are column-major float[16] exactly as the reference hands them to
+ *     glUniformMatrix4fv(..., GL_FALSE, &m[0][0]); images are row-major, row 0 = bottom (GL window
+ *     coordinates), so buffer texel (i, j) is what the reference's full-screen passes read at pixel (i, j);
+ *   - one context per GPU / process rank; a context is not thread-safe.
+ *
+ * No OpenGL, no torch types, no C++ in this header.
+ */
+#ifndef SHADOWGI_H
+#define SHADOWGI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgi_ctx sgi_ctx;
+
+typedef enum sgi_status {
+  SGI_OK = 0,
+  SGI_ERR_INVALID = -1,     /* bad argument / pass called before its inputs were set            */
+  SGI_ERR_CUDA = -2,        /* CUDA runtime failure (message in sgi_last_error)                 */
+  SGI_ERR_NOMEM = -3,
+  SGI_ERR_OVERFLOW = -4,    /* internal bin list overflow: the frame was re-sized, call again   */
+  SGI_ERR_NO_DEVICE = -5    /* no CUDA device: this library has no CPU fallback                 */
+} sgi_status;
+
+/* Technique selector = which fragment program computeHardShadows()/renderSoftShadows() binds
+ * (ShadowMapping/src/main.cpp:400-414, SoftShadowMapping/src/main.cpp:925-1022,756-811) and which
+ * ShadowParams bools select the branch inside it. */
+typedef enum sgi_technique {
+  SGI_TECH_HARD = 0,          /* Shadow.frag, naive                         (Shadow.frag:253-256)            */
+  SGI_TECH_PCF = 1,           /* Shadow.frag, PCF float-loop taps           (Shadow.frag:86-116)             */
+  SGI_TECH_PCSS = 2,          /* PlausibleSoftShadow.frag, PCSS             (:166-194,365-398,556-563)       */
+  SGI_TECH_RBSM_NONCONS = 3,  /* NonConservativeSMSR.frag, SMSR             (:288-304)                       */
+  SGI_TECH_RBSM_CONS = 4,     /* ConservativeSMSR.frag, SMSR                (:128-144)                       */
+  SGI_TECH_RPCF_NONCONS = 5,  /* NonConservativeSMSR.frag, RPCFPlusSMSR     (:306-349)                       */
+  SGI_TECH_RPCF_CONS = 6,     /* ConservativeSMSR.frag, RPCFPlusSMSR        (:146-198)                       */
+  SGI_TECH_RSMSS = 7,         /* FilteredRBSM.frag                          (:241,266-272,381-383)           */
+  SGI_TECH_MULTI_HARD = 8     /* AccurateSoftShadow.frag, monteCarlo        (:52-133), N lights              */
+} sgi_technique;
+
+typedef enum sgi_depth_func { SGI_DEPTH_LESS = 0, SGI_DEPTH_LEQUAL = 1 } sgi_depth_func;
+
+/* Replaces `struct ShadowParams` (ShadowMapping/include/Viewers/ShadowParams.h:6-37 and the superset
+ * SoftShadowMapping/include/Viewers/ShadowParams.h:6-69): the per-frame parameter block every pass reads.
+ * The matrices and GL texture names of the original live in sgi_set_camera / sgi_set_lights / the context.
+ * Defaults in comments are the reference's (ShadowMapping/src/main.cpp:859-877,
+ * SoftShadowMapping/src/main.cpp:1598-1614, ShadowVolumes/src/main.cpp:469). */
+typedef struct sgi_params {
+  int32_t technique;              /* sgi_technique                                          */
+  int32_t shadow_map_width;       /* informational; the authoritative size is sgi_set_lights */
+  int32_t shadow_map_height;
+  float   shadow_intensity;       /* 0.25                                                   */
+  int32_t kernel_order;           /* 7   PCF / RPCF taps per axis (float loop)   */
+  int32_t penumbra_size;          /* 1                                                      */
+  int32_t blocker_search_size;    /* 7   PCSS                                               */
+  int32_t kernel_size;            /* 15  PCSS                                               */
+  int32_t light_source_radius;    /* 8   PCSS                                               */
+  int32_t max_search;             /* 16  RBSM                                               */
+  float   depth_threshold;        /* Configs `d` line                                       */
+  int32_t z_near, z_far;          /* 1, 1000 (`uniform int zNear/zFar`)                     */
+  float   polygon_offset_factor;  /* 4   glPolygonOffset(4, 20), main.cpp:246               */
+  float   polygon_offset_units;   /* 20                                                     */
+  int32_t sv_depth_func;          /* SGI_DEPTH_LEQUAL (steady state of ShadowVolumes/src/main.cpp:174) */
+  int32_t sv_infinity;            /* 100                                                    */
+  int32_t rect_x0, rect_y0, rect_x1, rect_y1;  /* screen rectangle this context evaluates in
+                                     sgi_compute_visibility / shadow-volume counting (multi-GPU
+                                     screen tiles); an empty rectangle means the whole screen */
+} sgi_params;
+
+typedef enum sgi_buffer {
+  SGI_BUF_SHADOW_MAP = 0,   /* float   [N][Sh][Sw]  light-view window depth, cleared to 1.0          */
+  SGI_BUF_GBUF_POS = 1,     /* float4  [H][W]       (world x,y,z,1); background (0,0,0,1)             */
+  SGI_BUF_GBUF_NRM = 2,     /* float4  [H][W]       (object normal xyz, gl_FrontFacing); bg (0,0,0,1) */
+  SGI_BUF_CAM_DEPTH = 3,    /* float   [H][W]       camera-view window depth, cleared to 1.0          */
+  SGI_BUF_VISIBILITY = 4,   /* float   [H][W]       1 = lit, shadow_intensity = shadowed, bg 0        */
+  SGI_BUF_SV_COUNT = 5,     /* int32   [H][W]       signed z-pass count                               */
+  SGI_BUF_SV_STENCIL = 6,   /* uint8   [H][W]       count mod 256 (what the 8-bit stencil holds)      */
+  SGI_BUF_SV_PRISM_XYZ = 7, /* float   [6T][3]      ShadowVolume::update vertices                     */
+  SGI_BUF_SV_PRISM_IDX = 8, /* int32   [6T][3]      ShadowVolume::update indices                      */
+  SGI_BUF_COUNT_ = 9
+} sgi_buffer;
+
+/* passes that can be timed with sgi_pass_time_ms */
+typedef enum sgi_pass {
+  SGI_PASS_SHADOW_MAP = 0, SGI_PASS_GBUFFER = 1, SGI_PASS_VISIBILITY = 2, SGI_PASS_SHADOW_VOLUME = 3,
+  SGI_PASS_VIS_KERNEL = 4,  /* only the per-pixel shadow kernel inside SGI_PASS_VISIBILITY             */
+  SGI_PASS_COUNT_ = 5
+} sgi_pass;
+
+/* lifecycle — replaces initGL()'s FBO/texture/VBO creation (ShadowMapping/src/main.cpp:839-953) */
+int sgi_create(sgi_ctx** out, int device);
+int sgi_destroy(sgi_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the context's own */
+int sgi_set_stream(sgi_ctx* ctx, void* cuda_stream);
+
+/* geometry — replaces MyGLGeometryViewer::loadVBOs (ShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:383-405);
+ * arguments are the Mesh getters getPointCloud/getNormalVector/getIndices (ShadowMapping/include/Mesh.h:35-48).
+ * Uploaded once and kept resident (the reference re-uploads on every draw). */
+int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t num_vertices,
+                 const int32_t* idx, int32_t num_triangles);
+
+/* camera uniforms — replaces configureAmbient + configurePhong for the camera view
+ * (MyGLGeometryViewer.cpp:14-19,108-134): MVP, MV, frozen normalMatrix, window size. */
+int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const float normal_matrix[9],
+                   int32_t width, int32_t height);
+
+/* light uniforms — replaces displaySceneFromLightPOV's lightMVP (ShadowMapping/src/main.cpp:249-266) and
+ * configureShadow's bias multiply (MyGLGeometryViewer.cpp:136-186) done by the caller:
+ *   light_mvp        N x 16, un-biased  (rasterised by sgi_render_shadow_map)
+ *   light_mvp_biased N x 16, bias*lightMVP (sampled by sgi_compute_visibility; for SGI_TECH_MULTI_HARD
+ *                    the 3x4 part of the LAST one is the shader's common term and column 3 of each is
+ *                    lightMVPTrans[i], SoftShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:184-196)
+ *   light_pos_shading  the `lightPosition` uniform: light eye rotated 180 deg about Y (main.cpp:283) */
+int sgi_set_lights(sgi_ctx* ctx, int32_t num_lights, const float* light_mvp, const float* light_mvp_biased,
+                   const float light_pos_shading[3], int32_t map_width, int32_t map_height);
+
+int sgi_set_params(sgi_ctx* ctx, const sgi_params* params);
+void sgi_default_params(sgi_params* params);
+
+/* passes */
+int sgi_render_shadow_map(sgi_ctx* ctx);      /* renderShadowMap(), ShadowMapping/src/main.cpp:350-361 (all N lights) */
+int sgi_render_gbuffer(sgi_ctx* ctx);         /* renderGBuffer(),   ShadowMapping/src/main.cpp:363-372               */
+int sgi_compute_visibility(sgi_ctx* ctx);     /* computeHardShadows() :400-414 / renderSoftShadows()
+                                                 SoftShadowMapping/src/main.cpp:925-1022 / renderMonteCarlo() :756-811 */
+/* ShadowVolume::update (ShadowVolumes/src/ShadowVolume.cpp:116-195) + the stencil pass of display()
+ * (ShadowVolumes/src/main.cpp:154-172).  light_pos = un-rotated light eye.  Needs sgi_render_gbuffer first
+ * (its SGI_BUF_CAM_DEPTH is the depth pre-pass). */
+int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]);
+
+/* results */
+int sgi_read(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes);          /* blocking D2H */
+int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** device_ptr, size_t* bytes);/* borrowed     */
+int sgi_synchronize(sgi_ctx* ctx);
+
+/* instrumentation */
+int sgi_enable_timing(sgi_ctx* ctx, int32_t on);                 /* CUDA events around every pass            */
+int sgi_pass_time_ms(sgi_ctx* ctx, int32_t pass, double* total_ms, int64_t* calls);  /* since last reset      */
+int sgi_reset_timing(sgi_ctx* ctx);
+int sgi_kernel_launches(sgi_ctx* ctx, int64_t* launches);        /* kernels this context has launched so far */
+const char* sgi_last_error(sgi_ctx* ctx);
+const char* sgi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHADOWGI_H */

@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the reference's own sources (runs only where /root/reference exists).
+
+Everything here comes out of oracle/_ref — the reference's unmodified GLSL fragment shaders and its
+Mesh/SceneLoader/OBJLoader/ShadowVolume/UniformSampledLightSource/GLM sources compiled on the CPU by
+oracle/ref_build/build_ref.py.  The .npz files are the committed golden vectors; this script is how they
+were made:   python tests/golden/make_golden.py
+
+  scene_<name>.npz        the reference loader's output for Configs/<Name>.txt: xyz, nrm, idx + views
+  golden_host.npz         GLM frame matrices per config, ShadowVolume prisms, uniform light samples
+  golden_shaders.npz      one small frame (inputs + uniforms) and gl_FragData[0].r of every technique
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.normpath(os.path.join(HERE, "..", "..")))
+from oracle import oracle_py as O  # noqa: E402
+
+SCENES = {"teapot": "Configs/Teapot.txt", "door": "Configs/Door.txt", "dragon": "Configs/Dragon.txt",
+          "raptor": "Configs/Raptor.txt"}
+
+SHADER_OF = {
+    "hard": ("shadow", dict(naive=1, bilinearPCF=1)),
+    "pcf": ("shadow", dict(naive=0, bilinearPCF=1)),
+    "pcss": ("plausible", dict(PCSS=1)),
+    "rbsm_noncons": ("nonconservative", dict(SMSR=1)),
+    "rbsm_cons": ("conservative", dict(SMSR=1)),
+    "rpcf_noncons": ("nonconservative", dict(SMSR=0, RPCFPlusSMSR=1)),
+    "rpcf_cons": ("conservative", dict(SMSR=0, RPCFPlusSMSR=1)),
+    "rsmss": ("filtered", dict(SMSR=0, RPCFPlusSMSR=1)),
+}
+
+
+def shader_uniforms(fm, pos, nrm, sm, S, p):
+    return dict(
+        shadowMap=("tex", sm), vertexMap=("tex", pos), normalMap=("tex", nrm), MV=fm["cam_mv"], lightMVP=fm["light_mvp_b"],
+        normalMatrix=fm["normal_matrix"], lightPosition=fm["light_pos_shading"], shadowIntensity=np.float32(p.shadow_intensity),
+        shadowMapWidth=np.int32(S), shadowMapHeight=np.int32(S), zNear=np.int32(p.z_near), zFar=np.int32(p.z_far),
+        kernelOrder=np.int32(p.kernel_order), penumbraSize=np.int32(p.penumbra_size),
+        shadowMapStep=np.array([np.float32(1.0 / S), np.float32(1.0 / S)], np.float32),
+        depthThreshold=np.float32(p.depth_threshold), maxSearch=np.int32(p.max_search),
+        blockerSearchSize=np.int32(p.blocker_search_size), kernelSize=np.int32(p.kernel_size),
+        lightSourceRadius=np.int32(p.light_source_radius))
+
+
+def ref_visibility(tech, fm, pos, nrm, sm, S, p, W, H):
+    shader, extra = SHADER_OF[tech]
+    u = shader_uniforms(fm, pos, nrm, sm, S, p)
+    u.update({k: np.int32(v) for k, v in extra.items()})
+    return O.ref_run_shader(shader, u, W, H)[..., 0].copy()
+
+
+def multi_light_setup(sc, n_lights, size, W, H, S):
+    """renderMonteCarlo's light set: SoftShadowMapping/src/main.cpp:756-811 (+UniformSampledLightSource)."""
+    mvps, mvpbs = [], []
+    for i in range(n_lights):
+        e = O.ref_uniform_sample(sc["light_eye"], size, n_lights, i)
+        a = O.ref_uniform_sample(sc["light_at"], size, n_lights, i)
+        fm = O.ref_frame_matrices(sc["cam_eye"], sc["cam_at"], e, a, W, H, S, S)
+        mvps.append(fm["light_mvp"]); mvpbs.append(fm["light_mvp_b"])
+    return np.stack(mvps), np.stack(mvpbs)
+
+
+def main():
+    assert O.build_ref(), "oracle/_ref could not be built (is /root/reference mounted?)"
+    scenes = {}
+    for name, cfg in SCENES.items():
+        sc = O.ref_load_scene(cfg)
+        scenes[name] = sc
+        np.savez_compressed(os.path.join(HERE, f"scene_{name}.npz"), **sc)
+        print(name, sc["xyz"].shape, sc["idx"].shape)
+
+    host = {}
+    for name, sc in scenes.items():
+        for (W, H, S) in ((1280, 720, 1024), (1920, 1080, 2048), (640, 480, 512)):
+            fm = O.ref_frame_matrices(sc["cam_eye"], sc["cam_at"], sc["light_eye"], sc["light_at"], W, H, S, S)
+            for k, v in fm.items():
+                host[f"fm/{name}/{W}x{H}x{S}/{k}"] = v
+    d = scenes["door"]
+    pxyz, pidx = O.ref_sv_prisms(d["xyz"], d["nrm"], d["idx"], d["light_eye"], 100)
+    host["sv/door/xyz"], host["sv/door/idx"] = pxyz, pidx
+    for n, size in ((16, 16), (289, 16), (4, 8)):
+        host[f"uls/{n}/{size}"] = np.stack([O.ref_uniform_sample(np.array([10, 130, 100], np.float32), size, n, i) for i in range(n)])
+    host["rotate/33.5/y"] = np.zeros(16, np.float32)
+    O.ref_host().ref_rotate(O.C.c_float(33.5), O._fp(np.array([0, 1, 0], np.float32)), O._fp(host["rotate/33.5/y"]))
+    np.savez_compressed(os.path.join(HERE, "golden_host.npz"), **host)
+
+    # one small frame through every technique of the reference's shaders
+    W, H, S = 160, 90, 128
+    sc = scenes["teapot"]
+    fm = O.ref_frame_matrices(sc["cam_eye"], sc["cam_at"], sc["light_eye"], sc["light_at"], W, H, S, S)
+    sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    out = dict(W=W, H=H, S=S, pos=pos, nrm=nrm, sm=sm, depth_threshold=sc["depth_threshold"], **{f"fm_{k}": v for k, v in fm.items()})
+    for tech in SHADER_OF:
+        for variant, kw in (("default", {}), ("alt", dict(kernel_order=9, kernel_size=7, shadow_intensity=0.5, max_search=8))):
+            p = O.default_params(tech, S, depth_threshold=float(sc["depth_threshold"]), **kw)
+            out[f"vis/{tech}/{variant}"] = ref_visibility(tech, fm, pos, nrm, sm, S, p, W, H)
+    n_l = 4
+    mvps, mvpbs = multi_light_setup(sc, n_l, 8, W, H, S)
+    maps = np.stack([O.raster_depth(sc["xyz"], sc["idx"], mvps[i], S, S) for i in range(n_l)])
+    u = dict(shadowMapArray=("tex", maps, "array"), vertexMap=("tex", pos), normalMap=("tex", nrm), lightMVP=mvpbs[-1],
+             lightMVPTrans=np.ascontiguousarray(mvpbs[:, 12:16]), shadowIntensity=np.float32(0.25), numberOfSamples=np.int32(n_l),
+             shadowMapWidth=np.int32(S), shadowMapHeight=np.int32(S), monteCarlo=np.int32(1), adaptiveSampling=np.int32(0),
+             adaptiveSamplingLowerAccuracy=np.int32(0))
+    out["multi/maps"], out["multi/mvp"], out["multi/mvpb"] = maps, mvps, mvpbs
+    out["multi/vis"] = O.ref_run_shader("accurate", u, W, H)[..., 0].copy()
+    np.savez_compressed(os.path.join(HERE, "golden_shaders.npz"), **out)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

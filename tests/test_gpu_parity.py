@@ -1,0 +1,185 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs — bit-exact.
+
+Bar (BASELINE.json north_star): hard masks and shadow-volume counts bit-exact, soft visibility within 1e-3.
+The oracle and the kernels evaluate the same fp32 expressions in the same order with FMA contraction off
+on both sides, so here EVERYTHING (depth maps, G-buffer, all visibilities, counts) is required to be
+bit-identical; the 1e-3 tolerance is asserted separately so a future relaxation stays visible.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+SOFT_TOL = 1e-3
+TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from globalillumination_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def setup_frame(ctx, sc, W, H, S, pg):
+    fm = util.frame(sc, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    return fm
+
+
+@pytest.mark.parametrize("name,W,H,S", [("teapot", 320, 180, 256), ("door", 200, 150, 128), ("teapot", 1280, 720, 1024),
+                                        ("raptor", 333, 217, 300)])
+def test_depth_and_gbuffer_bit_exact(ctx, name, W, H, S):
+    sc = util.scene(name)
+    po, pg = util.params_pair("hard", S)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map()
+    ctx.render_gbuffer()
+    sm = ctx.read("shadow_map")[0]
+    pos, nrm, dep = ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("cam_depth")
+    sm_o = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    pos_o, nrm_o, dep_o = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    assert util.bits_equal(sm, sm_o), "shadow map: " + util.describe_diff(sm, sm_o)
+    assert util.bits_equal(dep, dep_o), "camera depth: " + util.describe_diff(dep, dep_o)
+    assert util.bits_equal(pos, pos_o), "G-buffer position: " + util.describe_diff(pos, pos_o)
+    assert util.bits_equal(nrm, nrm_o), "G-buffer normal: " + util.describe_diff(nrm, nrm_o)
+    assert (sm_o < 1).mean() > 0.05 and (dep_o < 1).mean() > 0.05     # the frame is not empty
+
+
+@pytest.mark.parametrize("tech", TECHS)
+@pytest.mark.parametrize("name,W,H,S", [("teapot", 320, 180, 256), ("teapot", 1280, 720, 1024)])
+def test_visibility_bit_exact(ctx, name, W, H, S, tech):
+    if tech in ("rpcf_noncons", "rpcf_cons", "rsmss") and W > 640:
+        W, H = 640, 360                                   # the oracle needs seconds per frame for 64x RBSM taps
+    sc = util.scene(name)
+    po, pg = util.params_pair(tech, S, depth_threshold=float(sc["depth_threshold"]))
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map()
+    ctx.render_gbuffer()
+    ctx.compute_visibility()
+    vis = ctx.read("visibility")
+    sm, pos, nrm = ctx.read("shadow_map")[0], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm")
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o = O.visibility(po, cam, fm["light_mvp_b"], pos, nrm, sm)
+    assert np.abs(vis - vis_o).max() <= SOFT_TOL
+    assert np.array_equal(vis == 1.0, vis_o == 1.0), "hard mask: " + util.describe_diff(vis == 1.0, vis_o == 1.0)
+    assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+    fg = pos[..., 0] != 0
+    assert 0.05 < (vis_o[fg] == 1.0).mean() < 0.999        # both lit and shadowed pixels exist
+
+
+@pytest.mark.parametrize("kw", [dict(kernel_order=9, shadow_intensity=0.5), dict(kernel_order=15, penumbra_size=2),
+                                dict(kernel_size=7, blocker_search_size=5, light_source_radius=4), dict(max_search=4, kernel_order=3)])
+@pytest.mark.parametrize("tech", ["pcf", "pcss", "rbsm_noncons", "rpcf_cons", "rsmss"])
+def test_visibility_parameter_sweep(ctx, tech, kw):
+    sc = util.scene("teapot")
+    W, H, S = 256, 144, 200
+    po, pg = util.params_pair(tech, S, depth_threshold=float(sc["depth_threshold"]), **kw)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    vis = ctx.read("visibility")
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o = O.visibility(po, cam, fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
+    assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+
+
+def test_visibility_rect_only_touches_rect(ctx):
+    sc = util.scene("teapot")
+    W, H, S = 320, 180, 256
+    po, pg = util.params_pair("pcf", S)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    full = ctx.read("visibility")
+    po, pg = util.params_pair("hard", S, rect_x0=37, rect_y0=11, rect_x1=200, rect_y1=97)
+    ctx.set_params(pg)
+    ctx.compute_visibility()
+    part = ctx.read("visibility")
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    ref = full.copy()
+    sub = O.visibility(po, cam, fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
+    ref[11:97, 37:200] = sub[11:97, 37:200]
+    assert util.bits_equal(part, ref), util.describe_diff(part, ref)
+
+
+@pytest.mark.parametrize("n_lights,S", [(4, 128), (16, 256)])
+def test_many_light_bit_exact(ctx, n_lights, S):
+    sc = util.scene("teapot")
+    W, H = 320, 180
+    po, pg = util.params_pair("multi_hard", S)
+    fm = util.frame(sc, W, H, S)
+    mvp, mvpb = util.multi_lights(sc, n_lights, 16, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(mvp, mvpb, fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    maps = ctx.read("shadow_map")
+    for i in range(n_lights):
+        m_o = O.raster_depth(sc["xyz"], sc["idx"], mvp[i], S, S)
+        assert util.bits_equal(maps[i], m_o), f"light {i}: " + util.describe_diff(maps[i], m_o)
+    vis = ctx.read("visibility")
+    vis_o = O.visibility_multi(po, mvpb[-1], mvpb[:, 12:16], ctx.read("gbuf_pos"), maps)
+    assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+    assert len(np.unique(vis_o)) > 3                        # penumbra levels exist
+
+
+@pytest.mark.parametrize("name,W,H,func", [("door", 320, 240, O.DEPTH_LEQUAL), ("door", 320, 240, O.DEPTH_LESS),
+                                           ("teapot", 640, 480, O.DEPTH_LEQUAL), ("raptor", 640, 480, O.DEPTH_LEQUAL)])
+def test_shadow_volume_counts_bit_exact(ctx, name, W, H, func):
+    sc = util.scene(name)
+    S = 64
+    po, pg = util.params_pair("hard", S, sv_depth_func=func)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_gbuffer()
+    ctx.compute_shadow_volume(sc["light_eye"])
+    cnt, st = ctx.read("sv_count"), ctx.read("sv_stencil")
+    pxyz, pidx = ctx.read("sv_prism_xyz"), ctx.read("sv_prism_idx")
+    pxyz_o, pidx_o = O.sv_build_prisms(sc["xyz"], sc["nrm"], sc["idx"], sc["light_eye"], 100)
+    assert util.bits_equal(pxyz, pxyz_o), "prism vertices: " + util.describe_diff(pxyz, pxyz_o)
+    assert np.array_equal(pidx, pidx_o)
+    dep = ctx.read("cam_depth")
+    cnt_o, st_o = O.sv_count(pxyz_o, pidx_o, fm["cam_mvp"], W, H, dep, func)
+    assert np.array_equal(cnt, cnt_o), "counts: " + util.describe_diff(cnt, cnt_o)
+    assert np.array_equal(st, st_o)
+    assert (cnt_o != 0).mean() > 0.01
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    from globalillumination_b200 import capi
+    sc = util.scene("door")
+    W, H, S = 64, 48, 32
+    po, pg = util.params_pair("hard", S)
+    fm = util.frame(sc, W, H, S)
+    # degenerate triangles (repeated vertex), a triangle behind the camera, NaN vertex
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [np.nan, 0, 0], [0, 500, -900], [1, 500, -900], [0, 501, -900]], np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (7, 1))
+    idx = np.array([[0, 0, 1], [0, 1, 2], [3, 1, 2], [4, 5, 6]], np.int32)
+    ctx.set_mesh(xyz, nrm, idx)
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    sm_o = O.raster_depth(xyz, idx, fm["light_mvp"], S, S)
+    pos_o, nrm_o, dep_o = O.raster_gbuffer(xyz, nrm, idx, fm["cam_mvp"], W, H)
+    assert util.bits_equal(ctx.read("shadow_map")[0], sm_o)
+    assert util.bits_equal(ctx.read("gbuf_pos"), pos_o)
+    assert util.bits_equal(ctx.read("cam_depth"), dep_o)
+    # zero triangles: cleared outputs
+    ctx.set_mesh(xyz, nrm, np.zeros((0, 3), np.int32))
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    assert (ctx.read("shadow_map") == 1.0).all() and (ctx.read("visibility") == 0.0).all()
+    assert (ctx.read("gbuf_pos")[..., 3] == 1.0).all() and (ctx.read("gbuf_pos")[..., :3] == 0.0).all()
+    # error paths: bad index, pass before inputs
+    with pytest.raises(capi.SgiError):
+        ctx.set_mesh(xyz, nrm, np.array([[0, 1, 99]], np.int32))
+    c2 = capi.Context(0)
+    with pytest.raises(capi.SgiError):
+        c2.render_shadow_map()
+    c2.close()
