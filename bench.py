@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py — frames/s of the shadow hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2_sponza|c5_many_light]
+
+A "step" is one frame of the hot path = light-view depth pass (K1) + camera G-buffer pass (K2) + per-pixel
+shadow pass (K3) on the workload BASELINE.json's metric is quoted on (c2: Sponza, 1920x1080, 2048^2 PCSS),
+driven through the C++ host side (SceneLoader -> ShadowApp::display) and the C ABI.  The light moves by the
+reference's animation step every frame (ShadowMapping/src/main.cpp:217,481).
+
+  value   frames/s, geometry resident in HBM, no readback; per-step CUDA-event times on the context's stream,
+          L2 flushed (256 MiB memset) before every timed step, max over ranks
+  e2e     frames/s through ShadowApp's host-buffer entry (geometry re-uploaded from pinned host memory every
+          frame as the reference's loadVBOs does + visibility read back to pinned host memory)
+  roofline  the kernel with the largest share of the step, timed with CUDA events around its launches
+  cpu_baseline  the CPU oracle (oracle/, a port of the reference's passes) on the host cores, a few frames
+N > 1: frame-parallel — every rank renders its own frames of the same animation (no data-path collective,
+"scaling": "weak"); `value` is the sum over ranks / max time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec at 1920x1080 (Sponza, 2048^2 PCSS)"
+ANIMATION_STEP = 6.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(w, V, T, L):
+    """SURVEY.md §8(d) / BASELINE.md §3 per-frame algorithmic bytes of each pass."""
+    px, S = w["W"] * w["H"], w["S"]
+    return {"shadow_map": L * (4 * S * S + 12 * (V + T)), "gbuffer": 32 * px + 12 * (V + T), "visibility": 36 * px + L * 4 * S * S}
+
+
+def run_reference(args, w, cfg_path):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference's GL
+    passes cannot run here: no OpenGL; its shaders compiled as C++ are used as the oracle's pin)."""
+    from oracle import oracle_py as O
+    from globalillumination_b200 import hostapi
+    sc = hostapi.load_scene(cfg_path)
+    W, H, S = w["W"], w["H"], w["S"]
+    n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
+    tech = {"pcss": "pcss", "montecarlo": "multi_hard"}[w["technique"]]
+    p = O.default_params(tech, S, depth_threshold=float(sc["depth_threshold"]),
+                         **{k2: w["params"][k1] for k1, k2 in (("blockerSearchSize", "blocker_search_size"), ("kernelSize", "kernel_size"),
+                                                                ("lightSourceRadius", "light_source_radius")) if k1 in w["params"]})
+
+    def frame(anim):
+        le = sc["light_eye"]
+        if anim is not None:
+            r = O.rotate(anim / 10.0, [0, 1, 0]).reshape(4, 4).T[:3, :3]
+            le = (r @ le).astype(np.float32)
+        if n_l == 1:
+            fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
+            sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+            pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+            cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+            return O.visibility(p, cam, fm["light_mvp_b"], pos, nrm, sm)
+        fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
+        pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+        maps, mvpb = [], []
+        for i in range(n_l):
+            e = O.uniform_light_sample(le, w["params"]["lightSourceSize"], n_l, i)
+            a = O.uniform_light_sample(sc["light_at"], w["params"]["lightSourceSize"], n_l, i)
+            f2 = O.frame_matrices(sc["cam_eye"], sc["cam_at"], e, a, W, H, S, S)
+            maps.append(O.raster_depth(sc["xyz"], sc["idx"], f2["light_mvp"], S, S)); mvpb.append(f2["light_mvp_b"])
+        mvpb = np.stack(mvpb)
+        return O.visibility_multi(p, mvpb[-1], mvpb[:, 12:16], pos, np.stack(maps))
+
+    anim = -1800.0
+    for _ in range(args.warmup):
+        frame(anim); anim += ANIMATION_STEP
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame(anim); anim += ANIMATION_STEP
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    cores = O.num_threads()
+    return {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "W": W, "H": H, "shadow_map": S, "technique": w["technique"], "lights": n_l, "scene": w["scene"]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full frames (depth + G-buffer + shadow pass) of the same workload, OpenMP over {cores} threads"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_sponza")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from globalillumination_b200 import scenes
+    w = scenes.WORKLOADS[args.workload]
+    cfg_path = scenes.write_config(args.workload)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        args.steps = args.steps or 3
+        args.warmup = 1 if args.warmup is None else args.warmup
+        print(json.dumps(run_reference(args, w, cfg_path)), flush=True)
+        return 0
+
+    args.steps = args.steps or 200
+    args.warmup = 10 if args.warmup is None else max(3, args.warmup)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the shadow path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from globalillumination_b200 import capi, hostapi
+    app = hostapi.App(local_rank)
+    app.load_scene(cfg_path)
+    app.configure(w["W"], w["H"], w["S"])
+    app.set_technique(w["technique"])
+    app.set(**w["params"])
+    app.set(animationOn=1, animation=-1800.0 + ANIMATION_STEP * rank)     # rank r renders frames r, r+N, ...
+    program = w["program"]
+    ctx = app.context()
+    stream = torch.cuda.Stream(device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    xyz, nrm, idx = app.scene_arrays()
+    V, T = xyz.shape[0], idx.shape[0]
+    n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    app.upload_scene()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            app.display(program); app.step_animation(ANIMATION_STEP * world)
+        ctx.synchronize()
+
+        # ---- timed region: K steps, per-step events, L2 flushed before each ----
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        launches0 = ctx.kernel_launches()
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record(stream)
+            app.display(program)
+            ev[k][1].record(stream)
+            app.step_animation(ANIMATION_STEP * world)
+        ctx.synchronize()
+        barrier()
+        clock_info = clocks.stop() if rank == 0 else None
+        launches = ctx.kernel_launches() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+
+        # ---- per-kernel shares (same steps again, CUDA events around the kernels of each pass) ----
+        ctx.enable_timing(True); ctx.reset_timing()
+        for k in range(min(args.steps, 100)):
+            flush.zero_()
+            app.display(program); app.step_animation(ANIMATION_STEP * world)
+        ctx.synchronize()
+        passes = {}
+        for name in capi.PASS:
+            ms, n = ctx.pass_time_ms(name)
+            if n:
+                passes[name] = ms / n * (n / min(args.steps, 100))       # ms per frame
+        ctx.enable_timing(False)
+
+        # ---- e2e: host buffers in, host buffer out, every frame ----
+        vis_bytes = w["W"] * w["H"] * 4
+        host_vis = torch.empty(w["W"] * w["H"], dtype=torch.float32).pin_memory()
+        e2e_steps = max(10, min(args.steps, 100))
+        for _ in range(3):
+            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(ANIMATION_STEP * world)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(ANIMATION_STEP * world)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        lit = float((host_vis == 1.0).float().mean())
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    fps = world * args.steps / (total_ms / 1e3)
+    peak, peak_src = load_peaks()
+    ab = algorithmic_bytes(w, V, T, n_l)
+    kernel_of = {"vis_kernel": ("k_visibility (per-pixel shadow test/filter)", ab["visibility"]),
+                 "tile_depth": ("k_tile<DEPTH> (light-view tile rasteriser)", ab["shadow_map"] // max(1, n_l)),
+                 "tile_gbuffer": ("k_tile<GBUFFER> (camera-view tile rasteriser + resolve)", ab["gbuffer"])}
+    cand = {k: v for k, v in passes.items() if k in kernel_of}
+    roof = None
+    if cand:
+        top = max(cand, key=cand.get)
+        calls = n_l if top == "tile_depth" else 1
+        per_launch_ms = cand[top] / calls
+        achieved = kernel_of[top][1] / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": kernel_of[top][0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": kernel_of[top][1], "launch_ms": per_launch_ms, "peak_source": peak_src,
+                "share_of_step": cand[top] / (total_ms / args.steps)}
+    out = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,
+                   "params": w["params"], "triangles": T, "vertices": V, "scene": w["scene"],
+                   "l2": "flushed before every timed step (256 MiB memset on the same stream, outside the event pair)",
+                   "parallelism": f"frames x{world}" if world > 1 else "single GPU", "lit_fraction": lit},
+        "clocks": clock_info, "gpu_launches": int(launches),
+        "e2e": {"value": world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * 24 + T * 12),
+                "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps},
+        "pass_ms": passes, "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup = 3, 1
+        out["cpu_baseline"] = run_reference(a2, w, cfg_path)["cpu_baseline"]
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,13 +63,14 @@ def build_host(force=False):
     deps = srcs + _sources(HOST, (".h",)) + [os.path.join(ROOT, "include", "shadowgi.h")]
     if force or _stale(out, deps):
         cmd = [_cxx(), "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-shared",
-               "-I", os.path.join(ROOT, "include"), "-o", out] + srcs + ["-ldl"]
+               "-I", os.path.join(ROOT, "include"), "-o", out] + srcs + ["-L", PKG, "-lshadowgi", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return out
 
 
 def build_all(force=False):
-    return build_cuda(force), build_host(force)
+    cuda = build_cuda(force)          # the host library links against it
+    return cuda, build_host(force)
 
 
 if __name__ == "__main__":

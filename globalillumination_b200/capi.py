@@ -14,7 +14,8 @@ TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf
         "rsmss": 7, "multi_hard": 8}
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
        "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8}
-PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4}
+PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
+        "tile_gbuffer": 6, "tile_sv": 7}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
 SGI_ERR_OVERFLOW = -4
 
@@ -38,7 +39,7 @@ EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
-    "sgi_pass_time_ms", "sgi_reset_timing", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
+    "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
 _lib = None

@@ -323,6 +323,12 @@ int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** dptr, size_t* bytes) {
   return ctx->buf[which] ? SGI_OK : SGI_ERR_INVALID;
 }
 
+int sgi_alloc_host(void** p, size_t bytes) {
+  if (!p || bytes == 0) return SGI_ERR_INVALID;
+  return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? SGI_OK : SGI_ERR_NOMEM;
+}
+int sgi_free_host(void* p) { return (p && cudaFreeHost(p) == cudaSuccess) ? SGI_OK : SGI_ERR_INVALID; }
+
 int sgi_enable_timing(sgi_ctx* ctx, int32_t on) {
   if (!ctx) return SGI_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -547,7 +547,10 @@ static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : (MODE == SGI_MODE_GBUFFER ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
+  int tslot = sgi_timing_begin(ctx, pass);
   k_tile<MODE><<<grid, SGI_TILE_THREADS, smem, ctx->stream>>>(ta);
+  sgi_timing_end(ctx, pass, tslot);
   ctx->launches++;
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;

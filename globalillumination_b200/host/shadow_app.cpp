@@ -1,0 +1,234 @@
+// shadow_app.cpp — see shadow_app.h.
+#include "shadow_app.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace sgh {
+
+ShadowApp::ShadowApp(int device) {
+  int rc = sgi_create(&ctx, device);
+  if (rc != SGI_OK) { ctx = nullptr; err = "sgi_create failed (no CUDA device; this path has no CPU fallback)"; }
+  normalMatrix = Mat3{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+}
+ShadowApp::~ShadowApp() { if (ctx) sgi_destroy(ctx); }
+
+int ShadowApp::fail(int rc, const char* where) {
+  err = std::string(where) + ": " + (ctx ? sgi_last_error(ctx) : "no context");
+  return rc;
+}
+
+int ShadowApp::loadScene(const char* config, const char* base_dir) {
+  scene = Mesh();
+  SceneLoader loader(config, &scene);
+  int rc = loader.load(base_dir ? base_dir : "");
+  if (rc) { err = loader.error(); return rc; }
+  cameraEye = Vec3{loader.getCameraPosition()[0], loader.getCameraPosition()[1], loader.getCameraPosition()[2]};   // main.cpp:861-865
+  cameraAt = Vec3{loader.getCameraAt()[0], loader.getCameraAt()[1], loader.getCameraAt()[2]};
+  lightPositionConfig = Vec3{loader.getLightPosition()[0], loader.getLightPosition()[1], loader.getLightPosition()[2]};
+  lightAt = Vec3{loader.getLightAt()[0], loader.getLightAt()[1], loader.getLightAt()[2]};
+  shadowParams.depthThreshold = loader.getDepthThreshold();
+  uploaded = false; normalMatrixSet = false;
+  return 0;
+}
+
+int ShadowApp::setScene(const float* xyz, const float* nrm, int nv, const int* idx, int nt, const float camEye[3], const float camAt_[3],
+                        const float lightEyeCfg[3], const float lightAt_[3], float depthThreshold) {
+  scene = Mesh();
+  scene.setGeometry(xyz, nv, idx, nt);
+  scene.computeNormals();
+  if (nrm) std::memcpy(scene.getNormalVector(), nrm, sizeof(float) * 3 * (size_t)nv);
+  cameraEye = Vec3{camEye[0], camEye[1], camEye[2]}; cameraAt = Vec3{camAt_[0], camAt_[1], camAt_[2]};
+  lightPositionConfig = Vec3{lightEyeCfg[0], lightEyeCfg[1], lightEyeCfg[2]}; lightAt = Vec3{lightAt_[0], lightAt_[1], lightAt_[2]};
+  shadowParams.depthThreshold = depthThreshold;
+  uploaded = false; normalMatrixSet = false;
+  return 0;
+}
+
+int ShadowApp::uploadScene() {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  int rc = sgi_set_mesh(ctx, scene.getPointCloud(), scene.getNormalVector(), scene.getPointCloudSize() / 3, scene.getIndices(),
+                        scene.getNumberOfTriangles());
+  if (rc) return fail(rc, "uploadScene");
+  uploaded = true;
+  return 0;
+}
+
+// main.cpp:209-219
+void ShadowApp::updateLight() {
+  lightEye.x = lightPositionConfig.x + lightTranslationVector[0];
+  lightEye.y = lightPositionConfig.y + lightTranslationVector[1];
+  lightEye.z = lightPositionConfig.z + lightTranslationVector[2];
+  if (animationOn) lightEye = mul3(rotate((float)animation / 10, Vec3{0, 1, 0}), lightEye);
+}
+
+// main.cpp:190-195
+Mat4 ShadowApp::modelMatrix() const {
+  Mat4 model = identity();
+  model = mul(model, translate(Vec3{translationVector[0], translationVector[1], translationVector[2]}));
+  model = mul(model, rotate(rotationAngles[0], Vec3{1, 0, 0}));
+  model = mul(model, rotate(rotationAngles[1], Vec3{0, 1, 0}));
+  model = mul(model, rotate(rotationAngles[2], Vec3{0, 0, 1}));
+  return model;
+}
+
+static FrameMatrices composeFrame(Vec3 lightEye, Vec3 lightAt, Vec3 lightUp, Vec3 camEye, Vec3 camAt, Vec3 camUp, const Mat4& model,
+                                  int W, int H, int SW, int SH) {
+  const float fov = 45.f, zNear = 1.0f, zFar = 1000.0f;                 // MyGLGeometryViewer.cpp:6-8
+  FrameMatrices f;
+  Mat4 projection = perspective(fov, (float)SW / SH, zNear, zFar);      // configureAmbient :17
+  Mat4 view = lookAt(lightEye, lightAt, lightUp);
+  f.lightMVP = mul(mul(projection, view), model);                       // main.cpp:264
+  f.lightMVPBiased = mul(biasMatrix(), f.lightMVP);                     // configureShadow :145
+  f.lightPositionShading = mul3(rotate(180.0f, Vec3{0, 1, 0}), lightEye);   // main.cpp:283
+  projection = perspective(fov, (float)W / H, zNear, zFar);
+  view = lookAt(camEye, camAt, camUp);
+  f.cameraMVP = mul(mul(projection, view), model);                      // configurePhong :111-112
+  f.cameraMV = mul(view, model);
+  f.normalMatrix = inverseTranspose3(f.cameraMV);                       // :115
+  return f;
+}
+
+FrameMatrices ShadowApp::frameMatrices() {
+  updateLight();
+  FrameMatrices f = composeFrame(lightEye, lightAt, lightUp, cameraEye, cameraAt, cameraUp, modelMatrix(), windowWidth, windowHeight,
+                                 shadowParams.shadowMapWidth, shadowParams.shadowMapHeight);
+  if (!normalMatrixSet) { normalMatrix = f.normalMatrix; normalMatrixSet = true; }   // frozen (:114-117)
+  f.normalMatrix = normalMatrix;
+  return f;
+}
+
+// computeHardShadows' program selection (main.cpp:406-411) + the branch each program takes on its uniforms
+int ShadowApp::technique() const {
+  const ShadowParams& p = shadowParams;
+  if (p.SMSR || p.RPCFPlusSMSR || p.EDTSM) {
+    bool smsr = p.SMSR || p.EDTSM;                                      // NonConservativeSMSR.frag:381
+    if (p.conservative) return smsr ? SGI_TECH_RBSM_CONS : SGI_TECH_RPCF_CONS;
+    return smsr ? SGI_TECH_RBSM_NONCONS : SGI_TECH_RPCF_NONCONS;
+  }
+  if (p.RSMSS || p.RPCFPlusRSMSS) return SGI_TECH_RSMSS;
+  if (p.naive) return SGI_TECH_HARD;                                    // Shadow.frag:253
+  if (p.VSM || p.ESM || p.EVSM || p.MSM || p.tricubicPCF) return -1;    // pre-filtered maps: out of scope
+  return SGI_TECH_PCF;
+}
+
+int ShadowApp::pushParams(int tech) {
+  sgi_params q;
+  sgi_default_params(&q);
+  const ShadowParams& p = shadowParams;
+  q.technique = tech;
+  curTech = tech;
+  q.shadow_map_width = p.shadowMapWidth; q.shadow_map_height = p.shadowMapHeight;
+  q.shadow_intensity = p.shadowIntensity;
+  q.kernel_order = p.kernelOrder; q.penumbra_size = p.penumbraSize;
+  q.blocker_search_size = p.blockerSearchSize; q.kernel_size = p.kernelSize; q.light_source_radius = p.lightSourceRadius;
+  q.max_search = p.maxSearch; q.depth_threshold = p.depthThreshold;
+  q.sv_depth_func = svDepthFunc; q.sv_infinity = svInfinity;
+  q.rect_x0 = rect[0]; q.rect_y0 = rect[1]; q.rect_x1 = rect[2]; q.rect_y1 = rect[3];
+  int rc = sgi_set_params(ctx, &q);
+  return rc ? fail(rc, "sgi_set_params") : 0;
+}
+
+int ShadowApp::renderShadowMap() {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  if (!uploaded) { int rc = uploadScene(); if (rc) return rc; }
+  FrameMatrices f = frameMatrices();
+  shadowParams.lightMVP = f.lightMVP;
+  int rc = sgi_set_lights(ctx, 1, f.lightMVP.m, f.lightMVPBiased.m, &f.lightPositionShading.x, shadowParams.shadowMapWidth,
+                          shadowParams.shadowMapHeight);
+  if (rc) return fail(rc, "sgi_set_lights");
+  if ((rc = pushParams(technique() < 0 ? SGI_TECH_HARD : technique()))) return rc;
+  rc = sgi_render_shadow_map(ctx);
+  return rc ? fail(rc, "sgi_render_shadow_map") : 0;
+}
+
+int ShadowApp::renderGBuffer() {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  if (!uploaded) { int rc = uploadScene(); if (rc) return rc; }
+  FrameMatrices f = frameMatrices();
+  int rc = pushParams(curTech);                              // the screen rectangle travels in the params block
+  if (rc) return rc;
+  rc = sgi_set_camera(ctx, f.cameraMVP.m, f.cameraMV.m, f.normalMatrix.m, windowWidth, windowHeight);
+  if (rc) return fail(rc, "sgi_set_camera");
+  rc = sgi_render_gbuffer(ctx);
+  return rc ? fail(rc, "sgi_render_gbuffer") : 0;
+}
+
+int ShadowApp::computeHardShadows() {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  int tech = technique();
+  if (tech < 0) { err = "computeHardShadows: VSM/ESM/EVSM/MSM/tricubic PCF are outside the shadow hot path (SURVEY.md C17)"; return SGI_ERR_INVALID; }
+  int rc = pushParams(tech);
+  if (rc) return rc;
+  rc = sgi_compute_visibility(ctx);
+  return rc ? fail(rc, "sgi_compute_visibility") : 0;
+}
+
+int ShadowApp::display() {                                  // main.cpp:459-472 without shadeScene/swap
+  int rc;
+  if ((rc = renderShadowMap())) return rc;
+  if ((rc = renderGBuffer())) return rc;
+  return computeHardShadows();
+}
+
+int ShadowApp::renderSoftShadows() {                        // SoftShadowMapping/src/main.cpp:925-1022: G-buffer first, then the map
+  int rc;
+  if ((rc = renderGBuffer())) return rc;
+  if ((rc = renderShadowMap())) return rc;
+  if (!shadowParams.PCSS) { err = "renderSoftShadows: only the PCSS branch is on the hot path (SURVEY.md C17/C18)"; return SGI_ERR_INVALID; }
+  if ((rc = pushParams(SGI_TECH_PCSS))) return rc;
+  rc = sgi_compute_visibility(ctx);
+  return rc ? fail(rc, "sgi_compute_visibility") : 0;
+}
+
+// UniformSampledLightSource::computeUniformSampling (SoftShadowMapping/src/Scene/LightSource/UniformSampledLightSource.cpp:27-38)
+static Vec3 uniformSample(Vec3 sample, int size, int numberOfPointLights, int sampleIndex) {
+  float halfSize = (float)((float)size / 2.0);
+  float factor = sqrtf((float)numberOfPointLights);
+  float sampleSize = (float)((factor - 1) / 2.0);
+  sample.x += (((sampleIndex % (int)factor) - sampleSize) / sampleSize) * halfSize;
+  sample.y += (((int)(sampleIndex / factor) - sampleSize) / sampleSize) * halfSize;
+  return sample;
+}
+
+int ShadowApp::renderMonteCarlo() {                          // SoftShadowMapping/src/main.cpp:756-811
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  int rc;
+  // the reference re-uses the previous technique's G-buffer; here it is rendered explicitly
+  if ((rc = renderGBuffer())) return rc;
+  updateLight();
+  int n = shadowParams.numberOfSamples;
+  if (n <= 0 || n > 1024) { err = "renderMonteCarlo: numberOfSamples must be in 1..1024"; return SGI_ERR_INVALID; }
+  std::vector<float> mvp((size_t)n * 16), mvpb((size_t)n * 16);
+  Mat4 model = modelMatrix();
+  FrameMatrices f;
+  for (int s = 0; s < n; s++) {
+    Vec3 e = uniformSample(lightEye, shadowParams.lightSourceSize, n, s), a = uniformSample(lightAt, shadowParams.lightSourceSize, n, s);
+    f = composeFrame(e, a, lightUp, cameraEye, cameraAt, cameraUp, model, windowWidth, windowHeight, shadowParams.shadowMapWidth,
+                     shadowParams.shadowMapHeight);
+    std::memcpy(&mvp[(size_t)s * 16], f.lightMVP.m, 64);
+    std::memcpy(&mvpb[(size_t)s * 16], f.lightMVPBiased.m, 64);
+  }
+  Vec3 shading = mul3(rotate(180.0f, Vec3{0, 1, 0}), lightEye);
+  rc = sgi_set_lights(ctx, n, mvp.data(), mvpb.data(), &shading.x, shadowParams.shadowMapWidth, shadowParams.shadowMapHeight);
+  if (rc) return fail(rc, "sgi_set_lights");
+  if ((rc = pushParams(SGI_TECH_MULTI_HARD))) return rc;
+  if ((rc = sgi_render_shadow_map(ctx))) return fail(rc, "sgi_render_shadow_map");
+  rc = sgi_compute_visibility(ctx);
+  return rc ? fail(rc, "sgi_compute_visibility") : 0;
+}
+
+int ShadowApp::displaySoft() { return shadowParams.monteCarlo ? renderMonteCarlo() : renderSoftShadows(); }
+
+int ShadowApp::renderShadowVolumes() {                       // ShadowVolumes/src/main.cpp:126-172
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  int rc;
+  if ((rc = renderGBuffer())) return rc;                     // depth pre-pass (:154-158)
+  if ((rc = pushParams(SGI_TECH_HARD))) return rc;
+  updateLight();
+  rc = sgi_compute_shadow_volume(ctx, &lightEye.x);          // shadowVolume->update(scene, lightEye) + stencil pass
+  return rc ? fail(rc, "sgi_compute_shadow_volume") : 0;
+}
+int ShadowApp::displayShadowVolumes() { return renderShadowVolumes(); }
+
+}  // namespace sgh

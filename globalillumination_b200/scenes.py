@@ -1,0 +1,39 @@
+"""The workloads of BASELINE.json as data: each is written out in the reference's Configs/*.txt grammar
+ and loaded through the C++ SceneLoader, so the bench exercises the same host path a
+reference user would.  Values are those of the reference's config files (cited per entry); geometry that is
+absent from the reference mount (.MISSING_LARGE_BLOBS) is replaced by the seeded procedural stand-ins of
+host/procedural.cpp via `o procedural:<spec>` lines.  /root/reference is never read at run time.
+"""
+import os
+import tempfile
+
+WORKLOADS = {
+    # Configs/Sponza.txt:1-12 — asset OBJ/Sponza/sponza.obj is missing from the mount -> procedural atrium
+    "c2_sponza": dict(
+        lines=["o procedural:sponza_like?seed=1", "s 2 2 2", "r 0 90 0", "t 0.0 0.0 -30.0", "c 0.5 0.0 0.0", "+",
+               "ve 0.0 19.0 -52.0", "va 0.0 -2.0 -22.0", "le 0.0 43.0 -50.0", "la 0.0 -17.0 -17.0", "d 0"],
+        W=1920, H=1080, S=2048, program="soft_shadow_mapping", technique="pcss",
+        params=dict(blockerSearchSize=7, kernelSize=15, lightSourceRadius=8),
+        scene="procedural sponza_like(seed=1), 69424 triangles (reference asset absent from the mount)"),
+    # Configs/SanDiego.txt:1-26 — building.obj is not shipped to the GPU box, spheres are missing upstream ->
+    # procedural city block of spheres over the plane; 16 lights = 4x4 UniformSampledLightSource, size 16
+    "c5_many_light": dict(
+        lines=["o procedural:sponza_like?seed=5", "s 1.2 1.2 1.2", "t -10.0 -8.0 0.0", "r 0.0 90.0 0.0", "c 1.0 1.0 0.5", "+",
+               "o procedural:sphere?seed=2", "s 1.5 1.5 1.5", "t 1.5 -8.0 6.0", "+",
+               "o procedural:sphere?seed=2", "s 1.5 1.5 1.5", "t -2.5 -8.0 6.0", "+",
+               "o procedural:plane", "s 60.0 1.0 40.0", "t 0.0 -8.0 0.0", "+",
+               "ve 0.0 41.0 -50.0", "va 0.0 16.0 -10.0", "le 10.0 130.0 100.0", "la 0.0 0.0 0.0", "d 0.000025"],
+        W=7680, H=4320, S=8192, program="soft_shadow_mapping", technique="montecarlo",
+        params=dict(numberOfSamples=16, lightSourceSize=16),
+        scene="procedural stand-in for Configs/SanDiego.txt (building/sphere assets not available on the GPU box)"),
+}
+
+
+def write_config(name, directory=None):
+    """Write WORKLOADS[name] as a Configs-style text file and return its path."""
+    w = WORKLOADS[name]
+    directory = directory or tempfile.mkdtemp(prefix="shadowgi_cfg_")
+    path = os.path.join(directory, name + ".txt")
+    with open(path, "w") as f:
+        f.write("\n".join(w["lines"]))          # no trailing newline, like the reference's files
+    return path

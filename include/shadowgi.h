@@ -104,7 +104,10 @@ typedef enum sgi_buffer {
 typedef enum sgi_pass {
   SGI_PASS_SHADOW_MAP = 0, SGI_PASS_GBUFFER = 1, SGI_PASS_VISIBILITY = 2, SGI_PASS_SHADOW_VOLUME = 3,
   SGI_PASS_VIS_KERNEL = 4,  /* only the per-pixel shadow kernel inside SGI_PASS_VISIBILITY             */
-  SGI_PASS_COUNT_ = 5
+  SGI_PASS_TILE_DEPTH = 5,  /* only the per-tile raster kernel of the light-view depth pass (per light)  */
+  SGI_PASS_TILE_GBUFFER = 6,/* only the per-tile raster+resolve kernel of the G-buffer pass              */
+  SGI_PASS_TILE_SV = 7,     /* only the per-tile counting kernel of the shadow-volume pass               */
+  SGI_PASS_COUNT_ = 8
 } sgi_pass;
 
 /* lifecycle — replaces initGL()'s FBO/texture/VBO creation (ShadowMapping/src/main.cpp:839-953) */
@@ -151,6 +154,11 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]);
 int sgi_read(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes);          /* blocking D2H */
 int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** device_ptr, size_t* bytes);/* borrowed     */
 int sgi_synchronize(sgi_ctx* ctx);
+
+/* page-locked host memory for callers that want sgi_set_mesh / sgi_read to be true async DMA
+ * (the reference keeps its Mesh arrays in malloc'd memory and lets the GL driver stage them) */
+int sgi_alloc_host(void** host_ptr, size_t bytes);
+int sgi_free_host(void* host_ptr);
 
 /* instrumentation */
 int sgi_enable_timing(sgi_ctx* ctx, int32_t on);                 /* CUDA events around every pass            */

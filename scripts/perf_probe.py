@@ -1,0 +1,38 @@
+"""Ad-hoc per-pass timing probe (developer tool, not the bench): golden scenes at bench-like sizes."""
+import sys, os, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from globalillumination_b200 import capi
+from tests import util
+
+def probe(name, W, H, S, tech, iters=20, **kw):
+    sc = util.scene(name)
+    ctx = capi.Context(0)
+    fm = util.frame(sc, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+    ctx.set_params(capi.default_params(tech, depth_threshold=float(sc["depth_threshold"]), **kw))
+    for _ in range(3):
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    ctx.synchronize()
+    ctx.enable_timing(True); ctx.reset_timing()
+    t0 = time.time()
+    for _ in range(iters):
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    ctx.synchronize()
+    wall = (time.time() - t0) / iters * 1e3
+    out = {p: ctx.pass_time_ms(p)[0] / max(1, ctx.pass_time_ms(p)[1]) for p in ("shadow_map", "gbuffer", "visibility", "vis_kernel")}
+    print(f"{name} {W}x{H} S={S} {tech} {kw}: wall {wall:.3f} ms/frame | " + " ".join(f"{k}={v:.3f}ms" for k, v in out.items()), flush=True)
+    ctx.close()
+
+if __name__ == "__main__":
+    probe("teapot", 1280, 720, 1024, "hard")
+    probe("teapot", 1920, 1080, 2048, "pcf")
+    probe("teapot", 1920, 1080, 2048, "pcss")
+    probe("teapot", 1920, 1080, 2048, "pcss", kernel_size=7)
+    probe("dragon", 1920, 1080, 2048, "pcss")
+    probe("dragon", 3840, 2160, 4096, "rbsm_noncons")
+    probe("dragon", 3840, 2160, 4096, "rbsm_cons")
+    probe("dragon", 3840, 2160, 4096, "hard")
+    probe("teapot", 7680, 4320, 8192, "hard", iters=5)
