@@ -11,10 +11,11 @@
 //   cub scan     exclusive sum of the per-tile counts
 //   k_bin<1>     same walk, writes record ids into the per-tile lists
 //   k_tile<MODE> 1 CTA / tile: the tile lives in shared memory (u32 depth, u64 depth|prim key or i32 count);
-//                triangles are expanded into bbox "candidates" that are spread evenly over the 256 threads
-//                (block prefix sum + binary search), so a floor triangle covering the tile and a 2-pixel
-//                triangle cost the same per candidate; shared-memory atomics resolve visibility; the tile
-//                is written to HBM exactly once, coalesced (the clear is fused: no separate memset pass).
+//                warps pull triangles off the tile's list, reject 8x4-pixel blocks of the bounding box 32 at
+//                a time (one block per lane, conservative corner test) and rasterise the surviving blocks
+//                with one lane per pixel (exact int64 edge functions, top-left rule); shared-memory atomics
+//                resolve visibility; the tile is written to HBM exactly once, coalesced (the clear is fused:
+//                there is no separate memset pass).
 //
 // HBM traffic per pass = geometry once + every output texel once; depth never bounces
 // through global atomics.  Numerics follow DESIGN.md §3 to the bit (-fmad=false).
@@ -276,14 +277,6 @@ struct TileArgs {
 
 #define ONE_BITS 0x3F800000u
 
-struct TriSmem {
-  int X0[SGI_TILE_THREADS], Y0[SGI_TILE_THREADS], X1[SGI_TILE_THREADS], Y1[SGI_TILE_THREADS], X2[SGI_TILE_THREADS], Y2[SGI_TILE_THREADS];
-  float z0[SGI_TILE_THREADS], dz1[SGI_TILE_THREADS], dz2[SGI_TILE_THREADS], ia[SGI_TILE_THREADS], zoff[SGI_TILE_THREADS];
-  int meta[SGI_TILE_THREADS];      // prim_front
-  int box[SGI_TILE_THREADS];       // lx0 | ly0<<8 | w<<16 (tile-local bbox origin and width)
-  int prefix[SGI_TILE_THREADS + 1];
-};
-
 __device__ __forceinline__ bool edge_in(long long e, int dx, int dy) {
   return e > 0 || (e == 0 && (dy < 0 || (dy == 0 && dx < 0)));
 }
@@ -312,142 +305,206 @@ __device__ __forceinline__ float frag_z(float z0, float dz1, float dz2, float ia
   return z;
 }
 
+// The tile payload in shared memory uses a row pitch of 72 words, so that the 8x4-pixel blocks the warps
+// work on (4 rows 8 banks apart) and full rows (flush) are both free of bank conflicts.
+#define SGI_PITCH (SGI_TILE + 8)
+#define SGI_BLK_W 8
+#define SGI_BLK_H 4
+
+// largest value of edge (a -> b) over the pixel centres of the 8x4 block whose first pixel is (px,py)
+__device__ __forceinline__ long long edge_block_max(int Xa, int Ya, int Xb, int Yb, int px, int py) {
+  int dx = Xb - Xa, dy = Yb - Ya;
+  int sx = (dy < 0) ? px + SGI_BLK_W - 1 : px;      // coefficient of x is -dy
+  int sy = (dx > 0) ? py + SGI_BLK_H - 1 : py;      // coefficient of y is  dx
+  int PX = sx * SGI_SUBPIX + SGI_SUBPIX / 2, PY = sy * SGI_SUBPIX + SGI_SUBPIX / 2;
+  return (long long)dx * (long long)(PY - Ya) - (long long)dy * (long long)(PX - Xa);
+}
+
+// Large triangles of the current chunk, parked in shared memory for the warp-cooperative phase.
+struct TriQueue {
+  int X0[SGI_TILE_THREADS], Y0[SGI_TILE_THREADS], X1[SGI_TILE_THREADS], Y1[SGI_TILE_THREADS], X2[SGI_TILE_THREADS], Y2[SGI_TILE_THREADS];
+  float z0[SGI_TILE_THREADS], dz1[SGI_TILE_THREADS], dz2[SGI_TILE_THREADS], ia[SGI_TILE_THREADS], zoff[SGI_TILE_THREADS];
+  int meta[SGI_TILE_THREADS];
+  int box[SGI_TILE_THREADS];       // lx0 | ly0<<8 | lx1<<16 | ly1<<24 (tile-local inclusive bbox)
+};
+#define SGI_SMALL_TRI 16           // bbox candidates up to which one thread rasterises the triangle alone
+
+template <int MODE>
+struct TileSink {                  // where fragments go: the tile payload in shared memory
+  unsigned int* zt; unsigned long long* kt; int* ct; const float* sd; int depth_func;
+  __device__ __forceinline__ void fragment(int lx, int ly, float z, int meta) const {
+    const int p = ly * SGI_PITCH + lx;
+    if (MODE == SGI_MODE_DEPTH) {
+      const unsigned int zb = __float_as_uint(z);
+      if (zb < zt[p]) atomicMin(&zt[p], zb);
+    } else if (MODE == SGI_MODE_GBUFFER) {
+      if (z < 1.0f) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)(meta >> 1);
+        if (key < kt[p]) atomicMin(&kt[p], key);
+      }
+    } else {
+      const float d = sd[p];
+      const bool pass = (depth_func == SGI_DEPTH_LESS) ? (z < d) : (z <= d);
+      if (pass) atomicAdd(&ct[p], (meta & 1) ? 1 : -1);
+    }
+  }
+};
+
+// One CTA per 64x64 tile.  The tile's triangle list is consumed in chunks of 256: every thread fetches one
+// record (all loads of a chunk in flight together); triangles whose bounding box holds <= 16 pixel centres are
+// rasterised by that thread on the spot, the others are parked in shared memory and then rasterised
+// warp-cooperatively: the bounding box is walked in 8x4 blocks, 32 blocks conservatively tested at once (one
+// per lane), surviving blocks rasterised one per trip with one lane per pixel.
 template <int MODE>
 __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: tile payload | (SV: scene depth) | TriSmem
   unsigned int* zt = reinterpret_cast<unsigned int*>(smem_raw);
   unsigned long long* kt = reinterpret_cast<unsigned long long*>(smem_raw);
   int* ct = reinterpret_cast<int*>(smem_raw);
-  constexpr int NPIX = SGI_TILE * SGI_TILE;
-  constexpr size_t PAYLOAD = (MODE == SGI_MODE_GBUFFER) ? NPIX * 8 : NPIX * 4;
+  constexpr int NCELL = SGI_TILE * SGI_PITCH;
+  constexpr size_t PAYLOAD = (MODE == SGI_MODE_GBUFFER) ? (size_t)NCELL * 8 : (size_t)NCELL * 4;
+  constexpr size_t SDBYTES = (MODE == SGI_MODE_SVCOUNT) ? (size_t)NCELL * 4 : 0;
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
-  TriSmem& ts = *reinterpret_cast<TriSmem*>(smem_raw + PAYLOAD + (MODE == SGI_MODE_SVCOUNT ? NPIX * 4 : 0));
+  TriQueue& tq = *reinterpret_cast<TriQueue*>(smem_raw + PAYLOAD + SDBYTES);
+  __shared__ int next_item, q_count;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int tx = a.tx0 + blockIdx.x, ty = a.ty0 + blockIdx.y;
   const int tile = ty * a.tiles_x + tx;
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
-  for (int p = tid; p < NPIX; p += SGI_TILE_THREADS) {
+  for (int p = tid; p < NCELL; p += SGI_TILE_THREADS) {
     if (MODE == SGI_MODE_DEPTH) zt[p] = ONE_BITS;
     else if (MODE == SGI_MODE_GBUFFER) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
     else {
       ct[p] = 0;
-      int x = ox + (p & (SGI_TILE - 1)), y = oy + (p >> SGI_TILE_LOG2);
-      sd[p] = (x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
+      int lx = p % SGI_PITCH, ly = p / SGI_PITCH;
+      int x = ox + lx, y = oy + ly;
+      sd[p] = (lx < SGI_TILE && x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
     }
   }
   long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
   if (end > a.pair_cap) end = a.pair_cap;
   if (beg > end) beg = end;
-  __syncthreads();
-
-  typedef cub::BlockScan<int, SGI_TILE_THREADS> BlockScan;
-  __shared__ typename BlockScan::TempStorage scan_tmp;
+  const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
 
   for (long long base = beg; base < end; base += SGI_TILE_THREADS) {
-    int ncand = 0;
+    if (tid == 0) { next_item = 0; q_count = 0; }
+    __syncthreads();                                           // payload initialised / previous chunk drained
     if (base + tid < end) {
-      const SgiRec* rp = &a.rec[a.pairs[base + tid]];
-      uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-      uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-      uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rp) + 2);
-      uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rp) + 3);
-      ts.X0[tid] = (int)q0.x; ts.Y0[tid] = (int)q0.y; ts.X1[tid] = (int)q0.z; ts.Y1[tid] = (int)q0.w;
-      ts.X2[tid] = (int)q1.x; ts.Y2[tid] = (int)q1.y;
-      ts.z0[tid] = __uint_as_float(q1.z); ts.dz1[tid] = __uint_as_float(q1.w);
-      ts.dz2[tid] = __uint_as_float(q2.x); ts.ia[tid] = __uint_as_float(q2.y); ts.zoff[tid] = __uint_as_float(q2.z);
-      ts.meta[tid] = (int)q2.w;
-      int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
-      int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
-      int lx0 = max(px0, ox) - ox, ly0 = max(py0, oy) - oy;
-      int lx1 = min(px1, ox + SGI_TILE - 1) - ox, ly1 = min(py1, oy + SGI_TILE - 1) - oy;
-      int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
-      if (w > 0 && h > 0) ncand = w * h; else w = 1;
-      ts.box[tid] = lx0 | (ly0 << 8) | (w << 16);
-    }
-    int excl, total;
-    BlockScan(scan_tmp).ExclusiveSum(ncand, excl, total);
-    ts.prefix[tid] = excl;
-    if (tid == 0) ts.prefix[SGI_TILE_THREADS] = total;
-    __syncthreads();
-
-    for (int c = tid; c < total; c += SGI_TILE_THREADS) {
-      // upper_bound over prefix[0..256): last k with prefix[k] <= c
-      int lo = 0, hi = SGI_TILE_THREADS;
-#pragma unroll
-      for (int s = 0; s < 8; s++) {
-        int mid = (lo + hi) >> 1;
-        if (ts.prefix[mid] <= c) lo = mid; else hi = mid;
-      }
-      int k = lo;
-      int local = c - ts.prefix[k];
-      int box = ts.box[k];
-      int w = box >> 16;
-      int jj = local / w, ii = local - jj * w;
-      int lx = (box & 0xFF) + ii, ly = ((box >> 8) & 0xFF) + jj;
-      long long E0, E1, E2;
-      if (!cover(ts.X0[k], ts.Y0[k], ts.X1[k], ts.Y1[k], ts.X2[k], ts.Y2[k], ox + lx, oy + ly, E0, E1, E2)) continue;
-      float z = frag_z(ts.z0[k], ts.dz1[k], ts.dz2[k], ts.ia[k], ts.zoff[k], E1, E2);
-      int p = (ly << SGI_TILE_LOG2) + lx;
-      if (MODE == SGI_MODE_DEPTH) {
-        atomicMin(&zt[p], __float_as_uint(z));
-      } else if (MODE == SGI_MODE_GBUFFER) {
-        if (z < 1.0f) {
-          unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)(ts.meta[k] >> 1);
-          atomicMin(&kt[p], key);
+      const SgiRec* rp = &a.rec[__ldg(&a.pairs[base + tid])];
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+      const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rp) + 2);
+      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rp) + 3);
+      const int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
+      const int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
+      const int lx0 = max(px0, ox) - ox, ly0 = max(py0, oy) - oy;
+      const int lx1 = min(px1, ox + SGI_TILE - 1) - ox, ly1 = min(py1, oy + SGI_TILE - 1) - oy;
+      const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
+      if (w > 0 && h > 0) {
+        if (w * h <= SGI_SMALL_TRI) {
+          const int X0 = (int)q0.x, Y0 = (int)q0.y, X1 = (int)q0.z, Y1 = (int)q0.w, X2 = (int)q1.x, Y2 = (int)q1.y;
+          const float z0 = __uint_as_float(q1.z), dz1 = __uint_as_float(q1.w), dz2 = __uint_as_float(q2.x);
+          const float ia = __uint_as_float(q2.y), zoff = __uint_as_float(q2.z);
+          for (int ly = ly0; ly <= ly1; ly++)
+            for (int lx = lx0; lx <= lx1; lx++) {
+              long long E0, E1, E2;
+              if (!cover(X0, Y0, X1, Y1, X2, Y2, ox + lx, oy + ly, E0, E1, E2)) continue;
+              sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), (int)q2.w);
+            }
+        } else {
+          const int k = atomicAdd(&q_count, 1);
+          tq.X0[k] = (int)q0.x; tq.Y0[k] = (int)q0.y; tq.X1[k] = (int)q0.z; tq.Y1[k] = (int)q0.w; tq.X2[k] = (int)q1.x; tq.Y2[k] = (int)q1.y;
+          tq.z0[k] = __uint_as_float(q1.z); tq.dz1[k] = __uint_as_float(q1.w); tq.dz2[k] = __uint_as_float(q2.x);
+          tq.ia[k] = __uint_as_float(q2.y); tq.zoff[k] = __uint_as_float(q2.z);
+          tq.meta[k] = (int)q2.w;
+          tq.box[k] = lx0 | (ly0 << 8) | (lx1 << 16) | (ly1 << 24);
         }
-      } else {
-        float d = sd[p];
-        bool pass = (a.depth_func == SGI_DEPTH_LESS) ? (z < d) : (z <= d);
-        if (pass) atomicAdd(&ct[p], (ts.meta[k] & 1) ? 1 : -1);
       }
     }
     __syncthreads();
+    const int nq = q_count;
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&next_item, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= nq) break;
+      const int X0 = tq.X0[item], Y0 = tq.Y0[item], X1 = tq.X1[item], Y1 = tq.Y1[item], X2 = tq.X2[item], Y2 = tq.Y2[item];
+      const float z0 = tq.z0[item], dz1 = tq.dz1[item], dz2 = tq.dz2[item], ia = tq.ia[item], zoff = tq.zoff[item];
+      const int meta = tq.meta[item], box = tq.box[item];
+      const int lx0 = box & 0xFF, ly0 = (box >> 8) & 0xFF, lx1 = (box >> 16) & 0xFF, ly1 = (box >> 24) & 0xFF;
+      const int bx0 = lx0 / SGI_BLK_W, bx1 = lx1 / SGI_BLK_W, by0 = ly0 / SGI_BLK_H, by1 = ly1 / SGI_BLK_H;
+      const int nbx = bx1 - bx0 + 1, nb = nbx * (by1 - by0 + 1);
+      const int sub_x = lane & (SGI_BLK_W - 1), sub_y = lane >> 3;
+      for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        const int bx = bx0 + b % nbx, by = by0 + b / nbx;
+        bool keep = b < nb;
+        if (keep && nb > 1) {
+          const int gx = ox + bx * SGI_BLK_W, gy = oy + by * SGI_BLK_H;
+          keep = edge_block_max(X1, Y1, X2, Y2, gx, gy) >= 0 && edge_block_max(X2, Y2, X0, Y0, gx, gy) >= 0 &&
+                 edge_block_max(X0, Y0, X1, Y1, gx, gy) >= 0;
+        }
+        unsigned int mask = __ballot_sync(0xffffffffu, keep);
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int lx = __shfl_sync(0xffffffffu, bx, k) * SGI_BLK_W + sub_x;
+          const int ly = __shfl_sync(0xffffffffu, by, k) * SGI_BLK_H + sub_y;
+          if (lx < lx0 || lx > lx1 || ly < ly0 || ly > ly1) continue;
+          long long E0, E1, E2;
+          if (!cover(X0, Y0, X1, Y1, X2, Y2, ox + lx, oy + ly, E0, E1, E2)) continue;
+          sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+        }
+      }
+    }
+    __syncthreads();                                           // every warp is done with this chunk's queue
   }
+  __syncthreads();
 
   // ---- write the tile to HBM exactly once ------------------------------------------------------------------
-  for (int p = tid; p < NPIX; p += SGI_TILE_THREADS) {
-    int lx = p & (SGI_TILE - 1), ly = p >> SGI_TILE_LOG2;
-    int x = ox + lx, y = oy + ly;
+  for (int q = tid; q < SGI_TILE * SGI_TILE; q += SGI_TILE_THREADS) {
+    const int lx = q & (SGI_TILE - 1), ly = q >> SGI_TILE_LOG2;
+    const int p = ly * SGI_PITCH + lx;
+    const int x = ox + lx, y = oy + ly;
     if (x < a.rx0 || x >= a.rx1 || y < a.ry0 || y >= a.ry1) continue;
-    size_t o = (size_t)y * a.W + x;
+    const size_t o = (size_t)y * a.W + x;
     if (MODE == SGI_MODE_DEPTH) {
       a.depth[o] = __uint_as_float(zt[p]);
     } else if (MODE == SGI_MODE_SVCOUNT) {
-      int c = ct[p];
+      const int c = ct[p];
       a.count[o] = c;
       a.stencil[o] = (uint8_t)((unsigned int)c & 255u);
     } else {
-      unsigned long long key = kt[p];
-      unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
+      const unsigned long long key = kt[p];
+      const unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
       if (lo32 == 0xFFFFFFFFu) {
         a.depth[o] = 1.0f;
         a.pos4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
         a.nrm4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
         continue;
       }
-      int prim = (int)lo32, t = prim >> 3, sub = prim & 7;
-      int slot = (sub == 0) ? t : a.ovf_base[t] + sub - 1;
-      SgiRec r = a.rec[slot];
-      SgiRecAttr q = a.attr[slot];
+      const int prim = (int)lo32, t = prim >> 3, sub = prim & 7;
+      const int slot = (sub == 0) ? t : a.ovf_base[t] + sub - 1;
+      const SgiRec r = a.rec[slot];
+      const SgiRecAttr at = a.attr[slot];
       long long E0, E1, E2;
       cover(r.X0, r.Y0, r.X1, r.Y1, r.X2, r.Y2, x, y, E0, E1, E2);
-      int i0 = a.idx[3 * (size_t)t], i1 = a.idx[3 * (size_t)t + 1], i2 = a.idx[3 * (size_t)t + 2];
-      float q0 = ((float)E0 * r.ia) * q.iw[0];
-      float q1 = ((float)E1 * r.ia) * q.iw[1];
-      float q2 = ((float)E2 * r.ia) * q.iw[2];
-      float qs = (q0 + q1) + q2;
+      const int i0 = a.idx[3 * (size_t)t], i1 = a.idx[3 * (size_t)t + 1], i2 = a.idx[3 * (size_t)t + 2];
+      const float q0 = ((float)E0 * r.ia) * at.iw[0];
+      const float q1 = ((float)E1 * r.ia) * at.iw[1];
+      const float q2 = ((float)E2 * r.ia) * at.iw[2];
+      const float qs = (q0 + q1) + q2;
       float outv[6];
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         const float* src = (c < 3) ? a.xyz : a.nrm;
-        int cc = (c < 3) ? c : c - 3;
-        float s0 = src[3 * (size_t)i0 + cc], s1 = src[3 * (size_t)i1 + cc], s2 = src[3 * (size_t)i2 + cc];
-        float A0 = (q.bary[0] * s0 + q.bary[1] * s1) + q.bary[2] * s2;
-        float A1 = (q.bary[3] * s0 + q.bary[4] * s1) + q.bary[5] * s2;
-        float A2 = (q.bary[6] * s0 + q.bary[7] * s1) + q.bary[8] * s2;
+        const int cc = (c < 3) ? c : c - 3;
+        const float s0 = src[3 * (size_t)i0 + cc], s1 = src[3 * (size_t)i1 + cc], s2 = src[3 * (size_t)i2 + cc];
+        const float A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
+        const float A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
+        const float A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
         outv[c] = ((q0 * A0 + q1 * A1) + q2 * A2) / qs;
       }
       a.depth[o] = __uint_as_float((unsigned int)(key >> 32));
@@ -459,8 +516,8 @@ __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
 
 template <int MODE>
 constexpr size_t tile_smem_bytes() {
-  return (size_t)SGI_TILE * SGI_TILE * (MODE == SGI_MODE_GBUFFER ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? SGI_TILE * SGI_TILE * 4 : 0) +
-         sizeof(TriSmem);
+  return (size_t)SGI_TILE * SGI_PITCH * (MODE == SGI_MODE_GBUFFER ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? (size_t)SGI_TILE * SGI_PITCH * 4 : 0) +
+         sizeof(TriQueue);
 }
 
 // ---- shadow-volume extrusion: ShadowVolumes/src/ShadowVolume.cpp:116-195 -----------------------------------------

@@ -26,7 +26,10 @@ def probe(name, W, H, S, tech, iters=20, **kw):
     print(f"{name} {W}x{H} S={S} {tech} {kw}: wall {wall:.3f} ms/frame | " + " ".join(f"{k}={v:.3f}ms" for k, v in out.items()), flush=True)
     ctx.close()
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1:
+    name, W, H, S, tech = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+    probe(name, W, H, S, tech, iters=int(sys.argv[6]) if len(sys.argv) > 6 else 5)
+elif __name__ == "__main__":
     probe("teapot", 1280, 720, 1024, "hard")
     probe("teapot", 1920, 1080, 2048, "pcf")
     probe("teapot", 1920, 1080, 2048, "pcss")
