@@ -19,6 +19,7 @@
 //
 // HBM traffic per pass = geometry once + every output texel once; depth never bounces
 // through global atomics.  Numerics follow DESIGN.md §3 to the bit (-fmad=false).
+#include <cstdlib>
 #include <cub/cub.cuh>
 #include "sgi_internal.cuh"
 
@@ -321,11 +322,12 @@ __device__ __forceinline__ long long edge_block_max(int Xa, int Ya, int Xb, int 
 }
 
 // Large triangles of the current chunk, parked in shared memory for the warp-cooperative phase.
+template <int NT>
 struct TriQueue {
-  int X0[SGI_TILE_THREADS], Y0[SGI_TILE_THREADS], X1[SGI_TILE_THREADS], Y1[SGI_TILE_THREADS], X2[SGI_TILE_THREADS], Y2[SGI_TILE_THREADS];
-  float z0[SGI_TILE_THREADS], dz1[SGI_TILE_THREADS], dz2[SGI_TILE_THREADS], ia[SGI_TILE_THREADS], zoff[SGI_TILE_THREADS];
-  int meta[SGI_TILE_THREADS];
-  int box[SGI_TILE_THREADS];       // lx0 | ly0<<8 | lx1<<16 | ly1<<24 (tile-local inclusive bbox)
+  int X0[NT], Y0[NT], X1[NT], Y1[NT], X2[NT], Y2[NT];
+  float z0[NT], dz1[NT], dz2[NT], ia[NT], zoff[NT];
+  int meta[NT];
+  int box[NT];                     // lx0 | ly0<<8 | lx1<<16 | ly1<<24 (tile-local inclusive bbox)
 };
 #define SGI_SMALL_TRI 16           // bbox candidates up to which one thread rasterises the triangle alone
 
@@ -355,8 +357,8 @@ struct TileSink {                  // where fragments go: the tile payload in sh
 // rasterised by that thread on the spot, the others are parked in shared memory and then rasterised
 // warp-cooperatively: the bounding box is walked in 8x4 blocks, 32 blocks conservatively tested at once (one
 // per lane), surviving blocks rasterised one per trip with one lane per pixel.
-template <int MODE>
-__global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned int* zt = reinterpret_cast<unsigned int*>(smem_raw);
   unsigned long long* kt = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
   constexpr size_t PAYLOAD = (MODE == SGI_MODE_GBUFFER) ? (size_t)NCELL * 8 : (size_t)NCELL * 4;
   constexpr size_t SDBYTES = (MODE == SGI_MODE_SVCOUNT) ? (size_t)NCELL * 4 : 0;
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
-  TriQueue& tq = *reinterpret_cast<TriQueue*>(smem_raw + PAYLOAD + SDBYTES);
+  TriQueue<NT>& tq = *reinterpret_cast<TriQueue<NT>*>(smem_raw + PAYLOAD + SDBYTES);
   __shared__ int next_item, q_count;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
   const int tile = ty * a.tiles_x + tx;
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
-  for (int p = tid; p < NCELL; p += SGI_TILE_THREADS) {
+  for (int p = tid; p < NCELL; p += NT) {
     if (MODE == SGI_MODE_DEPTH) zt[p] = ONE_BITS;
     else if (MODE == SGI_MODE_GBUFFER) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
     else {
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
   if (beg > end) beg = end;
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
 
-  for (long long base = beg; base < end; base += SGI_TILE_THREADS) {
+  for (long long base = beg; base < end; base += NT) {
     if (tid == 0) { next_item = 0; q_count = 0; }
     __syncthreads();                                           // payload initialised / previous chunk drained
     if (base + tid < end) {
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
   __syncthreads();
 
   // ---- write the tile to HBM exactly once ------------------------------------------------------------------
-  for (int q = tid; q < SGI_TILE * SGI_TILE; q += SGI_TILE_THREADS) {
+  for (int q = tid; q < SGI_TILE * SGI_TILE; q += NT) {
     const int lx = q & (SGI_TILE - 1), ly = q >> SGI_TILE_LOG2;
     const int p = ly * SGI_PITCH + lx;
     const int x = ox + lx, y = oy + ly;
@@ -514,10 +516,10 @@ __global__ void __launch_bounds__(SGI_TILE_THREADS) k_tile(const TileArgs a) {
   }
 }
 
-template <int MODE>
+template <int MODE, int NT>
 constexpr size_t tile_smem_bytes() {
   return (size_t)SGI_TILE * SGI_PITCH * (MODE == SGI_MODE_GBUFFER ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? (size_t)SGI_TILE * SGI_PITCH * 4 : 0) +
-         sizeof(TriQueue);
+         sizeof(TriQueue<NT>);
 }
 
 // ---- shadow-volume extrusion: ShadowVolumes/src/ShadowVolume.cpp:116-195 -----------------------------------------
@@ -596,21 +598,45 @@ int sgi_raster_reserve(sgi_ctx* ctx, int max_tris, int W, int H) {
   return SGI_OK;
 }
 
-template <int MODE>
-static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
+template <int MODE, int NT>
+static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
   static bool configured = false;
-  constexpr size_t smem = tile_smem_bytes<MODE>();
+  constexpr size_t smem = tile_smem_bytes<MODE, NT>();
   if (!configured) {
-    SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : (MODE == SGI_MODE_GBUFFER ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
   int tslot = sgi_timing_begin(ctx, pass);
-  k_tile<MODE><<<grid, SGI_TILE_THREADS, smem, ctx->stream>>>(ta);
+  k_tile<MODE, NT><<<grid, NT, smem, ctx->stream>>>(ta);
   sgi_timing_end(ctx, pass, tslot);
   ctx->launches++;
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;
+}
+
+// CTA size of the tile kernel.  The pass ends when the busiest tile ends, and a tile is worked on by one CTA, so
+// few-tile passes (<= 1200 tiles: up to 1080p / 2048^2) get 32 warps per tile; many-tile passes get 16 so that the
+// per-tile init/flush and barriers stay cheap.  Measured on B200 (profiles/r1_tile_cta_size.txt).  SGI_TILE_THREADS
+// overrides for experiments.
+static int tile_threads(int n_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("SGI_TILE_THREADS");
+    forced = e ? atoi(e) : 0;
+    if (forced != 256 && forced != 512 && forced != 1024) forced = 0;
+  }
+  if (forced) return forced;
+  return n_tiles <= 1200 ? 1024 : 512;
+}
+
+template <int MODE>
+static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
+  switch (tile_threads((int)(grid.x * grid.y))) {
+    case 256: return launch_tile_nt<MODE, 256>(ctx, ta, grid);
+    case 512: return launch_tile_nt<MODE, 512>(ctx, ta, grid);
+    default: return launch_tile_nt<MODE, 1024>(ctx, ta, grid);
+  }
 }
 
 int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
