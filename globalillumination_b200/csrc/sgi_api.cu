@@ -105,8 +105,8 @@ int sgi_destroy(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
-  void* ptrs[] = {ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->d_light_trans, ctx->d_rec, ctx->d_attr, ctx->d_ovf_base, ctx->d_counters,
-                  ctx->d_tile_cnt, ctx->d_tile_off, ctx->d_tile_fill, ctx->d_pairs, ctx->d_scan_tmp};
+  void* ptrs[] = {ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->d_light_trans, ctx->d_rec, ctx->d_attr, ctx->d_ovf_base, ctx->d_big, ctx->d_counters,
+                  ctx->d_tile_off, ctx->d_pairs};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);

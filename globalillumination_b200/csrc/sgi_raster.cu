@@ -7,8 +7,9 @@
 // Pipeline (all on one stream, no host round trip):
 //   k_setup      1 thread / source triangle: transform, clip (near/far + 16x guard band), snap to 1/256 px,
 //                integer edge set-up, depth plane, polygon offset -> 64-byte SgiRec (+ attribute record)
-//   k_bin<0>     1 warp / record: count the 64x64 tiles the triangle really overlaps
-//   cub scan     exclusive sum of the per-tile counts
+//   k_bin<0>     1 thread / record (whole warp for triangles spanning > 4 tiles): count the 64x64 tiles the
+//                triangle really overlaps (exact edge / tile-corner test)
+//   k_scan_tiles exclusive sum of the per-tile counts, one CTA
 //   k_bin<1>     same walk, writes record ids into the per-tile lists
 //   k_tile<MODE> 1 CTA / tile: the tile lives in shared memory (u32 depth, u64 depth|prim key or i32 count);
 //                warps pull triangles off the tile's list, reject 8x4-pixel blocks of the bounding box 32 at
@@ -204,10 +205,12 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
 
 // ---- binning -------------------------------------------------------------------------------------------------
 struct BinArgs {
-  const SgiRec* rec; const int32_t* counters; int T;
+  const SgiRec* rec; const int32_t* counters; int32_t* counters_rw; int T;
   int tiles_x, tiles_y, tx0, ty0, tx1, ty1;     // tile grid and the inclusive tile range of the job rectangle
   int32_t* tile_cnt; const int32_t* tile_off; int32_t* tile_fill; int32_t* pairs; long long pair_cap;
   int32_t* flags;                                // counters[1] = overflow flag
+  volatile int32_t* h_flags;                     // host-mapped: [0] sticky overflow, [1] largest total wanted
+  int32_t* big_list;                             // records spanning > SGI_BIG_TILES tiles: not binned, every tile CTA tests them (counters[3] = count)
 };
 
 // conservative triangle / tile overlap: for each edge evaluate at the tile corner that maximises it
@@ -228,47 +231,88 @@ __device__ __forceinline__ bool tile_overlaps(const SgiRec& r, int tx, int ty, i
   return true;
 }
 
+// One thread per record; triangles overlapping more than 4 tiles are handed to the whole warp (ballot loop), so
+// the two floor triangles that cover a thousand tiles cost 32 lanes x 32 trips instead of one lane x 1024.
+#define SGI_BIG_TILES 256
+
 template <int FILL>
 __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
-  int lane = threadIdx.x & 31;
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int nwarps = (gridDim.x * blockDim.x) >> 5;
-  int nrec = a.T + a.counters[0];
-  for (int slot = warp; slot < nrec; slot += nwarps) {
-    SgiRec r = a.rec[slot];
-    if (r.prim_front < 0) continue;
-    int bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0), bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1);
-    int by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
-    if (bx0 > bx1 || by0 > by1) continue;
-    int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
-    bool single = (nt == 1);
-    for (int k = lane; k < nt; k += 32) {
-      int ty = by0 + k / bw, tx = bx0 + k % bw;
-      if (!single && !tile_overlaps(r, tx, ty, W, H)) continue;
-      int tile = ty * a.tiles_x + tx;
+  const int lane = threadIdx.x & 31;
+  const int nrec = a.T + a.counters[0];
+  for (int base = blockIdx.x * blockDim.x; base < nrec; base += gridDim.x * blockDim.x) {
+    const int slot = base + threadIdx.x;
+    SgiRec r;
+    r.prim_front = -1;
+    if (slot < nrec) r = a.rec[slot];
+    int bx0 = 0, by0 = 0, bw = 0, nt = 0;
+    if (r.prim_front >= 0) {
+      bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0); by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
+      const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
+      if (bx0 <= bx1 && by0 <= by1) { bw = bx1 - bx0 + 1; nt = bw * (by1 - by0 + 1); }
+      if (nt > SGI_BIG_TILES) {        // e.g. the floor: listing it in thousands of tiles costs more than letting each tile test it
+        if (!FILL) a.big_list[atomicAdd(&a.counters_rw[3], 1)] = slot;
+        nt = 0;
+      }
+    }
+    auto emit = [&](int tile, int s) {
       if (!FILL) {
         atomicAdd(&a.tile_cnt[tile], 1);
       } else {
         long long pos = (long long)a.tile_off[tile] + atomicAdd(&a.tile_fill[tile], 1);
-        if (pos < a.pair_cap) a.pairs[pos] = slot;
-        else a.flags[1] = 1;
+        if (pos < a.pair_cap) a.pairs[pos] = s;
+        else { a.flags[1] = 1; a.h_flags[0] = 1; }
+      }
+    };
+    if (nt > 0 && nt <= 4) {
+      for (int k = 0; k < nt; k++) {
+        const int ty = by0 + k / bw, tx = bx0 + k % bw;
+        if (nt > 1 && !tile_overlaps(r, tx, ty, W, H)) continue;
+        emit(ty * a.tiles_x + tx, slot);
+      }
+    }
+    unsigned int big = __ballot_sync(0xffffffffu, nt > 4);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      SgiRec q;
+      q.X0 = __shfl_sync(0xffffffffu, r.X0, src); q.Y0 = __shfl_sync(0xffffffffu, r.Y0, src);
+      q.X1 = __shfl_sync(0xffffffffu, r.X1, src); q.Y1 = __shfl_sync(0xffffffffu, r.Y1, src);
+      q.X2 = __shfl_sync(0xffffffffu, r.X2, src); q.Y2 = __shfl_sync(0xffffffffu, r.Y2, src);
+      const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sby0 = __shfl_sync(0xffffffffu, by0, src);
+      const int sbw = __shfl_sync(0xffffffffu, bw, src), snt = __shfl_sync(0xffffffffu, nt, src);
+      const int sslot = __shfl_sync(0xffffffffu, slot, src);
+      for (int k = lane; k < snt; k += 32) {
+        const int ty = sby0 + k / sbw, tx = sbx0 + k % sbw;
+        if (!tile_overlaps(q, tx, ty, W, H)) continue;
+        emit(ty * a.tiles_x + tx, sslot);
       }
     }
   }
 }
 
-// h_flags is mapped pinned host memory: [0] sticky "a list overflowed", [1] largest list size ever wanted
-__global__ void k_publish_total(const int32_t* tile_off, int n_tiles, int32_t* counters, volatile int32_t* h_flags) {
-  int total = tile_off[n_tiles];
-  counters[2] = total;
-  if (total > h_flags[1]) h_flags[1] = total;
+// exclusive scan of the per-tile counts (n <= a few 10^4) in one CTA; publishes the total to the host-mapped flag word
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
+                                                     int32_t* counters, volatile int32_t* h_flags) {
+  typedef cub::BlockScan<int, 1024> BlockScan;
+  __shared__ typename BlockScan::TempStorage tmp;
+  const int per = (n + 1023) / 1024;
+  const int beg = threadIdx.x * per, end = min(beg + per, n);
+  int sum = 0;
+  for (int i = beg; i < end; i++) sum += cnt[i];
+  int excl, total;
+  BlockScan(tmp).ExclusiveSum(sum, excl, total);
+  for (int i = beg; i < end; i++) { off[i] = excl; excl += cnt[i]; }
+  if (threadIdx.x == 0) {
+    counters[2] = total;
+    if (total > h_flags[1]) h_flags[1] = total;      // largest list size ever wanted (host grows d_pairs from it)
+  }
 }
-__global__ void k_publish_flag(const int32_t* counters, volatile int32_t* h_flags) { if (counters[1]) h_flags[0] = 1; }
 
 // ---- per-tile rasterisation ----------------------------------------------------------------------------------
 struct TileArgs {
   const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
   const int32_t* tile_off; const int32_t* pairs; long long pair_cap;
+  const int32_t* big_list; const int32_t* counters;      // counters[3] = number of un-binned big triangles
   int tiles_x, tx0, ty0;
   int W, H, rx0, ry0, rx1, ry1;
   const float* xyz; const float* nrm; const int32_t* idx;
@@ -328,6 +372,7 @@ struct TriQueue {
   float z0[NT], dz1[NT], dz2[NT], ia[NT], zoff[NT];
   int meta[NT];
   int box[NT];                     // lx0 | ly0<<8 | lx1<<16 | ly1<<24 (tile-local inclusive bbox)
+  int group[4 * NT];               // work items: queue index << 3 | group of 32 blocks (a 64x64 bbox has 128 blocks)
 };
 #define SGI_SMALL_TRI 16           // bbox candidates up to which one thread rasterises the triangle alone
 
@@ -368,7 +413,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   constexpr size_t SDBYTES = (MODE == SGI_MODE_SVCOUNT) ? (size_t)NCELL * 4 : 0;
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
   TriQueue<NT>& tq = *reinterpret_cast<TriQueue<NT>*>(smem_raw + PAYLOAD + SDBYTES);
-  __shared__ int next_item, q_count;
+  __shared__ int next_item, q_count, g_count;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int tx = a.tx0 + blockIdx.x, ty = a.ty0 + blockIdx.y;
@@ -388,13 +433,16 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
   if (end > a.pair_cap) end = a.pair_cap;
   if (beg > end) beg = end;
+  const int nlisted = (int)(end - beg), nbig = a.counters[3];
+  const int nitems = nlisted + nbig;                           // this tile's list, then the un-binned big triangles
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
 
-  for (long long base = beg; base < end; base += NT) {
-    if (tid == 0) { next_item = 0; q_count = 0; }
+  for (int base = 0; base < nitems; base += NT) {
+    if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; }
     __syncthreads();                                           // payload initialised / previous chunk drained
-    if (base + tid < end) {
-      const SgiRec* rp = &a.rec[__ldg(&a.pairs[base + tid])];
+    if (base + tid < nitems) {
+      const int it = base + tid;
+      const SgiRec* rp = &a.rec[it < nlisted ? __ldg(&a.pairs[beg + it]) : __ldg(&a.big_list[it - nlisted])];
       const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
       const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
       const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rp) + 2);
@@ -405,8 +453,8 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       const int lx1 = min(px1, ox + SGI_TILE - 1) - ox, ly1 = min(py1, oy + SGI_TILE - 1) - oy;
       const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
       if (w > 0 && h > 0) {
+        const int X0 = (int)q0.x, Y0 = (int)q0.y, X1 = (int)q0.z, Y1 = (int)q0.w, X2 = (int)q1.x, Y2 = (int)q1.y;
         if (w * h <= SGI_SMALL_TRI) {
-          const int X0 = (int)q0.x, Y0 = (int)q0.y, X1 = (int)q0.z, Y1 = (int)q0.w, X2 = (int)q1.x, Y2 = (int)q1.y;
           const float z0 = __uint_as_float(q1.z), dz1 = __uint_as_float(q1.w), dz2 = __uint_as_float(q2.x);
           const float ia = __uint_as_float(q2.y), zoff = __uint_as_float(q2.z);
           for (int ly = ly0; ly <= ly1; ly++)
@@ -417,48 +465,55 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
             }
         } else {
           const int k = atomicAdd(&q_count, 1);
-          tq.X0[k] = (int)q0.x; tq.Y0[k] = (int)q0.y; tq.X1[k] = (int)q0.z; tq.Y1[k] = (int)q0.w; tq.X2[k] = (int)q1.x; tq.Y2[k] = (int)q1.y;
+          tq.X0[k] = X0; tq.Y0[k] = Y0; tq.X1[k] = X1; tq.Y1[k] = Y1; tq.X2[k] = X2; tq.Y2[k] = Y2;
           tq.z0[k] = __uint_as_float(q1.z); tq.dz1[k] = __uint_as_float(q1.w); tq.dz2[k] = __uint_as_float(q2.x);
           tq.ia[k] = __uint_as_float(q2.y); tq.zoff[k] = __uint_as_float(q2.z);
           tq.meta[k] = (int)q2.w;
           tq.box[k] = lx0 | (ly0 << 8) | (lx1 << 16) | (ly1 << 24);
+          // one work item per group of 32 blocks, so a triangle covering the tile is shared by 4 warps
+          const int nb = (lx1 / SGI_BLK_W - lx0 / SGI_BLK_W + 1) * (ly1 / SGI_BLK_H - ly0 / SGI_BLK_H + 1);
+          const int ng = (nb + 31) >> 5;
+          const int g0 = atomicAdd(&g_count, ng);
+          for (int g = 0; g < ng; g++) tq.group[g0 + g] = (k << 3) | g;
         }
       }
     }
     __syncthreads();
-    const int nq = q_count;
+    const int ngroups = g_count;
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&next_item, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= nq) break;
-      const int X0 = tq.X0[item], Y0 = tq.Y0[item], X1 = tq.X1[item], Y1 = tq.Y1[item], X2 = tq.X2[item], Y2 = tq.Y2[item];
-      const float z0 = tq.z0[item], dz1 = tq.dz1[item], dz2 = tq.dz2[item], ia = tq.ia[item], zoff = tq.zoff[item];
-      const int meta = tq.meta[item], box = tq.box[item];
+      if (item >= ngroups) break;
+      const int grp = tq.group[item];
+      const int qi = grp >> 3, b0 = (grp & 7) << 5;
+      const int X0 = tq.X0[qi], Y0 = tq.Y0[qi], X1 = tq.X1[qi], Y1 = tq.Y1[qi], X2 = tq.X2[qi], Y2 = tq.Y2[qi];
+      const int box = tq.box[qi];
       const int lx0 = box & 0xFF, ly0 = (box >> 8) & 0xFF, lx1 = (box >> 16) & 0xFF, ly1 = (box >> 24) & 0xFF;
       const int bx0 = lx0 / SGI_BLK_W, bx1 = lx1 / SGI_BLK_W, by0 = ly0 / SGI_BLK_H, by1 = ly1 / SGI_BLK_H;
       const int nbx = bx1 - bx0 + 1, nb = nbx * (by1 - by0 + 1);
       const int sub_x = lane & (SGI_BLK_W - 1), sub_y = lane >> 3;
-      for (int b0 = 0; b0 < nb; b0 += 32) {
-        const int b = b0 + lane;
-        const int bx = bx0 + b % nbx, by = by0 + b / nbx;
-        bool keep = b < nb;
-        if (keep && nb > 1) {
-          const int gx = ox + bx * SGI_BLK_W, gy = oy + by * SGI_BLK_H;
-          keep = edge_block_max(X1, Y1, X2, Y2, gx, gy) >= 0 && edge_block_max(X2, Y2, X0, Y0, gx, gy) >= 0 &&
-                 edge_block_max(X0, Y0, X1, Y1, gx, gy) >= 0;
-        }
-        unsigned int mask = __ballot_sync(0xffffffffu, keep);
-        while (mask) {
-          const int k = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int lx = __shfl_sync(0xffffffffu, bx, k) * SGI_BLK_W + sub_x;
-          const int ly = __shfl_sync(0xffffffffu, by, k) * SGI_BLK_H + sub_y;
-          if (lx < lx0 || lx > lx1 || ly < ly0 || ly > ly1) continue;
-          long long E0, E1, E2;
-          if (!cover(X0, Y0, X1, Y1, X2, Y2, ox + lx, oy + ly, E0, E1, E2)) continue;
-          sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
-        }
+      const int b = b0 + lane;
+      const int bx = bx0 + b % nbx, by = by0 + b / nbx;
+      bool keep = b < nb;
+      if (keep && nb > 1) {
+        const int gx = ox + bx * SGI_BLK_W, gy = oy + by * SGI_BLK_H;
+        keep = edge_block_max(X1, Y1, X2, Y2, gx, gy) >= 0 && edge_block_max(X2, Y2, X0, Y0, gx, gy) >= 0 &&
+               edge_block_max(X0, Y0, X1, Y1, gx, gy) >= 0;
+      }
+      unsigned int mask = __ballot_sync(0xffffffffu, keep);
+      if (!mask) continue;
+      const float z0 = tq.z0[qi], dz1 = tq.dz1[qi], dz2 = tq.dz2[qi], ia = tq.ia[qi], zoff = tq.zoff[qi];
+      const int meta = tq.meta[qi];
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int lx = __shfl_sync(0xffffffffu, bx, k) * SGI_BLK_W + sub_x;
+        const int ly = __shfl_sync(0xffffffffu, by, k) * SGI_BLK_H + sub_y;
+        if (lx < lx0 || lx > lx1 || ly < ly0 || ly > ly1) continue;
+        long long E0, E1, E2;
+        if (!cover(X0, Y0, X1, Y1, X2, Y2, ox + lx, oy + ly, E0, E1, E2)) continue;
+        sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
       }
     }
     __syncthreads();                                           // every warp is done with this chunk's queue
@@ -570,25 +625,22 @@ int sgi_raster_reserve(sgi_ctx* ctx, int max_tris, int W, int H) {
     if ((rc = grow(ctx, (void**)&ctx->d_rec, n * sizeof(SgiRec)))) return rc;
     if ((rc = grow(ctx, (void**)&ctx->d_attr, n * sizeof(SgiRecAttr)))) return rc;
     if ((rc = grow(ctx, (void**)&ctx->d_ovf_base, (size_t)max_tris * 4 + 16))) return rc;
+    if ((rc = grow(ctx, (void**)&ctx->d_big, n * 4))) return rc;
     ctx->rec_cap_tris = max_tris;
   }
-  if (!ctx->d_counters) {
-    if ((rc = grow(ctx, (void**)&ctx->d_counters, 64))) return rc;
+  if (!ctx->h_flags) {
     SGI_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 64, cudaHostAllocMapped));
     ctx->h_flags[0] = ctx->h_flags[1] = 0;
   }
   int tiles = ((W + SGI_TILE - 1) >> SGI_TILE_LOG2) * ((H + SGI_TILE - 1) >> SGI_TILE_LOG2);
   if (tiles + 1 > ctx->tile_cap) {
-    if ((rc = grow(ctx, (void**)&ctx->d_tile_cnt, (size_t)(tiles + 1) * 4))) return rc;
-    if ((rc = grow(ctx, (void**)&ctx->d_tile_off, (size_t)(tiles + 1) * 4))) return rc;
-    if ((rc = grow(ctx, (void**)&ctx->d_tile_fill, (size_t)(tiles + 1) * 4))) return rc;
-    ctx->tile_cap = tiles + 1;
-    size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_tile_cnt, ctx->d_tile_off, tiles + 1, ctx->stream);
-    if (tmp > ctx->scan_tmp_bytes) {
-      if ((rc = grow(ctx, &ctx->d_scan_tmp, tmp + 256))) return rc;
-      ctx->scan_tmp_bytes = tmp + 256;
-    }
+    int cap = tiles + 1 + 64;
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = grow(ctx, (void**)&ctx->d_counters, (size_t)(16 + 2 * cap) * 4))) return rc;   // counters | tile_cnt | tile_fill
+    ctx->d_tile_cnt = ctx->d_counters + 16;
+    ctx->d_tile_fill = ctx->d_tile_cnt + cap;
+    if ((rc = grow(ctx, (void**)&ctx->d_tile_off, (size_t)cap * 4))) return rc;
+    ctx->tile_cap = cap;
   }
   if (ctx->pair_cap == 0) {
     long long want = (long long)max_tris * 4 + (long long)tiles * 8 + (1 << 20);
@@ -616,8 +668,8 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
 }
 
 // CTA size of the tile kernel.  The pass ends when the busiest tile ends, and a tile is worked on by one CTA, so
-// few-tile passes (<= 1200 tiles: up to 1080p / 2048^2) get 32 warps per tile; many-tile passes get 16 so that the
-// per-tile init/flush and barriers stay cheap.  Measured on B200 (profiles/r1_tile_cta_size.txt).  SGI_TILE_THREADS
+// few-tile passes (<= 1200 tiles: up to 1080p / 2048^2) get 32 warps per tile; many-tile passes get 16 or 8 so that
+// the per-tile init/flush and barriers stay cheap.  Measured on B200 (profiles/r1_tile_cta_size.txt).  SGI_TILE_THREADS
 // overrides for experiments.
 static int tile_threads(int n_tiles) {
   static int forced = -1;
@@ -627,7 +679,7 @@ static int tile_threads(int n_tiles) {
     if (forced != 256 && forced != 512 && forced != 1024) forced = 0;
   }
   if (forced) return forced;
-  return n_tiles <= 1200 ? 1024 : 512;
+  return n_tiles <= 1200 ? 1024 : (n_tiles <= 6000 ? 512 : 256);
 }
 
 template <int MODE>
@@ -658,9 +710,8 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
   const int tx0 = rx0 >> SGI_TILE_LOG2, ty0 = ry0 >> SGI_TILE_LOG2;
   const int tx1 = (rx1 - 1) >> SGI_TILE_LOG2, ty1 = (ry1 - 1) >> SGI_TILE_LOG2;
 
-  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 16, st));
-  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_cnt, 0, (size_t)(n_tiles + 1) * 4, st));
-  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_fill, 0, (size_t)(n_tiles + 1) * 4, st));
+  // counters | tile_cnt | tile_fill live in one allocation: one memset
+  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, (size_t)(16 + 2 * ctx->tile_cap) * 4, st));
 
   SetupArgs sa;
   sa.xyz = job.xyz; sa.idx = job.idx; sa.T = job.T;
@@ -674,19 +725,15 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
   }
 
   BinArgs ba;
-  ba.rec = ctx->d_rec; ba.counters = ctx->d_counters; ba.T = job.T;
+  ba.rec = ctx->d_rec; ba.counters = ctx->d_counters; ba.counters_rw = ctx->d_counters; ba.T = job.T; ba.big_list = ctx->d_big;
   ba.tiles_x = tiles_x; ba.tiles_y = tiles_y; ba.tx0 = tx0; ba.ty0 = ty0; ba.tx1 = tx1; ba.ty1 = ty1;
   ba.tile_cnt = ctx->d_tile_cnt; ba.tile_off = ctx->d_tile_off; ba.tile_fill = ctx->d_tile_fill;
-  ba.pairs = ctx->d_pairs; ba.pair_cap = ctx->pair_cap; ba.flags = ctx->d_counters;
-  int bin_blocks = (job.T + 7) / 8;                 // 8 warps per CTA, one record per warp per trip
-  if (bin_blocks > 148 * 16) bin_blocks = 148 * 16;
+  ba.pairs = ctx->d_pairs; ba.pair_cap = ctx->pair_cap; ba.flags = ctx->d_counters; ba.h_flags = ctx->h_flags;
+  int bin_blocks = (job.T + job.T / 4 + 255) / 256;   // one thread per record; the loop strides over clipped extras
   if (bin_blocks < 1) bin_blocks = 1;
   k_bin<0><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
   ctx->launches++;
-  size_t tmp = ctx->scan_tmp_bytes;
-  SGI_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, tmp, ctx->d_tile_cnt, ctx->d_tile_off, n_tiles + 1, st));
-  ctx->launches += 1;
-  k_publish_total<<<1, 1, 0, st>>>(ctx->d_tile_off, n_tiles, ctx->d_counters, ctx->h_flags);
+  k_scan_tiles<<<1, 1024, 0, st>>>(ctx->d_tile_cnt, ctx->d_tile_off, n_tiles + 1, ctx->d_counters, ctx->h_flags);
   ctx->launches++;
   if (!ctx->sized[job.mode]) {
     // first pass of this kind on this context: size the tile lists from the real count (one sync, once)
@@ -701,13 +748,12 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
   }
   k_bin<1><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
   ctx->launches++;
-  k_publish_flag<<<1, 1, 0, st>>>(ctx->d_counters, ctx->h_flags);
-  ctx->launches++;
   ctx->overflow_pending = true;
 
   TileArgs ta;
   ta.rec = ctx->d_rec; ta.attr = ctx->d_attr; ta.ovf_base = ctx->d_ovf_base;
   ta.tile_off = ctx->d_tile_off; ta.pairs = ctx->d_pairs; ta.pair_cap = ctx->pair_cap;
+  ta.big_list = ctx->d_big; ta.counters = ctx->d_counters;
   ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
   ta.xyz = job.xyz; ta.nrm = job.nrm; ta.idx = job.idx;

@@ -61,41 +61,66 @@ __device__ __forceinline__ float pre_evaluation(const VisArgs& a, float4 vertex,
   return (g_max(dt, 0.0f) == 0.0f) ? a.p.shadow_intensity : 1.0f;
 }
 
+// Separable addressing of a tap grid: the texel column of a tap depends only on its u, the row only on its v
+// (texel = floor(coord*size), A.3), so both are computed once per axis position instead of once per tap; a tap is
+// then one add, one load and one compare.  Values are identical to calling sm_fetch per tap.
+__device__ __forceinline__ int axis_texel(float coord, float size) {      // texel index, or -1 outside [0,size) / NaN
+  float f = floorf(coord * size);
+  return (f >= 0.0f && f < size) ? (int)f : -1;
+}
+__device__ __forceinline__ float tap(const Smap& s, int row_off, int col) {
+  return ((row_off | col) < 0) ? 0.0f : __ldg(&s.d[(size_t)row_off + col]);
+}
+
 // ---- Shadow.frag:86-116 (tap offsets precomputed on the host with the same fp32 loop) ----
-__device__ float pcf(const VisArgs& a, const Smap& s, float4 c) {
-  float incrWidth = 1.0f / (float)a.SW, incrHeight = 1.0f / (float)a.SH;
-  float illum = 0.0f;
-  int n = a.pcf_n;
+// N = taps per axis known at compile time (0 = run-time count, columns kept in local memory)
+template <int N>
+__device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, float4 c) {
+  const float incrWidth = 1.0f / (float)a.SW, incrHeight = 1.0f / (float)a.SH;
+  const int n = N ? N : a.pcf_n;
   if (n <= 0) return 1.0f;
-  for (int iw = 0; iw < n; iw++) {
-    float u = c.x + a.pcf_off[iw] * incrWidth;
-    for (int ih = 0; ih < n; ih++) {
-      float dfl = sm_fetch(s, u, c.y + a.pcf_off[ih] * incrHeight);
-      if (c.z <= dfl) illum += 1.0f; else illum += a.p.shadow_intensity;
-    }
+  int rows[N ? N : SGI_MAX_PCF_TAPS];
+#pragma unroll
+  for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
+    if (ih < n) { int r = axis_texel(c.y + a.pcf_off[ih] * incrHeight, s.fh); rows[ih] = r < 0 ? -1 : r * s.w; }
+  float illum = 0.0f;
+  for (int iw = 0; iw < n; iw++) {                     // Shadow.frag:98-99: w outer, h inner
+    const int col = axis_texel(c.x + a.pcf_off[iw] * incrWidth, s.fw);
+#pragma unroll
+    for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
+      if (ih < n) { if (c.z <= tap(s, rows[ih], col)) illum += 1.0f; else illum += a.p.shadow_intensity; }
   }
   return illum / (float)(n * n);
 }
 
 // ---- PlausibleSoftShadow.frag:166-194, 365-374, 376-398 ----
-__device__ float pcss(const VisArgs& a, const Smap& s, float4 c) {
+// NB / NK = blocker-search / filter taps per axis at compile time (0 = run time)
+template <int NB, int NK>
+__device__ __forceinline__ float pcss_t(const VisArgs& a, const Smap& s, float4 c) {
   const sgi_params& p = a.p;
   float averageDepth = 0.0f;
   int numberOfBlockers = 0;
   float bsw;
   if ((float)a.SW <= 1024.0f) bsw = (float)p.light_source_radius / (float)a.SW;
   else bsw = (float)p.light_source_radius / 1024.0f;
-  float filterWidth = ((float)p.blocker_search_size - 1.0f) * 0.5f;
-  // u depends on w only: computed once per w instead of once per tap (identical values, 7 instead of 49 divides)
-  float us[SGI_MAX_PCF_TAPS];
-  const int w0 = (int)(-filterWidth);
-  int nw = 0;
-  for (int w = w0; (float)w <= filterWidth && nw < SGI_MAX_PCF_TAPS; w++) us[nw++] = c.x + ((float)w * bsw) / filterWidth;
-  for (int h = (int)(-filterWidth); (float)h <= filterWidth; h++) {
-    float v = c.y + ((float)h * bsw) / filterWidth;
-    for (int k = 0; k < nw; k++) {
-      float dfl = sm_fetch(s, us[k], v);
-      if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+  const float filterWidth = ((float)p.blocker_search_size - 1.0f) * 0.5f;
+  {
+    // `for(int w = -filterWidth; w <= filterWidth; w++)`: the int start truncates toward zero (A.7)
+    const int w0 = (int)(-filterWidth);
+    const int nb = NB ? NB : ((filterWidth >= 0.0f) ? (int)filterWidth - w0 + 1 : 0);
+    int cols[NB ? NB : SGI_MAX_PCF_TAPS];
+#pragma unroll
+    for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
+      if (k < nb) cols[k] = axis_texel(c.x + ((float)(w0 + k) * bsw) / filterWidth, s.fw);
+    for (int h = w0; (float)h <= filterWidth; h++) {
+      const int r = axis_texel(c.y + ((float)h * bsw) / filterWidth, s.fh);
+      const int row = r < 0 ? -1 : r * s.w;
+#pragma unroll
+      for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
+        if (k < nb) {
+          const float dfl = tap(s, row, cols[k]);
+          if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+        }
     }
   }
   if (numberOfBlockers == 0) averageDepth = 1.0f;
@@ -107,16 +132,22 @@ __device__ float pcss(const VisArgs& a, const Smap& s, float4 c) {
     penumbraWidth = ((float)p.z_near * pw) / c.z;
   }
   float illum = 0.0f;
-  float stepSize = 2.0f * penumbraWidth / (float)p.kernel_size;
-  float fw2 = ((float)p.kernel_size - 1.0f) * 0.5f;
+  const float stepSize = 2.0f * penumbraWidth / (float)p.kernel_size;
+  const float fw2 = ((float)p.kernel_size - 1.0f) * 0.5f;
   if (stepSize <= 0.0f || stepSize >= 1.0f) return 1.0f;
-  nw = 0;
-  for (int w = (int)(-fw2); (float)w <= fw2 && nw < SGI_MAX_PCF_TAPS; w++) us[nw++] = c.x + ((float)w * penumbraWidth) / fw2;
-  for (int h = (int)(-fw2); (float)h <= fw2; h++) {
-    float v = c.y + ((float)h * penumbraWidth) / fw2;
-    for (int k = 0; k < nw; k++) {
-      float dfl = sm_fetch(s, us[k], v);
-      if (c.z <= dfl) illum += 1.0f; else illum += p.shadow_intensity;
+  {
+    const int w0 = (int)(-fw2);
+    const int nk = NK ? NK : ((fw2 >= 0.0f) ? (int)fw2 - w0 + 1 : 0);
+    int cols[NK ? NK : SGI_MAX_PCF_TAPS];
+#pragma unroll
+    for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
+      if (k < nk) cols[k] = axis_texel(c.x + ((float)(w0 + k) * penumbraWidth) / fw2, s.fw);
+    for (int h = w0; (float)h <= fw2; h++) {
+      const int r = axis_texel(c.y + ((float)h * penumbraWidth) / fw2, s.fh);
+      const int row = r < 0 ? -1 : r * s.w;
+#pragma unroll
+      for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
+        if (k < nk) { if (c.z <= tap(s, row, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
     }
   }
   return illum / (float)(p.kernel_size * p.kernel_size);
@@ -386,7 +417,9 @@ __device__ float cs_rpcf(Rb& r, const VisArgs& a, float4 c) {
 }
 
 // ================================ kernels ========================================================
-template <int TECH>
+// VA / VB: compile-time tap counts of the specialised variants (PCF: VA = taps per axis; PCSS: VA = blocker taps,
+// VB = filter taps; 0 = generic run-time loops)
+template <int TECH, int VA, int VB>
 __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= a.rx1 || y >= a.ry1) return;
@@ -401,8 +434,8 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS) {
     if (sc.w > 0.0f && shadow == 1.0f) {
       if (TECH == SGI_TECH_HARD) shadow = (c.z <= sm_fetch(s, c.x, c.y)) ? 1.0f : a.p.shadow_intensity;
-      else if (TECH == SGI_TECH_PCF) shadow = pcf(a, s, c);
-      else shadow = pcss(a, s, c);
+      else if (TECH == SGI_TECH_PCF) shadow = pcf_t<VA>(a, s, c);
+      else shadow = pcss_t<VA, VB>(a, s, c);
     }
   } else if (shadow == 1.0f) {
     Rb r = {s, a.sx, a.sy, a.p.depth_threshold, a.p.max_search, a.p.shadow_intensity, TECH == SGI_TECH_RSMSS, a.fw, a.fh, 0.0f};
@@ -492,15 +525,26 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   ctx->launches++;
   dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
   int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL);
-  switch (ctx->params.technique) {
-    case SGI_TECH_HARD: k_visibility<SGI_TECH_HARD><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_PCF: k_visibility<SGI_TECH_PCF><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_PCSS: k_visibility<SGI_TECH_PCSS><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_RBSM_NONCONS: k_visibility<SGI_TECH_RBSM_NONCONS><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_RBSM_CONS: k_visibility<SGI_TECH_RBSM_CONS><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_RPCF_NONCONS: k_visibility<SGI_TECH_RPCF_NONCONS><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_RPCF_CONS: k_visibility<SGI_TECH_RPCF_CONS><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_RSMSS: k_visibility<SGI_TECH_RSMSS><<<grid, block, 0, st>>>(a); break;
+  const sgi_params& P = ctx->params;
+  // tap counts the float/int loops of the shaders produce for the current parameters
+  const int nb_taps = 2 * (int)(((float)P.blocker_search_size - 1.0f) * 0.5f) + 1;
+  const int nk_taps = 2 * (int)(((float)P.kernel_size - 1.0f) * 0.5f) + 1;
+  switch (P.technique) {
+    case SGI_TECH_HARD: k_visibility<SGI_TECH_HARD, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_PCF:
+      if (a.pcf_n == 7) k_visibility<SGI_TECH_PCF, 7, 0><<<grid, block, 0, st>>>(a);          // kernelOrder 7 (reference default)
+      else k_visibility<SGI_TECH_PCF, 0, 0><<<grid, block, 0, st>>>(a);
+      break;
+    case SGI_TECH_PCSS:
+      if (nb_taps == 7 && nk_taps == 15) k_visibility<SGI_TECH_PCSS, 7, 15><<<grid, block, 0, st>>>(a);   // reference default
+      else if (nb_taps == 7 && nk_taps == 7) k_visibility<SGI_TECH_PCSS, 7, 7><<<grid, block, 0, st>>>(a); // after "reset"
+      else k_visibility<SGI_TECH_PCSS, 0, 0><<<grid, block, 0, st>>>(a);
+      break;
+    case SGI_TECH_RBSM_NONCONS: k_visibility<SGI_TECH_RBSM_NONCONS, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RBSM_CONS: k_visibility<SGI_TECH_RBSM_CONS, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RPCF_NONCONS: k_visibility<SGI_TECH_RPCF_NONCONS, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RPCF_CONS: k_visibility<SGI_TECH_RPCF_CONS, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RSMSS: k_visibility<SGI_TECH_RSMSS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_MULTI_HARD: k_visibility_multi<<<grid, block, 0, st>>>(a); break;
     default: ctx->err = "unknown technique"; return SGI_ERR_INVALID;
   }
