@@ -3,6 +3,7 @@
 // SoftShadowMapping/src/main.cpp:756-811,925-1022, ShadowVolumes/src/main.cpp:120-206); see the header for
 // the entry-point -> reference mapping.  There is no CPU fallback: without a CUDA device sgi_create fails.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "sgi_internal.cuh"
@@ -30,27 +31,44 @@ int sgi_timing_drain(sgi_ctx* ctx) {
   }
   return SGI_OK;
 }
-int sgi_timing_begin(sgi_ctx* ctx, int pass) {
+int sgi_timing_begin(sgi_ctx* ctx, int pass, cudaStream_t stream) {
   if (!ctx->timing) return -1;
   if (ctx->ev_n[pass] >= SGI_EV_RING) sgi_timing_drain(ctx);
   int slot = ctx->ev_n[pass];
-  cudaEventRecord(ctx->ev[pass][slot][0], ctx->stream);
+  cudaEventRecord(ctx->ev[pass][slot][0], stream);
   return slot;
 }
-void sgi_timing_end(sgi_ctx* ctx, int pass, int slot) {
+void sgi_timing_end(sgi_ctx* ctx, int pass, int slot, cudaStream_t stream) {
   if (slot < 0) return;
-  cudaEventRecord(ctx->ev[pass][slot][1], ctx->stream);
+  cudaEventRecord(ctx->ev[pass][slot][1], stream);
   ctx->ev_n[pass] = slot + 1;
 }
 
 static int check_overflow(sgi_ctx* ctx) {
-  if (!ctx->overflow_pending || !ctx->h_flags) return SGI_OK;
-  ctx->overflow_pending = false;
-  if (ctx->h_flags[0]) {
-    ctx->h_flags[0] = 0;
-    ctx->gbuffer_valid = false; ctx->shadow_map_valid = false;
-    ctx->err = "tile list overflow: the lists were re-sized, run the frame again";
-    return SGI_ERR_OVERFLOW;       // sgi_raster_run grows d_pairs from h_flags[1] on the next call
+  int rc = SGI_OK;
+  for (SgiScratch& sc : ctx->scratch) {
+    if (!sc.overflow_pending || !sc.h_flags) continue;
+    sc.overflow_pending = false;
+    if (sc.h_flags[0]) {
+      sc.h_flags[0] = 0;
+      ctx->gbuffer_valid = false; ctx->shadow_map_valid = false;
+      ctx->err = "tile list overflow: the lists were re-sized, run the frame again";
+      rc = SGI_ERR_OVERFLOW;       // sgi_raster_run grows d_pairs from h_flags[1] on the next call
+    }
+  }
+  return rc;
+}
+
+// called after work that reads the G-buffer / rewrites the mesh has been queued on the main stream: the next G-buffer
+// pass (auxiliary stream) must not start before this point, but need not wait for anything queued later
+static void mark_gbuffer_use(sgi_ctx* ctx) { if (ctx->ev_fork) cudaEventRecord(ctx->ev_fork, ctx->stream); }
+
+// The G-buffer pass runs on the auxiliary stream so that it overlaps the light-view depth pass; every consumer of
+// its outputs (and every host-visible point) first makes the main stream wait for it.
+int sgi_join_gbuffer(sgi_ctx* ctx) {
+  if (ctx->gbuf_in_flight) {
+    SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gbuf_done, 0));
+    ctx->gbuf_in_flight = false;
   }
   return SGI_OK;
 }
@@ -90,6 +108,10 @@ int sgi_create(sgi_ctx** out, int device) {
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
+  if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_gbuf_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
+  { const char* e = getenv("SGI_NO_OVERLAP"); ctx->overlap_passes = !(e && e[0] == '1'); }
   sgi_default_params(&ctx->params);
   for (int p = 0; p < SGI_PASS_COUNT_; p++) {
     ctx->ev_n[p] = 0; ctx->pass_ms[p] = 0; ctx->pass_calls[p] = 0;
@@ -104,11 +126,14 @@ int sgi_destroy(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
-  void* ptrs[] = {ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->d_light_trans, ctx->d_rec, ctx->d_attr, ctx->d_ovf_base, ctx->d_big, ctx->d_counters,
-                  ctx->d_tile_off, ctx->d_pairs};
+  void* ptrs[] = {ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  for (SgiScratch& sc : ctx->scratch) sgi_raster_free(sc);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_gbuf_done) cudaEventDestroy(ctx->ev_gbuf_done);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);
   for (int p = 0; p < SGI_PASS_COUNT_; p++)
     for (int k = 0; k < SGI_EV_RING; k++) { if (ctx->ev[p][k][0]) cudaEventDestroy(ctx->ev[p][k][0]); if (ctx->ev[p][k][1]) cudaEventDestroy(ctx->ev[p][k][1]); }
@@ -119,8 +144,10 @@ int sgi_destroy(sgi_ctx* ctx) {
 
 int sgi_set_stream(sgi_ctx* ctx, void* cuda_stream) {
   if (!ctx) return SGI_ERR_INVALID;
+  sgi_join_gbuffer(ctx);
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  mark_gbuffer_use(ctx);
   return SGI_OK;
 }
 
@@ -129,6 +156,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   for (int64_t k = 0; k < (int64_t)T * 3; k++)
     if (idx[k] < 0 || idx[k] >= V) { ctx->err = "sgi_set_mesh: index out of range"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (V != ctx->V) {
     if (ctx->d_xyz) cudaFree(ctx->d_xyz);
@@ -148,6 +176,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
     SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm, nrm, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (T > 0) SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_idx, idx, (size_t)T * 12, cudaMemcpyHostToDevice, ctx->stream));
+  mark_gbuffer_use(ctx);
   ctx->gbuffer_valid = ctx->shadow_map_valid = false;
   return SGI_OK;
 }
@@ -155,6 +184,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
 int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const float nm[9], int32_t W, int32_t H) {
   if (!ctx || !mvp || !mv || !nm || W <= 0 || H <= 0 || W > 32767 || H > 32767) { if (ctx) ctx->err = "sgi_set_camera: bad arguments"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
   memcpy(ctx->cam_mvp, mvp, 64); memcpy(ctx->cam_mv, mv, 64); memcpy(ctx->cam_nm, nm, 36);
   int rc;
   size_t px = (size_t)W * H;
@@ -164,8 +194,9 @@ int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const 
   if ((rc = ensure_buf(ctx, SGI_BUF_VISIBILITY, px * 4))) return rc;
   if (W != ctx->W || H != ctx->H) {
     SGI_CUDA(ctx, cudaMemsetAsync(ctx->buf[SGI_BUF_VISIBILITY], 0, px * 4, ctx->stream));
-    ctx->sized[SGI_MODE_GBUFFER] = ctx->sized[SGI_MODE_SVCOUNT] = false;
+    ctx->scratch[1].sized[SGI_MODE_GBUFFER] = ctx->scratch[0].sized[SGI_MODE_SVCOUNT] = false;
   }
+  mark_gbuffer_use(ctx);
   ctx->W = W; ctx->H = H; ctx->has_camera = true; ctx->gbuffer_valid = false;
   return SGI_OK;
 }
@@ -186,18 +217,12 @@ int sgi_set_lights(sgi_ctx* ctx, int32_t N, const float* light_mvp, const float*
     ctx->d_light_trans = nullptr;
     SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_light_trans, (size_t)N * 16));
   }
-  if (SW != ctx->SW || SH != ctx->SH) ctx->sized[SGI_MODE_DEPTH] = false;
+  if (SW != ctx->SW || SH != ctx->SH) ctx->scratch[0].sized[SGI_MODE_DEPTH] = false;
   ctx->N = N; ctx->SW = SW; ctx->SH = SH;
   memcpy(ctx->h_light_mvp, light_mvp, (size_t)N * 64);
   memcpy(ctx->h_light_mvp_b, light_mvp_b, (size_t)N * 64);
   memcpy(ctx->light_pos, lpos, 12);
-  // lightMVPTrans[i] = column 3 of bias*lightMVP_i (SoftShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:187-190)
-  float* tmp = (float*)malloc((size_t)N * 16);
-  for (int i = 0; i < N; i++) memcpy(tmp + 4 * i, light_mvp_b + 16 * (size_t)i + 12, 16);
-  cudaError_t e = cudaMemcpyAsync(ctx->d_light_trans, tmp, (size_t)N * 16, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // tmp is pageable and freed below
-  free(tmp);
-  if (e != cudaSuccess) { ctx->err = std::string("light upload: ") + cudaGetErrorString(e); return SGI_ERR_CUDA; }
+  ctx->trans_dirty = true;          // lightMVPTrans[] is uploaded lazily by the many-light pass (no sync on the single-light path)
   ctx->shadow_map_valid = false;
   return SGI_OK;
 }
@@ -223,7 +248,7 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->d_idx || ctx->N <= 0) { ctx->err = "sgi_render_shadow_map: set mesh and lights first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP, ctx->stream);
   for (int l = 0; l < ctx->N; l++) {
     SgiRasterJob job;
     memset(&job, 0, sizeof(job));
@@ -233,10 +258,10 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
     job.W = ctx->SW; job.H = ctx->SH;
     job.use_offset = 1; job.factor = ctx->params.polygon_offset_factor; job.units = ctx->params.polygon_offset_units;
     job.depth = (float*)ctx->buf[SGI_BUF_SHADOW_MAP] + (size_t)l * ctx->SW * ctx->SH;
-    int rc = sgi_raster_run(ctx, job);
+    int rc = sgi_raster_run(ctx, job, 0, ctx->stream);
     if (rc) return rc;
   }
-  sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot);
+  sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot, ctx->stream);
   ctx->shadow_map_valid = true;
   return SGI_OK;
 }
@@ -245,7 +270,17 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->d_idx || !ctx->has_camera) { ctx->err = "sgi_render_gbuffer: set mesh and camera first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER);
+  // fork: the auxiliary stream picks up after everything already queued on the main stream (mesh upload, the
+  // previous frame's consumers of the G-buffer) and then runs concurrently with what the main stream does next
+  sgi_join_gbuffer(ctx);
+  cudaStream_t st = ctx->overlap_passes ? ctx->aux_stream : ctx->stream;
+  if (ctx->overlap_passes) {
+    // ev_fork marks the last point of the main stream that touched the G-buffer or the mesh (mark_gbuffer_use);
+    // if a device pointer was lent out, unknown readers may follow it, so fork from "now" instead
+    if (ctx->gbuf_exposed) SGI_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+  }
+  int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
   SgiRasterJob job;
   memset(&job, 0, sizeof(job));
   job.mode = SGI_MODE_GBUFFER;
@@ -255,9 +290,13 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   job.depth = (float*)ctx->buf[SGI_BUF_CAM_DEPTH];
   job.pos4 = (float4*)ctx->buf[SGI_BUF_GBUF_POS]; job.nrm4 = (float4*)ctx->buf[SGI_BUF_GBUF_NRM];
   job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
-  int rc = sgi_raster_run(ctx, job);
+  int rc = sgi_raster_run(ctx, job, 1, st);
   if (rc) return rc;
-  sgi_timing_end(ctx, SGI_PASS_GBUFFER, slot);
+  sgi_timing_end(ctx, SGI_PASS_GBUFFER, slot, st);
+  if (ctx->overlap_passes) {
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_gbuf_done, st));
+    ctx->gbuf_in_flight = true;
+  }
   ctx->gbuffer_valid = true;
   return SGI_OK;
 }
@@ -266,10 +305,13 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->gbuffer_valid || !ctx->shadow_map_valid) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY);
-  int rc = sgi_shadow_run(ctx);
+  int rc = sgi_join_gbuffer(ctx);
   if (rc) return rc;
-  sgi_timing_end(ctx, SGI_PASS_VISIBILITY, slot);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, ctx->stream);
+  rc = sgi_shadow_run(ctx);
+  if (rc) return rc;
+  sgi_timing_end(ctx, SGI_PASS_VISIBILITY, slot, ctx->stream);
+  mark_gbuffer_use(ctx);
   return SGI_OK;
 }
 
@@ -283,7 +325,8 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_STENCIL, px))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_XYZ, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_IDX, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
-  int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_VOLUME);
+  if ((rc = sgi_join_gbuffer(ctx))) return rc;
+  int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_VOLUME, ctx->stream);
   if ((rc = sgi_sv_extrude_run(ctx, light_pos, (float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ], (int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]))) return rc;
   SgiRasterJob job;
   memset(&job, 0, sizeof(job));
@@ -295,14 +338,16 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   job.scene_depth = (const float*)ctx->buf[SGI_BUF_CAM_DEPTH]; job.depth_func = ctx->params.sv_depth_func;
   job.count = (int32_t*)ctx->buf[SGI_BUF_SV_COUNT]; job.stencil = (uint8_t*)ctx->buf[SGI_BUF_SV_STENCIL];
   job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
-  if ((rc = sgi_raster_run(ctx, job))) return rc;
-  sgi_timing_end(ctx, SGI_PASS_SHADOW_VOLUME, slot);
+  if ((rc = sgi_raster_run(ctx, job, 0, ctx->stream))) return rc;
+  sgi_timing_end(ctx, SGI_PASS_SHADOW_VOLUME, slot, ctx->stream);
+  mark_gbuffer_use(ctx);
   return SGI_OK;
 }
 
 int sgi_synchronize(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->timing) sgi_timing_drain(ctx);
   return check_overflow(ctx);
@@ -312,13 +357,17 @@ int sgi_read(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes) {
   if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dst) return SGI_ERR_INVALID;
   if (!ctx->buf[which] || bytes > ctx->buf_bytes[which]) { ctx->err = "sgi_read: buffer not produced yet or size too large"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
   SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  mark_gbuffer_use(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return check_overflow(ctx);
 }
 
 int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** dptr, size_t* bytes) {
   if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dptr) return SGI_ERR_INVALID;
+  sgi_join_gbuffer(ctx);              // work queued on the main stream after this call sees a finished G-buffer
+  if (which == SGI_BUF_GBUF_POS || which == SGI_BUF_GBUF_NRM || which == SGI_BUF_CAM_DEPTH) ctx->gbuf_exposed = true;
   *dptr = ctx->buf[which];
   if (bytes) *bytes = ctx->buf_bytes[which];
   return ctx->buf[which] ? SGI_OK : SGI_ERR_INVALID;

@@ -618,40 +618,40 @@ static int grow(sgi_ctx* ctx, void** p, size_t bytes) {
   return SGI_OK;
 }
 
-int sgi_raster_reserve(sgi_ctx* ctx, int max_tris, int W, int H) {
+static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W, int H, cudaStream_t stream) {
   int rc;
-  if (max_tris > ctx->rec_cap_tris) {
+  if (max_tris > sc.rec_cap_tris) {
     size_t n = (size_t)max_tris * 7 + 16;
-    if ((rc = grow(ctx, (void**)&ctx->d_rec, n * sizeof(SgiRec)))) return rc;
-    if ((rc = grow(ctx, (void**)&ctx->d_attr, n * sizeof(SgiRecAttr)))) return rc;
-    if ((rc = grow(ctx, (void**)&ctx->d_ovf_base, (size_t)max_tris * 4 + 16))) return rc;
-    if ((rc = grow(ctx, (void**)&ctx->d_big, n * 4))) return rc;
-    ctx->rec_cap_tris = max_tris;
+    if ((rc = grow(ctx, (void**)&sc.d_rec, n * sizeof(SgiRec)))) return rc;
+    if ((rc = grow(ctx, (void**)&sc.d_attr, n * sizeof(SgiRecAttr)))) return rc;
+    if ((rc = grow(ctx, (void**)&sc.d_ovf_base, (size_t)max_tris * 4 + 16))) return rc;
+    if ((rc = grow(ctx, (void**)&sc.d_big, n * 4))) return rc;
+    sc.rec_cap_tris = max_tris;
   }
-  if (!ctx->h_flags) {
-    SGI_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 64, cudaHostAllocMapped));
-    ctx->h_flags[0] = ctx->h_flags[1] = 0;
+  if (!sc.h_flags) {
+    SGI_CUDA(ctx, cudaHostAlloc((void**)&sc.h_flags, 64, cudaHostAllocMapped));
+    sc.h_flags[0] = sc.h_flags[1] = 0;
   }
   int tiles = ((W + SGI_TILE - 1) >> SGI_TILE_LOG2) * ((H + SGI_TILE - 1) >> SGI_TILE_LOG2);
-  if (tiles + 1 > ctx->tile_cap) {
+  if (tiles + 1 > sc.tile_cap) {
     int cap = tiles + 1 + 64;
-    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if ((rc = grow(ctx, (void**)&ctx->d_counters, (size_t)(16 + 2 * cap) * 4))) return rc;   // counters | tile_cnt | tile_fill
-    ctx->d_tile_cnt = ctx->d_counters + 16;
-    ctx->d_tile_fill = ctx->d_tile_cnt + cap;
-    if ((rc = grow(ctx, (void**)&ctx->d_tile_off, (size_t)cap * 4))) return rc;
-    ctx->tile_cap = cap;
+    SGI_CUDA(ctx, cudaStreamSynchronize(stream));
+    if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(16 + 2 * cap) * 4))) return rc;   // counters | tile_cnt | tile_fill
+    sc.d_tile_cnt = sc.d_counters + 16;
+    sc.d_tile_fill = sc.d_tile_cnt + cap;
+    if ((rc = grow(ctx, (void**)&sc.d_tile_off, (size_t)cap * 4))) return rc;
+    sc.tile_cap = cap;
   }
-  if (ctx->pair_cap == 0) {
+  if (sc.pair_cap == 0) {
     long long want = (long long)max_tris * 4 + (long long)tiles * 8 + (1 << 20);
-    if ((rc = grow(ctx, (void**)&ctx->d_pairs, (size_t)want * 4))) return rc;
-    ctx->pair_cap = want;
+    if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
+    sc.pair_cap = want;
   }
   return SGI_OK;
 }
 
 template <int MODE, int NT>
-static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
+static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStream_t stream) {
   static bool configured = false;
   constexpr size_t smem = tile_smem_bytes<MODE, NT>();
   if (!configured) {
@@ -659,9 +659,9 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
     configured = true;
   }
   const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : (MODE == SGI_MODE_GBUFFER ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
-  int tslot = sgi_timing_begin(ctx, pass);
-  k_tile<MODE, NT><<<grid, NT, smem, ctx->stream>>>(ta);
-  sgi_timing_end(ctx, pass, tslot);
+  int tslot = sgi_timing_begin(ctx, pass, stream);
+  k_tile<MODE, NT><<<grid, NT, smem, stream>>>(ta);
+  sgi_timing_end(ctx, pass, tslot, stream);
   ctx->launches++;
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;
@@ -683,25 +683,26 @@ static int tile_threads(int n_tiles) {
 }
 
 template <int MODE>
-static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid) {
+static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStream_t stream) {
   switch (tile_threads((int)(grid.x * grid.y))) {
-    case 256: return launch_tile_nt<MODE, 256>(ctx, ta, grid);
-    case 512: return launch_tile_nt<MODE, 512>(ctx, ta, grid);
-    default: return launch_tile_nt<MODE, 1024>(ctx, ta, grid);
+    case 256: return launch_tile_nt<MODE, 256>(ctx, ta, grid, stream);
+    case 512: return launch_tile_nt<MODE, 512>(ctx, ta, grid, stream);
+    default: return launch_tile_nt<MODE, 1024>(ctx, ta, grid, stream);
   }
 }
 
-int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
-  int rc = sgi_raster_reserve(ctx, job.T, job.W, job.H);
+int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaStream_t stream) {
+  SgiScratch& sc = ctx->scratch[scratch_set];
+  int rc = sgi_raster_reserve(ctx, sc, job.T, job.W, job.H, stream);
   if (rc) return rc;
   // a previous frame asked for more list space than we had: grow before running again
-  if (ctx->h_flags[1] > 0 && (long long)ctx->h_flags[1] + 1024 > ctx->pair_cap) {
-    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    long long want = (long long)ctx->h_flags[1] * 3 / 2 + (1 << 16);
-    if ((rc = grow(ctx, (void**)&ctx->d_pairs, (size_t)want * 4))) return rc;
-    ctx->pair_cap = want;
+  if (sc.h_flags[1] > 0 && (long long)sc.h_flags[1] + 1024 > sc.pair_cap) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(stream));
+    long long want = (long long)sc.h_flags[1] * 3 / 2 + (1 << 16);
+    if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
+    sc.pair_cap = want;
   }
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = stream;
   const int tiles_x = (job.W + SGI_TILE - 1) >> SGI_TILE_LOG2, tiles_y = (job.H + SGI_TILE - 1) >> SGI_TILE_LOG2;
   const int n_tiles = tiles_x * tiles_y;
   int rx0 = job.rx0, ry0 = job.ry0, rx1 = job.rx1, ry1 = job.ry1;
@@ -711,59 +712,66 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job) {
   const int tx1 = (rx1 - 1) >> SGI_TILE_LOG2, ty1 = (ry1 - 1) >> SGI_TILE_LOG2;
 
   // counters | tile_cnt | tile_fill live in one allocation: one memset
-  SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, (size_t)(16 + 2 * ctx->tile_cap) * 4, st));
+  SGI_CUDA(ctx, cudaMemsetAsync(sc.d_counters, 0, (size_t)(16 + 2 * sc.tile_cap) * 4, st));
 
   SetupArgs sa;
   sa.xyz = job.xyz; sa.idx = job.idx; sa.T = job.T;
   for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
   sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
-  sa.rec = ctx->d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? ctx->d_attr : nullptr;
-  sa.ovf_base = ctx->d_ovf_base; sa.counters = ctx->d_counters;
+  sa.rec = sc.d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? sc.d_attr : nullptr;
+  sa.ovf_base = sc.d_ovf_base; sa.counters = sc.d_counters;
   if (job.T > 0) {
     k_setup<<<(job.T + 127) / 128, 128, 0, st>>>(sa);
     ctx->launches++;
   }
 
   BinArgs ba;
-  ba.rec = ctx->d_rec; ba.counters = ctx->d_counters; ba.counters_rw = ctx->d_counters; ba.T = job.T; ba.big_list = ctx->d_big;
+  ba.rec = sc.d_rec; ba.counters = sc.d_counters; ba.counters_rw = sc.d_counters; ba.T = job.T; ba.big_list = sc.d_big;
   ba.tiles_x = tiles_x; ba.tiles_y = tiles_y; ba.tx0 = tx0; ba.ty0 = ty0; ba.tx1 = tx1; ba.ty1 = ty1;
-  ba.tile_cnt = ctx->d_tile_cnt; ba.tile_off = ctx->d_tile_off; ba.tile_fill = ctx->d_tile_fill;
-  ba.pairs = ctx->d_pairs; ba.pair_cap = ctx->pair_cap; ba.flags = ctx->d_counters; ba.h_flags = ctx->h_flags;
+  ba.tile_cnt = sc.d_tile_cnt; ba.tile_off = sc.d_tile_off; ba.tile_fill = sc.d_tile_fill;
+  ba.pairs = sc.d_pairs; ba.pair_cap = sc.pair_cap; ba.flags = sc.d_counters; ba.h_flags = sc.h_flags;
   int bin_blocks = (job.T + job.T / 4 + 255) / 256;   // one thread per record; the loop strides over clipped extras
   if (bin_blocks < 1) bin_blocks = 1;
   k_bin<0><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
   ctx->launches++;
-  k_scan_tiles<<<1, 1024, 0, st>>>(ctx->d_tile_cnt, ctx->d_tile_off, n_tiles + 1, ctx->d_counters, ctx->h_flags);
+  k_scan_tiles<<<1, 1024, 0, st>>>(sc.d_tile_cnt, sc.d_tile_off, n_tiles + 1, sc.d_counters, sc.h_flags);
   ctx->launches++;
-  if (!ctx->sized[job.mode]) {
+  if (!sc.sized[job.mode]) {
     // first pass of this kind on this context: size the tile lists from the real count (one sync, once)
     SGI_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->sized[job.mode] = true;
-    if ((long long)ctx->h_flags[1] > ctx->pair_cap) {
-      long long want = (long long)ctx->h_flags[1] * 3 / 2 + (1 << 16);
-      if ((rc = grow(ctx, (void**)&ctx->d_pairs, (size_t)want * 4))) return rc;
-      ctx->pair_cap = want;
-      ba.pairs = ctx->d_pairs; ba.pair_cap = ctx->pair_cap;
+    sc.sized[job.mode] = true;
+    if ((long long)sc.h_flags[1] > sc.pair_cap) {
+      long long want = (long long)sc.h_flags[1] * 3 / 2 + (1 << 16);
+      if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
+      sc.pair_cap = want;
+      ba.pairs = sc.d_pairs; ba.pair_cap = sc.pair_cap;
     }
   }
   k_bin<1><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
   ctx->launches++;
-  ctx->overflow_pending = true;
+  sc.overflow_pending = true;
 
   TileArgs ta;
-  ta.rec = ctx->d_rec; ta.attr = ctx->d_attr; ta.ovf_base = ctx->d_ovf_base;
-  ta.tile_off = ctx->d_tile_off; ta.pairs = ctx->d_pairs; ta.pair_cap = ctx->pair_cap;
-  ta.big_list = ctx->d_big; ta.counters = ctx->d_counters;
+  ta.rec = sc.d_rec; ta.attr = sc.d_attr; ta.ovf_base = sc.d_ovf_base;
+  ta.tile_off = sc.d_tile_off; ta.pairs = sc.d_pairs; ta.pair_cap = sc.pair_cap;
+  ta.big_list = sc.d_big; ta.counters = sc.d_counters;
   ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
   ta.xyz = job.xyz; ta.nrm = job.nrm; ta.idx = job.idx;
   ta.depth = job.depth; ta.pos4 = job.pos4; ta.nrm4 = job.nrm4;
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
   dim3 grid(tx1 - tx0 + 1, ty1 - ty0 + 1);
-  if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid);
-  else if (job.mode == SGI_MODE_GBUFFER) rc = launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid);
-  else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid);
+  if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, st);
+  else if (job.mode == SGI_MODE_GBUFFER) rc = launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, st);
+  else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, st);
   return rc;
+}
+
+void sgi_raster_free(SgiScratch& sc) {
+  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_off, sc.d_pairs};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (sc.h_flags) cudaFreeHost(sc.h_flags);
+  sc = SgiScratch();
 }
 
 int sgi_sv_extrude_run(sgi_ctx* ctx, const float light[3], float* prism_xyz, int32_t* prism_idx) {

@@ -7,6 +7,7 @@
 //   many-light           SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag:52-133
 // Shadow-map taps are GL_NEAREST + CLAMP_TO_BORDER(0): texel = floor(coord*size) (MyGLTextureViewer.cpp:3-28).
 // fp32 in source order, -fmad=false: results are bit-identical to oracle/ (DESIGN.md §3).
+#include <vector>
 #include "sgi_internal.cuh"
 
 namespace {
@@ -520,11 +521,19 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
   if (rw <= 0 || rh <= 0) return SGI_OK;
   cudaStream_t st = ctx->stream;
+  if (multi && ctx->trans_dirty) {
+    // lightMVPTrans[i] = column 3 of bias*lightMVP_i (SoftShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:187-190)
+    std::vector<float> tmp((size_t)ctx->N * 4);
+    for (int i = 0; i < ctx->N; i++) for (int k = 0; k < 4; k++) tmp[4 * (size_t)i + k] = ctx->h_light_mvp_b[16 * (size_t)i + 12 + k];
+    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_light_trans, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, st));
+    SGI_CUDA(ctx, cudaStreamSynchronize(st));      // tmp is pageable
+    ctx->trans_dirty = false;
+  }
   // the reference clears the target to 0 before the full-screen pass (main.cpp:403-405); discarded pixels keep it
   k_clear_rect<<<dim3((rw + 255) / 256, rh), 256, 0, st>>>(a.vis, a.W, a.rx0, a.ry0, a.rx1, a.ry1);
   ctx->launches++;
   dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
-  int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL);
+  int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL, st);
   const sgi_params& P = ctx->params;
   // tap counts the float/int loops of the shaders produce for the current parameters
   const int nb_taps = 2 * (int)(((float)P.blocker_search_size - 1.0f) * 0.5f) + 1;
@@ -549,7 +558,7 @@ int sgi_shadow_run(sgi_ctx* ctx) {
     default: ctx->err = "unknown technique"; return SGI_ERR_INVALID;
   }
   ctx->launches++;
-  sgi_timing_end(ctx, SGI_PASS_VIS_KERNEL, tslot);
+  sgi_timing_end(ctx, SGI_PASS_VIS_KERNEL, tslot, st);
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;
 }
