@@ -172,7 +172,7 @@ def main():
         print(json.dumps(run_reference(args, w, cfg_path)), flush=True)
         return 0
 
-    args.steps = args.steps or 200
+    args.steps = args.steps or 400
     args.warmup = 10 if args.warmup is None else max(3, args.warmup)
 
     import torch
