@@ -15,7 +15,9 @@ reference's animation step every frame (ShadowMapping/src/main.cpp:217,481).
   roofline  the kernel with the largest share of the step, timed with CUDA events around its launches
   cpu_baseline  the CPU oracle (oracle/, a port of the reference's passes) on the host cores, a few frames
 N > 1: frame-parallel — every rank renders its own frames of the same animation (no data-path collective,
-"scaling": "weak"); `value` is the sum over ranks / max time.
+"scaling": "weak"); `value` is the sum over ranks / max time.  With --workload c5_many_light --mode lights the
+ranks instead share ONE frame: each builds and samples the depth maps of its own lights and the partial sums are
+all-reduced over NCCL ("scaling": "strong").
 """
 import argparse
 import json
@@ -153,6 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_sponza")
+    ap.add_argument("--mode", default="frames", choices=["frames", "lights"], help="N>1: frame-parallel, or light shards of one frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -190,7 +193,13 @@ def main():
     app.configure(w["W"], w["H"], w["S"])
     app.set_technique(w["technique"])
     app.set(**w["params"])
-    app.set(animationOn=1, animation=-1800.0 + ANIMATION_STEP * rank)     # rank r renders frames r, r+N, ...
+    lights_mode = args.mode == "lights" and world > 1 and w["technique"] == "montecarlo"
+    if lights_mode:
+        app.set(animationOn=1, animation=-1800.0)                          # every rank works on the same frame
+        app.set_light_shard(rank, world)
+    else:
+        app.set(animationOn=1, animation=-1800.0 + ANIMATION_STEP * rank)     # rank r renders frames r, r+N, ...
+    anim_stride = ANIMATION_STEP * (1 if lights_mode else world)
     program = w["program"]
     ctx = app.context()
     stream = torch.cuda.Stream(device=local_rank)
@@ -205,10 +214,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    class _DevView:      # torch tensor over the context's visibility buffer (the NCCL send buffer: no staging copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    vis_t = None
+
+    def frame():
+        nonlocal vis_t
+        app.display(program)
+        if lights_mode:
+            if vis_t is None:
+                ptr, nbytes = ctx.device_ptr("visibility")
+                vis_t = torch.as_tensor(_DevView(ptr, nbytes // 4), device=f"cuda:{local_rank}")
+            dist.all_reduce(vis_t)                       # sum of the per-rank partial sums, on the context's stream
+            vis_t.mul_(1.0 / n_l)                        # AccurateSoftShadow.frag:127
+
     app.upload_scene()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            app.display(program); app.step_animation(ANIMATION_STEP * world)
+            frame(); app.step_animation(anim_stride)
         ctx.synchronize()
 
         # ---- timed region: K steps, per-step events, L2 flushed before each ----
@@ -221,9 +246,9 @@ def main():
         for k in range(args.steps):
             flush.zero_()
             ev[k][0].record(stream)
-            app.display(program)
+            frame()
             ev[k][1].record(stream)
-            app.step_animation(ANIMATION_STEP * world)
+            app.step_animation(anim_stride)
         ctx.synchronize()
         barrier()
         clock_info = clocks.stop() if rank == 0 else None
@@ -235,7 +260,7 @@ def main():
         ctx.enable_timing(True); ctx.reset_timing()
         for k in range(min(args.steps, 100)):
             flush.zero_()
-            app.display(program); app.step_animation(ANIMATION_STEP * world)
+            frame(); app.step_animation(anim_stride)
         ctx.synchronize()
         passes = {}
         for name in capi.PASS:
@@ -249,11 +274,11 @@ def main():
         host_vis = torch.empty(w["W"] * w["H"], dtype=torch.float32).pin_memory()
         e2e_steps = max(10, min(args.steps, 100))
         for _ in range(3):
-            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(ANIMATION_STEP * world)
+            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(anim_stride)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(ANIMATION_STEP * world)
+            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(anim_stride)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         lit = float((host_vis == 1.0).float().mean())
@@ -267,7 +292,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    fps = world * args.steps / (total_ms / 1e3)
+    fps = (1 if lights_mode else world) * args.steps / (total_ms / 1e3)
     peak, peak_src = load_peaks()
     ab = algorithmic_bytes(w, V, T, n_l)
     kernel_of = {"vis_kernel": ("k_visibility (per-pixel shadow test/filter)", ab["visibility"]),
@@ -285,14 +310,14 @@ def main():
                 "share_of_step": cand[top] / (total_ms / args.steps)}
     out = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if lights_mode else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,
                    "params": w["params"], "triangles": T, "vertices": V, "scene": w["scene"],
                    "l2": "flushed before every timed step (256 MiB memset on the same stream, outside the event pair)",
-                   "parallelism": f"frames x{world}" if world > 1 else "single GPU", "lit_fraction": lit},
+                   "parallelism": (f"lights x{world} + all-reduce" if lights_mode else f"frames x{world}") if world > 1 else "single GPU", "lit_fraction": lit},
         "clocks": clock_info, "gpu_launches": int(launches),
-        "e2e": {"value": world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * 24 + T * 12),
+        "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * 24 + T * 12),
                 "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps},
         "pass_ms": passes, "roofline": roof,
     }

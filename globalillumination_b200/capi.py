@@ -32,11 +32,12 @@ class SgiParams(C.Structure):
         ("polygon_offset_factor", C.c_float), ("polygon_offset_units", C.c_float),
         ("sv_depth_func", C.c_int32), ("sv_infinity", C.c_int32),
         ("rect_x0", C.c_int32), ("rect_y0", C.c_int32), ("rect_x1", C.c_int32), ("rect_y1", C.c_int32),
+        ("multi_partial", C.c_int32),
     ]
 
 
 EXPORTS = [
-    "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params",
+    "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
@@ -138,6 +139,12 @@ class Context:
         assert a.shape == b.shape
         self.N, self.SW, self.SH = a.shape[0], int(SW), int(SH)
         self._ck(self.lib.sgi_set_lights(self.h, self.N, _fp(a), _fp(b), _fp(_f32(light_pos_shading)), self.SW, self.SH))
+
+    def set_multi_light_common(self, light_mvp_b):
+        if light_mvp_b is None:
+            self._ck(self.lib.sgi_set_multi_light_common(self.h, None))
+        else:
+            self._ck(self.lib.sgi_set_multi_light_common(self.h, _fp(_f32(light_mvp_b))))
 
     def set_params(self, params):
         self.params = params

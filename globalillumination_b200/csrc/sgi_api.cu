@@ -227,6 +227,13 @@ int sgi_set_lights(sgi_ctx* ctx, int32_t N, const float* light_mvp, const float*
   return SGI_OK;
 }
 
+int sgi_set_multi_light_common(sgi_ctx* ctx, const float m[16]) {
+  if (!ctx) return SGI_ERR_INVALID;
+  ctx->has_multi_common = m != nullptr;
+  if (m) memcpy(ctx->multi_common, m, 64);
+  return SGI_OK;
+}
+
 int sgi_set_params(sgi_ctx* ctx, const sgi_params* p) {
   if (!ctx || !p) return SGI_ERR_INVALID;
   if (p->technique < 0 || p->technique > SGI_TECH_MULTI_HARD) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }

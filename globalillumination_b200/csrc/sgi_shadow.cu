@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
     accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
     count += accFactor;
   }
-  a.vis[o] = accShadow / count;
+  a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
 }
 
 __global__ void k_clear_rect(float* vis, int W, int rx0, int ry0, int rx1, int ry1) {
@@ -502,6 +502,7 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   for (int k = 0; k < 3; k++) a.lpos[k] = ctx->light_pos[k];
   const bool multi = ctx->params.technique == SGI_TECH_MULTI_HARD;
   const float* lm = ctx->h_light_mvp_b + (multi ? (size_t)(ctx->N - 1) * 16 : 0);
+  if (multi && ctx->has_multi_common) lm = ctx->multi_common;
   for (int k = 0; k < 16; k++) a.lmvp[k] = lm[k];
   a.pos4 = (const float4*)ctx->buf[SGI_BUF_GBUF_POS];
   a.nrm4 = (const float4*)ctx->buf[SGI_BUF_GBUF_NRM];

@@ -107,6 +107,12 @@ int sgh_app_set_rect(sgh_app* a, int32_t x0, int32_t y0, int32_t x1, int32_t y1)
   return 0;
 }
 
+int sgh_app_set_light_shard(sgh_app* a, int32_t rank, int32_t world) {
+  if (!a || world <= 0 || rank < 0 || rank >= world) return -1;
+  a->app.lightShardRank = rank; a->app.lightShardWorld = world;
+  return 0;
+}
+
 // technique names = the reference's menu entries / ShadowParams flags
 int sgh_app_set_technique(sgh_app* a, const char* name) {
   if (!a || !name) return -1;

@@ -125,6 +125,7 @@ int ShadowApp::pushParams(int tech) {
   q.max_search = p.maxSearch; q.depth_threshold = p.depthThreshold;
   q.sv_depth_func = svDepthFunc; q.sv_infinity = svInfinity;
   q.rect_x0 = rect[0]; q.rect_y0 = rect[1]; q.rect_x1 = rect[2]; q.rect_y1 = rect[3];
+  q.multi_partial = (tech == SGI_TECH_MULTI_HARD && lightShardWorld > 1) ? 1 : 0;
   int rc = sgi_set_params(ctx, &q);
   return rc ? fail(rc, "sgi_set_params") : 0;
 }
@@ -199,19 +200,28 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
   updateLight();
   int n = shadowParams.numberOfSamples;
   if (n <= 0 || n > 1024) { err = "renderMonteCarlo: numberOfSamples must be in 1..1024"; return SGI_ERR_INVALID; }
-  std::vector<float> mvp((size_t)n * 16), mvpb((size_t)n * 16);
+  // light shard: this process builds and samples only lights s = rank (mod world); the shader's common
+  // term still comes from the LAST light of the whole set, as in the reference (main.cpp:790,806)
+  std::vector<float> mvp, mvpb;
   Mat4 model = modelMatrix();
   FrameMatrices f;
   for (int s = 0; s < n; s++) {
+    bool mine = (s % lightShardWorld) == lightShardRank;
+    if (!mine && s != n - 1) continue;
     Vec3 e = uniformSample(lightEye, shadowParams.lightSourceSize, n, s), a = uniformSample(lightAt, shadowParams.lightSourceSize, n, s);
     f = composeFrame(e, a, lightUp, cameraEye, cameraAt, cameraUp, model, windowWidth, windowHeight, shadowParams.shadowMapWidth,
                      shadowParams.shadowMapHeight);
-    std::memcpy(&mvp[(size_t)s * 16], f.lightMVP.m, 64);
-    std::memcpy(&mvpb[(size_t)s * 16], f.lightMVPBiased.m, 64);
+    if (mine) {
+      mvp.insert(mvp.end(), f.lightMVP.m, f.lightMVP.m + 16);
+      mvpb.insert(mvpb.end(), f.lightMVPBiased.m, f.lightMVPBiased.m + 16);
+    }
   }
+  if (mvp.empty()) { err = "renderMonteCarlo: this rank owns no light (more ranks than lights)"; return SGI_ERR_INVALID; }
   Vec3 shading = mul3(rotate(180.0f, Vec3{0, 1, 0}), lightEye);
-  rc = sgi_set_lights(ctx, n, mvp.data(), mvpb.data(), &shading.x, shadowParams.shadowMapWidth, shadowParams.shadowMapHeight);
+  rc = sgi_set_lights(ctx, (int)(mvp.size() / 16), mvp.data(), mvpb.data(), &shading.x, shadowParams.shadowMapWidth, shadowParams.shadowMapHeight);
   if (rc) return fail(rc, "sgi_set_lights");
+  rc = sgi_set_multi_light_common(ctx, lightShardWorld > 1 ? f.lightMVPBiased.m : nullptr);   // f = light n-1 here
+  if (rc) return fail(rc, "sgi_set_multi_light_common");
   if ((rc = pushParams(SGI_TECH_MULTI_HARD))) return rc;
   if ((rc = sgi_render_shadow_map(ctx))) return fail(rc, "sgi_render_shadow_map");
   rc = sgi_compute_visibility(ctx);

@@ -95,6 +95,7 @@ class ShadowApp {
   int svInfinity = 100;           // ShadowVolumes/src/main.cpp:469
   int svDepthFunc = SGI_DEPTH_LEQUAL;
   int rect[4] = {0, 0, 0, 0};     // multi-GPU screen tile (empty = whole window)
+  int lightShardRank = 0, lightShardWorld = 1;   // multi-GPU many-light: this process owns lights l = rank (mod world)
 
  private:
   int fail(int rc, const char* where);

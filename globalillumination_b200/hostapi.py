@@ -13,7 +13,7 @@ PROGRAM = {"shadow_mapping": 0, "soft_shadow_mapping": 1, "shadow_volumes": 2}
 EXPORTS = [
     "sgh_last_error", "sgh_scene_load", "sgh_scene_free", "sgh_scene_counts", "sgh_scene_copy", "sgh_scene_views",
     "sgh_scene_substitutions", "sgh_frame_matrices", "sgh_app_create", "sgh_app_destroy", "sgh_app_error", "sgh_app_context",
-    "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect",
+    "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
     "sgh_app_render_shadow_volumes", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
@@ -144,6 +144,9 @@ class App:
 
     def set_rect(self, x0, y0, x1, y1):
         self._ck(self.L.sgh_app_set_rect(self.h, x0, y0, x1, y1))
+
+    def set_light_shard(self, rank, world):
+        self._ck(self.L.sgh_app_set_light_shard(self.h, int(rank), int(world)))
 
     def set_technique(self, name):
         self._ck(self.L.sgh_app_set_technique(self.h, name.encode()))

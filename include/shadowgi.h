@@ -85,6 +85,8 @@ typedef struct sgi_params {
   int32_t rect_x0, rect_y0, rect_x1, rect_y1;  /* screen rectangle this context evaluates in
                                      sgi_compute_visibility / shadow-volume counting (multi-GPU
                                      screen tiles); an empty rectangle means the whole screen */
+  int32_t multi_partial;          /* SGI_TECH_MULTI_HARD on a light shard: 1 = write the un-normalised sum
+                                     over this context's lights (ranks are summed, then divided by the total) */
 } sgi_params;
 
 typedef enum sgi_buffer {
@@ -136,6 +138,11 @@ int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const 
  *   light_pos_shading  the `lightPosition` uniform: light eye rotated 180 deg about Y (main.cpp:283) */
 int sgi_set_lights(sgi_ctx* ctx, int32_t num_lights, const float* light_mvp, const float* light_mvp_biased,
                    const float light_pos_shading[3], int32_t map_width, int32_t map_height);
+
+/* many-light shards: the shader's common 3x4 term comes from the LAST light of the whole set
+ * (SoftShadowMapping/src/main.cpp:790,806); a rank that owns a subset passes that matrix (bias*lightMVP) here.
+ * NULL restores the default (last light given to sgi_set_lights). */
+int sgi_set_multi_light_common(sgi_ctx* ctx, const float light_mvp_biased[16]);
 
 int sgi_set_params(sgi_ctx* ctx, const sgi_params* params);
 void sgi_default_params(sgi_params* params);

@@ -46,6 +46,7 @@ int sgh_app_scene_counts(sgh_app* a, int32_t* nv, int32_t* nt);
 int sgh_app_scene_copy(sgh_app* a, float* xyz, float* nrm, int32_t* idx);
 int sgh_app_configure(sgh_app* a, int32_t W, int32_t H, int32_t SW, int32_t SH);
 int sgh_app_set_rect(sgh_app* a, int32_t x0, int32_t y0, int32_t x1, int32_t y1);
+int sgh_app_set_light_shard(sgh_app* a, int32_t rank, int32_t world);   /* many-light: own lights l = rank (mod world) */
 int sgh_app_set_technique(sgh_app* a, const char* name);
 int sgh_app_set_int(sgh_app* a, const char* name, int32_t v);
 int sgh_app_set_float(sgh_app* a, const char* name, float v);

@@ -69,6 +69,7 @@ typedef struct orc_params {
   int32_t sv_depth_func;
   int32_t sv_infinity;
   int32_t rect_x0, rect_y0, rect_x1, rect_y1;   /* screen rectangle to evaluate        */
+  int32_t multi_partial;         /* many-light: write the un-normalised sum over the given lights */
 } orc_params;
 
 /* per-frame camera-side uniforms of the full-screen shadow passes */

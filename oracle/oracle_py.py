@@ -33,6 +33,7 @@ class Params(C.Structure):
         ("polygon_offset_factor", C.c_float), ("polygon_offset_units", C.c_float),
         ("sv_depth_func", C.c_int32), ("sv_infinity", C.c_int32),
         ("rect_x0", C.c_int32), ("rect_y0", C.c_int32), ("rect_x1", C.c_int32), ("rect_y1", C.c_int32),
+        ("multi_partial", C.c_int32),
     ]
 
 
@@ -44,7 +45,7 @@ def default_params(technique="hard", S=1024, **kw):
         kernel_order=7, penumbra_size=1, blocker_search_size=7, kernel_size=15, light_source_radius=8,
         max_search=16, depth_threshold=0.0, z_near=1, z_far=1000,
         polygon_offset_factor=4.0, polygon_offset_units=20.0,
-        sv_depth_func=DEPTH_LEQUAL, sv_infinity=100, rect_x0=0, rect_y0=0, rect_x1=0, rect_y1=0,
+        sv_depth_func=DEPTH_LEQUAL, sv_infinity=100, rect_x0=0, rect_y0=0, rect_x1=0, rect_y1=0, multi_partial=0,
     )
     for k, v in kw.items():
         if not hasattr(p, k):

@@ -622,6 +622,6 @@ void orc_visibility_multi(const orc_params* p, const float m[16], int N, const f
         accShadow += ((sz <= dfl) ? 1.0f : p->shadow_intensity) * accFactor;
         count += accFactor;
       }
-      vis[o] = accShadow / count;
+      vis[o] = p->multi_partial ? accShadow : accShadow / count;
     }
 }

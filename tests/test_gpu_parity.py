@@ -183,3 +183,36 @@ def test_empty_and_degenerate_inputs(ctx):
     with pytest.raises(capi.SgiError):
         c2.render_shadow_map()
     c2.close()
+
+
+def test_many_light_shards_sum_to_the_single_context_result(ctx):
+    """Light sharding: partial sums of two shards (common matrix = last light of the WHOLE set) add up
+    bit-exactly to the un-sharded result, and each shard matches the oracle."""
+    sc = util.scene("teapot")
+    W, H, S, n_l = 256, 144, 128, 6
+    fm = util.frame(sc, W, H, S)
+    mvp, mvpb = util.multi_lights(sc, n_l, 16, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    po, pg = util.params_pair("multi_hard", S)
+    ctx.set_multi_light_common(None)
+    ctx.set_lights(mvp, mvpb, fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    full = ctx.read("visibility")
+    pos = ctx.read("gbuf_pos")
+    total = np.zeros_like(full)
+    po, pg = util.params_pair("multi_hard", S, multi_partial=1)
+    for r in range(2):
+        own = list(range(r, n_l, 2))
+        ctx.set_lights(mvp[own], mvpb[own], fm["light_pos_shading"], S, S)
+        ctx.set_multi_light_common(mvpb[-1])
+        ctx.set_params(pg)
+        ctx.render_shadow_map(); ctx.compute_visibility()
+        part = ctx.read("visibility")
+        maps = ctx.read("shadow_map")
+        part_o = O.visibility_multi(po, mvpb[-1], mvpb[own][:, 12:16], pos, maps)
+        assert util.bits_equal(part, part_o), util.describe_diff(part, part_o)
+        total += part
+    ctx.set_multi_light_common(None)
+    assert util.bits_equal(total / np.float32(n_l), full), util.describe_diff(total / np.float32(n_l), full)
