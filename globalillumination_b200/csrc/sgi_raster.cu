@@ -53,13 +53,15 @@ __device__ __forceinline__ CV clip_lerp(const CV& a, const CV& b, float da, floa
   return r;
 }
 
-__device__ int clip_polygon(CV* poly, int n) {
+__device__ int clip_polygon(CV* poly, int n, bool& clipped) {
   CV tmp[10];
   float d[10];
+  clipped = false;
   for (int p = 0; p < 6; p++) {
     bool any_out = false;
     for (int i = 0; i < n; i++) { d[i] = plane_dist(poly[i], p); if (!(d[i] >= 0.0f)) any_out = true; }
     if (!any_out) continue;
+    clipped = true;
     int m = 0;
     for (int i = 0; i < n; i++) {
       int j = (i + 1 == n) ? 0 : i + 1;
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
     }
     if (o0 == 3 || o1 == 3 || o2 == 3 || o3 == 3 || o4 == 3 || o5 == 3) { invalidate(&a.rec[t]); return; }
   }
-  int n = clip_polygon(poly, 3);
+  bool was_clipped;
+  int n = clip_polygon(poly, 3, was_clipped);
   if (n < 3) { invalidate(&a.rec[t]); return; }
   float hw = (float)a.W * 0.5f, hh = (float)a.H * 0.5f;
   int32_t X[10], Y[10];
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
     if (px0 > px1 || py0 > py1) { invalidate(&a.rec[slot]); continue; }
     r.px0 = (int16_t)px0; r.py0 = (int16_t)py0; r.px1 = (int16_t)px1; r.py1 = (int16_t)py1;
     r.prim_front = ((t * 8 + (f - 1)) << 1) | front;
-    r.pad0 = r.pad1 = 0;
+    r.pad0 = was_clipped ? 1 : 0;      // 0: attributes come straight from the source vertices (order in pad1)
+    r.pad1 = (id1 == 1) ? 0 : 1;        // unclipped only: 1 = vertices 1 and 2 were swapped to make the record CCW
     a.rec[slot] = r;
     if (a.attr) {
       SgiRecAttr q;
@@ -552,17 +556,24 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       const float q0 = ((float)E0 * r.ia) * at.iw[0];
       const float q1 = ((float)E1 * r.ia) * at.iw[1];
       const float q2 = ((float)E2 * r.ia) * at.iw[2];
-      const float qs = (q0 + q1) + q2;
+      const float iq = 1.0f / ((q0 + q1) + q2);
       float outv[6];
+      // unclipped triangles (pad0 == 0) interpolate the source vertices directly, in the record's CCW order
+      const int j1 = r.pad1 ? i2 : i1, j2 = r.pad1 ? i1 : i2;
 #pragma unroll
       for (int c = 0; c < 6; c++) {
         const float* src = (c < 3) ? a.xyz : a.nrm;
         const int cc = (c < 3) ? c : c - 3;
-        const float s0 = src[3 * (size_t)i0 + cc], s1 = src[3 * (size_t)i1 + cc], s2 = src[3 * (size_t)i2 + cc];
-        const float A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
-        const float A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
-        const float A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
-        outv[c] = ((q0 * A0 + q1 * A1) + q2 * A2) / qs;
+        float A0, A1, A2;
+        if (r.pad0 == 0) {
+          A0 = src[3 * (size_t)i0 + cc]; A1 = src[3 * (size_t)j1 + cc]; A2 = src[3 * (size_t)j2 + cc];
+        } else {
+          const float s0 = src[3 * (size_t)i0 + cc], s1 = src[3 * (size_t)i1 + cc], s2 = src[3 * (size_t)i2 + cc];
+          A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
+          A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
+          A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
+        }
+        outv[c] = ((q0 * A0 + q1 * A1) + q2 * A2) * iq;
       }
       a.depth[o] = __uint_as_float((unsigned int)(key >> 32));
       a.pos4[o] = make_float4(outv[0], outv[1], outv[2], 1.0f);

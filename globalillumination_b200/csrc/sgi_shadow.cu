@@ -22,6 +22,9 @@ struct VisArgs {
   float sx, sy;
   float pcf_off[SGI_MAX_PCF_TAPS]; int pcf_n;
   float rpcf_off[SGI_MAX_PCF_TAPS]; int rpcf_n;
+  // pixel-independent parts of the tap coordinates, evaluated once on the host with the shader's own fp32 operations:
+  float pcf_du[SGI_MAX_PCF_TAPS], pcf_dv[SGI_MAX_PCF_TAPS];   // pcf_off[k]*incrWidth, pcf_off[k]*incrHeight   (Shadow.frag:104)
+  float bs_q[SGI_MAX_PCF_TAPS]; int bs_w0, bs_n;              // (float(w)*blockerSearchWidth)/filterWidth      (PlausibleSoftShadow.frag:180)
   const float4* trans; int N; size_t layer;
 };
 
@@ -77,16 +80,15 @@ __device__ __forceinline__ float tap(const Smap& s, int row_off, int col) {
 // N = taps per axis known at compile time (0 = run-time count, columns kept in local memory)
 template <int N>
 __device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, float4 c) {
-  const float incrWidth = 1.0f / (float)a.SW, incrHeight = 1.0f / (float)a.SH;
   const int n = N ? N : a.pcf_n;
   if (n <= 0) return 1.0f;
   int rows[N ? N : SGI_MAX_PCF_TAPS];
 #pragma unroll
   for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
-    if (ih < n) { int r = axis_texel(c.y + a.pcf_off[ih] * incrHeight, s.fh); rows[ih] = r < 0 ? -1 : r * s.w; }
+    if (ih < n) { int r = axis_texel(c.y + a.pcf_dv[ih], s.fh); rows[ih] = r < 0 ? -1 : r * s.w; }
   float illum = 0.0f;
   for (int iw = 0; iw < n; iw++) {                     // Shadow.frag:98-99: w outer, h inner
-    const int col = axis_texel(c.x + a.pcf_off[iw] * incrWidth, s.fw);
+    const int col = axis_texel(c.x + a.pcf_du[iw], s.fw);
 #pragma unroll
     for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
       if (ih < n) { if (c.z <= tap(s, rows[ih], col)) illum += 1.0f; else illum += a.p.shadow_intensity; }
@@ -104,17 +106,16 @@ __device__ __forceinline__ float pcss_t(const VisArgs& a, const Smap& s, float4 
   float bsw;
   if ((float)a.SW <= 1024.0f) bsw = (float)p.light_source_radius / (float)a.SW;
   else bsw = (float)p.light_source_radius / 1024.0f;
-  const float filterWidth = ((float)p.blocker_search_size - 1.0f) * 0.5f;
   {
-    // `for(int w = -filterWidth; w <= filterWidth; w++)`: the int start truncates toward zero (A.7)
-    const int w0 = (int)(-filterWidth);
-    const int nb = NB ? NB : ((filterWidth >= 0.0f) ? (int)filterWidth - w0 + 1 : 0);
+    // `for(int w = -filterWidth; w <= filterWidth; w++)`: the int start truncates toward zero (A.7).  The offsets
+    // (float(w)*blockerSearchWidth)/filterWidth do not depend on the pixel: a.bs_q[] holds them (same fp32 ops, host)
+    const int nb = NB ? NB : a.bs_n;
     int cols[NB ? NB : SGI_MAX_PCF_TAPS];
 #pragma unroll
     for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
-      if (k < nb) cols[k] = axis_texel(c.x + ((float)(w0 + k) * bsw) / filterWidth, s.fw);
-    for (int h = w0; (float)h <= filterWidth; h++) {
-      const int r = axis_texel(c.y + ((float)h * bsw) / filterWidth, s.fh);
+      if (k < nb) cols[k] = axis_texel(c.x + a.bs_q[k], s.fw);
+    for (int j = 0; j < nb; j++) {
+      const int r = axis_texel(c.y + a.bs_q[j], s.fh);
       const int row = r < 0 ? -1 : r * s.w;
 #pragma unroll
       for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
@@ -518,6 +519,24 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   a.pcf_n = ctx->pcf_n; a.rpcf_n = ctx->rpcf_n;
   for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
   a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
+  {
+    volatile float incrWidth = 1.0f / (float)ctx->SW, incrHeight = 1.0f / (float)ctx->SH;      // Shadow.frag:89-90
+    for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) {
+      volatile float du = ctx->pcf_off[k] * incrWidth, dv = ctx->pcf_off[k] * incrHeight;
+      a.pcf_du[k] = du; a.pcf_dv[k] = dv;
+    }
+    // PlausibleSoftShadow.frag:172-180
+    volatile float bsw = ((float)ctx->SW <= 1024.0f) ? (float)ctx->params.light_source_radius / (float)ctx->SW
+                                                     : (float)ctx->params.light_source_radius / 1024.0f;
+    volatile float filterWidth = ((float)ctx->params.blocker_search_size - 1.0f) * 0.5f;
+    a.bs_w0 = (int)(-filterWidth);
+    a.bs_n = 0;
+    for (int w = a.bs_w0; (float)w <= filterWidth && a.bs_n < SGI_MAX_PCF_TAPS; w++) {
+      volatile float num = (float)w * bsw;
+      volatile float q = num / filterWidth;
+      a.bs_q[a.bs_n++] = q;
+    }
+  }
 
   int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
   if (rw <= 0 || rh <= 0) return SGI_OK;
@@ -537,7 +556,7 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL, st);
   const sgi_params& P = ctx->params;
   // tap counts the float/int loops of the shaders produce for the current parameters
-  const int nb_taps = 2 * (int)(((float)P.blocker_search_size - 1.0f) * 0.5f) + 1;
+  const int nb_taps = a.bs_n;
   const int nk_taps = 2 * (int)(((float)P.kernel_size - 1.0f) * 0.5f) + 1;
   switch (P.technique) {
     case SGI_TECH_HARD: k_visibility<SGI_TECH_HARD, 0, 0><<<grid, block, 0, st>>>(a); break;

@@ -28,6 +28,7 @@ typedef struct {
   int64_t area2;
   float zoff;                /* polygon offset (0 if disabled)                         */
   int32_t front;             /* gl_FrontFacing                                         */
+  int32_t clipped;           /* 0: the source triangle itself (attributes taken from its vertices as they are) */
   int32_t prim;              /* source triangle * 8 + fan index                        */
   int32_t px0, py0, px1, py1;/* inclusive pixel bbox, clamped to the viewport          */
 } SubTri;
@@ -58,13 +59,15 @@ static inline CV clip_lerp(const CV* a, const CV* b, float da, float db) {
   return r;
 }
 
-static int clip_polygon(CV* poly, int n) {
+static int clip_polygon(CV* poly, int n, int* clipped) {
   CV tmp[MAXPOLY];
+  *clipped = 0;
   for (int p = 0; p < 6; p++) {
     int any_out = 0;
     float d[MAXPOLY];
     for (int i = 0; i < n; i++) { d[i] = plane_dist(&poly[i], p); if (!(d[i] >= 0.0f)) any_out = 1; }
     if (!any_out) continue;
+    *clipped = 1;
     int m = 0;
     for (int i = 0; i < n; i++) {
       int j = (i + 1 == n) ? 0 : i + 1;
@@ -113,7 +116,8 @@ static int setup_triangle(const float* mvp, const float* p0, const float* p1, co
     }
     for (int p = 0; p < 6; p++) if (o[p] == 3) return 0;
   }
-  int n = clip_polygon(poly, 3);
+  int was_clipped;
+  int n = clip_polygon(poly, 3, &was_clipped);
   if (n < 3) return 0;
   float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
   int32_t X[MAXPOLY], Y[MAXPOLY];
@@ -150,6 +154,7 @@ static int setup_triangle(const float* mvp, const float* p0, const float* p1, co
     s->ia = 1.0f / (float)area2;
     s->z0 = Z[id[0]]; s->dz1 = Z[id[1]] - Z[id[0]]; s->dz2 = Z[id[2]] - Z[id[0]];
     s->prim = tri * 8 + (f - 1);
+    s->clipped = was_clipped;
     s->zoff = 0.0f;
     if (use_offset) {
       double dY1 = (double)(s->Y[1] - s->Y[0]), dY2 = (double)(s->Y[2] - s->Y[0]);
@@ -274,10 +279,17 @@ int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t*
       if (y0 > y1) continue;
       int t = s->prim >> 3;
       const int32_t* ix = idx + 3 * (size_t)t;
-      /* attributes of the (possibly clipped) sub-triangle's vertices */
+      /* attributes of the sub-triangle's vertices: the source vertices themselves (in the record's CCW order) when
+         nothing was clipped, otherwise their barycentric combination */
       float A[3][6];
       for (int v = 0; v < 3; v++)
         for (int c = 0; c < 3; c++) {
+          if (!s->clipped) {
+            int src = s->bary[v][0] == 1.0f ? 0 : (s->bary[v][1] == 1.0f ? 1 : 2);
+            A[v][c] = xyz[3 * (size_t)ix[src] + c];
+            A[v][3 + c] = nrm[3 * (size_t)ix[src] + c];
+            continue;
+          }
           A[v][c] = (s->bary[v][0] * xyz[3 * (size_t)ix[0] + c] + s->bary[v][1] * xyz[3 * (size_t)ix[1] + c]) +
                     s->bary[v][2] * xyz[3 * (size_t)ix[2] + c];
           A[v][3 + c] = (s->bary[v][0] * nrm[3 * (size_t)ix[0] + c] + s->bary[v][1] * nrm[3 * (size_t)ix[1] + c]) +
@@ -294,10 +306,10 @@ int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t*
           float q0 = ((float)E[0] * s->ia) * s->iw[0];
           float q1 = ((float)E[1] * s->ia) * s->iw[1];
           float q2 = ((float)E[2] * s->ia) * s->iw[2];
-          float qs = (q0 + q1) + q2;
+          float iq = 1.0f / ((q0 + q1) + q2);
           for (int c = 0; c < 3; c++) {
-            pos4[4 * o + c] = ((q0 * A[0][c] + q1 * A[1][c]) + q2 * A[2][c]) / qs;
-            nrm4[4 * o + c] = ((q0 * A[0][3 + c] + q1 * A[1][3 + c]) + q2 * A[2][3 + c]) / qs;
+            pos4[4 * o + c] = ((q0 * A[0][c] + q1 * A[1][c]) + q2 * A[2][c]) * iq;
+            nrm4[4 * o + c] = ((q0 * A[0][3 + c] + q1 * A[1][3 + c]) + q2 * A[2][3 + c]) * iq;
           }
           pos4[4 * o + 3] = 1.0f;
           nrm4[4 * o + 3] = s->front ? 1.0f : 0.0f;
