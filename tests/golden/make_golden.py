@@ -21,6 +21,17 @@ from oracle import oracle_py as O  # noqa: E402
 
 SCENES = {"teapot": "Configs/Teapot.txt", "door": "Configs/Door.txt", "dragon": "Configs/Dragon.txt",
           "raptor": "Configs/Raptor.txt"}
+# configs whose asset list is only partly present in the mount: the present objects of the config, same directives
+PARTIAL = {
+    # Configs/TreeWithLeaves.txt without the missing TreeSub1.obj (config c4)
+    "tree": ["o OBJ/TreeWithLeaves/TreeSub0.obj", "s 2.0 2.0 2.0", "t 0.0 -7.0 9.0", "+",
+             "o OBJ/TreeWithLeaves/plane.obj", "m OBJ/TreeWithLeaves/white.png", "s 60.0 1.0 40.0", "t 0.0 -8.0 0.0", "+",
+             "ve 0.0 41.0 -57.0", "va 0.0 16.0 -17.0", "le 10.0 130.0 100.0", "la 0.0 0.0 0.0", "d 0.000025"],
+    # Configs/SanDiego.txt without the two missing sphere.obj objects (config c5)
+    "sandiego": ["o OBJ/SanDiego/building.obj", "s 30.0 30.0 30.0", "t -10.0 -8.0 0.0", "r 0.0 90.0 0.0", "c 1.0 1.0 0.5", "+",
+                 "o OBJ/SanDiego/plane.obj", "m OBJ/SanDiego/white.png", "s 60.0 1.0 40.0", "t 0.0 -8.0 0.0", "+",
+                 "ve 0.0 41.0 -50.0", "va 0.0 16.0 -10.0", "le 10.0 130.0 100.0", "la 0.0 0.0 0.0", "d 0.000025"],
+}
 
 SHADER_OF = {
     "hard": ("shadow", dict(naive=1, bilinearPCF=1)),
@@ -70,6 +81,14 @@ def main():
     for name, cfg in SCENES.items():
         sc = O.ref_load_scene(cfg)
         scenes[name] = sc
+        np.savez_compressed(os.path.join(HERE, f"scene_{name}.npz"), **sc)
+        print(name, sc["xyz"].shape, sc["idx"].shape)
+    import tempfile
+    for name, lines in PARTIAL.items():
+        cfg = os.path.join(tempfile.mkdtemp(), name + ".txt")
+        with open(cfg, "w") as f:
+            f.write("\n".join(lines))
+        sc = O.ref_load_scene(cfg)
         np.savez_compressed(os.path.join(HERE, f"scene_{name}.npz"), **sc)
         print(name, sc["xyz"].shape, sc["idx"].shape)
 

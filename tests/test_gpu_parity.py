@@ -216,3 +216,120 @@ def test_many_light_shards_sum_to_the_single_context_result(ctx):
         total += part
     ctx.set_multi_light_common(None)
     assert util.bits_equal(total / np.float32(n_l), full), util.describe_diff(total / np.float32(n_l), full)
+
+
+# ---- BASELINE.json configs at (or near) their full sizes -------------------------------------------------------------
+def _full_frame(ctx, sc, W, H, S, tech, **kw):
+    po, pg = util.params_pair(tech, S, depth_threshold=float(sc["depth_threshold"]), **kw)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    return po, fm
+
+
+def test_config_c3_dragon_rbsm_4k(ctx):
+    """c3: Dragon, 3840x2160, 4096^2 map, RBSM conservative + non-conservative: every buffer bit-exact vs the oracle."""
+    sc = util.scene("dragon")
+    W, H, S = 3840, 2160, 4096
+    po, fm = _full_frame(ctx, sc, W, H, S, "rbsm_noncons")
+    sm, pos, nrm = ctx.read("shadow_map")[0], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm")
+    sm_o = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    assert util.bits_equal(sm, sm_o), util.describe_diff(sm, sm_o)
+    pos_o, nrm_o, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    assert util.bits_equal(pos, pos_o) and util.bits_equal(nrm, nrm_o)
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis = ctx.read("visibility")
+    vis_o = O.visibility(po, cam, fm["light_mvp_b"], pos, nrm, sm)
+    assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+    po2, pg2 = util.params_pair("rbsm_cons", S, depth_threshold=float(sc["depth_threshold"]))
+    ctx.set_params(pg2); ctx.compute_visibility()
+    vis2, vis2_o = ctx.read("visibility"), O.visibility(po2, cam, fm["light_mvp_b"], pos, nrm, sm)
+    assert util.bits_equal(vis2, vis2_o), util.describe_diff(vis2, vis2_o)
+    # revectorisation only moves shadow boundaries: both variants agree with the plain hard test away from edges
+    po3, pg3 = util.params_pair("hard", S)
+    ctx.set_params(pg3); ctx.compute_visibility()
+    hard = ctx.read("visibility")
+    assert ((vis != hard).mean() < 0.02) and ((vis2 != hard).mean() < 0.02) and (vis2 <= hard + 1e-6).all()   # conservative only adds shadow
+
+
+def test_config_c2_sponza_full_size_through_the_host(ctx):
+    """c2: the bench workload at full size through the C++ host (SceneLoader -> ShadowApp), PCSS and PCF, vs the oracle."""
+    from globalillumination_b200 import hostapi, scenes
+    cfg = scenes.write_config("c2_sponza")
+    w = scenes.WORKLOADS["c2_sponza"]
+    W, H, S = w["W"], w["H"], w["S"]
+    app = hostapi.App(0)
+    try:
+        app.load_scene(cfg); app.configure(W, H, S); app.set_technique("pcss"); app.set(**w["params"])
+        app.display("soft_shadow_mapping")
+        c = app.context()
+        vis, sm, pos, nrm = c.read("visibility"), c.read("shadow_map")[0], c.read("gbuf_pos"), c.read("gbuf_nrm")
+        sc = hostapi.load_scene(cfg)
+        fm = util.frame(sc, W, H, S)
+        sm_o = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+        pos_o, nrm_o, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+        assert util.bits_equal(sm, sm_o), util.describe_diff(sm, sm_o)
+        assert util.bits_equal(pos, pos_o), util.describe_diff(pos, pos_o)
+        assert util.bits_equal(nrm, nrm_o), util.describe_diff(nrm, nrm_o)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        vis_o = O.visibility(O.default_params("pcss", S), cam, fm["light_mvp_b"], pos_o, nrm_o, sm_o)
+        assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+        app.set_technique("pcf"); app.display("shadow_mapping")
+        vis_pcf = c.read("visibility")
+        vis_pcf_o = O.visibility(O.default_params("pcf", S), cam, fm["light_mvp_b"], pos_o, nrm_o, sm_o)
+        assert util.bits_equal(vis_pcf, vis_pcf_o), util.describe_diff(vis_pcf, vis_pcf_o)
+        assert 0.3 < (vis_pcf_o == 1).mean() < 0.9
+    finally:
+        app.close()
+
+
+def test_config_c4_tree_shadow_volumes(ctx):
+    """c4: TreeWithLeaves (the present half of it), 640x480 as in the reference: signed z-pass counts and 8-bit stencil."""
+    sc = util.scene("tree")
+    W, H, S = 640, 480, 64
+    po, pg = util.params_pair("hard", S)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_gbuffer(); ctx.compute_shadow_volume(sc["light_eye"])
+    cnt, st, dep = ctx.read("sv_count"), ctx.read("sv_stencil"), ctx.read("cam_depth")
+    pxyz_o, pidx_o = O.sv_build_prisms(sc["xyz"], sc["nrm"], sc["idx"], sc["light_eye"], 100)
+    assert util.bits_equal(ctx.read("sv_prism_xyz"), pxyz_o) and np.array_equal(ctx.read("sv_prism_idx"), pidx_o)
+    cnt_o, st_o = O.sv_count(pxyz_o, pidx_o, fm["cam_mvp"], W, H, dep, O.DEPTH_LEQUAL)
+    assert np.array_equal(cnt, cnt_o), util.describe_diff(cnt, cnt_o)
+    assert np.array_equal(st, st_o) and (st_o != 0).mean() > 0.01
+
+
+def test_config_c5_many_light_properties_at_full_size(ctx):
+    """c5 at full size (7680x4320, 16 x 8192^2 maps) is beyond what the oracle finishes in seconds: size-independent
+    properties instead.  (i) every light's map equals the same light rendered alone; (ii) the 16-light result equals the
+    mean of 16 single-light hard results computed by the same kernels; (iii) value set and background."""
+    sc = util.scene("sandiego")
+    W, H, S, n_l = 7680, 4320, 8192, 16
+    fm = util.frame(sc, W, H, S)
+    mvp, mvpb = util.multi_lights(sc, n_l, 16, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    po, pg = util.params_pair("multi_hard", S)
+    ctx.set_multi_light_common(None)
+    ctx.set_lights(mvp, mvpb, fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    vis = ctx.read("visibility")
+    pos = ctx.read("gbuf_pos")
+    fg = pos[..., 0] != 0
+    assert (vis[~fg] == 0).all() and fg.mean() > 0.3
+    levels = np.unique(vis[fg])
+    assert set(np.round((levels - 0.25) / 0.75 * 16).astype(int)) <= set(range(17)) and len(levels) > 4   # k/16 lit lights
+    maps_crc = [int(np.bitwise_xor.reduce(m.view(np.uint32).ravel())) for m in ctx.read("shadow_map")]
+    # (i)+(ii) on a strip (keeps the single-light re-runs cheap): partial sums over shards of one light each
+    po1, pg1 = util.params_pair("multi_hard", S, multi_partial=1, rect_x0=0, rect_y0=2048, rect_x1=W, rect_y1=2048 + 256)
+    acc = np.zeros((256, W), np.float32)
+    for i in range(n_l):
+        ctx.set_lights(mvp[i:i + 1], mvpb[i:i + 1], fm["light_pos_shading"], S, S)
+        ctx.set_multi_light_common(mvpb[-1]); ctx.set_params(pg1)
+        ctx.render_shadow_map(); ctx.compute_visibility()
+        assert int(np.bitwise_xor.reduce(ctx.read("shadow_map")[0].view(np.uint32).ravel())) == maps_crc[i]
+        acc += ctx.read("visibility")[2048:2048 + 256]
+    ctx.set_multi_light_common(None)
+    assert util.bits_equal(acc / np.float32(n_l), vis[2048:2048 + 256])
+    # spot-check one light's map against the oracle at full size
+    m0 = O.raster_depth(sc["xyz"], sc["idx"], mvp[3], S, S)
+    assert int(np.bitwise_xor.reduce(m0.view(np.uint32).ravel())) == maps_crc[3]
