@@ -39,7 +39,7 @@ class SgiParams(C.Structure):
 EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
-    "sgi_compute_shadow_volume", "sgi_read", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
+    "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -182,6 +182,14 @@ class Context:
 
     def read_raw(self, which, host_ptr, nbytes):
         self._ck(self.lib.sgi_read(self.h, BUF[which], C.c_void_p(host_ptr), nbytes))
+
+    def read_async(self, which, host_ptr, nbytes):
+        t = C.c_int32()
+        self._ck(self.lib.sgi_read_async(self.h, BUF[which], C.c_void_p(host_ptr), C.c_size_t(nbytes), C.byref(t)))
+        return t.value
+
+    def read_wait(self, ticket):
+        self._ck(self.lib.sgi_read_wait(self.h, int(ticket)))
 
     def device_ptr(self, which):
         p, n = C.c_void_p(), C.c_size_t()

@@ -10,7 +10,11 @@
 
 static int ensure_buf(sgi_ctx* ctx, int which, size_t bytes) {
   if (ctx->buf[which] && ctx->buf_bytes[which] == bytes) return SGI_OK;
-  if (ctx->buf[which]) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->buf[which]); ctx->buf[which] = nullptr; }
+  if (ctx->buf[which]) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->buf[which]); ctx->buf[which] = nullptr;
+  }
   ctx->buf_bytes[which] = 0;
   if (bytes == 0) return SGI_OK;
   cudaError_t e = cudaMalloc(&ctx->buf[which], bytes);
@@ -63,6 +67,12 @@ static int check_overflow(sgi_ctx* ctx) {
 // pass (auxiliary stream) must not start before this point, but need not wait for anything queued later
 static void mark_gbuffer_use(sgi_ctx* ctx) { if (ctx->ev_fork) cudaEventRecord(ctx->ev_fork, ctx->stream); }
 
+void sgi_wait_reads_of(sgi_ctx* ctx, int which, cudaStream_t writer) {
+  int t = ctx->buf_read_ticket[which];
+  if (t >= 0 && ctx->read_pending[t]) cudaStreamWaitEvent(writer, ctx->read_done[t], 0);
+  ctx->buf_read_ticket[which] = -1;
+}
+
 // The G-buffer pass runs on the auxiliary stream so that it overlaps the light-view depth pass; every consumer of
 // its outputs (and every host-visible point) first makes the main stream wait for it.
 int sgi_join_gbuffer(sgi_ctx* ctx) {
@@ -112,6 +122,10 @@ int sgi_create(sgi_ctx** out, int device) {
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_gbuf_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   { const char* e = getenv("SGI_NO_OVERLAP"); ctx->overlap_passes = !(e && e[0] == '1'); }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
+  for (int k = 0; k < 4; k++) if (cudaEventCreateWithFlags(&ctx->read_done[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
+  for (int b = 0; b < SGI_BUF_COUNT_; b++) ctx->buf_read_ticket[b] = -1;
   sgi_default_params(&ctx->params);
   for (int p = 0; p < SGI_PASS_COUNT_; p++) {
     ctx->ev_n[p] = 0; ctx->pass_ms[p] = 0; ctx->pass_calls[p] = 0;
@@ -127,13 +141,17 @@ int sgi_destroy(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
-  void* ptrs[] = {ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->d_light_trans};
+  void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (SgiScratch& sc : ctx->scratch) sgi_raster_free(sc);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_gbuf_done) cudaEventDestroy(ctx->ev_gbuf_done);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+  for (int k = 0; k < 4; k++) if (ctx->read_done[k]) cudaEventDestroy(ctx->read_done[k]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);
   for (int p = 0; p < SGI_PASS_COUNT_; p++)
     for (int k = 0; k < SGI_EV_RING; k++) { if (ctx->ev[p][k][0]) cudaEventDestroy(ctx->ev[p][k][0]); if (ctx->ev[p][k][1]) cudaEventDestroy(ctx->ev[p][k][1]); }
@@ -156,26 +174,29 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   for (int64_t k = 0; k < (int64_t)T * 3; k++)
     if (idx[k] < 0 || idx[k] >= V) { ctx->err = "sgi_set_mesh: index out of range"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  // Upload into the geometry set the frame in flight is NOT using.  Ordering on the main stream is enough: the passes
+  // that read this set two uploads ago were queued on (or joined into) the main stream before this copy.
   sgi_join_gbuffer(ctx);
-  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (V != ctx->V) {
-    if (ctx->d_xyz) cudaFree(ctx->d_xyz);
-    if (ctx->d_nrm) cudaFree(ctx->d_nrm);
-    ctx->d_xyz = ctx->d_nrm = nullptr;
-    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_xyz, (size_t)(V > 0 ? V : 1) * 12));
-    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_nrm, (size_t)(V > 0 ? V : 1) * 12));
+  const int s = ctx->mesh_cur ^ 1;
+  if (V != ctx->mesh_V[s] || T != ctx->mesh_T[s]) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_xyz_set[s]) cudaFree(ctx->d_xyz_set[s]);
+    if (ctx->d_nrm_set[s]) cudaFree(ctx->d_nrm_set[s]);
+    if (ctx->d_idx_set[s]) cudaFree(ctx->d_idx_set[s]);
+    ctx->d_xyz_set[s] = ctx->d_nrm_set[s] = nullptr; ctx->d_idx_set[s] = nullptr;
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_xyz_set[s], (size_t)(V > 0 ? V : 1) * 12));
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_nrm_set[s], (size_t)(V > 0 ? V : 1) * 12));
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_idx_set[s], (size_t)(T > 0 ? T : 1) * 12));
+    ctx->mesh_V[s] = V; ctx->mesh_T[s] = T;
   }
-  if (T != ctx->T) {
-    if (ctx->d_idx) cudaFree(ctx->d_idx);
-    ctx->d_idx = nullptr;
-    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_idx, (size_t)(T > 0 ? T : 1) * 12));
-  }
-  ctx->V = V; ctx->T = T;
   if (V > 0) {
-    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_xyz, xyz, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
-    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm, nrm, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
+    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_xyz_set[s], xyz, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
+    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm_set[s], nrm, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (T > 0) SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_idx, idx, (size_t)T * 12, cudaMemcpyHostToDevice, ctx->stream));
+  if (T > 0) SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_idx_set[s], idx, (size_t)T * 12, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->mesh_cur = s;
+  ctx->d_xyz = ctx->d_xyz_set[s]; ctx->d_nrm = ctx->d_nrm_set[s]; ctx->d_idx = ctx->d_idx_set[s];
+  ctx->V = V; ctx->T = T;
   mark_gbuffer_use(ctx);
   ctx->gbuffer_valid = ctx->shadow_map_valid = false;
   return SGI_OK;
@@ -255,6 +276,7 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->d_idx || ctx->N <= 0) { ctx->err = "sgi_render_shadow_map: set mesh and lights first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  sgi_wait_reads_of(ctx, SGI_BUF_SHADOW_MAP, ctx->stream);
   int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP, ctx->stream);
   for (int l = 0; l < ctx->N; l++) {
     SgiRasterJob job;
@@ -287,6 +309,7 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
     if (ctx->gbuf_exposed) SGI_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
   }
+  sgi_wait_reads_of(ctx, SGI_BUF_GBUF_POS, st); sgi_wait_reads_of(ctx, SGI_BUF_GBUF_NRM, st); sgi_wait_reads_of(ctx, SGI_BUF_CAM_DEPTH, st);
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
   SgiRasterJob job;
   memset(&job, 0, sizeof(job));
@@ -314,6 +337,7 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   int rc = sgi_join_gbuffer(ctx);
   if (rc) return rc;
+  sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, ctx->stream);
   int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, ctx->stream);
   rc = sgi_shadow_run(ctx);
   if (rc) return rc;
@@ -333,6 +357,7 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_XYZ, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_IDX, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
   if ((rc = sgi_join_gbuffer(ctx))) return rc;
+  for (int b : {SGI_BUF_SV_COUNT, SGI_BUF_SV_STENCIL, SGI_BUF_SV_PRISM_XYZ, SGI_BUF_SV_PRISM_IDX}) sgi_wait_reads_of(ctx, b, ctx->stream);
   int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_VOLUME, ctx->stream);
   if ((rc = sgi_sv_extrude_run(ctx, light_pos, (float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ], (int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]))) return rc;
   SgiRasterJob job;
@@ -356,6 +381,8 @@ int sgi_synchronize(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   sgi_join_gbuffer(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (int k = 0; k < 4; k++) ctx->read_pending[k] = false;
   if (ctx->timing) sgi_timing_drain(ctx);
   return check_overflow(ctx);
 }
@@ -368,6 +395,30 @@ int sgi_read(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes) {
   SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->stream));
   mark_gbuffer_use(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_overflow(ctx);
+}
+
+int sgi_read_async(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes, int32_t* ticket) {
+  if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dst || !ticket) return SGI_ERR_INVALID;
+  if (!ctx->buf[which] || bytes > ctx->buf_bytes[which]) { ctx->err = "sgi_read_async: buffer not produced yet or size too large"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
+  const int t = ctx->read_seq++ & 3;
+  if (ctx->read_pending[t]) { SGI_CUDA(ctx, cudaEventSynchronize(ctx->read_done[t])); ctx->read_pending[t] = false; }   // back-pressure
+  SGI_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->stream));                 // the buffer's producers are all on / joined into the main stream
+  SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
+  SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  SGI_CUDA(ctx, cudaEventRecord(ctx->read_done[t], ctx->copy_stream));
+  ctx->read_pending[t] = true;
+  ctx->buf_read_ticket[which] = t;
+  *ticket = t;
+  return SGI_OK;
+}
+
+int sgi_read_wait(sgi_ctx* ctx, int32_t ticket) {
+  if (!ctx || ticket < 0 || ticket > 3) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->read_pending[ticket]) { SGI_CUDA(ctx, cudaEventSynchronize(ctx->read_done[ticket])); ctx->read_pending[ticket] = false; }
   return check_overflow(ctx);
 }
 

@@ -182,6 +182,24 @@ int sgh_app_display_e2e(sgh_app* a, int32_t program, int32_t result_buffer, void
   if (rc) g_err = sgi_last_error(a->app.context());
   return rc;
 }
+// Pipelined form of the above: returns once the frame is queued; the result lands in host_dst when
+// sgh_app_e2e_wait(ticket) returns.  The next frame can be issued in between (the GPU then copies frame k out while it
+// renders frame k+1; the geometry upload is double-buffered on the device).
+int sgh_app_display_e2e_async(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes, int32_t* ticket) {
+  if (!a || !ticket) return -1;
+  int rc = a->app.uploadScene();
+  if (rc) return rc;
+  if ((rc = sgh_app_display(a, program))) return rc;
+  rc = sgi_read_async(a->app.context(), result_buffer, host_dst, bytes, ticket);
+  if (rc) g_err = sgi_last_error(a->app.context());
+  return rc;
+}
+int sgh_app_e2e_wait(sgh_app* a, int32_t ticket) {
+  if (!a) return -1;
+  int rc = sgi_read_wait(a->app.context(), ticket);
+  if (rc) g_err = sgi_last_error(a->app.context());
+  return rc;
+}
 int sgh_app_step_animation(sgh_app* a, float delta) {   // idle(): animation += 6 (ShadowMapping/src/main.cpp:481)
   if (!a) return -1;
   a->app.animation += delta;

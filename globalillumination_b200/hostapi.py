@@ -16,7 +16,7 @@ EXPORTS = [
     "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
-    "sgh_app_render_shadow_volumes", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
+    "sgh_app_render_shadow_volumes", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
 ]
 
 _lib = None
@@ -35,6 +35,8 @@ def load():
         _lib.sgh_app_error.restype = C.c_char_p
         _lib.sgh_app_context.restype = C.c_void_p
         _lib.sgh_app_display_e2e.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]
+        _lib.sgh_app_display_e2e_async.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
+        _lib.sgh_app_e2e_wait.argtypes = [C.c_void_p, C.c_int32]
     return _lib
 
 
@@ -166,6 +168,14 @@ class App:
 
     def display_e2e(self, program, which, host_ptr, nbytes):
         self._ck(self.L.sgh_app_display_e2e(self.h, PROGRAM[program], capi.BUF[which], C.c_void_p(host_ptr), nbytes))
+
+    def display_e2e_async(self, program, which, host_ptr, nbytes):
+        t = C.c_int32()
+        self._ck(self.L.sgh_app_display_e2e_async(self.h, PROGRAM[program], capi.BUF[which], C.c_void_p(host_ptr), C.c_size_t(nbytes), C.byref(t)))
+        return t.value
+
+    def e2e_wait(self, ticket):
+        self._ck(self.L.sgh_app_e2e_wait(self.h, int(ticket)))
 
     def step_animation(self, delta=6.0):
         self._ck(self.L.sgh_app_step_animation(self.h, C.c_float(delta)))

@@ -160,6 +160,12 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]);
 /* results */
 int sgi_read(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes);          /* blocking D2H */
 int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** device_ptr, size_t* bytes);/* borrowed     */
+/* Non-blocking readback for frame pipelining: the copy runs on the context's copy stream as soon as the buffer's
+ * producers have finished, while later passes (the next frame) proceed; a pass that would overwrite the buffer waits
+ * for the copy on the device.  host_dst should be page-locked (sgi_alloc_host).  sgi_read_wait blocks the host until
+ * the copy with that ticket has landed (up to 4 may be outstanding). */
+int sgi_read_async(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes, int32_t* ticket);
+int sgi_read_wait(sgi_ctx* ctx, int32_t ticket);
 int sgi_synchronize(sgi_ctx* ctx);
 
 /* page-locked host memory for callers that want sgi_set_mesh / sgi_read to be true async DMA

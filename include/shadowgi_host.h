@@ -59,6 +59,8 @@ int sgh_app_render_monte_carlo(sgh_app* a);
 int sgh_app_render_shadow_volumes(sgh_app* a);
 int sgh_app_display(sgh_app* a, int32_t program);
 int sgh_app_display_e2e(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes);
+int sgh_app_display_e2e_async(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes, int32_t* ticket);
+int sgh_app_e2e_wait(sgh_app* a, int32_t ticket);
 int sgh_app_step_animation(sgh_app* a, float delta);
 
 /* procedural stand-ins (malloc'd arrays, release with sgh_free) */

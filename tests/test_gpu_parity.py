@@ -333,3 +333,35 @@ def test_config_c5_many_light_properties_at_full_size(ctx):
     # spot-check one light's map against the oracle at full size
     m0 = O.raster_depth(sc["xyz"], sc["idx"], mvp[3], S, S)
     assert int(np.bitwise_xor.reduce(m0.view(np.uint32).ravel())) == maps_crc[3]
+
+
+def test_pipelined_readback_and_double_buffered_mesh(ctx):
+    """sgi_read_async / sgi_read_wait with the next frame (a different mesh!) issued before the previous result is
+    awaited: every result must be the one of its own frame."""
+    import ctypes as C
+    lib = ctx.lib
+    W, H, S = 320, 180, 256
+    names = ["teapot", "door", "raptor", "teapot"]
+    bufs, ptrs = [], []
+    for _ in names:
+        p = C.c_void_p()
+        assert lib.sgi_alloc_host(C.byref(p), C.c_size_t(W * H * 4)) == 0
+        ptrs.append(p)
+        bufs.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), (H, W)))
+    expect, tickets = [], []
+    for k, name in enumerate(names):
+        sc = util.scene(name)
+        po, pg = util.params_pair("pcf", S)
+        fm = setup_frame(ctx, sc, W, H, S, pg)
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+        tickets.append(ctx.read_async("visibility", ptrs[k].value, W * H * 4))
+        sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+        pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        expect.append(O.visibility(po, cam, fm["light_mvp_b"], pos, nrm, sm))
+    for k in range(len(names)):
+        ctx.read_wait(tickets[k])
+        assert util.bits_equal(bufs[k].copy(), expect[k]), (k, util.describe_diff(bufs[k], expect[k]))
+    ctx.synchronize()
+    for p in ptrs:
+        lib.sgi_free_host(p)
