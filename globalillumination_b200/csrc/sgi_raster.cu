@@ -354,6 +354,32 @@ __device__ __forceinline__ float frag_z(float z0, float dz1, float dz2, float ia
   return z;
 }
 
+// Edge set-up of one triangle for repeated coverage tests.  With bias_e = (edge e owns its boundary ? 0 : 1) the
+// top-left rule `E > 0 || (E == 0 && owns)` is `E - bias >= 0`, and the bias rides for free as the addend of the
+// second wide multiply; all three tests collapse to one sign test of e0|e1|e2.  Exactly the integers cover() produces.
+struct EdgeSet {
+  int X0, Y0, X1, Y1, X2, Y2;
+  int dx0, dy0, dx1, dy1, dx2, dy2;
+  long long b0, b1, b2;
+  __device__ __forceinline__ void init(int x0, int y0, int x1, int y1, int x2, int y2) {
+    X0 = x0; Y0 = y0; X1 = x1; Y1 = y1; X2 = x2; Y2 = y2;
+    dx0 = X2 - X1; dy0 = Y2 - Y1; dx1 = X0 - X2; dy1 = Y0 - Y2; dx2 = X1 - X0; dy2 = Y1 - Y0;
+    b0 = (dy0 < 0 || (dy0 == 0 && dx0 < 0)) ? 0 : 1;
+    b1 = (dy1 < 0 || (dy1 == 0 && dx1 < 0)) ? 0 : 1;
+    b2 = (dy2 < 0 || (dy2 == 0 && dx2 < 0)) ? 0 : 1;
+  }
+  // pixel (px,py) [absolute pixels]: true if covered; E1/E2 are the un-biased edge values the depth needs
+  __device__ __forceinline__ bool test(int px, int py, long long& E1, long long& E2) const {
+    const int PX = px * SGI_SUBPIX + SGI_SUBPIX / 2, PY = py * SGI_SUBPIX + SGI_SUBPIX / 2;
+    const long long e0 = (long long)dx0 * (long long)(PY - Y1) - ((long long)dy0 * (long long)(PX - X1) + b0);
+    const long long e1 = (long long)dx1 * (long long)(PY - Y2) - ((long long)dy1 * (long long)(PX - X2) + b1);
+    const long long e2 = (long long)dx2 * (long long)(PY - Y0) - ((long long)dy2 * (long long)(PX - X0) + b2);
+    if ((e0 | e1 | e2) < 0) return false;
+    E1 = e1 + b1; E2 = e2 + b2;
+    return true;
+  }
+};
+
 // The tile payload in shared memory uses a row pitch of 72 words, so that the 8x4-pixel blocks the warps
 // work on (4 rows 8 banks apart) and full rows (flush) are both free of bank conflicts.
 #define SGI_PITCH (SGI_TILE + 8)
@@ -461,10 +487,12 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         if (w * h <= SGI_SMALL_TRI) {
           const float z0 = __uint_as_float(q1.z), dz1 = __uint_as_float(q1.w), dz2 = __uint_as_float(q2.x);
           const float ia = __uint_as_float(q2.y), zoff = __uint_as_float(q2.z);
+          EdgeSet es;
+          es.init(X0, Y0, X1, Y1, X2, Y2);
           for (int ly = ly0; ly <= ly1; ly++)
             for (int lx = lx0; lx <= lx1; lx++) {
-              long long E0, E1, E2;
-              if (!cover(X0, Y0, X1, Y1, X2, Y2, ox + lx, oy + ly, E0, E1, E2)) continue;
+              long long E1, E2;
+              if (!es.test(ox + lx, oy + ly, E1, E2)) continue;
               sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), (int)q2.w);
             }
         } else {
@@ -509,14 +537,17 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       if (!mask) continue;
       const float z0 = tq.z0[qi], dz1 = tq.dz1[qi], dz2 = tq.dz2[qi], ia = tq.ia[qi], zoff = tq.zoff[qi];
       const int meta = tq.meta[qi];
+      EdgeSet es;
+      es.init(X0, Y0, X1, Y1, X2, Y2);
+      // No bounding-box test per pixel: a pixel outside the box cannot pass the edge tests, and pixels beyond the
+      // viewport (the box is clamped to it) land in tile cells that are never flushed.
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
         const int lx = __shfl_sync(0xffffffffu, bx, k) * SGI_BLK_W + sub_x;
         const int ly = __shfl_sync(0xffffffffu, by, k) * SGI_BLK_H + sub_y;
-        if (lx < lx0 || lx > lx1 || ly < ly0 || ly > ly1) continue;
-        long long E0, E1, E2;
-        if (!cover(X0, Y0, X1, Y1, X2, Y2, ox + lx, oy + ly, E0, E1, E2)) continue;
+        long long E1, E2;
+        if (!es.test(ox + lx, oy + ly, E1, E2)) continue;
         sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
       }
     }
