@@ -235,10 +235,14 @@ __device__ __forceinline__ bool tile_overlaps(const SgiRec& r, int tx, int ty, i
   return true;
 }
 
-// One thread per record; triangles overlapping more than 4 tiles are handed to the whole warp (ballot loop), so
-// the two floor triangles that cover a thousand tiles cost 32 lanes x 32 trips instead of one lane x 1024.
+#ifndef SGI_BIG_TILES
 #define SGI_BIG_TILES 256
+#endif
 
+// One thread per record.  Records overlapping <= 4 tiles are handled by their thread with all (up to 4) atomics in
+// flight before the first dependent store.  The larger ones of a warp are flattened into one (record, tile) index
+// space that the 32 lanes walk together, 4 pairs per lane per trip, so a trip keeps 128 atomics in flight instead of
+// serialising one record after the other behind the atomics' latency.
 template <int FILL>
 __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
   const int lane = threadIdx.x & 31;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
     SgiRec r;
     r.prim_front = -1;
     if (slot < nrec) r = a.rec[slot];
-    int bx0 = 0, by0 = 0, bw = 0, nt = 0;
+    int bx0 = 0, by0 = 0, bw = 1, nt = 0;
     if (r.prim_front >= 0) {
       bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0); by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
       const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
@@ -258,37 +262,81 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
         nt = 0;
       }
     }
-    auto emit = [&](int tile, int s) {
-      if (!FILL) {
-        atomicAdd(&a.tile_cnt[tile], 1);
-      } else {
-        long long pos = (long long)a.tile_off[tile] + atomicAdd(&a.tile_fill[tile], 1);
-        if (pos < a.pair_cap) a.pairs[pos] = s;
-        else { a.flags[1] = 1; a.h_flags[0] = 1; }
-      }
-    };
+    // ---- small records: this thread alone
     if (nt > 0 && nt <= 4) {
-      for (int k = 0; k < nt; k++) {
-        const int ty = by0 + k / bw, tx = bx0 + k % bw;
-        if (nt > 1 && !tile_overlaps(r, tx, ty, W, H)) continue;
-        emit(ty * a.tiles_x + tx, slot);
+      int tiles[4], pos[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        tiles[k] = -1;
+        if (k < nt) {
+          const int ty = by0 + k / bw, tx = bx0 + k % bw;
+          if (nt == 1 || tile_overlaps(r, tx, ty, W, H)) tiles[k] = ty * a.tiles_x + tx;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (tiles[k] >= 0) {
+          if (!FILL) atomicAdd(&a.tile_cnt[tiles[k]], 1);
+          else pos[k] = atomicAdd(&a.tile_fill[tiles[k]], 1);
+        }
+      if (FILL) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (tiles[k] >= 0) {
+            const long long q = (long long)a.tile_off[tiles[k]] + pos[k];
+            if (q < a.pair_cap) a.pairs[q] = slot;
+            else { a.flags[1] = 1; a.h_flags[0] = 1; }
+          }
       }
     }
-    unsigned int big = __ballot_sync(0xffffffffu, nt > 4);
-    while (big) {
-      const int src = __ffs(big) - 1;
-      big &= big - 1;
-      SgiRec q;
-      q.X0 = __shfl_sync(0xffffffffu, r.X0, src); q.Y0 = __shfl_sync(0xffffffffu, r.Y0, src);
-      q.X1 = __shfl_sync(0xffffffffu, r.X1, src); q.Y1 = __shfl_sync(0xffffffffu, r.Y1, src);
-      q.X2 = __shfl_sync(0xffffffffu, r.X2, src); q.Y2 = __shfl_sync(0xffffffffu, r.Y2, src);
-      const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sby0 = __shfl_sync(0xffffffffu, by0, src);
-      const int sbw = __shfl_sync(0xffffffffu, bw, src), snt = __shfl_sync(0xffffffffu, nt, src);
-      const int sslot = __shfl_sync(0xffffffffu, slot, src);
-      for (int k = lane; k < snt; k += 32) {
-        const int ty = sby0 + k / sbw, tx = sbx0 + k % sbw;
-        if (!tile_overlaps(q, tx, ty, W, H)) continue;
-        emit(ty * a.tiles_x + tx, sslot);
+    // ---- larger records of this warp, flattened
+    const int mine = (nt > 4) ? nt : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    for (int p0 = 0; p0 < total; p0 += 128) {
+      int tiles[4], pos[4], slots[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int p = p0 + u * 32 + lane;
+        // owner = first lane whose inclusive prefix exceeds p (5-step search over the warp's prefixes)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int probe = __shfl_sync(0xffffffffu, incl, min(lo + step - 1, 31));
+          if (lo + step - 1 < 32 && probe <= p) lo += step;
+        }
+        const int src = min(lo, 31);
+        const int s_incl = __shfl_sync(0xffffffffu, incl, src), s_nt = __shfl_sync(0xffffffffu, mine, src);
+        SgiRec q;
+        q.X0 = __shfl_sync(0xffffffffu, r.X0, src); q.Y0 = __shfl_sync(0xffffffffu, r.Y0, src);
+        q.X1 = __shfl_sync(0xffffffffu, r.X1, src); q.Y1 = __shfl_sync(0xffffffffu, r.Y1, src);
+        q.X2 = __shfl_sync(0xffffffffu, r.X2, src); q.Y2 = __shfl_sync(0xffffffffu, r.Y2, src);
+        const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sby0 = __shfl_sync(0xffffffffu, by0, src);
+        const int sbw = __shfl_sync(0xffffffffu, bw, src);
+        slots[u] = __shfl_sync(0xffffffffu, slot, src);
+        tiles[u] = -1;
+        if (p < total) {
+          const int k = p - (s_incl - s_nt);
+          const int ty = sby0 + k / sbw, tx = sbx0 + k % sbw;
+          if (tile_overlaps(q, tx, ty, W, H)) tiles[u] = ty * a.tiles_x + tx;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (tiles[u] >= 0) {
+          if (!FILL) atomicAdd(&a.tile_cnt[tiles[u]], 1);
+          else pos[u] = atomicAdd(&a.tile_fill[tiles[u]], 1);
+        }
+      if (FILL) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (tiles[u] >= 0) {
+            const long long q = (long long)a.tile_off[tiles[u]] + pos[u];
+            if (q < a.pair_cap) a.pairs[q] = slots[u];
+            else { a.flags[1] = 1; a.h_flags[0] = 1; }
+          }
       }
     }
   }
