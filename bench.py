@@ -219,16 +219,21 @@ def main():
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
     vis_t = None
+    vis_strip = None
 
     def frame():
-        nonlocal vis_t
+        nonlocal vis_t, vis_strip
         app.display(program)
         if lights_mode:
             if vis_t is None:
                 ptr, nbytes = ctx.device_ptr("visibility")
                 vis_t = torch.as_tensor(_DevView(ptr, nbytes // 4), device=f"cuda:{local_rank}")
-            dist.all_reduce(vis_t)                       # sum of the per-rank partial sums, on the context's stream
-            vis_t.mul_(1.0 / n_l)                        # AccurateSoftShadow.frag:127
+                assert vis_t.numel() % world == 0
+                vis_strip = torch.empty(vis_t.numel() // world, dtype=torch.float32, device=f"cuda:{local_rank}")
+            # sum of the per-rank partial sums: reduce-scatter, every rank ends up owning one strip of the final image
+            # (what tile-local shading consumes); one NCCL collective per frame, on the context's stream
+            dist.reduce_scatter_tensor(vis_strip, vis_t)
+            vis_strip.mul_(1.0 / n_l)                    # AccurateSoftShadow.frag:127
 
     app.upload_scene()
     with torch.cuda.stream(stream):
@@ -332,7 +337,7 @@ def main():
         "config": {"workload": args.workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,
                    "params": w["params"], "triangles": T, "vertices": V, "scene": w["scene"],
                    "l2": "flushed before every timed step (256 MiB memset on the same stream, outside the event pair)",
-                   "parallelism": (f"lights x{world} + all-reduce" if lights_mode else f"frames x{world}") if world > 1 else "single GPU", "lit_fraction": lit},
+                   "parallelism": (f"lights x{world} + reduce-scatter" if lights_mode else f"frames x{world}") if world > 1 else "single GPU", "lit_fraction": lit},
         "clocks": clock_info, "gpu_launches": int(launches),
         "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * 24 + T * 12),
                 "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps, "pipelined_frames_in_flight": 2,

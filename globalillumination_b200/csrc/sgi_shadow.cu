@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;
   float4 vertex = __ldg(&a.pos4[o]);
-  if (vertex.x == 0.0f) return;                                   // discard (Shadow.frag:244): output keeps 0
+  if (vertex.x == 0.0f) { a.vis[o] = 0.0f; return; }              // discard (Shadow.frag:244): the target keeps its clear value 0
   float4 normal = __ldg(&a.nrm4[o]);
   float4 sc = mat4_mul(a.lmvp, vertex);
   float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;
   float4 vertex = __ldg(&a.pos4[o]);
-  if (vertex.x == 0.0f) return;
+  if (vertex.x == 0.0f) { a.vis[o] = 0.0f; return; }
   const float* m = a.lmvp;
   float cx = m[0] * vertex.x + m[4] * vertex.y + m[8] * vertex.z;
   float cy = m[1] * vertex.x + m[5] * vertex.y + m[9] * vertex.z;
@@ -473,11 +473,6 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
     count += accFactor;
   }
   a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
-}
-
-__global__ void k_clear_rect(float* vis, int W, int rx0, int ry0, int rx1, int ry1) {
-  int x = rx0 + blockIdx.x * blockDim.x + threadIdx.x, y = ry0 + blockIdx.y;
-  if (x < rx1 && y < ry1) vis[(size_t)y * W + x] = 0.0f;
 }
 
 }  // namespace
@@ -549,9 +544,8 @@ int sgi_shadow_run(sgi_ctx* ctx) {
     SGI_CUDA(ctx, cudaStreamSynchronize(st));      // tmp is pageable
     ctx->trans_dirty = false;
   }
-  // the reference clears the target to 0 before the full-screen pass (main.cpp:403-405); discarded pixels keep it
-  k_clear_rect<<<dim3((rw + 255) / 256, rh), 256, 0, st>>>(a.vis, a.W, a.rx0, a.ry0, a.rx1, a.ry1);
-  ctx->launches++;
+  // the reference clears the target to 0 before the full-screen pass (main.cpp:403-405) and discarded pixels keep it:
+  // here the kernel writes that 0 itself (every pixel of the rectangle is visited), so there is no separate clear pass
   dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
   int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL, st);
   const sgi_params& P = ctx->params;
