@@ -746,6 +746,9 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
   constexpr size_t smem = tile_smem_bytes<MODE, NT>();
   if (!configured) {
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the largest shared-memory carve-out so that two 1024-thread CTAs (or more of the smaller ones) fit an SM;
+    // with the default carve-out ncu showed occupancy limited to ONE CTA by shared memory
+    SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : (MODE == SGI_MODE_GBUFFER ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
