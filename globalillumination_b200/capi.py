@@ -37,7 +37,7 @@ class SgiParams(C.Structure):
 
 
 EXPORTS = [
-    "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common",
+    "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
@@ -145,6 +145,9 @@ class Context:
             self._ck(self.lib.sgi_set_multi_light_common(self.h, None))
         else:
             self._ck(self.lib.sgi_set_multi_light_common(self.h, _fp(_f32(light_mvp_b))))
+
+    def set_option(self, name, value):
+        self._ck(self.lib.sgi_set_option(self.h, name.encode(), int(value)))
 
     def set_params(self, params):
         self.params = params

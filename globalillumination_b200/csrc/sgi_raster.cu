@@ -764,20 +764,14 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
 // few-tile passes (<= 1200 tiles: up to 1080p / 2048^2) get 32 warps per tile; many-tile passes get 16 or 8 so that
 // the per-tile init/flush and barriers stay cheap.  Measured on B200 (profiles/r1_tile_cta_size.txt).  SGI_TILE_THREADS
 // overrides for experiments.
-static int tile_threads(int n_tiles) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("SGI_TILE_THREADS");
-    forced = e ? atoi(e) : 0;
-    if (forced != 256 && forced != 512 && forced != 1024) forced = 0;
-  }
-  if (forced) return forced;
+static int tile_threads(const sgi_ctx* ctx, int n_tiles) {
+  if (ctx->tile_threads) return ctx->tile_threads;
   return n_tiles <= 1200 ? 1024 : (n_tiles <= 6000 ? 512 : 256);
 }
 
 template <int MODE>
 static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStream_t stream) {
-  switch (tile_threads((int)(grid.x * grid.y))) {
+  switch (tile_threads(ctx, (int)(grid.x * grid.y))) {
     case 256: return launch_tile_nt<MODE, 256>(ctx, ta, grid, stream);
     case 512: return launch_tile_nt<MODE, 512>(ctx, ta, grid, stream);
     default: return launch_tile_nt<MODE, 1024>(ctx, ta, grid, stream);

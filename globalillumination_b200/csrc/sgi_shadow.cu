@@ -7,6 +7,7 @@
 //   many-light           SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag:52-133
 // Shadow-map taps are GL_NEAREST + CLAMP_TO_BORDER(0): texel = floor(coord*size) (MyGLTextureViewer.cpp:3-28).
 // fp32 in source order, -fmad=false: results are bit-identical to oracle/ (DESIGN.md §3).
+#include <cstdlib>
 #include <vector>
 #include "sgi_internal.cuh"
 
@@ -72,87 +73,150 @@ __device__ __forceinline__ int axis_texel(float coord, float size) {      // tex
   float f = floorf(coord * size);
   return (f >= 0.0f && f < size) ? (int)f : -1;
 }
-__device__ __forceinline__ float tap(const Smap& s, int row_off, int col) {
-  return ((row_off | col) < 0) ? 0.0f : __ldg(&s.d[(size_t)row_off + col]);
-}
+
+// Where taps are read from: the depth map in global memory (through L1/L2), or a window of it that the CTA staged
+// in shared memory with 128-bit loads.  Rows/columns are turned into keys once per axis position: key < 0 = border.
+template <bool SHARED>
+struct TapSrc {
+  const float* base; int pitch, x0, y0;
+  __device__ __forceinline__ int rowkey(int r) const { return r < 0 ? -1 : (r - y0) * pitch; }
+  __device__ __forceinline__ int colkey(int c) const { return c < 0 ? -1 : c - x0; }
+  __device__ __forceinline__ float tap(int rk, int ck) const {
+    if ((rk | ck) < 0) return 0.0f;
+    return SHARED ? base[rk + ck] : __ldg(&base[(size_t)rk + ck]);
+  }
+};
 
 // ---- Shadow.frag:86-116 (tap offsets precomputed on the host with the same fp32 loop) ----
 // N = taps per axis known at compile time (0 = run-time count, columns kept in local memory)
-template <int N>
-__device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, float4 c) {
+template <int N, bool SHARED>
+__device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, const TapSrc<SHARED>& src, float4 c) {
   const int n = N ? N : a.pcf_n;
   if (n <= 0) return 1.0f;
   int rows[N ? N : SGI_MAX_PCF_TAPS];
 #pragma unroll
   for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
-    if (ih < n) { int r = axis_texel(c.y + a.pcf_dv[ih], s.fh); rows[ih] = r < 0 ? -1 : r * s.w; }
+    if (ih < n) rows[ih] = src.rowkey(axis_texel(c.y + a.pcf_dv[ih], s.fh));
   float illum = 0.0f;
   for (int iw = 0; iw < n; iw++) {                     // Shadow.frag:98-99: w outer, h inner
-    const int col = axis_texel(c.x + a.pcf_du[iw], s.fw);
+    const int col = src.colkey(axis_texel(c.x + a.pcf_du[iw], s.fw));
 #pragma unroll
     for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
-      if (ih < n) { if (c.z <= tap(s, rows[ih], col)) illum += 1.0f; else illum += a.p.shadow_intensity; }
+      if (ih < n) { if (c.z <= src.tap(rows[ih], col)) illum += 1.0f; else illum += a.p.shadow_intensity; }
   }
   return illum / (float)(n * n);
 }
 
-// ---- PlausibleSoftShadow.frag:166-194, 365-374, 376-398 ----
-// NB / NK = blocker-search / filter taps per axis at compile time (0 = run time)
-template <int NB, int NK>
-__device__ __forceinline__ float pcss_t(const VisArgs& a, const Smap& s, float4 c) {
-  const sgi_params& p = a.p;
+// ---- PlausibleSoftShadow.frag:166-194: mean depth of the blockers (1.0 if none) ----
+template <int NB, bool SHARED>
+__device__ __forceinline__ float pcss_blockers(const VisArgs& a, const Smap& s, const TapSrc<SHARED>& src, float4 c) {
   float averageDepth = 0.0f;
   int numberOfBlockers = 0;
-  float bsw;
-  if ((float)a.SW <= 1024.0f) bsw = (float)p.light_source_radius / (float)a.SW;
-  else bsw = (float)p.light_source_radius / 1024.0f;
-  {
-    // `for(int w = -filterWidth; w <= filterWidth; w++)`: the int start truncates toward zero (A.7).  The offsets
-    // (float(w)*blockerSearchWidth)/filterWidth do not depend on the pixel: a.bs_q[] holds them (same fp32 ops, host)
-    const int nb = NB ? NB : a.bs_n;
-    int cols[NB ? NB : SGI_MAX_PCF_TAPS];
+  // `for(int w = -filterWidth; w <= filterWidth; w++)`: the int start truncates toward zero (A.7).  The offsets
+  // (float(w)*blockerSearchWidth)/filterWidth do not depend on the pixel: a.bs_q[] holds them (same fp32 ops, host)
+  const int nb = NB ? NB : a.bs_n;
+  int cols[NB ? NB : SGI_MAX_PCF_TAPS];
+#pragma unroll
+  for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
+    if (k < nb) cols[k] = src.colkey(axis_texel(c.x + a.bs_q[k], s.fw));
+  for (int j = 0; j < nb; j++) {
+    const int row = src.rowkey(axis_texel(c.y + a.bs_q[j], s.fh));
 #pragma unroll
     for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
-      if (k < nb) cols[k] = axis_texel(c.x + a.bs_q[k], s.fw);
-    for (int j = 0; j < nb; j++) {
-      const int r = axis_texel(c.y + a.bs_q[j], s.fh);
-      const int row = r < 0 ? -1 : r * s.w;
-#pragma unroll
-      for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
-        if (k < nb) {
-          const float dfl = tap(s, row, cols[k]);
-          if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
-        }
-    }
+      if (k < nb) {
+        const float dfl = src.tap(row, cols[k]);
+        if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+      }
   }
-  if (numberOfBlockers == 0) averageDepth = 1.0f;
-  else averageDepth = averageDepth / (float)numberOfBlockers;
-  float penumbraWidth;
-  if (averageDepth < 0.99f) penumbraWidth = 0.0f;
-  else {
-    float pw = ((c.z - averageDepth) / averageDepth) * (float)p.light_source_radius;
-    penumbraWidth = ((float)p.z_near * pw) / c.z;
-  }
-  float illum = 0.0f;
-  const float stepSize = 2.0f * penumbraWidth / (float)p.kernel_size;
+  if (numberOfBlockers == 0) return 1.0f;
+  return averageDepth / (float)numberOfBlockers;
+}
+
+// ---- PlausibleSoftShadow.frag:365-374 ----
+__device__ __forceinline__ float pcss_penumbra(const sgi_params& p, float averageDepth, float z) {
+  if (averageDepth < 0.99f) return 0.0f;
+  float pw = ((z - averageDepth) / averageDepth) * (float)p.light_source_radius;
+  return ((float)p.z_near * pw) / z;
+}
+
+// ---- PlausibleSoftShadow.frag:376-398 (the caller has checked 0 < stepSize < 1) ----
+template <int NK, bool SHARED>
+__device__ __forceinline__ float pcss_filter(const VisArgs& a, const Smap& s, const TapSrc<SHARED>& src, float4 c, float penumbraWidth) {
+  const sgi_params& p = a.p;
   const float fw2 = ((float)p.kernel_size - 1.0f) * 0.5f;
-  if (stepSize <= 0.0f || stepSize >= 1.0f) return 1.0f;
-  {
-    const int w0 = (int)(-fw2);
-    const int nk = NK ? NK : ((fw2 >= 0.0f) ? (int)fw2 - w0 + 1 : 0);
-    int cols[NK ? NK : SGI_MAX_PCF_TAPS];
+  float illum = 0.0f;
+  const int w0 = (int)(-fw2);
+  const int nk = NK ? NK : ((fw2 >= 0.0f) ? (int)fw2 - w0 + 1 : 0);
+  int cols[NK ? NK : SGI_MAX_PCF_TAPS];
+#pragma unroll
+  for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
+    if (k < nk) cols[k] = src.colkey(axis_texel(c.x + ((float)(w0 + k) * penumbraWidth) / fw2, s.fw));
+  for (int h = w0; (float)h <= fw2; h++) {
+    const int row = src.rowkey(axis_texel(c.y + ((float)h * penumbraWidth) / fw2, s.fh));
 #pragma unroll
     for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
-      if (k < nk) cols[k] = axis_texel(c.x + ((float)(w0 + k) * penumbraWidth) / fw2, s.fw);
-    for (int h = w0; (float)h <= fw2; h++) {
-      const int r = axis_texel(c.y + ((float)h * penumbraWidth) / fw2, s.fh);
-      const int row = r < 0 ? -1 : r * s.w;
-#pragma unroll
-      for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
-        if (k < nk) { if (c.z <= tap(s, row, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
-    }
+      if (k < nk) { if (c.z <= src.tap(row, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
   }
   return illum / (float)(p.kernel_size * p.kernel_size);
+}
+
+template <int NB, int NK>
+__device__ __forceinline__ float pcss_t(const VisArgs& a, const Smap& s, float4 c) {
+  const TapSrc<false> g = {s.d, s.w, 0, 0};
+  const float avg = pcss_blockers<NB, false>(a, s, g, c);
+  const float pw = pcss_penumbra(a.p, avg, c.z);
+  const float stepSize = 2.0f * pw / (float)a.p.kernel_size;
+  if (stepSize <= 0.0f || stepSize >= 1.0f) return 1.0f;
+  return pcss_filter<NK, false>(a, s, g, c, pw);
+}
+
+// ---- shared-memory staging of the CTA's light-space footprint ---------------------------------------------------
+#define SGI_STAGE_FLOATS 12288                 // 48 KB window
+
+// texel index clamped into the map (for footprints only: taps outside the map never touch memory)
+__device__ __forceinline__ int clamp_texel(float coord, float size, bool& bad) {
+  float f = floorf(coord * size);
+  if (!(f == f)) { bad = true; return 0; }
+  f = fminf(fmaxf(f, 0.0f), size - 1.0f);
+  return (int)f;
+}
+
+// CTA-wide min/max of the per-thread footprints (warp shuffles, then one shared-memory round across the 8 warps).
+// Returns true if at least one thread takes part and the window (x0 rounded down, width rounded up to 4 texels)
+// fits the staging buffer; then stages it with 128-bit loads.  All 256 threads must call this.
+__device__ __forceinline__ bool stage_window(const Smap& s, float* smem, int* red, bool take, bool bad, int lx, int hx, int ly, int hy,
+                                             TapSrc<true>& out) {
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, warp = threadIdx.y;
+  int mnx = take ? lx : 0x7fffffff, mxx = take ? hx : -1, mny = take ? ly : 0x7fffffff, mxy = take ? hy : -1;
+  int anybad = (take && bad) ? 1 : 0;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    mnx = min(mnx, __shfl_xor_sync(full, mnx, d)); mxx = max(mxx, __shfl_xor_sync(full, mxx, d));
+    mny = min(mny, __shfl_xor_sync(full, mny, d)); mxy = max(mxy, __shfl_xor_sync(full, mxy, d));
+    anybad |= __shfl_xor_sync(full, anybad, d);
+  }
+  __syncthreads();                                   // previous users of `red` and of the staging buffer are done
+  if (lane == 0) { red[warp * 5 + 0] = mnx; red[warp * 5 + 1] = mxx; red[warp * 5 + 2] = mny; red[warp * 5 + 3] = mxy; red[warp * 5 + 4] = anybad; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    mnx = min(mnx, red[w * 5 + 0]); mxx = max(mxx, red[w * 5 + 1]); mny = min(mny, red[w * 5 + 2]); mxy = max(mxy, red[w * 5 + 3]);
+    anybad |= red[w * 5 + 4];
+  }
+  if (mxx < 0 || anybad || (s.w & 3)) return false;
+  const int x0 = mnx & ~3, wv = ((mxx - x0 + 4) >> 2), hh = mxy - mny + 1;     // wv = window width in float4
+  if (wv * 4 * hh > SGI_STAGE_FLOATS) return false;
+  const float4* __restrict__ g = reinterpret_cast<const float4*>(s.d);
+  float4* t4 = reinterpret_cast<float4*>(smem);
+  const int gw = s.w >> 2, gx = x0 >> 2;
+  for (int v = tid; v < wv * hh; v += 256) {
+    const int r = v / wv, cv = v - r * wv;
+    t4[v] = __ldg(&g[(size_t)(mny + r) * gw + gx + cv]);
+  }
+  __syncthreads();
+  out.base = smem; out.pitch = wv * 4; out.x0 = x0; out.y0 = mny;
+  return true;
 }
 
 // ================================ RBSM ===========================================================
@@ -436,7 +500,7 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS) {
     if (sc.w > 0.0f && shadow == 1.0f) {
       if (TECH == SGI_TECH_HARD) shadow = (c.z <= sm_fetch(s, c.x, c.y)) ? 1.0f : a.p.shadow_intensity;
-      else if (TECH == SGI_TECH_PCF) shadow = pcf_t<VA>(a, s, c);
+      else if (TECH == SGI_TECH_PCF) { const TapSrc<false> g = {s.d, s.w, 0, 0}; shadow = pcf_t<VA, false>(a, s, g, c); }
       else shadow = pcss_t<VA, VB>(a, s, c);
     }
   } else if (shadow == 1.0f) {
@@ -447,6 +511,67 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
     else if (TECH == SGI_TECH_RPCF_CONS) shadow = cs_rpcf(r, a, c);
   }
   a.vis[o] = shadow;
+}
+
+// PCF / PCSS with the shadow-map window of the CTA's 32x8 pixels staged in shared memory (128-bit loads, footprint found
+// by warp-shuffle min/max reductions).  Identical arithmetic; only where the taps are read from changes.  A CTA whose
+// footprint does not fit the 48 KB window (depth discontinuities, grazing angles) reads through L1/L2 as k_visibility.
+template <int TECH, int VA, int VB>
+__global__ void __launch_bounds__(256) k_visibility_staged(const VisArgs a) {
+  extern __shared__ __align__(16) float stage[];
+  __shared__ int red[40];
+  const int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  const bool inb = x < a.rx1 && y < a.ry1;
+  const size_t o = inb ? (size_t)y * a.W + x : 0;
+  float4 vertex = make_float4(0.f, 0.f, 0.f, 1.f), normal = vertex, sc = vertex, c = vertex;
+  float shadow = 0.0f;
+  bool need = false;
+  if (inb) {
+    vertex = __ldg(&a.pos4[o]);
+    if (vertex.x != 0.0f) {
+      normal = __ldg(&a.nrm4[o]);
+      sc = mat4_mul(a.lmvp, vertex);
+      c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+      shadow = pre_evaluation(a, vertex, normal);
+      need = sc.w > 0.0f && shadow == 1.0f;
+    }
+  }
+  const Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
+  const TapSrc<false> g = {s.d, s.w, 0, 0};
+  TapSrc<true> sh;
+  if (TECH == SGI_TECH_PCF) {
+    const int n = VA ? VA : a.pcf_n;
+    bool bad = false;
+    const int lx = clamp_texel(c.x + a.pcf_du[0], s.fw, bad), hx = clamp_texel(c.x + a.pcf_du[max(n - 1, 0)], s.fw, bad);
+    const int ly = clamp_texel(c.y + a.pcf_dv[0], s.fh, bad), hy = clamp_texel(c.y + a.pcf_dv[max(n - 1, 0)], s.fh, bad);
+    const bool staged = stage_window(s, stage, red, need, bad, lx, hx, ly, hy, sh);
+    if (need) shadow = staged ? pcf_t<VA, true>(a, s, sh, c) : pcf_t<VA, false>(a, s, g, c);
+  } else {
+    const int nb = VA ? VA : a.bs_n;
+    bool bad = false;
+    const int lx = clamp_texel(c.x + a.bs_q[0], s.fw, bad), hx = clamp_texel(c.x + a.bs_q[max(nb - 1, 0)], s.fw, bad);
+    const int ly = clamp_texel(c.y + a.bs_q[0], s.fh, bad), hy = clamp_texel(c.y + a.bs_q[max(nb - 1, 0)], s.fh, bad);
+    const bool staged = stage_window(s, stage, red, need, bad, lx, hx, ly, hy, sh);
+    float pw = 0.0f;
+    bool need2 = false;
+    if (need) {
+      const float avg = staged ? pcss_blockers<VA, true>(a, s, sh, c) : pcss_blockers<VA, false>(a, s, g, c);
+      pw = pcss_penumbra(a.p, avg, c.z);
+      const float stepSize = 2.0f * pw / (float)a.p.kernel_size;
+      need2 = !(stepSize <= 0.0f || stepSize >= 1.0f);
+      if (!need2) shadow = 1.0f;
+    }
+    if (__syncthreads_or(need2)) {                     // the filter runs only where a penumbra exists
+      const float fw2 = ((float)a.p.kernel_size - 1.0f) * 0.5f;
+      const int w0 = (int)(-fw2), w1 = (fw2 >= 0.0f) ? (int)fw2 : w0;
+      bool bad2 = false;
+      const int flx = clamp_texel(c.x + ((float)w0 * pw) / fw2, s.fw, bad2), fhx = clamp_texel(c.x + ((float)w1 * pw) / fw2, s.fw, bad2);
+      const int fly = clamp_texel(c.y + ((float)w0 * pw) / fw2, s.fh, bad2), fhy = clamp_texel(c.y + ((float)w1 * pw) / fw2, s.fh, bad2);
+      const bool staged2 = stage_window(s, stage, red, need2, bad2, flx, fhx, fly, fhy, sh);
+      if (need2) shadow = staged2 ? pcss_filter<VB, true>(a, s, sh, c, pw) : pcss_filter<VB, false>(a, s, g, c, pw);
+    }
+  }
+  if (inb) a.vis[o] = (vertex.x == 0.0f) ? 0.0f : shadow;
 }
 
 // AccurateSoftShadow.frag:52-133, monteCarlo branch
@@ -549,19 +674,44 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
   int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL, st);
   const sgi_params& P = ctx->params;
+  // shared-memory staging of the shadow-map window (PCF / PCSS) is an option (sgi_set_option "vis_staged"): measured on
+  // B200 it only pays when the map is much larger than L1 can cover (4096^2 PCSS: 1.01 -> 0.89 ms) and loses at the
+  // c2 sizes (0.077 -> 0.097 ms), because the kernel is issue-bound, not L1-bound (profiles/r1_vis_staging.txt)
+  static int staged_cfg = -1;
+  const size_t stage_bytes = (size_t)SGI_STAGE_FLOATS * 4;
+  if (staged_cfg < 0) {
+    staged_cfg = 1;
+    cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCF, 7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCF, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCSS, 7, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCSS, 7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCSS, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+  }
+  const bool staged = ctx->vis_staged != 0;
   // tap counts the float/int loops of the shaders produce for the current parameters
   const int nb_taps = a.bs_n;
   const int nk_taps = 2 * (int)(((float)P.kernel_size - 1.0f) * 0.5f) + 1;
   switch (P.technique) {
     case SGI_TECH_HARD: k_visibility<SGI_TECH_HARD, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_PCF:
-      if (a.pcf_n == 7) k_visibility<SGI_TECH_PCF, 7, 0><<<grid, block, 0, st>>>(a);          // kernelOrder 7 (reference default)
-      else k_visibility<SGI_TECH_PCF, 0, 0><<<grid, block, 0, st>>>(a);
+      if (staged) {
+        if (a.pcf_n == 7) k_visibility_staged<SGI_TECH_PCF, 7, 0><<<grid, block, stage_bytes, st>>>(a);
+        else k_visibility_staged<SGI_TECH_PCF, 0, 0><<<grid, block, stage_bytes, st>>>(a);
+      } else {
+        if (a.pcf_n == 7) k_visibility<SGI_TECH_PCF, 7, 0><<<grid, block, 0, st>>>(a);          // kernelOrder 7 (reference default)
+        else k_visibility<SGI_TECH_PCF, 0, 0><<<grid, block, 0, st>>>(a);
+      }
       break;
     case SGI_TECH_PCSS:
-      if (nb_taps == 7 && nk_taps == 15) k_visibility<SGI_TECH_PCSS, 7, 15><<<grid, block, 0, st>>>(a);   // reference default
-      else if (nb_taps == 7 && nk_taps == 7) k_visibility<SGI_TECH_PCSS, 7, 7><<<grid, block, 0, st>>>(a); // after "reset"
-      else k_visibility<SGI_TECH_PCSS, 0, 0><<<grid, block, 0, st>>>(a);
+      if (staged) {
+        if (nb_taps == 7 && nk_taps == 15) k_visibility_staged<SGI_TECH_PCSS, 7, 15><<<grid, block, stage_bytes, st>>>(a);
+        else if (nb_taps == 7 && nk_taps == 7) k_visibility_staged<SGI_TECH_PCSS, 7, 7><<<grid, block, stage_bytes, st>>>(a);
+        else k_visibility_staged<SGI_TECH_PCSS, 0, 0><<<grid, block, stage_bytes, st>>>(a);
+      } else {
+        if (nb_taps == 7 && nk_taps == 15) k_visibility<SGI_TECH_PCSS, 7, 15><<<grid, block, 0, st>>>(a);   // reference default
+        else if (nb_taps == 7 && nk_taps == 7) k_visibility<SGI_TECH_PCSS, 7, 7><<<grid, block, 0, st>>>(a); // after "reset"
+        else k_visibility<SGI_TECH_PCSS, 0, 0><<<grid, block, 0, st>>>(a);
+      }
       break;
     case SGI_TECH_RBSM_NONCONS: k_visibility<SGI_TECH_RBSM_NONCONS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_RBSM_CONS: k_visibility<SGI_TECH_RBSM_CONS, 0, 0><<<grid, block, 0, st>>>(a); break;

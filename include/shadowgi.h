@@ -173,6 +173,12 @@ int sgi_synchronize(sgi_ctx* ctx);
 int sgi_alloc_host(void** host_ptr, size_t bytes);
 int sgi_free_host(void* host_ptr);
 
+/* implementation switches (experiments / A-B measurements; results are identical either way):
+ *   "vis_staged"      0 (default) taps through L1/L2, 1 = PCF/PCSS stage the CTA's shadow-map window in shared memory
+ *   "overlap_passes"  1 (default) G-buffer pass on the auxiliary stream, 0 = everything on the main stream
+ *   "tile_threads"    0 (default) automatic, or 256 / 512 / 1024 threads per tile CTA */
+int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);
+
 /* instrumentation */
 int sgi_enable_timing(sgi_ctx* ctx, int32_t on);                 /* CUDA events around every pass            */
 int sgi_pass_time_ms(sgi_ctx* ctx, int32_t pass, double* total_ms, int64_t* calls);  /* since last reset      */
