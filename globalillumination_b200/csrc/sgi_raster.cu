@@ -443,12 +443,27 @@ __device__ __forceinline__ long long edge_block_max(int Xa, int Ya, int Xb, int 
   return (long long)dx * (long long)(PY - Ya) - (long long)dy * (long long)(PX - Xa);
 }
 
+// Hierarchical depth.  Each 8x4 block of the tile keeps an upper bound `bz` of the depths currently stored in it
+// (depths only ever decrease, so any earlier maximum stays an upper bound).  A triangle whose smallest possible depth
+// is above that bound cannot change the block and is skipped before any per-pixel work.  The triangle bound is the
+// smallest vertex depth plus the polygon offset, lowered by a slack that covers the fp32 rounding of the interpolation
+// z = (z0 + b1*dz1) + b2*dz2 (b in [0,1] up to rounding), so culling never removes a fragment that would have passed.
+__device__ __forceinline__ unsigned int tri_depth_lower_bound(float z0, float dz1, float dz2, float zoff) {
+  float zmin = fminf(z0, fminf(z0 + dz1, z0 + dz2)) + zoff;
+  zmin -= 4.0e-6f * (1.0f + fabsf(dz1) + fabsf(dz2) + fabsf(zoff));
+  if (!(zmin > 0.0f)) return 0u;                     // also catches NaN
+  return __float_as_uint(fminf(zmin, 1.0f));
+}
+#define SGI_NBLK ((SGI_TILE / SGI_BLK_W) * (SGI_TILE / SGI_BLK_H))     // 8 x 16 = 128 blocks per tile
+#define SGI_ZBUCKETS 64          // work items of a chunk are issued nearest-first (counting sort on their depth bound)
+
 // Large triangles of the current chunk, parked in shared memory for the warp-cooperative phase.
 template <int NT>
 struct TriQueue {
   int X0[NT], Y0[NT], X1[NT], Y1[NT], X2[NT], Y2[NT];
   float z0[NT], dz1[NT], dz2[NT], ia[NT], zoff[NT];
   int meta[NT];
+  unsigned int zlo[NT];            // conservative lower bound of every depth this triangle can produce (float bits)
   int box[NT];                     // lx0 | ly0<<8 | lx1<<16 | ly1<<24 (tile-local inclusive bbox)
   int group[4 * NT];               // work items: queue index << 3 | group of 32 blocks (a 64x64 bbox has 128 blocks)
 };
@@ -492,6 +507,9 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
   TriQueue<NT>& tq = *reinterpret_cast<TriQueue<NT>*>(smem_raw + PAYLOAD + SDBYTES);
   __shared__ int next_item, q_count, g_count;
+  __shared__ unsigned int bz[SGI_NBLK];          // per 8x4 block: upper bound of the stored depths (SV: of the scene depths)
+  __shared__ unsigned int zq_min, zq_max;        // depth range of the queued triangles of the chunk
+  __shared__ int bucket_cnt[SGI_ZBUCKETS], bucket_pos[SGI_ZBUCKETS];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int tx = a.tx0 + blockIdx.x, ty = a.ty0 + blockIdx.y;
@@ -508,6 +526,19 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       sd[p] = (lx < SGI_TILE && x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
     }
   }
+  if (MODE != SGI_MODE_SVCOUNT) { if (tid < SGI_NBLK) bz[tid] = ONE_BITS; }
+  else {
+    // shadow volumes test against a fixed scene depth: the block bound is its largest scene depth (LEQUAL / LESS both
+    // fail for fragments above it)
+    __syncthreads();
+    if (tid < SGI_NBLK) {
+      const int bx = tid % (SGI_TILE / SGI_BLK_W), by = tid / (SGI_TILE / SGI_BLK_W);
+      float m = 0.0f;
+      for (int j = 0; j < SGI_BLK_H; j++)
+        for (int i = 0; i < SGI_BLK_W; i++) m = fmaxf(m, sd[(by * SGI_BLK_H + j) * SGI_PITCH + bx * SGI_BLK_W + i]);
+      bz[tid] = __float_as_uint(fminf(fmaxf(m, 0.0f), 1.0f));
+    }
+  }
   long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
   if (end > a.pair_cap) end = a.pair_cap;
   if (beg > end) beg = end;
@@ -516,7 +547,10 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
 
   for (int base = 0; base < nitems; base += NT) {
-    if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; }
+    if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; zq_min = 0xFFFFFFFFu; zq_max = 0u; }
+    if (tid < SGI_ZBUCKETS) bucket_cnt[tid] = 0;
+    int my_k = -1, my_ng = 0;
+    unsigned int my_zlo = 0u;
     __syncthreads();                                           // payload initialised / previous chunk drained
     if (base + tid < nitems) {
       const int it = base + tid;
@@ -549,14 +583,37 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
           tq.z0[k] = __uint_as_float(q1.z); tq.dz1[k] = __uint_as_float(q1.w); tq.dz2[k] = __uint_as_float(q2.x);
           tq.ia[k] = __uint_as_float(q2.y); tq.zoff[k] = __uint_as_float(q2.z);
           tq.meta[k] = (int)q2.w;
+          my_zlo = tri_depth_lower_bound(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), __uint_as_float(q2.z));
+          tq.zlo[k] = my_zlo;
           tq.box[k] = lx0 | (ly0 << 8) | (lx1 << 16) | (ly1 << 24);
           // one work item per group of 32 blocks, so a triangle covering the tile is shared by 4 warps
           const int nb = (lx1 / SGI_BLK_W - lx0 / SGI_BLK_W + 1) * (ly1 / SGI_BLK_H - ly0 / SGI_BLK_H + 1);
-          const int ng = (nb + 31) >> 5;
-          const int g0 = atomicAdd(&g_count, ng);
-          for (int g = 0; g < ng; g++) tq.group[g0 + g] = (k << 3) | g;
+          my_k = k; my_ng = (nb + 31) >> 5;
+          atomicMin(&zq_min, my_zlo); atomicMax(&zq_max, my_zlo);
         }
       }
+    }
+    __syncthreads();
+    // nearest-first issue order: counting sort of the work items on their depth bound, so that the block bounds
+    // tighten early and the triangles behind them are culled
+    int my_b = 0;
+    if (my_k >= 0) {
+      const unsigned int lo = zq_min, span = zq_max - lo + 1u;
+      my_b = (int)(((unsigned long long)(my_zlo - lo) * SGI_ZBUCKETS) / span);
+      atomicAdd(&bucket_cnt[my_b], my_ng);
+    }
+    __syncthreads();
+    if (tid < 32) {                                            // exclusive prefix over the 64 buckets
+      int c0 = bucket_cnt[2 * tid], c1 = bucket_cnt[2 * tid + 1], incl = c0 + c1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+      bucket_pos[2 * tid] = incl - c0 - c1; bucket_pos[2 * tid + 1] = incl - c1;
+      if (tid == 31) g_count = incl;
+    }
+    __syncthreads();
+    if (my_k >= 0) {
+      const int g0 = atomicAdd(&bucket_pos[my_b], my_ng);
+      for (int g = 0; g < my_ng; g++) tq.group[g0 + g] = (my_k << 3) | g;
     }
     __syncthreads();
     const int ngroups = g_count;
@@ -575,7 +632,9 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       const int sub_x = lane & (SGI_BLK_W - 1), sub_y = lane >> 3;
       const int b = b0 + lane;
       const int bx = bx0 + b % nbx, by = by0 + b / nbx;
+      const unsigned int zlo = tq.zlo[qi];
       bool keep = b < nb;
+      if (keep) keep = zlo <= bz[by * (SGI_TILE / SGI_BLK_W) + bx];          // hierarchical depth: nothing in this block can change
       if (keep && nb > 1) {
         const int gx = ox + bx * SGI_BLK_W, gy = oy + by * SGI_BLK_H;
         keep = edge_block_max(X1, Y1, X2, Y2, gx, gy) >= 0 && edge_block_max(X2, Y2, X0, Y0, gx, gy) >= 0 &&
@@ -592,11 +651,18 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int lx = __shfl_sync(0xffffffffu, bx, k) * SGI_BLK_W + sub_x;
-        const int ly = __shfl_sync(0xffffffffu, by, k) * SGI_BLK_H + sub_y;
+        const int kbx = __shfl_sync(0xffffffffu, bx, k), kby = __shfl_sync(0xffffffffu, by, k);
+        const int lx = kbx * SGI_BLK_W + sub_x, ly = kby * SGI_BLK_H + sub_y;
         long long E1, E2;
-        if (!es.test(ox + lx, oy + ly, E1, E2)) continue;
-        sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+        if (es.test(ox + lx, oy + ly, E1, E2)) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+        if (MODE != SGI_MODE_SVCOUNT) {
+          // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
+          const int p = ly * SGI_PITCH + lx;
+          const unsigned int cur = (MODE == SGI_MODE_DEPTH) ? zt[p] : (unsigned int)(kt[p] >> 32);
+          const unsigned int wmax = __reduce_max_sync(0xffffffffu, cur);
+          const int bi = kby * (SGI_TILE / SGI_BLK_W) + kbx;
+          if (lane == 0 && wmax < bz[bi]) atomicMin(&bz[bi], wmax);
+        }
       }
     }
     __syncthreads();                                           // every warp is done with this chunk's queue
