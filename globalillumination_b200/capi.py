@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf_noncons": 5, "rpcf_cons": 6,
         "rsmss": 7, "multi_hard": 8}
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
-       "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8}
+       "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10}
 PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
         "tile_gbuffer": 6, "tile_sv": 7}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
@@ -37,7 +37,7 @@ class SgiParams(C.Structure):
 
 
 EXPORTS = [
-    "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
+    "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
@@ -130,6 +130,15 @@ class Context:
         self.T = T
         self._ck(self.lib.sgi_set_mesh(self.h, C.c_void_p(xyz_ptr), C.c_void_p(nrm_ptr), int(V), C.c_void_p(idx_ptr), int(T)))
 
+    def set_mesh_colors(self, rgb):
+        if rgb is None:
+            self._ck(self.lib.sgi_set_mesh_colors(self.h, None))
+        else:
+            self._ck(self.lib.sgi_set_mesh_colors(self.h, _fp(_f32(rgb))))
+
+    def shade_phong(self, clear=(0.63, 0.82, 0.96, 1.0)):
+        self._ck(self.lib.sgi_shade_phong(self.h, _fp(_f32(clear))))
+
     def set_camera(self, mvp, mv, normal_matrix, W, H):
         self.W, self.H = int(W), int(H)
         self._ck(self.lib.sgi_set_camera(self.h, _fp(_f32(mvp)), _fp(_f32(mv)), _fp(_f32(normal_matrix)), self.W, self.H))
@@ -173,7 +182,7 @@ class Context:
         return {
             "shadow_map": ((N, SH, SW), np.float32), "gbuf_pos": ((H, W, 4), np.float32), "gbuf_nrm": ((H, W, 4), np.float32),
             "cam_depth": ((H, W), np.float32), "visibility": ((H, W), np.float32), "sv_count": ((H, W), np.int32),
-            "sv_stencil": ((H, W), np.uint8), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
+            "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
         }[which]
 
     def read(self, which, out=None):

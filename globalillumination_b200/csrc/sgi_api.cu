@@ -145,6 +145,7 @@ int sgi_destroy(sgi_ctx* ctx) {
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
+  if (ctx->d_rgb) cudaFree(ctx->d_rgb);
   void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (SgiScratch& sc : ctx->scratch) sgi_raster_free(sc);
@@ -204,6 +205,25 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   return SGI_OK;
 }
 
+int sgi_set_mesh_colors(sgi_ctx* ctx, const float* rgb) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
+  if (!rgb) { ctx->has_rgb = false; ctx->gbuffer_valid = false; return SGI_OK; }
+  if (ctx->V <= 0) { ctx->err = "sgi_set_mesh_colors: set the mesh first"; return SGI_ERR_INVALID; }
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->rgb_V != ctx->V) {
+    if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+    ctx->d_rgb = nullptr;
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_rgb, (size_t)ctx->V * 12));
+    ctx->rgb_V = ctx->V;
+  }
+  SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_rgb, rgb, (size_t)ctx->V * 12, cudaMemcpyHostToDevice, ctx->stream));
+  mark_gbuffer_use(ctx);
+  ctx->has_rgb = true; ctx->gbuffer_valid = false;
+  return SGI_OK;
+}
+
 int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const float nm[9], int32_t W, int32_t H) {
   if (!ctx || !mvp || !mv || !nm || W <= 0 || H <= 0 || W > 32767 || H > 32767) { if (ctx) ctx->err = "sgi_set_camera: bad arguments"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
@@ -215,6 +235,8 @@ int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const 
   if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_NRM, px * 16))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_CAM_DEPTH, px * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_VISIBILITY, px * 4))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_ALBEDO, px * 16))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SHADED, px * 16))) return rc;
   if (W != ctx->W || H != ctx->H) {
     SGI_CUDA(ctx, cudaMemsetAsync(ctx->buf[SGI_BUF_VISIBILITY], 0, px * 4, ctx->stream));
     ctx->scratch[1].sized[SGI_MODE_GBUFFER] = ctx->scratch[0].sized[SGI_MODE_SVCOUNT] = false;
@@ -312,6 +334,7 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
     SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
   }
   sgi_wait_reads_of(ctx, SGI_BUF_GBUF_POS, st); sgi_wait_reads_of(ctx, SGI_BUF_GBUF_NRM, st); sgi_wait_reads_of(ctx, SGI_BUF_CAM_DEPTH, st);
+  sgi_wait_reads_of(ctx, SGI_BUF_GBUF_ALBEDO, st);
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
   SgiRasterJob job;
   memset(&job, 0, sizeof(job));
@@ -321,6 +344,8 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   job.W = ctx->W; job.H = ctx->H;
   job.depth = (float*)ctx->buf[SGI_BUF_CAM_DEPTH];
   job.pos4 = (float4*)ctx->buf[SGI_BUF_GBUF_POS]; job.nrm4 = (float4*)ctx->buf[SGI_BUF_GBUF_NRM];
+  const bool rgb_ok = ctx->has_rgb && ctx->rgb_V == ctx->V;
+  job.rgb = rgb_ok ? ctx->d_rgb : nullptr; job.albedo4 = rgb_ok ? (float4*)ctx->buf[SGI_BUF_GBUF_ALBEDO] : nullptr;
   job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
   int rc = sgi_raster_run(ctx, job, 1, st);
   if (rc) return rc;
@@ -346,6 +371,19 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   sgi_timing_end(ctx, SGI_PASS_VISIBILITY, slot, ctx->stream);
   mark_gbuffer_use(ctx);
   return SGI_OK;
+}
+
+int sgi_shade_phong(sgi_ctx* ctx, const float clear_rgba[4]) {
+  if (!ctx || !clear_rgba) return SGI_ERR_INVALID;
+  if (!ctx->gbuffer_valid) { ctx->err = "sgi_shade_phong: render the G-buffer and compute the visibility first"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int rc = sgi_join_gbuffer(ctx);
+  if (rc) return rc;
+  sgi_wait_reads_of(ctx, SGI_BUF_SHADED, ctx->stream);
+  if (ctx->has_rgb && ctx->rgb_V != ctx->V) { ctx->err = "sgi_shade_phong: colours do not match the current mesh"; return SGI_ERR_INVALID; }
+  rc = sgi_shade_run(ctx, clear_rgba);
+  mark_gbuffer_use(ctx);
+  return rc;
 }
 
 int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {

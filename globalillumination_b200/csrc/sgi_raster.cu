@@ -369,6 +369,7 @@ struct TileArgs {
   int W, H, rx0, ry0, rx1, ry1;
   const float* xyz; const float* nrm; const int32_t* idx;
   float* depth; float4* pos4; float4* nrm4;
+  const float* rgb; float4* albedo4;
   const float* scene_depth; int depth_func; int32_t* count; uint8_t* stencil;
 };
 
@@ -477,7 +478,7 @@ struct TileSink {                  // where fragments go: the tile payload in sh
     if (MODE == SGI_MODE_DEPTH) {
       const unsigned int zb = __float_as_uint(z);
       if (zb < zt[p]) atomicMin(&zt[p], zb);
-    } else if (MODE == SGI_MODE_GBUFFER) {
+    } else if ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) {
       if (z < 1.0f) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)(meta >> 1);
         if (key < kt[p]) atomicMin(&kt[p], key);
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   unsigned long long* kt = reinterpret_cast<unsigned long long*>(smem_raw);
   int* ct = reinterpret_cast<int*>(smem_raw);
   constexpr int NCELL = SGI_TILE * SGI_PITCH;
-  constexpr size_t PAYLOAD = (MODE == SGI_MODE_GBUFFER) ? (size_t)NCELL * 8 : (size_t)NCELL * 4;
+  constexpr size_t PAYLOAD = ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) ? (size_t)NCELL * 8 : (size_t)NCELL * 4;
   constexpr size_t SDBYTES = (MODE == SGI_MODE_SVCOUNT) ? (size_t)NCELL * 4 : 0;
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
   TriQueue<NT>& tq = *reinterpret_cast<TriQueue<NT>*>(smem_raw + PAYLOAD + SDBYTES);
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
 
   for (int p = tid; p < NCELL; p += NT) {
     if (MODE == SGI_MODE_DEPTH) zt[p] = ONE_BITS;
-    else if (MODE == SGI_MODE_GBUFFER) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
+    else if ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
     else {
       ct[p] = 0;
       int lx = p % SGI_PITCH, ly = p / SGI_PITCH;
@@ -634,11 +635,33 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       const int bx = bx0 + b % nbx, by = by0 + b / nbx;
       const unsigned int zlo = tq.zlo[qi];
       bool keep = b < nb;
-      if (keep) keep = zlo <= bz[by * (SGI_TILE / SGI_BLK_W) + bx];          // hierarchical depth: nothing in this block can change
+      const unsigned int bound = keep ? bz[by * (SGI_TILE / SGI_BLK_W) + bx] : 0u;
+      if (keep) keep = zlo <= bound;                           // hierarchical depth, triangle-wide bound
       if (keep && nb > 1) {
         const int gx = ox + bx * SGI_BLK_W, gy = oy + by * SGI_BLK_H;
         keep = edge_block_max(X1, Y1, X2, Y2, gx, gy) >= 0 && edge_block_max(X2, Y2, X0, Y0, gx, gy) >= 0 &&
                edge_block_max(X0, Y0, X1, Y1, gx, gy) >= 0;
+        if (keep && bound < ONE_BITS && MODE == SGI_MODE_SVCOUNT) {
+          // (only for shadow volumes and for triangles spanning many blocks, where the triangle-wide bound is loose;
+          //  for small ones the extra test costs more than it culls: measured, profiles/r1_hiz.txt)
+          // hierarchical depth, per-block bound: the interpolated depth is affine in the pixel position, so over the
+          // block it is smallest at one of the four corner pixels; evaluate those with the fragment formula and lower
+          // the result by a slack covering fp32 rounding (terms t = b*dz can be large at corners outside the triangle)
+          const float tz0 = tq.z0[qi], tdz1 = tq.dz1[qi], tdz2 = tq.dz2[qi], tia = tq.ia[qi], tzoff = tq.zoff[qi];
+          float zmin_blk = 2.0f;
+#pragma unroll
+          for (int cnr = 0; cnr < 4; cnr++) {
+            const int PX = (gx + ((cnr & 1) ? SGI_BLK_W - 1 : 0)) * SGI_SUBPIX + SGI_SUBPIX / 2;
+            const int PY = (gy + ((cnr & 2) ? SGI_BLK_H - 1 : 0)) * SGI_SUBPIX + SGI_SUBPIX / 2;
+            const long long E1 = (long long)(X0 - X2) * (long long)(PY - Y2) - (long long)(Y0 - Y2) * (long long)(PX - X2);
+            const long long E2 = (long long)(X1 - X0) * (long long)(PY - Y0) - (long long)(Y1 - Y0) * (long long)(PX - X0);
+            const float t1 = ((float)E1 * tia) * tdz1, t2 = ((float)E2 * tia) * tdz2;
+            const float zc = ((tz0 + t1) + t2) + tzoff - (1.0e-6f + 5.0e-7f * (fabsf(t1) + fabsf(t2) + fabsf(tzoff)));
+            zmin_blk = fminf(zmin_blk, zc);
+          }
+          if (zmin_blk > 1.0f) zmin_blk = 1.0f;
+          keep = !(zmin_blk > 0.0f) || __float_as_uint(zmin_blk) <= bound;     // NaN / negative bounds never cull
+        }
       }
       unsigned int mask = __ballot_sync(0xffffffffu, keep);
       if (!mask) continue;
@@ -689,6 +712,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         a.depth[o] = 1.0f;
         a.pos4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
         a.nrm4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (MODE == SGI_MODE_GBUFFER_RGB) a.albedo4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
         continue;
       }
       const int prim = (int)lo32, t = prim >> 3, sub = prim & 7;
@@ -723,13 +747,31 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       a.depth[o] = __uint_as_float((unsigned int)(key >> 32));
       a.pos4[o] = make_float4(outv[0], outv[1], outv[2], 1.0f);
       a.nrm4[o] = make_float4(outv[3], outv[4], outv[5], (r.prim_front & 1) ? 1.0f : 0.0f);
+      if (MODE == SGI_MODE_GBUFFER_RGB) {                // third target of GBuffer.frag: the interpolated vertex colour (own instantiation:
+                                                         // carrying this code in the colour-less kernel cost 8 % of its time)
+        float col[3];
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          float A0, A1, A2;
+          if (r.pad0 == 0) {
+            A0 = a.rgb[3 * (size_t)i0 + cc]; A1 = a.rgb[3 * (size_t)j1 + cc]; A2 = a.rgb[3 * (size_t)j2 + cc];
+          } else {
+            const float s0 = a.rgb[3 * (size_t)i0 + cc], s1 = a.rgb[3 * (size_t)i1 + cc], s2 = a.rgb[3 * (size_t)i2 + cc];
+            A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
+            A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
+            A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
+          }
+          col[cc] = ((q0 * A0 + q1 * A1) + q2 * A2) * iq;
+        }
+        a.albedo4[o] = make_float4(col[0], col[1], col[2], 1.0f);
+      }
     }
   }
 }
 
 template <int MODE, int NT>
 constexpr size_t tile_smem_bytes() {
-  return (size_t)SGI_TILE * SGI_PITCH * (MODE == SGI_MODE_GBUFFER ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? (size_t)SGI_TILE * SGI_PITCH * 4 : 0) +
+  return (size_t)SGI_TILE * SGI_PITCH * ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB) ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? (size_t)SGI_TILE * SGI_PITCH * 4 : 0) +
          sizeof(TriQueue<NT>);
 }
 
@@ -817,7 +859,7 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : (MODE == SGI_MODE_GBUFFER ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
+  const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB) ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
   int tslot = sgi_timing_begin(ctx, pass, stream);
   k_tile<MODE, NT><<<grid, NT, smem, stream>>>(ta);
   sgi_timing_end(ctx, pass, tslot, stream);
@@ -912,10 +954,11 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
   ta.xyz = job.xyz; ta.nrm = job.nrm; ta.idx = job.idx;
   ta.depth = job.depth; ta.pos4 = job.pos4; ta.nrm4 = job.nrm4;
+  ta.rgb = job.rgb; ta.albedo4 = job.albedo4;
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
   dim3 grid(tx1 - tx0 + 1, ty1 - ty0 + 1);
   if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, st);
-  else if (job.mode == SGI_MODE_GBUFFER) rc = launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, st);
+  else if (job.mode == SGI_MODE_GBUFFER) rc = (job.rgb && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, st);
   else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, st);
   return rc;
 }

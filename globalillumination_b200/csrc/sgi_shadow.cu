@@ -600,7 +600,65 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
   a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
 }
 
+// ShadowMapping/Shaders/GBuffer/PhongShading.frag:11-47 (shadeScene).  Note `vec3 E = normalize(-vertex)` normalises the
+// vec4 (w included) before truncation, and the specular term is scaled by (shadow - shadowIntensity).
+struct ShadeArgs {
+  float mv[16], nm[9], lpos[3]; float si; float clear[4];
+  const float4* pos4; const float4* nrm4; const float4* albedo4; const float* vis; float4* out; int W, H;
+};
+__global__ void __launch_bounds__(256) k_shade_phong(const ShadeArgs a) {
+  int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.W || y >= a.H) return;
+  size_t o = (size_t)y * a.W + x;
+  float4 vertex = __ldg(&a.pos4[o]);
+  if (vertex.x == 0.0f) { a.out[o] = make_float4(a.clear[0], a.clear[1], a.clear[2], a.clear[3]); return; }
+  float4 normal = __ldg(&a.nrm4[o]);
+  float shadow = __ldg(&a.vis[o]);
+  float specShadow = shadow - a.si;
+  float4 ev = mat4_mul(a.mv, vertex);
+  float n0 = (a.nm[0] * normal.x + a.nm[3] * normal.y) + a.nm[6] * normal.z;
+  float n1 = (a.nm[1] * normal.x + a.nm[4] * normal.y) + a.nm[7] * normal.z;
+  float n2 = (a.nm[2] * normal.x + a.nm[5] * normal.y) + a.nm[8] * normal.z;
+  { float inv = 1.0f / sqrtf((n0 * n0 + n1 * n1) + n2 * n2); n0 *= inv; n1 *= inv; n2 *= inv; }
+  float L0 = a.lpos[0] - ev.x, L1 = a.lpos[1] - ev.y, L2 = a.lpos[2] - ev.z;
+  { float inv = 1.0f / sqrtf((L0 * L0 + L1 * L1) + L2 * L2); L0 *= inv; L1 *= inv; L2 *= inv; }
+  float mx = -ev.x, my = -ev.y, mz = -ev.z, mw = -ev.w;
+  float einv = 1.0f / sqrtf(((mx * mx + my * my) + mz * mz) + mw * mw);
+  float E0 = mx * einv, E1 = my * einv, E2 = mz * einv;
+  float d = (n0 * L0 + n1 * L1) + n2 * L2;
+  float r0 = -(L0 - 2.0f * d * n0), r1 = -(L1 - 2.0f * d * n1), r2 = -(L2 - 2.0f * d * n2);
+  { float inv = 1.0f / sqrtf((r0 * r0 + r1 * r1) + r2 * r2); r0 *= inv; r1 *= inv; r2 *= inv; }
+  float ndl = g_max(d, 0.0f);
+  float rde = g_max((r0 * E0 + r1 * E1) + r2 * E2, 0.0f);
+  float pw = powf(rde, 0.3f * 10.0f);
+  float4 col = a.albedo4 ? __ldg(&a.albedo4[o]) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float cc[4] = {col.x, col.y, col.z, col.w};
+  const float amb[4] = {0.4f, 0.4f, 0.4f, 1.0f}, spec[4] = {0.25f, 0.25f, 0.25f, 1.0f}, diff[4] = {0.5f, 0.5f, 0.5f, 1.0f};
+  float res[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) res[c] = (shadow * cc[c]) * ((diff[c] * ndl + (specShadow * spec[c]) * pw) + amb[c]);
+  a.out[o] = make_float4(res[0], res[1], res[2], res[3]);
+}
+
 }  // namespace
+
+int sgi_shade_run(sgi_ctx* ctx, const float clear_rgba[4]) {
+  ShadeArgs a;
+  for (int k = 0; k < 16; k++) a.mv[k] = ctx->cam_mv[k];
+  for (int k = 0; k < 9; k++) a.nm[k] = ctx->cam_nm[k];
+  for (int k = 0; k < 3; k++) a.lpos[k] = ctx->light_pos[k];
+  for (int k = 0; k < 4; k++) a.clear[k] = clear_rgba[k];
+  a.si = ctx->params.shadow_intensity;
+  a.pos4 = (const float4*)ctx->buf[SGI_BUF_GBUF_POS]; a.nrm4 = (const float4*)ctx->buf[SGI_BUF_GBUF_NRM];
+  a.albedo4 = ctx->has_rgb ? (const float4*)ctx->buf[SGI_BUF_GBUF_ALBEDO] : nullptr;
+  a.vis = (const float*)ctx->buf[SGI_BUF_VISIBILITY]; a.out = (float4*)ctx->buf[SGI_BUF_SHADED];
+  a.W = ctx->W; a.H = ctx->H;
+  dim3 block(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+  k_shade_phong<<<grid, block, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
+}
 
 int sgi_host_pcf_offsets(int kernel_order, int penumbra_size, int inclusive, float* out, int cap) {
   // Shadow.frag:93-98 / NonConservativeSMSR.frag:313-319, evaluated in fp32 exactly as the shader's float loop

@@ -161,6 +161,7 @@ int sgh_app_render_gbuffer(sgh_app* a) { return a ? a->app.renderGBuffer() : -1;
 int sgh_app_compute_hard_shadows(sgh_app* a) { return a ? a->app.computeHardShadows() : -1; }
 int sgh_app_render_soft_shadows(sgh_app* a) { return a ? a->app.renderSoftShadows() : -1; }
 int sgh_app_render_monte_carlo(sgh_app* a) { return a ? a->app.renderMonteCarlo() : -1; }
+int sgh_app_shade_scene(sgh_app* a) { return a ? a->app.shadeScene() : -1; }
 int sgh_app_render_shadow_volumes(sgh_app* a) { return a ? a->app.renderShadowVolumes() : -1; }
 int sgh_app_display(sgh_app* a, int32_t program) {
   if (!a) return -1;

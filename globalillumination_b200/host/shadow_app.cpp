@@ -1,6 +1,7 @@
 // shadow_app.cpp — see shadow_app.h.
 #include "shadow_app.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -50,6 +51,13 @@ int ShadowApp::uploadScene() {
   int rc = sgi_set_mesh(ctx, scene.getPointCloud(), scene.getNormalVector(), scene.getPointCloudSize() / 3, scene.getIndices(),
                         scene.getNumberOfTriangles());
   if (rc) return fail(rc, "uploadScene");
+  // per-vertex colours (`c` / `cf` directives) feed the albedo target and shadeScene(); objects without a colour
+  // directive leave the reference's colour array short (Mesh::addObject): those vertices are shaded white here
+  if (scene.getColorsSize() > 0) {
+    std::vector<float> rgb((size_t)scene.getPointCloudSize(), 1.0f);
+    std::memcpy(rgb.data(), scene.getColors(), sizeof(float) * (size_t)std::min(scene.getColorsSize(), scene.getPointCloudSize()));
+    if ((rc = sgi_set_mesh_colors(ctx, rgb.data()))) return fail(rc, "sgi_set_mesh_colors");
+  } else if ((rc = sgi_set_mesh_colors(ctx, nullptr))) return fail(rc, "sgi_set_mesh_colors");
   uploaded = true;
   return 0;
 }
@@ -163,6 +171,13 @@ int ShadowApp::computeHardShadows() {
   if (rc) return rc;
   rc = sgi_compute_visibility(ctx);
   return rc ? fail(rc, "sgi_compute_visibility") : 0;
+}
+
+int ShadowApp::shadeScene() {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  const float clear[4] = {0.63f, 0.82f, 0.96f, 1.0f};        // glClearColor in shadeScene (main.cpp:453)
+  int rc = sgi_shade_phong(ctx, clear);
+  return rc ? fail(rc, "sgi_shade_phong") : 0;
 }
 
 int ShadowApp::display() {                                  // main.cpp:459-472 without shadeScene/swap

@@ -73,6 +73,7 @@ class ShadowApp {
   int renderSoftShadows();
   int renderMonteCarlo();
   int renderShadowVolumes();
+  int shadeScene();               // ShadowMapping/src/main.cpp:449-457 (deferred Phong into SGI_BUF_SHADED)
   int display();                  // ShadowMapping
   int displaySoft();              // SoftShadowMapping (PCSS or Monte-Carlo by shadowParams.monteCarlo)
   int displayShadowVolumes();     // ShadowVolumes

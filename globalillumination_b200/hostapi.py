@@ -16,7 +16,7 @@ EXPORTS = [
     "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
-    "sgh_app_render_shadow_volumes", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
+    "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
 ]
 
 _lib = None
@@ -186,6 +186,7 @@ class App:
     def render_soft_shadows(self): self._ck(self.L.sgh_app_render_soft_shadows(self.h))
     def render_monte_carlo(self): self._ck(self.L.sgh_app_render_monte_carlo(self.h))
     def render_shadow_volumes(self): self._ck(self.L.sgh_app_render_shadow_volumes(self.h))
+    def shade_scene(self): self._ck(self.L.sgh_app_shade_scene(self.h))
 
     def context(self):
         """A capi.Context view over the app's sgi_ctx (borrowed: do not close)."""

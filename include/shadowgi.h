@@ -99,7 +99,9 @@ typedef enum sgi_buffer {
   SGI_BUF_SV_STENCIL = 6,   /* uint8   [H][W]       count mod 256 (what the 8-bit stencil holds)      */
   SGI_BUF_SV_PRISM_XYZ = 7, /* float   [6T][3]      ShadowVolume::update vertices                     */
   SGI_BUF_SV_PRISM_IDX = 8, /* int32   [6T][3]      ShadowVolume::update indices                      */
-  SGI_BUF_COUNT_ = 9
+  SGI_BUF_GBUF_ALBEDO = 9,  /* float4  [H][W]       (vertex colour rgb, 1) when colours are set; bg (0,0,0,1)  */
+  SGI_BUF_SHADED = 10,      /* float4  [H][W]       deferred Phong image; background = the clear colour        */
+  SGI_BUF_COUNT_ = 11
 } sgi_buffer;
 
 /* passes that can be timed with sgi_pass_time_ms */
@@ -123,6 +125,11 @@ int sgi_set_stream(sgi_ctx* ctx, void* cuda_stream);
  * Uploaded once and kept resident (the reference re-uploads on every draw). */
 int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t num_vertices,
                  const int32_t* idx, int32_t num_triangles);
+
+/* per-vertex colours — Mesh::getColors() (`c r g b` / `cf` directives), the `color` attribute of GBuffer.vert:14,21 with
+ * useMeshColor == 1 (MyGLGeometryViewer.cpp:295-296).  rgb = 3 floats per vertex of the current mesh, or NULL to stop
+ * writing SGI_BUF_GBUF_ALBEDO (shading then uses white).  Call after sgi_set_mesh. */
+int sgi_set_mesh_colors(sgi_ctx* ctx, const float* rgb);
 
 /* camera uniforms — replaces configureAmbient + configurePhong for the camera view
  * (MyGLGeometryViewer.cpp:14-19,108-134): MVP, MV, frozen normalMatrix, window size. */
@@ -156,6 +163,10 @@ int sgi_compute_visibility(sgi_ctx* ctx);     /* computeHardShadows() :400-414 /
  * (ShadowVolumes/src/main.cpp:154-172).  light_pos = un-rotated light eye.  Needs sgi_render_gbuffer first
  * (its SGI_BUF_CAM_DEPTH is the depth pre-pass). */
 int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]);
+
+/* shadeScene(), ShadowMapping/src/main.cpp:449-457: deferred Phong shading of the G-buffer with the visibility buffer as
+ * hardShadowMap (PhongShading.frag:11-47) into SGI_BUF_SHADED; clear_rgba = glClearColor (0.63, 0.82, 0.96, 1). */
+int sgi_shade_phong(sgi_ctx* ctx, const float clear_rgba[4]);
 
 /* results */
 int sgi_read(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes);          /* blocking D2H */

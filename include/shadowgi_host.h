@@ -57,6 +57,7 @@ int sgh_app_compute_hard_shadows(sgh_app* a);
 int sgh_app_render_soft_shadows(sgh_app* a);
 int sgh_app_render_monte_carlo(sgh_app* a);
 int sgh_app_render_shadow_volumes(sgh_app* a);
+int sgh_app_shade_scene(sgh_app* a);              /* shadeScene(): deferred Phong of the last frame */
 int sgh_app_display(sgh_app* a, int32_t program);
 int sgh_app_display_e2e(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes);
 int sgh_app_display_e2e_async(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes, int32_t* ticket);

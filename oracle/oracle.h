@@ -102,6 +102,16 @@ int  orc_raster_depth(const float* xyz, int V, const int32_t* idx, int T, const 
 int  orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t* idx, int T,
                         const float mvp[16], int W, int H, float* pos4, float* nrm4, float* depth);
 
+/* same, plus the third MRT of GBuffer.frag:32-38 with useMeshColor==1: albedo4 = (interpolated vertex colour, 1),
+ * background (0,0,0,1).  rgb/albedo4 may be NULL. */
+int  orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, int V, const int32_t* idx, int T,
+                           const float mvp[16], int W, int H, float* pos4, float* nrm4, float* albedo4, float* depth);
+
+/* ---- deferred shading: ShadowMapping/Shaders/GBuffer/PhongShading.frag:11-47 (shadeScene, main.cpp:449-457) ----
+ * out4[H][W] float4; discarded (background) pixels get clear4 (0.63, 0.82, 0.96, 1). */
+void orc_shade_phong(const orc_camera* cam, float shadow_intensity, const float* pos4, const float* nrm4,
+                     const float* albedo4, const float* vis, int W, int H, const float clear4[4], float* out4);
+
 /* ---- per-pixel shadow passes ------------------------------------------------------------------ */
 /* light_mvp_b = bias*lightMVP.  vis[H][W], background pixels keep 0.                              */
 void orc_visibility(const orc_params* p, const orc_camera* cam, const float light_mvp_b[16],

@@ -197,6 +197,27 @@ def raster_gbuffer(xyz, nrm, idx, mvp, W, H):
     return pos, nr, d
 
 
+def raster_gbuffer_rgb(xyz, nrm, rgb, idx, mvp, W, H):
+    xyz, nrm, rgb, idx, mvp = _f32(xyz), _f32(nrm), _f32(rgb), _i32(idx), _f32(mvp)
+    pos, nr, alb = (np.empty((H, W, 4), np.float32) for _ in range(3))
+    d = np.empty((H, W), np.float32)
+    rc = lib().orc_raster_gbuffer_ex(_fp(xyz), _fp(nrm), _fp(rgb), xyz.size // 3, _ip(idx), idx.size // 3, _fp(mvp), W, H,
+                                     _fp(pos), _fp(nr), _fp(alb), _fp(d))
+    assert rc == 0
+    return pos, nr, alb, d
+
+
+CLEAR_COLOR = np.array([0.63, 0.82, 0.96, 1.0], np.float32)      # shadeScene, ShadowMapping/src/main.cpp:453
+
+
+def shade_phong(cam, shadow_intensity, pos4, nrm4, albedo4, vis):
+    H, W = pos4.shape[:2]
+    out = np.empty((H, W, 4), np.float32)
+    lib().orc_shade_phong(C.byref(cam), C.c_float(shadow_intensity), _fp(_f32(pos4)), _fp(_f32(nrm4)),
+                          _fp(_f32(albedo4)) if albedo4 is not None else None, _fp(_f32(vis)), W, H, _fp(CLEAR_COLOR), _fp(out))
+    return out
+
+
 def visibility(params, cam, light_mvp_b, pos4, nrm4, shadow_map):
     H, W = pos4.shape[:2]
     vis = np.zeros((H, W), np.float32)

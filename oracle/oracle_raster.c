@@ -260,7 +260,13 @@ int orc_raster_depth(const float* xyz, int V, const int32_t* idx, int T, const f
 
 int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t* idx, int T, const float mvp[16],
                        int W, int H, float* pos4, float* nrm4, float* depth) {
+  return orc_raster_gbuffer_ex(xyz, nrm, NULL, V, idx, T, mvp, W, H, pos4, nrm4, NULL, depth);
+}
+
+int orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, int V, const int32_t* idx, int T,
+                          const float mvp[16], int W, int H, float* pos4, float* nrm4, float* albedo4, float* depth) {
   (void)V;
+  const int with_rgb = rgb != NULL && albedo4 != NULL;
   int64_t n;
   SubTri* rec = build_records(xyz, idx, T, mvp, W, H, 0, 0.0f, 0.0f, &n);
   if (!rec) return -1;
@@ -268,6 +274,7 @@ int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t*
     depth[i] = 1.0f;
     pos4[4 * i + 0] = 0; pos4[4 * i + 1] = 0; pos4[4 * i + 2] = 0; pos4[4 * i + 3] = 1;
     nrm4[4 * i + 0] = 0; nrm4[4 * i + 1] = 0; nrm4[4 * i + 2] = 0; nrm4[4 * i + 3] = 1;
+    if (with_rgb) { albedo4[4 * i + 0] = 0; albedo4[4 * i + 1] = 0; albedo4[4 * i + 2] = 0; albedo4[4 * i + 3] = 1; }
   }
   int bands = H < 64 ? 1 : 64;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -281,19 +288,24 @@ int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t*
       const int32_t* ix = idx + 3 * (size_t)t;
       /* attributes of the sub-triangle's vertices: the source vertices themselves (in the record's CCW order) when
          nothing was clipped, otherwise their barycentric combination */
-      float A[3][6];
+      float A[3][9];
       for (int v = 0; v < 3; v++)
         for (int c = 0; c < 3; c++) {
+          A[v][6 + c] = 0.0f;
           if (!s->clipped) {
             int src = s->bary[v][0] == 1.0f ? 0 : (s->bary[v][1] == 1.0f ? 1 : 2);
             A[v][c] = xyz[3 * (size_t)ix[src] + c];
             A[v][3 + c] = nrm[3 * (size_t)ix[src] + c];
+            if (with_rgb) A[v][6 + c] = rgb[3 * (size_t)ix[src] + c];
             continue;
           }
           A[v][c] = (s->bary[v][0] * xyz[3 * (size_t)ix[0] + c] + s->bary[v][1] * xyz[3 * (size_t)ix[1] + c]) +
                     s->bary[v][2] * xyz[3 * (size_t)ix[2] + c];
           A[v][3 + c] = (s->bary[v][0] * nrm[3 * (size_t)ix[0] + c] + s->bary[v][1] * nrm[3 * (size_t)ix[1] + c]) +
                         s->bary[v][2] * nrm[3 * (size_t)ix[2] + c];
+          if (with_rgb)
+            A[v][6 + c] = (s->bary[v][0] * rgb[3 * (size_t)ix[0] + c] + s->bary[v][1] * rgb[3 * (size_t)ix[1] + c]) +
+                          s->bary[v][2] * rgb[3 * (size_t)ix[2] + c];
         }
       for (int j = y0; j <= y1; j++)
         for (int i = s->px0; i <= s->px1; i++) {
@@ -310,7 +322,9 @@ int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t*
           for (int c = 0; c < 3; c++) {
             pos4[4 * o + c] = ((q0 * A[0][c] + q1 * A[1][c]) + q2 * A[2][c]) * iq;
             nrm4[4 * o + c] = ((q0 * A[0][3 + c] + q1 * A[1][3 + c]) + q2 * A[2][3 + c]) * iq;
+            if (with_rgb) albedo4[4 * o + c] = ((q0 * A[0][6 + c] + q1 * A[1][6 + c]) + q2 * A[2][6 + c]) * iq;
           }
+          if (with_rgb) albedo4[4 * o + 3] = 1.0f;
           pos4[4 * o + 3] = 1.0f;
           nrm4[4 * o + 3] = s->front ? 1.0f : 0.0f;
         }

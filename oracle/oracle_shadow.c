@@ -625,3 +625,49 @@ void orc_visibility_multi(const orc_params* p, const float m[16], int N, const f
       vis[o] = p->multi_partial ? accShadow : accShadow / count;
     }
 }
+
+/* ================================ deferred Phong shading ====================================== */
+/* ShadowMapping/Shaders/GBuffer/PhongShading.frag:11-47, literally: note `vec3 E = normalize(-vertex)` normalises the
+ * vec4 (w = -1 included) before truncating to vec3, and specShadow = shadow - shadowIntensity. */
+void orc_shade_phong(const orc_camera* cam, float si, const float* pos4, const float* nrm4, const float* albedo4,
+                     const float* vis, int W, int H, const float clear4[4], float* out4) {
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      size_t o = (size_t)j * W + i;
+      float* out = out4 + 4 * o;
+      V4 vertex = {pos4[4 * o], pos4[4 * o + 1], pos4[4 * o + 2], pos4[4 * o + 3]};
+      if (vertex.x == 0.0f) { out[0] = clear4[0]; out[1] = clear4[1]; out[2] = clear4[2]; out[3] = clear4[3]; continue; }
+      float shadow = vis[o];
+      float specShadow = shadow - si;
+      V4 ev = mat4_mul_v4(cam->mv, vertex);
+      const float* nm = cam->normal_matrix;
+      float nx = nrm4[4 * o], ny = nrm4[4 * o + 1], nz = nrm4[4 * o + 2];
+      float n[3], L[3], E[3], R[3];
+      for (int k = 0; k < 3; k++) n[k] = (nm[0 + k] * nx + nm[3 + k] * ny) + nm[6 + k] * nz;
+      { float inv = 1.0f / sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]); n[0] *= inv; n[1] *= inv; n[2] *= inv; }
+      L[0] = cam->light_pos[0] - ev.x; L[1] = cam->light_pos[1] - ev.y; L[2] = cam->light_pos[2] - ev.z;
+      { float inv = 1.0f / sqrtf((L[0] * L[0] + L[1] * L[1]) + L[2] * L[2]); L[0] *= inv; L[1] *= inv; L[2] *= inv; }
+      { /* normalize(-vertex) on the vec4 */
+        float mx = -ev.x, my = -ev.y, mz = -ev.z, mw = -ev.w;
+        float inv = 1.0f / sqrtf(((mx * mx + my * my) + mz * mz) + mw * mw);
+        E[0] = mx * inv; E[1] = my * inv; E[2] = mz * inv;
+      }
+      { /* R = normalize(-reflect(L, n)), reflect(I,N) = I - 2*dot(N,I)*N */
+        float d = (n[0] * L[0] + n[1] * L[1]) + n[2] * L[2];
+        float r0 = -(L[0] - 2.0f * d * n[0]), r1 = -(L[1] - 2.0f * d * n[1]), r2 = -(L[2] - 2.0f * d * n[2]);
+        float inv = 1.0f / sqrtf((r0 * r0 + r1 * r1) + r2 * r2);
+        R[0] = r0 * inv; R[1] = r1 * inv; R[2] = r2 * inv;
+      }
+      float ndl = glsl_max((n[0] * L[0] + n[1] * L[1]) + n[2] * L[2], 0.0f);
+      float rde = glsl_max((R[0] * E[0] + R[1] * E[1]) + R[2] * E[2], 0.0f);
+      float pw = powf(rde, 0.3f * 10.0f);
+      const float amb[4] = {0.4f, 0.4f, 0.4f, 1.0f}, spec[4] = {0.25f, 0.25f, 0.25f, 1.0f}, diff[4] = {0.5f, 0.5f, 0.5f, 1.0f};
+      for (int c = 0; c < 4; c++) {
+        float col = albedo4 ? albedo4[4 * o + c] : 1.0f;
+        float Idiff = diff[c] * ndl;
+        float Ispec = (specShadow * spec[c]) * pw;
+        out[c] = (shadow * col) * ((Idiff + Ispec) + amb[c]);
+      }
+    }
+}

@@ -33,6 +33,7 @@ SHADERS = {
     "filtered": "ShadowMapping/Shaders/RBSM/FilteredRBSM.frag",
     "plausible": "SoftShadowMapping/Shaders/SoftShadow/PlausibleSoftShadow.frag",
     "accurate": "SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag",
+    "phong": "ShadowMapping/Shaders/GBuffer/PhongShading.frag",
 }
 
 

@@ -215,6 +215,7 @@ inline vec4 normalize(const vec4& v) { return v * inversesqrt(dot(v, v)); }
   inline vec4 F(const vec4& v) { return vec4(F(v.x), F(v.y), F(v.z), F(v.w)); }
 VEC_MAP1(abs) VEC_MAP1(floor) VEC_MAP1(fract) VEC_MAP1(sqrt) VEC_MAP1(exp) VEC_MAP1(log) VEC_MAP1(log2)
 #undef VEC_MAP1
+inline vec3 reflect(const vec3& I, const vec3& N) { return I - 2.0f * dot(N, I) * N; }
 inline vec2 mix(const vec2& x, const vec2& y, float a) { return x * (1.0f - a) + y * a; }
 inline vec3 mix(const vec3& x, const vec3& y, float a) { return x * (1.0f - a) + y * a; }
 inline vec4 mix(const vec4& x, const vec4& y, float a) { return x * (1.0f - a) + y * a; }

@@ -127,6 +127,15 @@ def main():
              adaptiveSamplingLowerAccuracy=np.int32(0))
     out["multi/maps"], out["multi/mvp"], out["multi/mvpb"] = maps, mvps, mvpbs
     out["multi/vis"] = O.ref_run_shader("accurate", u, W, H)[..., 0].copy()
+    # deferred shading (PhongShading.frag) of the PCF frame with seeded per-vertex colours
+    rgb = np.random.default_rng(11).uniform(0.1, 1.0, (len(sc["xyz"]), 3)).astype(np.float32)
+    _, _, alb, _ = O.raster_gbuffer_rgb(sc["xyz"], sc["nrm"], rgb, sc["idx"], fm["cam_mvp"], W, H)
+    vis_pcf = out["vis/pcf/default"]
+    hs = np.ascontiguousarray(np.stack([vis_pcf, np.zeros_like(vis_pcf), np.zeros_like(vis_pcf), np.ones_like(vis_pcf)], -1))
+    u = dict(hardShadowMap=("tex", hs), colorMap=("tex", alb), vertexMap=("tex", pos), normalMap=("tex", nrm), MV=fm["cam_mv"],
+             normalMatrix=fm["normal_matrix"], lightPosition=fm["light_pos_shading"], shadowIntensity=np.float32(0.25))
+    out["phong/rgb"], out["phong/albedo"] = rgb, alb
+    out["phong/image"] = O.ref_run_shader("phong", u, W, H)
     np.savez_compressed(os.path.join(HERE, "golden_shaders.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -387,3 +387,32 @@ def test_implementation_switches_do_not_change_results(ctx, option, value, tech,
     cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
     vis_o = O.visibility(po, cam, fm["light_mvp_b"], base[2], ctx.read("gbuf_nrm"), base[1][0])
     assert util.bits_equal(alt[0], vis_o)
+
+
+def test_albedo_target_and_phong_shading(ctx):
+    """Next-row §8f: third G-buffer target (vertex colours) bit-exact; deferred Phong image within 2e-6 relative (powf is
+    the only operation whose CPU and GPU implementations are not both correctly rounded)."""
+    sc = util.scene("teapot")
+    W, H, S = 640, 360, 512
+    rgb = np.random.default_rng(5).uniform(0.05, 1.0, (len(sc["xyz"]), 3)).astype(np.float32)
+    po, pg = util.params_pair("pcf", S)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.set_mesh_colors(rgb)
+    try:
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility(); ctx.shade_phong()
+        alb, img = ctx.read("gbuf_albedo"), ctx.read("shaded")
+        pos, nrm, vis = ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("visibility")
+        pos_o, nrm_o, alb_o, _ = O.raster_gbuffer_rgb(sc["xyz"], sc["nrm"], rgb, sc["idx"], fm["cam_mvp"], W, H)
+        assert util.bits_equal(pos, pos_o) and util.bits_equal(nrm, nrm_o)
+        assert util.bits_equal(alb, alb_o), util.describe_diff(alb, alb_o)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        img_o = O.shade_phong(cam, 0.25, pos, nrm, alb, vis)
+        assert np.allclose(img, img_o, rtol=2e-6, atol=1e-7), float(np.abs(img - img_o).max())
+        assert (img[pos[..., 0] == 0] == O.CLEAR_COLOR).all()
+    finally:
+        ctx.set_mesh_colors(None)
+    ctx.render_gbuffer(); ctx.compute_visibility(); ctx.shade_phong()           # without colours: white albedo
+    img2 = ctx.read("shaded")
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    img2_o = O.shade_phong(cam, 0.25, ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), None, ctx.read("visibility"))
+    assert np.allclose(img2, img2_o, rtol=2e-6, atol=1e-7)

@@ -107,3 +107,16 @@ def test_live_reference_shader_on_fresh_inputs(tech):
     vis = O.visibility(p, cam, fm["light_mvp_b"], pos, nrm, sm)
     ref = mg.ref_visibility(tech, fm, pos, nrm, sm, S, p, W, H)
     assert util.bits_equal(vis, ref), util.describe_diff(vis, ref)
+
+
+def test_phong_shading_matches_reference_shader_golden():
+    """Deferred shading (PhongShading.frag, next-row §8f): oracle == the reference's shader on the golden frame."""
+    g = util.golden("golden_shaders.npz")
+    fm, cam = _frame(g)
+    img = O.shade_phong(cam, 0.25, g["pos"], g["nrm"], g["phong/albedo"], g["vis/pcf/default"])
+    fg = g["pos"][..., 0] != 0
+    assert util.bits_equal(img[fg], g["phong/image"][fg])
+    assert np.allclose(img[~fg], O.CLEAR_COLOR)                       # discarded pixels keep glClearColor (main.cpp:453)
+    sc = util.scene("teapot")
+    _, _, alb, _ = O.raster_gbuffer_rgb(sc["xyz"], sc["nrm"], g["phong/rgb"], sc["idx"], fm["cam_mvp"], int(g["W"]), int(g["H"]))
+    assert util.bits_equal(alb, g["phong/albedo"])
