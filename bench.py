@@ -90,7 +90,9 @@ class ClockSampler:
 def algorithmic_bytes(w, V, T, L):
     """SURVEY.md §8(d) / BASELINE.md §3 per-frame algorithmic bytes of each pass."""
     px, S = w["W"] * w["H"], w["S"]
-    return {"shadow_map": L * (4 * S * S + 12 * (V + T)), "gbuffer": 32 * px + 12 * (V + T), "visibility": 36 * px + L * 4 * S * S}
+    # G-buffer: 32 B/px (position + normal), 48 B/px when the scene has vertex colours and the albedo target is written too
+    gb = (48 if any(l.startswith("c ") for l in w["lines"]) else 32) * px + 12 * (V + T)
+    return {"shadow_map": L * (4 * S * S + 12 * (V + T)), "gbuffer": gb, "visibility": 36 * px + L * 4 * S * S}
 
 
 def run_reference(args, w, cfg_path):
@@ -327,8 +329,17 @@ def main():
         calls = n_l if top == "tile_depth" else 1
         per_launch_ms = cand[top] / calls
         achieved = kernel_of[top][1] / (per_launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "dram_traffic_c2.json")
+        if args.workload == "c2_sponza" and os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            key = {"vis_kernel": "k_visibility", "tile_depth": "k_tile<DEPTH>", "tile_gbuffer": "k_tile<GBUFFER>"}[top]
+            if key in tj["kernels"]:
+                traffic = tj["kernels"][key]["dram_bytes_read"] + tj["kernels"][key]["dram_bytes_write"]
+                traffic_src = tj["source"]
         roof = {"bound": "hbm", "kernel": kernel_of[top][0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": kernel_of[top][1], "launch_ms": per_launch_ms, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": kernel_of[top][1], "launch_ms": per_launch_ms, "peak_source": peak_src,
                 "share_of_step": cand[top] / (total_ms / args.steps)}
     out = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
