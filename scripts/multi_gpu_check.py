@@ -1,0 +1,73 @@
+"""Multi-GPU parity check on real GPUs (run under torchrun, NCCL):
+  tiles  — every rank renders the full shadow map, its own 64-row-aligned strip of the G-buffer and of the visibility
+           (sgi_params.rect_*); strips are all-gathered; result must equal rank 0's un-sharded frame bit for bit
+  lights — every rank owns lights l = rank (mod N) of a 16-light frame; partial sums are all-reduced; result must equal
+           the un-sharded 16-light frame bit for bit
+usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/multi_gpu_check.py
+"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from globalillumination_b200 import capi, hostapi, scenes, sharding
+
+
+class DevView:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    # ---- tiles, PCF on the c2 scene at 1920x1080
+    w = scenes.WORKLOADS["c2_sponza"]
+    W, H, S = w["W"], w["H"], w["S"]
+    app = hostapi.App(local)
+    app.load_scene(scenes.write_config("c2_sponza")); app.configure(W, H, S); app.set_technique("pcf")
+    app.display("shadow_mapping")
+    full = torch.from_numpy(app.context().read("visibility")).cuda()
+    rects = sharding.strip_rects(W, H, world)
+    app.set_rect(*rects[rank])
+    app.display("shadow_mapping")
+    ctx = app.context()
+    ptr, nbytes = ctx.device_ptr("visibility")
+    ctx.synchronize()
+    vis = torch.as_tensor(DevView(ptr, nbytes // 4), device=f"cuda:{local}").view(H, W)
+    out = sharding.gather_strips(vis, rects)
+    same = bool(torch.equal(out, full))
+    ok &= same
+    if rank == 0:
+        print(f"tiles x{world}: gathered image == un-sharded image: {same} (strips {rects})", flush=True)
+    app.close()
+    # ---- lights, 16 lights, 2048x1152, 1024^2 maps
+    app = hostapi.App(local)
+    app.load_scene(scenes.write_config("c5_many_light")); app.configure(2048, 1152, 1024); app.set_technique("montecarlo")
+    app.set(numberOfSamples=16, lightSourceSize=16)
+    app.display("soft_shadow_mapping")
+    full = torch.from_numpy(app.context().read("visibility")).cuda()
+    app.set_light_shard(rank, world)
+    app.display("soft_shadow_mapping")
+    ctx = app.context()
+    ptr, nbytes = ctx.device_ptr("visibility")
+    ctx.synchronize()
+    part = torch.as_tensor(DevView(ptr, nbytes // 4), device=f"cuda:{local}").clone()
+    dist.all_reduce(part)
+    total = (part / 16.0).view(1152, 2048)
+    same = bool(torch.equal(total, full))
+    ok &= same
+    if rank == 0:
+        print(f"lights x{world}: all-reduced partial sums / 16 == un-sharded 16-light frame: {same}", flush=True)
+    app.close()
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
