@@ -123,6 +123,8 @@ int sgi_create(sgi_ctx** out, int device) {
       cudaEventCreateWithFlags(&ctx->ev_gbuf_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   { const char* e = getenv("SGI_NO_OVERLAP"); ctx->overlap_passes = !(e && e[0] == '1'); }
   { const char* e = getenv("SGI_VIS_STAGED"); ctx->vis_staged = (e && e[0] == '1') ? 1 : 0; }
+  { const char* e = getenv("SGI_TILE_SPLIT"); if (e) ctx->tile_split = atoi(e) < 0 ? 0 : atoi(e); }
+  { const char* e = getenv("SGI_TILE_ORDER"); ctx->tile_order = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("SGI_TILE_THREADS"); int v = e ? atoi(e) : 0; ctx->tile_threads = (v == 256 || v == 512 || v == 1024) ? v : 0; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
@@ -481,6 +483,8 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   if (!ctx || !name) return SGI_ERR_INVALID;
   if (!strcmp(name, "vis_staged")) ctx->vis_staged = value != 0;
   else if (!strcmp(name, "overlap_passes")) { sgi_join_gbuffer(ctx); ctx->overlap_passes = value != 0; }
+  else if (!strcmp(name, "tile_order")) ctx->tile_order = value ? 1 : 0;
+  else if (!strcmp(name, "tile_split")) ctx->tile_split = value < 0 ? 0 : value;
   else if (!strcmp(name, "tile_threads")) {
     if (value != 0 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;

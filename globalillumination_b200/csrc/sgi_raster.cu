@@ -342,11 +342,28 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
   }
 }
 
-// exclusive scan of the per-tile counts (n <= a few 10^4) in one CTA; publishes the total to the host-mapped flag word
+// exclusive scan of the per-tile counts (n <= a few 10^4) in one CTA; publishes the total to the host-mapped flag word.
+// Also emits the work items of the tile kernel (one CTA each):
+//  * adaptive subdivision: a tile whose list is much longer than the even share of the pass (total / (8 x 148 CTAs))
+//    is split into 4 sub-tiles of 32x32 or 16 of 16x16 pixels, each rasterised by its own CTA from the same list, so
+//    that hot tiles (a dense object in a few tiles, shadow-volume prisms at low resolution) do not serialise the pass
+//    on one SM.  The item count is capped by the launched grid (max_items): the threshold doubles until it fits.
+//  * launch order: busiest first (counting sort on a half-octave bucket of the item's weight), so that the long items
+//    start early and the short ones fill the tail (longest-processing-time-first; the order is irrelevant to the result).
+// item = tile | level << 20 | sub << 22, level 0/1/2 = 64/32/16-pixel region, sub = sy * (1 << level) + sx.
+__device__ __forceinline__ int split_level(int c, int w) { return c > 8 * (long long)w ? 2 : (c > 2 * (long long)w ? 1 : 0); }
+__device__ __forceinline__ int weight_bucket(int c) {
+  const int l = 31 - __clz(c | 1);
+  return c < 2 ? c : 2 * l + ((c >> (l - 1)) & 1);
+}
 __global__ void __launch_bounds__(1024) k_scan_tiles(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
-                                                     int32_t* counters, volatile int32_t* h_flags) {
+                                                     int32_t* counters, volatile int32_t* h_flags, int32_t* __restrict__ order,
+                                                     int tiles_x, int tx0, int ty0, int gx, int gy, int busiest_first,
+                                                     int max_items, int split_floor) {
   typedef cub::BlockScan<int, 1024> BlockScan;
   __shared__ typename BlockScan::TempStorage tmp;
+  __shared__ int hist[64];
+  __shared__ int s_items, s_w;
   const int per = (n + 1023) / 1024;
   const int beg = threadIdx.x * per, end = min(beg + per, n);
   int sum = 0;
@@ -357,13 +374,51 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const int32_t* __restrict__
   if (threadIdx.x == 0) {
     counters[2] = total;
     if (total > h_flags[1]) h_flags[1] = total;      // largest list size ever wanted (host grows d_pairs from it)
+    s_w = split_floor > 0 ? max(split_floor, total / (8 * 148)) : 0x7FFFFFF;
+  }
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  const int nl = gx * gy;
+  for (;;) {                                          // largest subdivision that fits the launched grid
+    __syncthreads();
+    if (threadIdx.x == 0) s_items = 0;
+    __syncthreads();
+    const int w = s_w;
+    int local = 0;
+    for (int i = threadIdx.x; i < nl; i += 1024)
+      local += 1 << (2 * split_level(cnt[(ty0 + i / gx) * tiles_x + tx0 + i % gx], w));
+    if (local) atomicAdd(&s_items, local);
+    __syncthreads();
+    if (s_items <= max_items || w >= 0x7FFFFFF) break;
+    __syncthreads();
+    if (threadIdx.x == 0) s_w = w >= 0x3FFFFFF ? 0x7FFFFFF : 2 * w;
+  }
+  const int w = s_w;
+  for (int i = threadIdx.x; i < nl; i += 1024) {
+    const int c = cnt[(ty0 + i / gx) * tiles_x + tx0 + i % gx];
+    const int lv = split_level(c, w);
+    atomicAdd(&hist[busiest_first ? weight_bucket(c >> lv) : 0], 1 << (2 * lv));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 63; b >= 0; b--) { const int h = hist[b]; hist[b] = run; run += h; }
+    counters[4] = min(run, max_items);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nl; i += 1024) {
+    const int tile = (ty0 + i / gx) * tiles_x + tx0 + i % gx;
+    const int c = cnt[tile];
+    const int lv = split_level(c, w), nsub = 1 << (2 * lv);
+    const int at = atomicAdd(&hist[busiest_first ? weight_bucket(c >> lv) : 0], nsub);
+    for (int sidx = 0; sidx < nsub; sidx++)
+      if (at + sidx < max_items) order[at + sidx] = tile | (lv << 20) | (sidx << 22);
   }
 }
 
 // ---- per-tile rasterisation ----------------------------------------------------------------------------------
 struct TileArgs {
   const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
-  const int32_t* tile_off; const int32_t* pairs; long long pair_cap;
+  const int32_t* tile_off; const int32_t* tile_order; const int32_t* pairs; long long pair_cap;
   const int32_t* big_list; const int32_t* counters;      // counters[3] = number of un-binned big triangles
   int tiles_x, tx0, ty0;
   int W, H, rx0, ry0, rx1, ry1;
@@ -468,6 +523,7 @@ struct TriQueue {
   int box[NT];                     // lx0 | ly0<<8 | lx1<<16 | ly1<<24 (tile-local inclusive bbox)
   int group[4 * NT];               // work items: queue index << 3 | group of 32 blocks (a 64x64 bbox has 128 blocks)
 };
+#define SGI_SPLIT_EXTRA 1536      // most CTAs a pass may add by subdividing hot tiles
 #define SGI_SMALL_TRI 16           // bbox candidates up to which one thread rasterises the triangle alone
 
 template <int MODE>
@@ -513,18 +569,23 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   __shared__ int bucket_cnt[SGI_ZBUCKETS], bucket_pos[SGI_ZBUCKETS];
 
   const int tid = threadIdx.x, lane = tid & 31;
-  const int tx = a.tx0 + blockIdx.x, ty = a.ty0 + blockIdx.y;
-  const int tile = ty * a.tiles_x + tx;
+  if ((int)blockIdx.x >= a.counters[4]) return;                  // the grid is an upper bound of the item count
+  const int item = a.tile_order[blockIdx.x];                     // work items of k_scan_tiles, busiest first
+  const int tile = item & 0xFFFFF, level = (item >> 20) & 3, sub = item >> 22;
+  const int rs_log2 = SGI_TILE_LOG2 - level, rs = 1 << rs_log2;  // this CTA's region of the tile: rs x rs pixels at (qx0,qy0)
+  const int qx0 = (sub & ((1 << level) - 1)) << rs_log2, qy0 = (sub >> level) << rs_log2;
+  const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
-  for (int p = tid; p < NCELL; p += NT) {
+  for (int q = tid; q < rs * rs; q += NT) {
+    const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
+    const int p = ly * SGI_PITCH + lx;
     if (MODE == SGI_MODE_DEPTH) zt[p] = ONE_BITS;
     else if ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
     else {
       ct[p] = 0;
-      int lx = p % SGI_PITCH, ly = p / SGI_PITCH;
-      int x = ox + lx, y = oy + ly;
-      sd[p] = (lx < SGI_TILE && x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
+      const int x = ox + lx, y = oy + ly;
+      sd[p] = (x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
     }
   }
   if (MODE != SGI_MODE_SVCOUNT) { if (tid < SGI_NBLK) bz[tid] = ONE_BITS; }
@@ -534,9 +595,11 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     __syncthreads();
     if (tid < SGI_NBLK) {
       const int bx = tid % (SGI_TILE / SGI_BLK_W), by = tid / (SGI_TILE / SGI_BLK_W);
+      const bool mine = bx * SGI_BLK_W >= qx0 && bx * SGI_BLK_W < qx0 + rs && by * SGI_BLK_H >= qy0 && by * SGI_BLK_H < qy0 + rs;
       float m = 0.0f;
-      for (int j = 0; j < SGI_BLK_H; j++)
-        for (int i = 0; i < SGI_BLK_W; i++) m = fmaxf(m, sd[(by * SGI_BLK_H + j) * SGI_PITCH + bx * SGI_BLK_W + i]);
+      if (mine)
+        for (int j = 0; j < SGI_BLK_H; j++)
+          for (int i = 0; i < SGI_BLK_W; i++) m = fmaxf(m, sd[(by * SGI_BLK_H + j) * SGI_PITCH + bx * SGI_BLK_W + i]);
       bz[tid] = __float_as_uint(fminf(fmaxf(m, 0.0f), 1.0f));
     }
   }
@@ -556,15 +619,20 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     if (base + tid < nitems) {
       const int it = base + tid;
       const SgiRec* rp = &a.rec[it < nlisted ? __ldg(&a.pairs[beg + it]) : __ldg(&a.big_list[it - nlisted])];
-      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rp));
-      const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-      const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(rp) + 2);
       const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rp) + 3);
       const int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
       const int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
-      const int lx0 = max(px0, ox) - ox, ly0 = max(py0, oy) - oy;
-      const int lx1 = min(px1, ox + SGI_TILE - 1) - ox, ly1 = min(py1, oy + SGI_TILE - 1) - oy;
+      const int lx0 = max(px0 - ox, qx0), ly0 = max(py0 - oy, qy0);
+      const int lx1 = min(px1 - ox, qx0 + rs - 1), ly1 = min(py1 - oy, qy0 + rs - 1);
       const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
+      // whole-tile items fetch the full record at once (nearly every listed triangle touches the tile); sub-tile items
+      // look at the bounding box first, most of the tile's list misses their region
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+      if (level == 0 || (w > 0 && h > 0)) {
+        q0 = __ldg(reinterpret_cast<const uint4*>(rp));
+        q1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+        q2 = __ldg(reinterpret_cast<const uint4*>(rp) + 2);
+      }
       if (w > 0 && h > 0) {
         const int X0 = (int)q0.x, Y0 = (int)q0.y, X1 = (int)q0.z, Y1 = (int)q0.w, X2 = (int)q1.x, Y2 = (int)q1.y;
         if (w * h <= SGI_SMALL_TRI) {
@@ -693,8 +761,8 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   __syncthreads();
 
   // ---- write the tile to HBM exactly once ------------------------------------------------------------------
-  for (int q = tid; q < SGI_TILE * SGI_TILE; q += NT) {
-    const int lx = q & (SGI_TILE - 1), ly = q >> SGI_TILE_LOG2;
+  for (int q = tid; q < rs * rs; q += NT) {
+    const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
     const int p = ly * SGI_PITCH + lx;
     const int x = ox + lx, y = oy + ly;
     if (x < a.rx0 || x >= a.rx1 || y < a.ry0 || y >= a.ry1) continue;
@@ -837,7 +905,8 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
     if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(16 + 2 * cap) * 4))) return rc;   // counters | tile_cnt | tile_fill
     sc.d_tile_cnt = sc.d_counters + 16;
     sc.d_tile_fill = sc.d_tile_cnt + cap;
-    if ((rc = grow(ctx, (void**)&sc.d_tile_off, (size_t)cap * 4))) return rc;
+    if ((rc = grow(ctx, (void**)&sc.d_tile_off, ((size_t)cap * 2 + SGI_SPLIT_EXTRA) * 4))) return rc;   // tile_off | tile_order (work items)
+    sc.d_tile_order = sc.d_tile_off + cap;
     sc.tile_cap = cap;
   }
   if (sc.pair_cap == 0) {
@@ -868,18 +937,21 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
   return SGI_OK;
 }
 
-// CTA size of the tile kernel.  The pass ends when the busiest tile ends, and a tile is worked on by one CTA, so
-// few-tile passes (<= 1200 tiles: up to 1080p / 2048^2) get 32 warps per tile; many-tile passes get 16 or 8 so that
-// the per-tile init/flush and barriers stay cheap.  Measured on B200 (profiles/r1_tile_cta_size.txt).  SGI_TILE_THREADS
-// overrides for experiments.
-static int tile_threads(const sgi_ctx* ctx, int n_tiles) {
+// CTA size of the tile kernel.  Registers cap an SM at 1024 resident threads of this kernel whatever the CTA size, so the
+// choice trades per-item latency (a hot item ends sooner with more warps) against barrier / init / flush overhead (cheaper
+// with small CTAs, and four small CTAs hide each other's barrier waits).  Few-tile passes (<= 300 tiles: up to 720p /
+// 1024^2) and shadow volumes (long lists, fill bound) get 32 warps per item, mid-size passes (<= 1200 tiles: 1080p / 2048^2)
+// 16, many-tile passes 8.  Measured on B200 with busiest-first order and hot-tile subdivision on
+// (profiles/r1_tile_cta_size.txt).  SGI_TILE_THREADS / "tile_threads" override for experiments.
+static int tile_threads(const sgi_ctx* ctx, int n_tiles, int mode) {
   if (ctx->tile_threads) return ctx->tile_threads;
-  return n_tiles <= 1200 ? 1024 : (n_tiles <= 6000 ? 512 : 256);
+  if (mode == SGI_MODE_SVCOUNT) return 1024;
+  return n_tiles <= 300 ? 1024 : (n_tiles <= 1200 ? 512 : 256);
 }
 
 template <int MODE>
-static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStream_t stream) {
-  switch (tile_threads(ctx, (int)(grid.x * grid.y))) {
+static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, int n_tiles, cudaStream_t stream) {
+  switch (tile_threads(ctx, n_tiles, MODE)) {
     case 256: return launch_tile_nt<MODE, 256>(ctx, ta, grid, stream);
     case 512: return launch_tile_nt<MODE, 512>(ctx, ta, grid, stream);
     default: return launch_tile_nt<MODE, 1024>(ctx, ta, grid, stream);
@@ -929,7 +1001,11 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   if (bin_blocks < 1) bin_blocks = 1;
   k_bin<0><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
   ctx->launches++;
-  k_scan_tiles<<<1, 1024, 0, st>>>(sc.d_tile_cnt, sc.d_tile_off, n_tiles + 1, sc.d_counters, sc.h_flags);
+  // grid of the tile kernel = upper bound of its work items: every tile of the rectangle + room for subdivided hot tiles
+  const int n_rect_tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+  const int max_items = n_rect_tiles + (15 * n_rect_tiles < SGI_SPLIT_EXTRA ? 15 * n_rect_tiles : SGI_SPLIT_EXTRA);
+  k_scan_tiles<<<1, 1024, 0, st>>>(sc.d_tile_cnt, sc.d_tile_off, n_tiles + 1, sc.d_counters, sc.h_flags, sc.d_tile_order, tiles_x,
+                                   tx0, ty0, tx1 - tx0 + 1, ty1 - ty0 + 1, ctx->tile_order, max_items, ctx->tile_split);
   ctx->launches++;
   if (!sc.sized[job.mode]) {
     // first pass of this kind on this context: size the tile lists from the real count (one sync, once)
@@ -948,7 +1024,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   TileArgs ta;
   ta.rec = sc.d_rec; ta.attr = sc.d_attr; ta.ovf_base = sc.d_ovf_base;
-  ta.tile_off = sc.d_tile_off; ta.pairs = sc.d_pairs; ta.pair_cap = sc.pair_cap;
+  ta.tile_off = sc.d_tile_off; ta.tile_order = sc.d_tile_order; ta.pairs = sc.d_pairs; ta.pair_cap = sc.pair_cap;
   ta.big_list = sc.d_big; ta.counters = sc.d_counters;
   ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
@@ -956,10 +1032,10 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.depth = job.depth; ta.pos4 = job.pos4; ta.nrm4 = job.nrm4;
   ta.rgb = job.rgb; ta.albedo4 = job.albedo4;
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
-  dim3 grid(tx1 - tx0 + 1, ty1 - ty0 + 1);
-  if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, st);
-  else if (job.mode == SGI_MODE_GBUFFER) rc = (job.rgb && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, st);
-  else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, st);
+  dim3 grid(max_items);
+  if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, n_rect_tiles, st);
+  else if (job.mode == SGI_MODE_GBUFFER) rc = (job.rgb && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, n_rect_tiles, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, n_rect_tiles, st);
+  else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
   return rc;
 }
 

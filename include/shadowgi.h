@@ -187,7 +187,8 @@ int sgi_free_host(void* host_ptr);
 /* implementation switches (experiments / A-B measurements; results are identical either way):
  *   "vis_staged"      0 (default) taps through L1/L2, 1 = PCF/PCSS stage the CTA's shadow-map window in shared memory
  *   "overlap_passes"  1 (default) G-buffer pass on the auxiliary stream, 0 = everything on the main stream
- *   "tile_threads"    0 (default) automatic, or 256 / 512 / 1024 threads per tile CTA */
+ *   "tile_threads"    0 (default) automatic, or 256 / 512 / 1024 threads per tile CTA
+ *   "tile_order"      1 (default) tile CTAs are launched busiest tile first, 0 = in raster order */
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);
 
 /* instrumentation */
