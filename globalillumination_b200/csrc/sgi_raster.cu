@@ -247,8 +247,12 @@ template <int FILL>
 __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
   const int lane = threadIdx.x & 31;
   const int nrec = a.T + a.counters[0];
-  for (int base = blockIdx.x * blockDim.x; base < nrec; base += gridDim.x * blockDim.x) {
-    const int slot = base + threadIdx.x;
+  // Records are dealt to threads through a multiplicative permutation of the index space: meshes list their large
+  // triangles (floors, walls) consecutively, and a warp holding 32 of them would walk thousands of (record, tile) pairs
+  // while the others idle; 7919 records apart, every warp gets the same mix.
+  const int nperm = gridDim.x * blockDim.x;                     // host guarantees gcd(nperm, 7919) == 1
+  for (int base = 0; base < nrec; base += nperm) {
+    const int slot = base + (int)(((long long)(blockIdx.x * blockDim.x + threadIdx.x) * 7919LL) % nperm);
     SgiRec r;
     r.prim_front = -1;
     if (slot < nrec) r = a.rec[slot];
@@ -784,12 +788,20 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         continue;
       }
       const int prim = (int)lo32, t = prim >> 3, sub = prim & 7;
-      const int slot = (sub == 0) ? t : a.ovf_base[t] + sub - 1;
-      const SgiRec r = a.rec[slot];
-      const SgiRecAttr at = a.attr[slot];
+      const int slot = (sub == 0) ? t : __ldg(&a.ovf_base[t]) + sub - 1;
+      // read-only path for every gather of the resolve: lets the loads of a pixel issue together instead of in
+      // program order behind the G-buffer stores
+      SgiRec r; SgiRecAttr at;
+      {
+        const uint4* rq = reinterpret_cast<const uint4*>(&a.rec[slot]);
+        const uint4* aq = reinterpret_cast<const uint4*>(&a.attr[slot]);
+        uint4* rd = reinterpret_cast<uint4*>(&r); uint4* ad = reinterpret_cast<uint4*>(&at);
+        rd[0] = __ldg(rq); rd[1] = __ldg(rq + 1); rd[2] = __ldg(rq + 2); rd[3] = __ldg(rq + 3);
+        ad[0] = __ldg(aq); ad[1] = __ldg(aq + 1); ad[2] = __ldg(aq + 2);
+      }
       long long E0, E1, E2;
       cover(r.X0, r.Y0, r.X1, r.Y1, r.X2, r.Y2, x, y, E0, E1, E2);
-      const int i0 = a.idx[3 * (size_t)t], i1 = a.idx[3 * (size_t)t + 1], i2 = a.idx[3 * (size_t)t + 2];
+      const int i0 = __ldg(&a.idx[3 * (size_t)t]), i1 = __ldg(&a.idx[3 * (size_t)t + 1]), i2 = __ldg(&a.idx[3 * (size_t)t + 2]);
       const float q0 = ((float)E0 * r.ia) * at.iw[0];
       const float q1 = ((float)E1 * r.ia) * at.iw[1];
       const float q2 = ((float)E2 * r.ia) * at.iw[2];
@@ -803,9 +815,9 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         const int cc = (c < 3) ? c : c - 3;
         float A0, A1, A2;
         if (r.pad0 == 0) {
-          A0 = src[3 * (size_t)i0 + cc]; A1 = src[3 * (size_t)j1 + cc]; A2 = src[3 * (size_t)j2 + cc];
+          A0 = __ldg(&src[3 * (size_t)i0 + cc]); A1 = __ldg(&src[3 * (size_t)j1 + cc]); A2 = __ldg(&src[3 * (size_t)j2 + cc]);
         } else {
-          const float s0 = src[3 * (size_t)i0 + cc], s1 = src[3 * (size_t)i1 + cc], s2 = src[3 * (size_t)i2 + cc];
+          const float s0 = __ldg(&src[3 * (size_t)i0 + cc]), s1 = __ldg(&src[3 * (size_t)i1 + cc]), s2 = __ldg(&src[3 * (size_t)i2 + cc]);
           A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
           A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
           A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
@@ -822,9 +834,9 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         for (int cc = 0; cc < 3; cc++) {
           float A0, A1, A2;
           if (r.pad0 == 0) {
-            A0 = a.rgb[3 * (size_t)i0 + cc]; A1 = a.rgb[3 * (size_t)j1 + cc]; A2 = a.rgb[3 * (size_t)j2 + cc];
+            A0 = __ldg(&a.rgb[3 * (size_t)i0 + cc]); A1 = __ldg(&a.rgb[3 * (size_t)j1 + cc]); A2 = __ldg(&a.rgb[3 * (size_t)j2 + cc]);
           } else {
-            const float s0 = a.rgb[3 * (size_t)i0 + cc], s1 = a.rgb[3 * (size_t)i1 + cc], s2 = a.rgb[3 * (size_t)i2 + cc];
+            const float s0 = __ldg(&a.rgb[3 * (size_t)i0 + cc]), s1 = __ldg(&a.rgb[3 * (size_t)i1 + cc]), s2 = __ldg(&a.rgb[3 * (size_t)i2 + cc]);
             A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
             A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
             A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
@@ -999,6 +1011,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ba.pairs = sc.d_pairs; ba.pair_cap = sc.pair_cap; ba.flags = sc.d_counters; ba.h_flags = sc.h_flags;
   int bin_blocks = (job.T + job.T / 4 + 255) / 256;   // one thread per record; the loop strides over clipped extras
   if (bin_blocks < 1) bin_blocks = 1;
+  if ((bin_blocks * 256) % 7919 == 0) bin_blocks++;   // k_bin's index permutation needs the thread count coprime to 7919
   k_bin<0><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
   ctx->launches++;
   // grid of the tile kernel = upper bound of its work items: every tile of the rectangle + room for subdivided hot tiles
