@@ -528,6 +528,7 @@ struct TriQueue {
   int group[4 * NT];               // work items: queue index << 3 | group of 32 blocks (a 64x64 bbox has 128 blocks)
 };
 #define SGI_SPLIT_EXTRA 1536      // most CTAs a pass may add by subdividing hot tiles
+#define SGI_MAX_FULL 8
 #define SGI_SMALL_TRI 16           // bbox candidates up to which one thread rasterises the triangle alone
 
 template <int MODE>
@@ -568,6 +569,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
   TriQueue<NT>& tq = *reinterpret_cast<TriQueue<NT>*>(smem_raw + PAYLOAD + SDBYTES);
   __shared__ int next_item, q_count, g_count;
+  __shared__ int fc_count, fc_list[SGI_MAX_FULL];   // queued triangles that cover this CTA's whole region (no block walk needed)
   __shared__ unsigned int bz[SGI_NBLK];          // per 8x4 block: upper bound of the stored depths (SV: of the scene depths)
   __shared__ unsigned int zq_min, zq_max;        // depth range of the queued triangles of the chunk
   __shared__ int bucket_cnt[SGI_ZBUCKETS], bucket_pos[SGI_ZBUCKETS];
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
 
   for (int base = 0; base < nitems; base += NT) {
-    if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; zq_min = 0xFFFFFFFFu; zq_max = 0u; }
+    if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; fc_count = 0; zq_min = 0xFFFFFFFFu; zq_max = 0u; }
     if (tid < SGI_ZBUCKETS) bucket_cnt[tid] = 0;
     int my_k = -1, my_ng = 0;
     unsigned int my_zlo = 0u;
@@ -662,6 +664,27 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
           // one work item per group of 32 blocks, so a triangle covering the tile is shared by 4 warps
           const int nb = (lx1 / SGI_BLK_W - lx0 / SGI_BLK_W + 1) * (ly1 / SGI_BLK_H - ly0 / SGI_BLK_H + 1);
           my_k = k; my_ng = (nb + 31) >> 5;
+          if (w == rs && h == rs) {
+            // the bounding box spans the whole region: if every edge function is inside at the region corner that
+            // minimises it (edge functions are affine), all rs x rs pixels are covered and the triangle is drawn by the
+            // whole CTA in one coalesced sweep, without block tests and per-pixel edge tests (floors, walls, SV prisms)
+            const int x0c = (ox + qx0) * SGI_SUBPIX + SGI_SUBPIX / 2, x1c = x0c + (rs - 1) * SGI_SUBPIX;
+            const int y0c = (oy + qy0) * SGI_SUBPIX + SGI_SUBPIX / 2, y1c = y0c + (rs - 1) * SGI_SUBPIX;
+            const int XA[3] = {X1, X2, X0}, YA[3] = {Y1, Y2, Y0}, XB[3] = {X2, X0, X1}, YB[3] = {Y2, Y0, Y1};
+            bool full = true;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+              const int dx = XB[e] - XA[e], dy = YB[e] - YA[e];
+              const int cx = (dy < 0) ? x0c : x1c, cy = (dx > 0) ? y0c : y1c;       // corner minimising this edge
+              const long long bias = (dy < 0 || (dy == 0 && dx < 0)) ? 0 : 1;
+              const long long v = (long long)dx * (long long)(cy - YA[e]) - ((long long)dy * (long long)(cx - XA[e]) + bias);
+              full = full && v >= 0;
+            }
+            if (full) {
+              const int f = atomicAdd(&fc_count, 1);
+              if (f < SGI_MAX_FULL) { fc_list[f] = k; my_ng = 0; }
+            }
+          }
           atomicMin(&zq_min, my_zlo); atomicMax(&zq_max, my_zlo);
         }
       }
@@ -690,6 +713,25 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     }
     __syncthreads();
     const int ngroups = g_count;
+    {  // region-covering triangles first: every thread takes its pixels of the region
+      const int nfull = min(fc_count, SGI_MAX_FULL);
+      for (int f = 0; f < nfull; f++) {
+        const int qi = fc_list[f];
+        const int X0 = tq.X0[qi], Y0 = tq.Y0[qi], X1 = tq.X1[qi], Y1 = tq.Y1[qi], X2 = tq.X2[qi], Y2 = tq.Y2[qi];
+        const float z0 = tq.z0[qi], dz1 = tq.dz1[qi], dz2 = tq.dz2[qi], ia = tq.ia[qi], zoff = tq.zoff[qi];
+        const int meta = tq.meta[qi];
+        const int dx1 = X0 - X2, dy1 = Y0 - Y2, dx2 = X1 - X0, dy2 = Y1 - Y0;
+        for (int q = tid; q < rs * rs; q += NT) {
+          const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
+          const int PX = (ox + lx) * SGI_SUBPIX + SGI_SUBPIX / 2, PY = (oy + ly) * SGI_SUBPIX + SGI_SUBPIX / 2;
+          const long long E1 = (long long)dx1 * (long long)(PY - Y2) - (long long)dy1 * (long long)(PX - X2);
+          const long long E2 = (long long)dx2 * (long long)(PY - Y0) - (long long)dy2 * (long long)(PX - X0);
+          sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+        }
+      }
+    }
+    // the per-block depth bounds only pay off when there is something to cull: refresh them only in busy chunks
+    const bool refresh_bounds = ngroups >= 8;
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&next_item, 1);
@@ -750,7 +792,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         const int lx = kbx * SGI_BLK_W + sub_x, ly = kby * SGI_BLK_H + sub_y;
         long long E1, E2;
         if (es.test(ox + lx, oy + ly, E1, E2)) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
-        if (MODE != SGI_MODE_SVCOUNT) {
+        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds) {
           // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
           const int p = ly * SGI_PITCH + lx;
           const unsigned int cur = (MODE == SGI_MODE_DEPTH) ? zt[p] : (unsigned int)(kt[p] >> 32);
