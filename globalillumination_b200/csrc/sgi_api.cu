@@ -154,6 +154,11 @@ int sgi_destroy(sgi_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_gbuf_done) cudaEventDestroy(ctx->ev_gbuf_done);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  for (int k = 0; k < SGI_LIGHT_LANES; k++) {
+    if (ctx->lane_stream[k]) { cudaStreamSynchronize(ctx->lane_stream[k]); cudaStreamDestroy(ctx->lane_stream[k]); }
+    if (ctx->ev_lane_done[k]) cudaEventDestroy(ctx->ev_lane_done[k]);
+  }
+  if (ctx->ev_lane_fork) cudaEventDestroy(ctx->ev_lane_fork);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
   for (int k = 0; k < 4; k++) if (ctx->read_done[k]) cudaEventDestroy(ctx->read_done[k]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -264,7 +269,8 @@ int sgi_set_lights(sgi_ctx* ctx, int32_t N, const float* light_mvp, const float*
     ctx->d_light_trans = nullptr;
     SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_light_trans, (size_t)N * 16));
   }
-  if (SW != ctx->SW || SH != ctx->SH) ctx->scratch[0].sized[SGI_MODE_DEPTH] = false;
+  if (SW != ctx->SW || SH != ctx->SH)
+    for (SgiScratch& sc : ctx->scratch) sc.sized[SGI_MODE_DEPTH] = false;
   ctx->N = N; ctx->SW = SW; ctx->SH = SH;
   memcpy(ctx->h_light_mvp, light_mvp, (size_t)N * 64);
   memcpy(ctx->h_light_mvp_b, light_mvp_b, (size_t)N * 64);
@@ -304,6 +310,19 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   sgi_wait_reads_of(ctx, SGI_BUF_SHADOW_MAP, ctx->stream);
   int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP, ctx->stream);
+  // one light: main stream, scratch set 0.  Several lights: dealt round-robin to SGI_LIGHT_LANES streams with their own
+  // scratch sets (forked from / joined into the main stream), so one light's binning overlaps another's tile kernel.
+  const bool lanes = ctx->N > 1 && ctx->overlap_passes;
+  if (lanes) {
+    for (int k = 0; k < SGI_LIGHT_LANES; k++)
+      if (!ctx->lane_stream[k]) {
+        SGI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[k], cudaStreamNonBlocking));
+        SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lane_done[k], cudaEventDisableTiming));
+        if (!ctx->ev_lane_fork) SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lane_fork, cudaEventDisableTiming));
+      }
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
+    for (int k = 0; k < SGI_LIGHT_LANES; k++) SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[k], ctx->ev_lane_fork, 0));
+  }
   for (int l = 0; l < ctx->N; l++) {
     SgiRasterJob job;
     memset(&job, 0, sizeof(job));
@@ -313,9 +332,15 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
     job.W = ctx->SW; job.H = ctx->SH;
     job.use_offset = 1; job.factor = ctx->params.polygon_offset_factor; job.units = ctx->params.polygon_offset_units;
     job.depth = (float*)ctx->buf[SGI_BUF_SHADOW_MAP] + (size_t)l * ctx->SW * ctx->SH;
-    int rc = sgi_raster_run(ctx, job, 0, ctx->stream);
+    const int lane = l % SGI_LIGHT_LANES;
+    int rc = lanes ? sgi_raster_run(ctx, job, 2 + lane, ctx->lane_stream[lane]) : sgi_raster_run(ctx, job, 0, ctx->stream);
     if (rc) return rc;
   }
+  if (lanes)
+    for (int k = 0; k < SGI_LIGHT_LANES; k++) {
+      SGI_CUDA(ctx, cudaEventRecord(ctx->ev_lane_done[k], ctx->lane_stream[k]));
+      SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[k], 0));
+    }
   sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot, ctx->stream);
   ctx->shadow_map_valid = true;
   return SGI_OK;

@@ -583,15 +583,35 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
-  for (int q = tid; q < rs * rs; q += NT) {
-    const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
-    const int p = ly * SGI_PITCH + lx;
-    if (MODE == SGI_MODE_DEPTH) zt[p] = ONE_BITS;
-    else if ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) kt[p] = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
-    else {
-      ct[p] = 0;
-      const int x = ox + lx, y = oy + ly;
-      sd[p] = (x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
+  long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
+  if (end > a.pair_cap) end = a.pair_cap;
+  if (beg > end) beg = end;
+  const int nlisted = (int)(end - beg), nbig = a.counters[3];
+  const int nitems = nlisted + nbig;                           // this tile's list, then the un-binned big triangles
+  const bool empty = nitems == 0;                              // nothing can touch the tile: the flush writes the clear values
+
+  if (!empty) {
+    if (MODE == SGI_MODE_DEPTH) {                              // 4 cells per store
+      const int rq_log2 = rs_log2 - 2;
+      for (int q = tid; q < (rs * rs) >> 2; q += NT) {
+        const int lx = qx0 + ((q & ((1 << rq_log2) - 1)) << 2), ly = qy0 + (q >> rq_log2);
+        *reinterpret_cast<uint4*>(&zt[ly * SGI_PITCH + lx]) = make_uint4(ONE_BITS, ONE_BITS, ONE_BITS, ONE_BITS);
+      }
+    } else if (MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB) {   // 2 cells per store
+      const int rq_log2 = rs_log2 - 1;
+      const unsigned long long clr = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
+      for (int q = tid; q < (rs * rs) >> 1; q += NT) {
+        const int lx = qx0 + ((q & ((1 << rq_log2) - 1)) << 1), ly = qy0 + (q >> rq_log2);
+        *reinterpret_cast<ulonglong2*>(&kt[ly * SGI_PITCH + lx]) = make_ulonglong2(clr, clr);
+      }
+    } else {
+      for (int q = tid; q < rs * rs; q += NT) {
+        const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
+        const int p = ly * SGI_PITCH + lx;
+        ct[p] = 0;
+        const int x = ox + lx, y = oy + ly;
+        sd[p] = (x < a.W && y < a.H) ? a.scene_depth[(size_t)y * a.W + x] : 0.0f;
+      }
     }
   }
   if (MODE != SGI_MODE_SVCOUNT) { if (tid < SGI_NBLK) bz[tid] = ONE_BITS; }
@@ -609,11 +629,6 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
       bz[tid] = __float_as_uint(fminf(fmaxf(m, 0.0f), 1.0f));
     }
   }
-  long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
-  if (end > a.pair_cap) end = a.pair_cap;
-  if (beg > end) beg = end;
-  const int nlisted = (int)(end - beg), nbig = a.counters[3];
-  const int nitems = nlisted + nbig;                           // this tile's list, then the un-binned big triangles
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
 
   for (int base = 0; base < nitems; base += NT) {
@@ -807,20 +822,40 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   __syncthreads();
 
   // ---- write the tile to HBM exactly once ------------------------------------------------------------------
+  if (MODE == SGI_MODE_DEPTH) {
+    // four texels per thread and store: 16-byte stores when the row pitch allows it
+    const int rq_log2 = rs_log2 - 2;
+    const bool vec_ok = (a.W & 3) == 0;
+    for (int q = tid; q < (rs * rs) >> 2; q += NT) {
+      const int lx = qx0 + ((q & ((1 << rq_log2) - 1)) << 2), ly = qy0 + (q >> rq_log2);
+      const int x = ox + lx, y = oy + ly;
+      if (y < a.ry0 || y >= a.ry1 || x + 3 < a.rx0 || x >= a.rx1) continue;
+      const uint4 v = empty ? make_uint4(ONE_BITS, ONE_BITS, ONE_BITS, ONE_BITS)
+                            : *reinterpret_cast<const uint4*>(&zt[ly * SGI_PITCH + lx]);
+      float* dst = a.depth + (size_t)y * a.W + x;
+      if (vec_ok && x >= a.rx0 && x + 3 < a.rx1) {
+        *reinterpret_cast<uint4*>(dst) = v;
+      } else {
+        const unsigned int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (x + i >= a.rx0 && x + i < a.rx1) dst[i] = __uint_as_float(vv[i]);
+      }
+    }
+    return;
+  }
   for (int q = tid; q < rs * rs; q += NT) {
     const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
     const int p = ly * SGI_PITCH + lx;
     const int x = ox + lx, y = oy + ly;
     if (x < a.rx0 || x >= a.rx1 || y < a.ry0 || y >= a.ry1) continue;
     const size_t o = (size_t)y * a.W + x;
-    if (MODE == SGI_MODE_DEPTH) {
-      a.depth[o] = __uint_as_float(zt[p]);
-    } else if (MODE == SGI_MODE_SVCOUNT) {
-      const int c = ct[p];
+    if (MODE == SGI_MODE_SVCOUNT) {
+      const int c = empty ? 0 : ct[p];
       a.count[o] = c;
       a.stencil[o] = (uint8_t)((unsigned int)c & 255u);
     } else {
-      const unsigned long long key = kt[p];
+      const unsigned long long key = empty ? 0xFFFFFFFFull : kt[p];
       const unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
       if (lo32 == 0xFFFFFFFFu) {
         a.depth[o] = 1.0f;
