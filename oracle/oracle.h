@@ -47,7 +47,8 @@ enum {
   ORC_TECH_RPCF_NONCONS = 5,  /* NonConservativeSMSR.frag RPCFPlusSMSR==1              */
   ORC_TECH_RPCF_CONS = 6,     /* ConservativeSMSR.frag RPCFPlusSMSR==1                 */
   ORC_TECH_RSMSS = 7,         /* FilteredRBSM.frag (always the accurate-RPCF branch)   */
-  ORC_TECH_MULTI_HARD = 8     /* AccurateSoftShadow.frag monteCarlo (N lights)         */
+  ORC_TECH_MULTI_HARD = 8,    /* AccurateSoftShadow.frag monteCarlo (N lights)         */
+  ORC_TECH_RBSSM = 9          /* RBSSM.frag (revectorization-based soft shadows)       */
 };
 
 enum { ORC_DEPTH_LESS = 0, ORC_DEPTH_LEQUAL = 1 };

@@ -15,7 +15,7 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 TECH = {
     "hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4,
-    "rpcf_noncons": 5, "rpcf_cons": 6, "rsmss": 7, "multi_hard": 8,
+    "rpcf_noncons": 5, "rpcf_cons": 6, "rsmss": 7, "multi_hard": 8, "rbssm": 9,
 }
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
 

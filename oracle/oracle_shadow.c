@@ -554,6 +554,8 @@ static float cs_rpcf(Rb* r, V4 c) {
   return illuminationCount / (float)count;
 }
 
+#include "oracle_rbssm_impl.h"   /* RBSSM.frag: ss_rbssm */
+
 /* ================================ drivers ===================================================== */
 void orc_visibility(const orc_params* p, const orc_camera* cam, const float light_mvp_b[16], const float* pos4,
                     const float* nrm4, int W, int H, const float* shadow_map, float* vis) {
@@ -575,10 +577,11 @@ void orc_visibility(const orc_params* p, const orc_camera* cam, const float ligh
       V4 sc = mat4_mul_v4(light_mvp_b, vertex);
       V4 c = {sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w};
       float shadow = pre_evaluation(cam, p->shadow_intensity, vertex, normal);
-      if (tech == ORC_TECH_HARD || tech == ORC_TECH_PCF || tech == ORC_TECH_PCSS) {
-        if (sc.w > 0.0f && shadow == 1.0f) {               /* Shadow.frag:251 / PlausibleSoftShadow.frag:616 */
+      if (tech == ORC_TECH_HARD || tech == ORC_TECH_PCF || tech == ORC_TECH_PCSS || tech == ORC_TECH_RBSSM) {
+        if (sc.w > 0.0f && shadow == 1.0f) {               /* Shadow.frag:251 / PlausibleSoftShadow.frag:616 / RBSSM.frag:1372 */
           if (tech == ORC_TECH_HARD) shadow = (c.z <= sm_fetch(&s, c.x, c.y)) ? 1.0f : p->shadow_intensity;
           else if (tech == ORC_TECH_PCF) shadow = pcf(p, &s, c);
+          else if (tech == ORC_TECH_RBSSM) shadow = ss_rbssm(&r, c);
           else shadow = pcss(p, &s, c);
         }
       } else if (shadow == 1.0f) {                         /* NonConservativeSMSR.frag:379 */

@@ -34,6 +34,7 @@ SHADERS = {
     "plausible": "SoftShadowMapping/Shaders/SoftShadow/PlausibleSoftShadow.frag",
     "accurate": "SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag",
     "phong": "ShadowMapping/Shaders/GBuffer/PhongShading.frag",
+    "rbssm": "SoftShadowMapping/Shaders/SoftShadow/RBSSM.frag",
 }
 
 
@@ -61,9 +62,19 @@ UNIFORM = re.compile(r"^\s*uniform\s+(\w+)\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?\s*;")
 PLAIN_GLOBAL = re.compile(r"^(float|int|bool|vec[234]|mat[34])\s+\w+\s*;")
 
 
+# Type leniencies of the GLSL compiler the reference was written against (NVIDIA's accepts a float where a vec4 return
+# type is declared and assigns the vec4 back to a float through .x): stated here as the equivalent declaration.
+DECL_FIXES = {
+    "vec4 revectorizationBasedShadowMappingSmoothing(vec4 normalizedShadowCoord)":
+        "float revectorizationBasedShadowMappingSmoothing(vec4 normalizedShadowCoord)",     # RBSSM.frag:1341 (every return is a float)
+}
+
+
 def transform(src):
     """Literal suffixes, drop #extension, thread_local file-scope variables. Returns (text, uniforms)."""
     out, uniforms, depth = [], [], 0
+    for a, b in DECL_FIXES.items():
+        src = src.replace(a, b)
     for line in src.splitlines():
         if line.lstrip().startswith("#extension"):
             out.append("// " + line)

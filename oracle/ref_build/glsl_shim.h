@@ -203,6 +203,8 @@ inline float max(float a, float b) { return a < b ? b : a; }
 inline float min(float a, float b) { return b < a ? b : a; }
 inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
 inline float mix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+inline float step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+inline float mod(float x, float y) { return x - y * std::floor(x / y); }
 inline float dot(const vec2& a, const vec2& b) { return a.x * b.x + a.y * b.y; }
 inline float dot(const vec3& a, const vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline float dot(const vec4& a, const vec4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }

@@ -42,6 +42,7 @@ SHADER_OF = {
     "rpcf_noncons": ("nonconservative", dict(SMSR=0, RPCFPlusSMSR=1)),
     "rpcf_cons": ("conservative", dict(SMSR=0, RPCFPlusSMSR=1)),
     "rsmss": ("filtered", dict(SMSR=0, RPCFPlusSMSR=1)),
+    "rbssm": ("rbssm", dict()),
 }
 
 

@@ -7,7 +7,7 @@ import pytest
 from oracle import oracle_py as O
 from tests import util
 
-TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss"]
+TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss", "rbssm"]
 ALT = dict(kernel_order=9, kernel_size=7, shadow_intensity=0.5, max_search=8)
 
 
