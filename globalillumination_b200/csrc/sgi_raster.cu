@@ -842,9 +842,8 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
           if (x + i >= a.rx0 && x + i < a.rx1) dst[i] = __uint_as_float(vv[i]);
       }
     }
-    return;
   }
-  for (int q = tid; q < rs * rs; q += NT) {
+  for (int q = tid; MODE != SGI_MODE_DEPTH && q < rs * rs; q += NT) {
     const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
     const int p = ly * SGI_PITCH + lx;
     const int x = ox + lx, y = oy + ly;

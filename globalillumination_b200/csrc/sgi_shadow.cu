@@ -482,6 +482,8 @@ __device__ float cs_rpcf(Rb& r, const VisArgs& a, float4 c) {
   return illum / (float)(n * n);
 }
 
+#include "sgi_rbssm.cuh"
+
 // ================================ kernels ========================================================
 // VA / VB: compile-time tap counts of the specialised variants (PCF: VA = taps per axis; PCSS: VA = blocker taps,
 // VB = filter taps; 0 = generic run-time loops)
@@ -497,9 +499,13 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
   float shadow = pre_evaluation(a, vertex, normal);
   Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
-  if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS) {
+  if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS || TECH == SGI_TECH_RBSSM) {
     if (sc.w > 0.0f && shadow == 1.0f) {
       if (TECH == SGI_TECH_HARD) shadow = (c.z <= sm_fetch(s, c.x, c.y)) ? 1.0f : a.p.shadow_intensity;
+      else if (TECH == SGI_TECH_RBSSM) {                             // RBSSM.frag:1372-1373
+        Rb r = {s, a.sx, a.sy, a.p.depth_threshold, a.p.max_search, a.p.shadow_intensity, 0, a.fw, a.fh, 0.0f};
+        shadow = ss_rbssm(a, r, c);
+      }
       else if (TECH == SGI_TECH_PCF) { const TapSrc<false> g = {s.d, s.w, 0, 0}; shadow = pcf_t<VA, false>(a, s, g, c); }
       else shadow = pcss_t<VA, VB>(a, s, c);
     }
@@ -777,6 +783,7 @@ int sgi_shadow_run(sgi_ctx* ctx) {
     case SGI_TECH_RPCF_CONS: k_visibility<SGI_TECH_RPCF_CONS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_RSMSS: k_visibility<SGI_TECH_RSMSS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_MULTI_HARD: k_visibility_multi<<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RBSSM: k_visibility<SGI_TECH_RBSSM, 0, 0><<<grid, block, 0, st>>>(a); break;
     default: ctx->err = "unknown technique"; return SGI_ERR_INVALID;
   }
   ctx->launches++;

@@ -119,7 +119,7 @@ int sgh_app_set_technique(sgh_app* a, const char* name) {
   ShadowParams& p = a->app.shadowParams;
   p.naive = p.SMSR = p.RPCFPlusSMSR = p.RSMSS = p.RPCFPlusRSMSS = p.EDTSM = p.conservative = false;
   p.VSM = p.ESM = p.EVSM = p.MSM = p.tricubicPCF = false;
-  p.bilinearPCF = true; p.PCSS = true; p.monteCarlo = false;
+  p.bilinearPCF = true; p.PCSS = true; p.monteCarlo = false; p.RBSSM = false;
   std::string n(name);
   if (n == "naive" || n == "hard") p.naive = true;
   else if (n == "pcf" || n == "bilinearPCF") {}
@@ -129,6 +129,7 @@ int sgh_app_set_technique(sgh_app* a, const char* name) {
   else if (n == "rpcf" || n == "rpcf_noncons") p.RPCFPlusSMSR = true;
   else if (n == "rpcf_conservative" || n == "rpcf_cons") { p.RPCFPlusSMSR = true; p.conservative = true; }
   else if (n == "rsmss") p.RSMSS = true;
+  else if (n == "rbssm" || n == "RBSSM") p.RBSSM = true;
   else if (n == "montecarlo" || n == "multi_hard") p.monteCarlo = true;
   else { g_err = "unknown technique " + n; return -2; }
   return 0;

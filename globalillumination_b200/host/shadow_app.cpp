@@ -191,8 +191,8 @@ int ShadowApp::renderSoftShadows() {                        // SoftShadowMapping
   int rc;
   if ((rc = renderGBuffer())) return rc;
   if ((rc = renderShadowMap())) return rc;
-  if (!shadowParams.PCSS) { err = "renderSoftShadows: only the PCSS branch is on the hot path (SURVEY.md C17/C18)"; return SGI_ERR_INVALID; }
-  if ((rc = pushParams(SGI_TECH_PCSS))) return rc;
+  if (!shadowParams.PCSS && !shadowParams.RBSSM) { err = "renderSoftShadows: only the PCSS and RBSSM branches are built (SURVEY.md C17/C18)"; return SGI_ERR_INVALID; }
+  if ((rc = pushParams(shadowParams.RBSSM ? SGI_TECH_RBSSM : SGI_TECH_PCSS))) return rc;      // main.cpp:1012-1013
   rc = sgi_compute_visibility(ctx);
   return rc ? fail(rc, "sgi_compute_visibility") : 0;
 }

@@ -39,7 +39,7 @@ struct ShadowParams {
   bool SMSR = false, RPCFPlusSMSR = false, RSMSS = false, RPCFPlusRSMSS = false, EDTSM = false;
   bool useHardShadowMap = false, conservative = false;
   // SoftShadowMapping additions
-  bool PCSS = true, monteCarlo = false;
+  bool PCSS = true, monteCarlo = false, RBSSM = false;   // SoftShadowMapping/include/Viewers/ShadowParams.h:45
   int blockerSearchSize = 7, kernelSize = 15, lightSourceRadius = 8, numberOfSamples = 289;
   int lightSourceSize = 16;       // LightSource::size of the area light
   int windowWidth = 1024, windowHeight = 1024;

@@ -55,7 +55,8 @@ typedef enum sgi_technique {
   SGI_TECH_RPCF_NONCONS = 5,  /* NonConservativeSMSR.frag, RPCFPlusSMSR     (:306-349)                       */
   SGI_TECH_RPCF_CONS = 6,     /* ConservativeSMSR.frag, RPCFPlusSMSR        (:146-198)                       */
   SGI_TECH_RSMSS = 7,         /* FilteredRBSM.frag                          (:241,266-272,381-383)           */
-  SGI_TECH_MULTI_HARD = 8     /* AccurateSoftShadow.frag, monteCarlo        (:52-133), N lights              */
+  SGI_TECH_MULTI_HARD = 8,    /* AccurateSoftShadow.frag, monteCarlo        (:52-133), N lights              */
+  SGI_TECH_RBSSM = 9          /* SoftShadow/RBSSM.frag: revectorization-based soft shadows (:1202-1376)     */
 } sgi_technique;
 
 typedef enum sgi_depth_func { SGI_DEPTH_LESS = 0, SGI_DEPTH_LEQUAL = 1 } sgi_depth_func;

@@ -7,3 +7,5 @@ python scripts/perf_probe.py teapot 7680 4320 8192 hard 10
 python scripts/perf_probe.py sv tree 640 480
 python scripts/perf_probe.py sv dragon 1920 1080
 python scripts/perf_probe.py app c5_many_light 5
+python scripts/perf_probe.py teapot 1920 1080 2048 rbssm 5
+python scripts/perf_probe.py dragon 1920 1080 2048 rbssm 5

@@ -14,7 +14,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 SOFT_TOL = 1e-3
-TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss"]
+TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss", "rbssm"]
 
 
 @pytest.fixture(scope="module")
@@ -56,7 +56,7 @@ def test_depth_and_gbuffer_bit_exact(ctx, name, W, H, S):
 @pytest.mark.parametrize("tech", TECHS)
 @pytest.mark.parametrize("name,W,H,S", [("teapot", 320, 180, 256), ("teapot", 1280, 720, 1024)])
 def test_visibility_bit_exact(ctx, name, W, H, S, tech):
-    if tech in ("rpcf_noncons", "rpcf_cons", "rsmss") and W > 640:
+    if tech in ("rpcf_noncons", "rpcf_cons", "rsmss", "rbssm") and W > 640:
         W, H = 640, 360                                   # the oracle needs seconds per frame for 64x RBSM taps
     sc = util.scene(name)
     po, pg = util.params_pair(tech, S, depth_threshold=float(sc["depth_threshold"]))
@@ -77,7 +77,7 @@ def test_visibility_bit_exact(ctx, name, W, H, S, tech):
 
 @pytest.mark.parametrize("kw", [dict(kernel_order=9, shadow_intensity=0.5), dict(kernel_order=15, penumbra_size=2),
                                 dict(kernel_size=7, blocker_search_size=5, light_source_radius=4), dict(max_search=4, kernel_order=3)])
-@pytest.mark.parametrize("tech", ["pcf", "pcss", "rbsm_noncons", "rpcf_cons", "rsmss"])
+@pytest.mark.parametrize("tech", ["pcf", "pcss", "rbsm_noncons", "rpcf_cons", "rsmss", "rbssm"])
 def test_visibility_parameter_sweep(ctx, tech, kw):
     sc = util.scene("teapot")
     W, H, S = 256, 144, 200
