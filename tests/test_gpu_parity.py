@@ -367,10 +367,12 @@ def test_pipelined_readback_and_double_buffered_mesh(ctx):
         lib.sgi_free_host(p)
 
 
-@pytest.mark.parametrize("option,value", [("vis_staged", 1), ("overlap_passes", 0), ("tile_threads", 256), ("tile_threads", 512)])
+@pytest.mark.parametrize("option,value", [("vis_staged", 1), ("overlap_passes", 0), ("tile_threads", 256), ("tile_threads", 512), ("tile_threads", 1024),
+                                          ("tile_order", 0), ("tile_split", 0), ("tile_split", 16)])
 @pytest.mark.parametrize("tech,name,W,H,S", [("pcss", "teapot", 640, 360, 512), ("pcf", "raptor", 333, 217, 300), ("pcss", "dragon", 1920, 1080, 4096)])
 def test_implementation_switches_do_not_change_results(ctx, option, value, tech, name, W, H, S):
-    """Shared-memory staged taps, single-stream execution and every tile-CTA size give the same bits as the defaults."""
+    """Shared-memory staged taps, single-stream execution, every tile-CTA size, raster-order tile launch, no / aggressive
+    hot-tile subdivision: all give the same bits as the defaults."""
     sc = util.scene(name)
     po, pg = util.params_pair(tech, S, kernel_size=15 if name != "raptor" else 9)
     fm = setup_frame(ctx, sc, W, H, S, pg)
@@ -381,7 +383,7 @@ def test_implementation_switches_do_not_change_results(ctx, option, value, tech,
         ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
         alt = (ctx.read("visibility"), ctx.read("shadow_map"), ctx.read("gbuf_pos"))
     finally:
-        ctx.set_option(option, {"vis_staged": 0, "overlap_passes": 1, "tile_threads": 0}[option])
+        ctx.set_option(option, {"vis_staged": 0, "overlap_passes": 1, "tile_threads": 0, "tile_order": 1, "tile_split": 256}[option])
     for a, b in zip(base, alt):
         assert util.bits_equal(a, b), (option, util.describe_diff(a, b))
     cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
