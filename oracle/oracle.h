@@ -48,7 +48,9 @@ enum {
   ORC_TECH_RPCF_CONS = 6,     /* ConservativeSMSR.frag RPCFPlusSMSR==1                 */
   ORC_TECH_RSMSS = 7,         /* FilteredRBSM.frag (always the accurate-RPCF branch)   */
   ORC_TECH_MULTI_HARD = 8,    /* AccurateSoftShadow.frag monteCarlo (N lights)         */
-  ORC_TECH_RBSSM = 9          /* RBSSM.frag (revectorization-based soft shadows)       */
+  ORC_TECH_RBSSM = 9,         /* RBSSM.frag (revectorization-based soft shadows)       */
+  ORC_TECH_EDTSM_NONCONS = 10,/* EDT shadow mapping over NonConservativeSMSR.frag      */
+  ORC_TECH_EDTSM_CONS = 11    /* EDT shadow mapping over ConservativeSMSR.frag         */
 };
 
 enum { ORC_DEPTH_LESS = 0, ORC_DEPTH_LEQUAL = 1 };
@@ -122,6 +124,18 @@ void orc_visibility(const orc_params* p, const orc_camera* cam, const float ligh
 void orc_visibility_multi(const orc_params* p, const float light_mvp_b_common[16], int N,
                           const float* trans4, const float* pos4, int W, int H,
                           const float* shadow_maps, float* vis);
+
+/* ---- EDT shadow mapping (oracle_edt_impl.h) --------------------------------------------------- */
+void orc_edt_hard_image(const orc_params* p, const orc_camera* cam, const float cam_mvp[16], const float light_mvp_b[16],
+                        const float* pos4, const float* nrm4, int W, int H, const float* shadow_map, float* img4);
+void orc_edt_sites(const float* img4, int W, int H, int16_t* site2);
+void orc_edt_nearest(const int16_t* site2, int W, int H, int16_t* near2);
+void orc_edt_normalize(const float* img4, const float* pos4, const int16_t* near2, int W, int H, float penumbraSize,
+                       float shadowIntensity, float* out2);
+void orc_mean_filter(const float* in2, const float* pos4, const float cam_mv[16], int W, int H, int order, int horizontal,
+                     int z_near, int z_far, int linear, float* out2);
+void orc_edtsm(const orc_params* p, const orc_camera* cam, const float cam_mvp[16], const float light_mvp_b[16],
+               const float* pos4, const float* nrm4, int W, int H, const float* shadow_map, float* vis, int16_t* near2_out);
 
 /* ---- shadow volumes --------------------------------------------------------------------------- */
 /* prism_xyz: 6T vertices*3, prism_idx: 6T triangles*3 (ShadowVolume::build/update)                */

@@ -15,7 +15,7 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 TECH = {
     "hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4,
-    "rpcf_noncons": 5, "rpcf_cons": 6, "rsmss": 7, "multi_hard": 8, "rbssm": 9,
+    "rpcf_noncons": 5, "rpcf_cons": 6, "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11,
 }
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
 
@@ -226,6 +226,64 @@ def visibility(params, cam, light_mvp_b, pos4, nrm4, shadow_map):
     return vis
 
 
+EDT_MARKER = -32768
+
+
+def edt_hard_image(params, cam, cam_mvp, light_mvp_b, pos4, nrm4, shadow_map):
+    """(shadow, camera depth, pre-evaluated shadow, 1) target of the RBSM shaders with EDTSM == 1."""
+    H, W = pos4.shape[:2]
+    img = np.zeros((H, W, 4), np.float32)
+    lib().orc_edt_hard_image(C.byref(params), C.byref(cam), _fp(_f32(cam_mvp)), _fp(_f32(light_mvp_b)), _fp(_f32(pos4)),
+                             _fp(_f32(nrm4)), W, H, _fp(_f32(shadow_map)), _fp(img))
+    return img
+
+
+def _i16p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int16))
+
+
+def edt_sites(img4):
+    H, W = img4.shape[:2]
+    out = np.empty((H, W, 2), np.int16)
+    lib().orc_edt_sites(_fp(_f32(img4)), W, H, _i16p(out))
+    return out
+
+
+def edt_nearest(site2):
+    site2 = np.ascontiguousarray(site2, np.int16)
+    H, W = site2.shape[:2]
+    out = np.empty((H, W, 2), np.int16)
+    lib().orc_edt_nearest(_i16p(site2), W, H, _i16p(out))
+    return out
+
+
+def edt_normalize(img4, pos4, near2, penumbra_size, shadow_intensity):
+    H, W = img4.shape[:2]
+    near2 = np.ascontiguousarray(near2, np.int16)
+    out = np.empty((H, W, 2), np.float32)
+    lib().orc_edt_normalize(_fp(_f32(img4)), _fp(_f32(pos4)), _i16p(near2), W, H, C.c_float(penumbra_size),
+                            C.c_float(shadow_intensity), _fp(out))
+    return out
+
+
+def mean_filter(in2, pos4, cam_mv, order, horizontal, z_near=1, z_far=1000, linear=False):
+    H, W = pos4.shape[:2]
+    out = np.empty((H, W, 2), np.float32)
+    lib().orc_mean_filter(_fp(_f32(in2)), _fp(_f32(pos4)), _fp(_f32(cam_mv)), W, H, int(order), int(bool(horizontal)),
+                          int(z_near), int(z_far), int(bool(linear)), _fp(out))
+    return out
+
+
+def edtsm(params, cam, cam_mvp, light_mvp_b, pos4, nrm4, shadow_map):
+    """Whole EDTSM pass sequence; returns (visibility[H,W], nearest site[H,W,2] int16)."""
+    H, W = pos4.shape[:2]
+    vis = np.zeros((H, W), np.float32)
+    near = np.empty((H, W, 2), np.int16)
+    lib().orc_edtsm(C.byref(params), C.byref(cam), _fp(_f32(cam_mvp)), _fp(_f32(light_mvp_b)), _fp(_f32(pos4)), _fp(_f32(nrm4)),
+                    W, H, _fp(_f32(shadow_map)), _fp(vis), _i16p(near))
+    return vis, near
+
+
 def visibility_multi(params, light_mvp_b_common, trans4, pos4, shadow_maps):
     H, W = pos4.shape[:2]
     trans4 = _f32(trans4)
@@ -312,7 +370,9 @@ def ref_run_shader(name, uniforms, W, H, rect=None):
     for k, v in uniforms.items():
         if isinstance(v, tuple) and v[0] == "tex":
             a = _f32(v[1])
-            if a.ndim == 2:
+            if len(v) >= 3 and v[2] == "linear":       # RGBA32F with GL_LINEAR (level 0)
+                s = _Sampler(a.ctypes.data, a.shape[1], a.shape[0], 4 | 0x100, 1)
+            elif a.ndim == 2:
                 s = _Sampler(a.ctypes.data, a.shape[1], a.shape[0], 1, 1)
             elif a.ndim == 3 and a.shape[2] == 4 and len(v) < 3:
                 s = _Sampler(a.ctypes.data, a.shape[1], a.shape[0], 4, 1)

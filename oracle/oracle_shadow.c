@@ -5,6 +5,7 @@
  */
 #include "oracle.h"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* ================================ matrices ==================================================== */
@@ -674,3 +675,5 @@ void orc_shade_phong(const orc_camera* cam, float si, const float* pos4, const f
       }
     }
 }
+
+#include "oracle_edt_impl.h"    /* EDT shadow mapping: orc_edt_*, orc_mean_filter, orc_edtsm */

@@ -35,6 +35,7 @@ SHADERS = {
     "accurate": "SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag",
     "phong": "ShadowMapping/Shaders/GBuffer/PhongShading.frag",
     "rbssm": "SoftShadowMapping/Shaders/SoftShadow/RBSSM.frag",
+    "meanfilter": "ShadowMapping/Shaders/Filter/MeanFilter.frag",
 }
 
 

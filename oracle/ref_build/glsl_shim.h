@@ -231,21 +231,37 @@ inline vec2 clamp(const vec2& v, float lo, float hi) { return vec2(clamp(v.x, lo
 struct Sampler {            // bound by the runner; plain data so it can be memcpy'd in
   const float* data;
   int32_t w, h;
-  int32_t channels;         // 1 = depth texture (returns d,d,d,1), 4 = RGBA32F
+  int32_t channels;         // 1 = depth texture (returns d,d,d,1), 4 = RGBA32F; | 0x100 = GL_LINEAR (level 0) instead of GL_NEAREST
   int32_t layers;
 };
 typedef Sampler sampler2D;
 typedef Sampler sampler2DArray;
 
-inline vec4 sampler_fetch(const Sampler& s, float u, float v, int layer) {
+inline vec4 sampler_texel(const Sampler& s, float fi, float fj, int layer) {     // integer texel coordinates as floats
   float fw = (float)s.w, fh = (float)s.h;
-  float fi = std::floor(u * fw), fj = std::floor(v * fh);
+  const int ch = s.channels & 0xFF;
   if (!(fi >= 0.0f && fi < fw && fj >= 0.0f && fj < fh) || layer < 0 || layer >= (s.layers > 0 ? s.layers : 1))
-    return s.channels == 1 ? vec4(0.0f, 0.0f, 0.0f, 1.0f) : vec4(0.0f);
+    return ch == 1 ? vec4(0.0f, 0.0f, 0.0f, 1.0f) : vec4(0.0f);
   size_t o = ((size_t)layer * s.h + (size_t)(int)fj) * s.w + (size_t)(int)fi;
-  if (s.channels == 1) { float d = s.data[o]; return vec4(d, d, d, 1.0f); }
+  if (ch == 1) { float d = s.data[o]; return vec4(d, d, d, 1.0f); }
   const float* p = s.data + 4 * o;
   return vec4(p[0], p[1], p[2], p[3]);
+}
+inline vec4 sampler_fetch(const Sampler& s, float u, float v, int layer) {
+  float fw = (float)s.w, fh = (float)s.h;
+  if (s.channels & 0x100) {
+    // GL_LINEAR of level 0 (the level of detail of a GL_LINEAR_MIPMAP_LINEAR lookup inside a data-dependent loop is
+    // undefined): weights from fract(u*size - 0.5), texels accumulated in the order 00,10,01,11
+    float x = u * fw - 0.5f, y = v * fh - 0.5f;
+    float x0 = std::floor(x), y0 = std::floor(y), ax = x - x0, ay = y - y0;
+    vec4 acc(0.0f);
+    for (int k = 0; k < 4; k++) {
+      float wgt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+      acc = acc + sampler_texel(s, x0 + (float)(k & 1), y0 + (float)(k >> 1), layer) * wgt;
+    }
+    return acc;
+  }
+  return sampler_texel(s, std::floor(u * fw), std::floor(v * fh), layer);
 }
 inline vec4 texture2D(const Sampler& s, const vec2& c) { return sampler_fetch(s, c.x, c.y, 0); }
 inline vec4 texture(const Sampler& s, const vec2& c) { return sampler_fetch(s, c.x, c.y, 0); }

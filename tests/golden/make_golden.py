@@ -137,6 +137,26 @@ def main():
              normalMatrix=fm["normal_matrix"], lightPosition=fm["light_pos_shading"], shadowIntensity=np.float32(0.25))
     out["phong/rgb"], out["phong/albedo"] = rgb, alb
     out["phong/image"] = O.ref_run_shader("phong", u, W, H)
+    # EDT shadow mapping: the RBSM shaders' EDTSM target and both MeanFilter.frag passes (the CUDA stages between them -
+    # site detection, Voronoi diagram, normalisation - have no compilable reference: oracle restatement, see its header)
+    for tech, shader in (("edtsm_noncons", "nonconservative"), ("edtsm_cons", "conservative")):
+        p = O.default_params(tech, S, depth_threshold=float(sc["depth_threshold"]), penumbra_size=5)
+        u = shader_uniforms(fm, pos, nrm, sm, S, p)
+        u.update(dict(SMSR=np.int32(0), RPCFPlusSMSR=np.int32(0), EDTSM=np.int32(1), MVP=fm["cam_mvp"]))
+        img = O.ref_run_shader(shader, u, W, H)
+        out[f"edt/{tech}/hard"] = img
+        near = O.edt_nearest(O.edt_sites(img))
+        a2 = O.edt_normalize(img, pos, near, np.float32(p.penumbra_size / 5.0), p.shadow_intensity)
+        stage = a2
+        for axis, horizontal, mode in (("x", 1, ()), ("y", 0, ("linear",))):
+            rgba = np.zeros((H, W, 4), np.float32)
+            rgba[..., :2] = stage
+            fu = dict(image=("tex", rgba) + mode, vertexMap=("tex", pos), MV=fm["cam_mv"], shadowIntensity=np.float32(p.shadow_intensity),
+                      fov=np.float32(45.0), width=np.int32(W), height=np.int32(H), order=np.int32(p.kernel_order),
+                      horizontal=np.int32(horizontal), vertical=np.int32(1 - horizontal), zNear=np.int32(1), zFar=np.int32(1000))
+            stage = np.ascontiguousarray(O.ref_run_shader("meanfilter", fu, W, H)[..., :2])
+            out[f"edt/{tech}/filter_{axis}_in"] = rgba[..., :2].copy()
+            out[f"edt/{tech}/filter_{axis}"] = stage
     np.savez_compressed(os.path.join(HERE, "golden_shaders.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

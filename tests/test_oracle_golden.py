@@ -31,6 +31,50 @@ def test_visibility_matches_reference_shader_golden(tech, variant):
     assert (ref[~fg] == 0).all() and 0.02 < (ref[fg] < 1).mean() < 0.98
 
 
+@pytest.mark.parametrize("tech", ["edtsm_noncons", "edtsm_cons"])
+def test_edt_shadow_mapping_stages_match_reference_shaders_golden(tech):
+    """EDTSM: the hard-shadow target (RBSM shader with EDTSM == 1) and both MeanFilter.frag passes bit-exact against the
+    reference's shaders; the filter inputs stored with them are what the oracle's own site / Voronoi / normalise stages
+    produce from that target."""
+    g = util.golden("golden_shaders.npz")
+    fm, cam = _frame(g)
+    S = int(g["S"])
+    p = O.default_params(tech, S, depth_threshold=float(g["depth_threshold"]), penumbra_size=5)
+    img = O.edt_hard_image(p, cam, fm["cam_mvp"], fm["light_mvp_b"], g["pos"], g["nrm"], g["sm"])
+    assert util.bits_equal(img, g[f"edt/{tech}/hard"]), util.describe_diff(img, g[f"edt/{tech}/hard"])
+    near = O.edt_nearest(O.edt_sites(img))
+    a2 = O.edt_normalize(img, g["pos"], near, np.float32(p.penumbra_size / 5.0), p.shadow_intensity)
+    assert util.bits_equal(a2, g[f"edt/{tech}/filter_x_in"])
+    fg = g["pos"][..., 0] != 0
+    bx = O.mean_filter(a2, g["pos"], fm["cam_mv"], p.kernel_order, True)
+    assert util.bits_equal(bx[fg], g[f"edt/{tech}/filter_x"][fg])
+    by = O.mean_filter(bx, g["pos"], fm["cam_mv"], p.kernel_order, False, linear=True)
+    assert util.bits_equal(by[fg], g[f"edt/{tech}/filter_y"][fg])
+    vis, near2 = O.edtsm(p, cam, fm["cam_mvp"], fm["light_mvp_b"], g["pos"], g["nrm"], g["sm"])
+    assert util.bits_equal(vis[fg], by[..., 0][fg]) and np.array_equal(near2, near)
+    ramp = (vis > p.shadow_intensity) & (vis < 1.0)
+    assert ramp.sum() > 200                                   # a penumbra exists
+
+
+@pytest.mark.parametrize("W,H,n_sites,seed", [(37, 23, 5, 0), (64, 64, 40, 1), (101, 33, 1, 2), (50, 70, 600, 3), (16, 16, 0, 4)])
+def test_edt_nearest_site_is_the_brute_force_answer(W, H, n_sites, seed):
+    """Exact Euclidean nearest site, ties to the smallest (y, x); no sites -> MARKER everywhere."""
+    rng = np.random.default_rng(seed)
+    sites = np.full((H, W, 2), O.EDT_MARKER, np.int16)
+    flat = rng.choice(W * H, size=n_sites, replace=False) if n_sites else np.zeros(0, np.int64)
+    ys, xs = flat // W, flat % W
+    sites[ys, xs, 0] = xs; sites[ys, xs, 1] = ys
+    near = O.edt_nearest(sites)
+    if n_sites == 0:
+        assert (near == O.EDT_MARKER).all()
+        return
+    yy, xx = np.mgrid[0:H, 0:W]
+    d = (xx[..., None] - xs) ** 2 + (yy[..., None] - ys) ** 2                  # [H, W, n]
+    key = d.astype(np.int64) * (1 << 32) + ys.astype(np.int64) * (1 << 16) + xs.astype(np.int64)
+    k = key.argmin(-1)
+    assert np.array_equal(near[..., 0], xs[k]) and np.array_equal(near[..., 1], ys[k])
+
+
 def test_many_light_matches_reference_shader_golden():
     g = util.golden("golden_shaders.npz")
     S = int(g["S"])
