@@ -11,9 +11,9 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf_noncons": 5, "rpcf_cons": 6,
-        "rsmss": 7, "multi_hard": 8, "rbssm": 9}
+        "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11}
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
-       "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10}
+       "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11}
 PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
         "tile_gbuffer": 6, "tile_sv": 7}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
@@ -182,7 +182,7 @@ class Context:
         return {
             "shadow_map": ((N, SH, SW), np.float32), "gbuf_pos": ((H, W, 4), np.float32), "gbuf_nrm": ((H, W, 4), np.float32),
             "cam_depth": ((H, W), np.float32), "visibility": ((H, W), np.float32), "sv_count": ((H, W), np.int32),
-            "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
+            "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "edt_nearest": ((H, W, 2), np.int16), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
         }[which]
 
     def read(self, which, out=None):

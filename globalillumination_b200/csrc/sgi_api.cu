@@ -147,6 +147,7 @@ int sgi_destroy(sgi_ctx* ctx) {
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
+  for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
   if (ctx->d_rgb) cudaFree(ctx->d_rgb);
   void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -289,7 +290,7 @@ int sgi_set_multi_light_common(sgi_ctx* ctx, const float m[16]) {
 
 int sgi_set_params(sgi_ctx* ctx, const sgi_params* p) {
   if (!ctx || !p) return SGI_ERR_INVALID;
-  if (p->technique < 0 || p->technique > SGI_TECH_RBSSM) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
+  if (p->technique < 0 || p->technique > SGI_TECH_EDTSM_CONS) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
   if (p->kernel_order <= 0 || p->blocker_search_size <= 0 || p->kernel_size <= 0 || p->max_search < 0 || p->max_search > 4096 ||
       p->blocker_search_size > SGI_MAX_PCF_TAPS || p->kernel_size > SGI_MAX_PCF_TAPS) {
     ctx->err = "sgi_set_params: kernel sizes must be in 1..64";
@@ -392,6 +393,10 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   int rc = sgi_join_gbuffer(ctx);
   if (rc) return rc;
   sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, ctx->stream);
+  if (ctx->params.technique == SGI_TECH_EDTSM_NONCONS || ctx->params.technique == SGI_TECH_EDTSM_CONS) {
+    if ((rc = ensure_buf(ctx, SGI_BUF_EDT_NEAREST, (size_t)ctx->W * ctx->H * 4))) return rc;
+    sgi_wait_reads_of(ctx, SGI_BUF_EDT_NEAREST, ctx->stream);
+  }
   int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, ctx->stream);
   rc = sgi_shadow_run(ctx);
   if (rc) return rc;

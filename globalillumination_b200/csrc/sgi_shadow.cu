@@ -483,6 +483,7 @@ __device__ float cs_rpcf(Rb& r, const VisArgs& a, float4 c) {
 }
 
 #include "sgi_rbssm.cuh"
+#include "sgi_edt.cuh"
 
 // ================================ kernels ========================================================
 // VA / VB: compile-time tap counts of the specialised variants (PCF: VA = taps per axis; PCSS: VA = blocker taps,
@@ -725,6 +726,24 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
   if (rw <= 0 || rh <= 0) return SGI_OK;
   cudaStream_t st = ctx->stream;
+  // EDT shadow mapping: the hard shadows are the SMSR branch of the RBSM programs (main.cpp:406-409,
+  // NonConservativeSMSR.frag:381) rendered into a side buffer, the EDT filter chain then produces the visibility
+  const bool edtsm = ctx->params.technique == SGI_TECH_EDTSM_NONCONS || ctx->params.technique == SGI_TECH_EDTSM_CONS;
+  if (edtsm) {
+    if (rw != ctx->W || rh != ctx->H) { ctx->err = "EDT shadow mapping needs the whole screen (no rect)"; return SGI_ERR_INVALID; }
+    const size_t px = (size_t)ctx->W * ctx->H;
+    const size_t need[SGI_EDT_NBUF] = {px * 4, px * 8, px, px * 2, px * 8, px * 8, 16};   // hard, aux, site, col, a2, b2, flag
+    for (int k = 0; k < SGI_EDT_NBUF; k++)
+      if (ctx->edt_bytes[k] != need[k]) {
+        SGI_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->edt_buf[k]) cudaFree(ctx->edt_buf[k]);
+        ctx->edt_buf[k] = nullptr; ctx->edt_bytes[k] = 0;
+        SGI_CUDA(ctx, cudaMalloc(&ctx->edt_buf[k], need[k]));
+        ctx->edt_bytes[k] = need[k];
+      }
+    a.vis = (float*)ctx->edt_buf[0];
+    a.p.technique = ctx->params.technique == SGI_TECH_EDTSM_CONS ? SGI_TECH_RBSM_CONS : SGI_TECH_RBSM_NONCONS;
+  }
   if (multi && ctx->trans_dirty) {
     // lightMVPTrans[i] = column 3 of bias*lightMVP_i (SoftShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:187-190)
     std::vector<float> tmp((size_t)ctx->N * 4);
@@ -737,7 +756,7 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   // here the kernel writes that 0 itself (every pixel of the rectangle is visited), so there is no separate clear pass
   dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
   int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL, st);
-  const sgi_params& P = ctx->params;
+  const sgi_params& P = a.p;
   // shared-memory staging of the shadow-map window (PCF / PCSS) is an option (sgi_set_option "vis_staged"): measured on
   // B200 it only pays when the map is much larger than L1 can cover (4096^2 PCSS: 1.01 -> 0.89 ms) and loses at the
   // c2 sizes (0.077 -> 0.097 ms), because the kernel is issue-bound, not L1-bound (profiles/r1_vis_staging.txt)
@@ -787,6 +806,28 @@ int sgi_shadow_run(sgi_ctx* ctx) {
     default: ctx->err = "unknown technique"; return SGI_ERR_INVALID;
   }
   ctx->launches++;
+  if (edtsm) {
+    // filterHardShadowsUsingEDT (main.cpp:416-447)
+    EdtArgs e;
+    e.pos4 = a.pos4; e.nrm4 = a.nrm4; e.vis_in = (const float*)ctx->edt_buf[0]; e.vis_out = (float*)ctx->buf[SGI_BUF_VISIBILITY];
+    e.aux = (float2*)ctx->edt_buf[1]; e.site = (unsigned char*)ctx->edt_buf[2]; e.col = (short*)ctx->edt_buf[3];
+    e.a2 = (float2*)ctx->edt_buf[4]; e.b2 = (float2*)ctx->edt_buf[5]; e.any_site = (int*)ctx->edt_buf[6];
+    e.nearest = (short2*)ctx->buf[SGI_BUF_EDT_NEAREST];
+    e.W = ctx->W; e.H = ctx->H;
+    for (int k = 0; k < 16; k++) { e.cmvp[k] = ctx->cam_mvp[k]; e.mv[k] = ctx->cam_mv[k]; }
+    { volatile double pen = (double)ctx->params.penumbra_size / 5.0; e.penumbra = (float)pen; }      // main.cpp:421: int / 5.0, narrowed
+    e.si = ctx->params.shadow_intensity; e.order = ctx->params.kernel_order; e.z_near = ctx->params.z_near; e.z_far = ctx->params.z_far;
+    { volatile float t = tanf(45.0f / 2.0f); volatile float d = 2.0f * t; e.dscreen = 1.0f / d; }    // MeanFilter.frag:43, fov = 45 as is (MyGLGeometryViewer.cpp:6)
+    SGI_CUDA(ctx, cudaMemsetAsync(e.any_site, 0, 4, st));
+    k_edt_prepare<<<grid, block, 0, st>>>(a, e);
+    k_edt_sites<<<grid, block, 0, st>>>(e);
+    k_edt_cols<<<(ctx->W + 63) / 64, 64, 0, st>>>(e);
+    k_edt_rows<<<grid, block, 0, st>>>(e);
+    k_edt_normalize<<<grid, block, 0, st>>>(e);
+    k_mean_filter<false, false><<<grid, block, 0, st>>>(e, e.a2, e.b2, 1);
+    k_mean_filter<true, true><<<grid, block, 0, st>>>(e, e.b2, nullptr, 0);
+    ctx->launches += 7;
+  }
   sgi_timing_end(ctx, SGI_PASS_VIS_KERNEL, tslot, st);
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;

@@ -130,6 +130,8 @@ int sgh_app_set_technique(sgh_app* a, const char* name) {
   else if (n == "rpcf_conservative" || n == "rpcf_cons") { p.RPCFPlusSMSR = true; p.conservative = true; }
   else if (n == "rsmss") p.RSMSS = true;
   else if (n == "rbssm" || n == "RBSSM") p.RBSSM = true;
+  else if (n == "edtsm" || n == "edtsm_noncons") p.EDTSM = true;
+  else if (n == "edtsm_conservative" || n == "edtsm_cons") { p.EDTSM = true; p.conservative = true; }
   else if (n == "montecarlo" || n == "multi_hard") p.monteCarlo = true;
   else { g_err = "unknown technique " + n; return -2; }
   return 0;

@@ -109,8 +109,9 @@ FrameMatrices ShadowApp::frameMatrices() {
 // computeHardShadows' program selection (main.cpp:406-411) + the branch each program takes on its uniforms
 int ShadowApp::technique() const {
   const ShadowParams& p = shadowParams;
-  if (p.SMSR || p.RPCFPlusSMSR || p.EDTSM) {
-    bool smsr = p.SMSR || p.EDTSM;                                      // NonConservativeSMSR.frag:381
+  if (p.EDTSM) return p.conservative ? SGI_TECH_EDTSM_CONS : SGI_TECH_EDTSM_NONCONS;   // + filterHardShadowsUsingEDT (main.cpp:466)
+  if (p.SMSR || p.RPCFPlusSMSR) {
+    bool smsr = p.SMSR;                                                 // NonConservativeSMSR.frag:381
     if (p.conservative) return smsr ? SGI_TECH_RBSM_CONS : SGI_TECH_RPCF_CONS;
     return smsr ? SGI_TECH_RBSM_NONCONS : SGI_TECH_RPCF_NONCONS;
   }

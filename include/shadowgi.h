@@ -56,7 +56,9 @@ typedef enum sgi_technique {
   SGI_TECH_RPCF_CONS = 6,     /* ConservativeSMSR.frag, RPCFPlusSMSR        (:146-198)                       */
   SGI_TECH_RSMSS = 7,         /* FilteredRBSM.frag                          (:241,266-272,381-383)           */
   SGI_TECH_MULTI_HARD = 8,    /* AccurateSoftShadow.frag, monteCarlo        (:52-133), N lights              */
-  SGI_TECH_RBSSM = 9          /* SoftShadow/RBSSM.frag: revectorization-based soft shadows (:1202-1376)     */
+  SGI_TECH_RBSSM = 9,         /* SoftShadow/RBSSM.frag: revectorization-based soft shadows (:1202-1376)     */
+  SGI_TECH_EDTSM_NONCONS = 10,/* EDT shadow mapping (main.cpp:416-447, EDT/pba2D*.cu|h, MeanFilter.frag) over   */
+  SGI_TECH_EDTSM_CONS = 11    /*   the non-conservative / conservative SMSR hard shadows; whole screen only      */
 } sgi_technique;
 
 typedef enum sgi_depth_func { SGI_DEPTH_LESS = 0, SGI_DEPTH_LEQUAL = 1 } sgi_depth_func;
@@ -102,7 +104,8 @@ typedef enum sgi_buffer {
   SGI_BUF_SV_PRISM_IDX = 8, /* int32   [6T][3]      ShadowVolume::update indices                      */
   SGI_BUF_GBUF_ALBEDO = 9,  /* float4  [H][W]       (vertex colour rgb, 1) when colours are set; bg (0,0,0,1)  */
   SGI_BUF_SHADED = 10,      /* float4  [H][W]       deferred Phong image; background = the clear colour        */
-  SGI_BUF_COUNT_ = 11
+  SGI_BUF_EDT_NEAREST = 11, /* int16x2 [H][W]       EDT shadow mapping: nearest shadow-boundary pixel (x, y), -32768 = none */
+  SGI_BUF_COUNT_ = 12
 } sgi_buffer;
 
 /* passes that can be timed with sgi_pass_time_ms */

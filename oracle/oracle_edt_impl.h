@@ -195,7 +195,8 @@ void orc_mean_filter(const float* in2, const float* pos4, const float cam_mv[16]
       int count = 0;
       float sum = 0.0f;
       const float deye = -(mat4_mul_v4(cam_mv, vertex)).z;
-      const float kernelCenter = (dscreen * (float)order * scaleFactor) / (deye * 2.0f);
+      float kernelCenter = (dscreen * (float)order * scaleFactor) / (deye * 2.0f);
+      if (kernelCenter > 4096.0f) kernelCenter = 4096.0f;   /* guard (eye distance ~ 0): the shader would loop without end */
       for (float sample = -kernelCenter; sample <= kernelCenter; sample++) {
         float r, g;
         edt_fetch2(in2, W, H, cs + dirs * sample * steps, ct + dirt * sample * stept, linear, &r, &g);

@@ -75,6 +75,45 @@ def test_visibility_bit_exact(ctx, name, W, H, S, tech):
     assert 0.05 < (vis_o[fg] == 1.0).mean() < 0.999        # both lit and shadowed pixels exist
 
 
+@pytest.mark.parametrize("tech,name,W,H,S,kw", [("edtsm_noncons", "teapot", 320, 180, 256, dict(penumbra_size=5)),
+                                                ("edtsm_cons", "teapot", 640, 360, 512, dict(penumbra_size=3, kernel_order=9)),
+                                                ("edtsm_noncons", "dragon", 1280, 720, 1024, dict(penumbra_size=10)),
+                                                ("edtsm_noncons", "door", 333, 217, 300, dict(penumbra_size=1, shadow_intensity=0.5))])
+def test_edt_shadow_mapping_bit_exact(ctx, tech, name, W, H, S, kw):
+    """EDTSM (next row f3): nearest-site map (exact Voronoi diagram) identical to the oracle's, final filtered visibility
+    bit-exact; the penumbra ramp exists."""
+    sc = util.scene(name)
+    po, pg = util.params_pair(tech, S, depth_threshold=float(sc["depth_threshold"]), **kw)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    vis, near = ctx.read("visibility"), ctx.read("edt_nearest")
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o, near_o = O.edtsm(po, cam, fm["cam_mvp"], fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
+    assert np.array_equal(near, near_o), f"nearest site differs at {int((near != near_o).any(-1).sum())} pixels"
+    assert np.abs(vis - vis_o).max() <= SOFT_TOL
+    assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+    assert (near_o[..., 0] != O.EDT_MARKER).all() and ((vis_o > po.shadow_intensity) & (vis_o < 1.0)).sum() > 100
+
+
+def test_edt_shadow_mapping_without_any_shadow_boundary(ctx):
+    """A frame with no site (light inside nothing: everything lit or everything failing the site test) keeps the hard
+    shadows and reports MARKER everywhere."""
+    xyz = np.array([[-50, 0, -50], [50, 0, -50], [50, 0, 50], [-50, 0, 50]], np.float32)
+    nrm = np.tile(np.array([[0, 1, 0]], np.float32), (4, 1))
+    idx = np.array([[0, 2, 1], [0, 3, 2]], np.int32)
+    sc = dict(xyz=xyz, nrm=nrm, idx=idx, cam_eye=np.array([0, 41, -50], np.float32), cam_at=np.array([0, 0, 0], np.float32),
+              light_eye=np.array([10, 130, 100], np.float32), light_at=np.zeros(3, np.float32))
+    W, H, S = 160, 90, 128
+    po, pg = util.params_pair("edtsm_noncons", S)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    near = ctx.read("edt_nearest")
+    assert (near == O.EDT_MARKER).all()
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o, near_o = O.edtsm(po, cam, fm["cam_mvp"], fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
+    assert np.array_equal(near, near_o) and util.bits_equal(ctx.read("visibility"), vis_o)
+
+
 @pytest.mark.parametrize("kw", [dict(kernel_order=9, shadow_intensity=0.5), dict(kernel_order=15, penumbra_size=2),
                                 dict(kernel_size=7, blocker_search_size=5, light_source_radius=4), dict(max_search=4, kernel_order=3)])
 @pytest.mark.parametrize("tech", ["pcf", "pcss", "rbsm_noncons", "rpcf_cons", "rsmss", "rbssm"])
