@@ -9,10 +9,11 @@
 //   two MeanFilter.frag passes                    src/main.cpp:425-445, Shaders/Filter/MeanFilter.frag -> k_mean_filter
 // (the only CUDA in the reference: legacy texture references + CUDA-GL interop; here plain global-memory kernels on the
 // context's buffers).  The Voronoi diagram is exact (what the Parallel Banding Algorithm computes) but found differently:
-//   k_edt_cols  one thread per column, two sweeps: nearest site row of the column for every row (coalesced across x)
-//   k_edt_rows  one thread per pixel: best of the columns' candidates, scanned outwards from the pixel's own column
-//               until the horizontal distance alone exceeds the best distance found — most pixels of a shadow image are
-//               within a few texels of a boundary, so the scan is short where it matters and L1-resident
+//   phase 1  nearest site row of the same column for every pixel: columns cut into 32-row bands, band ends exchanged
+//            through a small table, two register sweeps per band (k_edt_band_ends, k_edt_cols)
+//   phase 2  one thread per pixel: best of the columns' candidates, blocks of 32 columns visited outwards from the pixel;
+//            a per-row table of each block's smallest vertical distance (k_edt_blockmin) lets whole blocks be skipped, and
+//            the walk ends when the horizontal gap alone exceeds the best distance found (k_edt_rows)
 // Ties between equidistant sites go to the smallest (y, x) (PBA's own pick depends on its band schedule).  fp32 / fp64
 // sub-expressions follow the CUDA and GLSL sources literally; bit-identical to oracle/oracle_edt_impl.h.
 #pragma once
@@ -79,63 +80,98 @@ __global__ void __launch_bounds__(256) k_edt_sites(const EdtArgs e) {
   if (is_site && *e.any_site == 0) *e.any_site = 1;
 }
 
-// nearest site row of the same column (tie: the smaller row); MARKER if the column holds no site.  The sweeps carry one
-// value down / up the column; rows are taken 32 at a time so that the loads of a batch are independent and in flight
-// together (a plain row loop pays one memory latency per row: 1.7 ms at 1080p, this form 0.1 ms).
-__global__ void __launch_bounds__(64) k_edt_cols(const EdtArgs e) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- phase 1: nearest site row of the same column (tie: the smaller row); MARKER if the column holds no site -----------
+// The column is cut into bands of SGI_EDT_BAND rows so that W x bands threads work instead of W:
+//   k_edt_band_ends   per (column, band): lowest and highest site row inside the band
+//   k_edt_cols        per (column, band): carry the nearest site below / above the band in from the other bands' ends
+//                     (a walk over <= H/32 band records), then two register sweeps over the band's rows
+#define SGI_EDT_BAND 32
+__global__ void __launch_bounds__(128) k_edt_band_ends(const EdtArgs e, short2* __restrict__ ends, int nbands) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (x >= e.W) return;
-  constexpr int B = 32;
-  int last = SGI_EDT_MARKER;
-  for (int y0 = 0; y0 < e.H; y0 += B) {
-    unsigned char sv[B];
-#pragma unroll
-    for (int k = 0; k < B; k++) sv[k] = (y0 + k < e.H) ? e.site[(size_t)(y0 + k) * e.W + x] : 0;
-#pragma unroll
-    for (int k = 0; k < B; k++)
-      if (y0 + k < e.H) {
-        if (sv[k]) last = y0 + k;
-        e.col[(size_t)(y0 + k) * e.W + x] = (short)last;
-      }
+  int lo = SGI_EDT_MARKER, hi = SGI_EDT_MARKER;
+  const int y0 = b * SGI_EDT_BAND;
+#pragma unroll 8
+  for (int k = 0; k < SGI_EDT_BAND; k++) {
+    const int y = y0 + k;
+    if (y < e.H && e.site[(size_t)y * e.W + x]) { if (lo == SGI_EDT_MARKER) lo = y; hi = y; }
   }
-  last = SGI_EDT_MARKER;
-  for (int y1 = e.H - 1; y1 >= 0; y1 -= B) {
-    unsigned char sv[B]; short bl[B];
+  ends[(size_t)b * e.W + x] = make_short2((short)lo, (short)hi);
+}
+
+__global__ void __launch_bounds__(128) k_edt_cols(const EdtArgs e, const short2* __restrict__ ends, int nbands) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (x >= e.W) return;
+  int below = SGI_EDT_MARKER, above = SGI_EDT_MARKER;           // nearest sites strictly outside this band
+  for (int k = b - 1; k >= 0 && below == SGI_EDT_MARKER; k--) below = ends[(size_t)k * e.W + x].y;
+  for (int k = b + 1; k < nbands && above == SGI_EDT_MARKER; k++) above = ends[(size_t)k * e.W + x].x;
+  const int y0 = b * SGI_EDT_BAND;
+  unsigned char sv[SGI_EDT_BAND];
+  short dn[SGI_EDT_BAND];
 #pragma unroll
-    for (int k = 0; k < B; k++) {
-      const int y = y1 - k;
-      sv[k] = (y >= 0) ? e.site[(size_t)y * e.W + x] : 0;
-      bl[k] = (y >= 0) ? e.col[(size_t)y * e.W + x] : 0;
-    }
+  for (int k = 0; k < SGI_EDT_BAND; k++) sv[k] = (y0 + k < e.H) ? e.site[(size_t)(y0 + k) * e.W + x] : 0;
+  int last = below;
 #pragma unroll
-    for (int k = 0; k < B; k++) {
-      const int y = y1 - k;
-      if (y >= 0) {
-        if (sv[k]) last = y;
-        const int below = bl[k];
-        if (last != SGI_EDT_MARKER && (below == SGI_EDT_MARKER || last - y < y - below)) e.col[(size_t)y * e.W + x] = (short)last;
-      }
-    }
+  for (int k = 0; k < SGI_EDT_BAND; k++) { if (sv[k]) last = y0 + k; dn[k] = (short)last; }       // nearest at or below
+  last = above;
+#pragma unroll
+  for (int k = SGI_EDT_BAND - 1; k >= 0; k--) {                                                   // nearest above: strictly closer wins
+    const int y = y0 + k;
+    if (y >= e.H) continue;
+    if (sv[k]) last = y;
+    int best = dn[k];
+    if (last != SGI_EDT_MARKER && (best == SGI_EDT_MARKER || last - y < y - best)) best = last;
+    e.col[(size_t)y * e.W + x] = (short)best;
   }
 }
 
-__global__ void __launch_bounds__(256) k_edt_rows(const EdtArgs e) {
+// ---- phase 2: per pixel, the best of the columns' candidates ---------------------------------------------------------
+// k_edt_blockmin: per row and block of 32 columns, the smallest vertical distance^2 of the block's candidates; lets the
+// row scan skip whole blocks that cannot beat (or tie) the best distance found so far.
+__global__ void __launch_bounds__(256) k_edt_blockmin(const EdtArgs e, int* __restrict__ bmin, int nblk) {
+  const int lane = threadIdx.x, cb = blockIdx.x * 8 + threadIdx.y, y = blockIdx.y;
+  if (cb >= nblk) return;
+  const int c = cb * 32 + lane;
+  int v = 0x7fffffff;
+  if (c < e.W) {
+    const int sy = e.col[(size_t)y * e.W + c];
+    if (sy != SGI_EDT_MARKER) v = (y - sy) * (y - sy);
+  }
+  v = __reduce_min_sync(0xffffffffu, v);
+  if (lane == 0) bmin[(size_t)y * nblk + cb] = v;
+}
+
+__global__ void __launch_bounds__(256) k_edt_rows(const EdtArgs e, const int* __restrict__ bmin, int nblk) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (x >= e.W || y >= e.H) return;
   const size_t row = (size_t)y * e.W;
   int bx = SGI_EDT_MARKER, by = SGI_EDT_MARKER;
   if (*e.any_site) {
-    int best = -1;
-    for (int d = 0; d < e.W; d++) {
-      if (best >= 0 && d * d > best) break;
-      for (int s = 0; s < (d ? 2 : 1); s++) {
-        const int c = s ? x + d : x - d;
-        if (c < 0 || c >= e.W) continue;
-        const int sy = __ldg(&e.col[row + c]);
-        if (sy == SGI_EDT_MARKER) continue;
-        const int dd = d * d + (y - sy) * (y - sy);
-        if (best < 0 || dd < best || (dd == best && (sy < by || (sy == by && c < bx)))) { best = dd; bx = c; by = sy; }
+    int best = 0x7fffffff;
+    const int cb0 = x >> 5;
+    const int* __restrict__ bm = bmin + (size_t)y * nblk;
+    // blocks in order of their horizontal gap to x: own block, then left/right pairs.  A block is scanned only if
+    // gap^2 + (its smallest vertical distance^2) can beat or tie the best; the walk ends when the gap alone cannot.
+    for (int db = 0; db < nblk; db++) {
+      bool any_reachable = false;
+      for (int s = 0; s < (db ? 2 : 1); s++) {
+        const int cb = s ? cb0 + db : cb0 - db;
+        if (cb < 0 || cb >= nblk) continue;
+        const int c_lo = cb << 5, c_hi = min(c_lo + 31, e.W - 1);
+        const int gap = (x < c_lo) ? c_lo - x : ((x > c_hi) ? x - c_hi : 0);
+        if ((long long)gap * gap > (long long)best) continue;
+        any_reachable = true;
+        const int m = __ldg(&bm[cb]);
+        if (m == 0x7fffffff || (long long)gap * gap + m > (long long)best) continue;
+        for (int c = c_lo; c <= c_hi; c++) {
+          const int sy = __ldg(&e.col[row + c]);
+          if (sy == SGI_EDT_MARKER) continue;
+          const int d = c - x;
+          const int dd = d * d + (y - sy) * (y - sy);
+          if (dd < best || (dd == best && (sy < by || (sy == by && c < bx)))) { best = dd; bx = c; by = sy; }
+        }
       }
+      if (!any_reachable && db > 0) break;
     }
   }
   e.nearest[row + x] = make_short2((short)bx, (short)by);

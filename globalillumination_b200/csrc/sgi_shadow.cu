@@ -732,7 +732,8 @@ int sgi_shadow_run(sgi_ctx* ctx) {
   if (edtsm) {
     if (rw != ctx->W || rh != ctx->H) { ctx->err = "EDT shadow mapping needs the whole screen (no rect)"; return SGI_ERR_INVALID; }
     const size_t px = (size_t)ctx->W * ctx->H;
-    const size_t need[SGI_EDT_NBUF] = {px * 4, px * 8, px, px * 2, px * 8, px * 8, 16};   // hard, aux, site, col, a2, b2, flag
+    const int nbands = (ctx->H + 31) / 32, nblk = (ctx->W + 31) / 32;
+    const size_t need[SGI_EDT_NBUF] = {px * 4, px * 8, px, px * 2, px * 8, px * 8, 16, (size_t)nbands * ctx->W * 4, (size_t)ctx->H * nblk * 4};   // hard, aux, site, col, a2, b2, flag, band ends, block minima
     for (int k = 0; k < SGI_EDT_NBUF; k++)
       if (ctx->edt_bytes[k] != need[k]) {
         SGI_CUDA(ctx, cudaStreamSynchronize(st));
@@ -821,12 +822,16 @@ int sgi_shadow_run(sgi_ctx* ctx) {
     SGI_CUDA(ctx, cudaMemsetAsync(e.any_site, 0, 4, st));
     k_edt_prepare<<<grid, block, 0, st>>>(a, e);
     k_edt_sites<<<grid, block, 0, st>>>(e);
-    k_edt_cols<<<(ctx->W + 63) / 64, 64, 0, st>>>(e);
-    k_edt_rows<<<grid, block, 0, st>>>(e);
+    const int nbands = (ctx->H + SGI_EDT_BAND - 1) / SGI_EDT_BAND, nblk = (ctx->W + 31) / 32;
+    short2* ends = (short2*)ctx->edt_buf[7]; int* bmin = (int*)ctx->edt_buf[8];
+    k_edt_band_ends<<<dim3((ctx->W + 127) / 128, nbands), 128, 0, st>>>(e, ends, nbands);
+    k_edt_cols<<<dim3((ctx->W + 127) / 128, nbands), 128, 0, st>>>(e, ends, nbands);
+    k_edt_blockmin<<<dim3((nblk + 7) / 8, ctx->H), dim3(32, 8), 0, st>>>(e, bmin, nblk);
+    k_edt_rows<<<grid, block, 0, st>>>(e, bmin, nblk);
     k_edt_normalize<<<grid, block, 0, st>>>(e);
     k_mean_filter<false, false><<<grid, block, 0, st>>>(e, e.a2, e.b2, 1);
     k_mean_filter<true, true><<<grid, block, 0, st>>>(e, e.b2, nullptr, 0);
-    ctx->launches += 7;
+    ctx->launches += 9;
   }
   sgi_timing_end(ctx, SGI_PASS_VIS_KERNEL, tslot, st);
   SGI_CUDA(ctx, cudaGetLastError());
