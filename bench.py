@@ -177,8 +177,8 @@ def main():
         print(json.dumps(run_reference(args, w, cfg_path)), flush=True)
         return 0
 
-    args.steps = args.steps or 400
-    args.warmup = 10 if args.warmup is None else max(3, args.warmup)
+    args.steps = args.steps or 2000        # ~0.7 s of timed frames: several 100 ms nvidia-smi clock samples fall inside
+    args.warmup = 20 if args.warmup is None else max(3, args.warmup)
 
     import torch
     import torch.distributed as dist
@@ -294,12 +294,17 @@ def main():
         total_ms = float(ev_all[0].elapsed_time(ev_all[1])) if lights_mode else float(sum(step_ms))
 
         # ---- per-kernel shares (same steps again, CUDA events around the kernels of each pass) ----
+        # (pass overlap off here: with the depth and G-buffer passes on concurrent streams an event pair around one kernel
+        #  also counts the time it shares the SMs with the other stream's kernels; alone on the stream it is the kernel's own
+        #  duration, which is what the roofline and the ncu launch list describe)
+        ctx.set_option("overlap_passes", 0)
         ctx.enable_timing(True); ctx.reset_timing()
         for k in range(min(args.steps, 100)):
             flush.zero_()
             frame(); app.step_animation(anim_stride)
         join_comm()
         ctx.synchronize()
+        ctx.set_option("overlap_passes", 1)
         passes = {}
         for name in capi.PASS:
             ms, n = ctx.pass_time_ms(name)
