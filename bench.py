@@ -314,21 +314,23 @@ def main():
 
         # ---- e2e: host buffers in, host buffer out, every frame ----
         vis_bytes = w["W"] * w["H"] * 4
-        host_vis2 = [torch.empty(w["W"] * w["H"], dtype=torch.float32).pin_memory() for _ in range(2)]
+        E2E_DEPTH = 3            # frames in flight: the host queues frame k while k-1 renders and k-2 is copied out
+        host_vis2 = [torch.empty(w["W"] * w["H"], dtype=torch.float32).pin_memory() for _ in range(E2E_DEPTH)]
         host_vis = host_vis2[0]
         e2e_steps = max(10, min(args.steps, 200))
 
         def e2e_loop(n):
-            """Every frame: geometry host->device (pinned arrays of the Mesh), all passes, visibility device->host (pinned).
-            Frames are pipelined one deep: frame k's copy-out overlaps frame k+1's passes; all of it inside the timed region."""
-            prev = None
+            """Every frame: geometry host->device (the Mesh arrays), all passes, visibility device->host (pinned).
+            Frames are pipelined: frame k's copy-out overlaps the passes of the frames queued behind it; all of it inside
+            the timed region, which ends when the last frame's pixels are in host memory."""
+            pending = []
             for k in range(n):
-                t = app.display_e2e_async(program, "visibility", host_vis2[k & 1].data_ptr(), vis_bytes)
+                pending.append(app.display_e2e_async(program, "visibility", host_vis2[k % E2E_DEPTH].data_ptr(), vis_bytes))
                 app.step_animation(anim_stride)
-                if prev is not None:
-                    app.e2e_wait(prev)
-                prev = t
-            app.e2e_wait(prev)
+                if len(pending) >= E2E_DEPTH:
+                    app.e2e_wait(pending.pop(0))
+            for t in pending:
+                app.e2e_wait(t)
 
         e2e_loop(4)
         barrier()
@@ -388,7 +390,7 @@ def main():
                    "parallelism": (f"lights x{world} + reduce-scatter (pipelined one frame deep on a side stream)" if lights_mode else f"frames x{world}") if world > 1 else "single GPU", "lit_fraction": lit},
         "clocks": clock_info, "gpu_launches": int(launches),
         "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * 24 + T * 12),
-                "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps, "pipelined_frames_in_flight": 2,
+                "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps, "pipelined_frames_in_flight": 3,
                 "blocking_call_ms": 1e3 * e2e_blocking_s},
         "pass_ms": passes, "roofline": roof,
     }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include "sgi_internal.cuh"
 
 static int ensure_buf(sgi_ctx* ctx, int which, size_t bytes) {
@@ -126,6 +127,9 @@ int sgi_create(sgi_ctx** out, int device) {
   { const char* e = getenv("SGI_TILE_SPLIT"); if (e) ctx->tile_split = atoi(e) < 0 ? 0 : atoi(e); }
   { const char* e = getenv("SGI_TILE_ORDER"); ctx->tile_order = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("SGI_TILE_THREADS"); int v = e ? atoi(e) : 0; ctx->tile_threads = (v == 256 || v == 512 || v == 1024) ? v : 0; }
+  if (cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_upload_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_geom_main, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   for (int k = 0; k < 4; k++) if (cudaEventCreateWithFlags(&ctx->read_done[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
@@ -146,8 +150,10 @@ int sgi_destroy(sgi_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
+  if (ctx->vis_spare) cudaFree(ctx->vis_spare);
   if (ctx->d_rgb) cudaFree(ctx->d_rgb);
   void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -160,9 +166,13 @@ int sgi_destroy(sgi_ctx* ctx) {
     if (ctx->ev_lane_done[k]) cudaEventDestroy(ctx->ev_lane_done[k]);
   }
   if (ctx->ev_lane_fork) cudaEventDestroy(ctx->ev_lane_fork);
+  for (int k = 0; k < 4; k++) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); if (ctx->ev_stage[k]) cudaEventDestroy(ctx->ev_stage[k]); }
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
   for (int k = 0; k < 4; k++) if (ctx->read_done[k]) cudaEventDestroy(ctx->read_done[k]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  if (ctx->ev_upload_done) cudaEventDestroy(ctx->ev_upload_done);
+  if (ctx->ev_geom_main) cudaEventDestroy(ctx->ev_geom_main);
   free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);
   for (int p = 0; p < SGI_PASS_COUNT_; p++)
     for (int k = 0; k < SGI_EV_RING; k++) { if (ctx->ev[p][k][0]) cudaEventDestroy(ctx->ev[p][k][0]); if (ctx->ev[p][k][1]) cudaEventDestroy(ctx->ev[p][k][1]); }
@@ -180,10 +190,50 @@ int sgi_set_stream(sgi_ctx* ctx, void* cuda_stream) {
   return SGI_OK;
 }
 
+// Upload stream protocol: begin = wait for every pass queued so far that reads geometry / colours (the depth and
+// shadow-volume passes on the main stream, the G-buffer pass on the auxiliary stream); end = the main stream (and through
+// ev_fork the auxiliary one) waits for the copies.
+static int upload_begin(sgi_ctx* ctx) {
+  if (ctx->geom_main_recorded) SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_geom_main, 0));
+  if (ctx->gbuf_done_recorded) SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_gbuf_done, 0));
+  return SGI_OK;
+}
+static int upload_end(sgi_ctx* ctx) {
+  SGI_CUDA(ctx, cudaEventRecord(ctx->ev_upload_done, ctx->upload_stream));
+  SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_upload_done, 0));
+  return SGI_OK;
+}
+
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// page-locked staging slot of at least `bytes`, free to overwrite (its previous DMA has completed)
+static int stage_acquire(sgi_ctx* ctx, int slot, size_t bytes, char** out) {
+  if (!ctx->ev_stage[slot]) SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[slot], cudaEventDisableTiming));
+  else SGI_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[slot]));
+  if (ctx->h_stage_bytes[slot] < bytes) {
+    if (ctx->h_stage[slot]) cudaFreeHost(ctx->h_stage[slot]);
+    ctx->h_stage[slot] = nullptr; ctx->h_stage_bytes[slot] = 0;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(&ctx->h_stage[slot], cap, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "cudaHostAlloc (upload staging)"; return SGI_ERR_NOMEM; }
+    ctx->h_stage_bytes[slot] = cap;
+  }
+  *out = (char*)ctx->h_stage[slot];
+  return SGI_OK;
+}
+
 int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, const int32_t* idx, int32_t T) {
   if (!ctx || V < 0 || T < 0 || (V > 0 && (!xyz || !nrm)) || (T > 0 && !idx)) { if (ctx) ctx->err = "sgi_set_mesh: bad arguments"; return SGI_ERR_INVALID; }
-  for (int64_t k = 0; k < (int64_t)T * 3; k++)
-    if (idx[k] < 0 || idx[k] >= V) { ctx->err = "sgi_set_mesh: index out of range"; return SGI_ERR_INVALID; }
+  {
+    int32_t lo = 0, hi = -1;                       // min / max in one vectorisable sweep
+    const int64_t n = (int64_t)T * 3;
+    if (n > 0) { lo = idx[0]; hi = idx[0]; }
+    for (int64_t k = 0; k < n; k++) { const int32_t v = idx[k]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+    if (n > 0 && (lo < 0 || hi >= V)) { ctx->err = "sgi_set_mesh: index out of range"; return SGI_ERR_INVALID; }
+  }
   cudaSetDevice(ctx->device);
   // Upload into the geometry set the frame in flight is NOT using.  Ordering on the main stream is enough: the passes
   // that read this set two uploads ago were queued on (or joined into) the main stream before this copy.
@@ -191,6 +241,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   const int s = ctx->mesh_cur ^ 1;
   if (V != ctx->mesh_V[s] || T != ctx->mesh_T[s]) {
     SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     if (ctx->d_xyz_set[s]) cudaFree(ctx->d_xyz_set[s]);
     if (ctx->d_nrm_set[s]) cudaFree(ctx->d_nrm_set[s]);
     if (ctx->d_idx_set[s]) cudaFree(ctx->d_idx_set[s]);
@@ -200,11 +251,30 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
     SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_idx_set[s], (size_t)(T > 0 ? T : 1) * 12));
     ctx->mesh_V[s] = V; ctx->mesh_T[s] = T;
   }
-  if (V > 0) {
-    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_xyz_set[s], xyz, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
-    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm_set[s], nrm, (size_t)V * 12, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    const size_t vb = (size_t)V * 12, tb = (size_t)T * 12;
+    const void *sx = xyz, *sn = nrm, *si = idx;
+    const bool borrow = ctx->borrow_pinned && (V == 0 || (host_is_pinned(xyz) && host_is_pinned(nrm))) && (T == 0 || host_is_pinned(idx));
+    int slot = -1;
+    if (!borrow) {
+      char* stg = nullptr;
+      slot = ctx->stage_next_mesh; ctx->stage_next_mesh ^= 1;
+      int rc = stage_acquire(ctx, slot, 2 * vb + tb, &stg);
+      if (rc) return rc;
+      if (V > 0) { memcpy(stg, xyz, vb); memcpy(stg + vb, nrm, vb); }
+      if (T > 0) memcpy(stg + 2 * vb, idx, tb);
+      sx = stg; sn = stg + vb; si = stg + 2 * vb;
+    }
+    int rc = upload_begin(ctx);
+    if (rc) return rc;
+    if (V > 0) {
+      SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_xyz_set[s], sx, vb, cudaMemcpyHostToDevice, ctx->upload_stream));
+      SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm_set[s], sn, vb, cudaMemcpyHostToDevice, ctx->upload_stream));
+    }
+    if (T > 0) SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_idx_set[s], si, tb, cudaMemcpyHostToDevice, ctx->upload_stream));
+    if (slot >= 0) SGI_CUDA(ctx, cudaEventRecord(ctx->ev_stage[slot], ctx->upload_stream));
+    if ((rc = upload_end(ctx))) return rc;
   }
-  if (T > 0) SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_idx_set[s], idx, (size_t)T * 12, cudaMemcpyHostToDevice, ctx->stream));
   ctx->mesh_cur = s;
   ctx->d_xyz = ctx->d_xyz_set[s]; ctx->d_nrm = ctx->d_nrm_set[s]; ctx->d_idx = ctx->d_idx_set[s];
   ctx->V = V; ctx->T = T;
@@ -219,14 +289,33 @@ int sgi_set_mesh_colors(sgi_ctx* ctx, const float* rgb) {
   sgi_join_gbuffer(ctx);
   if (!rgb) { ctx->has_rgb = false; ctx->gbuffer_valid = false; return SGI_OK; }
   if (ctx->V <= 0) { ctx->err = "sgi_set_mesh_colors: set the mesh first"; return SGI_ERR_INVALID; }
-  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->rgb_V != ctx->V) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
     if (ctx->d_rgb) cudaFree(ctx->d_rgb);
     ctx->d_rgb = nullptr;
     SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_rgb, (size_t)ctx->V * 12));
     ctx->rgb_V = ctx->V;
   }
-  SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_rgb, rgb, (size_t)ctx->V * 12, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // stream order is enough for the device buffer: the G-buffer pass that last read it was joined into the main stream
+    // above, and the next one forks after this copy (mark_gbuffer_use)
+    const void* src = rgb;
+    int slot = -1;
+    if (!(ctx->borrow_pinned && host_is_pinned(rgb))) {
+      char* stg = nullptr;
+      slot = 2 + ctx->stage_next_rgb; ctx->stage_next_rgb ^= 1;
+      int rc = stage_acquire(ctx, slot, (size_t)ctx->V * 12, &stg);
+      if (rc) return rc;
+      memcpy(stg, rgb, (size_t)ctx->V * 12);
+      src = stg;
+    }
+    int rc = upload_begin(ctx);
+    if (rc) return rc;
+    SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_rgb, src, (size_t)ctx->V * 12, cudaMemcpyHostToDevice, ctx->upload_stream));
+    if (slot >= 0) SGI_CUDA(ctx, cudaEventRecord(ctx->ev_stage[slot], ctx->upload_stream));
+    if ((rc = upload_end(ctx))) return rc;
+  }
   mark_gbuffer_use(ctx);
   ctx->has_rgb = true; ctx->gbuffer_valid = false;
   return SGI_OK;
@@ -343,6 +432,7 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
       SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[k], 0));
     }
   sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot, ctx->stream);
+  SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
   ctx->shadow_map_valid = true;
   return SGI_OK;
 }
@@ -380,7 +470,9 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   sgi_timing_end(ctx, SGI_PASS_GBUFFER, slot, st);
   if (ctx->overlap_passes) {
     SGI_CUDA(ctx, cudaEventRecord(ctx->ev_gbuf_done, st));
-    ctx->gbuf_in_flight = true;
+    ctx->gbuf_in_flight = true; ctx->gbuf_done_recorded = true;
+  } else {
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
   }
   ctx->gbuffer_valid = true;
   return SGI_OK;
@@ -392,7 +484,32 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   int rc = sgi_join_gbuffer(ctx);
   if (rc) return rc;
-  sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, ctx->stream);
+  {
+    // If the visibility buffer is still being copied out by an asynchronous read (frame pipelining) and this call
+    // produces the whole screen, write into a spare buffer instead of making the shadow kernel wait for the copy:
+    // otherwise every frame's shadow pass would be chained behind the previous frame's device-to-host transfer.
+    const int t = ctx->buf_read_ticket[SGI_BUF_VISIBILITY];
+    const sgi_params& q = ctx->params;
+    const bool whole = (q.rect_x1 <= q.rect_x0 || q.rect_y1 <= q.rect_y0) || (q.rect_x0 <= 0 && q.rect_y0 <= 0 && q.rect_x1 >= ctx->W && q.rect_y1 >= ctx->H);
+    if (t >= 0 && ctx->read_pending[t] && whole && cudaEventQuery(ctx->read_done[t]) == cudaErrorNotReady) {
+      const size_t bytes = ctx->buf_bytes[SGI_BUF_VISIBILITY];
+      if (ctx->vis_spare_bytes != bytes) {
+        if (ctx->vis_spare) { SGI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); cudaFree(ctx->vis_spare); }
+        ctx->vis_spare = nullptr; ctx->vis_spare_bytes = 0; ctx->vis_spare_ticket = -1;
+        SGI_CUDA(ctx, cudaMalloc(&ctx->vis_spare, bytes));
+        ctx->vis_spare_bytes = bytes;
+      }
+      // the spare's own last copy-out (two frames ago) must have finished before it is overwritten
+      if (ctx->vis_spare_ticket >= 0 && ctx->read_pending[ctx->vis_spare_ticket])
+        cudaStreamWaitEvent(ctx->stream, ctx->read_done[ctx->vis_spare_ticket], 0);
+      std::swap(ctx->buf[SGI_BUF_VISIBILITY], ctx->vis_spare);
+      ctx->vis_spare_ticket = t;
+      ctx->buf_read_ticket[SGI_BUF_VISIBILITY] = -1;
+    } else {
+      cudaGetLastError();
+      sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, ctx->stream);
+    }
+  }
   if (ctx->params.technique == SGI_TECH_EDTSM_NONCONS || ctx->params.technique == SGI_TECH_EDTSM_CONS) {
     if ((rc = ensure_buf(ctx, SGI_BUF_EDT_NEAREST, (size_t)ctx->W * ctx->H * 4))) return rc;
     sgi_wait_reads_of(ctx, SGI_BUF_EDT_NEAREST, ctx->stream);
@@ -444,6 +561,7 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
   if ((rc = sgi_raster_run(ctx, job, 0, ctx->stream))) return rc;
   sgi_timing_end(ctx, SGI_PASS_SHADOW_VOLUME, slot, ctx->stream);
+  SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
   mark_gbuffer_use(ctx);
   return SGI_OK;
 }
@@ -508,6 +626,16 @@ int sgi_alloc_host(void** p, size_t bytes) {
   return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? SGI_OK : SGI_ERR_NOMEM;
 }
 int sgi_free_host(void* p) { return (p && cudaFreeHost(p) == cudaSuccess) ? SGI_OK : SGI_ERR_INVALID; }
+int sgi_register_host(void* p, size_t bytes) {
+  if (!p || bytes == 0) return SGI_ERR_INVALID;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return SGI_ERR_NOMEM; }
+  return SGI_OK;
+}
+int sgi_unregister_host(void* p) {
+  if (!p) return SGI_ERR_INVALID;
+  if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return SGI_ERR_INVALID; }
+  return SGI_OK;
+}
 
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   if (!ctx || !name) return SGI_ERR_INVALID;
@@ -515,6 +643,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "overlap_passes")) { sgi_join_gbuffer(ctx); ctx->overlap_passes = value != 0; }
   else if (!strcmp(name, "tile_order")) ctx->tile_order = value ? 1 : 0;
   else if (!strcmp(name, "tile_split")) ctx->tile_split = value < 0 ? 0 : value;
+  else if (!strcmp(name, "borrow_pinned")) ctx->borrow_pinned = value ? 1 : 0;
   else if (!strcmp(name, "tile_threads")) {
     if (value != 0 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;

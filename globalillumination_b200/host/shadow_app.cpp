@@ -12,7 +12,29 @@ ShadowApp::ShadowApp(int device) {
   if (rc != SGI_OK) { ctx = nullptr; err = "sgi_create failed (no CUDA device; this path has no CPU fallback)"; }
   normalMatrix = Mat3{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
 }
-ShadowApp::~ShadowApp() { if (ctx) sgi_destroy(ctx); }
+ShadowApp::~ShadowApp() {
+  if (ctx) sgi_synchronize(ctx);
+  unpinSceneArrays();
+  if (ctx) sgi_destroy(ctx);
+}
+
+// The Mesh arrays are re-uploaded on every frame of the end-to-end loop (the reference's loadVBOs per draw): page-lock
+// them in place once per scene so that the uploads are DMA transfers without a staging copy on the host.
+void ShadowApp::pinSceneArrays() {
+  if (!ctx || !pinned.empty()) return;
+  struct { void* p; size_t n; } arr[] = {
+      {scene.getPointCloud(), sizeof(float) * (size_t)scene.getPointCloudSize()}, {scene.getNormalVector(), sizeof(float) * (size_t)scene.getPointCloudSize()},
+      {scene.getIndices(), sizeof(int) * 3 * (size_t)scene.getNumberOfTriangles()}, {uploadColors.empty() ? nullptr : uploadColors.data(), sizeof(float) * uploadColors.size()}};
+  for (auto& a : arr)
+    if (a.p && a.n && sgi_register_host(a.p, a.n) == SGI_OK) pinned.push_back(a.p);
+  sgi_set_option(ctx, "borrow_pinned", 1);
+}
+void ShadowApp::unpinSceneArrays() {
+  if (pinned.empty()) return;
+  if (ctx) sgi_synchronize(ctx);                    // no DMA may still be reading them
+  for (void* p : pinned) sgi_unregister_host(p);
+  pinned.clear();
+}
 
 int ShadowApp::fail(int rc, const char* where) {
   err = std::string(where) + ": " + (ctx ? sgi_last_error(ctx) : "no context");
@@ -20,6 +42,7 @@ int ShadowApp::fail(int rc, const char* where) {
 }
 
 int ShadowApp::loadScene(const char* config, const char* base_dir) {
+  unpinSceneArrays(); uploadColors.clear(); uploadColorsSrc = nullptr;
   scene = Mesh();
   SceneLoader loader(config, &scene);
   int rc = loader.load(base_dir ? base_dir : "");
@@ -35,6 +58,7 @@ int ShadowApp::loadScene(const char* config, const char* base_dir) {
 
 int ShadowApp::setScene(const float* xyz, const float* nrm, int nv, const int* idx, int nt, const float camEye[3], const float camAt_[3],
                         const float lightEyeCfg[3], const float lightAt_[3], float depthThreshold) {
+  unpinSceneArrays(); uploadColors.clear(); uploadColorsSrc = nullptr;
   scene = Mesh();
   scene.setGeometry(xyz, nv, idx, nt);
   scene.computeNormals();
@@ -48,15 +72,20 @@ int ShadowApp::setScene(const float* xyz, const float* nrm, int nv, const int* i
 
 int ShadowApp::uploadScene() {
   if (!ctx) return SGI_ERR_NO_DEVICE;
+  if (scene.getColorsSize() > 0 && (uploadColors.size() != (size_t)scene.getPointCloudSize() || uploadColorsSrc != scene.getColors())) {
+    // per-vertex colours (`c` / `cf` directives): objects without a colour directive leave the reference's colour array
+    // short (Mesh::addObject); those vertices are shaded white here.  Built once per scene.
+    unpinSceneArrays();
+    uploadColors.assign((size_t)scene.getPointCloudSize(), 1.0f);
+    std::memcpy(uploadColors.data(), scene.getColors(), sizeof(float) * (size_t)std::min(scene.getColorsSize(), scene.getPointCloudSize()));
+    uploadColorsSrc = scene.getColors();
+  }
+  pinSceneArrays();
   int rc = sgi_set_mesh(ctx, scene.getPointCloud(), scene.getNormalVector(), scene.getPointCloudSize() / 3, scene.getIndices(),
                         scene.getNumberOfTriangles());
   if (rc) return fail(rc, "uploadScene");
-  // per-vertex colours (`c` / `cf` directives) feed the albedo target and shadeScene(); objects without a colour
-  // directive leave the reference's colour array short (Mesh::addObject): those vertices are shaded white here
-  if (scene.getColorsSize() > 0) {
-    std::vector<float> rgb((size_t)scene.getPointCloudSize(), 1.0f);
-    std::memcpy(rgb.data(), scene.getColors(), sizeof(float) * (size_t)std::min(scene.getColorsSize(), scene.getPointCloudSize()));
-    if ((rc = sgi_set_mesh_colors(ctx, rgb.data()))) return fail(rc, "sgi_set_mesh_colors");
+  if (scene.getColorsSize() > 0) {                 // feeds the albedo target and shadeScene()
+    if ((rc = sgi_set_mesh_colors(ctx, uploadColors.data()))) return fail(rc, "sgi_set_mesh_colors");
   } else if ((rc = sgi_set_mesh_colors(ctx, nullptr))) return fail(rc, "sgi_set_mesh_colors");
   uploaded = true;
   return 0;

@@ -108,6 +108,9 @@ class ShadowApp {
   Mat3 normalMatrix;              // frozen on the first camera-view pass (MyGLGeometryViewer.cpp:114-117)
   bool normalMatrixSet = false;
   bool uploaded = false;
+  std::vector<void*> pinned;        // scene arrays page-locked in place for DMA uploads (released before the arrays change)
+  void pinSceneArrays(); void unpinSceneArrays();
+  std::vector<float> uploadColors; const float* uploadColorsSrc = nullptr;   // colour array padded to the vertex count (uploadScene)
   int curTech = SGI_TECH_HARD;
 };
 

@@ -187,12 +187,20 @@ int sgi_synchronize(sgi_ctx* ctx);
  * (the reference keeps its Mesh arrays in malloc'd memory and lets the GL driver stage them) */
 int sgi_alloc_host(void** host_ptr, size_t bytes);
 int sgi_free_host(void* host_ptr);
+/* page-lock / release caller-owned arrays in place (e.g. the Mesh's own vectors).  With the option "borrow_pinned" = 1,
+ * sgi_set_mesh / sgi_set_mesh_colors read page-locked inputs by DMA after the call has returned instead of copying them
+ * inside it: the caller then keeps those arrays unchanged until the frame that uses them has completed
+ * (sgi_synchronize, sgi_read, sgi_read_wait). */
+int sgi_register_host(void* host_ptr, size_t bytes);
+int sgi_unregister_host(void* host_ptr);
 
 /* implementation switches (experiments / A-B measurements; results are identical either way):
  *   "vis_staged"      0 (default) taps through L1/L2, 1 = PCF/PCSS stage the CTA's shadow-map window in shared memory
  *   "overlap_passes"  1 (default) G-buffer pass on the auxiliary stream, 0 = everything on the main stream
  *   "tile_threads"    0 (default) automatic, or 256 / 512 / 1024 threads per tile CTA
- *   "tile_order"      1 (default) tile CTAs are launched busiest tile first, 0 = in raster order */
+ *   "tile_order"      1 (default) tile CTAs are launched busiest tile first, 0 = in raster order
+ *   "tile_split"      subdivision threshold of hot tiles in list records (default 256, 0 = off)
+ *   "borrow_pinned"   0 (default) inputs are copied inside the call, 1 = page-locked inputs are read later by DMA */
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);
 
 /* instrumentation */
