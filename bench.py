@@ -389,7 +389,7 @@ def main():
                           "flushed before every timed step (256 MiB memset on the same stream, outside the event pair)"),
                    "parallelism": (f"lights x{world} + reduce-scatter (pipelined one frame deep on a side stream)" if lights_mode else f"frames x{world}") if world > 1 else "single GPU", "lit_fraction": lit},
         "clocks": clock_info, "gpu_launches": int(launches),
-        "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * 24 + T * 12),
+        "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * (36 if any(l.startswith("c ") for l in w["lines"]) else 24) + T * 12),   # xyz + normals (+ colours) + indices
                 "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps, "pipelined_frames_in_flight": 3,
                 "blocking_call_ms": 1e3 * e2e_blocking_s},
         "pass_ms": passes, "roofline": roof,
