@@ -321,6 +321,52 @@ def test_config_c2_sponza_full_size_through_the_host(ctx):
         app.close()
 
 
+def test_end_to_end_pipeline_frames_are_their_own(ctx):
+    """The pipelined host-buffer path of bench.py's e2e (Mesh arrays page-locked in place and uploaded by DMA on the upload
+    stream, three frames in flight, spare visibility buffer, asynchronous copy-out): every frame of an animated light must
+    equal, bit for bit, the same frame rendered through the blocking call."""
+    import ctypes as C
+    from globalillumination_b200 import hostapi, scenes
+    cfg = scenes.write_config("c2_sponza")
+    w = scenes.WORKLOADS["c2_sponza"]
+    W, H, S = w["W"], w["H"], w["S"]
+    n_frames, depth, nbytes = 10, 3, W * H * 4
+    lib = ctx.lib
+    ptrs = []
+    for _ in range(depth + 1):
+        p = C.c_void_p()
+        assert lib.sgi_alloc_host(C.byref(p), C.c_size_t(nbytes)) == 0
+        ptrs.append(p)
+    view = lambda p: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), (H, W))
+    app = hostapi.App(0)
+    try:
+        app.load_scene(cfg); app.configure(W, H, S); app.set_technique("pcss"); app.set(**w["params"])
+        app.set(animationOn=1, animation=-1800.0)
+        blocking = []
+        for k in range(n_frames):
+            app.display_e2e("soft_shadow_mapping", "visibility", ptrs[depth].value, nbytes)
+            blocking.append(view(ptrs[depth]).copy())
+            app.step_animation(60.0)
+        assert not util.bits_equal(blocking[0], blocking[-1])            # the light really moves
+        app.set(animation=-1800.0)
+        pending, got = [], []
+        for k in range(n_frames):
+            pending.append((app.display_e2e_async("soft_shadow_mapping", "visibility", ptrs[k % depth].value, nbytes), k))
+            app.step_animation(60.0)
+            if len(pending) >= depth:
+                t, j = pending.pop(0)
+                app.e2e_wait(t); got.append((j, view(ptrs[j % depth]).copy()))
+        for t, j in pending:
+            app.e2e_wait(t); got.append((j, view(ptrs[j % depth]).copy()))
+        assert [j for j, _ in got] == list(range(n_frames))
+        for j, img in got:
+            assert util.bits_equal(img, blocking[j]), (j, util.describe_diff(img, blocking[j]))
+    finally:
+        app.close()
+        for p in ptrs:
+            lib.sgi_free_host(p)
+
+
 def test_config_c4_tree_shadow_volumes(ctx):
     """c4: TreeWithLeaves (the present half of it), 640x480 as in the reference: signed z-pass counts and 8-bit stencil."""
     sc = util.scene("tree")
