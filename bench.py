@@ -100,6 +100,13 @@ def run_reference(args, w, cfg_path):
     passes cannot run here: no OpenGL; its shaders compiled as C++ are used as the oracle's pin)."""
     from oracle import oracle_py as O
     from globalillumination_b200 import hostapi
+    # all the host threads the process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the
+    # CPU arm on one core at N > 1
+    try:
+        n_host = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_host = os.cpu_count() or 1
+    O.set_num_threads(n_host)
     sc = hostapi.load_scene(cfg_path)
     W, H, S = w["W"], w["H"], w["S"]
     n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
