@@ -215,6 +215,7 @@ struct BinArgs {
   int32_t* flags;                                // counters[1] = overflow flag
   volatile int32_t* h_flags;                     // host-mapped: [0] sticky overflow, [1] largest total wanted
   int32_t* big_list;                             // records spanning > SGI_BIG_TILES tiles: not binned, every tile CTA tests them (counters[3] = count)
+  const unsigned int* tile_zmax;                 // shadow volumes: largest scene depth of each tile (float bits), or null
 };
 
 // conservative triangle / tile overlap: for each edge evaluate at the tile corner that maximises it
@@ -233,6 +234,51 @@ __device__ __forceinline__ bool tile_overlaps(const SgiRec& r, int tx, int ty, i
     if (v < 0) return false;
   }
   return true;
+}
+
+// Shadow volumes: a prism triangle whose depth over the whole tile is behind the tile's farthest scene depth cannot
+// pass the depth test anywhere in it (z-pass counting), so the pair is not listed at all.  The interpolated depth is
+// affine in the pixel position: over the tile it is smallest at one of the four corner pixels (clamped to the viewport);
+// evaluated with the fragment formula and lowered by a slack that covers its fp32 rounding (the terms b*dz can be large
+// at corners outside the triangle).  Conservative: never removes a fragment that would have passed.  Deterministic, so
+// the counting and the filling walk of the binner agree.
+__device__ __forceinline__ bool tile_behind_scene(const SgiRec& r, int tx, int ty, int W, int H, const unsigned int* __restrict__ tile_zmax, int tiles_x) {
+  if (!tile_zmax) return false;
+  const unsigned int bound = __ldg(&tile_zmax[ty * tiles_x + tx]);
+  if (bound >= 0x3F800000u) return false;                       // background in the tile: everything in front of 1.0 counts
+  const int x0 = tx << SGI_TILE_LOG2, y0 = ty << SGI_TILE_LOG2;
+  const int x1 = min(x0 + SGI_TILE - 1, W - 1), y1 = min(y0 + SGI_TILE - 1, H - 1);
+  float zmin = 2.0f;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int PX = ((c & 1) ? x1 : x0) * SGI_SUBPIX + SGI_SUBPIX / 2, PY = ((c & 2) ? y1 : y0) * SGI_SUBPIX + SGI_SUBPIX / 2;
+    const long long E1 = (long long)(r.X0 - r.X2) * (long long)(PY - r.Y2) - (long long)(r.Y0 - r.Y2) * (long long)(PX - r.X2);
+    const long long E2 = (long long)(r.X1 - r.X0) * (long long)(PY - r.Y0) - (long long)(r.Y1 - r.Y0) * (long long)(PX - r.X0);
+    const float t1 = ((float)E1 * r.ia) * r.dz1, t2 = ((float)E2 * r.ia) * r.dz2;
+    const float zc = ((r.z0 + t1) + t2) + r.zoff - (1.0e-6f + 5.0e-7f * (fabsf(t1) + fabsf(t2) + fabsf(r.zoff)));
+    zmin = fminf(zmin, zc);
+  }
+  if (!(zmin > 0.0f)) return false;                             // NaN / negative bounds never cull
+  return __float_as_uint(fminf(zmin, 1.0f)) > bound;
+}
+
+// largest scene depth of every 64x64 tile (pixels outside the viewport ignored)
+__global__ void __launch_bounds__(256) k_tile_zmax(const float* __restrict__ depth, int W, int H, int tiles_x, unsigned int* __restrict__ out) {
+  const int tx = blockIdx.x, ty = blockIdx.y;
+  float m = 0.0f;
+  for (int q = threadIdx.x; q < SGI_TILE * SGI_TILE; q += 256) {
+    const int x = (tx << SGI_TILE_LOG2) + (q & (SGI_TILE - 1)), y = (ty << SGI_TILE_LOG2) + (q >> SGI_TILE_LOG2);
+    if (x < W && y < H) m = fmaxf(m, __ldg(&depth[(size_t)y * W + x]));
+  }
+  unsigned int v = __float_as_uint(fminf(fmaxf(m, 0.0f), 1.0f));
+  v = __reduce_max_sync(0xffffffffu, v);
+  __shared__ unsigned int red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) v = max(v, red[k]);
+    out[ty * tiles_x + tx] = v;
+  }
 }
 
 #ifndef SGI_BIG_TILES
@@ -274,7 +320,7 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
         tiles[k] = -1;
         if (k < nt) {
           const int ty = by0 + k / bw, tx = bx0 + k % bw;
-          if (nt == 1 || tile_overlaps(r, tx, ty, W, H)) tiles[k] = ty * a.tiles_x + tx;
+          if ((nt == 1 || tile_overlaps(r, tx, ty, W, H)) && !tile_behind_scene(r, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[k] = ty * a.tiles_x + tx;
         }
       }
 #pragma unroll
@@ -320,11 +366,15 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
         const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sby0 = __shfl_sync(0xffffffffu, by0, src);
         const int sbw = __shfl_sync(0xffffffffu, bw, src);
         slots[u] = __shfl_sync(0xffffffffu, slot, src);
+        if (a.tile_zmax) {                       // shadow volumes: the depth plane travels too (tile_behind_scene)
+          q.z0 = __shfl_sync(0xffffffffu, r.z0, src); q.dz1 = __shfl_sync(0xffffffffu, r.dz1, src); q.dz2 = __shfl_sync(0xffffffffu, r.dz2, src);
+          q.ia = __shfl_sync(0xffffffffu, r.ia, src); q.zoff = __shfl_sync(0xffffffffu, r.zoff, src);
+        }
         tiles[u] = -1;
         if (p < total) {
           const int k = p - (s_incl - s_nt);
           const int ty = sby0 + k / sbw, tx = sbx0 + k % sbw;
-          if (tile_overlaps(q, tx, ty, W, H)) tiles[u] = ty * a.tiles_x + tx;
+          if (tile_overlaps(q, tx, ty, W, H) && !tile_behind_scene(q, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
         }
       }
 #pragma unroll
@@ -999,6 +1049,7 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
     sc.d_tile_cnt = sc.d_counters + 16;
     sc.d_tile_fill = sc.d_tile_cnt + cap;
     if ((rc = grow(ctx, (void**)&sc.d_tile_off, ((size_t)cap * 2 + SGI_SPLIT_EXTRA) * 4))) return rc;   // tile_off | tile_order (work items)
+    if ((rc = grow(ctx, (void**)&sc.d_tile_zmax, (size_t)cap * 4))) return rc;
     sc.d_tile_order = sc.d_tile_off + cap;
     sc.tile_cap = cap;
   }
@@ -1085,7 +1136,15 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
     ctx->launches++;
   }
 
+  // shadow volumes: per-tile farthest scene depth, so that the binner drops (prism, tile) pairs that lie behind the scene
+  unsigned int* tile_zmax = nullptr;
+  if (job.mode == SGI_MODE_SVCOUNT && job.scene_depth && ctx->sv_tile_cull) {
+    tile_zmax = sc.d_tile_zmax;
+    k_tile_zmax<<<dim3(tiles_x, tiles_y), 256, 0, st>>>(job.scene_depth, job.W, job.H, tiles_x, tile_zmax);
+    ctx->launches++;
+  }
   BinArgs ba;
+  ba.tile_zmax = tile_zmax;
   ba.rec = sc.d_rec; ba.counters = sc.d_counters; ba.counters_rw = sc.d_counters; ba.T = job.T; ba.big_list = sc.d_big;
   ba.tiles_x = tiles_x; ba.tiles_y = tiles_y; ba.tx0 = tx0; ba.ty0 = ty0; ba.tx1 = tx1; ba.ty1 = ty1;
   ba.tile_cnt = sc.d_tile_cnt; ba.tile_off = sc.d_tile_off; ba.tile_fill = sc.d_tile_fill;
@@ -1134,7 +1193,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 }
 
 void sgi_raster_free(SgiScratch& sc) {
-  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_off, sc.d_pairs};
+  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_off, sc.d_pairs, sc.d_tile_zmax};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (sc.h_flags) cudaFreeHost(sc.h_flags);
   if (sc.d_sticky) cudaFree(sc.d_sticky);
