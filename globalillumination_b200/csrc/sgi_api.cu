@@ -154,6 +154,7 @@ int sgi_destroy(sgi_ctx* ctx) {
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
   if (ctx->vis_spare) cudaFree(ctx->vis_spare);
+  if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
   if (ctx->d_rgb) cudaFree(ctx->d_rgb);
   void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -645,6 +646,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "tile_split")) ctx->tile_split = value < 0 ? 0 : value;
   else if (!strcmp(name, "borrow_pinned")) ctx->borrow_pinned = value ? 1 : 0;
   else if (!strcmp(name, "sv_tile_cull")) ctx->sv_tile_cull = value ? 1 : 0;
+  else if (!strcmp(name, "rbssm_compact")) ctx->rbssm_compact = value ? 1 : 0;
   else if (!strcmp(name, "tile_threads")) {
     if (value != 0 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;

@@ -461,3 +461,84 @@ __device__ __noinline__ float ss_rbssm(const VisArgs& a, Rb& r, float4 c) {
     }
   return illuminationCount / (float)(p.kernel_size * p.kernel_size);
 }
+
+// ---- two-kernel form used by sgi_shadow_run ------------------------------------------------------------------------
+// One thread per pixel wastes most lanes here: only penumbra pixels (a few % of the screen) run the k x k tap loop, and
+// inside it only the taps next to a shadow-map discontinuity walk the map.  So:
+//   k_rbssm_prepare  one thread per pixel: pre-evaluation, blocker search, penumbra width; pixels that end there write
+//                    their visibility, the others are appended (pixel, light-space coordinate, width) to a work list
+//   k_rbssm_taps     one WARP per listed pixel, taps dealt to lanes; each tap's contribution is parked in shared memory
+//                    and lane 0 adds them up in the shader's loop order, so the sum is the same fp32 value
+struct RbssmItem { float4 c; float pw; int pixel; int pad0, pad1; };
+#define SGI_RBSSM_CHUNK 256            // taps summed per round (k = 15: 225 taps, one round)
+
+__device__ __forceinline__ float ss_tap(const VisArgs& a, Rb& r, float4 c, float penumbraWidth, float fw, int w, int h) {
+  const float4 lc = make_float4(c.x + ((float)w * penumbraWidth) / fw, c.y + ((float)h * penumbraWidth) / fw, c.z, c.w);
+  const float subx = g_fract(lc.x * r.SWf), suby = g_fract(lc.y * r.SHf);
+  const float dfl = sm_fetch(r.s, lc.x, lc.y);
+  float d[4];
+  ss_classify(r, lc, dfl, d);
+  if (d[0] > 0.0f || d[1] > 0.0f) {
+    const float left = ss_disc_length(r, d, lc, -1.0f, 0.0f), right = ss_disc_length(r, d, lc, 1.0f, 0.0f);
+    const float down = ss_disc_length(r, d, lc, 0.0f, -1.0f), up = ss_disc_length(r, d, lc, 0.0f, 1.0f);
+    const float nx = ss_normalize(r, left, right, subx), ny = ss_normalize(r, down, up, suby);
+    const float fill = ss_fill(r, lc, nx, ny, d, subx, suby);
+    return g_mix(fill, 1.0f, a.p.shadow_intensity);
+  }
+  return (lc.z <= dfl) ? 1.0f : a.p.shadow_intensity;
+}
+
+__global__ void __launch_bounds__(256) k_rbssm_prepare(const VisArgs a, RbssmItem* __restrict__ items, int* __restrict__ n_items) {
+  const int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.rx1 || y >= a.ry1) return;
+  const size_t o = (size_t)y * a.W + x;
+  const float4 vertex = __ldg(&a.pos4[o]);
+  if (vertex.x == 0.0f) { a.vis[o] = 0.0f; return; }
+  const float4 normal = __ldg(&a.nrm4[o]);
+  const float4 sc = mat4_mul(a.lmvp, vertex);
+  const float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+  float shadow = pre_evaluation(a, vertex, normal);
+  if (sc.w > 0.0f && shadow == 1.0f) {                         // RBSSM.frag:1372
+    const Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
+    const TapSrc<false> g = {s.d, s.w, 0, 0};
+    const float averageDepth = pcss_blockers<0, false>(a, s, g, c);
+    const float penumbraWidth = pcss_penumbra(a.p, averageDepth, c.z);
+    const float stepSize = 2.0f * penumbraWidth / (float)a.p.kernel_size;
+    if (stepSize <= 0.0f || stepSize >= 1.0f) shadow = 1.0f;
+    else {
+      RbssmItem it; it.c = c; it.pw = penumbraWidth; it.pixel = (int)o; it.pad0 = it.pad1 = 0;
+      items[atomicAdd(n_items, 1)] = it;
+      return;
+    }
+  }
+  a.vis[o] = shadow;
+}
+
+__global__ void __launch_bounds__(256) k_rbssm_taps(const VisArgs a, const RbssmItem* __restrict__ items, const int* __restrict__ n_items, int* __restrict__ cursor) {
+  __shared__ float vals[8][SGI_RBSSM_CHUNK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = *n_items;
+  const Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
+  const float fw = ((float)a.p.kernel_size - 1.0f) * 0.5f;
+  const int w0 = (int)(-fw);
+  const int nk = (fw >= 0.0f) ? (int)fw - w0 + 1 : 0;          // taps per axis of `for(int w = -fw; w <= fw; w++)`
+  const int ntaps = nk * nk;
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(cursor, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n) break;
+    const RbssmItem it = items[i];
+    Rb r = {s, a.sx, a.sy, a.p.depth_threshold, a.p.max_search, a.p.shadow_intensity, 0, a.fw, a.fh, 0.0f};
+    float illuminationCount = 0.0f;
+    for (int base = 0; base < ntaps; base += SGI_RBSSM_CHUNK) {
+      for (int t = base + lane; t < min(base + SGI_RBSSM_CHUNK, ntaps); t += 32)
+        vals[warp][t - base] = ss_tap(a, r, it.c, it.pw, fw, w0 + t % nk, w0 + t / nk);      // t = (h - w0) * nk + (w - w0)
+      __syncwarp();
+      if (lane == 0)
+        for (int t = base; t < min(base + SGI_RBSSM_CHUNK, ntaps); t++) illuminationCount += vals[warp][t - base];
+      __syncwarp();
+    }
+    if (lane == 0) a.vis[it.pixel] = illuminationCount / (float)(a.p.kernel_size * a.p.kernel_size);
+  }
+}

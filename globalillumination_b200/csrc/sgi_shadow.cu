@@ -803,7 +803,25 @@ int sgi_shadow_run(sgi_ctx* ctx) {
     case SGI_TECH_RPCF_CONS: k_visibility<SGI_TECH_RPCF_CONS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_RSMSS: k_visibility<SGI_TECH_RSMSS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_MULTI_HARD: k_visibility_multi<<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_RBSSM: k_visibility<SGI_TECH_RBSSM, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_RBSSM: {
+      if (!ctx->rbssm_compact) { k_visibility<SGI_TECH_RBSSM, 0, 0><<<grid, block, 0, st>>>(a); break; }
+      // work list of the penumbra pixels + one warp per listed pixel (sgi_rbssm.cuh)
+      const size_t need = (size_t)rw * rh * sizeof(RbssmItem) + 64;
+      if (ctx->rbssm_bytes < need) {
+        SGI_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
+        ctx->rbssm_buf = nullptr; ctx->rbssm_bytes = 0;
+        SGI_CUDA(ctx, cudaMalloc(&ctx->rbssm_buf, need));
+        ctx->rbssm_bytes = need;
+      }
+      int* counters = (int*)ctx->rbssm_buf;                    // [0] items, [1] cursor
+      RbssmItem* items = (RbssmItem*)((char*)ctx->rbssm_buf + 64);
+      SGI_CUDA(ctx, cudaMemsetAsync(counters, 0, 8, st));
+      k_rbssm_prepare<<<grid, block, 0, st>>>(a, items, counters);
+      k_rbssm_taps<<<148 * 4, 256, 0, st>>>(a, items, counters, counters + 1);
+      ctx->launches++;
+      break;
+    }
     default: ctx->err = "unknown technique"; return SGI_ERR_INVALID;
   }
   ctx->launches++;

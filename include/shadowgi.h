@@ -200,6 +200,7 @@ int sgi_unregister_host(void* host_ptr);
  *   "tile_threads"    0 (default) automatic, or 256 / 512 / 1024 threads per tile CTA
  *   "tile_order"      1 (default) tile CTAs are launched busiest tile first, 0 = in raster order
  *   "tile_split"      subdivision threshold of hot tiles in list records (default 256, 0 = off)
+ *   "rbssm_compact"   1 (default) RBSSM as work list + one warp per penumbra pixel, 0 = one thread per pixel
  *   "sv_tile_cull"    1 (default) shadow volumes: (prism, tile) pairs behind the tile's farthest scene depth are not listed
  *   "borrow_pinned"   0 (default) inputs are copied inside the call, 1 = page-locked inputs are read later by DMA */
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);

@@ -95,6 +95,26 @@ def test_edt_shadow_mapping_bit_exact(ctx, tech, name, W, H, S, kw):
     assert (near_o[..., 0] != O.EDT_MARKER).all() and ((vis_o > po.shadow_intensity) & (vis_o < 1.0)).sum() > 100
 
 
+def test_rbssm_work_list_form_equals_thread_per_pixel_form(ctx):
+    """RBSSM runs as a work list of penumbra pixels with one warp per pixel; the plain one-thread-per-pixel kernel must give
+    the same bits (tap contributions are summed in the shader's loop order in both)."""
+    sc = util.scene("dragon")
+    W, H, S = 640, 360, 1024
+    for kw in (dict(), dict(kernel_size=8, light_source_radius=16), dict(kernel_size=19, max_search=6)):
+        po, pg = util.params_pair("rbssm", S, depth_threshold=float(sc["depth_threshold"]), **kw)
+        setup_frame(ctx, sc, W, H, S, pg)
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+        a = ctx.read("visibility")
+        ctx.set_option("rbssm_compact", 0)
+        try:
+            ctx.compute_visibility()
+            b = ctx.read("visibility")
+        finally:
+            ctx.set_option("rbssm_compact", 1)
+        assert util.bits_equal(a, b), (kw, util.describe_diff(a, b))
+        assert ((a > po.shadow_intensity) & (a < 1.0)).sum() > 1000
+
+
 def test_edt_shadow_mapping_without_any_shadow_boundary(ctx):
     """A frame with no site (light inside nothing: everything lit or everything failing the site test) keeps the hard
     shadows and reports MARKER everywhere."""
