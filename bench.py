@@ -386,9 +386,22 @@ def main():
         roof = {"bound": "hbm", "kernel": kernel_of[top][0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": kernel_of[top][1], "launch_ms": per_launch_ms, "peak_source": peak_src,
                 "share_of_step": cand[top] / (total_ms / args.steps)}
+    # the shadow pass against both of its rooflines - HBM (G-buffer in, visibility out, every map texel once)
+    # and L2 (4 bytes per shadow-map tap; measured L2 read peak: profiles/r1_l2_bandwidth.txt)
+    shadow_pass = None
+    if "vis_kernel" in passes and passes["vis_kernel"] > 0:
+        px = w["W"] * w["H"]
+        k = w["params"].get("kernelSize", 15)
+        bs = w["params"].get("blockerSearchSize", 7)
+        taps = {"pcss": bs * bs + k * k, "montecarlo": n_l}.get(w["technique"], 1)
+        t_s = passes["vis_kernel"] * 1e-3
+        shadow_pass = {"launch_ms": passes["vis_kernel"], "hbm_GBs": ab["visibility"] / t_s / 1e9, "hbm_frac": ab["visibility"] / t_s / 1e9 / peak,
+                       "taps_per_lit_pixel": taps, "l2_taps_GBs_upper": 4.0 * taps * px / t_s / 1e9, "l2_read_peak_GBs": 9555.0,
+                       "note": "l2_taps is an upper bound (every foreground pixel taking every tap); PCSS pixels without blockers stop after the blocker search"}
+    med = float(np.median(step_ms)) if step_ms else None
     out = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if lights_mode else "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": total_ms / args.steps, "ms_per_step_median": med, "higher_is_better": True, "scaling": "strong" if lights_mode else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,
                    "params": w["params"], "triangles": T, "vertices": V, "scene": w["scene"],
@@ -399,7 +412,7 @@ def main():
         "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * (36 if any(l.startswith("c ") for l in w["lines"]) else 24) + T * 12),   # xyz + normals (+ colours) + indices
                 "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps, "pipelined_frames_in_flight": 3,
                 "blocking_call_ms": 1e3 * e2e_blocking_s},
-        "pass_ms": passes, "roofline": roof,
+        "pass_ms": passes, "roofline": roof, "shadow_pass": shadow_pass,
     }
     if not args.no_cpu_baseline and world == 1:
         a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup = 3, 1
