@@ -6,6 +6,7 @@
 #include "../../include/shadowgi_host.h"
 #include "procedural.h"
 #include "shadow_app.h"
+#include "png_writer.h"
 
 using namespace sgh;
 
@@ -165,6 +166,20 @@ int sgh_app_compute_hard_shadows(sgh_app* a) { return a ? a->app.computeHardShad
 int sgh_app_render_soft_shadows(sgh_app* a) { return a ? a->app.renderSoftShadows() : -1; }
 int sgh_app_render_monte_carlo(sgh_app* a) { return a ? a->app.renderMonteCarlo() : -1; }
 int sgh_app_shade_scene(sgh_app* a) { return a ? a->app.shadeScene() : -1; }
+// shadeScene() + the frame written as a PNG (the file-output counterpart of glutSwapBuffers / glReadPixels)
+int sgh_app_save_image(sgh_app* a, const char* path) {
+  if (!a || !path) return -1;
+  int rc = a->app.shadeScene();
+  if (rc) return rc;
+  const int W = a->app.windowWidth, H = a->app.windowHeight;
+  std::vector<float> img((size_t)W * H * 4);
+  if ((rc = sgi_read(a->app.context(), SGI_BUF_SHADED, img.data(), img.size() * sizeof(float)))) { g_err = sgi_last_error(a->app.context()); return rc; }
+  const std::vector<uint8_t> px = sgh::toRGBA8TopDown(img.data(), W, H);
+  if (!sgh::writePNG(path, px.data(), W, H)) { g_err = std::string("cannot write ") + path; return -3; }
+  return 0;
+}
+// the encoder alone (8-bit RGBA, row 0 = top): usable without a GPU
+int sgh_write_png(const char* path, const uint8_t* rgba, int32_t W, int32_t H) { return (path && sgh::writePNG(path, rgba, W, H)) ? 0 : -1; }
 int sgh_app_render_shadow_volumes(sgh_app* a) { return a ? a->app.renderShadowVolumes() : -1; }
 int sgh_app_display(sgh_app* a, int32_t program) {
   if (!a) return -1;

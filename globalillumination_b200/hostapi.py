@@ -16,7 +16,7 @@ EXPORTS = [
     "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
-    "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
+    "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_save_image", "sgh_write_png", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
 ]
 
 _lib = None
@@ -37,6 +37,7 @@ def load():
         _lib.sgh_app_display_e2e.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]
         _lib.sgh_app_display_e2e_async.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
         _lib.sgh_app_e2e_wait.argtypes = [C.c_void_p, C.c_int32]
+        _lib.sgh_app_save_image.argtypes = [C.c_void_p, C.c_char_p]
     return _lib
 
 
@@ -88,6 +89,17 @@ def frame_matrices(cam_eye, cam_at, light_eye, light_at, W, H, SW, SH):
     if rc:
         raise HostError("sgh_frame_matrices failed")
     return o
+
+
+def write_png(path, rgba8):
+    """8-bit RGBA image [H, W, 4], row 0 = top, through the host library's encoder (no GPU needed)."""
+    a = np.ascontiguousarray(rgba8, np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 4
+    L = load()
+    L.sgh_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
+    rc = L.sgh_write_png(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0])
+    if rc:
+        raise OSError(f"sgh_write_png({path}) failed")
 
 
 def procedural(spec):
@@ -187,6 +199,10 @@ class App:
     def render_monte_carlo(self): self._ck(self.L.sgh_app_render_monte_carlo(self.h))
     def render_shadow_volumes(self): self._ck(self.L.sgh_app_render_shadow_volumes(self.h))
     def shade_scene(self): self._ck(self.L.sgh_app_shade_scene(self.h))
+
+    def save_image(self, path):
+        """shadeScene() + the frame written as an 8-bit RGBA PNG."""
+        self._ck(self.L.sgh_app_save_image(self.h, str(path).encode()))
 
     def context(self):
         """A capi.Context view over the app's sgi_ctx (borrowed: do not close)."""

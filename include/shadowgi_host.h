@@ -58,6 +58,8 @@ int sgh_app_render_soft_shadows(sgh_app* a);
 int sgh_app_render_monte_carlo(sgh_app* a);
 int sgh_app_render_shadow_volumes(sgh_app* a);
 int sgh_app_shade_scene(sgh_app* a);              /* shadeScene(): deferred Phong of the last frame */
+int sgh_app_save_image(sgh_app* a, const char* path);   /* shadeScene() + the frame as an 8-bit RGBA PNG (top-down)    */
+int sgh_write_png(const char* path, const uint8_t* rgba, int32_t W, int32_t H);   /* the encoder alone (no GPU needed) */
 int sgh_app_display(sgh_app* a, int32_t program);
 int sgh_app_display_e2e(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes);
 int sgh_app_display_e2e_async(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes, int32_t* ticket);

@@ -387,6 +387,26 @@ def test_end_to_end_pipeline_frames_are_their_own(ctx):
             lib.sgi_free_host(p)
 
 
+def test_host_saves_the_shaded_frame_as_png(ctx, tmp_path):
+    """Next row f1 end: shadeScene() + PNG output through the host; the decoded file is the SHADED buffer flipped to
+    top-down and converted like a framebuffer (clamp, *255, round)."""
+    from PIL import Image
+    from globalillumination_b200 import hostapi, scenes
+    app = hostapi.App(0)
+    try:
+        app.load_scene(scenes.write_config("c2_sponza")); app.configure(480, 270, 512); app.set_technique("pcf")
+        app.display("shadow_mapping")
+        path = tmp_path / "frame.png"
+        app.save_image(path)
+        shaded = app.context().read("shaded")
+        want = np.rint(np.clip(shaded[::-1], 0.0, 1.0) * np.float32(255.0)).astype(np.uint8)
+        got = np.asarray(Image.open(path).convert("RGBA"))
+        assert got.shape == (270, 480, 4) and np.array_equal(got, want)
+        assert len(np.unique(got[..., :3].reshape(-1, 3), axis=0)) > 100          # a real image, not a flat colour
+    finally:
+        app.close()
+
+
 def test_config_c4_tree_shadow_volumes(ctx):
     """c4: TreeWithLeaves (the present half of it), 640x480 as in the reference: signed z-pass counts and 8-bit stencil."""
     sc = util.scene("tree")

@@ -97,3 +97,16 @@ def test_workload_configs_load_through_the_scene_loader():
     assert np.allclose(sc["xyz"].min(0), [-15, 0, -65], atol=1e-3) and np.allclose(sc["xyz"].max(0), [15, 30, 5], atol=1e-3)
     sc5 = hostapi.load_scene(scenes.write_config("c5_many_light"))
     assert sc5["idx"].shape[0] > 100000
+
+
+def test_png_writer_round_trip(tmp_path):
+    """The host library's PNG encoder (stored deflate blocks): decoded by an independent reader the pixels are the input;
+    images larger than one 64 KiB deflate block included."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    for (H, W) in ((1, 1), (7, 5), (90, 160), (300, 257)):
+        img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        path = tmp_path / f"t_{W}x{H}.png"
+        hostapi.write_png(path, img)
+        back = np.asarray(Image.open(path).convert("RGBA"))
+        assert back.shape == img.shape and np.array_equal(back, img)
