@@ -239,6 +239,7 @@ def main():
         One NCCL collective per frame; the timed region ends only when the last collective has completed."""
         nonlocal vis_t, ev_ready, ev_reduced, frame_no
         app.display(program)
+        ctx.join()            # the shadow pass runs on an internal stream: order `stream` (the timing events) after it
         if lights_mode:
             if vis_t is None:
                 ptr, nbytes = ctx.device_ptr("visibility")

@@ -39,7 +39,7 @@ class SgiParams(C.Structure):
 EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
-    "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_enable_timing",
+    "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -207,6 +207,9 @@ class Context:
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self.lib.sgi_device_ptr(self.h, BUF[which], C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def join(self):
+        self._ck(self.lib.sgi_join(self.h))
 
     def enable_timing(self, on=True):
         self._ck(self.lib.sgi_enable_timing(self.h, int(bool(on))))

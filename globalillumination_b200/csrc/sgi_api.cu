@@ -9,12 +9,21 @@
 #include <utility>
 #include "sgi_internal.cuh"
 
+static void sync_all_streams(sgi_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  cudaStream_t others[] = {ctx->aux_stream, ctx->vis_stream, ctx->copy_stream, ctx->upload_stream, ctx->lane_stream[0], ctx->lane_stream[1], ctx->lane_stream[2]};
+  for (cudaStream_t s : others) if (s) cudaStreamSynchronize(s);
+}
+
 static int ensure_buf(sgi_ctx* ctx, int which, size_t bytes) {
   if (ctx->buf[which] && ctx->buf_bytes[which] == bytes) return SGI_OK;
-  if (ctx->buf[which]) {
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    cudaFree(ctx->buf[which]); ctx->buf[which] = nullptr;
+  if (ctx->buf[which] || ctx->alt[which]) {
+    sync_all_streams(ctx);
+    if (ctx->buf[which]) cudaFree(ctx->buf[which]);
+    if (ctx->alt[which]) cudaFree(ctx->alt[which]);
+    ctx->buf[which] = nullptr; ctx->alt[which] = nullptr;
+    ctx->sm_reader_cur = ctx->sm_reader_alt = ctx->gb_reader_cur = ctx->gb_reader_alt = -1;   // everything has completed
+    ctx->vis_in_flight = false; ctx->gbuf_in_flight = false;
   }
   ctx->buf_bytes[which] = 0;
   if (bytes == 0) return SGI_OK;
@@ -84,6 +93,50 @@ int sgi_join_gbuffer(sgi_ctx* ctx) {
   return SGI_OK;
 }
 
+// The shadow pass runs on the visibility stream; consumers of its result on the main stream wait for it here.
+int sgi_join_vis(sgi_ctx* ctx) {
+  if (ctx->vis_in_flight && ctx->vis_last >= 0) {
+    SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_vis[ctx->vis_last], 0));
+    ctx->vis_in_flight = false;
+  }
+  return SGI_OK;
+}
+
+// Before a pass overwrites a render target that a shadow pass still reads (the previous frame's, on the visibility
+// stream): switch to the other instance of the target(s) if the whole target is produced and nobody holds its device
+// pointer, otherwise make the writer wait.  group 0 = shadow maps, 1 = G-buffer (position, normal, depth, albedo).
+static int prepare_target_write(sgi_ctx* ctx, int group, cudaStream_t writer, bool whole) {
+  int& cur = group ? ctx->gb_reader_cur : ctx->sm_reader_cur;
+  int& alt = group ? ctx->gb_reader_alt : ctx->sm_reader_alt;
+  if (cur >= 0 && cudaEventQuery(ctx->ev_vis[cur]) == cudaErrorNotReady) {
+    static const int sm_bufs[] = {SGI_BUF_SHADOW_MAP}, gb_bufs[] = {SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM, SGI_BUF_CAM_DEPTH, SGI_BUF_GBUF_ALBEDO};
+    const int* bufs = group ? gb_bufs : sm_bufs;
+    const int nb = group ? 4 : 1;
+    bool can_flip = whole && ctx->overlap_passes && !(group ? ctx->gbuf_exposed : ctx->sm_exposed);
+    if (can_flip)
+      for (int k = 0; k < nb && can_flip; k++)
+        if (!ctx->alt[bufs[k]] && ctx->buf[bufs[k]]) {
+          if (cudaMalloc(&ctx->alt[bufs[k]], ctx->buf_bytes[bufs[k]]) != cudaSuccess) { cudaGetLastError(); ctx->alt[bufs[k]] = nullptr; can_flip = false; }
+        }
+    if (can_flip) {
+      for (int k = 0; k < nb; k++) {
+        std::swap(ctx->buf[bufs[k]], ctx->alt[bufs[k]]);
+        // read tickets follow their instance: an asynchronous copy-out of the instance we are switching to must have
+        // finished before it is overwritten; the one we leave keeps its pending ticket
+        std::swap(ctx->buf_read_ticket[bufs[k]], ctx->alt_read_ticket[bufs[k]]);
+        sgi_wait_reads_of(ctx, bufs[k], writer);
+      }
+      std::swap(cur, alt);
+      if (cur >= 0) SGI_CUDA(ctx, cudaStreamWaitEvent(writer, ctx->ev_vis[cur], 0));   // its own last reader: two shadow passes ago
+    } else {
+      SGI_CUDA(ctx, cudaStreamWaitEvent(writer, ctx->ev_vis[cur], 0));
+    }
+  }
+  cudaGetLastError();
+  cur = -1;
+  return SGI_OK;
+}
+
 extern "C" {
 
 const char* sgi_version(void) { return "shadowgi-b200 0.1 (sm_100a)"; }
@@ -127,13 +180,21 @@ int sgi_create(sgi_ctx** out, int device) {
   { const char* e = getenv("SGI_TILE_SPLIT"); if (e) ctx->tile_split = atoi(e) < 0 ? 0 : atoi(e); }
   { const char* e = getenv("SGI_TILE_ORDER"); ctx->tile_order = (e && e[0] == '0') ? 0 : 1; }
   { const char* e = getenv("SGI_TILE_THREADS"); int v = e ? atoi(e) : 0; ctx->tile_threads = (v == 256 || v == 512 || v == 1024) ? v : 0; }
+  // lowest priority: when CTAs of the next frame's raster passes and of this frame's shadow pass compete for an SM, the raster
+  // ones go first (they are latency-bound chains on the critical path); the shadow pass fills what they leave
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  { const char* e = getenv("SGI_VIS_PRIORITY"); if (e && e[0] == '0') prio_lo = 0; }
+  if (cudaStreamCreateWithPriority(&ctx->vis_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_s2v, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
+  for (int k = 0; k < 4; k++) if (cudaEventCreateWithFlags(&ctx->ev_vis[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_upload_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_geom_main, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   for (int k = 0; k < 4; k++) if (cudaEventCreateWithFlags(&ctx->read_done[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
-  for (int b = 0; b < SGI_BUF_COUNT_; b++) ctx->buf_read_ticket[b] = -1;
+  for (int b = 0; b < SGI_BUF_COUNT_; b++) { ctx->buf_read_ticket[b] = -1; ctx->alt_read_ticket[b] = -1; }
   sgi_default_params(&ctx->params);
   for (int p = 0; p < SGI_PASS_COUNT_; p++) {
     ctx->ev_n[p] = 0; ctx->pass_ms[p] = 0; ctx->pass_calls[p] = 0;
@@ -147,11 +208,8 @@ int sgi_create(sgi_ctx** out, int device) {
 int sgi_destroy(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
-  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-  if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
-  for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->buf[b]) cudaFree(ctx->buf[b]);
+  sync_all_streams(ctx);
+  for (int b = 0; b < SGI_BUF_COUNT_; b++) { if (ctx->buf[b]) cudaFree(ctx->buf[b]); if (ctx->alt[b]) cudaFree(ctx->alt[b]); }
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
   if (ctx->vis_spare) cudaFree(ctx->vis_spare);
   if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
@@ -172,6 +230,9 @@ int sgi_destroy(sgi_ctx* ctx) {
   for (int k = 0; k < 4; k++) if (ctx->read_done[k]) cudaEventDestroy(ctx->read_done[k]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  if (ctx->vis_stream) cudaStreamDestroy(ctx->vis_stream);
+  if (ctx->ev_s2v) cudaEventDestroy(ctx->ev_s2v);
+  for (int k = 0; k < 4; k++) if (ctx->ev_vis[k]) cudaEventDestroy(ctx->ev_vis[k]);
   if (ctx->ev_upload_done) cudaEventDestroy(ctx->ev_upload_done);
   if (ctx->ev_geom_main) cudaEventDestroy(ctx->ev_geom_main);
   free(ctx->h_light_mvp); free(ctx->h_light_mvp_b);
@@ -184,8 +245,8 @@ int sgi_destroy(sgi_ctx* ctx) {
 
 int sgi_set_stream(sgi_ctx* ctx, void* cuda_stream) {
   if (!ctx) return SGI_ERR_INVALID;
-  sgi_join_gbuffer(ctx);
-  cudaStreamSynchronize(ctx->stream);
+  sgi_join_gbuffer(ctx); sgi_join_vis(ctx);
+  sync_all_streams(ctx);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   mark_gbuffer_use(ctx);
   return SGI_OK;
@@ -399,6 +460,10 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->d_idx || ctx->N <= 0) { ctx->err = "sgi_render_shadow_map: set mesh and lights first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  {
+    int rc0 = prepare_target_write(ctx, 0, ctx->stream, true);      // the depth passes always produce whole maps
+    if (rc0) return rc0;
+  }
   sgi_wait_reads_of(ctx, SGI_BUF_SHADOW_MAP, ctx->stream);
   int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP, ctx->stream);
   // one light: main stream, scratch set 0.  Several lights: dealt round-robin to SGI_LIGHT_LANES streams with their own
@@ -452,6 +517,12 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
     if (ctx->gbuf_exposed) SGI_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
   }
+  {
+    const sgi_params& q = ctx->params;
+    const bool whole = (q.rect_x1 <= q.rect_x0 || q.rect_y1 <= q.rect_y0) || (q.rect_x0 <= 0 && q.rect_y0 <= 0 && q.rect_x1 >= ctx->W && q.rect_y1 >= ctx->H);
+    int rc0 = prepare_target_write(ctx, 1, st, whole);
+    if (rc0) return rc0;
+  }
   sgi_wait_reads_of(ctx, SGI_BUF_GBUF_POS, st); sgi_wait_reads_of(ctx, SGI_BUF_GBUF_NRM, st); sgi_wait_reads_of(ctx, SGI_BUF_CAM_DEPTH, st);
   sgi_wait_reads_of(ctx, SGI_BUF_GBUF_ALBEDO, st);
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
@@ -483,8 +554,16 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->gbuffer_valid || !ctx->shadow_map_valid) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  int rc = sgi_join_gbuffer(ctx);
-  if (rc) return rc;
+  int rc;
+  // With pass overlap on, the shadow pass goes to the visibility stream: it waits for everything queued on the main stream
+  // so far (the depth pass, uploads) and for the G-buffer pass, and the main stream does NOT wait for it - the next frame's
+  // depth / G-buffer passes start right away into the other instance of their targets (prepare_target_write).
+  cudaStream_t vs = ctx->overlap_passes ? ctx->vis_stream : ctx->stream;
+  if (ctx->overlap_passes) {
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_s2v, ctx->stream));
+    SGI_CUDA(ctx, cudaStreamWaitEvent(vs, ctx->ev_s2v, 0));
+    if (ctx->gbuf_in_flight) SGI_CUDA(ctx, cudaStreamWaitEvent(vs, ctx->ev_gbuf_done, 0));
+  } else if ((rc = sgi_join_gbuffer(ctx))) return rc;
   {
     // If the visibility buffer is still being copied out by an asynchronous read (frame pipelining) and this call
     // produces the whole screen, write into a spare buffer instead of making the shadow kernel wait for the copy:
@@ -495,31 +574,39 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
     if (t >= 0 && ctx->read_pending[t] && whole && cudaEventQuery(ctx->read_done[t]) == cudaErrorNotReady) {
       const size_t bytes = ctx->buf_bytes[SGI_BUF_VISIBILITY];
       if (ctx->vis_spare_bytes != bytes) {
-        if (ctx->vis_spare) { SGI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); cudaFree(ctx->vis_spare); }
+        if (ctx->vis_spare) { sync_all_streams(ctx); cudaFree(ctx->vis_spare); }
         ctx->vis_spare = nullptr; ctx->vis_spare_bytes = 0; ctx->vis_spare_ticket = -1;
         SGI_CUDA(ctx, cudaMalloc(&ctx->vis_spare, bytes));
         ctx->vis_spare_bytes = bytes;
       }
       // the spare's own last copy-out (two frames ago) must have finished before it is overwritten
       if (ctx->vis_spare_ticket >= 0 && ctx->read_pending[ctx->vis_spare_ticket])
-        cudaStreamWaitEvent(ctx->stream, ctx->read_done[ctx->vis_spare_ticket], 0);
+        cudaStreamWaitEvent(vs, ctx->read_done[ctx->vis_spare_ticket], 0);
       std::swap(ctx->buf[SGI_BUF_VISIBILITY], ctx->vis_spare);
       ctx->vis_spare_ticket = t;
       ctx->buf_read_ticket[SGI_BUF_VISIBILITY] = -1;
     } else {
       cudaGetLastError();
-      sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, ctx->stream);
+      sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, vs);
     }
   }
   if (ctx->params.technique == SGI_TECH_EDTSM_NONCONS || ctx->params.technique == SGI_TECH_EDTSM_CONS) {
     if ((rc = ensure_buf(ctx, SGI_BUF_EDT_NEAREST, (size_t)ctx->W * ctx->H * 4))) return rc;
-    sgi_wait_reads_of(ctx, SGI_BUF_EDT_NEAREST, ctx->stream);
+    sgi_wait_reads_of(ctx, SGI_BUF_EDT_NEAREST, vs);
   }
-  int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, ctx->stream);
-  rc = sgi_shadow_run(ctx);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, vs);
+  rc = sgi_shadow_run(ctx, vs);
   if (rc) return rc;
-  sgi_timing_end(ctx, SGI_PASS_VISIBILITY, slot, ctx->stream);
-  mark_gbuffer_use(ctx);
+  sgi_timing_end(ctx, SGI_PASS_VISIBILITY, slot, vs);
+  if (ctx->overlap_passes) {
+    const int e = ctx->vis_ev_next; ctx->vis_ev_next = (ctx->vis_ev_next + 1) & 3;
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_vis[e], vs));
+    ctx->vis_last = e; ctx->vis_in_flight = true;
+    ctx->sm_reader_cur = e; ctx->gb_reader_cur = e;        // this pass reads the current instances of both target groups
+    // a caller holding the visibility buffer's device pointer queues its own work on the context's stream: keep that
+    // stream ordered after the pass for it
+    if (ctx->vis_exposed) { if ((rc = sgi_join_vis(ctx))) return rc; }
+  } else mark_gbuffer_use(ctx);
   return SGI_OK;
 }
 
@@ -529,6 +616,7 @@ int sgi_shade_phong(sgi_ctx* ctx, const float clear_rgba[4]) {
   cudaSetDevice(ctx->device);
   int rc = sgi_join_gbuffer(ctx);
   if (rc) return rc;
+  if ((rc = sgi_join_vis(ctx))) return rc;
   sgi_wait_reads_of(ctx, SGI_BUF_SHADED, ctx->stream);
   if (ctx->has_rgb && ctx->rgb_V != ctx->V) { ctx->err = "sgi_shade_phong: colours do not match the current mesh"; return SGI_ERR_INVALID; }
   rc = sgi_shade_run(ctx, clear_rgba);
@@ -567,10 +655,19 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   return SGI_OK;
 }
 
+// Orders the context's stream after every pass queued so far on the internal streams (G-buffer, shadow pass), without
+// blocking the host: work the caller queues on that stream afterwards sees the finished frame.
+int sgi_join(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = sgi_join_gbuffer(ctx);
+  return rc ? rc : sgi_join_vis(ctx);
+}
+
 int sgi_synchronize(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  sgi_join_gbuffer(ctx);
+  sgi_join_gbuffer(ctx); sgi_join_vis(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   for (int k = 0; k < 4; k++) ctx->read_pending[k] = false;
@@ -582,7 +679,7 @@ int sgi_read(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes) {
   if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dst) return SGI_ERR_INVALID;
   if (!ctx->buf[which] || bytes > ctx->buf_bytes[which]) { ctx->err = "sgi_read: buffer not produced yet or size too large"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  sgi_join_gbuffer(ctx);
+  sgi_join_gbuffer(ctx); sgi_join_vis(ctx);
   SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->stream));
   mark_gbuffer_use(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -598,6 +695,8 @@ int sgi_read_async(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes, int32_t
   if (ctx->read_pending[t]) { SGI_CUDA(ctx, cudaEventSynchronize(ctx->read_done[t])); ctx->read_pending[t] = false; }   // back-pressure
   SGI_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->stream));                 // the buffer's producers are all on / joined into the main stream
   SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
+  if (ctx->vis_in_flight && ctx->vis_last >= 0)                                 // ... or on the visibility stream (not joined: the main stream keeps going)
+    SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_vis[ctx->vis_last], 0));
   SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
   SGI_CUDA(ctx, cudaEventRecord(ctx->read_done[t], ctx->copy_stream));
   ctx->read_pending[t] = true;
@@ -615,8 +714,10 @@ int sgi_read_wait(sgi_ctx* ctx, int32_t ticket) {
 
 int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** dptr, size_t* bytes) {
   if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dptr) return SGI_ERR_INVALID;
-  sgi_join_gbuffer(ctx);              // work queued on the main stream after this call sees a finished G-buffer
-  if (which == SGI_BUF_GBUF_POS || which == SGI_BUF_GBUF_NRM || which == SGI_BUF_CAM_DEPTH) ctx->gbuf_exposed = true;
+  sgi_join_gbuffer(ctx); sgi_join_vis(ctx);   // work queued on the main stream after this call sees finished passes
+  if (which == SGI_BUF_GBUF_POS || which == SGI_BUF_GBUF_NRM || which == SGI_BUF_CAM_DEPTH || which == SGI_BUF_GBUF_ALBEDO) ctx->gbuf_exposed = true;
+  if (which == SGI_BUF_SHADOW_MAP) ctx->sm_exposed = true;     // a lent-out pointer pins the instance: no more switching
+  if (which == SGI_BUF_VISIBILITY || which == SGI_BUF_EDT_NEAREST) ctx->vis_exposed = true;
   *dptr = ctx->buf[which];
   if (bytes) *bytes = ctx->buf_bytes[which];
   return ctx->buf[which] ? SGI_OK : SGI_ERR_INVALID;
@@ -641,7 +742,7 @@ int sgi_unregister_host(void* p) {
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   if (!ctx || !name) return SGI_ERR_INVALID;
   if (!strcmp(name, "vis_staged")) ctx->vis_staged = value != 0;
-  else if (!strcmp(name, "overlap_passes")) { sgi_join_gbuffer(ctx); ctx->overlap_passes = value != 0; }
+  else if (!strcmp(name, "overlap_passes")) { sgi_join_gbuffer(ctx); sgi_join_vis(ctx); ctx->overlap_passes = value != 0; }
   else if (!strcmp(name, "tile_order")) ctx->tile_order = value ? 1 : 0;
   else if (!strcmp(name, "tile_split")) ctx->tile_split = value < 0 ? 0 : value;
   else if (!strcmp(name, "borrow_pinned")) ctx->borrow_pinned = value ? 1 : 0;

@@ -680,7 +680,7 @@ int sgi_host_pcf_offsets(int kernel_order, int penumbra_size, int inclusive, flo
   return n;
 }
 
-int sgi_shadow_run(sgi_ctx* ctx) {
+int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   VisArgs a;
   a.p = ctx->params;
   for (int k = 0; k < 16; k++) a.mv[k] = ctx->cam_mv[k];
@@ -725,7 +725,7 @@ int sgi_shadow_run(sgi_ctx* ctx) {
 
   int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
   if (rw <= 0 || rh <= 0) return SGI_OK;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = stream;
   // EDT shadow mapping: the hard shadows are the SMSR branch of the RBSM programs (main.cpp:406-409,
   // NonConservativeSMSR.frag:381) rendered into a side buffer, the EDT filter chain then produces the visibility
   const bool edtsm = ctx->params.technique == SGI_TECH_EDTSM_NONCONS || ctx->params.technique == SGI_TECH_EDTSM_CONS;

@@ -182,6 +182,10 @@ int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** device_ptr, size_t* bytes
 int sgi_read_async(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes, int32_t* ticket);
 int sgi_read_wait(sgi_ctx* ctx, int32_t ticket);
 int sgi_synchronize(sgi_ctx* ctx);
+/* Orders the context's stream after every pass queued so far (the G-buffer and shadow passes run on internal streams and
+ * overlap the next frame's passes); does not block the host.  sgi_read*, sgi_device_ptr, sgi_shade_phong and
+ * sgi_synchronize do this themselves. */
+int sgi_join(sgi_ctx* ctx);
 
 /* page-locked host memory for callers that want sgi_set_mesh / sgi_read to be true async DMA
  * (the reference keeps its Mesh arrays in malloc'd memory and lets the GL driver stage them) */
