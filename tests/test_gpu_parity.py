@@ -407,6 +407,50 @@ def test_host_saves_the_shaded_frame_as_png(ctx, tmp_path):
         app.close()
 
 
+def test_lent_device_pointer_sees_each_frame_on_the_callers_stream(ctx):
+    """A caller that holds the visibility buffer's device pointer and queues its own work on the context's stream (what
+    bench.py's light-shard mode does with NCCL) must see every frame's result without any explicit synchronisation, although
+    the shadow pass runs on an internal stream."""
+    import torch
+
+    class DevView:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    sc = util.scene("dragon")
+    W, H, S = 1280, 720, 2048
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    try:
+        po, pg = util.params_pair("pcss", S)
+        util_frames = []
+        fm0 = setup_frame(ctx, sc, W, H, S, pg)
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+        ptr, nbytes = ctx.device_ptr("visibility")
+        vis_t = torch.as_tensor(DevView(ptr, nbytes // 4), device="cuda:0")
+        snaps, expect = [], []
+        for k in range(6):
+            light = sc["light_eye"] + np.array([6.0 * k, 0, -4.0 * k], np.float32)
+            fm = util.frame(sc, W, H, S, light_eye=light)
+            ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+            ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+            with torch.cuda.stream(stream):
+                snaps.append(vis_t.clone())                     # queued on the context's stream right behind the frame
+            util_frames.append(fm)
+        for k in range(6):                                      # the same frames again, read through the blocking call
+            fm = util_frames[k]
+            ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+            ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+            expect.append(ctx.read("visibility"))
+        torch.cuda.synchronize()
+        for k in range(6):
+            assert util.bits_equal(snaps[k].cpu().numpy().reshape(H, W), expect[k]), k
+        assert not util.bits_equal(expect[0], expect[5])
+    finally:
+        ctx.synchronize()
+        ctx.set_stream(None)
+
+
 def test_config_c4_tree_shadow_volumes(ctx):
     """c4: TreeWithLeaves (the present half of it), 640x480 as in the reference: signed z-pass counts and 8-bit stencil."""
     sc = util.scene("tree")
