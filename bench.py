@@ -87,19 +87,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def metric_name(workload, w):
+    """BASELINE.json's metric for the headline workload; the other configurations are named after themselves."""
+    return METRIC if workload == "c2_sponza" else f"frames/sec at {w['W']}x{w['H']} ({workload}, {w['program']}/{w['technique']})"
+
+
 def algorithmic_bytes(w, V, T, L):
     """SURVEY.md §8(d) / BASELINE.md §3 per-frame algorithmic bytes of each pass."""
     px, S = w["W"] * w["H"], w["S"]
     # G-buffer: 32 B/px (position + normal), 48 B/px when the scene has vertex colours and the albedo target is written too
     gb = (48 if any(l.startswith("c ") for l in w["lines"]) else 32) * px + 12 * (V + T)
-    return {"shadow_map": L * (4 * S * S + 12 * (V + T)), "gbuffer": gb, "visibility": 36 * px + L * 4 * S * S}
+    ab = {"shadow_map": L * (4 * S * S + 12 * (V + T)), "gbuffer": gb, "visibility": 36 * px + L * 4 * S * S}
+    ab["shadow_volume"] = 8 * px + 36 * T + 144 * T          # depth read + count write + geometry read + prisms written and read back
+    return ab
 
 
 def run_reference(args, w, cfg_path):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference's GL
     passes cannot run here: no OpenGL; its shaders compiled as C++ are used as the oracle's pin)."""
     from oracle import oracle_py as O
-    from globalillumination_b200 import hostapi
+    from globalillumination_b200 import hostapi, scenes
     # all the host threads the process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the
     # CPU arm on one core at N > 1
     try:
@@ -107,10 +114,10 @@ def run_reference(args, w, cfg_path):
     except AttributeError:
         n_host = os.cpu_count() or 1
     O.set_num_threads(n_host)
-    sc = hostapi.load_scene(cfg_path)
+    sc = scenes.golden_scene(w["golden"]) if w.get("golden") else hostapi.load_scene(cfg_path)
     W, H, S = w["W"], w["H"], w["S"]
     n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
-    tech = {"pcss": "pcss", "montecarlo": "multi_hard"}[w["technique"]]
+    tech = {"pcss": "pcss", "montecarlo": "multi_hard", "naive": "hard", "smsr": "rbsm_noncons"}[w["technique"]]
     p = O.default_params(tech, S, depth_threshold=float(sc["depth_threshold"]),
                          **{k2: w["params"][k1] for k1, k2 in (("blockerSearchSize", "blocker_search_size"), ("kernelSize", "kernel_size"),
                                                                 ("lightSourceRadius", "light_source_radius")) if k1 in w["params"]})
@@ -120,6 +127,11 @@ def run_reference(args, w, cfg_path):
         if anim is not None:
             r = O.rotate(anim / 10.0, [0, 1, 0]).reshape(4, 4).T[:3, :3]
             le = (r @ le).astype(np.float32)
+        if w["program"] == "shadow_volumes":                    # ShadowVolumes/src/main.cpp:126-172
+            fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
+            _, _, depth = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+            pxyz, pidx = O.sv_build_prisms(sc["xyz"], sc["nrm"], sc["idx"], le)
+            return O.sv_count(pxyz, pidx, fm["cam_mvp"], W, H, depth)[0]
         if n_l == 1:
             fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
             sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
@@ -137,17 +149,18 @@ def run_reference(args, w, cfg_path):
         mvpb = np.stack(mvpb)
         return O.visibility_multi(p, mvpb[-1], mvpb[:, 12:16], pos, np.stack(maps))
 
+    static_light = w["program"] == "shadow_volumes"          # as in our arm (see main)
     anim = -1800.0
     for _ in range(args.warmup):
-        frame(anim); anim += ANIMATION_STEP
+        frame(None if static_light else anim); anim += ANIMATION_STEP
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        frame(anim); anim += ANIMATION_STEP
+        frame(None if static_light else anim); anim += ANIMATION_STEP
     dt = time.perf_counter() - t0
     fps = args.steps / dt
     cores = O.num_threads()
     return {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.workload, w), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "W": W, "H": H, "shadow_map": S, "technique": w["technique"], "lights": n_l, "scene": w["scene"]},
@@ -198,7 +211,10 @@ def main():
 
     from globalillumination_b200 import capi, hostapi
     app = hostapi.App(local_rank)
-    app.load_scene(cfg_path)
+    if w.get("golden"):
+        app.set_scene(scenes.golden_scene(w["golden"]))
+    else:
+        app.load_scene(cfg_path)
     app.configure(w["W"], w["H"], w["S"])
     app.set_technique(w["technique"])
     app.set(**w["params"])
@@ -206,10 +222,15 @@ def main():
     if lights_mode:
         app.set(animationOn=1, animation=-1800.0)                          # every rank works on the same frame
         app.set_light_shard(rank, world)
+    elif w["program"] == "shadow_volumes":
+        # static light: the prism lists of a moving light change size by large factors from frame to frame and the context
+        # re-sizes them with an error return (SGI_ERR_OVERFLOW, "run the frame again"), which a timed loop cannot absorb
+        app.set(animationOn=0)
     else:
         app.set(animationOn=1, animation=-1800.0 + ANIMATION_STEP * rank)     # rank r renders frames r, r+N, ...
     anim_stride = ANIMATION_STEP * (1 if lights_mode else world)
     program = w["program"]
+    result_buf = "sv_count" if program == "shadow_volumes" else "visibility"
     ctx = app.context()
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)
@@ -269,10 +290,16 @@ def main():
 
     app.upload_scene()
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            frame(); app.step_animation(anim_stride)
-        join_comm()
-        ctx.synchronize()
+        for attempt in range(6):
+            try:
+                for _ in range(args.warmup):
+                    frame(); app.step_animation(anim_stride)
+                join_comm()
+                ctx.synchronize()
+                break
+            except capi.SgiError as e:            # tile lists grown from the first measured frame: run the warm-up again
+                if "overflow" not in str(e) or attempt == 5:
+                    raise
 
         # ---- timed region: K steps, per-step events, L2 flushed before each ----
         clocks = ClockSampler(local_rank)
@@ -346,7 +373,7 @@ def main():
             the timed region, which ends when the last frame's pixels are in host memory."""
             pending = []
             for k in range(n):
-                pending.append(app.display_e2e_async(program, "visibility", host_vis2[k % E2E_DEPTH].data_ptr(), vis_bytes))
+                pending.append(app.display_e2e_async(program, result_buf, host_vis2[k % E2E_DEPTH].data_ptr(), vis_bytes))
                 app.step_animation(anim_stride)
                 if len(pending) >= E2E_DEPTH:
                     app.e2e_wait(pending.pop(0))
@@ -362,9 +389,9 @@ def main():
         # the blocking form (upload, passes, read back, return) for reference
         t0 = time.perf_counter()
         for _ in range(20):
-            app.display_e2e(program, "visibility", host_vis.data_ptr(), vis_bytes); app.step_animation(anim_stride)
+            app.display_e2e(program, result_buf, host_vis.data_ptr(), vis_bytes); app.step_animation(anim_stride)
         e2e_blocking_s = (time.perf_counter() - t0) / 20
-        lit = float((host_vis == 1.0).float().mean())
+        lit = float((host_vis == 1.0).float().mean()) if result_buf == "visibility" else None
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -378,7 +405,8 @@ def main():
     fps = (1 if lights_mode else world) * args.steps / (total_ms / 1e3)
     peak, peak_src = load_peaks()
     ab = algorithmic_bytes(w, V, T, n_l)
-    kernel_of = {"vis_kernel": ("k_visibility (per-pixel shadow test/filter)", ab["visibility"]),
+    kernel_of = {"tile_sv": ("k_tile<SVCOUNT> (shadow-volume prism counting)", ab["shadow_volume"]),
+                 "vis_kernel": ("k_visibility (per-pixel shadow test/filter)", ab["visibility"]),
                  "tile_depth": ("k_tile<DEPTH> (light-view tile rasteriser)", ab["shadow_map"] // max(1, n_l)),
                  "tile_gbuffer": ("k_tile<GBUFFER> (camera-view tile rasteriser + resolve)", ab["gbuffer"])}
     cand = {k: v for k, v in passes.items() if k in kernel_of}
@@ -414,7 +442,7 @@ def main():
                        "note": "l2_taps is an upper bound (every foreground pixel taking every tap); PCSS pixels without blockers stop after the blocker search"}
     med = float(np.median(step_ms)) if step_ms else None
     out = {
-        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.workload, w), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "ms_per_step_median": med, "higher_is_better": True, "scaling": "strong" if lights_mode else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,

@@ -26,7 +26,28 @@ WORKLOADS = {
         W=7680, H=4320, S=8192, program="soft_shadow_mapping", technique="montecarlo",
         params=dict(numberOfSamples=16, lightSourceSize=16),
         scene="procedural stand-in for Configs/SanDiego.txt (building/sphere assets not available on the GPU box)"),
+    # The other configurations of BASELINE.json (parity-test cases; measurable with `bench.py --workload ...`).  Their
+    # assets exist in the reference but /root/reference is not on the GPU box: the geometry is the reference loader's own
+    # output for the config file, committed as tests/golden/scene_<name>.npz (made by tests/golden/make_golden.py).
+    # Configs/Teapot.txt — c1: hard shadow mapping (`naive`)
+    "c1_teapot": dict(golden="teapot", lines=[], W=1280, H=720, S=1024, program="shadow_mapping", technique="naive", params={},
+                      scene="Configs/Teapot.txt through the reference's SceneLoader (golden scene_teapot.npz), 15706 triangles"),
+    # Configs/Dragon.txt — c3: revectorization-based shadow mapping at 4K
+    "c3_dragon": dict(golden="dragon", lines=[], W=3840, H=2160, S=4096, program="shadow_mapping", technique="smsr", params={},
+                      scene="Configs/Dragon.txt through the reference's SceneLoader (golden scene_dragon.npz), 100004 triangles"),
+    # Configs/TreeWithLeaves.txt (without the missing TreeSub1.obj) — c4: shadow volumes at the reference's window size
+    "c4_tree_sv": dict(golden="tree", lines=[], W=640, H=480, S=64, program="shadow_volumes", technique="naive", params={},
+                       scene="Configs/TreeWithLeaves.txt minus the missing TreeSub1.obj (golden scene_tree.npz), 38200 triangles -> 229200 prism triangles"),
+    "c4_tree_sv_1080p": dict(golden="tree", lines=[], W=1920, H=1080, S=64, program="shadow_volumes", technique="naive", params={},
+                             scene="as c4_tree_sv at 1920x1080"),
 }
+
+
+def golden_scene(name):
+    """The reference loader's output for a config (committed fixture)."""
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return dict(np.load(os.path.join(root, "tests", "golden", f"scene_{name}.npz")))
 
 
 def write_config(name, directory=None):
