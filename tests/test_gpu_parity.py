@@ -210,6 +210,67 @@ def test_shadow_volume_counts_bit_exact(ctx, name, W, H, func):
     assert (cnt_o != 0).mean() > 0.01
 
 
+@pytest.mark.parametrize("tech", ["hard", "pcf", "pcss", "rbsm_noncons", "rbssm", "edtsm_noncons"])
+def test_non_square_shadow_map(ctx, tech):
+    """Shadow map width != height (the light frustum's aspect follows, displaySceneFromLightPOV main.cpp:255): depth map and
+    visibility bit-exact."""
+    sc = util.scene("teapot")
+    W, H, SW, SH = 320, 180, 384, 200
+    fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], sc["light_eye"], sc["light_at"], W, H, SW, SH)
+    po, pg = util.params_pair(tech, SW, depth_threshold=float(sc["depth_threshold"]), shadow_map_height=SH, penumbra_size=5 if tech.startswith("edt") else 1)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], SW, SH)
+    ctx.set_params(pg)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    sm = ctx.read("shadow_map")[0]
+    assert sm.shape == (SH, SW)
+    sm_o = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], SW, SH)
+    assert util.bits_equal(sm, sm_o), util.describe_diff(sm, sm_o)
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    pos, nrm = ctx.read("gbuf_pos"), ctx.read("gbuf_nrm")
+    if tech.startswith("edt"):
+        vis_o, _ = O.edtsm(po, cam, fm["cam_mvp"], fm["light_mvp_b"], pos, nrm, sm)
+    else:
+        vis_o = O.visibility(po, cam, fm["light_mvp_b"], pos, nrm, sm)
+    vis = ctx.read("visibility")
+    assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+    fg = pos[..., 0] != 0
+    assert 0.02 < (vis_o[fg] < 1.0).mean() < 0.98
+
+
+def test_tile_list_overflow_is_reported_and_recovered():
+    """When a frame needs more tile-list space than the context sized from earlier frames, the call that next touches the
+    host reports SGI_ERR_OVERFLOW, the lists are re-sized, and running the frame again gives the right answer."""
+    from globalillumination_b200 import capi
+    c = capi.Context(0)
+    try:
+        W, H, S = 640, 480, 64
+        small, big = util.scene("door"), util.scene("tree")
+        po, pg = util.params_pair("hard", S)
+        fm = setup_frame(c, small, W, H, S, pg)
+        c.render_gbuffer(); c.compute_shadow_volume(small["light_eye"]); c.synchronize()      # lists sized for a few prisms
+        fm = setup_frame(c, big, W, H, S, pg)                                                  # 229 200 prism triangles now
+        errors = 0
+        for attempt in range(6):
+            try:
+                c.render_gbuffer(); c.compute_shadow_volume(big["light_eye"])
+                cnt = c.read("sv_count")
+                break
+            except capi.SgiError as e:
+                assert e.code == -4 and "overflow" in str(e)
+                errors += 1
+        else:
+            raise AssertionError("the lists never became large enough")
+        assert errors >= 1, "expected at least one overflow report on the way"
+        depth = c.read("cam_depth")
+        pxyz, pidx = O.sv_build_prisms(big["xyz"], big["nrm"], big["idx"], big["light_eye"])
+        cnt_o, _ = O.sv_count(pxyz, pidx, fm["cam_mvp"], W, H, depth)
+        assert np.array_equal(cnt, cnt_o)
+    finally:
+        c.close()
+
+
 def test_empty_and_degenerate_inputs(ctx):
     from globalillumination_b200 import capi
     sc = util.scene("door")

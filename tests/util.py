@@ -44,7 +44,7 @@ def params_pair(tech, S, **kw):
     """(oracle params, C-ABI params) with identical fields."""
     from globalillumination_b200 import capi
     po = O.default_params(tech, S, **kw)
-    pg = capi.default_params(tech, shadow_map_width=S, shadow_map_height=S, **kw)
+    pg = capi.default_params(tech, **{"shadow_map_width": S, "shadow_map_height": S, **kw})
     for f, _ in po._fields_:
         assert getattr(po, f) == getattr(pg, f), f
     return po, pg
