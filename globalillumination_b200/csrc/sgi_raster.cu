@@ -1109,7 +1109,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   // a previous frame asked for more list space than we had: grow before running again
   if (sc.h_flags[1] > 0 && (long long)sc.h_flags[1] + 1024 > sc.pair_cap) {
     SGI_CUDA(ctx, cudaStreamSynchronize(stream));
-    long long want = (long long)sc.h_flags[1] * 3 / 2 + (1 << 16);
+    long long want = (long long)sc.h_flags[1] * 2 + (1 << 16);
     if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
     sc.pair_cap = want;
   }
@@ -1165,7 +1165,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
     SGI_CUDA(ctx, cudaStreamSynchronize(st));
     sc.sized[job.mode] = true;
     if ((long long)sc.h_flags[1] > sc.pair_cap) {
-      long long want = (long long)sc.h_flags[1] * 3 / 2 + (1 << 16);
+      long long want = (long long)sc.h_flags[1] * 2 + (1 << 16);
       if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
       sc.pair_cap = want;
       ba.pairs = sc.d_pairs; ba.pair_cap = sc.pair_cap;
