@@ -194,10 +194,13 @@ int sgh_app_display(sgh_app* a, int32_t program) {
 // (loadVBOs on every draw), all passes, result read back to the caller's host buffer.
 int sgh_app_display_e2e(sgh_app* a, int32_t program, int32_t result_buffer, void* host_dst, size_t bytes) {
   if (!a) return -1;
-  int rc = a->app.uploadScene();
-  if (rc) return rc;
-  if ((rc = sgh_app_display(a, program))) return rc;
-  rc = sgi_read(a->app.context(), result_buffer, host_dst, bytes);
+  int rc = 0;
+  for (int attempt = 0; attempt < 4; attempt++) {     // a frame that outgrew the tile lists is run again (they have been re-sized)
+    if ((rc = a->app.uploadScene())) return rc;
+    if ((rc = sgh_app_display(a, program))) return rc;
+    rc = sgi_read(a->app.context(), result_buffer, host_dst, bytes);
+    if (rc != SGI_ERR_OVERFLOW) break;
+  }
   if (rc) g_err = sgi_last_error(a->app.context());
   return rc;
 }
