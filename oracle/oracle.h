@@ -50,7 +50,11 @@ enum {
   ORC_TECH_MULTI_HARD = 8,    /* AccurateSoftShadow.frag monteCarlo (N lights)         */
   ORC_TECH_RBSSM = 9,         /* RBSSM.frag (revectorization-based soft shadows)       */
   ORC_TECH_EDTSM_NONCONS = 10,/* EDT shadow mapping over NonConservativeSMSR.frag      */
-  ORC_TECH_EDTSM_CONS = 11    /* EDT shadow mapping over ConservativeSMSR.frag         */
+  ORC_TECH_EDTSM_CONS = 11,   /* EDT shadow mapping over ConservativeSMSR.frag         */
+  ORC_TECH_VSM = 12,          /* Shadow.frag VSM==1  (variance shadow mapping)         */
+  ORC_TECH_ESM = 13,          /* Shadow.frag ESM==1  (exponential)                     */
+  ORC_TECH_EVSM = 14,         /* Shadow.frag EVSM==1 (exponential variance)            */
+  ORC_TECH_MSM = 15           /* Shadow.frag MSM==1  (Hamburger 4-moment)              */
 };
 
 enum { ORC_DEPTH_LESS = 0, ORC_DEPTH_LEQUAL = 1 };
@@ -136,6 +140,21 @@ void orc_mean_filter(const float* in2, const float* pos4, const float cam_mv[16]
                      int z_near, int z_far, int linear, float* out2);
 void orc_edtsm(const orc_params* p, const orc_camera* cam, const float cam_mvp[16], const float light_mvp_b[16],
                const float* pos4, const float* nrm4, int W, int H, const float* shadow_map, float* vis, int16_t* near2_out);
+
+/* ---- moment shadow maps: VSM / ESM / EVSM / MSM (oracle_moments_impl.h, oracle_raster.c) ------- */
+void orc_msm_quantization(float m[16], float minv[16], float t[4]);
+void orc_moment_texel(int technique, float zwin, float zwin_px, float zwin_py, int x_odd, int y_odd, int z_near, int z_far,
+                      float out4[4]);
+/* mom4: float4[H][W] moment target of the light-view pass, cleared to (0,0,0,1) */
+int  orc_raster_moments(const float* xyz, int V, const int32_t* idx, int T, const float mvp[16], int W, int H, float factor,
+                        float units, int technique, int z_near, int z_far, float* mom4);
+void orc_gaussian_kernel(int order, float* kernel);
+/* one separable pass of filterShadowMap into a W x H target; src4 is sw x sh */
+void orc_filter_moments(const float* src4, int sw, int sh, int W, int H, int order, const float* kernel, int horizontal,
+                        int log_space, float* dst4);
+/* fmap4: the twice-filtered map (mw x mh = the window size in the reference) */
+void orc_visibility_moments(const orc_params* p, const orc_camera* cam, const float light_mvp_b[16], const float* pos4,
+                            const float* nrm4, int W, int H, const float* fmap4, int mw, int mh, float* vis);
 
 /* ---- shadow volumes --------------------------------------------------------------------------- */
 /* prism_xyz: 6T vertices*3, prism_idx: 6T triangles*3 (ShadowVolume::build/update)                */

@@ -16,7 +16,9 @@ REF_DIR = os.path.join(HERE, "_ref")
 TECH = {
     "hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4,
     "rpcf_noncons": 5, "rpcf_cons": 6, "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11,
+    "vsm": 12, "esm": 13, "evsm": 14, "msm": 15,
 }
+MOMENT_TECHS = ("vsm", "esm", "evsm", "msm")
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
 
 
@@ -85,7 +87,7 @@ def _i32(a):
 def build(force=False):
     """Compile oracle/liboracle.so (and oracle/_ref when /root/reference is present)."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("oracle_raster.c", "oracle_shadow.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("oracle_raster.c", "oracle_shadow.c", "oracle.h", "Makefile", "oracle_rbssm_impl.h", "oracle_edt_impl.h", "oracle_moments_impl.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return so
@@ -284,6 +286,60 @@ def edtsm(params, cam, cam_mvp, light_mvp_b, pos4, nrm4, shadow_map):
     return vis, near
 
 
+def msm_quantization():
+    """(mQuantization, mQuantizationInverse, tQuantization) as the uniforms hold them (column-major)."""
+    m, mi, t = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(4, np.float32)
+    lib().orc_msm_quantization(_fp(m), _fp(mi), _fp(t))
+    return m, mi, t
+
+
+def moment_texel(technique, zwin, zwin_px, zwin_py, x_odd, y_odd, z_near=1, z_far=1000):
+    out = np.zeros(4, np.float32)
+    lib().orc_moment_texel(TECH[technique], C.c_float(zwin), C.c_float(zwin_px), C.c_float(zwin_py), int(x_odd), int(y_odd),
+                           z_near, z_far, _fp(out))
+    return out
+
+
+def raster_moments(xyz, idx, mvp, W, H, technique, factor=4.0, units=20.0, z_near=1, z_far=1000):
+    xyz, idx, mvp = _f32(xyz), _i32(idx), _f32(mvp)
+    out = np.empty((H, W, 4), np.float32)
+    rc = lib().orc_raster_moments(_fp(xyz), xyz.size // 3, _ip(idx), idx.size // 3, _fp(mvp), W, H, C.c_float(factor),
+                                  C.c_float(units), TECH[technique], z_near, z_far, _fp(out))
+    assert rc == 0
+    return out
+
+
+def gaussian_kernel(order):
+    k = np.zeros(order, np.float32)
+    lib().orc_gaussian_kernel(order, _fp(k))
+    return k
+
+
+def filter_moments(src4, W, H, order, horizontal, log_space=False):
+    """One pass of filterShadowMap: src4[sh, sw, 4] -> float32[H, W, 4]."""
+    src4 = _f32(src4)
+    k = gaussian_kernel(order)
+    out = np.empty((H, W, 4), np.float32)
+    lib().orc_filter_moments(_fp(src4), src4.shape[1], src4.shape[0], W, H, order, _fp(k), int(bool(horizontal)),
+                             int(bool(log_space)), _fp(out))
+    return out
+
+
+def filter_shadow_map(mom4, W, H, order, technique):
+    """filterShadowMap(), ShadowMapping/src/main.cpp:374-398: X pass then Y pass into W x H targets."""
+    logs = technique == "esm"
+    return filter_moments(filter_moments(mom4, W, H, order, True, logs), W, H, order, False, logs)
+
+
+def visibility_moments(params, cam, light_mvp_b, pos4, nrm4, fmap4):
+    pos4, nrm4, fmap4, lm = _f32(pos4), _f32(nrm4), _f32(fmap4), _f32(light_mvp_b)
+    H, W = pos4.shape[:2]
+    vis = np.zeros((H, W), np.float32)
+    lib().orc_visibility_moments(C.byref(params), C.byref(cam), _fp(lm), _fp(pos4), _fp(nrm4), W, H, _fp(fmap4),
+                                 fmap4.shape[1], fmap4.shape[0], _fp(vis))
+    return vis
+
+
 def visibility_multi(params, light_mvp_b_common, trans4, pos4, shadow_maps):
     H, W = pos4.shape[:2]
     trans4 = _f32(trans4)
@@ -434,6 +490,13 @@ def ref_sv_prisms(xyz, nrm, idx, light, infinity=100):
     ref_host().ref_sv_prisms(_fp(xyz), _fp(nrm), xyz.size // 3, _ip(idx), T, _fp(_f32(light)), int(infinity),
                              _fp(pxyz), _ip(pidx))
     return pxyz, pidx
+
+
+def ref_moment_quantization(typed16):
+    t = _f32(typed16)
+    m, mi = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    ref_host().ref_moment_quantization(_fp(t), _fp(m), _fp(mi))
+    return m, mi
 
 
 def ref_uniform_sample(p, size, n_lights, index):

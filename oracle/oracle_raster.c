@@ -334,6 +334,58 @@ int orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, 
   return 0;
 }
 
+/* ---- moment shadow maps: the light-view pass with Moments.frag / Exponential.frag / ExponentialMoments.frag bound
+ * (ShadowMapping/src/main.cpp:227-243,350-361).  The depth test uses the polygon-offset depth (GL_LESS, first fragment in
+ * draw order wins ties); the colour written is a function of the un-offset plane depth of the winning fragment and of the
+ * same plane at its two 2x2-quad partners (oracle_moments_impl.h).  mom4: float4[H][W], cleared to (0,0,0,1) (:356). */
+static inline float plane_z(const SubTri* s, int i, int j) {
+  int64_t px = (int64_t)i * SUBPIX + SUBPIX / 2, py = (int64_t)j * SUBPIX + SUBPIX / 2;
+  int64_t E1 = ((int64_t)s->X[0] - s->X[2]) * (py - s->Y[2]) - ((int64_t)s->Y[0] - s->Y[2]) * (px - s->X[2]);
+  int64_t E2 = ((int64_t)s->X[1] - s->X[0]) * (py - s->Y[0]) - ((int64_t)s->Y[1] - s->Y[0]) * (px - s->X[0]);
+  float b1 = (float)E1 * s->ia, b2 = (float)E2 * s->ia;
+  return (s->z0 + b1 * s->dz1) + b2 * s->dz2;
+}
+
+int orc_raster_moments(const float* xyz, int V, const int32_t* idx, int T, const float mvp[16], int W, int H, float factor,
+                       float units, int technique, int z_near, int z_far, float* mom4) {
+  (void)V;
+  int64_t n;
+  SubTri* rec = build_records(xyz, idx, T, mvp, W, H, 1, factor, units, &n);
+  if (!rec) return -1;
+  float* depth = (float*)malloc(sizeof(float) * (size_t)W * H);
+  int64_t* win = (int64_t*)malloc(sizeof(int64_t) * (size_t)W * H);
+  if (!depth || !win) { free(rec); free(depth); free(win); return -1; }
+  for (size_t i = 0; i < (size_t)W * H; i++) { depth[i] = 1.0f; win[i] = -1; }
+  int bands = H < 64 ? 1 : 64;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int bnd = 0; bnd < bands; bnd++) {
+    int r0 = (int)((int64_t)H * bnd / bands), r1 = (int)((int64_t)H * (bnd + 1) / bands) - 1;
+    for (int64_t k = 0; k < n; k++) {
+      const SubTri* s = &rec[k];
+      int y0 = s->py0 > r0 ? s->py0 : r0, y1 = s->py1 < r1 ? s->py1 : r1;
+      for (int j = y0; j <= y1; j++)
+        for (int i = s->px0; i <= s->px1; i++) {
+          int64_t E[3];
+          if (!cover(s, i, j, E)) continue;
+          float z = frag_z(s, E);
+          size_t o = (size_t)j * W + i;
+          if (z < depth[o]) { depth[o] = z; win[o] = k; }
+        }
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      size_t o = (size_t)j * W + i;
+      float* m = mom4 + 4 * o;
+      if (win[o] < 0) { m[0] = 0.0f; m[1] = 0.0f; m[2] = 0.0f; m[3] = 1.0f; continue; }
+      const SubTri* s = &rec[win[o]];
+      orc_moment_texel(technique, plane_z(s, i, j), plane_z(s, i ^ 1, j), plane_z(s, i, j ^ 1), i & 1, j & 1, z_near, z_far, m);
+    }
+  free(rec); free(depth); free(win);
+  return 0;
+}
+
 /* ---- shadow volumes: ShadowVolumes/src/ShadowVolume.cpp:15-114 (build) == :116-195 (update) ---- */
 void orc_sv_build_prisms(const float* xyz, const float* nrm, int V, const int32_t* idx, int T, const float light[3],
                          int infinity, float* prism_xyz, int32_t* prism_idx) {

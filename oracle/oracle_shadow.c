@@ -677,3 +677,4 @@ void orc_shade_phong(const orc_camera* cam, float si, const float* pos4, const f
 }
 
 #include "oracle_edt_impl.h"    /* EDT shadow mapping: orc_edt_*, orc_mean_filter, orc_edtsm */
+#include "oracle_moments_impl.h" /* VSM / ESM / EVSM / MSM: orc_moment_texel, orc_filter_moments, orc_visibility_moments */

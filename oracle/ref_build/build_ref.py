@@ -36,6 +36,12 @@ SHADERS = {
     "phong": "ShadowMapping/Shaders/GBuffer/PhongShading.frag",
     "rbssm": "SoftShadowMapping/Shaders/SoftShadow/RBSSM.frag",
     "meanfilter": "ShadowMapping/Shaders/Filter/MeanFilter.frag",
+    # moment shadow maps: the light-view fragment programs and the separable blurs
+    "moments": "ShadowMapping/Shaders/ShadowMap/Moments.frag",
+    "exponential": "ShadowMapping/Shaders/ShadowMap/Exponential.frag",
+    "expmoments": "ShadowMapping/Shaders/ShadowMap/ExponentialMoments.frag",
+    "gaussian": "ShadowMapping/Shaders/Filter/GaussianFilter.frag",
+    "loggaussian": "ShadowMapping/Shaders/Filter/LogGaussianFilter.frag",
 }
 
 
@@ -59,6 +65,7 @@ def gen_swizzles():
 
 
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
+VARYING = re.compile(r"^\s*varying\s+vec4\s+(\w+)\s*;")
 UNIFORM = re.compile(r"^\s*uniform\s+(\w+)\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?\s*;")
 PLAIN_GLOBAL = re.compile(r"^(float|int|bool|vec[234]|mat[34])\s+\w+\s*;")
 
@@ -68,12 +75,15 @@ PLAIN_GLOBAL = re.compile(r"^(float|int|bool|vec[234]|mat[34])\s+\w+\s*;")
 DECL_FIXES = {
     "vec4 revectorizationBasedShadowMappingSmoothing(vec4 normalizedShadowCoord)":
         "float revectorizationBasedShadowMappingSmoothing(vec4 normalizedShadowCoord)",     # RBSSM.frag:1341 (every return is a float)
+    # LogGaussianFilter.frag:10 declares float for an expression of four identical components that the caller wraps in vec4()
+    "float log_conv ( float x0, vec4 X, float y0, vec4 Y )": "vec4 log_conv ( float x0, vec4 X, float y0, vec4 Y )",
 }
 
 
 def transform(src):
     """Literal suffixes, drop #extension, thread_local file-scope variables. Returns (text, uniforms)."""
     out, uniforms, depth = [], [], 0
+    varyings = []
     for a, b in DECL_FIXES.items():
         src = src.replace(a, b)
     for line in src.splitlines():
@@ -84,23 +94,42 @@ def transform(src):
         m = UNIFORM.match(code)
         if m:
             uniforms.append((m.group(1), m.group(2), int(m.group(3)) if m.group(3) else 0))
+        mv = VARYING.match(code)
+        if mv:
+            varyings.append(mv.group(1))
         new = FLOAT_LIT.sub(lambda mm: mm.group(1) + "f", line)
         if depth == 0 and PLAIN_GLOBAL.match(code):
             new = "thread_local " + new
         depth += code.count("{") - code.count("}")
         out.append(new)
-    return "\n".join(out) + "\n", uniforms
+    return "\n".join(out) + "\n", uniforms, varyings
 
 
 RUNNER = r"""
 struct RefBinding { const char* name; const void* data; uint64_t size; };
 
+// per-pixel inputs of programs that are not full-screen passes: `varying vec4` images ("varying:<name>", float4[H][W]) and
+// the values dFdx / dFdy return for this fragment ("dFdx", "dFdy", float[H][W]; the harness supplies the derivative, the
+// shader's own arithmetic runs unmodified)
+static thread_local const float* vary_img[8];
+static thread_local const float* ddx_img;
+static thread_local const float* ddy_img;
 static int bind_all(const RefBinding* b, int n) {
   int bound = 0;
+  for (int k = 0; k < 8; k++) vary_img[k] = nullptr;
+  ddx_img = nullptr; ddy_img = nullptr;
   for (int i = 0; i < n; i++) {
+    if (!strcmp(b[i].name, "dFdx")) { ddx_img = (const float*)b[i].data; continue; }
+    if (!strcmp(b[i].name, "dFdy")) { ddy_img = (const float*)b[i].data; continue; }
+    %(VBINDS)s
     %(BINDS)s
   }
   return bound;
+}
+static inline void set_varyings(size_t o) {
+  if (ddx_img) glsl::g_dfdx = ddx_img[o];
+  if (ddy_img) glsl::g_dfdy = ddy_img[o];
+  %(VSETS)s
 }
 }  // namespace shader_%(NAME)s
 
@@ -115,8 +144,9 @@ extern "C" int ref_%(NAME)s_run(const shader_%(NAME)s::RefBinding* b, int nb, in
       for (int i = x0; i < x1; i++) {
         // Shadow.vert:7-8: f_texcoord = texcoord*0.5+0.5 with texcoord the quad's NDC position
         float nx = ((float)i + 0.5f) / (float)W * 2.0f - 1.0f, ny = ((float)j + 0.5f) / (float)H * 2.0f - 1.0f;
-        f_texcoord = glsl::vec2(nx * 0.5f + 0.5f, ny * 0.5f + 0.5f);
+        %(TEXCOORD)sf_texcoord = glsl::vec2(nx * 0.5f + 0.5f, ny * 0.5f + 0.5f);
         gl_discarded = false;
+        set_varyings((size_t)j * W + i);
         float* o = out0 + 4 * ((size_t)j * W + i);
         gl_FragData[0] = glsl::vec4(o[0], o[1], o[2], o[3]);
         shader_main();
@@ -132,7 +162,7 @@ extern "C" int ref_%(NAME)s_run(const shader_%(NAME)s::RefBinding* b, int nb, in
 def gen_shader_tu(name, ref_root):
     path = os.path.join(ref_root, SHADERS[name])
     with open(path, "r", errors="replace") as f:
-        text, uniforms = transform(f.read())
+        text, uniforms, varyings = transform(f.read())
     binds = []
     for ty, nm, arr in uniforms:
         binds.append(
@@ -158,7 +188,14 @@ def gen_shader_tu(name, ref_root):
         "#undef varying",
         "#undef main",
         "#undef discard",
-        RUNNER % {"NAME": name, "BINDS": "\n    ".join(binds)},
+        RUNNER % {"NAME": name, "BINDS": "\n    ".join(binds),
+                  "TEXCOORD": "" if "f_texcoord" in text else "(void)nx; (void)ny; // no f_texcoord in this program: ",
+                  "VBINDS": "\n    ".join(
+                      f'if (!strcmp(b[i].name, "varying:{v}")) {{ vary_img[{k}] = (const float*)b[i].data; continue; }}'
+                      for k, v in enumerate(varyings)),
+                  "VSETS": "\n  ".join(
+                      f"if (vary_img[{k}]) {v} = glsl::vec4(vary_img[{k}][4 * o], vary_img[{k}][4 * o + 1], vary_img[{k}][4 * o + 2], vary_img[{k}][4 * o + 3]);"
+                      for k, v in enumerate(varyings))},
     ]
     out = os.path.join(GEN, f"shader_{name}.cpp")
     with open(out, "w") as f:

@@ -197,6 +197,11 @@ inline float exp(float x) { return std::exp(x); }
 inline float log(float x) { return std::log(x); }
 inline float log2(float x) { return std::log2(x); }
 inline float pow(float x, float y) { return std::pow(x, y); }
+// dFdx / dFdy: the runner supplies the derivative of the fragment (the quad differences are a property of the rasteriser, not
+// of the shader source); see build_ref.py RUNNER
+inline thread_local float g_dfdx = 0.0f, g_dfdy = 0.0f;
+inline float dFdx(float) { return g_dfdx; }
+inline float dFdy(float) { return g_dfdy; }
 inline float inversesqrt(float x) { return 1.0f / std::sqrt(x); }
 inline float fract(float x) { return x - std::floor(x); }
 inline float max(float a, float b) { return a < b ? b : a; }

@@ -125,6 +125,18 @@ void ref_sv_prisms(const float* xyz, const float* nrm, int V, const int* idx, in
   // leaked on purpose: the reference's destructors mix malloc/delete[]
 }
 
+// MyGLGeometryViewer::configureMoments (ShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:191-199): the 16 numbers are typed
+// into mQuantization[i][j] (passed in here in that order), then glm::transpose and glm::inverse of the vendored GLM run.
+void ref_moment_quantization(const float typed16[16], float m_out[16], float minv_out[16]) {
+  glm::mat4 mQuantization, mQuantizationInverse;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) mQuantization[i][j] = typed16[i * 4 + j];
+  mQuantization = glm::transpose(mQuantization);
+  mQuantizationInverse = glm::inverse(mQuantization);
+  put(mQuantization, m_out);
+  put(mQuantizationInverse, minv_out);
+}
+
 #ifdef SSM_INCLUDE
 void ref_uniform_sample(const float* p, int size, int n_lights, int index, float* eye_out) {
   LightSource base;

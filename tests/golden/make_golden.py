@@ -9,6 +9,9 @@ were made:   python tests/golden/make_golden.py
   scene_<name>.npz        the reference loader's output for Configs/<Name>.txt: xyz, nrm, idx + views
   golden_host.npz         GLM frame matrices per config, ShadowVolume prisms, uniform light samples
   golden_shaders.npz      one small frame (inputs + uniforms) and gl_FragData[0].r of every technique
+  golden_moments.npz      VSM / ESM / EVSM / MSM: the light-view moment programs on seeded fragments, both passes of
+                          filterShadowMap and Shadow.frag's reconstruction on a small frame, GLM's quantisation matrices
+                          (python tests/golden/make_golden.py --only-moments regenerates this file alone)
 """
 import os
 import sys
@@ -76,7 +79,93 @@ def multi_light_setup(sc, n_lights, size, W, H, S):
     return np.stack(mvps), np.stack(mvpbs)
 
 
+# ---- moment shadow maps (VSM / ESM / EVSM / MSM): golden_moments.npz -------------------------------------------------
+MOMENT_TYPED = [-2.07224649, 32.2370378, -68.5710746, 39.3703274, 13.7948857, -59.4683976, 82.035975, -35.3649032,
+                0.105877704, -1.90774663, 9.34965551, -6.65434907, 9.79240621, -33.76521106, 47.9456097, -23.9728048]
+MOMENT_SHADER = {"vsm": ("moments", dict(VSM=1, MSM=0)), "msm": ("moments", dict(VSM=0, MSM=1)),
+                 "esm": ("exponential", {}), "evsm": ("expmoments", {})}
+
+
+def lin32(d, n=1, f=1000):
+    n, f = np.float32(n), np.float32(f)
+    return (np.float32(2.0) * n) / (f + n - d * (f - n))
+
+
+def moment_texel_inputs(seed=5, W=32, H=24):
+    """Random per-fragment inputs of the light-view moment programs: window depth of the fragment and of its two quad
+    partners, the `position` varying that yields it and the dFdx / dFdy the fine quad differences give."""
+    rng = np.random.default_rng(seed)
+    ndc = rng.uniform(0.2, 0.9999, (H, W)).astype(np.float32)
+    ndc[::5, ::3] = rng.uniform(-1.0, 0.2, ndc[::5, ::3].shape).astype(np.float32)
+    zwin = ndc * np.float32(0.5) + np.float32(0.5)
+    zpx = (zwin + rng.uniform(-2e-4, 2e-4, (H, W)).astype(np.float32)).astype(np.float32)
+    zpy = (zwin + rng.uniform(-2e-4, 2e-4, (H, W)).astype(np.float32)).astype(np.float32)
+    xo = (np.arange(W)[None, :] & 1).astype(bool) & np.ones((H, W), bool)
+    yo = (np.arange(H)[:, None] & 1).astype(bool) & np.ones((H, W), bool)
+    d, dpx, dpy = lin32(zwin), lin32(zpx), lin32(zpy)
+    ddx = np.where(xo, d - dpx, dpx - d).astype(np.float32)
+    ddy = np.where(yo, d - dpy, dpy - d).astype(np.float32)
+    pos = np.zeros((H, W, 4), np.float32)
+    pos[..., 2] = ndc; pos[..., 3] = 1.0
+    return dict(zwin=zwin, zpx=zpx, zpy=zpy, ddx=ddx, ddy=ddy, position=pos)
+
+
+def ref_moment_texels(tech, ti, m_q, t_q):
+    shader, flags = MOMENT_SHADER[tech]
+    H, W = ti["zwin"].shape
+    u = {"varying:position": ti["position"], "dFdx": ti["ddx"], "dFdy": ti["ddy"], "zNear": np.int32(1), "zFar": np.int32(1000),
+         "mQuantization": m_q, "tQuantization": t_q}
+    u.update({k: np.int32(v) for k, v in flags.items()})
+    return O.ref_run_shader(shader, u, W, H)
+
+
+def ref_filter_pass(src4, W, H, order, horizontal, tech):
+    k = np.zeros(33, np.float32)
+    k[:order] = O.gaussian_kernel(order)
+    u = dict(image=("tex", src4, "linear"), width=np.int32(W), height=np.int32(H), order=np.int32(order),
+             horizontal=np.int32(horizontal), vertical=np.int32(1 - horizontal), kernel=k)
+    return O.ref_run_shader("loggaussian" if tech == "esm" else "gaussian", u, W, H)
+
+
+def ref_visibility_moments(tech, fm, pos, nrm, fmap, p, W, H, m_qi, t_q):
+    u = shader_uniforms(fm, pos, nrm, np.zeros((2, 2), np.float32), p.shadow_map_width, p)
+    u["shadowMap"] = ("tex", fmap, "linear")
+    u.update(dict(naive=np.int32(0), bilinearPCF=np.int32(0), VSM=np.int32(tech == "vsm"), ESM=np.int32(tech == "esm"),
+                  EVSM=np.int32(tech == "evsm"), MSM=np.int32(tech == "msm"), mQuantizationInverse=m_qi, tQuantization=t_q))
+    return O.ref_run_shader("shadow", u, W, H)[..., 0].copy()
+
+
+def make_moments(scenes):
+    out = {}
+    m_q, m_qi = O.ref_moment_quantization(MOMENT_TYPED)       # the reference's GLM: transpose + inverse
+    t_q = np.array([0.0359558848, 0, 0, 0], np.float32)
+    out["quant/m"], out["quant/minv"], out["quant/t"] = m_q, m_qi, t_q
+    ti = moment_texel_inputs()
+    for k, v in ti.items():
+        out[f"texel/{k}"] = v
+    W, H, S, order = 128, 72, 96, 7
+    sc = scenes["teapot"]
+    fm = O.ref_frame_matrices(sc["cam_eye"], sc["cam_at"], sc["light_eye"], sc["light_at"], W, H, S, S)
+    pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    out.update(W=W, H=H, S=S, order=order, **{f"fm_{k}": v for k, v in fm.items()})
+    for tech in O.MOMENT_TECHS:
+        out[f"texel/{tech}"] = ref_moment_texels(tech, ti, m_q, t_q)
+        # the chain's input is the moment target the oracle's own rasteriser produces (the GL rasteriser has no source)
+        mom = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
+        fx = ref_filter_pass(mom, W, H, order, 1, tech)
+        fy = ref_filter_pass(fx, W, H, order, 0, tech)
+        out[f"chain/{tech}/filter_x"], out[f"chain/{tech}/filter_y"] = fx, fy
+        for variant, si in (("default", 0.25), ("alt", 0.5)):
+            p = O.default_params(tech, S, shadow_intensity=si)
+            out[f"chain/{tech}/vis/{variant}"] = ref_visibility_moments(tech, fm, pos, nrm, fy, p, W, H, m_qi, t_q)
+    np.savez_compressed(os.path.join(HERE, "golden_moments.npz"), **out)
+    print("golden_moments.npz", os.path.getsize(os.path.join(HERE, "golden_moments.npz")) // 1024, "KiB")
+
+
 def main():
+    if "--only-moments" in sys.argv:
+        assert O.build_ref(), "oracle/_ref could not be built (is /root/reference mounted?)"
+        return make_moments({"teapot": O.ref_load_scene(SCENES["teapot"])})
     assert O.build_ref(), "oracle/_ref could not be built (is /root/reference mounted?)"
     scenes = {}
     for name, cfg in SCENES.items():
@@ -158,6 +247,7 @@ def main():
             out[f"edt/{tech}/filter_{axis}_in"] = rgba[..., :2].copy()
             out[f"edt/{tech}/filter_{axis}"] = stage
     np.savez_compressed(os.path.join(HERE, "golden_shaders.npz"), **out)
+    make_moments(scenes)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -1,0 +1,98 @@
+"""Moment shadow maps (VSM / ESM / EVSM / MSM): the CPU oracle against golden vectors made by the
+reference's own unmodified sources (tests/golden/make_golden.py --only-moments): Moments.frag / Exponential.frag /
+ExponentialMoments.frag on seeded fragments, both GaussianFilter.frag / LogGaussianFilter.frag passes of filterShadowMap,
+Shadow.frag's reconstruction branches, and GLM's transpose / inverse of the quantisation matrix.  All bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tests import util
+
+G = "golden_moments.npz"
+
+
+def test_quantization_matrices_match_the_reference_glm():
+    g = util.golden(G)
+    m, mi, t = O.msm_quantization()
+    assert util.bits_equal(m, g["quant/m"]) and util.bits_equal(mi, g["quant/minv"]) and util.bits_equal(t, g["quant/t"])
+    # sanity: it is an inverse
+    assert np.allclose(m.reshape(4, 4).T.astype(np.float64) @ mi.reshape(4, 4).T.astype(np.float64), np.eye(4), atol=1e-4)
+
+
+def test_gaussian_kernel_is_the_binomial_row():
+    # Filter::buildGaussianKernel(7): 1 6 15 20 15 6 1 over 64
+    assert O.gaussian_kernel(7).tolist() == [1 / 64, 6 / 64, 15 / 64, 20 / 64, 15 / 64, 6 / 64, 1 / 64]
+    for order in (3, 5, 9, 11):
+        k = O.gaussian_kernel(order)
+        assert abs(float(k.sum()) - 1.0) < 1e-6 and (k == k[::-1]).all()
+
+
+@pytest.mark.parametrize("tech", O.MOMENT_TECHS)
+def test_moment_texel_matches_reference_shader_golden(tech):
+    g = util.golden(G)
+    zw, zpx, zpy = g["texel/zwin"], g["texel/zpx"], g["texel/zpy"]
+    H, W = zw.shape
+    got = np.zeros((H, W, 4), np.float32)
+    for j in range(H):
+        for i in range(W):
+            got[j, i] = O.moment_texel(tech, zw[j, i], zpx[j, i], zpy[j, i], i & 1, j & 1)
+    ref = g[f"texel/{tech}"]
+    assert util.bits_equal(got, ref), util.describe_diff(got, ref)
+
+
+@pytest.mark.parametrize("tech", O.MOMENT_TECHS)
+def test_filter_and_reconstruction_match_reference_shader_golden(tech):
+    g = util.golden(G)
+    W, H, S, order = int(g["W"]), int(g["H"]), int(g["S"]), int(g["order"])
+    fm = {k[3:]: g[k] for k in g if k.startswith("fm_")}
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    sc = util.scene("teapot")
+    mom = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
+    covered = mom[..., 0] != 0
+    assert 0.2 < covered.mean() < 1.0 and (mom[~covered] == np.array([0, 0, 0, 1], np.float32)).all()
+    logs = tech == "esm"
+    fx = O.filter_moments(mom, W, H, order, True, logs)
+    assert util.bits_equal(fx, g[f"chain/{tech}/filter_x"]), util.describe_diff(fx, g[f"chain/{tech}/filter_x"])
+    fy = O.filter_moments(fx, W, H, order, False, logs)
+    assert util.bits_equal(fy, g[f"chain/{tech}/filter_y"]), util.describe_diff(fy, g[f"chain/{tech}/filter_y"])
+    assert util.bits_equal(fy, O.filter_shadow_map(mom, W, H, order, tech))
+    pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    for variant, si in (("default", 0.25), ("alt", 0.5)):
+        p = O.default_params(tech, S, shadow_intensity=si)
+        vis = O.visibility_moments(p, cam, fm["light_mvp_b"], pos, nrm, fy)
+        ref = g[f"chain/{tech}/vis/{variant}"]
+        assert util.bits_equal(vis, ref), util.describe_diff(vis, ref)
+        fg = pos[..., 0] != 0
+        ok = ~np.isnan(ref)        # Hamburger 4MSM takes the square root of a negative discriminant on a few texels: NaN in the reference too
+        assert (~ok).sum() <= (20 if tech == "msm" else 0)
+        assert (ref[~fg] == 0).all() and (ref[fg & ok] >= np.float32(si)).all() and (ref[fg & ok] <= 1).all()
+        assert 0.05 < (ref[fg & ok] < 0.999).mean() < 0.9      # part of the frame is in shadow
+
+
+def test_vsm_derivative_term_uses_the_quad_partner_on_the_same_plane():
+    """A single tilted triangle: every covered texel's second moment is d^2 + (dx^2 + dy^2) / 4 with the fine quad differences
+    of the triangle's own depth plane, also where the partner texel is outside the triangle."""
+    xyz = np.array([[-0.9, -0.8, 0.2], [0.8, -0.6, 0.5], [-0.2, 0.9, 0.9]], np.float32)
+    idx = np.array([[0, 1, 2]], np.int32)
+    mvp = np.eye(4, dtype=np.float32).T.ravel()
+    S = 32
+    mom = O.raster_moments(xyz, idx, mvp, S, S, "vsm", factor=0.0, units=0.0)
+    depth = O.raster_depth(xyz, idx, mvp, S, S, factor=0.0, units=0.0)
+    cov = depth < 1
+    assert cov.sum() > 100 and ((mom[..., 0] != 0) == cov).all()
+    n, f = np.float32(1), np.float32(1000)
+    lin = (np.float32(2) * n) / (f + n - depth * (f - n))
+    assert util.bits_equal(mom[..., 0][cov], lin[cov])
+    extra = mom[..., 1] - mom[..., 0] * mom[..., 0]
+    # interior quads (all four texels covered): the term equals the differences of the stored first moments
+    for j in range(0, S, 2):
+        for i in range(0, S, 2):
+            if cov[j:j + 2, i:i + 2].all():
+                for dj in (0, 1):
+                    for di in (0, 1):
+                        dx = mom[j + dj, i + 1, 0] - mom[j + dj, i, 0]
+                        dy = mom[j + 1, i + di, 0] - mom[j, i + di, 0]
+                        want = np.float32(0.25) * (dx * dx + dy * dy)
+                        assert abs(float(extra[j + dj, i + di]) - float(want)) <= 1e-7
+    # edge texels still get a plausible (same-plane) derivative, not a jump to the clear value
+    assert float(extra[cov].max()) < 1e-4
