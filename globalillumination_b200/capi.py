@@ -11,9 +11,12 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf_noncons": 5, "rpcf_cons": 6,
-        "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11}
+        "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11,
+        "vsm": 12, "esm": 13, "evsm": 14, "msm": 15}
+MOMENT_TECHS = ("vsm", "esm", "evsm", "msm")
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
-       "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11}
+       "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11,
+       "moments": 12, "moments_x": 13, "moments_filtered": 14}
 PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
         "tile_gbuffer": 6, "tile_sv": 7}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
@@ -38,7 +41,7 @@ class SgiParams(C.Structure):
 
 EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
-    "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility",
+    "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility", "sgi_filter_shadow_map", "sgi_moment_quantization",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
@@ -76,6 +79,13 @@ def _fp(a):
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def moment_quantization():
+    """sgi_moment_quantization: (mQuantization, mQuantizationInverse, tQuantization), host arithmetic only."""
+    m, mi, t = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(4, np.float32)
+    load().sgi_moment_quantization(_fp(m), _fp(mi), _fp(t))
+    return m, mi, t
 
 
 def default_params(technique="hard", **kw):
@@ -168,6 +178,9 @@ class Context:
     def render_gbuffer(self):
         self._ck(self.lib.sgi_render_gbuffer(self.h))
 
+    def filter_shadow_map(self):
+        self._ck(self.lib.sgi_filter_shadow_map(self.h))
+
     def compute_visibility(self):
         self._ck(self.lib.sgi_compute_visibility(self.h))
 
@@ -183,6 +196,7 @@ class Context:
             "shadow_map": ((N, SH, SW), np.float32), "gbuf_pos": ((H, W, 4), np.float32), "gbuf_nrm": ((H, W, 4), np.float32),
             "cam_depth": ((H, W), np.float32), "visibility": ((H, W), np.float32), "sv_count": ((H, W), np.int32),
             "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "edt_nearest": ((H, W, 2), np.int16), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
+            "moments": ((SH, SW, 4), np.float32), "moments_x": ((H, W, 4), np.float32), "moments_filtered": ((H, W, 4), np.float32),
         }[which]
 
     def read(self, which, out=None):

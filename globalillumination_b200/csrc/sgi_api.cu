@@ -8,6 +8,7 @@
 #include <new>
 #include <utility>
 #include "sgi_internal.cuh"
+#include "sgi_moments.cuh"
 
 static void sync_all_streams(sgi_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
@@ -441,10 +442,14 @@ int sgi_set_multi_light_common(sgi_ctx* ctx, const float m[16]) {
 
 int sgi_set_params(sgi_ctx* ctx, const sgi_params* p) {
   if (!ctx || !p) return SGI_ERR_INVALID;
-  if (p->technique < 0 || p->technique > SGI_TECH_EDTSM_CONS) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
+  if (p->technique < 0 || p->technique > SGI_TECH_MSM) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
   if (p->kernel_order <= 0 || p->blocker_search_size <= 0 || p->kernel_size <= 0 || p->max_search < 0 || p->max_search > 4096 ||
       p->blocker_search_size > SGI_MAX_PCF_TAPS || p->kernel_size > SGI_MAX_PCF_TAPS) {
     ctx->err = "sgi_set_params: kernel sizes must be in 1..64";
+    return SGI_ERR_INVALID;
+  }
+  if (sgi_is_moment_tech(p->technique) && (p->kernel_order < 2 || p->kernel_order > (p->technique == SGI_TECH_ESM ? 25 : SGI_MOM_MAX_ORDER))) {
+    ctx->err = "sgi_set_params: blur order must be in 2..33 (2..25 for ESM: `uniform float kernel[25]`, LogGaussianFilter.frag:8)";
     return SGI_ERR_INVALID;
   }
   int n1 = sgi_host_pcf_offsets(p->kernel_order, p->penumbra_size, 0, ctx->pcf_off, SGI_MAX_PCF_TAPS);
@@ -463,6 +468,33 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
   {
     int rc0 = prepare_target_write(ctx, 0, ctx->stream, true);      // the depth passes always produce whole maps
     if (rc0) return rc0;
+  }
+  if (sgi_is_moment_tech(ctx->params.technique)) {
+    // VSM / ESM / EVSM / MSM: the light-view pass writes the moment target instead of a depth map (displaySceneFromLightPOV
+    // binds Moments / Exponential / ExponentialMoments.frag, main.cpp:227-243).  One light; the shadow pass of the previous
+    // frame may still read the filtered map on the visibility stream, but not this target: only the blur reads it.
+    if (ctx->N != 1) { ctx->err = "sgi_render_shadow_map: moment shadow maps take one light"; return SGI_ERR_INVALID; }
+    int rc = ensure_buf(ctx, SGI_BUF_MOMENTS, (size_t)ctx->SW * ctx->SH * 16);
+    if (rc) return rc;
+    sgi_wait_reads_of(ctx, SGI_BUF_MOMENTS, ctx->stream);
+    int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP, ctx->stream);
+    SgiRasterJob job;
+    memset(&job, 0, sizeof(job));
+    job.mode = SGI_MODE_MOMENTS;
+    job.xyz = ctx->d_xyz; job.nrm = ctx->d_nrm; job.idx = ctx->d_idx; job.T = ctx->T;
+    memcpy(job.mvp, ctx->h_light_mvp, 64);
+    job.W = ctx->SW; job.H = ctx->SH;
+    job.use_offset = 1; job.factor = ctx->params.polygon_offset_factor; job.units = ctx->params.polygon_offset_units;
+    job.mom4 = (float4*)ctx->buf[SGI_BUF_MOMENTS]; job.mom_tech = ctx->params.technique;
+    job.z_near = ctx->params.z_near; job.z_far = ctx->params.z_far;
+    float minv[16];
+    sgi_moments_quantization(job.mq, minv, job.mqt);
+    rc = sgi_raster_run(ctx, job, 0, ctx->stream);
+    if (rc) return rc;
+    sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot, ctx->stream);
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
+    ctx->moments_tech = ctx->params.technique; ctx->filtered_tech = -1;
+    return SGI_OK;
   }
   sgi_wait_reads_of(ctx, SGI_BUF_SHADOW_MAP, ctx->stream);
   int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_MAP, ctx->stream);
@@ -550,8 +582,36 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   return SGI_OK;
 }
 
+int sgi_filter_shadow_map(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  if (!sgi_is_moment_tech(ctx->params.technique) || ctx->moments_tech != ctx->params.technique) {
+    ctx->err = "sgi_filter_shadow_map: render the shadow map with a moment technique (VSM / ESM / EVSM / MSM) first";
+    return SGI_ERR_INVALID;
+  }
+  if (!ctx->has_camera) { ctx->err = "sgi_filter_shadow_map: set the camera first (the filtered maps are window-sized, main.cpp:887-888)"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int rc;
+  const size_t bytes = (size_t)ctx->W * ctx->H * 16;
+  if ((rc = ensure_buf(ctx, SGI_BUF_MOMENTS_X, bytes))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_MOMENTS_FILTERED, bytes))) return rc;
+  // the previous frame's shadow pass (visibility stream) may still be sampling the filtered map
+  if ((rc = sgi_join_vis(ctx))) return rc;
+  sgi_wait_reads_of(ctx, SGI_BUF_MOMENTS_X, ctx->stream); sgi_wait_reads_of(ctx, SGI_BUF_MOMENTS_FILTERED, ctx->stream);
+  if ((rc = sgi_moments_filter_run(ctx, ctx->stream))) return rc;
+  ctx->filtered_tech = ctx->params.technique; ctx->filtered_w = ctx->W; ctx->filtered_h = ctx->H;
+  return SGI_OK;
+}
+
+void sgi_moment_quantization(float m[16], float m_inverse[16], float t[4]) { sgi_moments_quantization(m, m_inverse, t); }
+
 int sgi_compute_visibility(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
+  if (sgi_is_moment_tech(ctx->params.technique)) {
+    if (!ctx->gbuffer_valid || ctx->filtered_tech != ctx->params.technique || ctx->filtered_w != ctx->W || ctx->filtered_h != ctx->H) {
+      ctx->err = "sgi_compute_visibility: render and filter the moment shadow map and render the G-buffer first";
+      return SGI_ERR_INVALID;
+    }
+  } else
   if (!ctx->gbuffer_valid || !ctx->shadow_map_valid) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
   int rc;

@@ -23,6 +23,10 @@
 #include <cstdlib>
 #include <cub/cub.cuh>
 #include "sgi_internal.cuh"
+#include "sgi_moments.cuh"
+
+// modes whose tile payload is the 64-bit (depth | primitive) key: the attribute passes that need to know the winning triangle
+#define SGI_KEYED(M) ((M) == SGI_MODE_GBUFFER || (M) == SGI_MODE_GBUFFER_RGB || (M) == SGI_MODE_MOMENTS)
 
 namespace {
 
@@ -483,6 +487,7 @@ struct TileArgs {
   float* depth; float4* pos4; float4* nrm4;
   const float* rgb; float4* albedo4;
   const float* scene_depth; int depth_func; int32_t* count; uint8_t* stencil;
+  float4* mom4; int mom_tech, z_near, z_far; float mq[16], mqt[4];      // MOMENTS
 };
 
 #define ONE_BITS 0x3F800000u
@@ -592,7 +597,7 @@ struct TileSink {                  // where fragments go: the tile payload in sh
     if (MODE == SGI_MODE_DEPTH) {
       const unsigned int zb = __float_as_uint(z);
       if (zb < zt[p]) atomicMin(&zt[p], zb);
-    } else if ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) {
+    } else if SGI_KEYED(MODE) {
       if (z < 1.0f) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned int)(meta >> 1);
         if (key < kt[p]) atomicMin(&kt[p], key);
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   unsigned long long* kt = reinterpret_cast<unsigned long long*>(smem_raw);
   int* ct = reinterpret_cast<int*>(smem_raw);
   constexpr int NCELL = SGI_TILE * SGI_PITCH;
-  constexpr size_t PAYLOAD = ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB)) ? (size_t)NCELL * 8 : (size_t)NCELL * 4;
+  constexpr size_t PAYLOAD = SGI_KEYED(MODE) ? (size_t)NCELL * 8 : (size_t)NCELL * 4;
   constexpr size_t SDBYTES = (MODE == SGI_MODE_SVCOUNT) ? (size_t)NCELL * 4 : 0;
   float* sd = reinterpret_cast<float*>(smem_raw + PAYLOAD);
   TriQueue<NT>& tq = *reinterpret_cast<TriQueue<NT>*>(smem_raw + PAYLOAD + SDBYTES);
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         const int lx = qx0 + ((q & ((1 << rq_log2) - 1)) << 2), ly = qy0 + (q >> rq_log2);
         *reinterpret_cast<uint4*>(&zt[ly * SGI_PITCH + lx]) = make_uint4(ONE_BITS, ONE_BITS, ONE_BITS, ONE_BITS);
       }
-    } else if (MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB) {   // 2 cells per store
+    } else if SGI_KEYED(MODE) {   // 2 cells per store
       const int rq_log2 = rs_log2 - 1;
       const unsigned long long clr = ((unsigned long long)ONE_BITS << 32) | 0xFFFFFFFFull;
       for (int q = tid; q < (rs * rs) >> 1; q += NT) {
@@ -909,6 +914,30 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     } else {
       const unsigned long long key = empty ? 0xFFFFFFFFull : kt[p];
       const unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
+      if (MODE == SGI_MODE_MOMENTS) {
+        // Moments.frag / Exponential.frag / ExponentialMoments.frag on the winning fragment: a function of the un-offset depth
+        // plane at this texel and at its two quad partners (dFdx / dFdy), fused into the flush - the moment target crosses
+        // HBM once and no depth map is written at all
+        if (lo32 == 0xFFFFFFFFu) { a.mom4[o] = make_float4(0.f, 0.f, 0.f, 1.f); continue; }      // glClearColor(0,0,0,1), main.cpp:356
+        const int prim = (int)lo32, t = prim >> 3, sub = prim & 7;
+        const int slot = (sub == 0) ? t : __ldg(&a.ovf_base[t]) + sub - 1;
+        SgiRec r;
+        {
+          const uint4* rq = reinterpret_cast<const uint4*>(&a.rec[slot]);
+          uint4* rd = reinterpret_cast<uint4*>(&r);
+          rd[0] = __ldg(rq); rd[1] = __ldg(rq + 1); rd[2] = __ldg(rq + 2); rd[3] = __ldg(rq + 3);
+        }
+        const int dx1 = r.X0 - r.X2, dy1 = r.Y0 - r.Y2, dx2 = r.X1 - r.X0, dy2 = r.Y1 - r.Y0;
+        auto plane = [&](int px, int py) -> float {
+          const int PX = px * SGI_SUBPIX + SGI_SUBPIX / 2, PY = py * SGI_SUBPIX + SGI_SUBPIX / 2;
+          const long long E1 = (long long)dx1 * (long long)(PY - r.Y2) - (long long)dy1 * (long long)(PX - r.X2);
+          const long long E2 = (long long)dx2 * (long long)(PY - r.Y0) - (long long)dy2 * (long long)(PX - r.X0);
+          const float b1 = (float)E1 * r.ia, b2 = (float)E2 * r.ia;
+          return (r.z0 + b1 * r.dz1) + b2 * r.dz2;
+        };
+        a.mom4[o] = mom_texel(a.mom_tech, plane(x, y), plane(x ^ 1, y), plane(x, y ^ 1), x & 1, y & 1, a.z_near, a.z_far, a.mq, a.mqt);
+        continue;
+      }
       if (lo32 == 0xFFFFFFFFu) {
         a.depth[o] = 1.0f;
         a.pos4[o] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -980,7 +1009,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
 
 template <int MODE, int NT>
 constexpr size_t tile_smem_bytes() {
-  return (size_t)SGI_TILE * SGI_PITCH * ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB) ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? (size_t)SGI_TILE * SGI_PITCH * 4 : 0) +
+  return (size_t)SGI_TILE * SGI_PITCH * (SGI_KEYED(MODE) ? 8 : 4) + (MODE == SGI_MODE_SVCOUNT ? (size_t)SGI_TILE * SGI_PITCH * 4 : 0) +
          sizeof(TriQueue<NT>);
 }
 
@@ -1072,7 +1101,7 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  const int pass = MODE == SGI_MODE_DEPTH ? SGI_PASS_TILE_DEPTH : ((MODE == SGI_MODE_GBUFFER || MODE == SGI_MODE_GBUFFER_RGB) ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
+  const int pass = (MODE == SGI_MODE_DEPTH || MODE == SGI_MODE_MOMENTS) ? SGI_PASS_TILE_DEPTH : (SGI_KEYED(MODE) ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
   int tslot = sgi_timing_begin(ctx, pass, stream);
   k_tile<MODE, NT><<<grid, NT, smem, stream>>>(ta);
   sgi_timing_end(ctx, pass, tslot, stream);
@@ -1160,10 +1189,11 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   k_scan_tiles<<<1, 1024, 0, st>>>(sc.d_tile_cnt, sc.d_tile_off, n_tiles + 1, sc.d_counters, sc.h_flags, sc.d_sticky, sc.d_tile_order, tiles_x,
                                    tx0, ty0, tx1 - tx0 + 1, ty1 - ty0 + 1, ctx->tile_order, max_items, ctx->tile_split);
   ctx->launches++;
-  if (!sc.sized[job.mode]) {
+  const int size_class = job.mode == SGI_MODE_MOMENTS ? SGI_MODE_DEPTH : job.mode;   // the moment pass bins exactly like the depth pass
+  if (!sc.sized[size_class]) {
     // first pass of this kind on this context: size the tile lists from the real count (one sync, once)
     SGI_CUDA(ctx, cudaStreamSynchronize(st));
-    sc.sized[job.mode] = true;
+    sc.sized[size_class] = true;
     if ((long long)sc.h_flags[1] > sc.pair_cap) {
       long long want = (long long)sc.h_flags[1] * 2 + (1 << 16);
       if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
@@ -1185,9 +1215,13 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.depth = job.depth; ta.pos4 = job.pos4; ta.nrm4 = job.nrm4;
   ta.rgb = job.rgb; ta.albedo4 = job.albedo4;
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
+  ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far;
+  for (int k = 0; k < 16; k++) ta.mq[k] = job.mq[k];
+  for (int k = 0; k < 4; k++) ta.mqt[k] = job.mqt[k];
   dim3 grid(max_items);
   if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_GBUFFER) rc = (job.rgb && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, n_rect_tiles, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, n_rect_tiles, st);
+  else if (job.mode == SGI_MODE_MOMENTS) rc = launch_tile<SGI_MODE_MOMENTS>(ctx, ta, grid, n_rect_tiles, st);
   else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
   return rc;
 }

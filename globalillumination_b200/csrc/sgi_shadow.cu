@@ -484,6 +484,10 @@ __device__ float cs_rpcf(Rb& r, const VisArgs& a, float4 c) {
 
 #include "sgi_rbssm.cuh"
 #include "sgi_edt.cuh"
+}  // namespace
+#define SGI_MOMENTS_KERNELS
+#include "sgi_moments.cuh"
+namespace {
 
 // ================================ kernels ========================================================
 // VA / VB: compile-time tap counts of the specialised variants (PCF: VA = taps per axis; PCSS: VA = blocker taps,
@@ -680,7 +684,67 @@ int sgi_host_pcf_offsets(int kernel_order, int penumbra_size, int inclusive, flo
   return n;
 }
 
+void sgi_moments_quantization(float m[16], float minv[16], float t[4]) {
+  MomQuant Q;
+  mom_quantization(Q);
+  for (int k = 0; k < 16; k++) { m[k] = Q.m[k]; minv[k] = Q.minv[k]; }
+  for (int k = 0; k < 4; k++) t[k] = Q.t[k];
+}
+
+// filterShadowMap(), ShadowMapping/src/main.cpp:374-398: X pass (moment target -> FILTER_X) then Y pass (FILTER_X -> FILTER_Y),
+// both into window-sized targets with the window's texel step
+int sgi_moments_filter_run(sgi_ctx* ctx, cudaStream_t st) {
+  MomFilterArgs f;
+  f.W = ctx->W; f.H = ctx->H;
+  f.order = ctx->params.kernel_order;
+  for (int k = 0; k < SGI_MOM_MAX_ORDER; k++) f.kernel[k] = 0.0f;
+  mom_gaussian_kernel(f.order, f.kernel);
+  { volatile float ss = 1.0f / (float)ctx->W, tt = 1.0f / (float)ctx->H; f.step_s = ss; f.step_t = tt; }      // GaussianFilter.frag:27-28
+  const bool logs = ctx->params.technique == SGI_TECH_ESM;
+  dim3 block(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+  f.src = (const float4*)ctx->buf[SGI_BUF_MOMENTS]; f.sw = ctx->SW; f.sh = ctx->SH; f.dst = (float4*)ctx->buf[SGI_BUF_MOMENTS_X];
+  if (logs) k_mom_filter<true, true><<<grid, block, 0, st>>>(f); else k_mom_filter<true, false><<<grid, block, 0, st>>>(f);
+  f.src = (const float4*)ctx->buf[SGI_BUF_MOMENTS_X]; f.sw = ctx->W; f.sh = ctx->H; f.dst = (float4*)ctx->buf[SGI_BUF_MOMENTS_FILTERED];
+  if (logs) k_mom_filter<false, true><<<grid, block, 0, st>>>(f); else k_mom_filter<false, false><<<grid, block, 0, st>>>(f);
+  ctx->launches += 2;
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
+}
+
+static int moments_visibility_run(sgi_ctx* ctx, cudaStream_t st) {
+  MomVisArgs a;
+  for (int k = 0; k < 16; k++) { a.mv[k] = ctx->cam_mv[k]; a.lmvp[k] = ctx->h_light_mvp_b[k]; }
+  for (int k = 0; k < 9; k++) a.nm[k] = ctx->cam_nm[k];
+  for (int k = 0; k < 3; k++) a.lpos[k] = ctx->light_pos[k];
+  a.shadow_intensity = ctx->params.shadow_intensity; a.z_near = ctx->params.z_near; a.z_far = ctx->params.z_far;
+  a.pos4 = (const float4*)ctx->buf[SGI_BUF_GBUF_POS]; a.nrm4 = (const float4*)ctx->buf[SGI_BUF_GBUF_NRM];
+  a.vis = (float*)ctx->buf[SGI_BUF_VISIBILITY];
+  a.W = ctx->W; a.H = ctx->H;
+  a.rx0 = ctx->params.rect_x0; a.ry0 = ctx->params.rect_y0; a.rx1 = ctx->params.rect_x1; a.ry1 = ctx->params.rect_y1;
+  if (a.rx1 <= a.rx0 || a.ry1 <= a.ry0) { a.rx0 = 0; a.ry0 = 0; a.rx1 = ctx->W; a.ry1 = ctx->H; }
+  a.rx0 = a.rx0 < 0 ? 0 : a.rx0; a.ry0 = a.ry0 < 0 ? 0 : a.ry0;
+  a.rx1 = a.rx1 > ctx->W ? ctx->W : a.rx1; a.ry1 = a.ry1 > ctx->H ? ctx->H : a.ry1;
+  a.fmap = (const float4*)ctx->buf[SGI_BUF_MOMENTS_FILTERED]; a.mw = ctx->filtered_w; a.mh = ctx->filtered_h;
+  float m[16];
+  sgi_moments_quantization(m, a.minv, a.qt);
+  const int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
+  if (rw <= 0 || rh <= 0) return SGI_OK;
+  dim3 block(32, 8), grid((rw + 31) / 32, (rh + 7) / 8);
+  int tslot = sgi_timing_begin(ctx, SGI_PASS_VIS_KERNEL, st);
+  switch (ctx->params.technique) {
+    case SGI_TECH_VSM: k_mom_visibility<SGI_TECH_VSM><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_ESM: k_mom_visibility<SGI_TECH_ESM><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_EVSM: k_mom_visibility<SGI_TECH_EVSM><<<grid, block, 0, st>>>(a); break;
+    default: k_mom_visibility<SGI_TECH_MSM><<<grid, block, 0, st>>>(a); break;
+  }
+  ctx->launches++;
+  sgi_timing_end(ctx, SGI_PASS_VIS_KERNEL, tslot, st);
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
+}
+
 int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
+  if (sgi_is_moment_tech(ctx->params.technique)) return moments_visibility_run(ctx, stream);
   VisArgs a;
   a.p = ctx->params;
   for (int k = 0; k < 16; k++) a.mv[k] = ctx->cam_mv[k];

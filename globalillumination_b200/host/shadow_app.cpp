@@ -146,7 +146,11 @@ int ShadowApp::technique() const {
   }
   if (p.RSMSS || p.RPCFPlusRSMSS) return SGI_TECH_RSMSS;
   if (p.naive) return SGI_TECH_HARD;                                    // Shadow.frag:253
-  if (p.VSM || p.ESM || p.EVSM || p.MSM || p.tricubicPCF) return -1;    // pre-filtered maps: out of scope
+  if (p.VSM) return SGI_TECH_VSM;                                       // Shadow.frag:257-264, in the shader's order
+  if (p.ESM) return SGI_TECH_ESM;
+  if (p.EVSM) return SGI_TECH_EVSM;
+  if (p.MSM) return SGI_TECH_MSM;
+  if (p.tricubicPCF) return -1;                                         // bicubic PCF taps: not built
   return SGI_TECH_PCF;
 }
 
@@ -196,7 +200,7 @@ int ShadowApp::renderGBuffer() {
 int ShadowApp::computeHardShadows() {
   if (!ctx) return SGI_ERR_NO_DEVICE;
   int tech = technique();
-  if (tech < 0) { err = "computeHardShadows: VSM/ESM/EVSM/MSM/tricubic PCF are outside the shadow hot path (SURVEY.md C17)"; return SGI_ERR_INVALID; }
+  if (tech < 0) { err = "computeHardShadows: tricubic PCF is outside the shadow hot path (SURVEY.md C11)"; return SGI_ERR_INVALID; }
   int rc = pushParams(tech);
   if (rc) return rc;
   rc = sgi_compute_visibility(ctx);
@@ -210,9 +214,20 @@ int ShadowApp::shadeScene() {
   return rc ? fail(rc, "sgi_shade_phong") : 0;
 }
 
+// filterShadowMap(), main.cpp:374-398: the blurred maps are window-sized, so the window goes down with the camera uniforms first
+int ShadowApp::filterShadowMap() {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  FrameMatrices f = frameMatrices();
+  int rc = sgi_set_camera(ctx, f.cameraMVP.m, f.cameraMV.m, f.normalMatrix.m, windowWidth, windowHeight);
+  if (rc) return fail(rc, "sgi_set_camera");
+  rc = sgi_filter_shadow_map(ctx);
+  return rc ? fail(rc, "sgi_filter_shadow_map") : 0;
+}
+
 int ShadowApp::display() {                                  // main.cpp:459-472 without shadeScene/swap
   int rc;
   if ((rc = renderShadowMap())) return rc;
+  if (shadowParams.VSM || shadowParams.ESM || shadowParams.EVSM || shadowParams.MSM) { if ((rc = filterShadowMap())) return rc; }   // :463
   if ((rc = renderGBuffer())) return rc;
   return computeHardShadows();
 }

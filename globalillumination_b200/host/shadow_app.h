@@ -6,6 +6,7 @@
 //   updateLight             ShadowMapping/src/main.cpp:209-219
 //   renderShadowMap         :350-361  (displaySceneFromLightPOV :221-274)
 //   renderGBuffer           :363-372  (displaySceneFromCameraPOV :276-300)
+//   filterShadowMap         :374-398  (separable blur of the moment map; VSM / ESM / EVSM / MSM)
 //   computeHardShadows      :400-414  (displaySceneFromGBuffer :302-348, configureShadow/configureRevectorization)
 //   display                 :459-472
 //   renderSoftShadows       SoftShadowMapping/src/main.cpp:925-1022 (PCSS branch)
@@ -69,6 +70,7 @@ class ShadowApp {
   // per-frame passes
   int renderShadowMap();
   int renderGBuffer();
+  int filterShadowMap();          // ShadowMapping/src/main.cpp:374-398 (VSM / ESM / EVSM / MSM)
   int computeHardShadows();
   int renderSoftShadows();
   int renderMonteCarlo();

@@ -58,7 +58,14 @@ typedef enum sgi_technique {
   SGI_TECH_MULTI_HARD = 8,    /* AccurateSoftShadow.frag, monteCarlo        (:52-133), N lights              */
   SGI_TECH_RBSSM = 9,         /* SoftShadow/RBSSM.frag: revectorization-based soft shadows (:1202-1376)     */
   SGI_TECH_EDTSM_NONCONS = 10,/* EDT shadow mapping (main.cpp:416-447, EDT/pba2D*.cu|h, MeanFilter.frag) over   */
-  SGI_TECH_EDTSM_CONS = 11    /*   the non-conservative / conservative SMSR hard shadows; whole screen only      */
+  SGI_TECH_EDTSM_CONS = 11,   /*   the non-conservative / conservative SMSR hard shadows; whole screen only      */
+  /* pre-filtered ("moment") shadow maps of the ShadowMapping program: sgi_render_shadow_map renders the moment target
+   * (Shaders/ShadowMap/{Moments,Exponential,ExponentialMoments}.frag, main.cpp:227-243) instead of a depth map,
+   * sgi_filter_shadow_map blurs it (main.cpp:374-398), sgi_compute_visibility reconstructs (Shadow.frag:118-220,257-264) */
+  SGI_TECH_VSM = 12,          /* variance shadow mapping, chebyshevUpperBound       (Shadow.frag:118-141)            */
+  SGI_TECH_ESM = 13,          /* exponential shadow mapping, c = 80, log-space blur (Shadow.frag:144-157)            */
+  SGI_TECH_EVSM = 14,         /* exponential variance shadow mapping, c = 60        (Shadow.frag:160-175)            */
+  SGI_TECH_MSM = 15           /* Hamburger 4-moment shadow mapping, quantised       (Shadow.frag:168-220)            */
 } sgi_technique;
 
 typedef enum sgi_depth_func { SGI_DEPTH_LESS = 0, SGI_DEPTH_LEQUAL = 1 } sgi_depth_func;
@@ -73,7 +80,8 @@ typedef struct sgi_params {
   int32_t shadow_map_width;       /* informational; the authoritative size is sgi_set_lights */
   int32_t shadow_map_height;
   float   shadow_intensity;       /* 0.25                                                   */
-  int32_t kernel_order;           /* 7   PCF / RPCF taps per axis (float loop)   */
+  int32_t kernel_order;           /* 7   PCF / RPCF taps per axis (float loop); for VSM / ESM / EVSM / MSM the order
+                                     of the separable blur (shadowParams.kernelOrder = gaussianFilter->getOrder(), main.cpp:321) */
   int32_t penumbra_size;          /* 1                                                      */
   int32_t blocker_search_size;    /* 7   PCSS                                               */
   int32_t kernel_size;            /* 15  PCSS                                               */
@@ -105,7 +113,10 @@ typedef enum sgi_buffer {
   SGI_BUF_GBUF_ALBEDO = 9,  /* float4  [H][W]       (vertex colour rgb, 1) when colours are set; bg (0,0,0,1)  */
   SGI_BUF_SHADED = 10,      /* float4  [H][W]       deferred Phong image; background = the clear colour        */
   SGI_BUF_EDT_NEAREST = 11, /* int16x2 [H][W]       EDT shadow mapping: nearest shadow-boundary pixel (x, y), -32768 = none */
-  SGI_BUF_COUNT_ = 12
+  SGI_BUF_MOMENTS = 12,     /* float4  [Sh][Sw]     VSM/ESM/EVSM/MSM: moment target of the light-view pass, cleared to (0,0,0,1) */
+  SGI_BUF_MOMENTS_X = 13,   /* float4  [H][W]       filterShadowMap: after the horizontal pass (FILTER_X_MAP_COLOR, window-sized) */
+  SGI_BUF_MOMENTS_FILTERED = 14, /* float4 [H][W]   filterShadowMap: after the vertical pass (FILTER_Y_MAP_COLOR), what Shadow.frag samples */
+  SGI_BUF_COUNT_ = 15
 } sgi_buffer;
 
 /* passes that can be timed with sgi_pass_time_ms */
@@ -161,6 +172,15 @@ void sgi_default_params(sgi_params* params);
 /* passes */
 int sgi_render_shadow_map(sgi_ctx* ctx);      /* renderShadowMap(), ShadowMapping/src/main.cpp:350-361 (all N lights) */
 int sgi_render_gbuffer(sgi_ctx* ctx);         /* renderGBuffer(),   ShadowMapping/src/main.cpp:363-372               */
+/* filterShadowMap(), ShadowMapping/src/main.cpp:374-398 (display() calls it between renderShadowMap and renderGBuffer when
+ * VSM / ESM / EVSM / MSM is on, :471): the separable binomial blur of order params.kernel_order (Filter::buildGaussianKernel,
+ * src/Filter.cpp:17-46) - GaussianFilter.frag, or LogGaussianFilter.frag for ESM - from the moment target into the two
+ * window-sized targets.  Needs sgi_render_shadow_map with the same technique and sgi_set_camera (window size) first. */
+int sgi_filter_shadow_map(sgi_ctx* ctx);
+/* MyGLGeometryViewer::configureMoments (ShadowMapping/src/Viewers/MyGLGeometryViewer.cpp:188-213): the MSM quantisation
+ * uniforms mQuantization, mQuantizationInverse (column-major) and tQuantization, computed in fp32 in GLM's operation order.
+ * Pure host arithmetic (no device needed); the passes use the same values internally. */
+void sgi_moment_quantization(float m[16], float m_inverse[16], float t[4]);
 int sgi_compute_visibility(sgi_ctx* ctx);     /* computeHardShadows() :400-414 / renderSoftShadows()
                                                  SoftShadowMapping/src/main.cpp:925-1022 / renderMonteCarlo() :756-811 */
 /* ShadowVolume::update (ShadowVolumes/src/ShadowVolume.cpp:116-195) + the stencil pass of display()

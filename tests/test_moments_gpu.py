@@ -1,0 +1,140 @@
+"""Moment shadow maps (VSM / ESM / EVSM / MSM) through the C ABI against the CPU oracle.
+
+Everything without exp / log is required bit-identical (moment target, Gaussian blur, VSM and MSM reconstruction); the
+exponential paths (ESM's log-space blur, ESM / EVSM reconstruction) go through expf / logf, whose CUDA and glibc versions
+differ by a few ulp, so they carry an explicit tolerance far inside north_star's 1e-3 for soft visibility."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tests import util
+
+SOFT_TOL = 1e-3        # north_star: soft visibility within 1e-3 absolute
+EXP_TOL = 2e-5         # what expf / logf implementations may differ by after the c = 80 exponent (measured: < 1e-5)
+
+
+def test_host_quantization_equals_oracle_and_reference_glm():
+    """sgi_moment_quantization is host arithmetic (no device): same bits as the oracle and as the reference's GLM golden."""
+    from globalillumination_b200 import capi
+    g = util.golden("golden_moments.npz")
+    m, mi, t = capi.moment_quantization()
+    assert util.bits_equal(m, g["quant/m"]) and util.bits_equal(mi, g["quant/minv"]) and util.bits_equal(t, g["quant/t"])
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from globalillumination_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _setup(ctx, sc, W, H, S, pg):
+    fm = util.frame(sc, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    return fm
+
+
+def _close(a, b, tol):
+    both_nan = np.isnan(a) & np.isnan(b)
+    return bool(((np.abs(a - b) <= tol) | both_nan).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tech", O.MOMENT_TECHS)
+@pytest.mark.parametrize("name,W,H,S,kw", [("teapot", 320, 180, 256, {}), ("teapot", 1280, 720, 1024, {}),
+                                           ("raptor", 333, 217, 300, dict(kernel_order=5, shadow_intensity=0.5)),
+                                           ("dragon", 640, 360, 512, dict(kernel_order=11))])
+def test_moment_chain_matches_oracle(ctx, tech, name, W, H, S, kw):
+    sc = util.scene(name)
+    po, pg = util.params_pair(tech, S, **kw)
+    fm = _setup(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    mom, fx, fy, vis = ctx.read("moments"), ctx.read("moments_x"), ctx.read("moments_filtered"), ctx.read("visibility")
+    pos, nrm = ctx.read("gbuf_pos"), ctx.read("gbuf_nrm")
+    # 1. light-view moment target: bit-exact (no transcendental functions on this stage)
+    mom_o = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
+    assert util.bits_equal(mom, mom_o), "moment target: " + util.describe_diff(mom, mom_o)
+    assert (mom_o[..., 0] != 0).mean() > 0.05
+    # 2. filterShadowMap: Gaussian bit-exact; ESM's log-space blur within EXP_TOL
+    order = po.kernel_order
+    fx_o = O.filter_moments(mom, W, H, order, True, tech == "esm")
+    fy_o = O.filter_moments(fx, W, H, order, False, tech == "esm")          # from the GPU's own X pass: stage-wise comparison
+    if tech == "esm":
+        assert _close(fx, fx_o, EXP_TOL) and _close(fy, fy_o, EXP_TOL), (np.nanmax(np.abs(fx - fx_o)), np.nanmax(np.abs(fy - fy_o)))
+    else:
+        assert util.bits_equal(fx, fx_o), "X pass: " + util.describe_diff(fx, fx_o)
+        assert util.bits_equal(fy, fy_o), "Y pass: " + util.describe_diff(fy, fy_o)
+    # 3. Shadow.frag reconstruction on the GPU's own filtered map
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o = O.visibility_moments(po, cam, fm["light_mvp_b"], pos, nrm, fy)
+    assert np.array_equal(np.isnan(vis), np.isnan(vis_o))
+    ok = ~np.isnan(vis_o)
+    assert (~ok).mean() < 0.01                                               # MSM: sqrt of a negative discriminant, as in the shader
+    assert np.abs(vis[ok] - vis_o[ok]).max() <= SOFT_TOL
+    if tech in ("vsm", "msm"):
+        assert util.bits_equal(vis[ok], vis_o[ok]), util.describe_diff(vis[ok], vis_o[ok])
+    else:
+        assert np.abs(vis[ok] - vis_o[ok]).max() <= EXP_TOL, float(np.abs(vis[ok] - vis_o[ok]).max())
+    fg = pos[..., 0] != 0
+    assert (vis_o[~fg] == 0).all() and 0.02 < (vis_o[fg & ok] < 0.999).mean() < 0.98
+    # 4. end to end against the all-oracle chain: inside north_star's soft-shadow tolerance
+    vis_full = O.visibility_moments(po, cam, fm["light_mvp_b"], pos, nrm, O.filter_shadow_map(mom_o, W, H, order, tech))
+    okf = ok & ~np.isnan(vis_full)
+    assert np.abs(vis[okf] - vis_full[okf]).max() <= SOFT_TOL
+
+
+@pytest.mark.gpu
+def test_moment_passes_need_their_inputs_and_switch_back_to_depth_maps(ctx):
+    from globalillumination_b200 import capi
+    sc = util.scene("teapot")
+    W, H, S = 160, 90, 128
+    po, pg = util.params_pair("vsm", S)
+    fm = _setup(ctx, sc, W, H, S, pg)
+    ctx.render_gbuffer()
+    with pytest.raises(capi.SgiError):
+        ctx.compute_visibility()                    # no moment map yet
+    ctx.render_shadow_map()
+    with pytest.raises(capi.SgiError):
+        ctx.compute_visibility()                    # not filtered yet
+    ctx.filter_shadow_map(); ctx.compute_visibility()
+    v_vsm = ctx.read("visibility")
+    # another moment technique needs its own map
+    po2, pg2 = util.params_pair("esm", S)
+    ctx.set_params(pg2)
+    with pytest.raises(capi.SgiError):
+        ctx.filter_shadow_map()
+    with pytest.raises(capi.SgiError):
+        ctx.compute_visibility()
+    # blur order outside the shader's kernel[] array is refused
+    with pytest.raises(capi.SgiError):
+        ctx.set_params(capi.default_params("vsm", kernel_order=35))
+    # back to a depth-map technique on the same context: unchanged results
+    po3, pg3 = util.params_pair("pcf", S)
+    ctx.set_params(pg3)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    v_o = O.visibility(po3, cam, fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
+    assert util.bits_equal(ctx.read("visibility"), v_o)
+    assert not np.array_equal(v_vsm, v_o)
+
+
+@pytest.mark.gpu
+def test_moment_visibility_respects_the_screen_rectangle(ctx):
+    """Multi-GPU screen tiles: a rank evaluates only its rectangle; the union of two strips equals the whole frame."""
+    sc = util.scene("teapot")
+    W, H, S = 320, 180, 256
+    po, pg = util.params_pair("evsm", S)
+    _setup(ctx, sc, W, H, S, pg)
+    ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    whole = ctx.read("visibility").copy()
+    parts = np.zeros_like(whole)
+    for y0, y1 in ((0, 77), (77, H)):
+        po_r, pg_r = util.params_pair("evsm", S, rect_x0=0, rect_y0=y0, rect_x1=W, rect_y1=y1)
+        ctx.set_params(pg_r)
+        ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+        parts[y0:y1] = ctx.read("visibility")[y0:y1]
+    assert util.bits_equal(parts, whole)
