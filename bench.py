@@ -99,6 +99,12 @@ def algorithmic_bytes(w, V, T, L):
     gb = (48 if any(l.startswith("c ") for l in w["lines"]) else 32) * px + 12 * (V + T)
     ab = {"shadow_map": L * (4 * S * S + 12 * (V + T)), "gbuffer": gb, "visibility": 36 * px + L * 4 * S * S}
     ab["shadow_volume"] = 8 * px + 36 * T + 144 * T          # depth read + count write + geometry read + prisms written and read back
+    if w["technique"] in ("vsm", "esm", "evsm", "msm"):
+        # moment shadow maps: float4 moment target written once; blur X reads it and writes a window-sized float4 target, blur Y
+        # reads that and writes another; the shadow pass reads G-buffer + filtered map and writes the visibility
+        ab["shadow_map"] = 16 * S * S + 12 * (V + T)
+        ab["moment_filter"] = 16 * S * S + 48 * px
+        ab["visibility"] = 36 * px + 16 * px
     return ab
 
 
@@ -117,7 +123,8 @@ def run_reference(args, w, cfg_path):
     sc = scenes.golden_scene(w["golden"]) if w.get("golden") else hostapi.load_scene(cfg_path)
     W, H, S = w["W"], w["H"], w["S"]
     n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
-    tech = {"pcss": "pcss", "montecarlo": "multi_hard", "naive": "hard", "smsr": "rbsm_noncons"}[w["technique"]]
+    tech = {"pcss": "pcss", "montecarlo": "multi_hard", "naive": "hard", "smsr": "rbsm_noncons", "vsm": "vsm", "esm": "esm", "evsm": "evsm",
+            "msm": "msm"}[w["technique"]]
     p = O.default_params(tech, S, depth_threshold=float(sc["depth_threshold"]),
                          **{k2: w["params"][k1] for k1, k2 in (("blockerSearchSize", "blocker_search_size"), ("kernelSize", "kernel_size"),
                                                                 ("lightSourceRadius", "light_source_radius")) if k1 in w["params"]})
@@ -132,12 +139,19 @@ def run_reference(args, w, cfg_path):
             _, _, depth = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
             pxyz, pidx = O.sv_build_prisms(sc["xyz"], sc["nrm"], sc["idx"], le)
             return O.sv_count(pxyz, pidx, fm["cam_mvp"], W, H, depth)[0]
-        if n_l == 1:
+        if n_l == 1 and tech not in O.MOMENT_TECHS:
             fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
             sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
             pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
             cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
             return O.visibility(p, cam, fm["light_mvp_b"], pos, nrm, sm)
+        if tech in O.MOMENT_TECHS:                               # ShadowMapping/src/main.cpp:459-472 with VSM / ESM / EVSM / MSM
+            fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
+            mom = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
+            fmap = O.filter_shadow_map(mom, W, H, p.kernel_order, tech)
+            pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+            cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+            return O.visibility_moments(p, cam, fm["light_mvp_b"], pos, nrm, fmap)
         fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], le, sc["light_at"], W, H, S, S)
         pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
         maps, mvpb = [], []
@@ -409,11 +423,15 @@ def main():
                  "vis_kernel": ("k_visibility (per-pixel shadow test/filter)", ab["visibility"]),
                  "tile_depth": ("k_tile<DEPTH> (light-view tile rasteriser)", ab["shadow_map"] // max(1, n_l)),
                  "tile_gbuffer": ("k_tile<GBUFFER> (camera-view tile rasteriser + resolve)", ab["gbuffer"])}
+    if "moment_filter" in ab:
+        kernel_of["moment_filter"] = ("k_mom_filter (separable blur of the moment map, X + Y launches)", ab["moment_filter"] // 2)
+        kernel_of["tile_depth"] = ("k_tile<MOMENTS> (light-view tile rasteriser + moment resolve)", ab["shadow_map"])
+        kernel_of["vis_kernel"] = ("k_mom_visibility (moment reconstruction)", ab["visibility"])
     cand = {k: v for k, v in passes.items() if k in kernel_of}
     roof = None
     if cand:
         top = max(cand, key=cand.get)
-        calls = n_l if top == "tile_depth" else 1
+        calls = n_l if top == "tile_depth" else (2 if top == "moment_filter" else 1)
         per_launch_ms = cand[top] / calls
         achieved = kernel_of[top][1] / (per_launch_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None

@@ -18,7 +18,7 @@ BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibilit
        "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11,
        "moments": 12, "moments_x": 13, "moments_filtered": 14}
 PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
-        "tile_gbuffer": 6, "tile_sv": 7}
+        "tile_gbuffer": 6, "tile_sv": 7, "moment_filter": 8}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
 SGI_ERR_OVERFLOW = -4
 

@@ -597,7 +597,9 @@ int sgi_filter_shadow_map(sgi_ctx* ctx) {
   // the previous frame's shadow pass (visibility stream) may still be sampling the filtered map
   if ((rc = sgi_join_vis(ctx))) return rc;
   sgi_wait_reads_of(ctx, SGI_BUF_MOMENTS_X, ctx->stream); sgi_wait_reads_of(ctx, SGI_BUF_MOMENTS_FILTERED, ctx->stream);
+  const int slot = sgi_timing_begin(ctx, SGI_PASS_MOMENT_FILTER, ctx->stream);
   if ((rc = sgi_moments_filter_run(ctx, ctx->stream))) return rc;
+  sgi_timing_end(ctx, SGI_PASS_MOMENT_FILTER, slot, ctx->stream);
   ctx->filtered_tech = ctx->params.technique; ctx->filtered_w = ctx->W; ctx->filtered_h = ctx->H;
   return SGI_OK;
 }

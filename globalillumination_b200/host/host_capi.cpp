@@ -133,6 +133,10 @@ int sgh_app_set_technique(sgh_app* a, const char* name) {
   else if (n == "rbssm" || n == "RBSSM") p.RBSSM = true;
   else if (n == "edtsm" || n == "edtsm_noncons") p.EDTSM = true;
   else if (n == "edtsm_conservative" || n == "edtsm_cons") { p.EDTSM = true; p.conservative = true; }
+  else if (n == "vsm" || n == "VSM") p.VSM = true;
+  else if (n == "esm" || n == "ESM") p.ESM = true;
+  else if (n == "evsm" || n == "EVSM") p.EVSM = true;
+  else if (n == "msm" || n == "MSM") p.MSM = true;
   else if (n == "montecarlo" || n == "multi_hard") p.monteCarlo = true;
   else { g_err = "unknown technique " + n; return -2; }
   return 0;
@@ -162,6 +166,7 @@ int sgh_app_set_float(sgh_app* a, const char* name, float v) {
 int sgh_app_upload_scene(sgh_app* a) { return a ? a->app.uploadScene() : -1; }
 int sgh_app_render_shadow_map(sgh_app* a) { return a ? a->app.renderShadowMap() : -1; }
 int sgh_app_render_gbuffer(sgh_app* a) { return a ? a->app.renderGBuffer() : -1; }
+int sgh_app_filter_shadow_map(sgh_app* a) { return a ? a->app.filterShadowMap() : -1; }
 int sgh_app_compute_hard_shadows(sgh_app* a) { return a ? a->app.computeHardShadows() : -1; }
 int sgh_app_render_soft_shadows(sgh_app* a) { return a ? a->app.renderSoftShadows() : -1; }
 int sgh_app_render_monte_carlo(sgh_app* a) { return a ? a->app.renderMonteCarlo() : -1; }

@@ -15,7 +15,7 @@ EXPORTS = [
     "sgh_scene_substitutions", "sgh_frame_matrices", "sgh_app_create", "sgh_app_destroy", "sgh_app_error", "sgh_app_context",
     "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
-    "sgh_app_render_gbuffer", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
+    "sgh_app_render_gbuffer", "sgh_app_filter_shadow_map", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
     "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_save_image", "sgh_write_png", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
 ]
 
@@ -194,6 +194,7 @@ class App:
 
     def render_shadow_map(self): self._ck(self.L.sgh_app_render_shadow_map(self.h))
     def render_gbuffer(self): self._ck(self.L.sgh_app_render_gbuffer(self.h))
+    def filter_shadow_map(self): self._ck(self.L.sgh_app_filter_shadow_map(self.h))
     def compute_hard_shadows(self): self._ck(self.L.sgh_app_compute_hard_shadows(self.h))
     def render_soft_shadows(self): self._ck(self.L.sgh_app_render_soft_shadows(self.h))
     def render_monte_carlo(self): self._ck(self.L.sgh_app_render_monte_carlo(self.h))

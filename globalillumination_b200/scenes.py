@@ -43,6 +43,13 @@ WORKLOADS = {
 }
 
 
+# Moment shadow maps on the headline scene: the ShadowMapping program with VSM / ESM / EVSM / MSM set
+# (ShadowMapping/src/main.cpp:459-472), Gaussian order 7 (:859).  Measurable with `bench.py --workload c2_sponza_vsm` etc.
+for _t in ("vsm", "esm", "evsm", "msm"):
+    WORKLOADS["c2_sponza_" + _t] = dict(WORKLOADS["c2_sponza"], program="shadow_mapping", technique=_t, params={},
+                                        scene=WORKLOADS["c2_sponza"]["scene"] + f"; moment shadow map ({_t}), blur order 7")
+
+
 def golden_scene(name):
     """The reference loader's output for a config (committed fixture)."""
     import numpy as np

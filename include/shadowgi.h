@@ -126,7 +126,8 @@ typedef enum sgi_pass {
   SGI_PASS_TILE_DEPTH = 5,  /* only the per-tile raster kernel of the light-view depth pass (per light)  */
   SGI_PASS_TILE_GBUFFER = 6,/* only the per-tile raster+resolve kernel of the G-buffer pass              */
   SGI_PASS_TILE_SV = 7,     /* only the per-tile counting kernel of the shadow-volume pass               */
-  SGI_PASS_COUNT_ = 8
+  SGI_PASS_MOMENT_FILTER = 8, /* both blur passes of sgi_filter_shadow_map                                  */
+  SGI_PASS_COUNT_ = 9
 } sgi_pass;
 
 /* lifecycle — replaces initGL()'s FBO/texture/VBO creation (ShadowMapping/src/main.cpp:839-953) */

@@ -53,6 +53,7 @@ int sgh_app_set_float(sgh_app* a, const char* name, float v);
 int sgh_app_upload_scene(sgh_app* a);
 int sgh_app_render_shadow_map(sgh_app* a);
 int sgh_app_render_gbuffer(sgh_app* a);
+int sgh_app_filter_shadow_map(sgh_app* a);       /* filterShadowMap(), ShadowMapping/src/main.cpp:374-398 (VSM/ESM/EVSM/MSM) */
 int sgh_app_compute_hard_shadows(sgh_app* a);
 int sgh_app_render_soft_shadows(sgh_app* a);
 int sgh_app_render_monte_carlo(sgh_app* a);

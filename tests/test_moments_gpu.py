@@ -138,3 +138,44 @@ def test_moment_visibility_respects_the_screen_rectangle(ctx):
         ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
         parts[y0:y1] = ctx.read("visibility")[y0:y1]
     assert util.bits_equal(parts, whole)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tech", ["vsm", "msm"])
+def test_host_display_runs_the_reference_frame_order(tech):
+    """ShadowApp::display with shadowParams.VSM / MSM set: renderShadowMap, filterShadowMap, renderGBuffer,
+    computeHardShadows (ShadowMapping/src/main.cpp:459-472) through the C++ host; the result equals the oracle chain."""
+    from globalillumination_b200 import hostapi, scenes
+    cfg = scenes.write_config("c1_teapot")
+    w = scenes.WORKLOADS["c1_teapot"]
+    W, H, S = w["W"] // 2, w["H"] // 2, w["S"] // 2
+    app = hostapi.App(0)
+    try:
+        app.load_scene(cfg); app.configure(W, H, S); app.set_technique(tech)
+        app.display("shadow_mapping")
+        c = app.context()
+        vis, mom, fy = c.read("visibility"), c.read("moments"), c.read("moments_filtered")
+        sc = hostapi.load_scene(cfg)
+        fm = util.frame(sc, W, H, S)
+        mom_o = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
+        assert util.bits_equal(mom, mom_o), util.describe_diff(mom, mom_o)
+        fy_o = O.filter_shadow_map(mom_o, W, H, 7, tech)
+        assert util.bits_equal(fy, fy_o), util.describe_diff(fy, fy_o)
+        pos_o, nrm_o, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        vis_o = O.visibility_moments(O.default_params(tech, S), cam, fm["light_mvp_b"], pos_o, nrm_o, fy_o)
+        ok = ~np.isnan(vis_o)
+        assert np.array_equal(np.isnan(vis), ~ok) and util.bits_equal(vis[ok], vis_o[ok]), util.describe_diff(vis[ok], vis_o[ok])
+        # frames queued back to back without a host sync (the shadow pass of frame k overlaps the raster passes of frame k+1):
+        # every frame still gets its own filtered map
+        app.set(animationOn=1, animation=-1800.0)
+        frames = []
+        for k in range(4):
+            app.display("shadow_mapping"); frames.append(c.read("visibility").copy()); app.step_animation(120.0)
+        app.set(animation=-1800.0)
+        for k in range(4):
+            app.display("shadow_mapping"); app.step_animation(120.0)
+        last = c.read("visibility")
+        assert util.bits_equal(np.nan_to_num(last), np.nan_to_num(frames[3])) and not util.bits_equal(np.nan_to_num(frames[0]), np.nan_to_num(frames[3]))
+    finally:
+        app.close()
