@@ -15,6 +15,8 @@
 // the two points GL leaves to the implementation, fixed in DESIGN.md §2.  fp32 in source order (-fmad=false): everything
 // without exp / log is bit-identical to oracle/; the exponential paths agree to a few ulp of expf / logf.
 #pragma once
+#include <climits>
+#include <cstddef>
 #include "sgi_internal.cuh"
 
 #define SGI_MOM_MAX_ORDER 33            // `uniform float kernel[33]`, GaussianFilter.frag:8
@@ -110,28 +112,39 @@ void mom_gaussian_kernel(int order, float* kernel) {
   }
 }
 
-// GL_LINEAR of level 0, CLAMP_TO_BORDER (0,0,0,0), RGBA32F
-__device__ __forceinline__ float4 mom_fetch4(const float4* __restrict__ img, int w, int h, float fw, float fh, float u, float v) {
+// GL_LINEAR of level 0, CLAMP_TO_BORDER (0,0,0,0), RGBA32F.  MomTap = where a bilinear sample lands: the four texels are
+// (ix, iy), (ix+1, iy), (ix, iy+1), (ix+1, iy+1); a false c* flag means that column / row is outside the image (border colour).
+struct MomTap {
+  int ix, iy; bool cx0, cx1, cy0, cy1;
+  float w00, w10, w01, w11;
+};
+__device__ __forceinline__ MomTap mom_tap(float fw, float fh, float u, float v) {
+  MomTap t;
   const float x = u * fw - 0.5f, y = v * fh - 0.5f;
   const float x0 = floorf(x), y0 = floorf(y), ax = x - x0, ay = y - y0;
   const float bx = 1.0f - ax, by = 1.0f - ay;
-  const bool cx0 = x0 >= 0.0f && x0 < fw, cx1 = x0 + 1.0f >= 0.0f && x0 + 1.0f < fw;
-  const bool cy0 = y0 >= 0.0f && y0 < fh, cy1 = y0 + 1.0f >= 0.0f && y0 + 1.0f < fh;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  t.cx0 = x0 >= 0.0f && x0 < fw; t.cx1 = x0 + 1.0f >= 0.0f && x0 + 1.0f < fw;
+  t.cy0 = y0 >= 0.0f && y0 < fh; t.cy1 = y0 + 1.0f >= 0.0f && y0 + 1.0f < fh;
   // NaN coordinates fail every range test: all four texels are the border colour
-  const int ix = cx0 ? (int)x0 : (cx1 ? (int)(x0 + 1.0f) - 1 : 0), iy = cy0 ? (int)y0 : (cy1 ? (int)(y0 + 1.0f) - 1 : 0);
-  const float4* row0 = img + (size_t)iy * w + ix;
-  const float4 t00 = (cx0 && cy0) ? __ldg(row0) : zero;
-  const float4 t10 = (cx1 && cy0) ? __ldg(row0 + 1) : zero;
-  const float4 t01 = (cx0 && cy1) ? __ldg(row0 + w) : zero;
-  const float4 t11 = (cx1 && cy1) ? __ldg(row0 + w + 1) : zero;
-  const float w00 = bx * by, w10 = ax * by, w01 = bx * ay, w11 = ax * ay;
+  t.ix = t.cx0 ? (int)x0 : (t.cx1 ? -1 : INT_MIN / 2); t.iy = t.cy0 ? (int)y0 : (t.cy1 ? -1 : INT_MIN / 2);
+  t.w00 = bx * by; t.w10 = ax * by; t.w01 = bx * ay; t.w11 = ax * ay;
+  return t;
+}
+__device__ __forceinline__ float4 mom_texel_at(const float4* __restrict__ img, int w, int ix, int iy, bool inside) {
+  return inside ? __ldg(img + ((ptrdiff_t)iy * w + ix)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float4 mom_blend(const MomTap& t, float4 t00, float4 t10, float4 t01, float4 t11) {
   float4 r;
-  r.x = (((0.0f + t00.x * w00) + t10.x * w10) + t01.x * w01) + t11.x * w11;
-  r.y = (((0.0f + t00.y * w00) + t10.y * w10) + t01.y * w01) + t11.y * w11;
-  r.z = (((0.0f + t00.z * w00) + t10.z * w10) + t01.z * w01) + t11.z * w11;
-  r.w = (((0.0f + t00.w * w00) + t10.w * w10) + t01.w * w01) + t11.w * w11;
+  r.x = (((0.0f + t00.x * t.w00) + t10.x * t.w10) + t01.x * t.w01) + t11.x * t.w11;
+  r.y = (((0.0f + t00.y * t.w00) + t10.y * t.w10) + t01.y * t.w01) + t11.y * t.w11;
+  r.z = (((0.0f + t00.z * t.w00) + t10.z * t.w10) + t01.z * t.w01) + t11.z * t.w11;
+  r.w = (((0.0f + t00.w * t.w00) + t10.w * t.w10) + t01.w * t.w01) + t11.w * t.w11;
   return r;
+}
+__device__ __forceinline__ float4 mom_fetch4(const float4* __restrict__ img, int w, int h, float fw, float fh, float u, float v) {
+  const MomTap t = mom_tap(fw, fh, u, v);
+  return mom_blend(t, mom_texel_at(img, w, t.ix, t.iy, t.cx0 && t.cy0), mom_texel_at(img, w, t.ix + 1, t.iy, t.cx1 && t.cy0),
+                   mom_texel_at(img, w, t.ix, t.iy + 1, t.cx0 && t.cy1), mom_texel_at(img, w, t.ix + 1, t.iy + 1, t.cx1 && t.cy1));
 }
 
 struct MomFilterArgs {
@@ -144,7 +157,9 @@ struct MomFilterArgs {
 // source is read with the TARGET's step (drawTextureOnShader's imageWidth / imageHeight).  One thread per target texel;
 // the taps of neighbouring threads overlap almost entirely, so the source is served from L1 and crosses HBM once.
 // LOGSPACE: LogGaussianFilter.frag (ESM) on .x, replicated into the four channels.
-template <bool HORIZONTAL, bool LOGSPACE>
+// ORDER: compile-time tap count of the specialised variant (7 = the reference's default, main.cpp:859: all 28 texel loads of a
+// target texel are independent and issue together), 0 = run-time loop.
+template <bool HORIZONTAL, bool LOGSPACE, int ORDER>
 __global__ void __launch_bounds__(256) k_mom_filter(const MomFilterArgs a) {
   const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
   if (i >= a.W || j >= a.H) return;
@@ -152,10 +167,12 @@ __global__ void __launch_bounds__(256) k_mom_filter(const MomFilterArgs a) {
   const float cs = nx * 0.5f + 0.5f, ct = ny * 0.5f + 0.5f;
   const float dir_s = HORIZONTAL ? 1.0f : 0.0f, dir_t = HORIZONTAL ? 0.0f : 1.0f;
   const float fw = (float)a.sw, fh = (float)a.sh;
-  const int kc = a.order / 2;
+  const int order = ORDER ? ORDER : a.order;
+  const int kc = order / 2;
   float4 out;
   if (!LOGSPACE) {
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
     for (int s = -kc; s <= kc; s++) {
       const float4 t = mom_fetch4(a.src, a.sw, a.sh, fw, fh, cs + dir_s * (float)s * a.step_s, ct + dir_t * (float)s * a.step_t);
       const float k = a.kernel[kc + s];
@@ -168,7 +185,8 @@ __global__ void __launch_bounds__(256) k_mom_filter(const MomFilterArgs a) {
     ks++;
     const float s1 = mom_fetch4(a.src, a.sw, a.sh, fw, fh, cs + dir_s * (float)ks * a.step_s, ct + dir_t * (float)ks * a.step_t).x;
     float sum = s0 + logf(a.kernel[0] + (a.kernel[1] * expf(s1 - s0)));                      // log_conv, :10-13
-    for (int k = 2; k < a.order; k++) {
+#pragma unroll
+    for (int k = 2; k < order; k++) {
       ks++;
       const float sk = mom_fetch4(a.src, a.sw, a.sh, fw, fh, cs + dir_s * (float)ks * a.step_s, ct + dir_t * (float)ks * a.step_t).x;
       sum = sum + logf(1.0f + (a.kernel[k] * expf(sk - sum)));

@@ -703,9 +703,12 @@ int sgi_moments_filter_run(sgi_ctx* ctx, cudaStream_t st) {
   const bool logs = ctx->params.technique == SGI_TECH_ESM;
   dim3 block(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
   f.src = (const float4*)ctx->buf[SGI_BUF_MOMENTS]; f.sw = ctx->SW; f.sh = ctx->SH; f.dst = (float4*)ctx->buf[SGI_BUF_MOMENTS_X];
-  if (logs) k_mom_filter<true, true><<<grid, block, 0, st>>>(f); else k_mom_filter<true, false><<<grid, block, 0, st>>>(f);
+  const bool o7 = f.order == 7;
+  if (logs) { if (o7) k_mom_filter<true, true, 7><<<grid, block, 0, st>>>(f); else k_mom_filter<true, true, 0><<<grid, block, 0, st>>>(f); }
+  else { if (o7) k_mom_filter<true, false, 7><<<grid, block, 0, st>>>(f); else k_mom_filter<true, false, 0><<<grid, block, 0, st>>>(f); }
   f.src = (const float4*)ctx->buf[SGI_BUF_MOMENTS_X]; f.sw = ctx->W; f.sh = ctx->H; f.dst = (float4*)ctx->buf[SGI_BUF_MOMENTS_FILTERED];
-  if (logs) k_mom_filter<false, true><<<grid, block, 0, st>>>(f); else k_mom_filter<false, false><<<grid, block, 0, st>>>(f);
+  if (logs) { if (o7) k_mom_filter<false, true, 7><<<grid, block, 0, st>>>(f); else k_mom_filter<false, true, 0><<<grid, block, 0, st>>>(f); }
+  else { if (o7) k_mom_filter<false, false, 7><<<grid, block, 0, st>>>(f); else k_mom_filter<false, false, 0><<<grid, block, 0, st>>>(f); }
   ctx->launches += 2;
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;

@@ -146,17 +146,17 @@ def test_host_display_runs_the_reference_frame_order(tech):
     """ShadowApp::display with shadowParams.VSM / MSM set: renderShadowMap, filterShadowMap, renderGBuffer,
     computeHardShadows (ShadowMapping/src/main.cpp:459-472) through the C++ host; the result equals the oracle chain."""
     from globalillumination_b200 import hostapi, scenes
-    cfg = scenes.write_config("c1_teapot")
     w = scenes.WORKLOADS["c1_teapot"]
     W, H, S = w["W"] // 2, w["H"] // 2, w["S"] // 2
+    sc = scenes.golden_scene(w["golden"])              # Configs/Teapot.txt through the reference's loader
     app = hostapi.App(0)
     try:
-        app.load_scene(cfg); app.configure(W, H, S); app.set_technique(tech)
+        app.set_scene(sc); app.configure(W, H, S); app.set_technique(tech)
         app.display("shadow_mapping")
         c = app.context()
         vis, mom, fy = c.read("visibility"), c.read("moments"), c.read("moments_filtered")
-        sc = hostapi.load_scene(cfg)
         fm = util.frame(sc, W, H, S)
+        assert (mom[..., 0] != 0).mean() > 0.2
         mom_o = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
         assert util.bits_equal(mom, mom_o), util.describe_diff(mom, mom_o)
         fy_o = O.filter_shadow_map(mom_o, W, H, 7, tech)
