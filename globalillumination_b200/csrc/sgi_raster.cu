@@ -94,7 +94,7 @@ __device__ __forceinline__ CV xform(const float* __restrict__ m, float x, float 
 }
 
 struct SetupArgs {
-  const float* xyz; const int32_t* idx; int T;
+  const float* xyz; const float* nrm; const float* rgb; const int32_t* idx; int T;
   float mvp[16];
   int W, H;
   int use_offset; float factor, units;
@@ -201,10 +201,26 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
     if (a.attr) {
       SgiRecAttr q;
       const int ids[3] = {id0, id1, id2};
+      const int src[3] = {i0, i1, i2};
+      q.pad = 0.0f; q.pad2 = 0.0f;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         q.iw[k] = IW[ids[k]];
-        q.bary[3 * k + 0] = poly[ids[k]].b0; q.bary[3 * k + 1] = poly[ids[k]].b1; q.bary[3 * k + 2] = poly[ids[k]].b2;
+        const float b0 = poly[ids[k]].b0, b1 = poly[ids[k]].b1, b2 = poly[ids[k]].b2;
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+          const float* arr = (c < 3) ? a.xyz : (c < 6 ? a.nrm : a.rgb);
+          const int cc = c % 3;
+          float v = 0.0f;
+          if (arr) {
+            if (!was_clipped) v = arr[3 * (size_t)src[ids[k]] + cc];       // the source vertex itself (ids[] = 0,1,2 or 0,2,1)
+            else {
+              const float s0 = arr[3 * (size_t)i0 + cc], s1 = arr[3 * (size_t)i1 + cc], s2 = arr[3 * (size_t)i2 + cc];
+              v = (b0 * s0 + b1 * s1) + b2 * s2;
+            }
+          }
+          if (c < 6) q.A[k][c] = v; else q.C[k][cc] = v;
+        }
       }
       a.attr[slot] = q;
     }
@@ -955,33 +971,18 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         const uint4* aq = reinterpret_cast<const uint4*>(&a.attr[slot]);
         uint4* rd = reinterpret_cast<uint4*>(&r); uint4* ad = reinterpret_cast<uint4*>(&at);
         rd[0] = __ldg(rq); rd[1] = __ldg(rq + 1); rd[2] = __ldg(rq + 2); rd[3] = __ldg(rq + 3);
-        ad[0] = __ldg(aq); ad[1] = __ldg(aq + 1); ad[2] = __ldg(aq + 2);
+        ad[0] = __ldg(aq); ad[1] = __ldg(aq + 1); ad[2] = __ldg(aq + 2); ad[3] = __ldg(aq + 3); ad[4] = __ldg(aq + 4); ad[5] = __ldg(aq + 5);
+        if (MODE == SGI_MODE_GBUFFER_RGB) { ad[6] = __ldg(aq + 6); ad[7] = __ldg(aq + 7); }
       }
       long long E0, E1, E2;
       cover(r.X0, r.Y0, r.X1, r.Y1, r.X2, r.Y2, x, y, E0, E1, E2);
-      const int i0 = __ldg(&a.idx[3 * (size_t)t]), i1 = __ldg(&a.idx[3 * (size_t)t + 1]), i2 = __ldg(&a.idx[3 * (size_t)t + 2]);
       const float q0 = ((float)E0 * r.ia) * at.iw[0];
       const float q1 = ((float)E1 * r.ia) * at.iw[1];
       const float q2 = ((float)E2 * r.ia) * at.iw[2];
       const float iq = 1.0f / ((q0 + q1) + q2);
       float outv[6];
-      // unclipped triangles (pad0 == 0) interpolate the source vertices directly, in the record's CCW order
-      const int j1 = r.pad1 ? i2 : i1, j2 = r.pad1 ? i1 : i2;
 #pragma unroll
-      for (int c = 0; c < 6; c++) {
-        const float* src = (c < 3) ? a.xyz : a.nrm;
-        const int cc = (c < 3) ? c : c - 3;
-        float A0, A1, A2;
-        if (r.pad0 == 0) {
-          A0 = __ldg(&src[3 * (size_t)i0 + cc]); A1 = __ldg(&src[3 * (size_t)j1 + cc]); A2 = __ldg(&src[3 * (size_t)j2 + cc]);
-        } else {
-          const float s0 = __ldg(&src[3 * (size_t)i0 + cc]), s1 = __ldg(&src[3 * (size_t)i1 + cc]), s2 = __ldg(&src[3 * (size_t)i2 + cc]);
-          A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
-          A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
-          A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
-        }
-        outv[c] = ((q0 * A0 + q1 * A1) + q2 * A2) * iq;
-      }
+      for (int c = 0; c < 6; c++) outv[c] = ((q0 * at.A[0][c] + q1 * at.A[1][c]) + q2 * at.A[2][c]) * iq;
       a.depth[o] = __uint_as_float((unsigned int)(key >> 32));
       a.pos4[o] = make_float4(outv[0], outv[1], outv[2], 1.0f);
       a.nrm4[o] = make_float4(outv[3], outv[4], outv[5], (r.prim_front & 1) ? 1.0f : 0.0f);
@@ -989,18 +990,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
                                                          // carrying this code in the colour-less kernel cost 8 % of its time)
         float col[3];
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++) {
-          float A0, A1, A2;
-          if (r.pad0 == 0) {
-            A0 = __ldg(&a.rgb[3 * (size_t)i0 + cc]); A1 = __ldg(&a.rgb[3 * (size_t)j1 + cc]); A2 = __ldg(&a.rgb[3 * (size_t)j2 + cc]);
-          } else {
-            const float s0 = __ldg(&a.rgb[3 * (size_t)i0 + cc]), s1 = __ldg(&a.rgb[3 * (size_t)i1 + cc]), s2 = __ldg(&a.rgb[3 * (size_t)i2 + cc]);
-            A0 = (at.bary[0] * s0 + at.bary[1] * s1) + at.bary[2] * s2;
-            A1 = (at.bary[3] * s0 + at.bary[4] * s1) + at.bary[5] * s2;
-            A2 = (at.bary[6] * s0 + at.bary[7] * s1) + at.bary[8] * s2;
-          }
-          col[cc] = ((q0 * A0 + q1 * A1) + q2 * A2) * iq;
-        }
+        for (int cc = 0; cc < 3; cc++) col[cc] = ((q0 * at.C[0][cc] + q1 * at.C[1][cc]) + q2 * at.C[2][cc]) * iq;
         a.albedo4[o] = make_float4(col[0], col[1], col[2], 1.0f);
       }
     }
@@ -1155,7 +1145,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   SGI_CUDA(ctx, cudaMemsetAsync(sc.d_counters, 0, (size_t)(16 + 2 * sc.tile_cap) * 4, st));
 
   SetupArgs sa;
-  sa.xyz = job.xyz; sa.idx = job.idx; sa.T = job.T;
+  sa.xyz = job.xyz; sa.nrm = job.nrm; sa.rgb = (job.rgb && job.albedo4) ? job.rgb : nullptr; sa.idx = job.idx; sa.T = job.T;
   for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
   sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
   sa.rec = sc.d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? sc.d_attr : nullptr;
