@@ -173,7 +173,21 @@ def run_reference(args, w, cfg_path):
     dt = time.perf_counter() - t0
     fps = args.steps / dt
     cores = O.num_threads()
+    taps = None
+    if tech == "pcss":
+        # exact tap count of one frame (the first of the animation): which pixels run the blocker search, which the filter loop
+        r = O.rotate(-1800.0 / 10.0, [0, 1, 0]).reshape(4, 4).T[:3, :3]
+        fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], (r @ sc["light_eye"]).astype(np.float32), sc["light_at"], W, H, S, S)
+        sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+        pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        n_search, n_filter, n_fg = O.pcss_tap_count(p, cam, fm["light_mvp_b"], pos, nrm, sm)
+        bsz = 2 * int((p.blocker_search_size - 1) * 0.5) + 1
+        ksz = 2 * int((p.kernel_size - 1) * 0.5) + 1
+        taps = {"foreground_pixels": n_fg, "blocker_search_pixels": n_search, "filter_pixels": n_filter,
+                "taps": bsz * bsz * n_search + ksz * ksz * n_filter, "frame": "first frame of the animation (counted with the CPU port)"}
     return {
+        "pcss_taps": taps,
         "impl": "reference", "metric": metric_name(args.workload, w), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -476,7 +490,14 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup = 3, 1
-        out["cpu_baseline"] = run_reference(a2, w, cfg_path)["cpu_baseline"]
+        ref = run_reference(a2, w, cfg_path)
+        out["cpu_baseline"] = ref["cpu_baseline"]
+        if ref.get("pcss_taps") and out.get("shadow_pass"):
+            # L2_taps / t_K3 with the taps the program really executes (4 bytes each), against the measured L2 read peak
+            sp, tp = out["shadow_pass"], ref["pcss_taps"]
+            sp["taps_executed"] = tp
+            sp["l2_taps_GBs"] = 4.0 * tp["taps"] / (sp["launch_ms"] * 1e-3) / 1e9
+            sp["l2_taps_frac"] = sp["l2_taps_GBs"] / sp["l2_read_peak_GBs"]
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

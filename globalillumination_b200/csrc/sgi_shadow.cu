@@ -85,7 +85,19 @@ struct TapSrc {
     if ((rk | ck) < 0) return 0.0f;
     return SHARED ? base[rk + ck] : __ldg(&base[(size_t)rk + ck]);
   }
+  // Row-wise form of the same taps: when the row and every column of the grid are inside the map (all but the pixels whose
+  // footprint crosses the map border), a tap is one address add and one load off the row pointer - no border test, no 64-bit
+  // index arithmetic per tap.  Same texels, same values.
+  __device__ __forceinline__ const float* rowptr(int rk) const { return base + rk; }
+  __device__ __forceinline__ float tap_in(const float* __restrict__ rp, int ck) const { return SHARED ? rp[ck] : __ldg(rp + ck); }
 };
+template <int N>
+__device__ __forceinline__ int keys_or(const int (&k)[N], int n) {
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) if (i < n) m |= k[i];
+  return m;
+}
 
 // ---- Shadow.frag:86-116 (tap offsets precomputed on the host with the same fp32 loop) ----
 // N = taps per axis known at compile time (0 = run-time count, columns kept in local memory)
@@ -98,11 +110,19 @@ __device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, const Ta
   for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
     if (ih < n) rows[ih] = src.rowkey(axis_texel(c.y + a.pcf_dv[ih], s.fh));
   float illum = 0.0f;
+  const int rows_or = keys_or(rows, n);
   for (int iw = 0; iw < n; iw++) {                     // Shadow.frag:98-99: w outer, h inner
     const int col = src.colkey(axis_texel(c.x + a.pcf_du[iw], s.fw));
+    if ((rows_or | col) >= 0) {
+      const float* __restrict__ cp = src.rowptr(col);     // base + column; the row keys are the offsets
 #pragma unroll
-    for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
-      if (ih < n) { if (c.z <= src.tap(rows[ih], col)) illum += 1.0f; else illum += a.p.shadow_intensity; }
+      for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
+        if (ih < n) { if (c.z <= src.tap_in(cp, rows[ih])) illum += 1.0f; else illum += a.p.shadow_intensity; }
+    } else {
+#pragma unroll
+      for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
+        if (ih < n) { if (c.z <= src.tap(rows[ih], col)) illum += 1.0f; else illum += a.p.shadow_intensity; }
+    }
   }
   return illum / (float)(n * n);
 }
@@ -119,14 +139,25 @@ __device__ __forceinline__ float pcss_blockers(const VisArgs& a, const Smap& s, 
 #pragma unroll
   for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
     if (k < nb) cols[k] = src.colkey(axis_texel(c.x + a.bs_q[k], s.fw));
+  const int cols_or = keys_or(cols, nb);
   for (int j = 0; j < nb; j++) {
     const int row = src.rowkey(axis_texel(c.y + a.bs_q[j], s.fh));
+    if ((cols_or | row) >= 0) {
+      const float* __restrict__ rp = src.rowptr(row);
 #pragma unroll
-    for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
-      if (k < nb) {
-        const float dfl = src.tap(row, cols[k]);
-        if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
-      }
+      for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
+        if (k < nb) {
+          const float dfl = src.tap_in(rp, cols[k]);
+          if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
+        if (k < nb) {
+          const float dfl = src.tap(row, cols[k]);
+          if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+        }
+    }
   }
   if (numberOfBlockers == 0) return 1.0f;
   return averageDepth / (float)numberOfBlockers;
@@ -151,11 +182,19 @@ __device__ __forceinline__ float pcss_filter(const VisArgs& a, const Smap& s, co
 #pragma unroll
   for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
     if (k < nk) cols[k] = src.colkey(axis_texel(c.x + ((float)(w0 + k) * penumbraWidth) / fw2, s.fw));
+  const int cols_or = keys_or(cols, nk);
   for (int h = w0; (float)h <= fw2; h++) {
     const int row = src.rowkey(axis_texel(c.y + ((float)h * penumbraWidth) / fw2, s.fh));
+    if ((cols_or | row) >= 0) {
+      const float* __restrict__ rp = src.rowptr(row);
 #pragma unroll
-    for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
-      if (k < nk) { if (c.z <= src.tap(row, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
+      for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
+        if (k < nk) { if (c.z <= src.tap_in(rp, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
+        if (k < nk) { if (c.z <= src.tap(row, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
+    }
   }
   return illum / (float)(p.kernel_size * p.kernel_size);
 }

@@ -124,6 +124,9 @@ void orc_shade_phong(const orc_camera* cam, float shadow_intensity, const float*
 void orc_visibility(const orc_params* p, const orc_camera* cam, const float light_mvp_b[16],
                     const float* pos4, const float* nrm4, int W, int H,
                     const float* shadow_map, float* vis);
+/* bench.py measurement helper: out = {pixels running the blocker search, pixels running the filter loop, foreground pixels} */
+void orc_pcss_tap_count(const orc_params* p, const orc_camera* cam, const float light_mvp_b[16], const float* pos4,
+                        const float* nrm4, int W, int H, const float* shadow_map, int64_t out[3]);
 /* many-light: maps[N][S][S]; common3x4 taken from light_mvp_b_common; trans[N][4]; weights NULL=1 */
 void orc_visibility_multi(const orc_params* p, const float light_mvp_b_common[16], int N,
                           const float* trans4, const float* pos4, int W, int H,

@@ -231,6 +231,16 @@ def visibility(params, cam, light_mvp_b, pos4, nrm4, shadow_map):
 EDT_MARKER = -32768
 
 
+def pcss_tap_count(params, cam, light_mvp_b, pos4, nrm4, shadow_map):
+    """(pixels running the blocker search, pixels running the filter loop, foreground pixels) of a PCSS frame."""
+    pos4, nrm4, sm, lm = _f32(pos4), _f32(nrm4), _f32(shadow_map), _f32(light_mvp_b)
+    H, W = pos4.shape[:2]
+    out = np.zeros(3, np.int64)
+    lib().orc_pcss_tap_count(C.byref(params), C.byref(cam), _fp(lm), _fp(pos4), _fp(nrm4), W, H, _fp(sm),
+                             out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return int(out[0]), int(out[1]), int(out[2])
+
+
 def edt_hard_image(params, cam, cam_mvp, light_mvp_b, pos4, nrm4, shadow_map):
     """(shadow, camera depth, pre-evaluated shadow, 1) target of the RBSM shaders with EDTSM == 1."""
     H, W = pos4.shape[:2]

@@ -225,7 +225,7 @@ static float pcf(const orc_params* p, const Smap* s, V4 c) {
 }
 
 /* ---- PlausibleSoftShadow.frag:166-194, 365-374, 376-398, 556-563 ---- */
-static float pcss(const orc_params* p, const Smap* s, V4 c) {
+static float pcss_penumbra(const orc_params* p, const Smap* s, V4 c) {
   float averageDepth = 0.0f;
   int numberOfBlockers = 0;
   float blockerSearchWidth;
@@ -248,6 +248,10 @@ static float pcss(const orc_params* p, const Smap* s, V4 c) {
     float pw = ((c.z - averageDepth) / averageDepth) * (float)p->light_source_radius;
     penumbraWidth = ((float)p->z_near * pw) / c.z;
   }
+  return penumbraWidth;
+}
+static float pcss(const orc_params* p, const Smap* s, V4 c) {
+  float penumbraWidth = pcss_penumbra(p, s, c);
   /* PCF */
   float illuminationCount = 0.0f;
   float stepSize = 2.0f * penumbraWidth / (float)p->kernel_size;
@@ -598,6 +602,31 @@ void orc_visibility(const orc_params* p, const orc_camera* cam, const float ligh
       vis[o] = shadow;
     }
   }
+}
+
+/* Measurement helper for bench.py (not a shader pass): how many shadow-map taps the PCSS program executes on this frame.
+ * out[0] = pixels that reach the blocker search (each takes every tap of the blocker_search_size^2 grid), out[1] = pixels that
+ * go on to the kernel_size^2 filter loop (PlausibleSoftShadow.frag:376-398: 0 < stepSize < 1), out[2] = foreground pixels. */
+void orc_pcss_tap_count(const orc_params* p, const orc_camera* cam, const float light_mvp_b[16], const float* pos4,
+                        const float* nrm4, int W, int H, const float* shadow_map, int64_t out[3]) {
+  Smap s = {shadow_map, p->shadow_map_width, p->shadow_map_height, (float)p->shadow_map_width, (float)p->shadow_map_height};
+  int64_t n_search = 0, n_filter = 0, n_fg = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : n_search, n_filter, n_fg)
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      size_t o = (size_t)j * W + i;
+      V4 vertex = {pos4[4 * o], pos4[4 * o + 1], pos4[4 * o + 2], pos4[4 * o + 3]};
+      if (vertex.x == 0.0f) continue;
+      n_fg++;
+      V4 normal = {nrm4[4 * o], nrm4[4 * o + 1], nrm4[4 * o + 2], nrm4[4 * o + 3]};
+      V4 sc = mat4_mul_v4(light_mvp_b, vertex);
+      V4 c = {sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w};
+      if (!(sc.w > 0.0f && pre_evaluation(cam, p->shadow_intensity, vertex, normal) == 1.0f)) continue;
+      n_search++;
+      float stepSize = 2.0f * pcss_penumbra(p, &s, c) / (float)p->kernel_size;
+      if (!(stepSize <= 0.0f || stepSize >= 1.0f)) n_filter++;
+    }
+  out[0] = n_search; out[1] = n_filter; out[2] = n_fg;
 }
 
 /* AccurateSoftShadow.frag:52-133 (monteCarlo branch: accFactor = 1, adaptiveSamplingLowerAccuracy = 0) */
