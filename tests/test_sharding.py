@@ -50,6 +50,13 @@ def _worker(rank, world, port, q):
         assert (mine[:y0] == 0).all() and (mine[y1:] == 0).all()
         out = sharding.gather_strips(torch.from_numpy(mine), rects).numpy()
         ok_tiles = np.array_equal(out, full)
+        # tiles with a moment shadow map (VSM): the moment target and its blur are replicated like the depth map, every rank
+        # reconstructs only its strip
+        fmap = O.filter_shadow_map(O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, "vsm"), W, H, 7, "vsm")
+        full_m = O.visibility_moments(O.default_params("vsm", S), cam, fm["light_mvp_b"], pos, nrm, fmap)
+        mine_m = O.visibility_moments(O.default_params("vsm", S, rect_x0=x0, rect_y0=y0, rect_x1=x1, rect_y1=y1), cam, fm["light_mvp_b"], pos, nrm, fmap)
+        out_m = sharding.gather_strips(torch.from_numpy(mine_m), rects).numpy()
+        ok_tiles = ok_tiles and np.array_equal(out_m, full_m) and (mine_m[:y0] == 0).all() and (mine_m[y1:] == 0).all()
         # lights: each rank accumulates its own lights, partial sums are reduced
         n_l = 4
         mvp, mvpb = util.multi_lights(sc, n_l, 16, W, H, S)
