@@ -88,8 +88,9 @@ struct TapSrc {
   // Row-wise form of the same taps: when the row and every column of the grid are inside the map (all but the pixels whose
   // footprint crosses the map border), a tap is one address add and one load off the row pointer - no border test, no 64-bit
   // index arithmetic per tap.  Same texels, same values.
-  __device__ __forceinline__ const float* rowptr(int rk) const { return base + rk; }
-  __device__ __forceinline__ float tap_in(const float* __restrict__ rp, int ck) const { return SHARED ? rp[ck] : __ldg(rp + ck); }
+  // (the element offset is formed in 32 bits - it is below S*S <= 2^26 - and widened once by the address multiply-add)
+  __device__ __forceinline__ int rowptr(int rk) const { return rk; }
+  __device__ __forceinline__ float tap_in(int rk, int ck) const { const unsigned off = (unsigned)(rk + ck); return SHARED ? base[off] : __ldg(base + off); }
 };
 template <int N>
 __device__ __forceinline__ int keys_or(const int (&k)[N], int n) {
@@ -114,7 +115,7 @@ __device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, const Ta
   for (int iw = 0; iw < n; iw++) {                     // Shadow.frag:98-99: w outer, h inner
     const int col = src.colkey(axis_texel(c.x + a.pcf_du[iw], s.fw));
     if ((rows_or | col) >= 0) {
-      const float* __restrict__ cp = src.rowptr(col);     // base + column; the row keys are the offsets
+      const int cp = src.rowptr(col);     // base + column; the row keys are the offsets
 #pragma unroll
       for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
         if (ih < n) { if (c.z <= src.tap_in(cp, rows[ih])) illum += 1.0f; else illum += a.p.shadow_intensity; }
@@ -143,13 +144,24 @@ __device__ __forceinline__ float pcss_blockers(const VisArgs& a, const Smap& s, 
   for (int j = 0; j < nb; j++) {
     const int row = src.rowkey(axis_texel(c.y + a.bs_q[j], s.fh));
     if ((cols_or | row) >= 0) {
-      const float* __restrict__ rp = src.rowptr(row);
+      const int rp = src.rowptr(row);
+      if (NB > 0 && NB <= 8) {
+        // specialised grid: the row's blockers are collected as bits and counted with one popc instead of one add per tap
+        unsigned int hit = 0u;
 #pragma unroll
-      for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
-        if (k < nb) {
+        for (int k = 0; k < (NB ? NB : 1); k++) {
           const float dfl = src.tap_in(rp, cols[k]);
-          if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+          if (c.z > dfl) { averageDepth += dfl; hit |= 1u << k; }
         }
+        numberOfBlockers += __popc(hit);
+      } else {
+#pragma unroll
+        for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
+          if (k < nb) {
+            const float dfl = src.tap_in(rp, cols[k]);
+            if (c.z > dfl) { averageDepth += dfl; numberOfBlockers++; }
+          }
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
@@ -186,7 +198,7 @@ __device__ __forceinline__ float pcss_filter(const VisArgs& a, const Smap& s, co
   for (int h = w0; (float)h <= fw2; h++) {
     const int row = src.rowkey(axis_texel(c.y + ((float)h * penumbraWidth) / fw2, s.fh));
     if ((cols_or | row) >= 0) {
-      const float* __restrict__ rp = src.rowptr(row);
+      const int rp = src.rowptr(row);
 #pragma unroll
       for (int k = 0; k < (NK ? NK : SGI_MAX_PCF_TAPS); k++)
         if (k < nk) { if (c.z <= src.tap_in(rp, cols[k])) illum += 1.0f; else illum += p.shadow_intensity; }
