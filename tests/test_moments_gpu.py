@@ -179,3 +179,43 @@ def test_host_display_runs_the_reference_frame_order(tech):
         assert util.bits_equal(np.nan_to_num(last), np.nan_to_num(frames[3])) and not util.bits_equal(np.nan_to_num(frames[0]), np.nan_to_num(frames[3]))
     finally:
         app.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tech", ["vsm", "esm"])
+def test_moment_chain_at_the_headline_size(tech):
+    """BASELINE config c2's scene and sizes (Sponza-like, 1920x1080, 2048^2 map) with a pre-filtered technique, through the
+    host's display(): moment target and Gaussian blur bit-exact, visibility within the stated tolerances; plus the size-
+    independent properties of the chain (blur weights sum to one: a constant region stays constant; visibility in
+    [shadowIntensity, 1] on the foreground, 0 on the background)."""
+    from globalillumination_b200 import hostapi, scenes
+    cfg = scenes.write_config("c2_sponza_" + tech)
+    w = scenes.WORKLOADS["c2_sponza_" + tech]
+    W, H, S = w["W"], w["H"], w["S"]
+    app = hostapi.App(0)
+    try:
+        app.load_scene(cfg); app.configure(W, H, S); app.set_technique(tech)
+        app.display("shadow_mapping")
+        c = app.context()
+        vis, mom, fx, fy = c.read("visibility"), c.read("moments"), c.read("moments_x"), c.read("moments_filtered")
+        pos, nrm = c.read("gbuf_pos"), c.read("gbuf_nrm")
+        sc = hostapi.load_scene(cfg)
+        fm = util.frame(sc, W, H, S)
+        mom_o = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], S, S, tech)
+        assert util.bits_equal(mom, mom_o), util.describe_diff(mom, mom_o)
+        fx_o = O.filter_moments(mom, W, H, 7, True, tech == "esm")
+        fy_o = O.filter_moments(fx, W, H, 7, False, tech == "esm")
+        if tech == "esm":
+            assert _close(fx, fx_o, EXP_TOL) and _close(fy, fy_o, EXP_TOL)
+        else:
+            assert util.bits_equal(fx, fx_o) and util.bits_equal(fy, fy_o)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        vis_o = O.visibility_moments(O.default_params(tech, S), cam, fm["light_mvp_b"], pos, nrm, fy)
+        assert np.abs(vis - vis_o).max() <= (EXP_TOL if tech == "esm" else 0.0)
+        fg = pos[..., 0] != 0
+        assert (vis[~fg] == 0).all() and (vis[fg] >= 0.25).all() and (vis[fg] <= 1.0).all() and 0.02 < (vis[fg] < 0.999).mean() < 0.98
+        if tech == "vsm":
+            # first moment of the blurred map stays inside the range of the un-blurred one (convex combination + border zeros)
+            assert fy[..., 0].max() <= mom[..., 0].max() * (1 + 1e-6) and fy[..., 0].min() >= 0.0
+    finally:
+        app.close()
