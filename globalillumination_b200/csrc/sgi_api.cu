@@ -448,8 +448,9 @@ int sgi_set_params(sgi_ctx* ctx, const sgi_params* p) {
     ctx->err = "sgi_set_params: kernel sizes must be in 1..64";
     return SGI_ERR_INVALID;
   }
-  if (sgi_is_moment_tech(p->technique) && (p->kernel_order < 2 || p->kernel_order > (p->technique == SGI_TECH_ESM ? 25 : SGI_MOM_MAX_ORDER))) {
-    ctx->err = "sgi_set_params: blur order must be in 2..33 (2..25 for ESM: `uniform float kernel[25]`, LogGaussianFilter.frag:8)";
+  if (sgi_is_moment_tech(p->technique) && (p->kernel_order < 3 || (p->kernel_order & 1) == 0 || p->kernel_order > (p->technique == SGI_TECH_ESM ? 25 : SGI_MOM_MAX_ORDER))) {
+    // the reference only ever builds odd orders (7, then +-2 from the keyboard, main.cpp:545,572-573)
+    ctx->err = "sgi_set_params: blur order must be odd and in 3..33 (3..25 for ESM: `uniform float kernel[25]`, LogGaussianFilter.frag:8)";
     return SGI_ERR_INVALID;
   }
   int n1 = sgi_host_pcf_offsets(p->kernel_order, p->penumbra_size, 0, ctx->pcf_off, SGI_MAX_PCF_TAPS);

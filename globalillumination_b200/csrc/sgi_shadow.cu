@@ -141,6 +141,7 @@ __device__ __forceinline__ float pcss_blockers(const VisArgs& a, const Smap& s, 
   for (int k = 0; k < (NB ? NB : SGI_MAX_PCF_TAPS); k++)
     if (k < nb) cols[k] = src.colkey(axis_texel(c.x + a.bs_q[k], s.fw));
   const int cols_or = keys_or(cols, nb);
+#pragma unroll
   for (int j = 0; j < nb; j++) {
     const int row = src.rowkey(axis_texel(c.y + a.bs_q[j], s.fh));
     if ((cols_or | row) >= 0) {

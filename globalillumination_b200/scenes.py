@@ -50,6 +50,14 @@ for _t in ("vsm", "esm", "evsm", "msm"):
                                         scene=WORKLOADS["c2_sponza"]["scene"] + f"; moment shadow map ({_t}), blur order 7")
 
 
+# PCSS where its filter loop really runs: on the Sponza-like light every blocker average is below the shader's 0.99 cut-off
+# (PlausibleSoftShadow.frag:368) and the pass ends after the blocker search; under the Dragon / Teapot light
+# (10,130,100) the light-space depths are 0.991-0.996 and penumbra pixels take all kernelSize^2 filter taps as well.
+WORKLOADS["dragon_pcss"] = dict(golden="dragon", lines=[], W=1920, H=1080, S=2048, program="soft_shadow_mapping", technique="pcss",
+                                params=dict(blockerSearchSize=7, kernelSize=15, lightSourceRadius=8),
+                                scene="Configs/Dragon.txt through the reference's SceneLoader (golden scene_dragon.npz), 100004 triangles; PCSS at the c2 sizes")
+
+
 def golden_scene(name):
     """The reference loader's output for a config (committed fixture)."""
     import numpy as np

@@ -320,7 +320,13 @@ def raster_moments(xyz, idx, mvp, W, H, technique, factor=4.0, units=20.0, z_nea
 
 
 def gaussian_kernel(order):
-    k = np.zeros(order, np.float32)
+    k = np.zeros(34, np.float32)               # `uniform float kernel[33]`: entries past `order` stay 0
+    lib().orc_gaussian_kernel(order, _fp(k))
+    return k[:order]
+
+
+def _kernel33(order):
+    k = np.zeros(34, np.float32)
     lib().orc_gaussian_kernel(order, _fp(k))
     return k
 
@@ -328,7 +334,7 @@ def gaussian_kernel(order):
 def filter_moments(src4, W, H, order, horizontal, log_space=False):
     """One pass of filterShadowMap: src4[sh, sw, 4] -> float32[H, W, 4]."""
     src4 = _f32(src4)
-    k = gaussian_kernel(order)
+    k = _kernel33(order)
     out = np.empty((H, W, 4), np.float32)
     lib().orc_filter_moments(_fp(src4), src4.shape[1], src4.shape[0], W, H, order, _fp(k), int(bool(horizontal)),
                              int(bool(log_space)), _fp(out))

@@ -110,8 +110,9 @@ def test_moment_passes_need_their_inputs_and_switch_back_to_depth_maps(ctx):
     with pytest.raises(capi.SgiError):
         ctx.compute_visibility()
     # blur order outside the shader's kernel[] array is refused
-    with pytest.raises(capi.SgiError):
-        ctx.set_params(capi.default_params("vsm", kernel_order=35))
+    for bad in (35, 8, 1):                          # past `kernel[33]`, even, too small
+        with pytest.raises(capi.SgiError):
+            ctx.set_params(capi.default_params("vsm", kernel_order=bad))
     # back to a depth-map technique on the same context: unchanged results
     po3, pg3 = util.params_pair("pcf", S)
     ctx.set_params(pg3)
@@ -213,7 +214,13 @@ def test_moment_chain_at_the_headline_size(tech):
         vis_o = O.visibility_moments(O.default_params(tech, S), cam, fm["light_mvp_b"], pos, nrm, fy)
         assert np.abs(vis - vis_o).max() <= (EXP_TOL if tech == "esm" else 0.0)
         fg = pos[..., 0] != 0
-        assert (vis[~fg] == 0).all() and (vis[fg] >= 0.25).all() and (vis[fg] <= 1.0).all() and 0.02 < (vis[fg] < 0.999).mean() < 0.98
+        # (ESM clamps to [shadowIntensity, 1]; Chebyshev's variance / (variance + d^2) does not: where the blurred moments give a
+        #  slightly negative variance the reference's formula leaves [0, 1], and so do the oracle and the kernel)
+        assert (vis[~fg] == 0).all() and np.isfinite(vis).all() and 0.02 < (vis[fg] < 0.999).mean() < 0.98
+        if tech == "esm":
+            assert (vis[fg] >= 0.25).all() and (vis[fg] <= 1.0).all()
+        else:
+            assert ((vis[fg] < 0.25) | (vis[fg] > 1.0)).mean() < 0.01
         if tech == "vsm":
             # first moment of the blurred map stays inside the range of the un-blurred one (convex combination + border zeros)
             assert fy[..., 0].max() <= mom[..., 0].max() * (1 + 1e-6) and fy[..., 0].min() >= 0.0
