@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 
 TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf_noncons": 5, "rpcf_cons": 6,
         "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11,
-        "vsm": 12, "esm": 13, "evsm": 14, "msm": 15}
+        "vsm": 12, "esm": 13, "evsm": 14, "msm": 15, "pcf_tricubic": 16}
 MOMENT_TECHS = ("vsm", "esm", "evsm", "msm")
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
        "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11,

@@ -442,7 +442,7 @@ int sgi_set_multi_light_common(sgi_ctx* ctx, const float m[16]) {
 
 int sgi_set_params(sgi_ctx* ctx, const sgi_params* p) {
   if (!ctx || !p) return SGI_ERR_INVALID;
-  if (p->technique < 0 || p->technique > SGI_TECH_MSM) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
+  if (p->technique < 0 || p->technique > SGI_TECH_PCF_TRICUBIC) { ctx->err = "sgi_set_params: unknown technique"; return SGI_ERR_INVALID; }
   if (p->kernel_order <= 0 || p->blocker_search_size <= 0 || p->kernel_size <= 0 || p->max_search < 0 || p->max_search > 4096 ||
       p->blocker_search_size > SGI_MAX_PCF_TAPS || p->kernel_size > SGI_MAX_PCF_TAPS) {
     ctx->err = "sgi_set_params: kernel sizes must be in 1..64";

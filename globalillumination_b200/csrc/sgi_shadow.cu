@@ -128,6 +128,45 @@ __device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, const Ta
   return illum / (float)(n * n);
 }
 
+// ---- Shadow.frag:41-84: cubic() weights and textureBicubic() on the NEAREST depth texture, .z; :86-116 with tricubicPCF == 1 ----
+__device__ __forceinline__ void cubic4(float v, float (&o)[4]) {
+  const float n0 = 1.0f - v, n1 = 2.0f - v, n2 = 3.0f - v, n3 = 4.0f - v;
+  const float s0 = n0 * n0 * n0, s1 = n1 * n1 * n1, s2 = n2 * n2 * n2, s3 = n3 * n3 * n3;
+  (void)s3;
+  const float x = s0;
+  const float y = s1 - 4.0f * s0;
+  const float z = s2 - 4.0f * s1 + 6.0f * s0;
+  const float w = 6.0f - x - y - z;
+  const float sixth = 1.0f / 6.0f;
+  o[0] = x * sixth; o[1] = y * sixth; o[2] = z * sixth; o[3] = w * sixth;
+}
+__device__ __forceinline__ float texture_bicubic_z(const Smap& sm, float u, float v) {
+  const float invx = 1.0f / sm.fw, invy = 1.0f / sm.fh;
+  float tx = u * sm.fw - 0.5f, ty = v * sm.fh - 0.5f;
+  const float fx = g_fract(tx), fy = g_fract(ty);
+  tx -= fx; ty -= fy;
+  float xc[4], yc[4];
+  cubic4(fx, xc); cubic4(fy, yc);
+  const float c0 = tx + -0.5f, c1 = tx + 1.5f, c2 = ty + -0.5f, c3 = ty + 1.5f;
+  const float s0 = xc[0] + xc[1], s1 = xc[2] + xc[3], s2 = yc[0] + yc[1], s3 = yc[2] + yc[3];
+  float o0 = c0 + xc[1] / s0, o1 = c1 + xc[3] / s1, o2 = c2 + yc[1] / s2, o3 = c3 + yc[3] / s3;
+  o0 *= invx; o1 *= invx; o2 *= invy; o3 *= invy;
+  const float sample0 = sm_fetch(sm, o0, o2), sample1 = sm_fetch(sm, o1, o2), sample2 = sm_fetch(sm, o0, o3), sample3 = sm_fetch(sm, o1, o3);
+  const float sx = s0 / (s0 + s1), sy = s2 / (s2 + s3);
+  return g_mix(g_mix(sample3, sample2, sx), g_mix(sample1, sample0, sx), sy);
+}
+__device__ __forceinline__ float pcf_tricubic(const VisArgs& a, const Smap& s, float4 c) {
+  const int n = a.pcf_n;
+  if (n <= 0) return 1.0f;
+  float illum = 0.0f;
+  for (int iw = 0; iw < n; iw++)                       // Shadow.frag:98-99: w outer, h inner
+    for (int ih = 0; ih < n; ih++) {
+      const float dfl = texture_bicubic_z(s, c.x + a.pcf_du[iw], c.y + a.pcf_dv[ih]);
+      if (c.z <= dfl) illum += 1.0f; else illum += a.p.shadow_intensity;
+    }
+  return illum / (float)(n * n);
+}
+
 // ---- PlausibleSoftShadow.frag:166-194: mean depth of the blockers (1.0 if none) ----
 template <int NB, bool SHARED>
 __device__ __forceinline__ float pcss_blockers(const VisArgs& a, const Smap& s, const TapSrc<SHARED>& src, float4 c) {
@@ -556,9 +595,10 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
   float shadow = pre_evaluation(a, vertex, normal);
   Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
-  if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS || TECH == SGI_TECH_RBSSM) {
+  if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS || TECH == SGI_TECH_RBSSM || TECH == SGI_TECH_PCF_TRICUBIC) {
     if (sc.w > 0.0f && shadow == 1.0f) {
       if (TECH == SGI_TECH_HARD) shadow = (c.z <= sm_fetch(s, c.x, c.y)) ? 1.0f : a.p.shadow_intensity;
+      else if (TECH == SGI_TECH_PCF_TRICUBIC) shadow = pcf_tricubic(a, s, c);
       else if (TECH == SGI_TECH_RBSSM) {                             // RBSSM.frag:1372-1373
         Rb r = {s, a.sx, a.sy, a.p.depth_threshold, a.p.max_search, a.p.shadow_intensity, 0, a.fw, a.fh, 0.0f};
         shadow = ss_rbssm(a, r, c);
@@ -896,6 +936,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   const int nk_taps = 2 * (int)(((float)P.kernel_size - 1.0f) * 0.5f) + 1;
   switch (P.technique) {
     case SGI_TECH_HARD: k_visibility<SGI_TECH_HARD, 0, 0><<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_PCF_TRICUBIC: k_visibility<SGI_TECH_PCF_TRICUBIC, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_PCF:
       if (staged) {
         if (a.pcf_n == 7) k_visibility_staged<SGI_TECH_PCF, 7, 0><<<grid, block, stage_bytes, st>>>(a);

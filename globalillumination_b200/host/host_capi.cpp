@@ -133,6 +133,7 @@ int sgh_app_set_technique(sgh_app* a, const char* name) {
   else if (n == "rbssm" || n == "RBSSM") p.RBSSM = true;
   else if (n == "edtsm" || n == "edtsm_noncons") p.EDTSM = true;
   else if (n == "edtsm_conservative" || n == "edtsm_cons") { p.EDTSM = true; p.conservative = true; }
+  else if (n == "tricubic" || n == "tricubicPCF" || n == "pcf_tricubic") { p.tricubicPCF = true; p.bilinearPCF = false; }   // shadowFilteringMenu case 1, main.cpp:672-675
   else if (n == "vsm" || n == "VSM") p.VSM = true;
   else if (n == "esm" || n == "ESM") p.ESM = true;
   else if (n == "evsm" || n == "EVSM") p.EVSM = true;

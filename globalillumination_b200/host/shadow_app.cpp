@@ -150,7 +150,7 @@ int ShadowApp::technique() const {
   if (p.ESM) return SGI_TECH_ESM;
   if (p.EVSM) return SGI_TECH_EVSM;
   if (p.MSM) return SGI_TECH_MSM;
-  if (p.tricubicPCF) return -1;                                         // bicubic PCF taps: not built
+  if (p.tricubicPCF && !p.bilinearPCF) return SGI_TECH_PCF_TRICUBIC;    // Shadow.frag:101-104: the bilinear assignment comes second and wins
   return SGI_TECH_PCF;
 }
 
@@ -200,7 +200,7 @@ int ShadowApp::renderGBuffer() {
 int ShadowApp::computeHardShadows() {
   if (!ctx) return SGI_ERR_NO_DEVICE;
   int tech = technique();
-  if (tech < 0) { err = "computeHardShadows: tricubic PCF is outside the shadow hot path (SURVEY.md C11)"; return SGI_ERR_INVALID; }
+  if (tech < 0) { err = "computeHardShadows: no technique selected"; return SGI_ERR_INVALID; }
   int rc = pushParams(tech);
   if (rc) return rc;
   rc = sgi_compute_visibility(ctx);

@@ -65,7 +65,8 @@ typedef enum sgi_technique {
   SGI_TECH_VSM = 12,          /* variance shadow mapping, chebyshevUpperBound       (Shadow.frag:118-141)            */
   SGI_TECH_ESM = 13,          /* exponential shadow mapping, c = 80, log-space blur (Shadow.frag:144-157)            */
   SGI_TECH_EVSM = 14,         /* exponential variance shadow mapping, c = 60        (Shadow.frag:160-175)            */
-  SGI_TECH_MSM = 15           /* Hamburger 4-moment shadow mapping, quantised       (Shadow.frag:168-220)            */
+  SGI_TECH_MSM = 15,          /* Hamburger 4-moment shadow mapping, quantised       (Shadow.frag:168-220)            */
+  SGI_TECH_PCF_TRICUBIC = 16  /* Shadow.frag PCF whose taps are textureBicubic() (tricubicPCF == 1, :41-84,101)          */
 } sgi_technique;
 
 typedef enum sgi_depth_func { SGI_DEPTH_LESS = 0, SGI_DEPTH_LEQUAL = 1 } sgi_depth_func;

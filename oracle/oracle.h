@@ -54,7 +54,8 @@ enum {
   ORC_TECH_VSM = 12,          /* Shadow.frag VSM==1  (variance shadow mapping)         */
   ORC_TECH_ESM = 13,          /* Shadow.frag ESM==1  (exponential)                     */
   ORC_TECH_EVSM = 14,         /* Shadow.frag EVSM==1 (exponential variance)            */
-  ORC_TECH_MSM = 15           /* Shadow.frag MSM==1  (Hamburger 4-moment)              */
+  ORC_TECH_MSM = 15,          /* Shadow.frag MSM==1  (Hamburger 4-moment)              */
+  ORC_TECH_PCF_TRICUBIC = 16  /* Shadow.frag PCF with tricubicPCF==1 (textureBicubic)  */
 };
 
 enum { ORC_DEPTH_LESS = 0, ORC_DEPTH_LEQUAL = 1 };

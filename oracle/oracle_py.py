@@ -16,7 +16,7 @@ REF_DIR = os.path.join(HERE, "_ref")
 TECH = {
     "hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4,
     "rpcf_noncons": 5, "rpcf_cons": 6, "rsmss": 7, "multi_hard": 8, "rbssm": 9, "edtsm_noncons": 10, "edtsm_cons": 11,
-    "vsm": 12, "esm": 13, "evsm": 14, "msm": 15,
+    "vsm": 12, "esm": 13, "evsm": 14, "msm": 15, "pcf_tricubic": 16,
 }
 MOMENT_TECHS = ("vsm", "esm", "evsm", "msm")
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1

@@ -206,6 +206,52 @@ static float pre_evaluation(const orc_camera* cam, float si, V4 vertex, V4 norma
 }
 
 /* ---- Shadow.frag:86-116 ---- */
+/* ---- Shadow.frag:41-84: cubic() weights and textureBicubic() on the NEAREST depth texture (4 fetches), .z component ---- */
+static void cubic4(float v, float o[4]) {
+  float n[4] = {1.0f - v, 2.0f - v, 3.0f - v, 4.0f - v}, s[4];
+  for (int k = 0; k < 4; k++) s[k] = n[k] * n[k] * n[k];
+  float x = s[0];
+  float y = s[1] - 4.0f * s[0];
+  float z = s[2] - 4.0f * s[1] + 6.0f * s[0];
+  float w = 6.0f - x - y - z;
+  const float sixth = 1.0f / 6.0f;
+  o[0] = x * sixth; o[1] = y * sixth; o[2] = z * sixth; o[3] = w * sixth;
+}
+static float texture_bicubic_z(const Smap* sm, float u, float v) {
+  float invx = 1.0f / sm->fw, invy = 1.0f / sm->fh;
+  float tx = u * sm->fw - 0.5f, ty = v * sm->fh - 0.5f;
+  float fx = glsl_fract(tx), fy = glsl_fract(ty);
+  tx -= fx; ty -= fy;
+  float xc[4], yc[4];
+  cubic4(fx, xc); cubic4(fy, yc);
+  float c0 = tx + -0.5f, c1 = tx + 1.5f, c2 = ty + -0.5f, c3 = ty + 1.5f;
+  float s0 = xc[0] + xc[1], s1 = xc[2] + xc[3], s2 = yc[0] + yc[1], s3 = yc[2] + yc[3];
+  float o0 = c0 + xc[1] / s0, o1 = c1 + xc[3] / s1, o2 = c2 + yc[1] / s2, o3 = c3 + yc[3] / s3;
+  o0 *= invx; o1 *= invx; o2 *= invy; o3 *= invy;
+  float sample0 = sm_fetch(sm, o0, o2), sample1 = sm_fetch(sm, o1, o2), sample2 = sm_fetch(sm, o0, o3), sample3 = sm_fetch(sm, o1, o3);
+  float sx = s0 / (s0 + s1), sy = s2 / (s2 + s3);
+  return glsl_mix(glsl_mix(sample3, sample2, sx), glsl_mix(sample1, sample0, sx), sy);
+}
+
+/* Shadow.frag:86-116 with tricubicPCF == 1, bilinearPCF == 0 (:101-102) */
+static float pcf_tricubic(const orc_params* p, const Smap* s, V4 c) {
+  float incrWidth = 1.0f / (float)p->shadow_map_width;
+  float incrHeight = 1.0f / (float)p->shadow_map_height;
+  float illuminationCount = 0;
+  float offset = (float)p->penumbra_size;
+  float stepSize = 2 * offset / (float)p->kernel_order;
+  int count = 0;
+  if (!(stepSize > 0.0f)) return 1.0f;
+  for (float w = -offset; w < offset; w += stepSize)
+    for (float h = -offset; h < offset; h += stepSize) {
+      float dfl = texture_bicubic_z(s, c.x + w * incrWidth, c.y + h * incrHeight);
+      if (c.z <= dfl) illuminationCount++;
+      else illuminationCount += p->shadow_intensity;
+      count++;
+    }
+  return illuminationCount / (float)count;
+}
+
 static float pcf(const orc_params* p, const Smap* s, V4 c) {
   float incrWidth = 1.0f / (float)p->shadow_map_width;
   float incrHeight = 1.0f / (float)p->shadow_map_height;
@@ -582,10 +628,11 @@ void orc_visibility(const orc_params* p, const orc_camera* cam, const float ligh
       V4 sc = mat4_mul_v4(light_mvp_b, vertex);
       V4 c = {sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w};
       float shadow = pre_evaluation(cam, p->shadow_intensity, vertex, normal);
-      if (tech == ORC_TECH_HARD || tech == ORC_TECH_PCF || tech == ORC_TECH_PCSS || tech == ORC_TECH_RBSSM) {
+      if (tech == ORC_TECH_HARD || tech == ORC_TECH_PCF || tech == ORC_TECH_PCSS || tech == ORC_TECH_RBSSM || tech == ORC_TECH_PCF_TRICUBIC) {
         if (sc.w > 0.0f && shadow == 1.0f) {               /* Shadow.frag:251 / PlausibleSoftShadow.frag:616 / RBSSM.frag:1372 */
           if (tech == ORC_TECH_HARD) shadow = (c.z <= sm_fetch(&s, c.x, c.y)) ? 1.0f : p->shadow_intensity;
           else if (tech == ORC_TECH_PCF) shadow = pcf(p, &s, c);
+          else if (tech == ORC_TECH_PCF_TRICUBIC) shadow = pcf_tricubic(p, &s, c);
           else if (tech == ORC_TECH_RBSSM) shadow = ss_rbssm(&r, c);
           else shadow = pcss(p, &s, c);
         }

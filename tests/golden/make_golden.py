@@ -158,6 +158,14 @@ def make_moments(scenes):
         for variant, si in (("default", 0.25), ("alt", 0.5)):
             p = O.default_params(tech, S, shadow_intensity=si)
             out[f"chain/{tech}/vis/{variant}"] = ref_visibility_moments(tech, fm, pos, nrm, fy, p, W, H, m_qi, t_q)
+    # tricubic PCF (Shadow.frag:41-84,101 with tricubicPCF == 1): same small frame with the plain depth map
+    sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    for variant, kw in (("default", {}), ("alt", dict(kernel_order=5, penumbra_size=2, shadow_intensity=0.5))):
+        p = O.default_params("pcf_tricubic", S, **kw)
+        u = shader_uniforms(fm, pos, nrm, sm, S, p)
+        u.update(dict(naive=np.int32(0), bilinearPCF=np.int32(0), tricubicPCF=np.int32(1), VSM=np.int32(0), ESM=np.int32(0),
+                      EVSM=np.int32(0), MSM=np.int32(0)))          # uniforms keep their last value between runs of one program
+        out[f"tricubic/vis/{variant}"] = O.ref_run_shader("shadow", u, W, H)[..., 0].copy()
     np.savez_compressed(os.path.join(HERE, "golden_moments.npz"), **out)
     print("golden_moments.npz", os.path.getsize(os.path.join(HERE, "golden_moments.npz")) // 1024, "KiB")
 

@@ -14,7 +14,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 SOFT_TOL = 1e-3
-TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss", "rbssm"]
+TECHS = ["hard", "pcf", "pcss", "rbsm_noncons", "rbsm_cons", "rpcf_noncons", "rpcf_cons", "rsmss", "rbssm", "pcf_tricubic"]
 
 
 @pytest.fixture(scope="module")

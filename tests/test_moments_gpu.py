@@ -226,3 +226,29 @@ def test_moment_chain_at_the_headline_size(tech):
             assert fy[..., 0].max() <= mom[..., 0].max() * (1 + 1e-6) and fy[..., 0].min() >= 0.0
     finally:
         app.close()
+
+
+@pytest.mark.gpu
+def test_host_selects_tricubic_pcf_like_the_filtering_menu():
+    """shadowFilteringMenu case 1 (ShadowMapping/src/main.cpp:672-675): tricubicPCF alone -> every PCF tap is textureBicubic();
+    with bilinearPCF set as well the bilinear assignment wins (Shadow.frag:101-104)."""
+    from globalillumination_b200 import hostapi, scenes
+    w = scenes.WORKLOADS["c1_teapot"]
+    W, H, S = w["W"] // 2, w["H"] // 2, w["S"] // 2
+    sc = scenes.golden_scene(w["golden"])
+    app = hostapi.App(0)
+    try:
+        app.set_scene(sc); app.configure(W, H, S); app.set_technique("tricubic")
+        app.display("shadow_mapping")
+        c = app.context()
+        vis, sm, pos, nrm = c.read("visibility"), c.read("shadow_map")[0], c.read("gbuf_pos"), c.read("gbuf_nrm")
+        fm = util.frame(sc, W, H, S)
+        cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+        vis_o = O.visibility(O.default_params("pcf_tricubic", S), cam, fm["light_mvp_b"], pos, nrm, sm)
+        assert util.bits_equal(vis, vis_o), util.describe_diff(vis, vis_o)
+        app.set_technique("pcf"); app.display("shadow_mapping")
+        vis_pcf = c.read("visibility")
+        assert util.bits_equal(vis_pcf, O.visibility(O.default_params("pcf", S), cam, fm["light_mvp_b"], pos, nrm, sm))
+        assert not util.bits_equal(vis, vis_pcf)
+    finally:
+        app.close()

@@ -96,3 +96,21 @@ def test_vsm_derivative_term_uses_the_quad_partner_on_the_same_plane():
                         assert abs(float(extra[j + dj, i + di]) - float(want)) <= 1e-7
     # edge texels still get a plausible (same-plane) derivative, not a jump to the clear value
     assert float(extra[cov].max()) < 1e-4
+
+
+@pytest.mark.parametrize("variant,kw", [("default", {}), ("alt", dict(kernel_order=5, penumbra_size=2, shadow_intensity=0.5))])
+def test_tricubic_pcf_matches_reference_shader_golden(variant, kw):
+    """Shadow.frag's PCF with tricubicPCF == 1: every tap is textureBicubic() (:41-84) on the NEAREST depth texture."""
+    g = util.golden(G)
+    W, H, S = int(g["W"]), int(g["H"]), int(g["S"])
+    fm = {k[3:]: g[k] for k in g if k.startswith("fm_")}
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    sc = util.scene("teapot")
+    sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    vis = O.visibility(O.default_params("pcf_tricubic", S, **kw), cam, fm["light_mvp_b"], pos, nrm, sm)
+    ref = g[f"tricubic/vis/{variant}"]
+    assert util.bits_equal(vis, ref), util.describe_diff(vis, ref)
+    plain = O.visibility(O.default_params("pcf", S, **kw), cam, fm["light_mvp_b"], pos, nrm, sm)
+    fg = pos[..., 0] != 0
+    assert not np.array_equal(vis, plain) and 0.05 < (ref[fg] < 1).mean() < 0.95      # it is a different filter, and it shadows
