@@ -124,10 +124,11 @@ def run_reference(args, w, cfg_path):
     W, H, S = w["W"], w["H"], w["S"]
     n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
     tech = {"pcss": "pcss", "montecarlo": "multi_hard", "naive": "hard", "smsr": "rbsm_noncons", "vsm": "vsm", "esm": "esm", "evsm": "evsm",
-            "msm": "msm"}[w["technique"]]
+            "msm": "msm", "pcf": "pcf"}[w["technique"]]
     p = O.default_params(tech, S, depth_threshold=float(sc["depth_threshold"]),
                          **{k2: w["params"][k1] for k1, k2 in (("blockerSearchSize", "blocker_search_size"), ("kernelSize", "kernel_size"),
-                                                                ("lightSourceRadius", "light_source_radius")) if k1 in w["params"]})
+                                                                ("lightSourceRadius", "light_source_radius"), ("kernelOrder", "kernel_order"),
+                                                                ("penumbraSize", "penumbra_size")) if k1 in w["params"]})
 
     def frame(anim):
         le = sc["light_eye"]
@@ -467,7 +468,8 @@ def main():
         px = w["W"] * w["H"]
         k = w["params"].get("kernelSize", 15)
         bs = w["params"].get("blockerSearchSize", 7)
-        taps = {"pcss": bs * bs + k * k, "montecarlo": n_l}.get(w["technique"], 1)
+        ko = w["params"].get("kernelOrder", 7)
+        taps = {"pcss": bs * bs + k * k, "montecarlo": n_l, "pcf": ko * ko}.get(w["technique"], 1)
         t_s = passes["vis_kernel"] * 1e-3
         shadow_pass = {"launch_ms": passes["vis_kernel"], "hbm_GBs": ab["visibility"] / t_s / 1e9, "hbm_frac": ab["visibility"] / t_s / 1e9 / peak,
                        "taps_per_lit_pixel": taps, "l2_taps_GBs_upper": 4.0 * taps * px / t_s / 1e9, "l2_read_peak_GBs": 9555.0,

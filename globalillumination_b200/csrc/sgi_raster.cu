@@ -603,7 +603,7 @@ struct TriQueue {
 };
 #define SGI_SPLIT_EXTRA 1536      // most CTAs a pass may add by subdividing hot tiles
 #define SGI_MAX_FULL 8
-#define SGI_SMALL_TRI 16           // bbox candidates up to which one thread rasterises the triangle alone
+#define SGI_SMALL_TRI 8           // bbox candidates up to which one thread rasterises the triangle alone
 
 template <int MODE>
 struct TileSink {                  // where fragments go: the tile payload in shared memory

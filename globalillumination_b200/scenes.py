@@ -50,6 +50,12 @@ for _t in ("vsm", "esm", "evsm", "msm"):
                                         scene=WORKLOADS["c2_sponza"]["scene"] + f"; moment shadow map ({_t}), blur order 7")
 
 
+# The other two parameter sets SURVEY 8(d) lists for config c2: (i) PCF order 7, penumbra 1 (ShadowMapping program, bilinearPCF) and
+# (ii) PCSS with kernelSize 7 (the state after the reference's "reset"); the headline c2_sponza is (iii), kernelSize 15.
+WORKLOADS["c2_sponza_pcf"] = dict(WORKLOADS["c2_sponza"], program="shadow_mapping", technique="pcf", params=dict(kernelOrder=7, penumbraSize=1),
+                                  scene=WORKLOADS["c2_sponza"]["scene"] + "; PCF 7x7")
+WORKLOADS["c2_sponza_pcss_k7"] = dict(WORKLOADS["c2_sponza"], params=dict(blockerSearchSize=7, kernelSize=7, lightSourceRadius=8),
+                                      scene=WORKLOADS["c2_sponza"]["scene"] + "; PCSS kernelSize 7")
 # PCSS where its filter loop really runs: on the Sponza-like light every blocker average is below the shader's 0.99 cut-off
 # (PlausibleSoftShadow.frag:368) and the pass ends after the blocker search; under the Dragon / Teapot light
 # (10,130,100) the light-space depths are 0.991-0.996 and penumbra pixels take all kernelSize^2 filter taps as well.
