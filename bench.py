@@ -433,10 +433,12 @@ def main():
 
     fps = (1 if lights_mode else world) * args.steps / (total_ms / 1e3)
     peak, peak_src = load_peaks()
-    ab = algorithmic_bytes(w, V, T, n_l)
+    # light shards: a rank's kernels process only its own lights (pass_ms are rank 0's), so the per-kernel bytes count those
+    n_l_rank = max(1, n_l // world) if lights_mode else n_l
+    ab = algorithmic_bytes(w, V, T, n_l_rank)
     kernel_of = {"tile_sv": ("k_tile<SVCOUNT> (shadow-volume prism counting)", ab["shadow_volume"]),
                  "vis_kernel": ("k_visibility (per-pixel shadow test/filter)", ab["visibility"]),
-                 "tile_depth": ("k_tile<DEPTH> (light-view tile rasteriser)", ab["shadow_map"] // max(1, n_l)),
+                 "tile_depth": ("k_tile<DEPTH> (light-view tile rasteriser)", ab["shadow_map"] // max(1, n_l_rank)),
                  "tile_gbuffer": ("k_tile<GBUFFER> (camera-view tile rasteriser + resolve)", ab["gbuffer"])}
     if "moment_filter" in ab:
         kernel_of["moment_filter"] = ("k_mom_filter (separable blur of the moment map, X + Y launches)", ab["moment_filter"] // 2)
@@ -446,7 +448,7 @@ def main():
     roof = None
     if cand:
         top = max(cand, key=cand.get)
-        calls = n_l if top == "tile_depth" else (2 if top == "moment_filter" else 1)
+        calls = n_l_rank if top == "tile_depth" else (2 if top == "moment_filter" else 1)
         per_launch_ms = cand[top] / calls
         achieved = kernel_of[top][1] / (per_launch_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None

@@ -10,6 +10,7 @@ python bench.py --workload c3_dragon --steps 500 > gpurun_out/r1_bench_c3_dragon
 python bench.py --workload c4_tree_sv --steps 60 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_c4_tree_sv.json 2>> gpurun_out/r1_bench.err
 python bench.py --workload c4_tree_sv_1080p --steps 60 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_c4_tree_sv_1080p.json 2>> gpurun_out/r1_bench.err
 python bench.py --workload c5_many_light --steps 60 --warmup 3 --no-cpu-baseline > gpurun_out/r1_bench_c5_1gpu.json 2>> gpurun_out/r1_bench.err
+for w in c2_sponza_pcf c2_sponza_pcss_k7 dragon_pcss; do python bench.py --workload $w --steps 500 > gpurun_out/r1_bench_$w.json 2>> gpurun_out/r1_bench.err; done
 for t in vsm esm evsm msm; do python bench.py --workload c2_sponza_$t --steps 1000 > gpurun_out/r1_bench_c2_$t.json 2>> gpurun_out/r1_bench.err; done
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file gpurun_out/r1_launches_c2_final.csv python bench.py --steps 16 --warmup 3 --no-cpu-baseline > gpurun_out/r1_ncu_launch.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file gpurun_out/r1_launches_c2_vsm.csv python bench.py --workload c2_sponza_vsm --steps 16 --warmup 3 --no-cpu-baseline > gpurun_out/r1_ncu_launch_vsm.log 2>&1
