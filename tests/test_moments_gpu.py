@@ -252,3 +252,49 @@ def test_host_selects_tricubic_pcf_like_the_filtering_menu():
         assert not util.bits_equal(vis, vis_pcf)
     finally:
         app.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tech", ["vsm", "msm"])
+def test_moment_chain_ragged_sizes_and_empty_scene(ctx, tech):
+    """Non-square shadow map, window sizes that are no multiple of the CTA footprint, a window LARGER than the map (the blur then
+    magnifies), degenerate / NaN triangles, and a scene without triangles: cleared moment target (0,0,0,1), its blur, and what
+    Shadow.frag makes of it."""
+    from globalillumination_b200 import capi
+    sc = util.scene("teapot")
+    W, H, SW, SH = 333, 217, 200, 120
+    fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], sc["light_eye"], sc["light_at"], W, H, SW, SH)
+    po, pg = util.params_pair(tech, SW, shadow_map_height=SH, kernel_order=9)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], SW, SH)
+    ctx.set_params(pg)
+    ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    mom, fy, vis = ctx.read("moments"), ctx.read("moments_filtered"), ctx.read("visibility")
+    assert mom.shape == (SH, SW, 4) and fy.shape == (H, W, 4)
+    mom_o = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], SW, SH, tech)
+    assert util.bits_equal(mom, mom_o), util.describe_diff(mom, mom_o)
+    fy_o = O.filter_shadow_map(mom_o, W, H, 9, tech)
+    assert util.bits_equal(fy, fy_o), util.describe_diff(fy, fy_o)
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o = O.visibility_moments(po, cam, fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), fy_o)
+    ok = ~np.isnan(vis_o)
+    assert np.array_equal(np.isnan(vis), ~ok) and util.bits_equal(vis[ok], vis_o[ok]), util.describe_diff(vis[ok], vis_o[ok])
+    # degenerate triangles, a NaN vertex, a triangle behind the light
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [np.nan, 0, 0], [0, 500, 900], [1, 500, 900], [0, 501, 900]], np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (7, 1))
+    idx = np.array([[0, 0, 1], [0, 1, 2], [3, 1, 2], [4, 5, 6]], np.int32)
+    ctx.set_mesh(xyz, nrm, idx)
+    ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    mom_d = O.raster_moments(xyz, idx, fm["light_mvp"], SW, SH, tech)
+    assert util.bits_equal(ctx.read("moments"), mom_d)
+    assert util.bits_equal(ctx.read("moments_filtered"), O.filter_shadow_map(mom_d, W, H, 9, tech))
+    # no triangles at all
+    ctx.set_mesh(xyz, nrm, np.zeros((0, 3), np.int32))
+    ctx.render_shadow_map(); ctx.filter_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    mom_e = ctx.read("moments")
+    assert (mom_e == np.array([0, 0, 0, 1], np.float32)).all()
+    assert util.bits_equal(ctx.read("moments_filtered"), O.filter_shadow_map(mom_e, W, H, 9, tech))
+    assert (ctx.read("visibility") == 0.0).all()                       # every pixel is background
+    # restore a valid mesh for the tests that follow on this context
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
