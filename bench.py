@@ -389,6 +389,26 @@ def main():
                 passes[name] = ms / n * (n / min(args.steps, 100))       # ms per frame
         ctx.enable_timing(False)
 
+        # ---- secondary figure, PCSS only: the same loop with the exact early-out of the blocker search switched on
+        #      (sgi_set_option "pcss_early_out": bit-identical results, off by default so that `value` counts every tap) ----
+        early = None
+        if w["technique"] == "pcss" and not lights_mode:
+            ctx.set_option("pcss_early_out", 1)
+            n_e = min(args.steps, 500)
+            for k in range(5):
+                frame(); app.step_animation(anim_stride)
+            ctx.synchronize()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_e)]
+            for k in range(n_e):                   # timed exactly like the headline loop: L2 flush outside each event pair
+                flush.zero_()
+                evs[k][0].record(stream); frame(); evs[k][1].record(stream)
+                app.step_animation(anim_stride)
+            ctx.synchronize()
+            ms_e = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+            ctx.set_option("pcss_early_out", 0)
+            early = {"value": world * n_e / (ms_e / 1e3), "unit": "frames/s", "steps": n_e,
+                     "note": "option pcss_early_out = 1: pixels with light-space depth in (0, 0.989) return 1.0 without taps (provably the program's result, bit-identical); not the headline"}
+
         # ---- e2e: host buffers in, host buffer out, every frame ----
         vis_bytes = w["W"] * w["H"] * 4
         E2E_DEPTH = 3            # frames in flight: the host queues frame k while k-1 renders and k-2 is copied out
@@ -492,6 +512,8 @@ def main():
                 "blocking_call_ms": 1e3 * e2e_blocking_s},
         "pass_ms": passes, "roofline": roof, "shadow_pass": shadow_pass,
     }
+    if early:
+        out["with_pcss_early_out"] = early
     if not args.no_cpu_baseline and world == 1:
         a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup = 3, 1
         ref = run_reference(a2, w, cfg_path)

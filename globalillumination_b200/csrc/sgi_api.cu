@@ -811,6 +811,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "borrow_pinned")) ctx->borrow_pinned = value ? 1 : 0;
   else if (!strcmp(name, "sv_tile_cull")) ctx->sv_tile_cull = value ? 1 : 0;
   else if (!strcmp(name, "rbssm_compact")) ctx->rbssm_compact = value ? 1 : 0;
+  else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_threads")) {
     if (value != 0 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;

@@ -27,6 +27,7 @@ struct VisArgs {
   float pcf_du[SGI_MAX_PCF_TAPS], pcf_dv[SGI_MAX_PCF_TAPS];   // pcf_off[k]*incrWidth, pcf_off[k]*incrHeight   (Shadow.frag:104)
   float bs_q[SGI_MAX_PCF_TAPS]; int bs_w0, bs_n;              // (float(w)*blockerSearchWidth)/filterWidth      (PlausibleSoftShadow.frag:180)
   const float4* trans; int N; size_t layer;
+  int pcss_early_out;      // option "pcss_early_out" (validated on the host): see pcss_t
 };
 
 struct Smap { const float* __restrict__ d; int w, h; float fw, fh; };
@@ -251,8 +252,16 @@ __device__ __forceinline__ float pcss_filter(const VisArgs& a, const Smap& s, co
   return illum / (float)(p.kernel_size * p.kernel_size);
 }
 
+// Option "pcss_early_out": for 0 < z < 0.989 the program's result is 1.0 whatever the shadow map holds, so no tap is needed.
+// Proof, in the shader's own fp32 terms: every blocker depth d satisfies 0 <= d < z (the maps hold [0,1], border taps 0), so the
+// fp32 mean of up to 64x64 of them is below z(1 + 4096 eps) < 0.98925 < 0.99, computePenumbraWidth (PlausibleSoftShadow.frag:368)
+// returns 0 and the step size 0 ends the program with 1.0 (:386); without blockers the mean is 1, the width
+// ((z - 1) / 1) * lightSourceRadius * zNear / z is <= 0 for z in (0, 1) and the non-negative parameters the host checked, and
+// the step size <= 0 ends it with 1.0 as well.  (under a near light this is every pixel.)
+#define SGI_PCSS_EARLY_Z 0.989f
 template <int NB, int NK>
 __device__ __forceinline__ float pcss_t(const VisArgs& a, const Smap& s, float4 c) {
+  if (a.pcss_early_out && c.z > 0.0f && c.z < SGI_PCSS_EARLY_Z) return 1.0f;
   const TapSrc<false> g = {s.d, s.w, 0, 0};
   const float avg = pcss_blockers<NB, false>(a, s, g, c);
   const float pw = pcss_penumbra(a.p, avg, c.z);
@@ -863,6 +872,8 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   a.pcf_n = ctx->pcf_n; a.rpcf_n = ctx->rpcf_n;
   for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
   a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
+  a.pcss_early_out = (ctx->pcss_early_out && ctx->params.light_source_radius >= 0 && ctx->params.z_near >= 0 && ctx->params.kernel_size > 0 &&
+                      ctx->params.blocker_search_size <= SGI_MAX_PCF_TAPS && !ctx->vis_staged) ? 1 : 0;
   {
     volatile float incrWidth = 1.0f / (float)ctx->SW, incrHeight = 1.0f / (float)ctx->SH;      // Shadow.frag:89-90
     for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) {

@@ -227,6 +227,9 @@ int sgi_unregister_host(void* host_ptr);
  *   "tile_order"      1 (default) tile CTAs are launched busiest tile first, 0 = in raster order
  *   "tile_split"      subdivision threshold of hot tiles in list records (default 256, 0 = off)
  *   "rbssm_compact"   1 (default) RBSSM as work list + one warp per penumbra pixel, 0 = one thread per pixel
+ *   "pcss_early_out"  0 (default) every PCSS pixel runs its blocker search as the shader does, 1 = pixels whose light-space depth
+ *                     is in (0, 0.989) return 1.0 without a tap: provably what the program computes there (the 0.99 cut-off of
+ *                     PlausibleSoftShadow.frag:368), so results stay bit-identical; off by default so that timings count the taps
  *   "sv_tile_cull"    1 (default) shadow volumes: (prism, tile) pairs behind the tile's farthest scene depth are not listed
  *   "borrow_pinned"   0 (default) inputs are copied inside the call, 1 = page-locked inputs are read later by DMA */
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);

@@ -648,3 +648,39 @@ def test_albedo_target_and_phong_shading(ctx):
     cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
     img2_o = O.shade_phong(cam, 0.25, ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), None, ctx.read("visibility"))
     assert np.allclose(img2, img2_o, rtol=2e-6, atol=1e-7)
+
+
+def test_pcss_early_out_option_is_exact(ctx):
+    """Option "pcss_early_out": pixels with light-space depth in (0, 0.989) return 1.0 without taps.  The result must equal the
+    oracle's (which runs every tap) bit for bit - on the Sponza-like light, where the shortcut covers every pixel, under the Teapot
+    light, where it covers none, and with a light moved close enough that the depth range straddles the threshold."""
+    from globalillumination_b200 import hostapi, scenes
+    cfg = scenes.write_config("c2_sponza")
+    sponza = hostapi.load_scene(cfg)
+    teapot = util.scene("teapot")
+    near = dict(teapot)
+    near["light_eye"] = (np.asarray(teapot["light_eye"], np.float32) * np.float32(0.55)).astype(np.float32)      # depths around 0.989
+    hit = []
+    for sc, (W, H, S) in ((sponza, (480, 270, 512)), (teapot, (320, 180, 256)), (near, (320, 180, 256))):
+        for kw in (dict(), dict(kernel_size=7, blocker_search_size=5, light_source_radius=16)):
+            po, pg = util.params_pair("pcss", S, **kw)
+            fm = setup_frame(ctx, sc, W, H, S, pg)
+            ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+            plain = ctx.read("visibility").copy()
+            ctx.set_option("pcss_early_out", 1)
+            try:
+                ctx.compute_visibility()
+                fast = ctx.read("visibility").copy()
+            finally:
+                ctx.set_option("pcss_early_out", 0)
+            cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+            pos, nrm, sm = ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0]
+            vis_o = O.visibility(po, cam, fm["light_mvp_b"], pos, nrm, sm)
+            assert util.bits_equal(plain, vis_o), util.describe_diff(plain, vis_o)
+            assert util.bits_equal(fast, vis_o), util.describe_diff(fast, vis_o)
+            # which share of the foreground the shortcut applies to (light-space depth of the pixel)
+            p4 = pos.reshape(-1, 4).astype(np.float64) @ fm["light_mvp_b"].reshape(4, 4).astype(np.float64)
+            z = p4[:, 2] / p4[:, 3]
+            fg = pos.reshape(-1, 4)[:, 0] != 0
+            hit.append(float(((z > 0) & (z < 0.989))[fg].mean()))
+    assert hit[0] > 0.9 and hit[2] < 0.01 and 0.05 < hit[4] < 0.95, hit
