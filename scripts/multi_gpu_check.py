@@ -43,6 +43,20 @@ def main():
     ok &= same
     if rank == 0:
         print(f"tiles x{world}: gathered image == un-sharded image: {same} (strips {rects})", flush=True)
+    # ---- tiles with a pre-filtered technique (VSM): the moment target and its blur are replicated, each rank reconstructs its strip
+    app.set_rect(0, 0, 0, 0); app.set_technique("vsm")
+    app.display("shadow_mapping")
+    full = torch.from_numpy(ctx.read("visibility")).cuda()
+    app.set_rect(*rects[rank])
+    app.display("shadow_mapping")
+    ptr, nbytes = ctx.device_ptr("visibility")
+    ctx.synchronize()
+    vis = torch.as_tensor(DevView(ptr, nbytes // 4), device=f"cuda:{local}").view(H, W)
+    out = sharding.gather_strips(vis, rects)
+    same = bool(torch.equal(out, full))
+    ok &= same
+    if rank == 0:
+        print(f"tiles x{world}, VSM: gathered image == un-sharded image: {same}", flush=True)
     app.close()
     # ---- lights, 16 lights, 2048x1152, 1024^2 maps
     app = hostapi.App(local)
