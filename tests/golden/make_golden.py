@@ -64,6 +64,8 @@ def shader_uniforms(fm, pos, nrm, sm, S, p):
 def ref_visibility(tech, fm, pos, nrm, sm, S, p, W, H):
     shader, extra = SHADER_OF[tech]
     u = shader_uniforms(fm, pos, nrm, sm, S, p)
+    if shader == "shadow":      # uniforms keep their last value between runs of one program: clear the branches other runs may have set
+        u.update({k: np.int32(0) for k in ("VSM", "ESM", "EVSM", "MSM", "tricubicPCF")})
     u.update({k: np.int32(v) for k, v in extra.items()})
     return O.ref_run_shader(shader, u, W, H)[..., 0].copy()
 

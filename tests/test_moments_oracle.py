@@ -158,3 +158,64 @@ def test_closed_form_quad_shadow_with_moment_maps(tech):
     assert (vis[inside & ok] < 0.6).all(), float(vis[inside & ok].max())
     if tech == "vsm":
         assert np.abs(vis[inside] - 0.25).max() < 0.02
+
+
+def _make_golden_module():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(util.GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    return mg
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("tech,order", [("vsm", 5), ("esm", 9), ("evsm", 3), ("msm", 11)])
+def test_live_reference_shaders_on_fresh_inputs(tech, order):
+    """The golden comparisons again on another scene, a non-square map, a window that magnifies the map vertically, other
+    blur orders and shadow intensities - executing the reference's shader sources now (oracle/_ref)."""
+    mg = _make_golden_module()
+    m_q, m_qi = O.ref_moment_quantization(mg.MOMENT_TYPED)
+    t_q = np.array([0.0359558848, 0, 0, 0], np.float32)
+    # the light-view programs on other fragments
+    ti = mg.moment_texel_inputs(seed=23, W=17, H=9)
+    got = np.zeros((9, 17, 4), np.float32)
+    for j in range(9):
+        for i in range(17):
+            got[j, i] = O.moment_texel(tech, ti["zwin"][j, i], ti["zpx"][j, i], ti["zpy"][j, i], i & 1, j & 1)
+    ref = mg.ref_moment_texels(tech, ti, m_q, t_q)
+    assert util.bits_equal(got, ref), util.describe_diff(got, ref)
+    # blur and reconstruction
+    sc = util.scene("raptor")
+    W, H, SW, SH = 150, 130, 120, 72
+    fm = O.frame_matrices(sc["cam_eye"], sc["cam_at"], sc["light_eye"], sc["light_at"], W, H, SW, SH)
+    mom = O.raster_moments(sc["xyz"], sc["idx"], fm["light_mvp"], SW, SH, tech)
+    assert (mom[..., 0] != 0).mean() > 0.05
+    fx = O.filter_moments(mom, W, H, order, True, tech == "esm")
+    fx_r = mg.ref_filter_pass(mom, W, H, order, 1, tech)
+    assert util.bits_equal(fx, fx_r), util.describe_diff(fx, fx_r)
+    fy = O.filter_moments(fx, W, H, order, False, tech == "esm")
+    fy_r = mg.ref_filter_pass(fx_r, W, H, order, 0, tech)
+    assert util.bits_equal(fy, fy_r), util.describe_diff(fy, fy_r)
+    pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    p = O.default_params(tech, SW, shadow_map_height=SH, shadow_intensity=0.4, kernel_order=order)
+    vis = O.visibility_moments(p, cam, fm["light_mvp_b"], pos, nrm, fy)
+    vis_r = mg.ref_visibility_moments(tech, fm, pos, nrm, fy_r, p, W, H, m_qi, t_q)
+    assert util.bits_equal(vis, vis_r), util.describe_diff(vis, vis_r)
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_live_tricubic_pcf_on_fresh_inputs():
+    mg = _make_golden_module()
+    sc = util.scene("door")
+    W, H, S = 140, 100, 112
+    fm = util.frame(sc, W, H, S)
+    sm = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    pos, nrm, _ = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    p = O.default_params("pcf_tricubic", S, kernel_order=4, penumbra_size=3, shadow_intensity=0.1)
+    u = mg.shader_uniforms(fm, pos, nrm, sm, S, p)
+    u.update(dict(naive=np.int32(0), bilinearPCF=np.int32(0), tricubicPCF=np.int32(1), VSM=np.int32(0), ESM=np.int32(0),
+                  EVSM=np.int32(0), MSM=np.int32(0)))
+    ref = O.ref_run_shader("shadow", u, W, H)[..., 0]
+    vis = O.visibility(p, cam, fm["light_mvp_b"], pos, nrm, sm)
+    assert util.bits_equal(vis, np.ascontiguousarray(ref)), util.describe_diff(vis, ref)
