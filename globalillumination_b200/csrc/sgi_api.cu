@@ -171,6 +171,7 @@ int sgi_create(sgi_ctx** out, int device) {
   sgi_ctx* ctx = new (std::nothrow) sgi_ctx();
   if (!ctx) return SGI_ERR_NOMEM;
   ctx->device = device;
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->n_sm = v; }
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SGI_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
   if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -343,6 +344,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   ctx->V = V; ctx->T = T;
   mark_gbuffer_use(ctx);
   ctx->gbuffer_valid = ctx->shadow_map_valid = false;
+  ctx->moments_tech = ctx->filtered_tech = -1;        // the moment target / filtered map describe the previous geometry
   return SGI_OK;
 }
 
@@ -430,6 +432,7 @@ int sgi_set_lights(sgi_ctx* ctx, int32_t N, const float* light_mvp, const float*
   memcpy(ctx->light_pos, lpos, 12);
   ctx->trans_dirty = true;          // lightMVPTrans[] is uploaded lazily by the many-light pass (no sync on the single-light path)
   ctx->shadow_map_valid = false;
+  ctx->moments_tech = ctx->filtered_tech = -1;        // a moment target rendered for the previous light (possibly another map size) is stale
   return SGI_OK;
 }
 
@@ -466,7 +469,9 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
   if (!ctx->d_idx || ctx->N <= 0) { ctx->err = "sgi_render_shadow_map: set mesh and lights first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  {
+  if (!sgi_is_moment_tech(ctx->params.technique)) {
+    // (the moment pass writes SGI_BUF_MOMENTS, not the depth map: it must not switch depth-map instances, which would leave
+    //  shadow_map_valid pointing at a stale instance)
     int rc0 = prepare_target_write(ctx, 0, ctx->stream, true);      // the depth passes always produce whole maps
     if (rc0) return rc0;
   }
@@ -495,6 +500,7 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
     sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot, ctx->stream);
     SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
     ctx->moments_tech = ctx->params.technique; ctx->filtered_tech = -1;
+    ctx->moments_w = ctx->SW; ctx->moments_h = ctx->SH;
     return SGI_OK;
   }
   sgi_wait_reads_of(ctx, SGI_BUF_SHADOW_MAP, ctx->stream);
@@ -585,7 +591,7 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
 
 int sgi_filter_shadow_map(sgi_ctx* ctx) {
   if (!ctx) return SGI_ERR_INVALID;
-  if (!sgi_is_moment_tech(ctx->params.technique) || ctx->moments_tech != ctx->params.technique) {
+  if (!sgi_is_moment_tech(ctx->params.technique) || ctx->moments_tech != ctx->params.technique || ctx->moments_w != ctx->SW || ctx->moments_h != ctx->SH) {
     ctx->err = "sgi_filter_shadow_map: render the shadow map with a moment technique (VSM / ESM / EVSM / MSM) first";
     return SGI_ERR_INVALID;
   }
@@ -634,7 +640,8 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
     const int t = ctx->buf_read_ticket[SGI_BUF_VISIBILITY];
     const sgi_params& q = ctx->params;
     const bool whole = (q.rect_x1 <= q.rect_x0 || q.rect_y1 <= q.rect_y0) || (q.rect_x0 <= 0 && q.rect_y0 <= 0 && q.rect_x1 >= ctx->W && q.rect_y1 >= ctx->H);
-    if (t >= 0 && ctx->read_pending[t] && whole && cudaEventQuery(ctx->read_done[t]) == cudaErrorNotReady) {
+    // (not when the caller holds the buffer's device pointer: a swap would make that pointer alternate between frames)
+    if (t >= 0 && ctx->read_pending[t] && whole && !ctx->vis_exposed && cudaEventQuery(ctx->read_done[t]) == cudaErrorNotReady) {
       const size_t bytes = ctx->buf_bytes[SGI_BUF_VISIBILITY];
       if (ctx->vis_spare_bytes != bytes) {
         if (ctx->vis_spare) { sync_all_streams(ctx); cudaFree(ctx->vis_spare); }

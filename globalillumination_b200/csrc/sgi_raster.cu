@@ -4,19 +4,20 @@
 //   renderGBuffer()     ShadowMapping/src/main.cpp:363-372   (GBuffer.vert:12-23, GBuffer.frag:32-38)
 //   stencil pass        ShadowVolumes/src/main.cpp:154-172   (INCR_WRAP/DECR_WRAP on z-pass)
 //
-// Pipeline (all on one stream, no host round trip):
-//   k_setup      1 thread / source triangle: transform, clip (near/far + 16x guard band), snap to 1/256 px,
-//                integer edge set-up, depth plane, polygon offset -> 64-byte SgiRec (+ attribute record)
-//   k_bin<0>     1 thread / record (whole warp for triangles spanning > 4 tiles): count the 64x64 tiles the
-//                triangle really overlaps (exact edge / tile-corner test)
-//   k_scan_tiles exclusive sum of the per-tile counts, one CTA
-//   k_bin<1>     same walk, writes record ids into the per-tile lists
+// Pipeline (all on one stream, no host round trip, no memset):
+//   k_setup_bin  1 thread / source triangle: transform, clip (near/far + 16x guard band), snap to 1/256 px,
+//                integer edge set-up, depth plane, polygon offset -> 64-byte SgiRec (+ attribute record); the same
+//                thread then appends the record to the list of every 64x64 tile it really overlaps (exact edge /
+//                tile-corner test; the larger records of a warp are flattened into (record, tile) pairs walked by all
+//                32 lanes).  Lists are fixed-capacity segments (one atomic per pair): single pass, no count + scan + fill.
+//   k_order      one CTA: list lengths -> work items of the tile kernel (hot tiles subdivided, busiest first); snapshots
+//                and re-zeroes the binner's counters for the next pass
 //   k_tile<MODE> 1 CTA / tile: the tile lives in shared memory (u32 depth, u64 depth|prim key or i32 count);
 //                warps pull triangles off the tile's list, reject 8x4-pixel blocks of the bounding box 32 at
 //                a time (one block per lane, conservative corner test) and rasterise the surviving blocks
 //                with one lane per pixel (exact int64 edge functions, top-left rule); shared-memory atomics
-//                resolve visibility; the tile is written to HBM exactly once, coalesced (the clear is fused:
-//                there is no separate memset pass).
+//                resolve visibility; the tile is written to HBM exactly once (depth tiles: one bulk copy per row,
+//                cp.async.bulk shared -> global; the clear is fused: there is no separate memset pass).
 //
 // HBM traffic per pass = geometry once + every output texel once; depth never bounces
 // through global atomics.  Numerics follow DESIGN.md §3 to the bit (-fmad=false).
@@ -57,11 +58,12 @@ __device__ __forceinline__ CV clip_lerp(const CV& a, const CV& b, float da, floa
   return r;
 }
 
-__device__ int clip_polygon(CV* poly, int n, bool& clipped) {
+__device__ int clip_polygon(CV* poly, int n, bool& clipped, int skip_far) {
   CV tmp[10];
   float d[10];
   clipped = false;
   for (int p = 0; p < 6; p++) {
+    if (p == 1 && skip_far) continue;
     bool any_out = false;
     for (int i = 0; i < n; i++) { d[i] = plane_dist(poly[i], p); if (!(d[i] >= 0.0f)) any_out = true; }
     if (!any_out) continue;
@@ -93,12 +95,20 @@ __device__ __forceinline__ CV xform(const float* __restrict__ m, float x, float 
   return o;
 }
 
-struct SetupArgs {
+struct SetupBinArgs {
+  // set-up
   const float* xyz; const float* nrm; const float* rgb; const int32_t* idx; int T;
   float mvp[16];
   int W, H;
   int use_offset; float factor, units;
+  int no_far_clip;                               // depth clamp (shadow volumes, depth-fail mode): the far plane does not clip, depths saturate at 1
   SgiRec* rec; SgiRecAttr* attr; int32_t* ovf_base; int32_t* counters;
+  // binning
+  int tiles_x, tx0, ty0, tx1, ty1;               // tile grid pitch and the inclusive tile range of the job rectangle
+  int32_t* tile_cnt; int32_t* pairs; int cap;    // per-tile append cursor; list of tile t = pairs[t * cap .. t * cap + cap)
+  int32_t* big_list;                             // records spanning > SGI_BIG_TILES tiles: not binned, every tile CTA tests them (counters[3] = count)
+  const unsigned int* tile_zmax;                 // shadow volumes: largest scene depth of each tile (float bits), or null
+  int nperm;                                     // launched threads, coprime to 7919 (index permutation)
 };
 
 __device__ __forceinline__ void invalidate(SgiRec* r) {
@@ -111,9 +121,12 @@ __device__ __forceinline__ void invalidate(SgiRec* r) {
   *r = z;
 }
 
-__global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.T) return;
+// Set-up of source triangle t: writes its record (slot t) and the records of the extra fan triangles clipping produced
+// (consecutive slots from `base`), valid or invalidated.  Returns the number of fan triangles (0 = rejected; `first` is then
+// invalid) and the record of slot t in registers for the binning that follows.
+__device__ __forceinline__ int setup_triangle(const SetupBinArgs& a, int t, SgiRec& first, int& base) {
+  first.prim_front = -1;
+  base = -1;
   a.ovf_base[t] = -1;
   int i0 = a.idx[3 * t], i1 = a.idx[3 * t + 1], i2 = a.idx[3 * t + 2];
   CV poly[10];
@@ -135,11 +148,12 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
       if (!(v.w + v.y >= 0.0f)) o4++;
       if (!(v.w - v.y >= 0.0f)) o5++;
     }
-    if (o0 == 3 || o1 == 3 || o2 == 3 || o3 == 3 || o4 == 3 || o5 == 3) { invalidate(&a.rec[t]); return; }
+    if (a.no_far_clip) o1 = 0;
+    if (o0 == 3 || o1 == 3 || o2 == 3 || o3 == 3 || o4 == 3 || o5 == 3) { invalidate(&a.rec[t]); return 0; }
   }
   bool was_clipped;
-  int n = clip_polygon(poly, 3, was_clipped);
-  if (n < 3) { invalidate(&a.rec[t]); return; }
+  int n = clip_polygon(poly, 3, was_clipped, a.no_far_clip);
+  if (n < 3) { invalidate(&a.rec[t]); return 0; }
   float hw = (float)a.W * 0.5f, hh = (float)a.H * 0.5f;
   int32_t X[10], Y[10];
   float Z[10], IW[10];
@@ -149,11 +163,10 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
     Z[k] = nz * 0.5f + 0.5f;
     IW[k] = 1.0f / poly[k].w;
     float sx = xw * (float)SGI_SUBPIX, sy = yw * (float)SGI_SUBPIX;
-    if (!(fabsf(sx) < 1.0e9f) || !(fabsf(sy) < 1.0e9f) || !(fabsf(Z[k]) < 1.0e9f)) { invalidate(&a.rec[t]); return; }
+    if (!(fabsf(sx) < 1.0e9f) || !(fabsf(sy) < 1.0e9f) || !(fabsf(Z[k]) < 1.0e9f)) { invalidate(&a.rec[t]); return 0; }
     X[k] = __float2int_rn(sx);
     Y[k] = __float2int_rn(sy);
   }
-  int base = -1;
   if (n > 3) {
     base = a.T + atomicAdd(&a.counters[0], n - 3);
     a.ovf_base[t] = base;
@@ -198,6 +211,7 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
     r.pad0 = was_clipped ? 1 : 0;      // 0: attributes come straight from the source vertices (order in pad1)
     r.pad1 = (id1 == 1) ? 0 : 1;        // unclipped only: 1 = vertices 1 and 2 were swapped to make the record CCW
     a.rec[slot] = r;
+    if (f == 1) first = r;
     if (a.attr) {
       SgiRecAttr q;
       const int ids[3] = {id0, id1, id2};
@@ -225,19 +239,10 @@ __global__ void __launch_bounds__(128) k_setup(const SetupArgs a) {
       a.attr[slot] = q;
     }
   }
+  return n - 2;
 }
 
 // ---- binning -------------------------------------------------------------------------------------------------
-struct BinArgs {
-  const SgiRec* rec; const int32_t* counters; int32_t* counters_rw; int T;
-  int tiles_x, tiles_y, tx0, ty0, tx1, ty1;     // tile grid and the inclusive tile range of the job rectangle
-  int32_t* tile_cnt; const int32_t* tile_off; int32_t* tile_fill; int32_t* pairs; long long pair_cap;
-  int32_t* flags;                                // counters[1] = overflow flag
-  volatile int32_t* h_flags;                     // host-mapped: [0] sticky overflow, [1] largest total wanted
-  int32_t* big_list;                             // records spanning > SGI_BIG_TILES tiles: not binned, every tile CTA tests them (counters[3] = count)
-  const unsigned int* tile_zmax;                 // shadow volumes: largest scene depth of each tile (float bits), or null
-};
-
 // conservative triangle / tile overlap: for each edge evaluate at the tile corner that maximises it
 __device__ __forceinline__ bool tile_overlaps(const SgiRec& r, int tx, int ty, int W, int H) {
   long long cx0 = (long long)(tx << SGI_TILE_LOG2) * SGI_SUBPIX + SGI_SUBPIX / 2;
@@ -305,30 +310,42 @@ __global__ void __launch_bounds__(256) k_tile_zmax(const float* __restrict__ dep
 #define SGI_BIG_TILES 256
 #endif
 
-// One thread per record.  Records overlapping <= 4 tiles are handled by their thread with all (up to 4) atomics in
-// flight before the first dependent store.  The larger ones of a warp are flattened into one (record, tile) index
-// space that the 32 lanes walk together, 4 pairs per lane per trip, so a trip keeps 128 atomics in flight instead of
-// serialising one record after the other behind the atomics' latency.
-template <int FILL>
-__global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
+// Set-up and binning in one pass, one thread per source triangle.  A record overlapping <= 4 tiles is appended by its thread
+// with all (up to 4) atomics in flight before the first dependent store.  The larger ones of a warp are flattened into one
+// (record, tile) index space that the 32 lanes walk together, 4 pairs per lane per trip, so a trip keeps 128 atomics in
+// flight instead of serialising one record after the other behind the atomics' latency.  The extra fan triangles of a
+// clipped source triangle (rare) go through the same walk in further rounds, re-read from the records just written.
+// Lists are fixed-capacity segments: position = atomicAdd(cursor of the tile); entries beyond the capacity are dropped
+// and k_order reports the overflow (the frame is then re-run with larger lists: SGI_ERR_OVERFLOW protocol).
+__device__ __forceinline__ void list_append(const SetupBinArgs& a, int tile, int pos, int slot) {
+  if (pos < a.cap) a.pairs[(size_t)tile * a.cap + pos] = slot;
+}
+
+__global__ void __launch_bounds__(128) k_setup_bin(const SetupBinArgs a) {
   const int lane = threadIdx.x & 31;
-  const int nrec = a.T + a.counters[0];
-  // Records are dealt to threads through a multiplicative permutation of the index space: meshes list their large
+  const int W = a.W, H = a.H;
+  // Triangles are dealt to threads through a multiplicative permutation of the index space: meshes list their large
   // triangles (floors, walls) consecutively, and a warp holding 32 of them would walk thousands of (record, tile) pairs
-  // while the others idle; 7919 records apart, every warp gets the same mix.
-  const int nperm = gridDim.x * blockDim.x;                     // host guarantees gcd(nperm, 7919) == 1
-  for (int base = 0; base < nrec; base += nperm) {
-    const int slot = base + (int)(((long long)(blockIdx.x * blockDim.x + threadIdx.x) * 7919LL) % nperm);
-    SgiRec r;
-    r.prim_front = -1;
-    if (slot < nrec) r = a.rec[slot];
+  // while the others idle; 7919 triangles apart, every warp gets the same mix.
+  const int t = (int)(((long long)(blockIdx.x * blockDim.x + threadIdx.x) * 7919LL) % a.nperm);   // host guarantees gcd(nperm, 7919) == 1
+  SgiRec r;
+  r.prim_front = -1;
+  int base = -1, nf = 0;
+  if (t < a.T) nf = setup_triangle(a, t, r, base);
+  const int rounds = __reduce_max_sync(0xffffffffu, nf);
+  for (int f = 0; f < rounds; f++) {
+    int slot = t;
+    if (f > 0) {
+      r.prim_front = -1;
+      if (f < nf) { slot = base + f - 1; r = a.rec[slot]; }
+    }
     int bx0 = 0, by0 = 0, bw = 1, nt = 0;
     if (r.prim_front >= 0) {
       bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0); by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
       const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
       if (bx0 <= bx1 && by0 <= by1) { bw = bx1 - bx0 + 1; nt = bw * (by1 - by0 + 1); }
       if (nt > SGI_BIG_TILES) {        // e.g. the floor: listing it in thousands of tiles costs more than letting each tile test it
-        if (!FILL) a.big_list[atomicAdd(&a.counters_rw[3], 1)] = slot;
+        a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
         nt = 0;
       }
     }
@@ -345,19 +362,10 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
       }
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if (tiles[k] >= 0) {
-          if (!FILL) atomicAdd(&a.tile_cnt[tiles[k]], 1);
-          else pos[k] = atomicAdd(&a.tile_fill[tiles[k]], 1);
-        }
-      if (FILL) {
+        if (tiles[k] >= 0) pos[k] = atomicAdd(&a.tile_cnt[tiles[k]], 1);
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (tiles[k] >= 0) {
-            const long long q = (long long)a.tile_off[tiles[k]] + pos[k];
-            if (q < a.pair_cap) a.pairs[q] = slot;
-            else { a.flags[1] = 1; a.h_flags[0] = 1; }
-          }
-      }
+      for (int k = 0; k < 4; k++)
+        if (tiles[k] >= 0) list_append(a, tiles[k], pos[k], slot);
     }
     // ---- larger records of this warp, flattened
     const int mine = (nt > 4) ? nt : 0;
@@ -399,104 +407,141 @@ __global__ void __launch_bounds__(256) k_bin(const BinArgs a, int W, int H) {
       }
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (tiles[u] >= 0) {
-          if (!FILL) atomicAdd(&a.tile_cnt[tiles[u]], 1);
-          else pos[u] = atomicAdd(&a.tile_fill[tiles[u]], 1);
-        }
-      if (FILL) {
+        if (tiles[u] >= 0) pos[u] = atomicAdd(&a.tile_cnt[tiles[u]], 1);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (tiles[u] >= 0) {
-            const long long q = (long long)a.tile_off[tiles[u]] + pos[u];
-            if (q < a.pair_cap) a.pairs[q] = slots[u];
-            else { a.flags[1] = 1; a.h_flags[0] = 1; }
-          }
-      }
+      for (int u = 0; u < 4; u++)
+        if (tiles[u] >= 0) list_append(a, tiles[u], pos[u], slots[u]);
     }
   }
 }
 
-// exclusive scan of the per-tile counts (n <= a few 10^4) in one CTA; publishes the total to the host-mapped flag word.
-// Also emits the work items of the tile kernel (one CTA each):
-//  * adaptive subdivision: a tile whose list is much longer than the even share of the pass (total / (8 x 148 CTAs))
+// After the binner: one CTA turns the list lengths into the work items of the tile kernel (one CTA each).
+//  * list length the tile kernel reads = min(cursor, capacity); the longest list ever wanted goes to the host-mapped flag word
+//    (the host sizes the capacity from it), a cursor beyond the capacity raises the sticky overflow flag;
+//  * the binner's live counters (append cursors, clipped-extra slots, big-triangle count) are snapshotted and zeroed here,
+//    so the next pass on this scratch set needs no memset;
+//  * adaptive subdivision: a tile whose list is much longer than the even share of the pass (total / (8 x SM count CTAs))
 //    is split into 4 sub-tiles of 32x32 or 16 of 16x16 pixels, each rasterised by its own CTA from the same list, so
 //    that hot tiles (a dense object in a few tiles, shadow-volume prisms at low resolution) do not serialise the pass
 //    on one SM.  The item count is capped by the launched grid (max_items): the threshold doubles until it fits.
 //  * launch order: busiest first (counting sort on a half-octave bucket of the item's weight), so that the long items
 //    start early and the short ones fill the tail (longest-processing-time-first; the order is irrelevant to the result).
 // item = tile | level << 20 | sub << 22, level 0/1/2 = 64/32/16-pixel region, sub = sy * (1 << level) + sx.
+// Histogram and scatter use one shared-memory atomic per distinct key per warp (__match_any_sync): most tiles of a pass fall
+// into two or three buckets, and same-address shared atomics serialise (the previous form of this kernel, one atomic per
+// tile, took 36 us on the 16 384 tiles of an 8192^2 map).
 __device__ __forceinline__ int split_level(int c, int w) { return c > 8 * (long long)w ? 2 : (c > 2 * (long long)w ? 1 : 0); }
 __device__ __forceinline__ int weight_bucket(int c) {
   const int l = 31 - __clz(c | 1);
   return c < 2 ? c : 2 * l + ((c >> (l - 1)) & 1);
 }
-__global__ void __launch_bounds__(1024) k_scan_tiles(const int32_t* __restrict__ cnt, int32_t* __restrict__ off, int n,
-                                                     int32_t* counters, volatile int32_t* h_flags, int32_t* d_sticky, int32_t* __restrict__ order,
-                                                     int tiles_x, int tx0, int ty0, int gx, int gy, int busiest_first,
-                                                     int max_items, int split_floor) {
-  typedef cub::BlockScan<int, 1024> BlockScan;
-  __shared__ typename BlockScan::TempStorage tmp;
-  __shared__ int hist[64];
+struct OrderArgs {
+  int32_t* tile_cnt; int32_t* tile_n; int n_tiles; int cap;
+  int32_t* counters; int32_t* snap; volatile int32_t* h_flags; int32_t* d_sticky; int size_class;
+  int32_t* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
+};
+#define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
+__global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
+  __shared__ int hist[SGI_ORDER_KEYS];
+  __shared__ int red_sum[32], red_max[32];
   __shared__ int s_items, s_w;
-  const int per = (n + 1023) / 1024;
-  const int beg = threadIdx.x * per, end = min(beg + per, n);
-  int sum = 0;
-  for (int i = beg; i < end; i++) sum += cnt[i];
-  int excl, total;
-  BlockScan(tmp).ExclusiveSum(sum, excl, total);
-  for (int i = beg; i < end; i++) { off[i] = excl; excl += cnt[i]; }
-  if (threadIdx.x == 0) {
-    counters[2] = total;
-    // largest list size ever wanted (the host grows d_pairs from it).  The running maximum lives in device memory and the
-    // host-mapped word is only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind whatever DMA
-    // traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
-    if (total > d_sticky[0]) { d_sticky[0] = total; h_flags[1] = total; }
-    s_w = split_floor > 0 ? max(split_floor, total / (8 * 148)) : 0x7FFFFFF;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- list lengths, totals, re-zero the cursors
+  int sum = 0, mx = 0;
+  for (int i = tid; i < a.n_tiles; i += 1024) {
+    const int c = a.tile_cnt[i];
+    const int n = min(c, a.cap);
+    a.tile_n[i] = n;
+    if (c) a.tile_cnt[i] = 0;
+    sum += n; mx = max(mx, c);
   }
-  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
-  const int nl = gx * gy;
+  sum = __reduce_add_sync(0xffffffffu, sum); mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) { red_sum[warp] = sum; red_max[warp] = mx; }
+  for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
+  __syncthreads();
+  if (warp == 0) {
+    int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
+    if (lane == 0) {
+      a.snap[0] = a.counters[0]; a.snap[3] = a.counters[3]; a.snap[2] = s2;
+      a.counters[0] = 0; a.counters[3] = 0;
+      // longest list ever wanted (the host sizes the capacity from it).  The running maximum lives in device memory and the
+      // host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind whatever DMA
+      // traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
+      if (m2 > a.d_sticky[a.size_class]) { a.d_sticky[a.size_class] = m2; a.h_flags[1 + a.size_class] = m2; }
+      if (m2 > a.cap) a.h_flags[0] = 1;
+      s_w = a.split_floor > 0 ? max(a.split_floor, s2 / (8 * a.n_sm)) : 0x7FFFFFF;
+    }
+  }
+  const int nl = a.gx * a.gy;
+  // per-thread tiles of the job rectangle: i = tid + 1024 k  (the same tiles in all three loops below)
   for (;;) {                                          // largest subdivision that fits the launched grid
     __syncthreads();
-    if (threadIdx.x == 0) s_items = 0;
+    if (tid == 0) s_items = 0;
     __syncthreads();
     const int w = s_w;
     int local = 0;
-    for (int i = threadIdx.x; i < nl; i += 1024)
-      local += 1 << (2 * split_level(cnt[(ty0 + i / gx) * tiles_x + tx0 + i % gx], w));
-    if (local) atomicAdd(&s_items, local);
+    for (int i = tid; i < nl; i += 1024) {
+      const int y = i / a.gx, x = i - y * a.gx;
+      local += 1 << (2 * split_level(a.tile_n[(a.ty0 + y) * a.tiles_x + a.tx0 + x], w));
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0 && local) atomicAdd(&s_items, local);
     __syncthreads();
-    if (s_items <= max_items || w >= 0x7FFFFFF) break;
+    if (s_items <= a.max_items || w >= 0x7FFFFFF) break;
     __syncthreads();
-    if (threadIdx.x == 0) s_w = w >= 0x3FFFFFF ? 0x7FFFFFF : 2 * w;
+    if (tid == 0) s_w = w >= 0x3FFFFFF ? 0x7FFFFFF : 2 * w;
   }
   const int w = s_w;
-  for (int i = threadIdx.x; i < nl; i += 1024) {
-    const int c = cnt[(ty0 + i / gx) * tiles_x + tx0 + i % gx];
-    const int lv = split_level(c, w);
-    atomicAdd(&hist[busiest_first ? weight_bucket(c >> lv) : 0], 1 << (2 * lv));
+  // ---- histogram of the items over (weight bucket, level)
+  for (int i0 = 0; i0 < nl; i0 += 1024) {
+    const int i = i0 + tid;
+    int key = -1;
+    if (i < nl) {
+      const int y = i / a.gx, x = i - y * a.gx;
+      const int c = a.tile_n[(a.ty0 + y) * a.tiles_x + a.tx0 + x];
+      const int lv = split_level(c, w);
+      key = (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv;
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&hist[key], __popc(grp) << (2 * (key & 3)));
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     int run = 0;
-    for (int b = 63; b >= 0; b--) { const int h = hist[b]; hist[b] = run; run += h; }
-    counters[4] = min(run, max_items);
+    for (int k = SGI_ORDER_KEYS - 1; k >= 0; k--) { const int h = hist[k]; hist[k] = run; run += h; }
+    a.snap[4] = min(run, a.max_items);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nl; i += 1024) {
-    const int tile = (ty0 + i / gx) * tiles_x + tx0 + i % gx;
-    const int c = cnt[tile];
-    const int lv = split_level(c, w), nsub = 1 << (2 * lv);
-    const int at = atomicAdd(&hist[busiest_first ? weight_bucket(c >> lv) : 0], nsub);
-    for (int sidx = 0; sidx < nsub; sidx++)
-      if (at + sidx < max_items) order[at + sidx] = tile | (lv << 20) | (sidx << 22);
+  // ---- scatter
+  for (int i0 = 0; i0 < nl; i0 += 1024) {
+    const int i = i0 + tid;
+    int key = -1, tile = 0;
+    if (i < nl) {
+      const int y = i / a.gx, x = i - y * a.gx;
+      tile = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
+      const int c = a.tile_n[tile];
+      const int lv = split_level(c, w);
+      key = (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv;
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(grp) - 1;
+    int at = 0;
+    const int lv = key & 3, nsub = 1 << (2 * lv);
+    if (key >= 0 && lane == leader) at = atomicAdd(&hist[key], __popc(grp) * nsub);
+    at = __shfl_sync(0xffffffffu, at, leader);
+    if (key >= 0) {
+      at += __popc(grp & ((1u << lane) - 1u)) * nsub;
+      for (int sidx = 0; sidx < nsub; sidx++)
+        if (at + sidx < a.max_items) a.order[at + sidx] = tile | (lv << 20) | (sidx << 22);
+    }
   }
 }
 
 // ---- per-tile rasterisation ----------------------------------------------------------------------------------
 struct TileArgs {
   const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
-  const int32_t* tile_off; const int32_t* tile_order; const int32_t* pairs; long long pair_cap;
-  const int32_t* big_list; const int32_t* counters;      // counters[3] = number of un-binned big triangles
+  const int32_t* tile_n; const int32_t* tile_order; const int32_t* pairs; int cap;   // list of tile t: pairs[t * cap .. + tile_n[t])
+  const int32_t* big_list; const int32_t* counters;      // k_order's snapshot: [3] = number of un-binned big triangles, [4] = work items
   int tiles_x, tx0, ty0;
   int W, H, rx0, ry0, rx1, ry1;
   const float* xyz; const float* nrm; const int32_t* idx;
@@ -650,17 +695,15 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31;
   if ((int)blockIdx.x >= a.counters[4]) return;                  // the grid is an upper bound of the item count
-  const int item = a.tile_order[blockIdx.x];                     // work items of k_scan_tiles, busiest first
+  const int item = a.tile_order[blockIdx.x];                     // work items of k_order, busiest first
   const int tile = item & 0xFFFFF, level = (item >> 20) & 3, sub = item >> 22;
   const int rs_log2 = SGI_TILE_LOG2 - level, rs = 1 << rs_log2;  // this CTA's region of the tile: rs x rs pixels at (qx0,qy0)
   const int qx0 = (sub & ((1 << level) - 1)) << rs_log2, qy0 = (sub >> level) << rs_log2;
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
-  long long beg = a.tile_off[tile], end = a.tile_off[tile + 1];
-  if (end > a.pair_cap) end = a.pair_cap;
-  if (beg > end) beg = end;
-  const int nlisted = (int)(end - beg), nbig = a.counters[3];
+  const int32_t* __restrict__ list = a.pairs + (size_t)tile * a.cap;
+  const int nlisted = a.tile_n[tile], nbig = a.counters[3];
   const int nitems = nlisted + nbig;                           // this tile's list, then the un-binned big triangles
   const bool empty = nitems == 0;                              // nothing can touch the tile: the flush writes the clear values
 
@@ -713,7 +756,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     __syncthreads();                                           // payload initialised / previous chunk drained
     if (base + tid < nitems) {
       const int it = base + tid;
-      const SgiRec* rp = &a.rec[it < nlisted ? __ldg(&a.pairs[beg + it]) : __ldg(&a.big_list[it - nlisted])];
+      const SgiRec* rp = &a.rec[it < nlisted ? __ldg(&list[it]) : __ldg(&a.big_list[it - nlisted])];
       const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rp) + 3);
       const int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
       const int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
@@ -810,12 +853,41 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
         const float z0 = tq.z0[qi], dz1 = tq.dz1[qi], dz2 = tq.dz2[qi], ia = tq.ia[qi], zoff = tq.zoff[qi];
         const int meta = tq.meta[qi];
         const int dx1 = X0 - X2, dy1 = Y0 - Y2, dx2 = X1 - X0, dy2 = Y1 - Y0;
-        for (int q = tid; q < rs * rs; q += NT) {
-          const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
-          const int PX = (ox + lx) * SGI_SUBPIX + SGI_SUBPIX / 2, PY = (oy + ly) * SGI_SUBPIX + SGI_SUBPIX / 2;
-          const long long E1 = (long long)dx1 * (long long)(PY - Y2) - (long long)dy1 * (long long)(PX - X2);
-          const long long E2 = (long long)dx2 * (long long)(PY - Y0) - (long long)dy2 * (long long)(PX - X0);
-          sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+        // The edge values the depth needs are affine in the pixel position with integer coefficients: one pixel to the right
+        // is -256 dy, one row up +256 dx.  Where every value over the region stays below 2^52 in magnitude (affine: checked
+        // with the value at the region origin plus the largest possible excursion) they are exact in double precision, so a
+        // thread steps from row to row with one double add per edge instead of two wide multiplies, and (float) of the exact
+        // double rounds once, to the same float as (float) of the 64-bit integer: identical depths, a quarter of the instructions.
+        const int PXo = (ox + qx0) * SGI_SUBPIX + SGI_SUBPIX / 2, PYo = (oy + qy0) * SGI_SUBPIX + SGI_SUBPIX / 2;
+        const long long E1o = (long long)dx1 * (long long)(PYo - Y2) - (long long)dy1 * (long long)(PXo - X2);
+        const long long E2o = (long long)dx2 * (long long)(PYo - Y0) - (long long)dy2 * (long long)(PXo - X0);
+        const long long span = (long long)(SGI_TILE - 1) * SGI_SUBPIX;
+        const long long m1 = llabs(E1o) + span * (llabs((long long)dx1) + llabs((long long)dy1));
+        const long long m2 = llabs(E2o) + span * (llabs((long long)dx2) + llabs((long long)dy2));
+        if (m1 < (1LL << 52) && m2 < (1LL << 52)) {
+          // NT is a multiple of the region width: a thread keeps its column and moves up NT / rs rows per step
+          const int lxr = tid & (rs - 1), lyr0 = tid >> rs_log2, ystep = NT >> rs_log2;
+          double e1 = (double)(E1o - (long long)lxr * (256LL * dy1) + (long long)lyr0 * (256LL * dx1));
+          double e2 = (double)(E2o - (long long)lxr * (256LL * dy2) + (long long)lyr0 * (256LL * dx2));
+          const double s1 = (double)((long long)ystep * (256LL * dx1)), s2 = (double)((long long)ystep * (256LL * dx2));
+          const int lx = qx0 + lxr;
+          for (int lyr = lyr0; lyr < rs; lyr += ystep) {
+            const float b1 = (float)e1 * ia, b2 = (float)e2 * ia;
+            float z = (z0 + b1 * dz1) + b2 * dz2;
+            z = z + zoff;
+            if (!(z >= 0.0f)) z = 0.0f;
+            if (z > 1.0f) z = 1.0f;
+            sink.fragment(lx, qy0 + lyr, z, meta);
+            e1 += s1; e2 += s2;
+          }
+        } else {
+          for (int q = tid; q < rs * rs; q += NT) {
+            const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
+            const int PX = (ox + lx) * SGI_SUBPIX + SGI_SUBPIX / 2, PY = (oy + ly) * SGI_SUBPIX + SGI_SUBPIX / 2;
+            const long long E1 = (long long)dx1 * (long long)(PY - Y2) - (long long)dy1 * (long long)(PX - X2);
+            const long long E2 = (long long)dx2 * (long long)(PY - Y0) - (long long)dy2 * (long long)(PX - X0);
+            sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+          }
         }
       }
     }
@@ -893,10 +965,30 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     }
     __syncthreads();                                           // every warp is done with this chunk's queue
   }
+  if (MODE == SGI_MODE_DEPTH) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was written through the generic proxy
   __syncthreads();
 
   // ---- write the tile to HBM exactly once ------------------------------------------------------------------
   if (MODE == SGI_MODE_DEPTH) {
+    const int gx0 = ox + qx0, gy0 = oy + qy0;
+    const int wv = min(rs, a.W - gx0);                          // columns of the region inside the map
+    // Whole rows of the region inside the job rectangle, 16-byte aligned: one bulk copy per row, shared -> global, issued by
+    // one thread per row (cp.async.bulk, the TMA engine's linear form: the row pitch of 72 words that keeps the raster free of
+    // bank conflicts rules out a 2-D tensor box).  The SM's load/store path carries no flush traffic and the other threads are done.
+    const bool bulk = !empty && (a.W & 3) == 0 && (wv & 3) == 0 && wv > 0 && gx0 >= a.rx0 && gx0 + wv <= a.rx1;
+    if (bulk) {
+      if (tid < rs) {
+        const int y = gy0 + tid;
+        if (y >= a.ry0 && y < a.ry1) {
+          const unsigned src = (unsigned)__cvta_generic_to_shared(&zt[(qy0 + tid) * SGI_PITCH + qx0]);
+          float* dst = a.depth + (size_t)y * a.W + gx0;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(wv * 4) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the copy's reads
+        }
+      }
+      return;
+    }
     // four texels per thread and store: 16-byte stores when the row pitch allows it
     const int rq_log2 = rs_log2 - 2;
     const bool vec_ok = (a.W & 3) == 0;
@@ -1047,6 +1139,7 @@ static int grow(sgi_ctx* ctx, void** p, size_t bytes) {
 static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W, int H, cudaStream_t stream) {
   int rc;
   if (max_tris > sc.rec_cap_tris) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(stream));
     size_t n = (size_t)max_tris * 7 + 16;
     if ((rc = grow(ctx, (void**)&sc.d_rec, n * sizeof(SgiRec)))) return rc;
     if ((rc = grow(ctx, (void**)&sc.d_attr, n * sizeof(SgiRecAttr)))) return rc;
@@ -1056,7 +1149,7 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
   }
   if (!sc.h_flags) {
     SGI_CUDA(ctx, cudaHostAlloc((void**)&sc.h_flags, 64, cudaHostAllocMapped));
-    sc.h_flags[0] = sc.h_flags[1] = 0;
+    for (int k = 0; k < 16; k++) sc.h_flags[k] = 0;
     SGI_CUDA(ctx, cudaMalloc((void**)&sc.d_sticky, 64));
     SGI_CUDA(ctx, cudaMemset(sc.d_sticky, 0, 64));
   }
@@ -1064,32 +1157,41 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
   if (tiles + 1 > sc.tile_cap) {
     int cap = tiles + 1 + 64;
     SGI_CUDA(ctx, cudaStreamSynchronize(stream));
-    if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(16 + 2 * cap) * 4))) return rc;   // counters | tile_cnt | tile_fill
-    sc.d_tile_cnt = sc.d_counters + 16;
-    sc.d_tile_fill = sc.d_tile_cnt + cap;
-    if ((rc = grow(ctx, (void**)&sc.d_tile_off, ((size_t)cap * 2 + SGI_SPLIT_EXTRA) * 4))) return rc;   // tile_off | tile_order (work items)
+    if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(32 + 2 * cap) * 4))) return rc;   // counters | snapshot | tile_cnt | tile_n
+    sc.d_snap = sc.d_counters + 16;
+    sc.d_tile_cnt = sc.d_counters + 32;
+    sc.d_tile_n = sc.d_tile_cnt + cap;
+    if ((rc = grow(ctx, (void**)&sc.d_tile_order, ((size_t)cap + SGI_SPLIT_EXTRA) * 4))) return rc;   // work items
     if ((rc = grow(ctx, (void**)&sc.d_tile_zmax, (size_t)cap * 4))) return rc;
-    sc.d_tile_order = sc.d_tile_off + cap;
     sc.tile_cap = cap;
-  }
-  if (sc.pair_cap == 0) {
-    long long want = (long long)max_tris * 4 + (long long)tiles * 8 + (1 << 20);
-    if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
-    sc.pair_cap = want;
+    sc.needs_clear = true;
   }
   return SGI_OK;
 }
 
+// room for `cap` list entries per tile
+static int sgi_raster_reserve_lists(sgi_ctx* ctx, SgiScratch& sc, int cap, int n_tiles, cudaStream_t stream) {
+  const size_t want = (size_t)cap * (size_t)n_tiles + 16;
+  if (want <= sc.pair_alloc) return SGI_OK;
+  if (want > ((size_t)1 << 30)) { ctx->err = "tile lists would exceed 4 GiB (a single 64x64 tile lists millions of triangles)"; return SGI_ERR_NOMEM; }
+  SGI_CUDA(ctx, cudaStreamSynchronize(stream));
+  int rc = grow(ctx, (void**)&sc.d_pairs, want * 4);
+  sc.pair_alloc = rc ? 0 : want;
+  return rc;
+}
+
+// Per-device function attributes (the opt-in to > 48 KB of dynamic shared memory applies to the CURRENT device only): kept per
+// context, so a second context on another GPU of the same process configures its own device.
 template <int MODE, int NT>
 static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStream_t stream) {
-  static bool configured = false;
   constexpr size_t smem = tile_smem_bytes<MODE, NT>();
-  if (!configured) {
+  constexpr int cfg_bit = MODE * 3 + (NT == 256 ? 0 : (NT == 512 ? 1 : 2));
+  if (!(ctx->func_cfg & (1ull << cfg_bit))) {
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ask for the largest shared-memory carve-out so that two 1024-thread CTAs (or more of the smaller ones) fit an SM;
     // with the default carve-out ncu showed occupancy limited to ONE CTA by shared memory
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    configured = true;
+    ctx->func_cfg |= 1ull << cfg_bit;
   }
   const int pass = (MODE == SGI_MODE_DEPTH || MODE == SGI_MODE_MOMENTS) ? SGI_PASS_TILE_DEPTH : (SGI_KEYED(MODE) ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
   int tslot = sgi_timing_begin(ctx, pass, stream);
@@ -1125,13 +1227,6 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   SgiScratch& sc = ctx->scratch[scratch_set];
   int rc = sgi_raster_reserve(ctx, sc, job.T, job.W, job.H, stream);
   if (rc) return rc;
-  // a previous frame asked for more list space than we had: grow before running again
-  if (sc.h_flags[1] > 0 && (long long)sc.h_flags[1] + 1024 > sc.pair_cap) {
-    SGI_CUDA(ctx, cudaStreamSynchronize(stream));
-    long long want = (long long)sc.h_flags[1] * 2 + (1 << 16);
-    if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
-    sc.pair_cap = want;
-  }
   cudaStream_t st = stream;
   const int tiles_x = (job.W + SGI_TILE - 1) >> SGI_TILE_LOG2, tiles_y = (job.H + SGI_TILE - 1) >> SGI_TILE_LOG2;
   const int n_tiles = tiles_x * tiles_y;
@@ -1140,19 +1235,18 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   rx0 = rx0 < 0 ? 0 : rx0; ry0 = ry0 < 0 ? 0 : ry0; rx1 = rx1 > job.W ? job.W : rx1; ry1 = ry1 > job.H ? job.H : ry1;
   const int tx0 = rx0 >> SGI_TILE_LOG2, ty0 = ry0 >> SGI_TILE_LOG2;
   const int tx1 = (rx1 - 1) >> SGI_TILE_LOG2, ty1 = (ry1 - 1) >> SGI_TILE_LOG2;
+  // size class of the pass: the moment and id passes bin exactly like the depth / G-buffer passes
+  const int size_class = (job.mode == SGI_MODE_MOMENTS) ? SGI_MODE_DEPTH : (job.mode == SGI_MODE_SVCOUNT ? SGI_MODE_SVCOUNT : (job.mode == SGI_MODE_DEPTH ? SGI_MODE_DEPTH : SGI_MODE_GBUFFER));
 
-  // counters | tile_cnt | tile_fill live in one allocation: one memset
-  SGI_CUDA(ctx, cudaMemsetAsync(sc.d_counters, 0, (size_t)(16 + 2 * sc.tile_cap) * 4, st));
+  // a previous frame wanted longer lists than we had: grow before running again (2x headroom over the longest list seen)
+  int cap = sc.cap_of[size_class];
+  if (sc.h_flags[1 + size_class] > cap) cap = sc.h_flags[1 + size_class] * 2 + 64;
+  if ((rc = sgi_raster_reserve_lists(ctx, sc, cap, n_tiles, st))) return rc;
+  sc.cap_of[size_class] = cap;
 
-  SetupArgs sa;
-  sa.xyz = job.xyz; sa.nrm = job.nrm; sa.rgb = (job.rgb && job.albedo4) ? job.rgb : nullptr; sa.idx = job.idx; sa.T = job.T;
-  for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
-  sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
-  sa.rec = sc.d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? sc.d_attr : nullptr;
-  sa.ovf_base = sc.d_ovf_base; sa.counters = sc.d_counters;
-  if (job.T > 0) {
-    k_setup<<<(job.T + 127) / 128, 128, 0, st>>>(sa);
-    ctx->launches++;
+  if (sc.needs_clear) {     // live counters | snapshot | cursors in one allocation: cleared once; k_order re-zeroes what the binner dirtied
+    SGI_CUDA(ctx, cudaMemsetAsync(sc.d_counters, 0, (size_t)(32 + 2 * sc.tile_cap) * 4, st));
+    sc.needs_clear = false;
   }
 
   // shadow volumes: per-tile farthest scene depth, so that the binner drops (prism, tile) pairs that lie behind the scene
@@ -1162,43 +1256,61 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
     k_tile_zmax<<<dim3(tiles_x, tiles_y), 256, 0, st>>>(job.scene_depth, job.W, job.H, tiles_x, tile_zmax);
     ctx->launches++;
   }
-  BinArgs ba;
-  ba.tile_zmax = tile_zmax;
-  ba.rec = sc.d_rec; ba.counters = sc.d_counters; ba.counters_rw = sc.d_counters; ba.T = job.T; ba.big_list = sc.d_big;
-  ba.tiles_x = tiles_x; ba.tiles_y = tiles_y; ba.tx0 = tx0; ba.ty0 = ty0; ba.tx1 = tx1; ba.ty1 = ty1;
-  ba.tile_cnt = sc.d_tile_cnt; ba.tile_off = sc.d_tile_off; ba.tile_fill = sc.d_tile_fill;
-  ba.pairs = sc.d_pairs; ba.pair_cap = sc.pair_cap; ba.flags = sc.d_counters; ba.h_flags = sc.h_flags;
-  int bin_blocks = (job.T + job.T / 4 + 255) / 256;   // one thread per record; the loop strides over clipped extras
-  if (bin_blocks < 1) bin_blocks = 1;
-  if ((bin_blocks * 256) % 7919 == 0) bin_blocks++;   // k_bin's index permutation needs the thread count coprime to 7919
-  k_bin<0><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
-  ctx->launches++;
+
+  SetupBinArgs sa;
+  sa.xyz = job.xyz; sa.nrm = job.nrm; sa.rgb = (job.rgb && job.albedo4) ? job.rgb : nullptr; sa.idx = job.idx; sa.T = job.T;
+  for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
+  sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
+  sa.no_far_clip = job.no_far_clip;
+  sa.rec = sc.d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? sc.d_attr : nullptr;
+  sa.ovf_base = sc.d_ovf_base; sa.counters = sc.d_counters;
+  sa.tiles_x = tiles_x; sa.tx0 = tx0; sa.ty0 = ty0; sa.tx1 = tx1; sa.ty1 = ty1;
+  sa.tile_cnt = sc.d_tile_cnt; sa.pairs = sc.d_pairs; sa.cap = cap; sa.big_list = sc.d_big; sa.tile_zmax = tile_zmax;
+  int sb_blocks = (job.T + 127) / 128;
+  if (sb_blocks < 1) sb_blocks = 1;
+  if ((sb_blocks * 128) % 7919 == 0) sb_blocks++;     // the index permutation needs the thread count coprime to 7919 (a prime)
+  sa.nperm = sb_blocks * 128;
+
   // grid of the tile kernel = upper bound of its work items: every tile of the rectangle + room for subdivided hot tiles
   const int n_rect_tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
   const int max_items = n_rect_tiles + (15 * n_rect_tiles < SGI_SPLIT_EXTRA ? 15 * n_rect_tiles : SGI_SPLIT_EXTRA);
-  k_scan_tiles<<<1, 1024, 0, st>>>(sc.d_tile_cnt, sc.d_tile_off, n_tiles + 1, sc.d_counters, sc.h_flags, sc.d_sticky, sc.d_tile_order, tiles_x,
-                                   tx0, ty0, tx1 - tx0 + 1, ty1 - ty0 + 1, ctx->tile_order, max_items, ctx->tile_split);
-  ctx->launches++;
-  const int size_class = job.mode == SGI_MODE_MOMENTS ? SGI_MODE_DEPTH : job.mode;   // the moment pass bins exactly like the depth pass
+  OrderArgs oa;
+  oa.tile_cnt = sc.d_tile_cnt; oa.tile_n = sc.d_tile_n; oa.n_tiles = n_tiles; oa.cap = cap;
+  oa.counters = sc.d_counters; oa.snap = sc.d_snap; oa.h_flags = sc.h_flags; oa.d_sticky = sc.d_sticky; oa.size_class = size_class;
+  oa.order = sc.d_tile_order; oa.tiles_x = tiles_x; oa.tx0 = tx0; oa.ty0 = ty0; oa.gx = tx1 - tx0 + 1; oa.gy = ty1 - ty0 + 1;
+  oa.busiest_first = ctx->tile_order; oa.max_items = max_items; oa.split_floor = ctx->tile_split; oa.n_sm = ctx->n_sm;
+
+  sc.needs_clear = true;                 // until k_order has been queued behind the binner
+  k_setup_bin<<<sb_blocks, 128, 0, st>>>(sa);
+  k_order<<<1, 1024, 0, st>>>(oa);
+  ctx->launches += 2;
+  SGI_CUDA(ctx, cudaGetLastError());
+  sc.needs_clear = false;
   if (!sc.sized[size_class]) {
-    // first pass of this kind on this context: size the tile lists from the real count (one sync, once)
+    // first pass of this kind on this context: size the tile lists from the measured frame (one sync, once) and bin again
     SGI_CUDA(ctx, cudaStreamSynchronize(st));
     sc.sized[size_class] = true;
-    if ((long long)sc.h_flags[1] > sc.pair_cap) {
-      long long want = (long long)sc.h_flags[1] * 2 + (1 << 16);
-      if ((rc = grow(ctx, (void**)&sc.d_pairs, (size_t)want * 4))) return rc;
-      sc.pair_cap = want;
-      ba.pairs = sc.d_pairs; ba.pair_cap = sc.pair_cap;
+    const int longest = sc.h_flags[1 + size_class];
+    if (longest > cap) {
+      cap = longest * 2 + 64;
+      if ((rc = sgi_raster_reserve_lists(ctx, sc, cap, n_tiles, st))) return rc;
+      sc.cap_of[size_class] = cap;
+      sc.h_flags[0] = 0;                 // raised by the measuring run; the stream is idle
+      sa.pairs = sc.d_pairs; sa.cap = cap; oa.cap = cap;
+      sc.needs_clear = true;
+      k_setup_bin<<<sb_blocks, 128, 0, st>>>(sa);
+      k_order<<<1, 1024, 0, st>>>(oa);
+      ctx->launches += 2;
+      SGI_CUDA(ctx, cudaGetLastError());
+      sc.needs_clear = false;
     }
   }
-  k_bin<1><<<bin_blocks, 256, 0, st>>>(ba, job.W, job.H);
-  ctx->launches++;
   sc.overflow_pending = true;
 
   TileArgs ta;
   ta.rec = sc.d_rec; ta.attr = sc.d_attr; ta.ovf_base = sc.d_ovf_base;
-  ta.tile_off = sc.d_tile_off; ta.tile_order = sc.d_tile_order; ta.pairs = sc.d_pairs; ta.pair_cap = sc.pair_cap;
-  ta.big_list = sc.d_big; ta.counters = sc.d_counters;
+  ta.tile_n = sc.d_tile_n; ta.tile_order = sc.d_tile_order; ta.pairs = sc.d_pairs; ta.cap = cap;
+  ta.big_list = sc.d_big; ta.counters = sc.d_snap;
   ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
   ta.xyz = job.xyz; ta.nrm = job.nrm; ta.idx = job.idx;
@@ -1217,7 +1329,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 }
 
 void sgi_raster_free(SgiScratch& sc) {
-  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_off, sc.d_pairs, sc.d_tile_zmax};
+  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_order, sc.d_pairs, sc.d_tile_zmax};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (sc.h_flags) cudaFreeHost(sc.h_flags);
   if (sc.d_sticky) cudaFree(sc.d_sticky);

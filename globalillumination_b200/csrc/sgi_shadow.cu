@@ -931,10 +931,9 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   // shared-memory staging of the shadow-map window (PCF / PCSS) is an option (sgi_set_option "vis_staged"): measured on
   // B200 it only pays when the map is much larger than L1 can cover (4096^2 PCSS: 1.01 -> 0.89 ms) and loses at the
   // c2 sizes (0.077 -> 0.097 ms), because the kernel is issue-bound, not L1-bound (profiles/r1_vis_staging.txt)
-  static int staged_cfg = -1;
   const size_t stage_bytes = (size_t)SGI_STAGE_FLOATS * 4;
-  if (staged_cfg < 0) {
-    staged_cfg = 1;
+  if (ctx->vis_staged && !(ctx->func_cfg & (1ull << 40))) {        // per-device attribute: once per context
+    ctx->func_cfg |= 1ull << 40;
     cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCF, 7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
     cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCF, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
     cudaFuncSetAttribute(k_visibility_staged<SGI_TECH_PCSS, 7, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
@@ -989,7 +988,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
       RbssmItem* items = (RbssmItem*)((char*)ctx->rbssm_buf + 64);
       SGI_CUDA(ctx, cudaMemsetAsync(counters, 0, 8, st));
       k_rbssm_prepare<<<grid, block, 0, st>>>(a, items, counters);
-      k_rbssm_taps<<<148 * 4, 256, 0, st>>>(a, items, counters, counters + 1);
+      k_rbssm_taps<<<ctx->n_sm * 4, 256, 0, st>>>(a, items, counters, counters + 1);
       ctx->launches++;
       break;
     }
