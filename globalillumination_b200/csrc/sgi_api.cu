@@ -181,7 +181,8 @@ int sgi_create(sgi_ctx** out, int device) {
   { const char* e = getenv("SGI_VIS_STAGED"); ctx->vis_staged = (e && e[0] == '1') ? 1 : 0; }
   { const char* e = getenv("SGI_TILE_SPLIT"); if (e) ctx->tile_split = atoi(e) < 0 ? 0 : atoi(e); }
   { const char* e = getenv("SGI_TILE_ORDER"); ctx->tile_order = (e && e[0] == '0') ? 0 : 1; }
-  { const char* e = getenv("SGI_TILE_THREADS"); int v = e ? atoi(e) : 0; ctx->tile_threads = (v == 256 || v == 512 || v == 1024) ? v : 0; }
+  { const char* e = getenv("SGI_TILE_THREADS"); int v = e ? atoi(e) : 0; ctx->tile_threads = (v == 128 || v == 256 || v == 512 || v == 1024) ? v : 0; }
+  { const char* e = getenv("SGI_TILE_BULK"); if (e) ctx->tile_bulk_flush = e[0] != '0'; }
   // lowest priority: when CTAs of the next frame's raster passes and of this frame's shadow pass compete for an SM, the raster
   // ones go first (they are latency-bound chains on the critical path); the shadow pass fills what they leave
   int prio_lo = 0, prio_hi = 0;
@@ -819,8 +820,9 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "sv_tile_cull")) ctx->sv_tile_cull = value ? 1 : 0;
   else if (!strcmp(name, "rbssm_compact")) ctx->rbssm_compact = value ? 1 : 0;
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
+  else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
   else if (!strcmp(name, "tile_threads")) {
-    if (value != 0 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 256, 512 or 1024"; return SGI_ERR_INVALID; }
+    if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 128 (depth pass only), 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;
   } else { ctx->err = std::string("unknown option ") + name; return SGI_ERR_INVALID; }
   return SGI_OK;

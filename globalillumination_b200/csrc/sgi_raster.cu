@@ -106,9 +106,9 @@ struct SetupBinArgs {
   // binning
   int tiles_x, tx0, ty0, tx1, ty1;               // tile grid pitch and the inclusive tile range of the job rectangle
   int32_t* tile_cnt; int32_t* pairs; int cap;    // per-tile append cursor; list of tile t = pairs[t * cap .. t * cap + cap)
+  int2* spill; int spill_cap;                    // (tile, record) pairs that found their tile's list full (counters[5] = count)
   int32_t* big_list;                             // records spanning > SGI_BIG_TILES tiles: not binned, every tile CTA tests them (counters[3] = count)
   const unsigned int* tile_zmax;                 // shadow volumes: largest scene depth of each tile (float bits), or null
-  int nperm;                                     // launched threads, coprime to 7919 (index permutation)
 };
 
 __device__ __forceinline__ void invalidate(SgiRec* r) {
@@ -310,99 +310,76 @@ __global__ void __launch_bounds__(256) k_tile_zmax(const float* __restrict__ dep
 #define SGI_BIG_TILES 256
 #endif
 
-// Set-up and binning in one pass, one thread per source triangle.  A record overlapping <= 4 tiles is appended by its thread
-// with all (up to 4) atomics in flight before the first dependent store.  The larger ones of a warp are flattened into one
-// (record, tile) index space that the 32 lanes walk together, 4 pairs per lane per trip, so a trip keeps 128 atomics in
-// flight instead of serialising one record after the other behind the atomics' latency.  The extra fan triangles of a
-// clipped source triangle (rare) go through the same walk in further rounds, re-read from the records just written.
-// Lists are fixed-capacity segments: position = atomicAdd(cursor of the tile); entries beyond the capacity are dropped
-// and k_order reports the overflow (the frame is then re-run with larger lists: SGI_ERR_OVERFLOW protocol).
+// Set-up and binning in one pass, one thread per source triangle, triangles in mesh order (all loads and stores coalesced,
+// neighbouring triangles share their vertices in L1).  A record overlapping <= 4 tiles is appended by its thread with all (up
+// to 4) atomics in flight before the first dependent store.  Larger records are parked in shared memory and, after a barrier,
+// flattened into one (record, tile) index space that the CTA's 128 threads walk together, 4 pairs per thread per trip: meshes
+// list their large triangles (floors, walls) consecutively, and left to their own threads a few warps would walk thousands
+// of pairs while the others idle.  The extra fan triangles of a clipped source triangle (rare) take the same two routes,
+// re-read from the records just written.
+// Lists are fixed-capacity segments: position = atomicAdd(cursor of the tile).  Entries beyond the capacity go to a shared
+// spill list of (tile, record) pairs that the tile kernel scans for the tiles that overflowed, so a frame whose triangles
+// gather in one tile (an object crossing a tile corner changes the longest list by 4x) still renders completely; only
+// when the spill list itself is full is the frame reported (SGI_ERR_OVERFLOW) and re-run with larger lists.
+#define SGI_SB_THREADS 128
+#define SGI_SB_QCAP 256
+struct BinRec {                  // what the tile walk of a large record needs (64 B)
+  int X0, Y0, X1, Y1, X2, Y2;
+  float z0, dz1, dz2, ia, zoff;
+  int slot, bx0, by0, bw, nt;
+};
 __device__ __forceinline__ void list_append(const SetupBinArgs& a, int tile, int pos, int slot) {
   if (pos < a.cap) a.pairs[(size_t)tile * a.cap + pos] = slot;
+  else {
+    const int o = atomicAdd(&a.counters[5], 1);
+    if (o < a.spill_cap) a.spill[o] = make_int2(tile, slot);
+  }
 }
 
-__global__ void __launch_bounds__(128) k_setup_bin(const SetupBinArgs a) {
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs a) {
+  __shared__ BinRec q[SGI_SB_QCAP];
+  __shared__ int q_pref[SGI_SB_QCAP + 1];
+  __shared__ int q_n, warp_sum[SGI_SB_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
   const int W = a.W, H = a.H;
-  // Triangles are dealt to threads through a multiplicative permutation of the index space: meshes list their large
-  // triangles (floors, walls) consecutively, and a warp holding 32 of them would walk thousands of (record, tile) pairs
-  // while the others idle; 7919 triangles apart, every warp gets the same mix.
-  const int t = (int)(((long long)(blockIdx.x * blockDim.x + threadIdx.x) * 7919LL) % a.nperm);   // host guarantees gcd(nperm, 7919) == 1
+  if (tid == 0) q_n = 0;
+  __syncthreads();
+  const int t = blockIdx.x * SGI_SB_THREADS + tid;
   SgiRec r;
   r.prim_front = -1;
   int base = -1, nf = 0;
   if (t < a.T) nf = setup_triangle(a, t, r, base);
-  const int rounds = __reduce_max_sync(0xffffffffu, nf);
-  for (int f = 0; f < rounds; f++) {
+  for (int f = 0; f < nf; f++) {
     int slot = t;
-    if (f > 0) {
-      r.prim_front = -1;
-      if (f < nf) { slot = base + f - 1; r = a.rec[slot]; }
+    if (f > 0) { slot = base + f - 1; r = a.rec[slot]; }
+    if (r.prim_front < 0) continue;
+    const int bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
+    const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
+    if (bx0 > bx1 || by0 > by1) continue;
+    const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
+    if (nt > SGI_BIG_TILES) {          // e.g. the floor: listing it in thousands of tiles costs more than letting each tile test it
+      a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
+      continue;
     }
-    int bx0 = 0, by0 = 0, bw = 1, nt = 0;
-    if (r.prim_front >= 0) {
-      bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0); by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
-      const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
-      if (bx0 <= bx1 && by0 <= by1) { bw = bx1 - bx0 + 1; nt = bw * (by1 - by0 + 1); }
-      if (nt > SGI_BIG_TILES) {        // e.g. the floor: listing it in thousands of tiles costs more than letting each tile test it
-        a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
-        nt = 0;
-      }
+    int k = -1;
+    if (nt > 4) { k = atomicAdd(&q_n, 1); if (k >= SGI_SB_QCAP) k = -1; }
+    if (k >= 0) {
+      BinRec b;
+      b.X0 = r.X0; b.Y0 = r.Y0; b.X1 = r.X1; b.Y1 = r.Y1; b.X2 = r.X2; b.Y2 = r.Y2;
+      b.z0 = r.z0; b.dz1 = r.dz1; b.dz2 = r.dz2; b.ia = r.ia; b.zoff = r.zoff;
+      b.slot = slot; b.bx0 = bx0; b.by0 = by0; b.bw = bw; b.nt = nt;
+      q[k] = b;
+      continue;
     }
-    // ---- small records: this thread alone
-    if (nt > 0 && nt <= 4) {
+    // ---- small records (and the ones the shared queue had no room for): this thread alone, 4 tiles at a time
+    for (int k0 = 0; k0 < nt; k0 += 4) {
       int tiles[4], pos[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        tiles[k] = -1;
-        if (k < nt) {
-          const int ty = by0 + k / bw, tx = bx0 + k % bw;
-          if ((nt == 1 || tile_overlaps(r, tx, ty, W, H)) && !tile_behind_scene(r, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[k] = ty * a.tiles_x + tx;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (tiles[k] >= 0) pos[k] = atomicAdd(&a.tile_cnt[tiles[k]], 1);
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (tiles[k] >= 0) list_append(a, tiles[k], pos[k], slot);
-    }
-    // ---- larger records of this warp, flattened
-    const int mine = (nt > 4) ? nt : 0;
-    int incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    for (int p0 = 0; p0 < total; p0 += 128) {
-      int tiles[4], pos[4], slots[4];
-#pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int p = p0 + u * 32 + lane;
-        // owner = first lane whose inclusive prefix exceeds p (5-step search over the warp's prefixes)
-        int lo = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const int probe = __shfl_sync(0xffffffffu, incl, min(lo + step - 1, 31));
-          if (lo + step - 1 < 32 && probe <= p) lo += step;
-        }
-        const int src = min(lo, 31);
-        const int s_incl = __shfl_sync(0xffffffffu, incl, src), s_nt = __shfl_sync(0xffffffffu, mine, src);
-        SgiRec q;
-        q.X0 = __shfl_sync(0xffffffffu, r.X0, src); q.Y0 = __shfl_sync(0xffffffffu, r.Y0, src);
-        q.X1 = __shfl_sync(0xffffffffu, r.X1, src); q.Y1 = __shfl_sync(0xffffffffu, r.Y1, src);
-        q.X2 = __shfl_sync(0xffffffffu, r.X2, src); q.Y2 = __shfl_sync(0xffffffffu, r.Y2, src);
-        const int sbx0 = __shfl_sync(0xffffffffu, bx0, src), sby0 = __shfl_sync(0xffffffffu, by0, src);
-        const int sbw = __shfl_sync(0xffffffffu, bw, src);
-        slots[u] = __shfl_sync(0xffffffffu, slot, src);
-        if (a.tile_zmax) {                       // shadow volumes: the depth plane travels too (tile_behind_scene)
-          q.z0 = __shfl_sync(0xffffffffu, r.z0, src); q.dz1 = __shfl_sync(0xffffffffu, r.dz1, src); q.dz2 = __shfl_sync(0xffffffffu, r.dz2, src);
-          q.ia = __shfl_sync(0xffffffffu, r.ia, src); q.zoff = __shfl_sync(0xffffffffu, r.zoff, src);
-        }
         tiles[u] = -1;
-        if (p < total) {
-          const int k = p - (s_incl - s_nt);
-          const int ty = sby0 + k / sbw, tx = sbx0 + k % sbw;
-          if (tile_overlaps(q, tx, ty, W, H) && !tile_behind_scene(q, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
+        if (k0 + u < nt) {
+          const int ty = by0 + (k0 + u) / bw, tx = bx0 + (k0 + u) % bw;
+          if ((nt == 1 || tile_overlaps(r, tx, ty, W, H)) && !tile_behind_scene(r, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
         }
       }
 #pragma unroll
@@ -410,8 +387,54 @@ __global__ void __launch_bounds__(128) k_setup_bin(const SetupBinArgs a) {
         if (tiles[u] >= 0) pos[u] = atomicAdd(&a.tile_cnt[tiles[u]], 1);
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (tiles[u] >= 0) list_append(a, tiles[u], pos[u], slots[u]);
+        if (tiles[u] >= 0) list_append(a, tiles[u], pos[u], slot);
     }
+  }
+  __syncthreads();
+  // ---- larger records of this CTA, flattened: inclusive prefix of their tile counts, then every thread takes pairs
+  const int nq = min(q_n, SGI_SB_QCAP);
+  if (nq == 0) return;
+  {
+    const int i0 = 2 * tid, i1 = 2 * tid + 1;
+    const int c0 = i0 < nq ? q[i0].nt : 0, c1 = i1 < nq ? q[i1].nt : 0;
+    int incl = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) warp_sum[tid >> 5] = incl;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < (tid >> 5); w++) off += warp_sum[w];
+    incl += off;
+    q_pref[i0 + 1] = incl - c1; q_pref[i1 + 1] = incl;       // q_pref[i + 1] = pairs of records 0..i
+    if (tid == 0) q_pref[0] = 0;
+    __syncthreads();
+  }
+  const int total = q_pref[nq];
+  for (int p0 = 0; p0 < total; p0 += 4 * SGI_SB_THREADS) {
+    int tiles[4], pos[4], slots[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int p = p0 + u * SGI_SB_THREADS + tid;
+      tiles[u] = -1;
+      if (p < total) {
+        int lo = 0, hi = nq;                                 // owner = the record i with q_pref[i] <= p < q_pref[i + 1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_pref[mid] <= p) lo = mid; else hi = mid; }
+        const BinRec& b = q[lo];
+        const int k = p - q_pref[lo];
+        const int ty = b.by0 + k / b.bw, tx = b.bx0 + k % b.bw;
+        SgiRec rr;
+        rr.X0 = b.X0; rr.Y0 = b.Y0; rr.X1 = b.X1; rr.Y1 = b.Y1; rr.X2 = b.X2; rr.Y2 = b.Y2;
+        rr.z0 = b.z0; rr.dz1 = b.dz1; rr.dz2 = b.dz2; rr.ia = b.ia; rr.zoff = b.zoff;
+        slots[u] = b.slot;
+        if (tile_overlaps(rr, tx, ty, W, H) && !tile_behind_scene(rr, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (tiles[u] >= 0) pos[u] = atomicAdd(&a.tile_cnt[tiles[u]], 1);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (tiles[u] >= 0) list_append(a, tiles[u], pos[u], slots[u]);
   }
 }
 
@@ -436,11 +459,12 @@ __device__ __forceinline__ int weight_bucket(int c) {
   return c < 2 ? c : 2 * l + ((c >> (l - 1)) & 1);
 }
 struct OrderArgs {
-  int32_t* tile_cnt; int32_t* tile_n; int n_tiles; int cap;
+  int32_t* tile_cnt; int32_t* tile_n; int n_tiles; int cap; int spill_cap;
   int32_t* counters; int32_t* snap; volatile int32_t* h_flags; int32_t* d_sticky; int size_class;
   int32_t* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
 };
 #define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
+#define SGI_ORDER_REG 16        // tiles per thread held in registers (grids up to 16 384 tiles: an 8192^2 map); larger grids re-read
 __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   __shared__ int hist[SGI_ORDER_KEYS];
   __shared__ int red_sum[32], red_max[32];
@@ -448,12 +472,20 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- list lengths, totals, re-zero the cursors
   int sum = 0, mx = 0;
-  for (int i = tid; i < a.n_tiles; i += 1024) {
-    const int c = a.tile_cnt[i];
-    const int n = min(c, a.cap);
-    a.tile_n[i] = n;
-    if (c) a.tile_cnt[i] = 0;
-    sum += n; mx = max(mx, c);
+  for (int i0 = 0; i0 < a.n_tiles; i0 += 1024 * SGI_ORDER_REG) {
+    int c[SGI_ORDER_REG];
+#pragma unroll
+    for (int k = 0; k < SGI_ORDER_REG; k++) { const int i = i0 + k * 1024 + tid; c[k] = i < a.n_tiles ? a.tile_cnt[i] : 0; }
+#pragma unroll
+    for (int k = 0; k < SGI_ORDER_REG; k++) {
+      const int i = i0 + k * 1024 + tid;
+      if (i < a.n_tiles) {
+        const int n = min(c[k], a.cap);
+        a.tile_n[i] = c[k] > a.cap ? (n | 0x40000000) : n;      // bit 30: the tile has entries in the spill list
+        if (c[k]) a.tile_cnt[i] = 0;
+        sum += n; mx = max(mx, c[k]);
+      }
+    }
   }
   sum = __reduce_add_sync(0xffffffffu, sum); mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) { red_sum[warp] = sum; red_max[warp] = mx; }
@@ -462,28 +494,48 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   if (warp == 0) {
     int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
     if (lane == 0) {
-      a.snap[0] = a.counters[0]; a.snap[3] = a.counters[3]; a.snap[2] = s2;
-      a.counters[0] = 0; a.counters[3] = 0;
-      // longest list ever wanted (the host sizes the capacity from it).  The running maximum lives in device memory and the
-      // host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind whatever DMA
-      // traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
+      const int spilled = a.counters[5];
+      a.snap[0] = a.counters[0]; a.snap[3] = a.counters[3]; a.snap[2] = s2; a.snap[5] = min(spilled, a.spill_cap);
+      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0;
+      // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
+      // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
+      // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
       if (m2 > a.d_sticky[a.size_class]) { a.d_sticky[a.size_class] = m2; a.h_flags[1 + a.size_class] = m2; }
-      if (m2 > a.cap) a.h_flags[0] = 1;
+      if (s2 + spilled > a.d_sticky[4 + a.size_class]) { a.d_sticky[4 + a.size_class] = s2 + spilled; a.h_flags[4 + a.size_class] = s2 + spilled; }
+      if (spilled > a.spill_cap) a.h_flags[0] = 1;              // entries were dropped: the frame is incomplete
       s_w = a.split_floor > 0 ? max(a.split_floor, s2 / (8 * a.n_sm)) : 0x7FFFFFF;
     }
   }
   const int nl = a.gx * a.gy;
-  // per-thread tiles of the job rectangle: i = tid + 1024 k  (the same tiles in all three loops below)
+  const bool in_regs = nl <= 1024 * SGI_ORDER_REG;
+  // this thread's tiles of the job rectangle, i = tid + 1024 k: index and list length (spill flag stripped)
+  int til[SGI_ORDER_REG], cnt[SGI_ORDER_REG];
+  __syncthreads();                                    // tile_n is complete
+#pragma unroll
+  for (int k = 0; k < SGI_ORDER_REG; k++) {
+    const int i = k * 1024 + tid;
+    til[k] = -1; cnt[k] = 0;
+    if (i < nl) {
+      const int y = i / a.gx, x = i - y * a.gx;
+      til[k] = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
+      cnt[k] = a.tile_n[til[k]] & 0x3FFFFFFF;
+    }
+  }
+  auto tile_of = [&](int i, int& c) -> int {          // grids beyond the register window: recompute
+    const int y = i / a.gx, x = i - y * a.gx;
+    const int tl = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
+    c = a.tile_n[tl] & 0x3FFFFFFF;
+    return tl;
+  };
   for (;;) {                                          // largest subdivision that fits the launched grid
     __syncthreads();
     if (tid == 0) s_items = 0;
     __syncthreads();
     const int w = s_w;
     int local = 0;
-    for (int i = tid; i < nl; i += 1024) {
-      const int y = i / a.gx, x = i - y * a.gx;
-      local += 1 << (2 * split_level(a.tile_n[(a.ty0 + y) * a.tiles_x + a.tx0 + x], w));
-    }
+#pragma unroll
+    for (int k = 0; k < SGI_ORDER_REG; k++) if (til[k] >= 0) local += 1 << (2 * split_level(cnt[k], w));
+    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(c, w)); }
     local = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0 && local) atomicAdd(&s_items, local);
     __syncthreads();
@@ -492,37 +544,36 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     if (tid == 0) s_w = w >= 0x3FFFFFF ? 0x7FFFFFF : 2 * w;
   }
   const int w = s_w;
-  // ---- histogram of the items over (weight bucket, level)
-  for (int i0 = 0; i0 < nl; i0 += 1024) {
-    const int i = i0 + tid;
-    int key = -1;
-    if (i < nl) {
-      const int y = i / a.gx, x = i - y * a.gx;
-      const int c = a.tile_n[(a.ty0 + y) * a.tiles_x + a.tx0 + x];
-      const int lv = split_level(c, w);
-      key = (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv;
-    }
+  // ---- histogram of the items over (weight bucket, level): one shared atomic per distinct key per warp
+  auto key_of = [&](int c) -> int { const int lv = split_level(c, w); return (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv; };
+  auto hist_step = [&](int key) {
     const unsigned grp = __match_any_sync(0xffffffffu, key);
     if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&hist[key], __popc(grp) << (2 * (key & 3)));
+  };
+#pragma unroll
+  for (int k = 0; k < SGI_ORDER_REG; k++)
+    if (k * 1024 < nl) hist_step(til[k] >= 0 ? key_of(cnt[k]) : -1);          // (warp-uniform condition)
+  for (int i0 = 1024 * SGI_ORDER_REG; i0 < nl; i0 += 1024) {
+    int key = -1;
+    if (i0 + tid < nl) { int c; tile_of(i0 + tid, c); key = key_of(c); }
+    hist_step(key);
   }
   __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int k = SGI_ORDER_KEYS - 1; k >= 0; k--) { const int h = hist[k]; hist[k] = run; run += h; }
-    a.snap[4] = min(run, a.max_items);
+  if (warp == 0) {                                    // exclusive prefix in descending key order: lane l owns keys 255 - 8 l .. 248 - 8 l
+    int v[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = hist[SGI_ORDER_KEYS - 1 - (8 * lane + j)]; tot += v[j]; }
+    int incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+    int run = incl - tot;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { hist[SGI_ORDER_KEYS - 1 - (8 * lane + j)] = run; run += v[j]; }
+    if (lane == 31) a.snap[4] = min(incl, a.max_items);
   }
   __syncthreads();
   // ---- scatter
-  for (int i0 = 0; i0 < nl; i0 += 1024) {
-    const int i = i0 + tid;
-    int key = -1, tile = 0;
-    if (i < nl) {
-      const int y = i / a.gx, x = i - y * a.gx;
-      tile = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
-      const int c = a.tile_n[tile];
-      const int lv = split_level(c, w);
-      key = (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv;
-    }
+  auto scatter_step = [&](int key, int tile) {
     const unsigned grp = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(grp) - 1;
     int at = 0;
@@ -534,6 +585,14 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
       for (int sidx = 0; sidx < nsub; sidx++)
         if (at + sidx < a.max_items) a.order[at + sidx] = tile | (lv << 20) | (sidx << 22);
     }
+  };
+#pragma unroll
+  for (int k = 0; k < SGI_ORDER_REG; k++)
+    if (k * 1024 < nl) scatter_step(til[k] >= 0 ? key_of(cnt[k]) : -1, til[k]);
+  for (int i0 = 1024 * SGI_ORDER_REG; i0 < nl; i0 += 1024) {
+    int key = -1, tile = 0;
+    if (i0 + tid < nl) { int c; tile = tile_of(i0 + tid, c); key = key_of(c); }
+    scatter_step(key, tile);
   }
 }
 
@@ -541,7 +600,9 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
 struct TileArgs {
   const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
   const int32_t* tile_n; const int32_t* tile_order; const int32_t* pairs; int cap;   // list of tile t: pairs[t * cap .. + tile_n[t])
-  const int32_t* big_list; const int32_t* counters;      // k_order's snapshot: [3] = number of un-binned big triangles, [4] = work items
+  const int32_t* big_list; const int32_t* counters;      // k_order's snapshot: [3] = number of un-binned big triangles, [4] = work items, [5] = spill entries
+  const int2* spill;
+  int bulk_flush;                                        // depth tiles: cp.async.bulk row copies (option "tile_bulk_flush")
   int tiles_x, tx0, ty0;
   int W, H, rx0, ry0, rx1, ry1;
   const float* xyz; const float* nrm; const int32_t* idx;
@@ -703,8 +764,10 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
   const int32_t* __restrict__ list = a.pairs + (size_t)tile * a.cap;
-  const int nlisted = a.tile_n[tile], nbig = a.counters[3];
-  const int nitems = nlisted + nbig;                           // this tile's list, then the un-binned big triangles
+  const int tn = a.tile_n[tile];
+  const int nlisted = tn & 0x3FFFFFFF, nbig = a.counters[3];
+  const int nspill = (tn & 0x40000000) ? a.counters[5] : 0;    // the list was full: this tile's further entries are somewhere in the spill list
+  const int nitems = nlisted + nbig + nspill;                  // this tile's list, then the un-binned big triangles, then the spill list (all tiles')
   const bool empty = nitems == 0;                              // nothing can touch the tile: the flush writes the clear values
 
   if (!empty) {
@@ -754,9 +817,15 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     int my_k = -1, my_ng = 0;
     unsigned int my_zlo = 0u;
     __syncthreads();                                           // payload initialised / previous chunk drained
+    int my_slot = -1;
     if (base + tid < nitems) {
       const int it = base + tid;
-      const SgiRec* rp = &a.rec[it < nlisted ? __ldg(&list[it]) : __ldg(&a.big_list[it - nlisted])];
+      if (it < nlisted) my_slot = __ldg(&list[it]);
+      else if (it < nlisted + nbig) my_slot = __ldg(&a.big_list[it - nlisted]);
+      else { const int2 e = __ldg(&a.spill[it - nlisted - nbig]); if (e.x == tile) my_slot = e.y; }
+    }
+    if (my_slot >= 0) {
+      const SgiRec* rp = &a.rec[my_slot];
       const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(rp) + 3);
       const int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
       const int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
@@ -975,7 +1044,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
     // Whole rows of the region inside the job rectangle, 16-byte aligned: one bulk copy per row, shared -> global, issued by
     // one thread per row (cp.async.bulk, the TMA engine's linear form: the row pitch of 72 words that keeps the raster free of
     // bank conflicts rules out a 2-D tensor box).  The SM's load/store path carries no flush traffic and the other threads are done.
-    const bool bulk = !empty && (a.W & 3) == 0 && (wv & 3) == 0 && wv > 0 && gx0 >= a.rx0 && gx0 + wv <= a.rx1;
+    const bool bulk = a.bulk_flush && !empty && (a.W & 3) == 0 && (wv & 3) == 0 && wv > 0 && gx0 >= a.rx0 && gx0 + wv <= a.rx1;
     if (bulk) {
       if (tid < rs) {
         const int y = gy0 + tid;
@@ -1169,15 +1238,31 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
   return SGI_OK;
 }
 
-// room for `cap` list entries per tile
-static int sgi_raster_reserve_lists(sgi_ctx* ctx, SgiScratch& sc, int cap, int n_tiles, cudaStream_t stream) {
+// room for `cap` list entries per tile and `spill` (tile, record) pairs
+#define SGI_LIST_BUDGET ((size_t)1 << 28)       // entries (1 GiB) in per-tile lists; beyond that the lists are capped and the spill list carries the rest
+static int sgi_raster_reserve_lists(sgi_ctx* ctx, SgiScratch& sc, int cap, int n_tiles, int spill, cudaStream_t stream) {
+  int rc = SGI_OK;
   const size_t want = (size_t)cap * (size_t)n_tiles + 16;
-  if (want <= sc.pair_alloc) return SGI_OK;
-  if (want > ((size_t)1 << 30)) { ctx->err = "tile lists would exceed 4 GiB (a single 64x64 tile lists millions of triangles)"; return SGI_ERR_NOMEM; }
-  SGI_CUDA(ctx, cudaStreamSynchronize(stream));
-  int rc = grow(ctx, (void**)&sc.d_pairs, want * 4);
-  sc.pair_alloc = rc ? 0 : want;
+  if (want > sc.pair_alloc) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(stream));
+    rc = grow(ctx, (void**)&sc.d_pairs, want * 4);
+    sc.pair_alloc = rc ? 0 : want;
+    if (rc) return rc;
+  }
+  if (spill > sc.spill_cap) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(stream));
+    const int cap2 = spill + spill / 4;
+    rc = grow(ctx, (void**)&sc.d_spill, (size_t)cap2 * 8);
+    sc.spill_cap = rc ? 0 : cap2;
+  }
   return rc;
+}
+// list capacity per tile for a longest list of `longest` entries: 2x headroom, within the memory budget
+static int list_capacity(int longest, int n_tiles) {
+  long long cap = (long long)longest * 2 + 64;
+  const long long lim = (long long)(SGI_LIST_BUDGET / (size_t)(n_tiles > 0 ? n_tiles : 1));
+  if (cap > lim) cap = lim < 64 ? 64 : lim;
+  return (int)cap;
 }
 
 // Per-device function attributes (the opt-in to > 48 KB of dynamic shared memory applies to the CURRENT device only): kept per
@@ -1185,7 +1270,7 @@ static int sgi_raster_reserve_lists(sgi_ctx* ctx, SgiScratch& sc, int cap, int n
 template <int MODE, int NT>
 static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStream_t stream) {
   constexpr size_t smem = tile_smem_bytes<MODE, NT>();
-  constexpr int cfg_bit = MODE * 3 + (NT == 256 ? 0 : (NT == 512 ? 1 : 2));
+  constexpr int cfg_bit = MODE * 4 + (NT == 256 ? 0 : (NT == 512 ? 1 : (NT == 1024 ? 2 : 3)));
   if (!(ctx->func_cfg & (1ull << cfg_bit))) {
     SGI_CUDA(ctx, cudaFuncSetAttribute(k_tile<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ask for the largest shared-memory carve-out so that two 1024-thread CTAs (or more of the smaller ones) fit an SM;
@@ -1217,6 +1302,7 @@ static int tile_threads(const sgi_ctx* ctx, int n_tiles, int mode) {
 template <int MODE>
 static int launch_tile(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, int n_tiles, cudaStream_t stream) {
   switch (tile_threads(ctx, n_tiles, MODE)) {
+    case 128: if (MODE == SGI_MODE_DEPTH) return launch_tile_nt<SGI_MODE_DEPTH, 128>(ctx, ta, grid, stream);   // (experiments; depth pass only)
     case 256: return launch_tile_nt<MODE, 256>(ctx, ta, grid, stream);
     case 512: return launch_tile_nt<MODE, 512>(ctx, ta, grid, stream);
     default: return launch_tile_nt<MODE, 1024>(ctx, ta, grid, stream);
@@ -1238,10 +1324,14 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   // size class of the pass: the moment and id passes bin exactly like the depth / G-buffer passes
   const int size_class = (job.mode == SGI_MODE_MOMENTS) ? SGI_MODE_DEPTH : (job.mode == SGI_MODE_SVCOUNT ? SGI_MODE_SVCOUNT : (job.mode == SGI_MODE_DEPTH ? SGI_MODE_DEPTH : SGI_MODE_GBUFFER));
 
-  // a previous frame wanted longer lists than we had: grow before running again (2x headroom over the longest list seen)
+  // a previous frame wanted longer lists than we had: grow before running again (2x headroom over the longest list seen;
+  // the spill list takes a whole frame's pairs, so a frame is only ever incomplete when its pair total grows past that)
   int cap = sc.cap_of[size_class];
-  if (sc.h_flags[1 + size_class] > cap) cap = sc.h_flags[1 + size_class] * 2 + 64;
-  if ((rc = sgi_raster_reserve_lists(ctx, sc, cap, n_tiles, st))) return rc;
+  if (sc.h_flags[1 + size_class] > cap) cap = list_capacity(sc.h_flags[1 + size_class], n_tiles);
+  {
+    const int total_seen = sc.h_flags[4 + size_class];
+    if ((rc = sgi_raster_reserve_lists(ctx, sc, cap, n_tiles, total_seen > (1 << 16) ? total_seen : (1 << 16), st))) return rc;
+  }
   sc.cap_of[size_class] = cap;
 
   if (sc.needs_clear) {     // live counters | snapshot | cursors in one allocation: cleared once; k_order re-zeroes what the binner dirtied
@@ -1266,22 +1356,21 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   sa.ovf_base = sc.d_ovf_base; sa.counters = sc.d_counters;
   sa.tiles_x = tiles_x; sa.tx0 = tx0; sa.ty0 = ty0; sa.tx1 = tx1; sa.ty1 = ty1;
   sa.tile_cnt = sc.d_tile_cnt; sa.pairs = sc.d_pairs; sa.cap = cap; sa.big_list = sc.d_big; sa.tile_zmax = tile_zmax;
-  int sb_blocks = (job.T + 127) / 128;
+  sa.spill = sc.d_spill; sa.spill_cap = sc.spill_cap;
+  int sb_blocks = (job.T + SGI_SB_THREADS - 1) / SGI_SB_THREADS;
   if (sb_blocks < 1) sb_blocks = 1;
-  if ((sb_blocks * 128) % 7919 == 0) sb_blocks++;     // the index permutation needs the thread count coprime to 7919 (a prime)
-  sa.nperm = sb_blocks * 128;
 
   // grid of the tile kernel = upper bound of its work items: every tile of the rectangle + room for subdivided hot tiles
   const int n_rect_tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
   const int max_items = n_rect_tiles + (15 * n_rect_tiles < SGI_SPLIT_EXTRA ? 15 * n_rect_tiles : SGI_SPLIT_EXTRA);
   OrderArgs oa;
-  oa.tile_cnt = sc.d_tile_cnt; oa.tile_n = sc.d_tile_n; oa.n_tiles = n_tiles; oa.cap = cap;
+  oa.tile_cnt = sc.d_tile_cnt; oa.tile_n = sc.d_tile_n; oa.n_tiles = n_tiles; oa.cap = cap; oa.spill_cap = sc.spill_cap;
   oa.counters = sc.d_counters; oa.snap = sc.d_snap; oa.h_flags = sc.h_flags; oa.d_sticky = sc.d_sticky; oa.size_class = size_class;
   oa.order = sc.d_tile_order; oa.tiles_x = tiles_x; oa.tx0 = tx0; oa.ty0 = ty0; oa.gx = tx1 - tx0 + 1; oa.gy = ty1 - ty0 + 1;
   oa.busiest_first = ctx->tile_order; oa.max_items = max_items; oa.split_floor = ctx->tile_split; oa.n_sm = ctx->n_sm;
 
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
-  k_setup_bin<<<sb_blocks, 128, 0, st>>>(sa);
+  k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
   k_order<<<1, 1024, 0, st>>>(oa);
   ctx->launches += 2;
   SGI_CUDA(ctx, cudaGetLastError());
@@ -1290,15 +1379,16 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
     // first pass of this kind on this context: size the tile lists from the measured frame (one sync, once) and bin again
     SGI_CUDA(ctx, cudaStreamSynchronize(st));
     sc.sized[size_class] = true;
-    const int longest = sc.h_flags[1 + size_class];
-    if (longest > cap) {
-      cap = longest * 2 + 64;
-      if ((rc = sgi_raster_reserve_lists(ctx, sc, cap, n_tiles, st))) return rc;
+    const int longest = sc.h_flags[1 + size_class], total = sc.h_flags[4 + size_class];
+    if (longest > cap || sc.h_flags[0]) {
+      if (longest > cap) cap = list_capacity(longest, n_tiles);
+      if ((rc = sgi_raster_reserve_lists(ctx, sc, cap, n_tiles, total > (1 << 16) ? total : (1 << 16), st))) return rc;
       sc.cap_of[size_class] = cap;
       sc.h_flags[0] = 0;                 // raised by the measuring run; the stream is idle
       sa.pairs = sc.d_pairs; sa.cap = cap; oa.cap = cap;
+      sa.spill = sc.d_spill; sa.spill_cap = sc.spill_cap; oa.spill_cap = sc.spill_cap;
       sc.needs_clear = true;
-      k_setup_bin<<<sb_blocks, 128, 0, st>>>(sa);
+      k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
       k_order<<<1, 1024, 0, st>>>(oa);
       ctx->launches += 2;
       SGI_CUDA(ctx, cudaGetLastError());
@@ -1310,7 +1400,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   TileArgs ta;
   ta.rec = sc.d_rec; ta.attr = sc.d_attr; ta.ovf_base = sc.d_ovf_base;
   ta.tile_n = sc.d_tile_n; ta.tile_order = sc.d_tile_order; ta.pairs = sc.d_pairs; ta.cap = cap;
-  ta.big_list = sc.d_big; ta.counters = sc.d_snap;
+  ta.big_list = sc.d_big; ta.counters = sc.d_snap; ta.spill = sc.d_spill; ta.bulk_flush = ctx->tile_bulk_flush;
   ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;
   ta.xyz = job.xyz; ta.nrm = job.nrm; ta.idx = job.idx;
@@ -1329,7 +1419,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 }
 
 void sgi_raster_free(SgiScratch& sc) {
-  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_order, sc.d_pairs, sc.d_tile_zmax};
+  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_order, sc.d_pairs, sc.d_tile_zmax, sc.d_spill};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (sc.h_flags) cudaFreeHost(sc.h_flags);
   if (sc.d_sticky) cudaFree(sc.d_sticky);
