@@ -349,29 +349,28 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
   r.prim_front = -1;
   int base = -1, nf = 0;
   if (t < a.T) nf = setup_triangle(a, t, r, base);
-  for (int f = 0; f < nf; f++) {
-    int slot = t;
-    if (f > 0) { slot = base + f - 1; r = a.rec[slot]; }
-    if (r.prim_front < 0) continue;
-    const int bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
-    const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
-    if (bx0 > bx1 || by0 > by1) continue;
+  // one record: un-binned big list / shared queue of large records / this thread alone, 4 tiles at a time with plain atomics
+  auto bin_plain = [&](const SgiRec& rr, int slot, bool small_done) {
+    if (rr.prim_front < 0) return;
+    const int bx0 = max((int)rr.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)rr.py0 >> SGI_TILE_LOG2, a.ty0);
+    const int bx1 = min((int)rr.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)rr.py1 >> SGI_TILE_LOG2, a.ty1);
+    if (bx0 > bx1 || by0 > by1) return;
     const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
+    if (nt <= 4 && small_done) return;                   // appended by the aggregated path below
     if (nt > SGI_BIG_TILES) {          // e.g. the floor: listing it in thousands of tiles costs more than letting each tile test it
       a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
-      continue;
+      return;
     }
     int k = -1;
     if (nt > 4) { k = atomicAdd(&q_n, 1); if (k >= SGI_SB_QCAP) k = -1; }
     if (k >= 0) {
       BinRec b;
-      b.X0 = r.X0; b.Y0 = r.Y0; b.X1 = r.X1; b.Y1 = r.Y1; b.X2 = r.X2; b.Y2 = r.Y2;
-      b.z0 = r.z0; b.dz1 = r.dz1; b.dz2 = r.dz2; b.ia = r.ia; b.zoff = r.zoff;
+      b.X0 = rr.X0; b.Y0 = rr.Y0; b.X1 = rr.X1; b.Y1 = rr.Y1; b.X2 = rr.X2; b.Y2 = rr.Y2;
+      b.z0 = rr.z0; b.dz1 = rr.dz1; b.dz2 = rr.dz2; b.ia = rr.ia; b.zoff = rr.zoff;
       b.slot = slot; b.bx0 = bx0; b.by0 = by0; b.bw = bw; b.nt = nt;
       q[k] = b;
-      continue;
+      return;
     }
-    // ---- small records (and the ones the shared queue had no room for): this thread alone, 4 tiles at a time
     for (int k0 = 0; k0 < nt; k0 += 4) {
       int tiles[4], pos[4];
 #pragma unroll
@@ -379,7 +378,7 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
         tiles[u] = -1;
         if (k0 + u < nt) {
           const int ty = by0 + (k0 + u) / bw, tx = bx0 + (k0 + u) % bw;
-          if ((nt == 1 || tile_overlaps(r, tx, ty, W, H)) && !tile_behind_scene(r, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
+          if ((nt == 1 || tile_overlaps(rr, tx, ty, W, H)) && !tile_behind_scene(rr, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
         }
       }
 #pragma unroll
@@ -389,7 +388,41 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
       for (int u = 0; u < 4; u++)
         if (tiles[u] >= 0) list_append(a, tiles[u], pos[u], slot);
     }
+  };
+  // ---- the triangle's own record when it overlaps <= 4 tiles (the common case): neighbouring triangles of a mesh land in the
+  //      same tile, so the lanes of a warp that append to the same list share ONE atomic (match_any), which takes the
+  //      serialisation of same-address atomics on the lists of dense tiles off the critical path
+  {
+    int tiles[4] = {-1, -1, -1, -1};
+    if (r.prim_front >= 0) {
+      const int bx0 = max((int)r.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)r.py0 >> SGI_TILE_LOG2, a.ty0);
+      const int bx1 = min((int)r.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)r.py1 >> SGI_TILE_LOG2, a.ty1);
+      const int bw = bx1 - bx0 + 1, nt = (bx0 <= bx1 && by0 <= by1) ? bw * (by1 - by0 + 1) : 0;
+      if (nt >= 1 && nt <= 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (u < nt) {
+            const int ty = by0 + u / bw, tx = bx0 + u % bw;
+            if ((nt == 1 || tile_overlaps(r, tx, ty, W, H)) && !tile_behind_scene(r, tx, ty, W, H, a.tile_zmax, a.tiles_x)) tiles[u] = ty * a.tiles_x + tx;
+          }
+      }
+    }
+    unsigned grp[4];
+    int pos[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {                        // all four atomics of the warp in flight before the first dependent store
+      grp[u] = __match_any_sync(0xffffffffu, tiles[u]);
+      pos[u] = 0;
+      if (tiles[u] >= 0 && lane == __ffs(grp[u]) - 1) pos[u] = atomicAdd(&a.tile_cnt[tiles[u]], __popc(grp[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      pos[u] = __shfl_sync(0xffffffffu, pos[u], __ffs(grp[u]) - 1);
+      if (tiles[u] >= 0) list_append(a, tiles[u], pos[u] + __popc(grp[u] & ((1u << lane) - 1u)), t);
+    }
   }
+  bin_plain(r, t, true);                                 // big / large: un-binned list or shared queue
+  for (int f = 1; f < nf; f++) { const int slot = base + f - 1; const SgiRec rr = a.rec[slot]; bin_plain(rr, slot, false); }
   __syncthreads();
   // ---- larger records of this CTA, flattened: inclusive prefix of their tile counts, then every thread takes pairs
   const int nq = min(q_n, SGI_SB_QCAP);
@@ -459,58 +492,25 @@ __device__ __forceinline__ int weight_bucket(int c) {
   return c < 2 ? c : 2 * l + ((c >> (l - 1)) & 1);
 }
 struct OrderArgs {
-  int32_t* tile_cnt; int32_t* tile_n; int n_tiles; int cap; int spill_cap;
+  int32_t* tile_cnt; int n_tiles; int cap; int spill_cap;
   int32_t* counters; int32_t* snap; volatile int32_t* h_flags; int32_t* d_sticky; int size_class;
-  int32_t* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
+  int2* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
 };
 #define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
 #define SGI_ORDER_REG 16        // tiles per thread held in registers (grids up to 16 384 tiles: an 8192^2 map); larger grids re-read
+// (one global round trip on the critical path: the cursors and the binner's counters are all loaded up front; everything
+//  else happens in registers and shared memory; the work items are fire-and-forget stores)
 __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   __shared__ int hist[SGI_ORDER_KEYS];
   __shared__ int red_sum[32], red_max[32];
   __shared__ int s_items, s_w;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- list lengths, totals, re-zero the cursors
-  int sum = 0, mx = 0;
-  for (int i0 = 0; i0 < a.n_tiles; i0 += 1024 * SGI_ORDER_REG) {
-    int c[SGI_ORDER_REG];
-#pragma unroll
-    for (int k = 0; k < SGI_ORDER_REG; k++) { const int i = i0 + k * 1024 + tid; c[k] = i < a.n_tiles ? a.tile_cnt[i] : 0; }
-#pragma unroll
-    for (int k = 0; k < SGI_ORDER_REG; k++) {
-      const int i = i0 + k * 1024 + tid;
-      if (i < a.n_tiles) {
-        const int n = min(c[k], a.cap);
-        a.tile_n[i] = c[k] > a.cap ? (n | 0x40000000) : n;      // bit 30: the tile has entries in the spill list
-        if (c[k]) a.tile_cnt[i] = 0;
-        sum += n; mx = max(mx, c[k]);
-      }
-    }
-  }
-  sum = __reduce_add_sync(0xffffffffu, sum); mx = __reduce_max_sync(0xffffffffu, mx);
-  if (lane == 0) { red_sum[warp] = sum; red_max[warp] = mx; }
-  for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
-  __syncthreads();
-  if (warp == 0) {
-    int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
-    if (lane == 0) {
-      const int spilled = a.counters[5];
-      a.snap[0] = a.counters[0]; a.snap[3] = a.counters[3]; a.snap[2] = s2; a.snap[5] = min(spilled, a.spill_cap);
-      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0;
-      // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
-      // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
-      // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
-      if (m2 > a.d_sticky[a.size_class]) { a.d_sticky[a.size_class] = m2; a.h_flags[1 + a.size_class] = m2; }
-      if (s2 + spilled > a.d_sticky[4 + a.size_class]) { a.d_sticky[4 + a.size_class] = s2 + spilled; a.h_flags[4 + a.size_class] = s2 + spilled; }
-      if (spilled > a.spill_cap) a.h_flags[0] = 1;              // entries were dropped: the frame is incomplete
-      s_w = a.split_floor > 0 ? max(a.split_floor, s2 / (8 * a.n_sm)) : 0x7FFFFFF;
-    }
-  }
   const int nl = a.gx * a.gy;
   const bool in_regs = nl <= 1024 * SGI_ORDER_REG;
-  // this thread's tiles of the job rectangle, i = tid + 1024 k: index and list length (spill flag stripped)
+  int c0 = 0, c3 = 0, c5 = 0, st_long = 0, st_tot = 0;
+  if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; }
+  // this thread's tiles of the job rectangle, i = tid + 1024 k: tile index and cursor
   int til[SGI_ORDER_REG], cnt[SGI_ORDER_REG];
-  __syncthreads();                                    // tile_n is complete
 #pragma unroll
   for (int k = 0; k < SGI_ORDER_REG; k++) {
     const int i = k * 1024 + tid;
@@ -518,15 +518,42 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     if (i < nl) {
       const int y = i / a.gx, x = i - y * a.gx;
       til[k] = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
-      cnt[k] = a.tile_n[til[k]] & 0x3FFFFFFF;
+      cnt[k] = a.tile_cnt[til[k]];
     }
   }
-  auto tile_of = [&](int i, int& c) -> int {          // grids beyond the register window: recompute
+  auto tile_of = [&](int i, int& c) -> int {          // grids beyond the register window: re-read (the cursors stay until the end)
     const int y = i / a.gx, x = i - y * a.gx;
     const int tl = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
-    c = a.tile_n[tl] & 0x3FFFFFFF;
+    c = a.tile_cnt[tl];
     return tl;
   };
+  // ---- totals (tiles outside the job rectangle are never listed: their cursors are zero)
+  int sum = 0, mx = 0;
+#pragma unroll
+  for (int k = 0; k < SGI_ORDER_REG; k++) { sum += min(cnt[k], a.cap); mx = max(mx, cnt[k]); }
+  if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); sum += min(c, a.cap); mx = max(mx, c); }
+  sum = __reduce_add_sync(0xffffffffu, sum); mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) { red_sum[warp] = sum; red_max[warp] = mx; }
+  for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
+  __syncthreads();
+  if (warp == 0) {
+    int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
+    if (lane == 0) {
+      a.snap[0] = c0; a.snap[3] = c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
+      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0;
+      // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
+      // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
+      // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
+      if (m2 > st_long) { a.d_sticky[a.size_class] = m2; a.h_flags[1 + a.size_class] = m2; }
+      if (s2 + c5 > st_tot) { a.d_sticky[4 + a.size_class] = s2 + c5; a.h_flags[4 + a.size_class] = s2 + c5; }
+      if (c5 > a.spill_cap) a.h_flags[0] = 1;                   // entries were dropped: the frame is incomplete
+      s_w = a.split_floor > 0 ? max(a.split_floor, s2 / (8 * a.n_sm)) : 0x7FFFFFF;
+    }
+  }
+  // list length per tile (what the tile kernel reads) | bit 30: the tile has further entries in the spill list
+#pragma unroll
+  for (int k = 0; k < SGI_ORDER_REG; k++) cnt[k] = cnt[k] > a.cap ? (a.cap | 0x40000000) : cnt[k];
+  auto len_of = [&](int c) -> int { return c > a.cap ? (a.cap | 0x40000000) : c; };
   for (;;) {                                          // largest subdivision that fits the launched grid
     __syncthreads();
     if (tid == 0) s_items = 0;
@@ -534,8 +561,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     const int w = s_w;
     int local = 0;
 #pragma unroll
-    for (int k = 0; k < SGI_ORDER_REG; k++) if (til[k] >= 0) local += 1 << (2 * split_level(cnt[k], w));
-    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(c, w)); }
+    for (int k = 0; k < SGI_ORDER_REG; k++) if (til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w));
+    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(min(c, a.cap), w)); }
     local = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0 && local) atomicAdd(&s_items, local);
     __syncthreads();
@@ -545,7 +572,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   }
   const int w = s_w;
   // ---- histogram of the items over (weight bucket, level): one shared atomic per distinct key per warp
-  auto key_of = [&](int c) -> int { const int lv = split_level(c, w); return (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv; };
+  auto key_of = [&](int len) -> int { const int c = len & 0x3FFFFFFF; const int lv = split_level(c, w); return (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv; };
   auto hist_step = [&](int key) {
     const unsigned grp = __match_any_sync(0xffffffffu, key);
     if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&hist[key], __popc(grp) << (2 * (key & 3)));
@@ -555,7 +582,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     if (k * 1024 < nl) hist_step(til[k] >= 0 ? key_of(cnt[k]) : -1);          // (warp-uniform condition)
   for (int i0 = 1024 * SGI_ORDER_REG; i0 < nl; i0 += 1024) {
     int key = -1;
-    if (i0 + tid < nl) { int c; tile_of(i0 + tid, c); key = key_of(c); }
+    if (i0 + tid < nl) { int c; tile_of(i0 + tid, c); key = key_of(len_of(c)); }
     hist_step(key);
   }
   __syncthreads();
@@ -572,8 +599,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     if (lane == 31) a.snap[4] = min(incl, a.max_items);
   }
   __syncthreads();
-  // ---- scatter
-  auto scatter_step = [&](int key, int tile) {
+  // ---- scatter the work items; re-zero the cursors for the next pass on this scratch set (no memset between passes)
+  auto scatter_step = [&](int key, int tile, int len) {
     const unsigned grp = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(grp) - 1;
     int at = 0;
@@ -583,23 +610,24 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     if (key >= 0) {
       at += __popc(grp & ((1u << lane) - 1u)) * nsub;
       for (int sidx = 0; sidx < nsub; sidx++)
-        if (at + sidx < a.max_items) a.order[at + sidx] = tile | (lv << 20) | (sidx << 22);
+        if (at + sidx < a.max_items) a.order[at + sidx] = make_int2(tile | (lv << 20) | (sidx << 22), len);
+      if (len) a.tile_cnt[tile] = 0;
     }
   };
 #pragma unroll
   for (int k = 0; k < SGI_ORDER_REG; k++)
-    if (k * 1024 < nl) scatter_step(til[k] >= 0 ? key_of(cnt[k]) : -1, til[k]);
+    if (k * 1024 < nl) scatter_step(til[k] >= 0 ? key_of(cnt[k]) : -1, til[k], cnt[k]);
   for (int i0 = 1024 * SGI_ORDER_REG; i0 < nl; i0 += 1024) {
-    int key = -1, tile = 0;
-    if (i0 + tid < nl) { int c; tile = tile_of(i0 + tid, c); key = key_of(c); }
-    scatter_step(key, tile);
+    int key = -1, tile = 0, len = 0;
+    if (i0 + tid < nl) { int c; tile = tile_of(i0 + tid, c); len = len_of(c); key = key_of(len); }
+    scatter_step(key, tile, len);
   }
 }
 
 // ---- per-tile rasterisation ----------------------------------------------------------------------------------
 struct TileArgs {
   const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
-  const int32_t* tile_n; const int32_t* tile_order; const int32_t* pairs; int cap;   // list of tile t: pairs[t * cap .. + tile_n[t])
+  const int2* tile_order; const int32_t* pairs; int cap;   // work items (item, list length); list of tile t: pairs[t * cap .. + length)
   const int32_t* big_list; const int32_t* counters;      // k_order's snapshot: [3] = number of un-binned big triangles, [4] = work items, [5] = spill entries
   const int2* spill;
   int bulk_flush;                                        // depth tiles: cp.async.bulk row copies (option "tile_bulk_flush")
@@ -737,8 +765,10 @@ struct TileSink {                  // where fragments go: the tile payload in sh
 // rasterised by that thread on the spot, the others are parked in shared memory and then rasterised
 // warp-cooperatively: the bounding box is walked in 8x4 blocks, 32 blocks conservatively tested at once (one
 // per lane), surviving blocks rasterised one per trip with one lane per pixel.
+// (min blocks = 1024 / NT: 64 registers per thread, i.e. 1024 resident threads per SM whatever the CTA size; left to itself
+//  the compiler took 80-94 registers for the small-CTA depth variants and occupancy fell to 768 threads)
 template <int MODE, int NT>
-__global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
+__global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned int* zt = reinterpret_cast<unsigned int*>(smem_raw);
   unsigned long long* kt = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -756,7 +786,8 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31;
   if ((int)blockIdx.x >= a.counters[4]) return;                  // the grid is an upper bound of the item count
-  const int item = a.tile_order[blockIdx.x];                     // work items of k_order, busiest first
+  const int2 item2 = a.tile_order[blockIdx.x];                   // work items of k_order, busiest first: (item, list length | spill flag)
+  const int item = item2.x;
   const int tile = item & 0xFFFFF, level = (item >> 20) & 3, sub = item >> 22;
   const int rs_log2 = SGI_TILE_LOG2 - level, rs = 1 << rs_log2;  // this CTA's region of the tile: rs x rs pixels at (qx0,qy0)
   const int qx0 = (sub & ((1 << level) - 1)) << rs_log2, qy0 = (sub >> level) << rs_log2;
@@ -764,7 +795,7 @@ __global__ void __launch_bounds__(NT) k_tile(const TileArgs a) {
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
   const int32_t* __restrict__ list = a.pairs + (size_t)tile * a.cap;
-  const int tn = a.tile_n[tile];
+  const int tn = item2.y;
   const int nlisted = tn & 0x3FFFFFFF, nbig = a.counters[3];
   const int nspill = (tn & 0x40000000) ? a.counters[5] : 0;    // the list was full: this tile's further entries are somewhere in the spill list
   const int nitems = nlisted + nbig + nspill;                  // this tile's list, then the un-binned big triangles, then the spill list (all tiles')
@@ -1226,11 +1257,10 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
   if (tiles + 1 > sc.tile_cap) {
     int cap = tiles + 1 + 64;
     SGI_CUDA(ctx, cudaStreamSynchronize(stream));
-    if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(32 + 2 * cap) * 4))) return rc;   // counters | snapshot | tile_cnt | tile_n
+    if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(32 + cap) * 4))) return rc;   // counters | snapshot | tile cursors
     sc.d_snap = sc.d_counters + 16;
     sc.d_tile_cnt = sc.d_counters + 32;
-    sc.d_tile_n = sc.d_tile_cnt + cap;
-    if ((rc = grow(ctx, (void**)&sc.d_tile_order, ((size_t)cap + SGI_SPLIT_EXTRA) * 4))) return rc;   // work items
+    if ((rc = grow(ctx, (void**)&sc.d_tile_order, ((size_t)cap + SGI_SPLIT_EXTRA) * 8))) return rc;   // work items
     if ((rc = grow(ctx, (void**)&sc.d_tile_zmax, (size_t)cap * 4))) return rc;
     sc.tile_cap = cap;
     sc.needs_clear = true;
@@ -1335,7 +1365,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   sc.cap_of[size_class] = cap;
 
   if (sc.needs_clear) {     // live counters | snapshot | cursors in one allocation: cleared once; k_order re-zeroes what the binner dirtied
-    SGI_CUDA(ctx, cudaMemsetAsync(sc.d_counters, 0, (size_t)(32 + 2 * sc.tile_cap) * 4, st));
+    SGI_CUDA(ctx, cudaMemsetAsync(sc.d_counters, 0, (size_t)(32 + sc.tile_cap) * 4, st));
     sc.needs_clear = false;
   }
 
@@ -1364,7 +1394,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   const int n_rect_tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
   const int max_items = n_rect_tiles + (15 * n_rect_tiles < SGI_SPLIT_EXTRA ? 15 * n_rect_tiles : SGI_SPLIT_EXTRA);
   OrderArgs oa;
-  oa.tile_cnt = sc.d_tile_cnt; oa.tile_n = sc.d_tile_n; oa.n_tiles = n_tiles; oa.cap = cap; oa.spill_cap = sc.spill_cap;
+  oa.tile_cnt = sc.d_tile_cnt; oa.n_tiles = n_tiles; oa.cap = cap; oa.spill_cap = sc.spill_cap;
   oa.counters = sc.d_counters; oa.snap = sc.d_snap; oa.h_flags = sc.h_flags; oa.d_sticky = sc.d_sticky; oa.size_class = size_class;
   oa.order = sc.d_tile_order; oa.tiles_x = tiles_x; oa.tx0 = tx0; oa.ty0 = ty0; oa.gx = tx1 - tx0 + 1; oa.gy = ty1 - ty0 + 1;
   oa.busiest_first = ctx->tile_order; oa.max_items = max_items; oa.split_floor = ctx->tile_split; oa.n_sm = ctx->n_sm;
@@ -1399,7 +1429,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   TileArgs ta;
   ta.rec = sc.d_rec; ta.attr = sc.d_attr; ta.ovf_base = sc.d_ovf_base;
-  ta.tile_n = sc.d_tile_n; ta.tile_order = sc.d_tile_order; ta.pairs = sc.d_pairs; ta.cap = cap;
+  ta.tile_order = sc.d_tile_order; ta.pairs = sc.d_pairs; ta.cap = cap;
   ta.big_list = sc.d_big; ta.counters = sc.d_snap; ta.spill = sc.d_spill; ta.bulk_flush = ctx->tile_bulk_flush;
   ta.tiles_x = tiles_x; ta.tx0 = tx0; ta.ty0 = ty0;
   ta.W = job.W; ta.H = job.H; ta.rx0 = rx0; ta.ry0 = ry0; ta.rx1 = rx1; ta.ry1 = ry1;

@@ -26,15 +26,18 @@ def probe(name, W, H, S, tech, iters=20, **kw):
     print(f"{name} {W}x{H} S={S} {tech} {kw}: wall {wall:.3f} ms/frame | " + " ".join(f"{k}={v:.3f}ms" for k, v in out.items()), flush=True)
     ctx.close()
 
-def probe_app(workload, iters=10):
-    """A bench.py workload through the C++ host (ShadowApp)."""
+def probe_app(workload, iters=10, overlap=True):
+    """A bench.py workload through the C++ host (ShadowApp).  overlap=False: passes one after the other on one stream, so the
+    per-kernel event times are the kernels' own durations."""
     from globalillumination_b200 import hostapi, scenes
     w = scenes.WORKLOADS[workload]
     app = hostapi.App(0)
     app.load_scene(scenes.write_config(workload))
     app.configure(w["W"], w["H"], w["S"]); app.set_technique(w["technique"]); app.set(**w["params"])
     ctx = app.context()
-    for _ in range(2):
+    if not overlap:
+        ctx.set_option("overlap_passes", 0)
+    for _ in range(3):
         app.display(w["program"])
     ctx.synchronize()
     ctx.enable_timing(True); ctx.reset_timing()
