@@ -208,6 +208,128 @@ def run_reference(args, w, cfg_path):
     }
 
 
+SHARDED_N1_CACHE = os.path.join(ROOT, "gpurun_out", ".sharded_n1.json")
+
+
+def run_sharded(rank, world, local_rank, steps=24, warmup=4):
+    """The north-star multi-GPU partitioning, measured at every N (same keys at N = 1, 2, 4, 8): config c5 on the reference's
+    SanDiego geometry (16 lights x 8192^2 depth maps, 7680x4320), ONE frame shared by all ranks.  Rank r owns lights
+    l = r (mod N): it renders only those depth maps; the camera pass is reduced to primitive ids, each rank rasterising its own
+    screen strip, strips all-gathered over NCCL (4 B/pixel); the accumulation kernel resolves positions from the ids and sums the
+    rank's lights; partial sums are reduce-scattered and divided (sgi_reduce_lights), so rank r ends with the final visibility
+    of its strip.  Both collectives are issued by the library (C ABI) on its communication stream and overlap the next frame's
+    depth passes.  Time = one CUDA-event pair around `steps` frames on every rank + the tail of the last exchange, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from globalillumination_b200 import capi, hostapi, scenes
+    name = "c5_sandiego"
+    w = scenes.WORKLOADS[name]
+    app = hostapi.App(local_rank)
+    app.set_scene(scenes.golden_scene(w["golden"]))
+    app.configure(w["W"], w["H"], w["S"])
+    app.set_technique(w["technique"])
+    app.set(**w["params"])
+    app.set(fusedMonteCarlo=1, animationOn=1, animation=-1800.0)
+    if world > 1:
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        app.comm_init(uid[0], rank, world)
+    ctx = app.context()
+    stream = torch.cuda.Stream(device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    n_l = w["params"]["numberOfSamples"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(n):
+                app.display(w["program"]); app.step_animation(ANIMATION_STEP)
+            ctx.join()
+            e1.record(stream)
+            ctx.synchronize()                    # includes the communication stream: the last frame's exchange has landed
+        t_host = time.perf_counter()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / n
+
+    with torch.cuda.stream(stream):
+        for attempt in range(6):
+            try:
+                for _ in range(warmup):
+                    app.display(w["program"]); app.step_animation(ANIMATION_STEP)
+                ctx.synchronize()
+                break
+            except (capi.SgiError, hostapi.HostError) as e:      # tile lists grown from the first measured frame: warm up again
+                if "overflow" not in str(e) or attempt == 5:
+                    raise
+    ms_frame = timed(steps)
+    # what the exchanges cost on the critical path: the same frames with the collectives skipped (camera static: the gathered ids stay valid)
+    ms_nocomm = None
+    if world > 1:
+        app.set(commSkip=1)
+        timed(2)
+        ms_nocomm = timed(steps)
+        app.set(commSkip=0)
+        timed(1)
+    # rank 0's own pass times (passes one after the other, CUDA events around each)
+    ctx.set_option("overlap_passes", 0)
+    ctx.enable_timing(True); ctx.reset_timing()
+    n_p = 6
+    with torch.cuda.stream(stream):
+        for _ in range(n_p):
+            app.display(w["program"]); app.step_animation(ANIMATION_STEP)
+        ctx.synchronize()
+    passes = {}
+    for pname in capi.PASS:
+        ms, n = ctx.pass_time_ms(pname)
+        if n:
+            passes[pname] = ms / n_p
+    ctx.enable_timing(False)
+    ctx.set_option("overlap_passes", 1)
+    r0, r1 = ctx.comm_strip(rank) if world > 1 else (0, w["H"])
+    vis = ctx.read("visibility")[r0:r1]
+    lit = float((vis == 1.0).mean())
+    xyz, nrm, idx = app.scene_arrays()
+    app.close()
+    if rank != 0:
+        return None
+    px = w["W"] * w["H"]
+    rec = {
+        "workload": name, "mode": "lights" if world > 1 else "single GPU (same code path, no exchange)", "n_gpus": world,
+        "W": w["W"], "H": w["H"], "shadow_map": w["S"], "lights": n_l, "lights_per_rank": max(1, n_l // world), "triangles": int(idx.shape[0]),
+        "scene": w["scene"], "frames_per_s": 1e3 / ms_frame, "ms_per_frame": ms_frame, "steps": steps, "scaling": "strong",
+        "collective": ("ncclAllGather(primitive-id strips, in place, %d MB) + ncclReduceScatter(fp32 partial visibility, in place, %d MB), "
+                       "issued by the C ABI (sgi_gather / sgi_reduce_lights)" % (px * 4 // 1000000, px * 4 // 1000000)) if world > 1 else None,
+        "ms_per_frame_without_exchanges": ms_nocomm, "exposed_comm_ms": (ms_frame - ms_nocomm) if ms_nocomm is not None else 0.0,
+        "pass_ms_rank0": passes, "strip_rows_rank0": [r0, r1], "lit_fraction_rank0_strip": lit,
+    }
+    try:
+        if world == 1:
+            os.makedirs(os.path.dirname(SHARDED_N1_CACHE), exist_ok=True)
+            with open(SHARDED_N1_CACHE, "w") as f:
+                json.dump({"ms_per_frame": ms_frame}, f)
+            rec["speedup_vs_n1"] = 1.0
+        elif os.path.exists(SHARDED_N1_CACHE):
+            with open(SHARDED_N1_CACHE) as f:
+                rec["speedup_vs_n1"] = json.load(f)["ms_per_frame"] / ms_frame
+            rec["speedup_vs_n1_source"] = "N=1 record of an earlier run on this box (gpurun_out/.sharded_n1.json)"
+        else:
+            rec["speedup_vs_n1"] = None
+    except Exception:
+        rec["speedup_vs_n1"] = None
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +339,7 @@ def main():
     ap.add_argument("--workload", default="c2_sponza")
     ap.add_argument("--mode", default="frames", choices=["frames", "lights"], help="N>1: frame-parallel, or light shards of one frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the `sharded` record (config c5 light shards, every N)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -455,6 +578,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(t[0]), float(t[1])
+    sharded = None
+    if not args.no_sharded and args.workload == "c2_sponza" and not lights_mode:
+        app.close()                                   # free the headline context's targets first
+        sharded = run_sharded(rank, world, local_rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -523,6 +650,8 @@ def main():
     }
     if early:
         out["with_pcss_early_out"] = early
+    if sharded:
+        out["sharded"] = sharded
     if not args.no_cpu_baseline and world == 1:
         a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup = 3, 1
         ref = run_reference(a2, w, cfg_path)

@@ -16,7 +16,7 @@ TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf
 MOMENT_TECHS = ("vsm", "esm", "evsm", "msm")
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
        "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11,
-       "moments": 12, "moments_x": 13, "moments_filtered": 14}
+       "moments": 12, "moments_x": 13, "moments_filtered": 14, "prim_id": 15}
 PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
         "tile_gbuffer": 6, "tile_sv": 7, "moment_filter": 8}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
@@ -35,7 +35,7 @@ class SgiParams(C.Structure):
         ("polygon_offset_factor", C.c_float), ("polygon_offset_units", C.c_float),
         ("sv_depth_func", C.c_int32), ("sv_infinity", C.c_int32),
         ("rect_x0", C.c_int32), ("rect_y0", C.c_int32), ("rect_x1", C.c_int32), ("rect_y1", C.c_int32),
-        ("multi_partial", C.c_int32),
+        ("multi_partial", C.c_int32), ("multi_fused", C.c_int32), ("sv_silhouette", C.c_int32), ("sv_zfail", C.c_int32),
     ]
 
 
@@ -43,6 +43,7 @@ EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility", "sgi_filter_shadow_map", "sgi_moment_quantization",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
+    "sgi_render_prim_ids", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -64,6 +65,8 @@ def load():
         _lib.sgi_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]
         _lib.sgi_device_ptr.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _lib.sgi_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.sgi_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.sgi_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
     return _lib
 
 
@@ -86,6 +89,15 @@ def moment_quantization():
     m, mi, t = np.zeros(16, np.float32), np.zeros(16, np.float32), np.zeros(4, np.float32)
     load().sgi_moment_quantization(_fp(m), _fp(mi), _fp(t))
     return m, mi, t
+
+
+def comm_unique_id():
+    """sgi_comm_unique_id: the 128-byte NCCL id (made on rank 0; ship it to the other ranks and pass it to comm_init)."""
+    buf = (C.c_char * 128)()
+    rc = load().sgi_comm_unique_id(buf, 128)
+    if rc != 0:
+        raise SgiError(rc, "sgi_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(buf)
 
 
 def default_params(technique="hard", **kw):
@@ -178,6 +190,28 @@ class Context:
     def render_gbuffer(self):
         self._ck(self.lib.sgi_render_gbuffer(self.h))
 
+    def render_prim_ids(self):
+        self._ck(self.lib.sgi_render_prim_ids(self.h))
+
+    # ---- multi-GPU (NCCL inside the library) ----
+    def comm_init(self, unique_id, rank, nranks):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.sgi_comm_init(self.h, buf, 128, int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.sgi_comm_destroy(self.h))
+
+    def comm_strip(self, rank):
+        r0, r1 = C.c_int32(), C.c_int32()
+        self._ck(self.lib.sgi_comm_strip(self.h, int(rank), C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
+
+    def gather(self, which):
+        self._ck(self.lib.sgi_gather(self.h, BUF[which]))
+
+    def reduce_lights(self, total_lights):
+        self._ck(self.lib.sgi_reduce_lights(self.h, int(total_lights)))
+
     def filter_shadow_map(self):
         self._ck(self.lib.sgi_filter_shadow_map(self.h))
 
@@ -197,6 +231,7 @@ class Context:
             "cam_depth": ((H, W), np.float32), "visibility": ((H, W), np.float32), "sv_count": ((H, W), np.int32),
             "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "edt_nearest": ((H, W, 2), np.int16), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
             "moments": ((SH, SW, 4), np.float32), "moments_x": ((H, W, 4), np.float32), "moments_filtered": ((H, W, 4), np.float32),
+            "prim_id": ((H, W), np.uint32),
         }[which]
 
     def read(self, which, out=None):

@@ -12,7 +12,7 @@
 
 static void sync_all_streams(sgi_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
-  cudaStream_t others[] = {ctx->aux_stream, ctx->vis_stream, ctx->copy_stream, ctx->upload_stream, ctx->lane_stream[0], ctx->lane_stream[1], ctx->lane_stream[2]};
+  cudaStream_t others[] = {ctx->aux_stream, ctx->vis_stream, ctx->copy_stream, ctx->upload_stream, ctx->lane_stream[0], ctx->lane_stream[1], ctx->lane_stream[2], ctx->comm_stream};
   for (cudaStream_t s : others) if (s) cudaStreamSynchronize(s);
 }
 
@@ -213,6 +213,10 @@ int sgi_destroy(sgi_ctx* ctx) {
   cudaSetDevice(ctx->device);
   sync_all_streams(ctx);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) { if (ctx->buf[b]) cudaFree(ctx->buf[b]); if (ctx->alt[b]) cudaFree(ctx->alt[b]); }
+  sgi_comm_destroy(ctx);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->ev_comm_in) cudaEventDestroy(ctx->ev_comm_in);
+  for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->ev_comm_done[b]) cudaEventDestroy(ctx->ev_comm_done[b]);
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
   if (ctx->vis_spare) cudaFree(ctx->vis_spare);
   if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
@@ -344,7 +348,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   ctx->d_xyz = ctx->d_xyz_set[s]; ctx->d_nrm = ctx->d_nrm_set[s]; ctx->d_idx = ctx->d_idx_set[s];
   ctx->V = V; ctx->T = T;
   mark_gbuffer_use(ctx);
-  ctx->gbuffer_valid = ctx->shadow_map_valid = false;
+  ctx->gbuffer_valid = ctx->shadow_map_valid = false; ctx->ids_valid = false;
   ctx->moments_tech = ctx->filtered_tech = -1;        // the moment target / filtered map describe the previous geometry
   return SGI_OK;
 }
@@ -393,19 +397,22 @@ int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const 
   sgi_join_gbuffer(ctx);
   memcpy(ctx->cam_mvp, mvp, 64); memcpy(ctx->cam_mv, mv, 64); memcpy(ctx->cam_nm, nm, 36);
   int rc;
-  size_t px = (size_t)W * H;
+  const bool resized = W != ctx->W || H != ctx->H;
+  ctx->W = W; ctx->H = H;
+  // screen targets are padded to comm_n equal strips (sgi_comm.cu), so that a multi-GPU exchange is one in-place collective
+  const size_t px = sgi_padded_pixels(ctx);
   if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_POS, px * 16))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_NRM, px * 16))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_CAM_DEPTH, px * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_VISIBILITY, px * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_GBUF_ALBEDO, px * 16))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SHADED, px * 16))) return rc;
-  if (W != ctx->W || H != ctx->H) {
+  if (resized) {
     SGI_CUDA(ctx, cudaMemsetAsync(ctx->buf[SGI_BUF_VISIBILITY], 0, px * 4, ctx->stream));
     ctx->scratch[1].sized[SGI_MODE_GBUFFER] = ctx->scratch[0].sized[SGI_MODE_SVCOUNT] = false;
   }
   mark_gbuffer_use(ctx);
-  ctx->W = W; ctx->H = H; ctx->has_camera = true; ctx->gbuffer_valid = false;
+  ctx->has_camera = true; ctx->gbuffer_valid = false; ctx->ids_valid = false;
   return SGI_OK;
 }
 
@@ -565,6 +572,10 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   }
   sgi_wait_reads_of(ctx, SGI_BUF_GBUF_POS, st); sgi_wait_reads_of(ctx, SGI_BUF_GBUF_NRM, st); sgi_wait_reads_of(ctx, SGI_BUF_CAM_DEPTH, st);
   sgi_wait_reads_of(ctx, SGI_BUF_GBUF_ALBEDO, st);
+  for (int b : {SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM, SGI_BUF_CAM_DEPTH, SGI_BUF_GBUF_ALBEDO}) sgi_wait_comm(ctx, b, st);
+  // a fused many-light pass still resolving positions from this scratch set's records (previous frame, visibility stream)
+  if (ctx->rec_reader >= 0) { SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_vis[ctx->rec_reader], 0)); ctx->rec_reader = -1; }
+  ctx->ids_valid = false;
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
   SgiRasterJob job;
   memset(&job, 0, sizeof(job));
@@ -587,6 +598,45 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
     SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
   }
   ctx->gbuffer_valid = true;
+  return SGI_OK;
+}
+
+int sgi_render_prim_ids(sgi_ctx* ctx) {
+  if (!ctx) return SGI_ERR_INVALID;
+  if (!ctx->d_idx || !ctx->has_camera) { ctx->err = "sgi_render_prim_ids: set mesh and camera first"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  int rc = ensure_buf(ctx, SGI_BUF_PRIM_ID, sgi_padded_pixels(ctx) * 4);
+  if (rc) return rc;
+  // same stream protocol as sgi_render_gbuffer: auxiliary stream, forked from the last point of the main stream that touched the mesh
+  sgi_join_gbuffer(ctx);
+  cudaStream_t st = ctx->overlap_passes ? ctx->aux_stream : ctx->stream;
+  if (ctx->overlap_passes) {
+    if (ctx->gbuf_exposed) SGI_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+  }
+  // the previous frame's fused many-light pass reads this buffer and this scratch set's records on the visibility stream
+  if (ctx->rec_reader >= 0) { SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_vis[ctx->rec_reader], 0)); ctx->rec_reader = -1; }
+  sgi_wait_reads_of(ctx, SGI_BUF_PRIM_ID, st);
+  sgi_wait_comm(ctx, SGI_BUF_PRIM_ID, st);
+  int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
+  SgiRasterJob job;
+  memset(&job, 0, sizeof(job));
+  job.mode = SGI_MODE_IDS;
+  job.xyz = ctx->d_xyz; job.nrm = ctx->d_nrm; job.idx = ctx->d_idx; job.T = ctx->T;
+  memcpy(job.mvp, ctx->cam_mvp, 64);
+  job.W = ctx->W; job.H = ctx->H;
+  job.ids = (unsigned int*)ctx->buf[SGI_BUF_PRIM_ID];
+  job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
+  rc = sgi_raster_run(ctx, job, 1, st);
+  if (rc) return rc;
+  sgi_timing_end(ctx, SGI_PASS_GBUFFER, slot, st);
+  if (ctx->overlap_passes) {
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_gbuf_done, st));
+    ctx->gbuf_in_flight = true; ctx->gbuf_done_recorded = true;
+  } else {
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
+  }
+  ctx->ids_valid = true; ctx->gbuffer_valid = false;      // the scratch set's records now describe this pass
   return SGI_OK;
 }
 
@@ -621,8 +671,11 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
       ctx->err = "sgi_compute_visibility: render and filter the moment shadow map and render the G-buffer first";
       return SGI_ERR_INVALID;
     }
-  } else
-  if (!ctx->gbuffer_valid || !ctx->shadow_map_valid) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
+  } else {
+    const bool fused = ctx->params.technique == SGI_TECH_MULTI_HARD && ctx->params.multi_fused;
+    if (fused && (!ctx->ids_valid || !ctx->shadow_map_valid)) { ctx->err = "sgi_compute_visibility: multi_fused needs sgi_render_prim_ids and the shadow maps first"; return SGI_ERR_INVALID; }
+    if (!fused && (!ctx->gbuffer_valid || !ctx->shadow_map_valid)) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
+  }
   cudaSetDevice(ctx->device);
   int rc;
   // With pass overlap on, the shadow pass goes to the visibility stream: it waits for everything queued on the main stream
@@ -665,6 +718,10 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
     if ((rc = ensure_buf(ctx, SGI_BUF_EDT_NEAREST, (size_t)ctx->W * ctx->H * 4))) return rc;
     sgi_wait_reads_of(ctx, SGI_BUF_EDT_NEAREST, vs);
   }
+  // collectives still running on the buffers this pass reads / overwrites (gathered primitive ids; the previous frame's exchange
+  // of the visibility buffer)
+  sgi_wait_comm(ctx, SGI_BUF_PRIM_ID, vs); sgi_wait_comm(ctx, SGI_BUF_VISIBILITY, vs);
+  for (int b : {SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM}) sgi_wait_comm(ctx, b, vs);
   int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, vs);
   rc = sgi_shadow_run(ctx, vs);
   if (rc) return rc;
@@ -674,6 +731,7 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
     SGI_CUDA(ctx, cudaEventRecord(ctx->ev_vis[e], vs));
     ctx->vis_last = e; ctx->vis_in_flight = true;
     ctx->sm_reader_cur = e; ctx->gb_reader_cur = e;        // this pass reads the current instances of both target groups
+    if (ctx->params.technique == SGI_TECH_MULTI_HARD && ctx->params.multi_fused) ctx->rec_reader = e;   // ... and the camera pass's records
     // a caller holding the visibility buffer's device pointer queues its own work on the context's stream: keep that
     // stream ordered after the pass for it
     if (ctx->vis_exposed) { if ((rc = sgi_join_vis(ctx))) return rc; }
@@ -688,6 +746,7 @@ int sgi_shade_phong(sgi_ctx* ctx, const float clear_rgba[4]) {
   int rc = sgi_join_gbuffer(ctx);
   if (rc) return rc;
   if ((rc = sgi_join_vis(ctx))) return rc;
+  for (int b : {SGI_BUF_VISIBILITY, SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM, SGI_BUF_GBUF_ALBEDO, SGI_BUF_SHADED}) sgi_wait_comm(ctx, b, ctx->stream);
   sgi_wait_reads_of(ctx, SGI_BUF_SHADED, ctx->stream);
   if (ctx->has_rgb && ctx->rgb_V != ctx->V) { ctx->err = "sgi_shade_phong: colours do not match the current mesh"; return SGI_ERR_INVALID; }
   rc = sgi_shade_run(ctx, clear_rgba);
@@ -700,7 +759,7 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   if (!ctx->gbuffer_valid) { ctx->err = "sgi_compute_shadow_volume: render the G-buffer (depth pre-pass) first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
   int rc;
-  size_t px = (size_t)ctx->W * ctx->H;
+  size_t px = sgi_padded_pixels(ctx);
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_COUNT, px * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_STENCIL, px))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_XYZ, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
@@ -741,6 +800,8 @@ int sgi_synchronize(sgi_ctx* ctx) {
   sgi_join_gbuffer(ctx); sgi_join_vis(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->comm_stream) SGI_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  for (int b = 0; b < SGI_BUF_COUNT_; b++) ctx->comm_pending[b] = false;
   for (int k = 0; k < 4; k++) ctx->read_pending[k] = false;
   if (ctx->timing) sgi_timing_drain(ctx);
   return check_overflow(ctx);
@@ -751,6 +812,7 @@ int sgi_read(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes) {
   if (!ctx->buf[which] || bytes > ctx->buf_bytes[which]) { ctx->err = "sgi_read: buffer not produced yet or size too large"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
   sgi_join_gbuffer(ctx); sgi_join_vis(ctx);
+  sgi_wait_comm(ctx, which, ctx->stream);
   SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->stream));
   mark_gbuffer_use(ctx);
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -768,6 +830,7 @@ int sgi_read_async(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes, int32_t
   SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
   if (ctx->vis_in_flight && ctx->vis_last >= 0)                                 // ... or on the visibility stream (not joined: the main stream keeps going)
     SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_vis[ctx->vis_last], 0));
+  sgi_wait_comm(ctx, which, ctx->copy_stream);
   SGI_CUDA(ctx, cudaMemcpyAsync(dst, ctx->buf[which], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
   SGI_CUDA(ctx, cudaEventRecord(ctx->read_done[t], ctx->copy_stream));
   ctx->read_pending[t] = true;
@@ -786,6 +849,7 @@ int sgi_read_wait(sgi_ctx* ctx, int32_t ticket) {
 int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** dptr, size_t* bytes) {
   if (!ctx || which < 0 || which >= SGI_BUF_COUNT_ || !dptr) return SGI_ERR_INVALID;
   sgi_join_gbuffer(ctx); sgi_join_vis(ctx);   // work queued on the main stream after this call sees finished passes
+  sgi_wait_comm(ctx, which, ctx->stream);
   if (which == SGI_BUF_GBUF_POS || which == SGI_BUF_GBUF_NRM || which == SGI_BUF_CAM_DEPTH || which == SGI_BUF_GBUF_ALBEDO) ctx->gbuf_exposed = true;
   if (which == SGI_BUF_SHADOW_MAP) ctx->sm_exposed = true;     // a lent-out pointer pins the instance: no more switching
   if (which == SGI_BUF_VISIBILITY || which == SGI_BUF_EDT_NEAREST) ctx->vis_exposed = true;

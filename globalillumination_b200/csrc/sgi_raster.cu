@@ -27,7 +27,7 @@
 #include "sgi_moments.cuh"
 
 // modes whose tile payload is the 64-bit (depth | primitive) key: the attribute passes that need to know the winning triangle
-#define SGI_KEYED(M) ((M) == SGI_MODE_GBUFFER || (M) == SGI_MODE_GBUFFER_RGB || (M) == SGI_MODE_MOMENTS)
+#define SGI_KEYED(M) ((M) == SGI_MODE_GBUFFER || (M) == SGI_MODE_GBUFFER_RGB || (M) == SGI_MODE_MOMENTS || (M) == SGI_MODE_IDS)
 
 namespace {
 
@@ -511,14 +511,21 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; }
   // this thread's tiles of the job rectangle, i = tid + 1024 k: tile index and cursor
   int til[SGI_ORDER_REG], cnt[SGI_ORDER_REG];
+  {
+    // (x, y) of tile i = tid + 1024 k in the rectangle, stepped without a division per tile
+    const int qy = 1024 / a.gx, qx = 1024 - qy * a.gx;
+    int y = tid / a.gx, x = tid - y * a.gx;
 #pragma unroll
-  for (int k = 0; k < SGI_ORDER_REG; k++) {
-    const int i = k * 1024 + tid;
-    til[k] = -1; cnt[k] = 0;
-    if (i < nl) {
-      const int y = i / a.gx, x = i - y * a.gx;
-      til[k] = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
-      cnt[k] = a.tile_cnt[til[k]];
+    for (int k = 0; k < SGI_ORDER_REG; k++) {
+      til[k] = -1; cnt[k] = 0;
+      if (k * 1024 < nl) {                             // (warp-uniform)
+        if (k * 1024 + tid < nl) {
+          til[k] = (a.ty0 + y) * a.tiles_x + a.tx0 + x;
+          cnt[k] = a.tile_cnt[til[k]];
+        }
+        y += qy; x += qx;
+        if (x >= a.gx) { x -= a.gx; y++; }
+      }
     }
   }
   auto tile_of = [&](int i, int& c) -> int {          // grids beyond the register window: re-read (the cursors stay until the end)
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   // ---- totals (tiles outside the job rectangle are never listed: their cursors are zero)
   int sum = 0, mx = 0;
 #pragma unroll
-  for (int k = 0; k < SGI_ORDER_REG; k++) { sum += min(cnt[k], a.cap); mx = max(mx, cnt[k]); }
+  for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl) { sum += min(cnt[k], a.cap); mx = max(mx, cnt[k]); }
   if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); sum += min(c, a.cap); mx = max(mx, c); }
   sum = __reduce_add_sync(0xffffffffu, sum); mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) { red_sum[warp] = sum; red_max[warp] = mx; }
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   }
   // list length per tile (what the tile kernel reads) | bit 30: the tile has further entries in the spill list
 #pragma unroll
-  for (int k = 0; k < SGI_ORDER_REG; k++) cnt[k] = cnt[k] > a.cap ? (a.cap | 0x40000000) : cnt[k];
+  for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl) cnt[k] = cnt[k] > a.cap ? (a.cap | 0x40000000) : cnt[k];
   auto len_of = [&](int c) -> int { return c > a.cap ? (a.cap | 0x40000000) : c; };
   for (;;) {                                          // largest subdivision that fits the launched grid
     __syncthreads();
@@ -561,7 +568,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     const int w = s_w;
     int local = 0;
 #pragma unroll
-    for (int k = 0; k < SGI_ORDER_REG; k++) if (til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w));
+    for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl && til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w));
     if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(min(c, a.cap), w)); }
     local = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0 && local) atomicAdd(&s_items, local);
@@ -638,6 +645,7 @@ struct TileArgs {
   const float* rgb; float4* albedo4;
   const float* scene_depth; int depth_func; int32_t* count; uint8_t* stencil;
   float4* mom4; int mom_tech, z_near, z_far; float mq[16], mqt[4];      // MOMENTS
+  unsigned int* ids;                                                   // IDS
 };
 
 #define ONE_BITS 0x3F800000u
@@ -841,6 +849,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     }
   }
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
+  // the nearest-first order only pays where hierarchical depth has something to cull: lists of a few dozen triangles skip it
+  const bool sort_items = nitems > 48;
 
   for (int base = 0; base < nitems; base += NT) {
     if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; fc_count = 0; zq_min = 0xFFFFFFFFu; zq_max = 0u; }
@@ -917,7 +927,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
               if (f < SGI_MAX_FULL) { fc_list[f] = k; my_ng = 0; }
             }
           }
-          atomicMin(&zq_min, my_zlo); atomicMax(&zq_max, my_zlo);
+          if (sort_items) { atomicMin(&zq_min, my_zlo); atomicMax(&zq_max, my_zlo); }
+          else if (my_ng > 0) {          // short list: work items in arrival order, no sort phases (three barriers less per chunk)
+            const int g0 = atomicAdd(&g_count, my_ng);
+            for (int g = 0; g < my_ng; g++) tq.group[g0 + g] = (k << 3) | g;
+          }
         }
       }
     }
@@ -925,6 +939,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     // nearest-first issue order: counting sort of the work items on their depth bound, so that the block bounds
     // tighten early and the triangles behind them are culled
     int my_b = 0;
+    if (sort_items) {
     if (my_k >= 0) {
       const unsigned int lo = zq_min, span = zq_max - lo + 1u;
       my_b = (int)(((unsigned long long)(my_zlo - lo) * SGI_ZBUCKETS) / span);
@@ -944,6 +959,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
       for (int g = 0; g < my_ng; g++) tq.group[g0 + g] = (my_k << 3) | g;
     }
     __syncthreads();
+    }
     const int ngroups = g_count;
     {  // region-covering triangles first: every thread takes its pixels of the region
       const int nfull = min(fc_count, SGI_MAX_FULL);
@@ -1122,6 +1138,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     } else {
       const unsigned long long key = empty ? 0xFFFFFFFFull : kt[p];
       const unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
+      if (MODE == SGI_MODE_IDS) { a.ids[o] = lo32; continue; }     // visibility only: the winning primitive (0xFFFFFFFF = background)
       if (MODE == SGI_MODE_MOMENTS) {
         // Moments.frag / Exponential.frag / ExponentialMoments.frag on the winning fragment: a function of the un-offset depth
         // plane at this texel and at its two quad partners (dFdx / dFdy), fused into the flush - the moment target crosses
@@ -1326,6 +1343,9 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
 static int tile_threads(const sgi_ctx* ctx, int n_tiles, int mode) {
   if (ctx->tile_threads) return ctx->tile_threads;
   if (mode == SGI_MODE_SVCOUNT) return 1024;
+  // (round 2, after the 64-register cap: the depth pass of a 2048^2 map - 1024 tiles - is faster with 256-thread CTAs, 75 vs 87 us;
+  //  the keyed G-buffer pass at 1080p - 510 tiles - stays at 512, 82 vs 123 us; profiles/r2_tile_ab.txt)
+  if (mode == SGI_MODE_DEPTH) return n_tiles <= 300 ? 1024 : (n_tiles <= 600 ? 512 : 256);
   return n_tiles <= 300 ? 1024 : (n_tiles <= 1200 ? 512 : 256);
 }
 
@@ -1382,7 +1402,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
   sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
   sa.no_far_clip = job.no_far_clip;
-  sa.rec = sc.d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER) ? sc.d_attr : nullptr;
+  sa.rec = sc.d_rec; sa.attr = (job.mode == SGI_MODE_GBUFFER || job.mode == SGI_MODE_IDS) ? sc.d_attr : nullptr;
   sa.ovf_base = sc.d_ovf_base; sa.counters = sc.d_counters;
   sa.tiles_x = tiles_x; sa.tx0 = tx0; sa.ty0 = ty0; sa.tx1 = tx1; sa.ty1 = ty1;
   sa.tile_cnt = sc.d_tile_cnt; sa.pairs = sc.d_pairs; sa.cap = cap; sa.big_list = sc.d_big; sa.tile_zmax = tile_zmax;
@@ -1437,13 +1457,14 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.depth = job.depth; ta.pos4 = job.pos4; ta.nrm4 = job.nrm4;
   ta.rgb = job.rgb; ta.albedo4 = job.albedo4;
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
-  ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far;
+  ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
   for (int k = 0; k < 16; k++) ta.mq[k] = job.mq[k];
   for (int k = 0; k < 4; k++) ta.mqt[k] = job.mqt[k];
   dim3 grid(max_items);
   if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_GBUFFER) rc = (job.rgb && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, n_rect_tiles, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_MOMENTS) rc = launch_tile<SGI_MODE_MOMENTS>(ctx, ta, grid, n_rect_tiles, st);
+  else if (job.mode == SGI_MODE_IDS) rc = launch_tile<SGI_MODE_IDS>(ctx, ta, grid, n_rect_tiles, st);
   else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
   return rc;
 }

@@ -28,6 +28,8 @@ struct VisArgs {
   float bs_q[SGI_MAX_PCF_TAPS]; int bs_w0, bs_n;              // (float(w)*blockerSearchWidth)/filterWidth      (PlausibleSoftShadow.frag:180)
   const float4* trans; int N; size_t layer;
   int pcss_early_out;      // option "pcss_early_out" (validated on the host): see pcss_t
+  // multi_fused: the camera pass's primitive ids and raster records (positions are resolved here instead of read from a G-buffer)
+  const unsigned int* ids; const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
 };
 
 struct Smap { const float* __restrict__ d; int w, h; float fw, fh; };
@@ -712,6 +714,57 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
   a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
 }
 
+// The same accumulation with the vertex map resolved on the fly: GBuffer.vert/frag's world position of the pixel's winning
+// primitive, interpolated exactly as the tile rasteriser's resolve does (perspective-correct, same expression order), so the
+// positions - and with them every tap - are identical to the materialised-G-buffer path while 16 B/pixel less is written and read.
+__global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a) {
+  int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.rx1 || y >= a.ry1) return;
+  size_t o = (size_t)y * a.W + x;
+  const unsigned int prim = __ldg(&a.ids[o]);
+  if (prim == 0xFFFFFFFFu) { a.vis[o] = 0.0f; return; }           // background: vertex map (0,0,0,1), discarded (x == 0)
+  const int t = (int)(prim >> 3), sub = (int)(prim & 7u);
+  const int slot = (sub == 0) ? t : __ldg(&a.ovf_base[t]) + sub - 1;
+  if (slot < 0) { a.vis[o] = 0.0f; return; }                     // (an id that does not belong to this camera pass: never dereferenced)
+  SgiRec r; SgiRecAttr at;
+  {
+    const uint4* rq = reinterpret_cast<const uint4*>(&a.rec[slot]);
+    const uint4* aq = reinterpret_cast<const uint4*>(&a.attr[slot]);
+    uint4* rd = reinterpret_cast<uint4*>(&r); uint4* ad = reinterpret_cast<uint4*>(&at);
+    rd[0] = __ldg(rq); rd[1] = __ldg(rq + 1); rd[2] = __ldg(rq + 2);
+    ad[0] = __ldg(aq); ad[1] = __ldg(aq + 1); ad[2] = __ldg(aq + 2); ad[3] = __ldg(aq + 3); ad[4] = __ldg(aq + 4); ad[5] = __ldg(aq + 5);
+  }
+  const int PX = x * SGI_SUBPIX + SGI_SUBPIX / 2, PY = y * SGI_SUBPIX + SGI_SUBPIX / 2;
+  const long long E0 = (long long)(r.X2 - r.X1) * (long long)(PY - r.Y1) - (long long)(r.Y2 - r.Y1) * (long long)(PX - r.X1);
+  const long long E1 = (long long)(r.X0 - r.X2) * (long long)(PY - r.Y2) - (long long)(r.Y0 - r.Y2) * (long long)(PX - r.X2);
+  const long long E2 = (long long)(r.X1 - r.X0) * (long long)(PY - r.Y0) - (long long)(r.Y1 - r.Y0) * (long long)(PX - r.X0);
+  const float q0 = ((float)E0 * r.ia) * at.iw[0];
+  const float q1 = ((float)E1 * r.ia) * at.iw[1];
+  const float q2 = ((float)E2 * r.ia) * at.iw[2];
+  const float iq = 1.0f / ((q0 + q1) + q2);
+  const float vx = ((q0 * at.A[0][0] + q1 * at.A[1][0]) + q2 * at.A[2][0]) * iq;
+  const float vy = ((q0 * at.A[0][1] + q1 * at.A[1][1]) + q2 * at.A[2][1]) * iq;
+  const float vz = ((q0 * at.A[0][2] + q1 * at.A[1][2]) + q2 * at.A[2][2]) * iq;
+  if (vx == 0.0f) { a.vis[o] = 0.0f; return; }
+  const float* m = a.lmvp;
+  float cx = m[0] * vx + m[4] * vy + m[8] * vz;
+  float cy = m[1] * vx + m[5] * vy + m[9] * vz;
+  float cz = m[2] * vx + m[6] * vy + m[10] * vz;
+  float cw = m[3] * vx + m[7] * vy + m[11] * vz;
+  float accShadow = 0.0f, count = 0.0f;
+  const float accFactor = 1.0f;
+  for (int l = 0; l < a.N; l++) {
+    float4 tr = __ldg(&a.trans[l]);
+    float sx = cx + tr.x, sy = cy + tr.y, sz = cz + tr.z, sw = cw + tr.w;
+    sx = sx / sw; sy = sy / sw; sz = sz / sw;
+    Smap s = {a.sm + a.layer * l, a.SW, a.SH, a.fw, a.fh};
+    float dfl = sm_fetch(s, sx, sy);
+    accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
+    count += accFactor;
+  }
+  a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
+}
+
 // ShadowMapping/Shaders/GBuffer/PhongShading.frag:11-47 (shadeScene).  Note `vec3 E = normalize(-vertex)` normalises the
 // vec4 (w included) before truncation, and the specular term is scaled by (shadow - shadowIntensity).
 struct ShadeArgs {
@@ -872,6 +925,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   a.pcf_n = ctx->pcf_n; a.rpcf_n = ctx->rpcf_n;
   for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
   a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
+  a.ids = nullptr; a.rec = nullptr; a.attr = nullptr; a.ovf_base = nullptr;
   a.pcss_early_out = (ctx->pcss_early_out && ctx->params.light_source_radius >= 0 && ctx->params.z_near >= 0 && ctx->params.kernel_size > 0 &&
                       ctx->params.blocker_search_size <= SGI_MAX_PCF_TAPS && !ctx->vis_staged) ? 1 : 0;
   {
@@ -972,7 +1026,13 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
     case SGI_TECH_RPCF_NONCONS: k_visibility<SGI_TECH_RPCF_NONCONS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_RPCF_CONS: k_visibility<SGI_TECH_RPCF_CONS, 0, 0><<<grid, block, 0, st>>>(a); break;
     case SGI_TECH_RSMSS: k_visibility<SGI_TECH_RSMSS, 0, 0><<<grid, block, 0, st>>>(a); break;
-    case SGI_TECH_MULTI_HARD: k_visibility_multi<<<grid, block, 0, st>>>(a); break;
+    case SGI_TECH_MULTI_HARD:
+      if (ctx->params.multi_fused) {
+        const SgiScratch& sc = ctx->scratch[1];          // the camera pass's records (sgi_render_prim_ids)
+        a.ids = (const unsigned int*)ctx->buf[SGI_BUF_PRIM_ID]; a.rec = sc.d_rec; a.attr = sc.d_attr; a.ovf_base = sc.d_ovf_base;
+        k_visibility_multi_fused<<<grid, block, 0, st>>>(a);
+      } else k_visibility_multi<<<grid, block, 0, st>>>(a);
+      break;
     case SGI_TECH_RBSSM: {
       if (!ctx->rbssm_compact) { k_visibility<SGI_TECH_RBSSM, 0, 0><<<grid, block, 0, st>>>(a); break; }
       // work list of the penumbra pixels + one warp per listed pixel (sgi_rbssm.cuh)

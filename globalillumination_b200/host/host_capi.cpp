@@ -114,6 +114,15 @@ int sgh_app_set_light_shard(sgh_app* a, int32_t rank, int32_t world) {
   return 0;
 }
 
+// multi-GPU: join the NCCL communicator (id from sgi_comm_unique_id on rank 0, shipped by the caller); the many-light frame is
+// then sharded by lights with the exchanges done by the library (ShadowApp::renderMonteCarlo)
+int sgh_app_comm_init(sgh_app* a, const void* id128, size_t bytes, int32_t rank, int32_t world) {
+  if (!a) return -1;
+  int rc = a->app.commInit(id128, bytes, rank, world);
+  if (rc) g_err = a->app.error();
+  return rc;
+}
+
 // technique names = the reference's menu entries / ShadowParams flags
 int sgh_app_set_technique(sgh_app* a, const char* name) {
   if (!a || !name) return -1;
@@ -152,6 +161,8 @@ int sgh_app_set_int(sgh_app* a, const char* name, int32_t v) {
   else if (n == "numberOfSamples") p.numberOfSamples = v; else if (n == "lightSourceSize") p.lightSourceSize = v;
   else if (n == "svInfinity") a->app.svInfinity = v; else if (n == "svDepthFunc") a->app.svDepthFunc = v;
   else if (n == "animationOn") a->app.animationOn = v != 0;
+  else if (n == "fusedMonteCarlo") a->app.fusedMonteCarlo = v != 0;
+  else if (n == "commSkip") a->app.commSkip = v != 0;
   else { g_err = "unknown int parameter " + n; return -2; }
   return 0;
 }

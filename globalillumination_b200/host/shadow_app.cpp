@@ -168,6 +168,7 @@ int ShadowApp::pushParams(int tech) {
   q.sv_depth_func = svDepthFunc; q.sv_infinity = svInfinity;
   q.rect_x0 = rect[0]; q.rect_y0 = rect[1]; q.rect_x1 = rect[2]; q.rect_y1 = rect[3];
   q.multi_partial = (tech == SGI_TECH_MULTI_HARD && lightShardWorld > 1) ? 1 : 0;
+  q.multi_fused = (tech == SGI_TECH_MULTI_HARD && fusedMonteCarlo) ? 1 : 0;
   int rc = sgi_set_params(ctx, &q);
   return rc ? fail(rc, "sgi_set_params") : 0;
 }
@@ -256,7 +257,26 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
   if (!ctx) return SGI_ERR_NO_DEVICE;
   int rc;
   // the reference re-uses the previous technique's G-buffer; here it is rendered explicitly
-  if ((rc = renderGBuffer())) return rc;
+  if (!fusedMonteCarlo) { if ((rc = renderGBuffer())) return rc; }
+  else {
+    // AccurateSoftShadow.frag reads only the vertex map: the camera pass stores the winning primitive per pixel and the
+    // accumulation kernel interpolates the position itself.  On a light shard every rank rasterises its own screen strip and
+    // the id strips are all-gathered (4 B/pixel over NVLink) while the rank's depth passes run.
+    if (!uploaded) { if ((rc = uploadScene())) return rc; }
+    FrameMatrices fc = frameMatrices();
+    if ((rc = sgi_set_camera(ctx, fc.cameraMVP.m, fc.cameraMV.m, fc.normalMatrix.m, windowWidth, windowHeight))) return fail(rc, "sgi_set_camera");
+    int keep[4] = {rect[0], rect[1], rect[2], rect[3]};
+    if (commOn && lightShardWorld > 1) {
+      int32_t r0 = 0, r1 = 0;
+      if ((rc = sgi_comm_strip(ctx, lightShardRank, &r0, &r1))) return fail(rc, "sgi_comm_strip");
+      rect[0] = 0; rect[1] = r0; rect[2] = windowWidth; rect[3] = r1;
+    }
+    rc = pushParams(SGI_TECH_MULTI_HARD);
+    for (int k = 0; k < 4; k++) rect[k] = keep[k];
+    if (rc) return rc;
+    if ((rc = sgi_render_prim_ids(ctx))) return fail(rc, "sgi_render_prim_ids");
+    if (commOn && lightShardWorld > 1 && !commSkip) { if ((rc = sgi_gather(ctx, SGI_BUF_PRIM_ID))) return fail(rc, "sgi_gather"); }
+  }
   updateLight();
   int n = shadowParams.numberOfSamples;
   if (n <= 0 || n > 1024) { err = "renderMonteCarlo: numberOfSamples must be in 1..1024"; return SGI_ERR_INVALID; }
@@ -284,8 +304,18 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
   if (rc) return fail(rc, "sgi_set_multi_light_common");
   if ((rc = pushParams(SGI_TECH_MULTI_HARD))) return rc;
   if ((rc = sgi_render_shadow_map(ctx))) return fail(rc, "sgi_render_shadow_map");
-  rc = sgi_compute_visibility(ctx);
-  return rc ? fail(rc, "sgi_compute_visibility") : 0;
+  if ((rc = sgi_compute_visibility(ctx))) return fail(rc, "sgi_compute_visibility");
+  // partial sums of the ranks -> final visibility of this rank's strip (reduce-scatter + the division of AccurateSoftShadow.frag:127)
+  if (commOn && lightShardWorld > 1 && !commSkip) { if ((rc = sgi_reduce_lights(ctx, n))) return fail(rc, "sgi_reduce_lights"); }
+  return 0;
+}
+
+int ShadowApp::commInit(const void* id128, size_t bytes, int rank, int world) {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  int rc = sgi_comm_init(ctx, id128, bytes, rank, world);
+  if (rc) return fail(rc, "sgi_comm_init");
+  lightShardRank = rank; lightShardWorld = world; commOn = true;
+  return 0;
 }
 
 int ShadowApp::displaySoft() { return shadowParams.monteCarlo ? renderMonteCarlo() : renderSoftShadows(); }

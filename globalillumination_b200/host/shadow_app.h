@@ -99,6 +99,11 @@ class ShadowApp {
   int svDepthFunc = SGI_DEPTH_LEQUAL;
   int rect[4] = {0, 0, 0, 0};     // multi-GPU screen tile (empty = whole window)
   int lightShardRank = 0, lightShardWorld = 1;   // multi-GPU many-light: this process owns lights l = rank (mod world)
+  bool fusedMonteCarlo = false;   // renderMonteCarlo: camera pass reduced to primitive ids (sgi_render_prim_ids), positions resolved inside
+                                  // the accumulation kernel (sgi_params.multi_fused); identical visibility, no vertex map materialised
+  bool commSkip = false;          // measurement aid: run the sharded frame without its exchanges (what the collectives cost = the difference)
+  bool commOn = false;            // sgi_comm_init done (commInit): renderMonteCarlo exchanges id strips / partial sums over NCCL itself
+  int commInit(const void* id128, size_t bytes, int rank, int world);   // joins the NCCL communicator; light shard = (rank, world)
 
  private:
   int fail(int rc, const char* where);

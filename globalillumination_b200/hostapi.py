@@ -13,7 +13,7 @@ PROGRAM = {"shadow_mapping": 0, "soft_shadow_mapping": 1, "shadow_volumes": 2}
 EXPORTS = [
     "sgh_last_error", "sgh_scene_load", "sgh_scene_free", "sgh_scene_counts", "sgh_scene_copy", "sgh_scene_views",
     "sgh_scene_substitutions", "sgh_frame_matrices", "sgh_app_create", "sgh_app_destroy", "sgh_app_error", "sgh_app_context",
-    "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard",
+    "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard", "sgh_app_comm_init",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_filter_shadow_map", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
     "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_save_image", "sgh_write_png", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
@@ -38,6 +38,7 @@ def load():
         _lib.sgh_app_display_e2e_async.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
         _lib.sgh_app_e2e_wait.argtypes = [C.c_void_p, C.c_int32]
         _lib.sgh_app_save_image.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.sgh_app_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
     return _lib
 
 
@@ -161,6 +162,12 @@ class App:
 
     def set_light_shard(self, rank, world):
         self._ck(self.L.sgh_app_set_light_shard(self.h, int(rank), int(world)))
+
+    def comm_init(self, unique_id, rank, world):
+        """Join the NCCL communicator inside the library (id from capi.comm_unique_id() on rank 0): the many-light frame is then
+        sharded by lights with the exchanges done by ShadowApp::renderMonteCarlo."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.sgh_app_comm_init(self.h, buf, 128, int(rank), int(world)))
 
     def set_technique(self, name):
         self._ck(self.L.sgh_app_set_technique(self.h, name.encode()))

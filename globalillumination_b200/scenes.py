@@ -28,7 +28,7 @@ WORKLOADS = {
         scene="procedural stand-in for Configs/SanDiego.txt (building/sphere assets not available on the GPU box)"),
     # The other configurations of BASELINE.json (parity-test cases; measurable with `bench.py --workload ...`).  Their
     # assets exist in the reference but /root/reference is not on the GPU box: the geometry is the reference loader's own
-    # output for the config file, committed as tests/golden/scene_<name>.npz (made by tests/golden/make_golden.py).
+    # output for the config file, committed as globalillumination_b200/data/scene_<name>.npz (made by tests/golden/make_golden.py).
     # Configs/Teapot.txt — c1: hard shadow mapping (`naive`)
     "c1_teapot": dict(golden="teapot", lines=[], W=1280, H=720, S=1024, program="shadow_mapping", technique="naive", params={},
                       scene="Configs/Teapot.txt through the reference's SceneLoader (golden scene_teapot.npz), 15706 triangles"),
@@ -41,6 +41,14 @@ WORKLOADS = {
     "c4_tree_sv_1080p": dict(golden="tree", lines=[], W=1920, H=1080, S=64, program="shadow_volumes", technique="naive", params={},
                              scene="as c4_tree_sv at 1920x1080"),
 }
+
+
+# Config c5 on the reference's own geometry: Configs/SanDiego.txt through the reference's SceneLoader (building.obj + plane; the two
+# spheres are missing upstream, .MISSING_LARGE_BLOBS), 16 lights = 4x4 UniformSampledLightSource of size 16, 8192^2 maps, 7680x4320.
+# This is the workload of bench.py's `sharded` record (light shards over 1/2/4/8 GPUs).
+WORKLOADS["c5_sandiego"] = dict(golden="sandiego", lines=[], W=7680, H=4320, S=8192, program="soft_shadow_mapping", technique="montecarlo",
+                                params=dict(numberOfSamples=16, lightSourceSize=16),
+                                scene="Configs/SanDiego.txt through the reference's SceneLoader (scene_sandiego.npz), 39500 triangles; 16 lights")
 
 
 # Moment shadow maps on the headline scene: the ShadowMapping program with VSM / ESM / EVSM / MSM set
@@ -65,10 +73,10 @@ WORKLOADS["dragon_pcss"] = dict(golden="dragon", lines=[], W=1920, H=1080, S=204
 
 
 def golden_scene(name):
-    """The reference loader's output for a config (committed fixture)."""
+    """The reference loader's output for a config (input fixture shipped with the package: globalillumination_b200/data/,
+    written by tests/golden/make_golden.py from the reference's own SceneLoader)."""
     import numpy as np
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    return dict(np.load(os.path.join(root, "tests", "golden", f"scene_{name}.npz")))
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", f"scene_{name}.npz")))
 
 
 def write_config(name, directory=None):

@@ -99,6 +99,14 @@ typedef struct sgi_params {
                                      screen tiles); an empty rectangle means the whole screen */
   int32_t multi_partial;          /* SGI_TECH_MULTI_HARD on a light shard: 1 = write the un-normalised sum
                                      over this context's lights (ranks are summed, then divided by the total) */
+  int32_t multi_fused;            /* SGI_TECH_MULTI_HARD: 1 = the accumulation kernel resolves each pixel's world position itself from
+                                     SGI_BUF_PRIM_ID (sgi_render_prim_ids) instead of reading a materialised G-buffer: the same
+                                     positions to the bit, without the 16 B/pixel write and read of the position target */
+  int32_t sv_silhouette;          /* shadow volumes: 0 = one open prism per triangle, as ShadowVolume::update builds them (parity mode);
+                                     1 = side quads of edges shared by two triangles of the same orientation class are dropped in
+                                     pairs (they cancel +1/-1): silhouette, boundary and non-manifold edges only */
+  int32_t sv_zfail;               /* shadow volumes: 0 = depth-pass counting (the reference's stencil ops, main.cpp:166-168),
+                                     1 = depth-fail counting over capped volumes with depth clamp (robust when the eye is inside a volume) */
 } sgi_params;
 
 typedef enum sgi_buffer {
@@ -117,7 +125,9 @@ typedef enum sgi_buffer {
   SGI_BUF_MOMENTS = 12,     /* float4  [Sh][Sw]     VSM/ESM/EVSM/MSM: moment target of the light-view pass, cleared to (0,0,0,1) */
   SGI_BUF_MOMENTS_X = 13,   /* float4  [H][W]       filterShadowMap: after the horizontal pass (FILTER_X_MAP_COLOR, window-sized) */
   SGI_BUF_MOMENTS_FILTERED = 14, /* float4 [H][W]   filterShadowMap: after the vertical pass (FILTER_Y_MAP_COLOR), what Shadow.frag samples */
-  SGI_BUF_COUNT_ = 15
+  SGI_BUF_PRIM_ID = 15,     /* uint32  [H][W]       sgi_render_prim_ids: winning primitive per pixel = source triangle * 8 + fan index of its clipped
+                                                    polygon; 0xFFFFFFFF = background */
+  SGI_BUF_COUNT_ = 16
 } sgi_buffer;
 
 /* passes that can be timed with sgi_pass_time_ms */
@@ -174,6 +184,11 @@ void sgi_default_params(sgi_params* params);
 /* passes */
 int sgi_render_shadow_map(sgi_ctx* ctx);      /* renderShadowMap(), ShadowMapping/src/main.cpp:350-361 (all N lights) */
 int sgi_render_gbuffer(sgi_ctx* ctx);         /* renderGBuffer(),   ShadowMapping/src/main.cpp:363-372               */
+/* The camera pass reduced to what AccurateSoftShadow.frag consumes (it reads only the vertex map; the normal test is commented
+ * out, :59-60): the same rasterisation as sgi_render_gbuffer, but only the winning primitive of every pixel of the rectangle is
+ * stored (4 B/pixel, SGI_BUF_PRIM_ID).  With params.multi_fused the many-light pass interpolates the position from it on the fly.
+ * On a light shard each rank rasterises its screen strip and the strips are exchanged with sgi_gather. */
+int sgi_render_prim_ids(sgi_ctx* ctx);
 /* filterShadowMap(), ShadowMapping/src/main.cpp:374-398 (display() calls it between renderShadowMap and renderGBuffer when
  * VSM / ESM / EVSM / MSM is on, :471): the separable binomial blur of order params.kernel_order (Filter::buildGaussianKernel,
  * src/Filter.cpp:17-46) - GaussianFilter.frag, or LogGaussianFilter.frag for ESM - from the moment target into the two
@@ -208,6 +223,26 @@ int sgi_synchronize(sgi_ctx* ctx);
  * overlap the next frame's passes); does not block the host.  sgi_read*, sgi_device_ptr, sgi_shade_phong and
  * sgi_synchronize do this themselves. */
 int sgi_join(sgi_ctx* ctx);
+
+/* ---- multi-GPU (one context per GPU / process rank; SURVEY 8e: screen tiles, and lights for many-light scenes) ------------
+ * NCCL over NVLink / NVSwitch, loaded at run time (libnccl.so.2); nothing here is needed on one GPU.
+ *   sgi_comm_unique_id  rank 0 makes the 128-byte NCCL id; the caller ships it to the other ranks (MPI, torch.distributed, a file)
+ *   sgi_comm_init       every rank joins; screen strips = ceil(H / nranks) rows per rank (sgi_comm_strip), the exchanged buffers
+ *                       are padded to nranks equal strips so that every exchange is ONE collective, in place, with no packing
+ *   sgi_gather          tile sharding: every rank has produced its strip of `which` (rect_* = its strip) -> ncclAllGather in place;
+ *                       afterwards every rank holds the whole buffer (visibility, shadow-volume counts, primitive ids, ...)
+ *   sgi_reduce_lights   light sharding (renderMonteCarlo, AccurateSoftShadow.frag:127): the ranks' un-normalised partial sums in
+ *                       SGI_BUF_VISIBILITY (params.multi_partial) -> ncclReduceScatter in place, then divided by the number of
+ *                       lights of the whole set: rank r ends with the final visibility of ITS strip (what tile-local shading
+ *                       consumes); rows outside the strip are left as partial sums
+ * The collectives run on the context's communication stream behind the passes that produce their input and ahead of the passes
+ * that consume their output (device-side ordering, the host does not block). */
+int sgi_comm_unique_id(void* id128, size_t bytes);
+int sgi_comm_init(sgi_ctx* ctx, const void* id128, size_t bytes, int32_t rank, int32_t nranks);
+int sgi_comm_destroy(sgi_ctx* ctx);
+int sgi_comm_strip(sgi_ctx* ctx, int32_t rank, int32_t* row0, int32_t* row1);
+int sgi_gather(sgi_ctx* ctx, int32_t which);
+int sgi_reduce_lights(sgi_ctx* ctx, int32_t total_lights);
 
 /* page-locked host memory for callers that want sgi_set_mesh / sgi_read to be true async DMA
  * (the reference keeps its Mesh arrays in malloc'd memory and lets the GL driver stage them) */

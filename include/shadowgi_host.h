@@ -47,6 +47,9 @@ int sgh_app_scene_copy(sgh_app* a, float* xyz, float* nrm, int32_t* idx);
 int sgh_app_configure(sgh_app* a, int32_t W, int32_t H, int32_t SW, int32_t SH);
 int sgh_app_set_rect(sgh_app* a, int32_t x0, int32_t y0, int32_t x1, int32_t y1);
 int sgh_app_set_light_shard(sgh_app* a, int32_t rank, int32_t world);   /* many-light: own lights l = rank (mod world) */
+/* multi-GPU inside the library: sgi_comm_init on the app's context (id from sgi_comm_unique_id on rank 0); renderMonteCarlo then
+ * shards the lights over the ranks and exchanges primitive-id strips / partial sums over NCCL itself (sgi_gather, sgi_reduce_lights) */
+int sgh_app_comm_init(sgh_app* a, const void* id128, size_t bytes, int32_t rank, int32_t world);
 int sgh_app_set_technique(sgh_app* a, const char* name);
 int sgh_app_set_int(sgh_app* a, const char* name, int32_t v);
 int sgh_app_set_float(sgh_app* a, const char* name, float v);

@@ -78,6 +78,9 @@ typedef struct orc_params {
   int32_t sv_infinity;
   int32_t rect_x0, rect_y0, rect_x1, rect_y1;   /* screen rectangle to evaluate        */
   int32_t multi_partial;         /* many-light: write the un-normalised sum over the given lights */
+  int32_t multi_fused;           /* (implementation switch of the CUDA path; the oracle has one form) */
+  int32_t sv_silhouette;         /* shadow volumes: drop the side quads of interior edges in cancelling pairs */
+  int32_t sv_zfail;              /* shadow volumes: depth-fail counting over capped volumes, depth clamp */
 } orc_params;
 
 /* per-frame camera-side uniforms of the full-screen shadow passes */

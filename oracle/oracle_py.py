@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("polygon_offset_factor", C.c_float), ("polygon_offset_units", C.c_float),
         ("sv_depth_func", C.c_int32), ("sv_infinity", C.c_int32),
         ("rect_x0", C.c_int32), ("rect_y0", C.c_int32), ("rect_x1", C.c_int32), ("rect_y1", C.c_int32),
-        ("multi_partial", C.c_int32),
+        ("multi_partial", C.c_int32), ("multi_fused", C.c_int32), ("sv_silhouette", C.c_int32), ("sv_zfail", C.c_int32),
     ]
 
 

@@ -77,6 +77,47 @@ def main():
     if rank == 0:
         print(f"lights x{world}: all-reduced partial sums / 16 == un-sharded 16-light frame: {same}", flush=True)
     app.close()
+
+    # ---- the same two partitionings with the exchange inside the C ABI (sgi_comm_init / sgi_gather / sgi_reduce_lights)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    # tiles: PCF on the c2 scene, strips = sgi_comm_strip, one in-place ncclAllGather
+    app = hostapi.App(local)
+    app.load_scene(scenes.write_config("c2_sponza")); app.configure(W, H, S); app.set_technique("pcf")
+    app.display("shadow_mapping")
+    full = app.context().read("visibility")
+    app.comm_init(uid[0], rank, world)
+    app.display("shadow_mapping")                       # (sizes the padded targets for the rank count)
+    ctx = app.context()
+    r0, r1 = ctx.comm_strip(rank)
+    app.set_rect(0, r0, W, r1)
+    app.display("shadow_mapping")
+    ctx.gather("visibility")
+    same = bool(np.array_equal(ctx.read("visibility").view(np.uint32), full.view(np.uint32)))
+    ok &= same
+    if rank == 0:
+        print(f"C ABI tiles x{world}: sgi_gather(visibility) == un-sharded image: {same} (rows {r0}..{r1} on rank 0)", flush=True)
+    app.close()
+    # lights: 16 lights, fused many-light path (primitive-id strips all-gathered, partial sums reduce-scattered + divided)
+    for (Wl, Hl) in ((2048, 1152), (1000, 563)):        # the second height does not divide by the rank count: padded strips
+        app = hostapi.App(local)
+        app.load_scene(scenes.write_config("c5_many_light")); app.configure(Wl, Hl, 1024); app.set_technique("montecarlo")
+        app.set(numberOfSamples=16, lightSourceSize=16)
+        app.display("soft_shadow_mapping")
+        full = app.context().read("visibility")
+        app.set(fusedMonteCarlo=1)
+        uid2 = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid2, src=0)
+        app.comm_init(uid2[0], rank, world)
+        for _ in range(3):                               # several frames: the exchanges of consecutive frames overlap
+            app.display("soft_shadow_mapping")
+        ctx = app.context()
+        r0, r1 = ctx.comm_strip(rank)
+        mine = ctx.read("visibility")[r0:r1]
+        same = bool(np.array_equal(mine.view(np.uint32), full[r0:r1].view(np.uint32)))
+        ok &= same
+        print(f"C ABI lights x{world} {Wl}x{Hl}, rank {rank}: rows {r0}..{r1} of sgi_reduce_lights == un-sharded frame: {same}", flush=True)
+        app.close()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -19,6 +19,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+SCENE_DIR = os.path.join(os.path.dirname(os.path.dirname(HERE)), "globalillumination_b200", "data")   # input scenes ship with the package
 sys.path.insert(0, os.path.normpath(os.path.join(HERE, "..", "..")))
 from oracle import oracle_py as O  # noqa: E402
 
@@ -181,7 +182,7 @@ def main():
     for name, cfg in SCENES.items():
         sc = O.ref_load_scene(cfg)
         scenes[name] = sc
-        np.savez_compressed(os.path.join(HERE, f"scene_{name}.npz"), **sc)
+        np.savez_compressed(os.path.join(SCENE_DIR, f"scene_{name}.npz"), **sc)
         print(name, sc["xyz"].shape, sc["idx"].shape)
     import tempfile
     for name, lines in PARTIAL.items():
@@ -189,7 +190,7 @@ def main():
         with open(cfg, "w") as f:
             f.write("\n".join(lines))
         sc = O.ref_load_scene(cfg)
-        np.savez_compressed(os.path.join(HERE, f"scene_{name}.npz"), **sc)
+        np.savez_compressed(os.path.join(SCENE_DIR, f"scene_{name}.npz"), **sc)
         print(name, sc["xyz"].shape, sc["idx"].shape)
 
     host = {}

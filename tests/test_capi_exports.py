@@ -35,7 +35,7 @@ def test_libshadowgi_host_exports_every_declared_symbol():
 
 def test_params_struct_layout_matches_header_and_oracle():
     from oracle import oracle_py as O
-    assert C.sizeof(capi.SgiParams) == 22 * 4 == C.sizeof(O.Params)
+    assert C.sizeof(capi.SgiParams) == 25 * 4 == C.sizeof(O.Params)
     assert [f for f, _ in capi.SgiParams._fields_] == [f for f, _ in O.Params._fields_]
     p = capi.default_params("pcss")
     assert (p.shadow_intensity, p.kernel_order, p.penumbra_size, p.blocker_search_size, p.kernel_size, p.light_source_radius,

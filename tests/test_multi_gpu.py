@@ -1,0 +1,132 @@
+"""Many-light fast path (primitive-id camera pass + fused position resolve) and the multi-GPU exchange of the C ABI
+(sgi_comm_init / sgi_gather / sgi_reduce_lights).  Single-GPU tests run everywhere a GPU is; the 2-rank test needs two GPUs
+(it launches scripts/multi_gpu_check.py under torchrun, NCCL) and is skipped on a one-GPU box."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from globalillumination_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _many_light_frame(ctx, sc, W, H, S, n_lights, **kw):
+    po, pg = util.params_pair("multi_hard", S, **kw)
+    fm = util.frame(sc, W, H, S)
+    mvp, mvpb = util.multi_lights(sc, n_lights, 16, W, H, S)
+    ctx.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+    ctx.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+    ctx.set_multi_light_common(None)
+    ctx.set_lights(mvp, mvpb, fm["light_pos_shading"], S, S)
+    ctx.set_params(pg)
+    return po, pg, fm, mvp, mvpb
+
+
+@pytest.mark.parametrize("name,n_lights,S,W,H,eye", [("teapot", 4, 128, 320, 180, None), ("teapot", 16, 256, 333, 187, None),
+                                                     ("teapot", 5, 200, 640, 360, (2.0, 6.0, -4.0)),      # camera inside the scene: clipped triangles
+                                                     ("sandiego", 16, 512, 960, 540, None)])
+def test_many_light_fused_equals_the_gbuffer_path_and_the_oracle(ctx, name, n_lights, S, W, H, eye):
+    sc = dict(util.scene(name))
+    if eye is not None:
+        sc["cam_eye"] = np.asarray(eye, np.float32)
+    po, pg, fm, mvp, mvpb = _many_light_frame(ctx, sc, W, H, S, n_lights)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    vis_a, pos, dep = ctx.read("visibility"), ctx.read("gbuf_pos"), ctx.read("cam_depth")
+    maps = ctx.read("shadow_map")
+    vis_o = O.visibility_multi(po, mvpb[-1], mvpb[:, 12:16], pos, maps)
+    assert util.bits_equal(vis_a, vis_o), util.describe_diff(vis_a, vis_o)
+    # the same frame from primitive ids: positions resolved inside the accumulation kernel
+    _, pg_f = util.params_pair("multi_hard", S, multi_fused=1)
+    ctx.set_params(pg_f)
+    ctx.render_prim_ids(); ctx.compute_visibility()
+    vis_b, ids = ctx.read("visibility"), ctx.read("prim_id")
+    assert util.bits_equal(vis_a, vis_b), util.describe_diff(vis_a, vis_b)
+    assert np.array_equal(ids != 0xFFFFFFFF, dep < 1.0)                  # a primitive wherever the depth pre-pass has a surface
+    assert (ids[ids != 0xFFFFFFFF] >> 3).max() < sc["idx"].shape[0]
+    # id strips rendered separately (what the ranks of a light shard do) assemble the same buffer
+    for (y0, y1) in ((0, H // 3), (H // 3, H)):
+        _, pg_s = util.params_pair("multi_hard", S, multi_fused=1, rect_x0=0, rect_y0=y0, rect_x1=W, rect_y1=y1)
+        ctx.set_params(pg_s); ctx.render_prim_ids()
+    assert np.array_equal(ctx.read("prim_id"), ids)
+    ctx.set_params(pg_f); ctx.compute_visibility()
+    assert util.bits_equal(ctx.read("visibility"), vis_a)
+
+
+def test_fused_needs_the_id_pass(ctx):
+    from globalillumination_b200 import capi
+    sc = util.scene("door")
+    po, pg, fm, mvp, mvpb = _many_light_frame(ctx, sc, 160, 120, 64, 4, multi_fused=1)
+    ctx.render_shadow_map(); ctx.render_gbuffer()
+    with pytest.raises(capi.SgiError):
+        ctx.compute_visibility()                                         # G-buffer rendered, but no primitive ids
+
+
+def test_comm_single_rank_strip_gather_and_reduce():
+    """One rank: the strip is the screen, sgi_gather is a no-op, sgi_reduce_lights is the division by the light count."""
+    from globalillumination_b200 import capi
+    c = capi.Context(0)
+    try:
+        c.comm_init(capi.comm_unique_id(), 0, 1)
+        sc = util.scene("teapot")
+        W, H, S, n_l = 256, 145, 128, 6
+        po, pg, fm, mvp, mvpb = _many_light_frame(c, sc, W, H, S, n_l)
+        assert c.comm_strip(0) == (0, H)
+        c.render_shadow_map(); c.render_gbuffer(); c.compute_visibility()
+        full = c.read("visibility")
+        _, pg_p = util.params_pair("multi_hard", S, multi_partial=1, multi_fused=1)
+        c.set_params(pg_p)
+        c.render_prim_ids(); c.gather("prim_id"); c.compute_visibility(); c.reduce_lights(n_l)
+        assert util.bits_equal(c.read("visibility"), full)
+        c.comm_destroy()
+    finally:
+        c.close()
+
+
+def test_two_contexts_on_one_device_and_kernel_attributes_per_context():
+    """function attributes (dynamic shared memory opt-in) are per device; every context configures its own.  With one
+    GPU this checks two contexts in one process side by side; with two GPUs the second context lives on device 1."""
+    import torch
+    from globalillumination_b200 import capi
+    dev2 = 1 if torch.cuda.device_count() > 1 else 0
+    a, b = capi.Context(0), capi.Context(dev2)
+    try:
+        sc = util.scene("teapot")
+        W, H, S = 640, 360, 512
+        out = []
+        for c in (a, b):
+            po, pg = util.params_pair("pcf", S)
+            fm = util.frame(sc, W, H, S)
+            c.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+            c.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+            c.set_lights(fm["light_mvp"], fm["light_mvp_b"], fm["light_pos_shading"], S, S)
+            c.set_params(pg)
+            c.render_shadow_map(); c.render_gbuffer(); c.compute_visibility()
+            out.append((c.read("shadow_map"), c.read("visibility")))
+        assert util.bits_equal(out[0][0], out[1][0]) and util.bits_equal(out[0][1], out[1][1])
+        sm_o = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+        assert util.bits_equal(out[1][0][0], sm_o)
+    finally:
+        a.close(); b.close()
+
+
+def test_two_ranks_over_nccl_match_the_unsharded_frame():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29677", os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

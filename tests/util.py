@@ -7,12 +7,14 @@ import numpy as np
 from oracle import oracle_py as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# input scenes (the reference loader's arrays for its config files): shipped with the package, shared with bench.py
+SCENES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "globalillumination_b200", "data")
 _cache = {}
 
 
 def scene(name):
     if name not in _cache:
-        z = np.load(os.path.join(GOLDEN, f"scene_{name}.npz"))
+        z = np.load(os.path.join(SCENES, f"scene_{name}.npz"))
         _cache[name] = {k: z[k] for k in z.files}
     return _cache[name]
 
