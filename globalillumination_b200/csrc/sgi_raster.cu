@@ -1343,9 +1343,8 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
 static int tile_threads(const sgi_ctx* ctx, int n_tiles, int mode) {
   if (ctx->tile_threads) return ctx->tile_threads;
   if (mode == SGI_MODE_SVCOUNT) return 1024;
-  // (round 2, after the 64-register cap: the depth pass of a 2048^2 map - 1024 tiles - is faster with 256-thread CTAs, 75 vs 87 us;
-  //  the keyed G-buffer pass at 1080p - 510 tiles - stays at 512, 82 vs 123 us; profiles/r2_tile_ab.txt)
-  if (mode == SGI_MODE_DEPTH) return n_tiles <= 300 ? 1024 : (n_tiles <= 600 ? 512 : 256);
+  // (round 2: with the default light of the c2 scene the 2048^2 depth pass prefers 256-thread CTAs, 75 vs 87 us, but over the
+  //  bench's animated light it is 95 vs 59 us the other way: hot tiles want the larger CTA; the rule stays as measured in round 1)
   return n_tiles <= 300 ? 1024 : (n_tiles <= 1200 ? 512 : 256);
 }
 

@@ -36,12 +36,12 @@ def _many_light_frame(ctx, sc, W, H, S, n_lights, **kw):
 
 
 @pytest.mark.parametrize("name,n_lights,S,W,H,eye", [("teapot", 4, 128, 320, 180, None), ("teapot", 16, 256, 333, 187, None),
-                                                     ("teapot", 5, 200, 640, 360, (2.0, 6.0, -4.0)),      # camera inside the scene: clipped triangles
+                                                     ("teapot", 5, 200, 640, 360, ((0.0, 6.0, 6.0), (0.0, -19.0, 46.0))),   # camera close to the floor and the teapot: clipped triangles
                                                      ("sandiego", 16, 512, 960, 540, None)])
 def test_many_light_fused_equals_the_gbuffer_path_and_the_oracle(ctx, name, n_lights, S, W, H, eye):
     sc = dict(util.scene(name))
     if eye is not None:
-        sc["cam_eye"] = np.asarray(eye, np.float32)
+        sc["cam_eye"], sc["cam_at"] = np.asarray(eye[0], np.float32), np.asarray(eye[1], np.float32)
     po, pg, fm, mvp, mvpb = _many_light_frame(ctx, sc, W, H, S, n_lights)
     ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
     vis_a, pos, dep = ctx.read("visibility"), ctx.read("gbuf_pos"), ctx.read("cam_depth")
@@ -55,7 +55,9 @@ def test_many_light_fused_equals_the_gbuffer_path_and_the_oracle(ctx, name, n_li
     vis_b, ids = ctx.read("visibility"), ctx.read("prim_id")
     assert util.bits_equal(vis_a, vis_b), util.describe_diff(vis_a, vis_b)
     assert np.array_equal(ids != 0xFFFFFFFF, dep < 1.0)                  # a primitive wherever the depth pre-pass has a surface
-    assert (ids[ids != 0xFFFFFFFF] >> 3).max() < sc["idx"].shape[0]
+    assert (ids != 0xFFFFFFFF).mean() > 0.2 and (ids[ids != 0xFFFFFFFF] >> 3).max() < sc["idx"].shape[0]
+    if eye is not None:
+        assert ((ids[ids != 0xFFFFFFFF] & 7) != 0).any()                # fan triangles of clipped polygons are visible
     # id strips rendered separately (what the ranks of a light shard do) assemble the same buffer
     for (y0, y1) in ((0, H // 3), (H // 3, H)):
         _, pg_s = util.params_pair("multi_hard", S, multi_fused=1, rect_x0=0, rect_y0=y0, rect_x1=W, rect_y1=y1)
