@@ -43,7 +43,7 @@ EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility", "sgi_filter_shadow_map", "sgi_moment_quantization",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
-    "sgi_render_prim_ids", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
+    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -221,6 +221,11 @@ class Context:
     def compute_shadow_volume(self, light_pos):
         self._ck(self.lib.sgi_compute_shadow_volume(self.h, _fp(_f32(light_pos))))
 
+    def sv_fragments(self):
+        n = C.c_int64()
+        self._ck(self.lib.sgi_sv_fragments(self.h, C.byref(n)))
+        return n.value
+
     def synchronize(self):
         self._ck(self.lib.sgi_synchronize(self.h))
 
@@ -229,7 +234,7 @@ class Context:
         return {
             "shadow_map": ((N, SH, SW), np.float32), "gbuf_pos": ((H, W, 4), np.float32), "gbuf_nrm": ((H, W, 4), np.float32),
             "cam_depth": ((H, W), np.float32), "visibility": ((H, W), np.float32), "sv_count": ((H, W), np.int32),
-            "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "edt_nearest": ((H, W, 2), np.int16), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * 6, 3), np.int32),
+            "sv_stencil": ((H, W), np.uint8), "gbuf_albedo": ((H, W, 4), np.float32), "shaded": ((H, W, 4), np.float32), "edt_nearest": ((H, W, 2), np.int16), "sv_prism_xyz": ((T * 6, 3), np.float32), "sv_prism_idx": ((T * (8 if getattr(getattr(self, "params", None), "sv_zfail", 0) else 6), 3), np.int32),
             "moments": ((SH, SW, 4), np.float32), "moments_x": ((H, W, 4), np.float32), "moments_filtered": ((H, W, 4), np.float32),
             "prim_id": ((H, W), np.uint32),
         }[which]

@@ -219,6 +219,7 @@ int sgi_destroy(sgi_ctx* ctx) {
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->ev_comm_done[b]) cudaEventDestroy(ctx->ev_comm_done[b]);
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
   if (ctx->vis_spare) cudaFree(ctx->vis_spare);
+  for (void* p : {(void*)ctx->d_sv_grp_start, (void*)ctx->d_sv_grp_ent, (void*)ctx->d_sv_cls, (void*)ctx->d_sv_frags}) if (p) cudaFree(p);
   if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
   if (ctx->d_rgb) cudaFree(ctx->d_rgb);
   void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
@@ -302,6 +303,12 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
     if (n > 0) { lo = idx[0]; hi = idx[0]; }
     for (int64_t k = 0; k < n; k++) { const int32_t v = idx[k]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
     if (n > 0 && (lo < 0 || hi >= V)) { ctx->err = "sgi_set_mesh: index out of range"; return SGI_ERR_INVALID; }
+    if (ctx->sv_track) {        // shadow volumes, silhouette form: the edge groups survive a re-upload of the same indices
+      if ((int64_t)ctx->h_idx_copy.size() != n || (n > 0 && memcmp(ctx->h_idx_copy.data(), idx, (size_t)n * 4) != 0)) {
+        ctx->h_idx_copy.assign(idx, idx + n);
+        ctx->sv_edges_valid = false;
+      }
+    }
   }
   cudaSetDevice(ctx->device);
   // Upload into the geometry set the frame in flight is NOT using.  Ordering on the main stream is enough: the passes
@@ -759,29 +766,51 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   if (!ctx->gbuffer_valid) { ctx->err = "sgi_compute_shadow_volume: render the G-buffer (depth pre-pass) first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
   int rc;
+  const int zfail = ctx->params.sv_zfail ? 1 : 0, silhouette = ctx->params.sv_silhouette ? 1 : 0;
+  const int per = zfail ? 8 : 6;                 // triangles per source triangle: 3 side quads (+ near cap + far cap)
   size_t px = sgi_padded_pixels(ctx);
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_COUNT, px * 4))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_STENCIL, px))) return rc;
   if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_XYZ, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
-  if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_IDX, (size_t)(ctx->T > 0 ? ctx->T : 1) * 18 * 4))) return rc;
+  if ((rc = ensure_buf(ctx, SGI_BUF_SV_PRISM_IDX, (size_t)(ctx->T > 0 ? ctx->T : 1) * per * 3 * 4))) return rc;
   if ((rc = sgi_join_gbuffer(ctx))) return rc;
-  for (int b : {SGI_BUF_SV_COUNT, SGI_BUF_SV_STENCIL, SGI_BUF_SV_PRISM_XYZ, SGI_BUF_SV_PRISM_IDX}) sgi_wait_reads_of(ctx, b, ctx->stream);
+  for (int b : {SGI_BUF_SV_COUNT, SGI_BUF_SV_STENCIL, SGI_BUF_SV_PRISM_XYZ, SGI_BUF_SV_PRISM_IDX}) { sgi_wait_reads_of(ctx, b, ctx->stream); sgi_wait_comm(ctx, b, ctx->stream); }
+  unsigned long long* frags = nullptr;
+  if (ctx->sv_count_fragments) {
+    if (!ctx->d_sv_frags) SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_sv_frags, 8));
+    SGI_CUDA(ctx, cudaMemsetAsync(ctx->d_sv_frags, 0, 8, ctx->stream));
+    frags = ctx->d_sv_frags;
+  }
   int slot = sgi_timing_begin(ctx, SGI_PASS_SHADOW_VOLUME, ctx->stream);
-  if ((rc = sgi_sv_extrude_run(ctx, light_pos, (float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ], (int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]))) return rc;
+  if ((rc = sgi_sv_extrude_run(ctx, light_pos, (float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ], (int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX], per, silhouette))) return rc;
   SgiRasterJob job;
   memset(&job, 0, sizeof(job));
   job.mode = SGI_MODE_SVCOUNT;
   job.xyz = (const float*)ctx->buf[SGI_BUF_SV_PRISM_XYZ]; job.nrm = nullptr;
-  job.idx = (const int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]; job.T = ctx->T * 6;
+  job.idx = (const int32_t*)ctx->buf[SGI_BUF_SV_PRISM_IDX]; job.T = ctx->T * per;
   memcpy(job.mvp, ctx->cam_mvp, 64);
   job.W = ctx->W; job.H = ctx->H;
   job.scene_depth = (const float*)ctx->buf[SGI_BUF_CAM_DEPTH]; job.depth_func = ctx->params.sv_depth_func;
   job.count = (int32_t*)ctx->buf[SGI_BUF_SV_COUNT]; job.stencil = (uint8_t*)ctx->buf[SGI_BUF_SV_STENCIL];
   job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
+  job.no_far_clip = zfail; job.sv_zfail = zfail; job.sv_caps = zfail; job.frag_counter = frags;
   if ((rc = sgi_raster_run(ctx, job, 0, ctx->stream))) return rc;
   sgi_timing_end(ctx, SGI_PASS_SHADOW_VOLUME, slot, ctx->stream);
   SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
   mark_gbuffer_use(ctx);
+  return SGI_OK;
+}
+
+// option "sv_count_fragments": covered prism fragments of the last sgi_compute_shadow_volume (the unit of work SURVEY 8(d) names)
+int sgi_sv_fragments(sgi_ctx* ctx, int64_t* fragments) {
+  if (!ctx || !fragments) return SGI_ERR_INVALID;
+  *fragments = 0;
+  if (!ctx->d_sv_frags) return SGI_OK;
+  cudaSetDevice(ctx->device);
+  unsigned long long v = 0;
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  SGI_CUDA(ctx, cudaMemcpy(&v, ctx->d_sv_frags, 8, cudaMemcpyDeviceToHost));
+  *fragments = (int64_t)v;
   return SGI_OK;
 }
 
@@ -885,6 +914,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "rbssm_compact")) ctx->rbssm_compact = value ? 1 : 0;
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
+  else if (!strcmp(name, "sv_count_fragments")) ctx->sv_count_fragments = value ? 1 : 0;
   else if (!strcmp(name, "tile_threads")) {
     if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 128 (depth pass only), 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;

@@ -21,8 +21,9 @@
 //
 // HBM traffic per pass = geometry once + every output texel once; depth never bounces
 // through global atomics.  Numerics follow DESIGN.md §3 to the bit (-fmad=false).
+#include <algorithm>
 #include <cstdlib>
-#include <cub/cub.cuh>
+#include <vector>
 #include "sgi_internal.cuh"
 #include "sgi_moments.cuh"
 
@@ -646,6 +647,7 @@ struct TileArgs {
   const float* scene_depth; int depth_func; int32_t* count; uint8_t* stencil;
   float4* mom4; int mom_tech, z_near, z_far; float mq[16], mqt[4];      // MOMENTS
   unsigned int* ids;                                                   // IDS
+  int sv_zfail, sv_caps; unsigned long long* frag_counter;             // SVCOUNT: depth-fail mode, capped volumes, optional fragment tally
 };
 
 #define ONE_BITS 0x3F800000u
@@ -750,6 +752,7 @@ struct TriQueue {
 template <int MODE>
 struct TileSink {                  // where fragments go: the tile payload in shared memory
   unsigned int* zt; unsigned long long* kt; int* ct; const float* sd; int depth_func;
+  int zfail, caps; int* nfrag;     // shadow volumes: depth-fail counting, capped volumes (8 triangles per source triangle), fragment tally
   __device__ __forceinline__ void fragment(int lx, int ly, float z, int meta) const {
     const int p = ly * SGI_PITCH + lx;
     if (MODE == SGI_MODE_DEPTH) {
@@ -761,9 +764,16 @@ struct TileSink {                  // where fragments go: the tile payload in sh
         if (key < kt[p]) atomicMin(&kt[p], key);
       }
     } else {
+      // ShadowVolumes/src/main.cpp:160-172: front faces +1 / back faces -1 on fragments that pass the depth test (depth-pass);
+      // depth-fail mode: back faces +1 / front faces -1 on fragments that fail it.  Cap triangles (6 and 7 of each group of 8)
+      // are tested strictly: a cap fragment coplanar with the visible surface - the surface's own triangle - counts as failing,
+      // which is what makes the depth-fail count equal the depth-pass count of the open prisms (shadow volumes)
+      (*nfrag)++;
       const float d = sd[p];
-      const bool pass = (depth_func == SGI_DEPTH_LESS) ? (z < d) : (z <= d);
-      if (pass) atomicAdd(&ct[p], (meta & 1) ? 1 : -1);
+      const bool strict = depth_func == SGI_DEPTH_LESS || (caps && ((meta >> 4) & 7) >= 6);
+      const bool pass = strict ? (z < d) : (z <= d);
+      if (!zfail) { if (pass) atomicAdd(&ct[p], (meta & 1) ? 1 : -1); }
+      else if (!pass) atomicAdd(&ct[p], (meta & 1) ? -1 : 1);
     }
   }
 };
@@ -845,10 +855,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
       if (mine)
         for (int j = 0; j < SGI_BLK_H; j++)
           for (int i = 0; i < SGI_BLK_W; i++) m = fmaxf(m, sd[(by * SGI_BLK_H + j) * SGI_PITCH + bx * SGI_BLK_W + i]);
-      bz[tid] = __float_as_uint(fminf(fmaxf(m, 0.0f), 1.0f));
+      // (depth-fail counting tallies the fragments BEHIND the scene: nothing may be culled on that side)
+      bz[tid] = a.sv_zfail ? ONE_BITS : __float_as_uint(fminf(fmaxf(m, 0.0f), 1.0f));
     }
   }
-  const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func};
+  int nfrag = 0;
+  const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func, a.sv_zfail, a.sv_caps, &nfrag};
   // the nearest-first order only pays where hierarchical depth has something to cull: lists of a few dozen triangles skip it
   const bool sort_items = nitems > 48;
 
@@ -1125,6 +1137,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
       }
     }
   }
+  if (MODE == SGI_MODE_SVCOUNT && a.frag_counter && nfrag) atomicAdd(a.frag_counter, (unsigned long long)nfrag);
   for (int q = tid; MODE != SGI_MODE_DEPTH && q < rs * rs; q += NT) {
     const int lx = qx0 + (q & (rs - 1)), ly = qy0 + (q >> rs_log2);
     const int p = ly * SGI_PITCH + lx;
@@ -1213,9 +1226,13 @@ constexpr size_t tile_smem_bytes() {
 }
 
 // ---- shadow-volume extrusion: ShadowVolumes/src/ShadowVolume.cpp:116-195 -----------------------------------------
+// `per` = 6: the three side quads of the reference's open prism; 8: + near cap (the triangle itself, first vertex first so that
+// its raster record - and with it every fragment depth - is the scene triangle's own) + far cap, closing the volume for
+// depth-fail counting.  cls[t] = the orientation class (dot(average normal, light position) >= 0) the silhouette pass pairs on.
 __global__ void __launch_bounds__(128) k_sv_extrude(const float* __restrict__ xyz, const float* __restrict__ nrm,
                                                     const int32_t* __restrict__ idx, int T, float lx, float ly, float lz,
-                                                    int infinity, float* __restrict__ pxyz, int32_t* __restrict__ pidx) {
+                                                    int infinity, int per, float* __restrict__ pxyz, int32_t* __restrict__ pidx,
+                                                    unsigned char* __restrict__ cls) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const float L[3] = {lx, ly, lz};
@@ -1236,10 +1253,47 @@ __global__ void __launch_bounds__(128) k_sv_extrude(const float* __restrict__ xy
   }
   float d = n[0] * L[0] + n[1] * L[1] + n[2] * L[2];
   // index order flips on dot(avg normal, light POSITION) >= 0  (:61 / :162)
-  const int ordA[18] = {1, 0, 3, 1, 3, 4, 2, 1, 4, 2, 4, 5, 0, 2, 5, 0, 5, 3};
-  const int ordB[18] = {4, 3, 0, 4, 0, 1, 5, 4, 1, 5, 1, 2, 3, 5, 2, 3, 2, 0};
+  const int ordA[24] = {1, 0, 3, 1, 3, 4, 2, 1, 4, 2, 4, 5, 0, 2, 5, 0, 5, 3, 0, 1, 2, 4, 3, 5};
+  const int ordB[24] = {4, 3, 0, 4, 0, 1, 5, 4, 1, 5, 1, 2, 3, 5, 2, 3, 2, 0, 0, 2, 1, 3, 4, 5};
+  const bool A = d >= 0.0f;
+  if (cls) cls[t] = A ? 1 : 0;
 #pragma unroll
-  for (int k = 0; k < 18; k++) pidx[(size_t)t * 18 + k] = t * 6 + ((d >= 0.0f) ? ordA[k] : ordB[k]);
+  for (int k = 0; k < 24; k++)
+    if (k < per * 3) pidx[(size_t)t * per * 3 + k] = t * 6 + (A ? ordA[k] : ordB[k]);
+}
+
+// Silhouette form: one thread per undirected edge of the mesh (groups prepared once per mesh on the host: the directed edges
+// (triangle, local edge) that share a vertex-index pair, backward ones - first index > second - first, each side by triangle).
+// Per orientation class, min(#backward, #forward) quads of either direction cancel in pairs, lowest triangles first; the
+// index triples of a dropped quad become (0,0,0), a degenerate triangle the rasteriser discards at set-up.
+__global__ void __launch_bounds__(128) k_sv_silhouette(const int32_t* __restrict__ grp_start, const int32_t* __restrict__ grp_ent, int G,
+                                                       const unsigned char* __restrict__ cls, int per, int32_t* __restrict__ pidx) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int e0 = grp_start[g], e1 = grp_start[g + 1];
+  if (e1 - e0 < 2) return;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    int nb = 0, nf = 0;
+    for (int e = e0; e < e1; e++) {
+      const int ent = grp_ent[e];                        // (3 t + local edge) << 1 | forward
+      if (cls[(ent >> 1) / 3] == c) { if (ent & 1) nf++; else nb++; }
+    }
+    int kb = min(nb, nf), kf = kb;
+    if (!kb) continue;
+    for (int e = e0; e < e1; e++) {
+      const int ent = grp_ent[e];
+      const int te = ent >> 1, t = te / 3, le = te - 3 * t;
+      if (cls[t] != c) continue;
+      int& k = (ent & 1) ? kf : kb;
+      if (k > 0) {
+        k--;
+        int32_t* o = pidx + ((size_t)t * per + 2 * le) * 3;
+#pragma unroll
+        for (int j = 0; j < 6; j++) o[j] = 0;
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -1390,7 +1444,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   // shadow volumes: per-tile farthest scene depth, so that the binner drops (prism, tile) pairs that lie behind the scene
   unsigned int* tile_zmax = nullptr;
-  if (job.mode == SGI_MODE_SVCOUNT && job.scene_depth && ctx->sv_tile_cull) {
+  if (job.mode == SGI_MODE_SVCOUNT && job.scene_depth && ctx->sv_tile_cull && !job.sv_zfail) {
     tile_zmax = sc.d_tile_zmax;
     k_tile_zmax<<<dim3(tiles_x, tiles_y), 256, 0, st>>>(job.scene_depth, job.W, job.H, tiles_x, tile_zmax);
     ctx->launches++;
@@ -1457,6 +1511,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.rgb = job.rgb; ta.albedo4 = job.albedo4;
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
   ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
+  ta.sv_zfail = job.sv_zfail; ta.sv_caps = job.sv_caps; ta.frag_counter = job.frag_counter;
   for (int k = 0; k < 16; k++) ta.mq[k] = job.mq[k];
   for (int k = 0; k < 4; k++) ta.mqt[k] = job.mqt[k];
   dim3 grid(max_items);
@@ -1476,11 +1531,75 @@ void sgi_raster_free(SgiScratch& sc) {
   sc = SgiScratch();
 }
 
-int sgi_sv_extrude_run(sgi_ctx* ctx, const float light[3], float* prism_xyz, int32_t* prism_idx) {
+// Edge groups of the current mesh for the silhouette pass, built on the host once per index buffer (the topology does not
+// depend on the light): entries sorted by (edge key, direction, triangle).
+static int sv_prepare_edges(sgi_ctx* ctx) {
+  if (ctx->sv_edges_T == ctx->T && ctx->sv_edges_valid) return SGI_OK;
+  const int T = ctx->T;
+  // the host copy of the index buffer: from now on sgi_set_mesh keeps it and only invalidates the groups when the indices change
+  // (a caller that re-uploads the same mesh every frame, as the reference's loadVBOs does, pays one memcmp)
+  std::vector<int32_t>& idx = ctx->h_idx_copy;
+  if (!ctx->sv_track || (int)idx.size() != T * 3) {
+    idx.resize((size_t)T * 3);
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
+    SGI_CUDA(ctx, cudaMemcpyAsync(idx.data(), ctx->d_idx, idx.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->sv_track = true;
+  }
+  struct Ent { long long key; int32_t ent; };
+  std::vector<Ent> e;
+  e.reserve((size_t)T * 3);
+  for (int t = 0; t < T; t++)
+    for (int k = 0; k < 3; k++) {
+      const int a = idx[3 * (size_t)t + k], b = idx[3 * (size_t)t + (k + 1) % 3];
+      if (a == b) continue;                                  // a degenerate edge extrudes a degenerate quad: nothing to pair
+      const long long key = a < b ? ((long long)a << 32) | (unsigned)b : ((long long)b << 32) | (unsigned)a;
+      e.push_back({key, ((3 * t + k) << 1) | (a < b ? 1 : 0)});
+    }
+  std::sort(e.begin(), e.end(), [](const Ent& x, const Ent& y) {
+    if (x.key != y.key) return x.key < y.key;
+    if ((x.ent & 1) != (y.ent & 1)) return (x.ent & 1) < (y.ent & 1);
+    return x.ent < y.ent;
+  });
+  std::vector<int32_t> start, ent(e.size());
+  for (size_t i = 0; i < e.size(); i++) {
+    if (i == 0 || e[i].key != e[i - 1].key) start.push_back((int32_t)i);
+    ent[i] = e[i].ent;
+  }
+  const int G = (int)start.size();
+  start.push_back((int32_t)e.size());
+  if (ctx->d_sv_grp_start) cudaFree(ctx->d_sv_grp_start);
+  if (ctx->d_sv_grp_ent) cudaFree(ctx->d_sv_grp_ent);
+  ctx->d_sv_grp_start = ctx->d_sv_grp_ent = nullptr;
+  SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_sv_grp_start, start.size() * 4));
+  SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_sv_grp_ent, (ent.size() + 1) * 4));
+  SGI_CUDA(ctx, cudaMemcpy(ctx->d_sv_grp_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+  if (!ent.empty()) SGI_CUDA(ctx, cudaMemcpy(ctx->d_sv_grp_ent, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice));
+  ctx->sv_groups = G; ctx->sv_edges_T = T; ctx->sv_edges_valid = true;
+  return SGI_OK;
+}
+
+int sgi_sv_extrude_run(sgi_ctx* ctx, const float light[3], float* prism_xyz, int32_t* prism_idx, int per, int silhouette) {
   if (ctx->T <= 0) return SGI_OK;
+  if (silhouette) {
+    int rc = sv_prepare_edges(ctx);
+    if (rc) return rc;
+    if (ctx->sv_cls_cap < ctx->T) {
+      SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_sv_cls) cudaFree(ctx->d_sv_cls);
+      ctx->d_sv_cls = nullptr; ctx->sv_cls_cap = 0;
+      SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_sv_cls, (size_t)ctx->T));
+      ctx->sv_cls_cap = ctx->T;
+    }
+  }
   k_sv_extrude<<<(ctx->T + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_xyz, ctx->d_nrm, ctx->d_idx, ctx->T, light[0], light[1],
-                                                             light[2], ctx->params.sv_infinity, prism_xyz, prism_idx);
+                                                             light[2], ctx->params.sv_infinity, per, prism_xyz, prism_idx,
+                                                             silhouette ? ctx->d_sv_cls : nullptr);
   ctx->launches++;
+  if (silhouette && ctx->sv_groups > 0) {
+    k_sv_silhouette<<<(ctx->sv_groups + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_sv_grp_start, ctx->d_sv_grp_ent, ctx->sv_groups, ctx->d_sv_cls, per, prism_idx);
+    ctx->launches++;
+  }
   SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;
 }

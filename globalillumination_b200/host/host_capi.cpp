@@ -160,6 +160,7 @@ int sgh_app_set_int(sgh_app* a, const char* name, int32_t v) {
   else if (n == "kernelSize") p.kernelSize = v; else if (n == "lightSourceRadius") p.lightSourceRadius = v;
   else if (n == "numberOfSamples") p.numberOfSamples = v; else if (n == "lightSourceSize") p.lightSourceSize = v;
   else if (n == "svInfinity") a->app.svInfinity = v; else if (n == "svDepthFunc") a->app.svDepthFunc = v;
+  else if (n == "svSilhouette") a->app.svSilhouette = v != 0; else if (n == "svZfail") a->app.svZfail = v != 0;
   else if (n == "animationOn") a->app.animationOn = v != 0;
   else if (n == "fusedMonteCarlo") a->app.fusedMonteCarlo = v != 0;
   else if (n == "commSkip") a->app.commSkip = v != 0;

@@ -166,6 +166,7 @@ int ShadowApp::pushParams(int tech) {
   q.blocker_search_size = p.blockerSearchSize; q.kernel_size = p.kernelSize; q.light_source_radius = p.lightSourceRadius;
   q.max_search = p.maxSearch; q.depth_threshold = p.depthThreshold;
   q.sv_depth_func = svDepthFunc; q.sv_infinity = svInfinity;
+  q.sv_silhouette = svSilhouette ? 1 : 0; q.sv_zfail = svZfail ? 1 : 0;
   q.rect_x0 = rect[0]; q.rect_y0 = rect[1]; q.rect_x1 = rect[2]; q.rect_y1 = rect[3];
   q.multi_partial = (tech == SGI_TECH_MULTI_HARD && lightShardWorld > 1) ? 1 : 0;
   q.multi_fused = (tech == SGI_TECH_MULTI_HARD && fusedMonteCarlo) ? 1 : 0;

@@ -97,6 +97,8 @@ class ShadowApp {
   int windowWidth = 1024, windowHeight = 1024;
   int svInfinity = 100;           // ShadowVolumes/src/main.cpp:469
   int svDepthFunc = SGI_DEPTH_LEQUAL;
+  bool svSilhouette = false;      // extrude silhouette / boundary edges only (interior side quads cancel in pairs); false = the reference's per-triangle prisms
+  bool svZfail = false;           // depth-fail counting over capped volumes (robust when the eye is inside a volume); false = the reference's depth-pass stencil ops
   int rect[4] = {0, 0, 0, 0};     // multi-GPU screen tile (empty = whole window)
   int lightShardRank = 0, lightShardWorld = 1;   // multi-GPU many-light: this process owns lights l = rank (mod world)
   bool fusedMonteCarlo = false;   // renderMonteCarlo: camera pass reduced to primitive ids (sgi_render_prim_ids), positions resolved inside

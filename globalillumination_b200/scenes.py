@@ -36,10 +36,16 @@ WORKLOADS = {
     "c3_dragon": dict(golden="dragon", lines=[], W=3840, H=2160, S=4096, program="shadow_mapping", technique="smsr", params={},
                       scene="Configs/Dragon.txt through the reference's SceneLoader (golden scene_dragon.npz), 100004 triangles"),
     # Configs/TreeWithLeaves.txt (without the missing TreeSub1.obj) — c4: shadow volumes at the reference's window size
-    "c4_tree_sv": dict(golden="tree", lines=[], W=640, H=480, S=64, program="shadow_volumes", technique="naive", params={},
-                       scene="Configs/TreeWithLeaves.txt minus the missing TreeSub1.obj (golden scene_tree.npz), 38200 triangles -> 229200 prism triangles"),
-    "c4_tree_sv_1080p": dict(golden="tree", lines=[], W=1920, H=1080, S=64, program="shadow_volumes", technique="naive", params={},
+    # north_star (4): silhouette extrusion - the side quads of interior edges cancel in pairs and are not drawn (svSilhouette);
+    # the `_pertri` variants draw the reference's per-triangle prisms (ShadowVolume::update as is: the parity mode)
+    "c4_tree_sv": dict(golden="tree", lines=[], W=640, H=480, S=64, program="shadow_volumes", technique="naive", params=dict(svSilhouette=1),
+                       scene="Configs/TreeWithLeaves.txt minus the missing TreeSub1.obj (scene_tree.npz), 38200 triangles; silhouette quads: 74644 of 229200 prism triangles"),
+    "c4_tree_sv_1080p": dict(golden="tree", lines=[], W=1920, H=1080, S=64, program="shadow_volumes", technique="naive", params=dict(svSilhouette=1),
                              scene="as c4_tree_sv at 1920x1080"),
+    "c4_tree_sv_pertri": dict(golden="tree", lines=[], W=640, H=480, S=64, program="shadow_volumes", technique="naive", params={},
+                              scene="Configs/TreeWithLeaves.txt minus the missing TreeSub1.obj (scene_tree.npz), 38200 triangles -> 229200 prism triangles (per-triangle prisms)"),
+    "c4_tree_sv_zfail": dict(golden="tree", lines=[], W=640, H=480, S=64, program="shadow_volumes", technique="naive", params=dict(svSilhouette=1, svZfail=1),
+                             scene="as c4_tree_sv, depth-fail counting over capped volumes"),
 }
 
 

@@ -118,7 +118,8 @@ typedef enum sgi_buffer {
   SGI_BUF_SV_COUNT = 5,     /* int32   [H][W]       signed z-pass count                               */
   SGI_BUF_SV_STENCIL = 6,   /* uint8   [H][W]       count mod 256 (what the 8-bit stencil holds)      */
   SGI_BUF_SV_PRISM_XYZ = 7, /* float   [6T][3]      ShadowVolume::update vertices                     */
-  SGI_BUF_SV_PRISM_IDX = 8, /* int32   [6T][3]      ShadowVolume::update indices                      */
+  SGI_BUF_SV_PRISM_IDX = 8, /* int32   [6T][3]      ShadowVolume::update indices ([8T][3] with sv_zfail: + near cap, far cap per triangle;
+                                                    sv_silhouette: the two triangles of a dropped side quad read (0,0,0))          */
   SGI_BUF_GBUF_ALBEDO = 9,  /* float4  [H][W]       (vertex colour rgb, 1) when colours are set; bg (0,0,0,1)  */
   SGI_BUF_SHADED = 10,      /* float4  [H][W]       deferred Phong image; background = the clear colour        */
   SGI_BUF_EDT_NEAREST = 11, /* int16x2 [H][W]       EDT shadow mapping: nearest shadow-boundary pixel (x, y), -32768 = none */
@@ -204,6 +205,9 @@ int sgi_compute_visibility(sgi_ctx* ctx);     /* computeHardShadows() :400-414 /
  * (ShadowVolumes/src/main.cpp:154-172).  light_pos = un-rotated light eye.  Needs sgi_render_gbuffer first
  * (its SGI_BUF_CAM_DEPTH is the depth pre-pass). */
 int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]);
+/* with the option "sv_count_fragments" = 1: how many prism fragments (pixel centres covered by a volume triangle inside the
+ * rectangle, before the depth test) the last sgi_compute_shadow_volume visited - the unit of work of the stencil pass */
+int sgi_sv_fragments(sgi_ctx* ctx, int64_t* fragments);
 
 /* shadeScene(), ShadowMapping/src/main.cpp:449-457: deferred Phong shading of the G-buffer with the visibility buffer as
  * hardShadowMap (PhongShading.frag:11-47) into SGI_BUF_SHADED; clear_rgba = glClearColor (0.63, 0.82, 0.96, 1). */
@@ -265,6 +269,8 @@ int sgi_unregister_host(void* host_ptr);
  *   "pcss_early_out"  0 (default) every PCSS pixel runs its blocker search as the shader does, 1 = pixels whose light-space depth
  *                     is in (0, 0.989) return 1.0 without a tap: provably what the program computes there (the 0.99 cut-off of
  *                     PlausibleSoftShadow.frag:368), so results stay bit-identical; off by default so that timings count the taps
+ *   "sv_count_fragments" 0 (default); 1 = shadow-volume passes tally their fragments (sgi_sv_fragments; costs a little)
+ *   "tile_bulk_flush" 1 (default) depth tiles leave shared memory by cp.async.bulk row copies, 0 = by 16-byte stores
  *   "sv_tile_cull"    1 (default) shadow volumes: (prism, tile) pairs behind the tile's farthest scene depth are not listed
  *   "borrow_pinned"   0 (default) inputs are copied inside the call, 1 = page-locked inputs are read later by DMA */
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);

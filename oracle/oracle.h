@@ -172,6 +172,14 @@ int  orc_sv_count(const float* prism_xyz, int PV, const int32_t* prism_idx, int 
                   int W, int H, const float* scene_depth, int depth_func,
                   int32_t* count, uint8_t* stencil);
 
+/* silhouette form: keep[3T] = which side quads survive the pairwise cancellation of interior edges */
+void orc_sv_silhouette_keep(const float* nrm, const int32_t* idx, int T, const float light[3], uint8_t* keep);
+/* 6 (caps == 0) or 8 (sides, near cap, far cap) triangles per source triangle; dropped quads are degenerate (0,0,0) */
+void orc_sv_build_volumes(const float* xyz, const float* nrm, int V, const int32_t* idx, int T, const float light[3], int infinity,
+                          const uint8_t* keep, int caps, float* prism_xyz, int32_t* vol_idx);
+int  orc_sv_count_ex(const float* prism_xyz, int PV, const int32_t* prism_idx, int PT, const float mvp[16], int W, int H,
+                     const float* scene_depth, int depth_func, int zfail, int per, int32_t* count, uint8_t* stencil);
+
 int  orc_num_threads(void);
 void orc_set_num_threads(int n);
 

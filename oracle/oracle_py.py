@@ -385,6 +385,39 @@ def sv_count(prism_xyz, prism_idx, mvp, W, H, scene_depth, depth_func=DEPTH_LEQU
     return cnt, st
 
 
+def sv_silhouette_keep(nrm, idx, light):
+    """keep[T, 3]: which side quads survive the pairwise cancellation of interior edges (silhouette form)."""
+    nrm, idx = _f32(nrm), _i32(idx)
+    T = idx.size // 3
+    keep = np.zeros((T, 3), np.uint8)
+    lib().orc_sv_silhouette_keep(_fp(nrm), _ip(idx), T, _fp(_f32(light)), keep.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return keep
+
+
+def sv_build_volumes(xyz, nrm, idx, light, infinity=100, keep=None, caps=False):
+    """(prism vertices [6T,3], volume triangles [(8 if caps else 6) T, 3]); dropped quads are (0,0,0)."""
+    xyz, nrm, idx = _f32(xyz), _f32(nrm), _i32(idx)
+    T = idx.size // 3
+    per = 8 if caps else 6
+    pxyz = np.empty((T * 6, 3), np.float32)
+    vidx = np.empty((T * per, 3), np.int32)
+    kp = None if keep is None else np.ascontiguousarray(keep, np.uint8).ctypes.data_as(C.POINTER(C.c_uint8))
+    lib().orc_sv_build_volumes(_fp(xyz), _fp(nrm), xyz.size // 3, _ip(idx), T, _fp(_f32(light)), int(infinity), kp, int(bool(caps)),
+                               _fp(pxyz), _ip(vidx))
+    return pxyz, vidx
+
+
+def sv_count_ex(prism_xyz, vol_idx, mvp, W, H, scene_depth, depth_func=DEPTH_LEQUAL, zfail=False, per=6):
+    pxyz, pidx = _f32(prism_xyz), _i32(vol_idx)
+    cnt = np.zeros((H, W), np.int32)
+    st = np.zeros((H, W), np.uint8)
+    rc = lib().orc_sv_count_ex(_fp(pxyz), pxyz.size // 3, _ip(pidx), pidx.size // 3, _fp(_f32(mvp)), W, H,
+                               _fp(_f32(scene_depth)), int(depth_func), int(bool(zfail)), int(per), _ip(cnt),
+                               st.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert rc == 0
+    return cnt, st
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -59,10 +59,15 @@ static inline CV clip_lerp(const CV* a, const CV* b, float da, float db) {
   return r;
 }
 
+/* depth clamp (GL_DEPTH_CLAMP semantics for the far plane only): set around the depth-fail shadow-volume pass; the far plane then
+ * neither rejects nor clips and fragment depths saturate at 1 (frag_z clamps to [0,1]) */
+static int g_no_far_clip = 0;
+
 static int clip_polygon(CV* poly, int n, int* clipped) {
   CV tmp[MAXPOLY];
   *clipped = 0;
   for (int p = 0; p < 6; p++) {
+    if (p == 1 && g_no_far_clip) continue;
     int any_out = 0;
     float d[MAXPOLY];
     for (int i = 0; i < n; i++) { d[i] = plane_dist(&poly[i], p); if (!(d[i] >= 0.0f)) any_out = 1; }
@@ -114,6 +119,7 @@ static int setup_triangle(const float* mvp, const float* p0, const float* p1, co
       if (!(v->w + v->y >= 0.0f)) o[4]++;
       if (!(v->w - v->y >= 0.0f)) o[5]++;
     }
+    if (g_no_far_clip) o[1] = 0;
     for (int p = 0; p < 6; p++) if (o[p] == 3) return 0;
   }
   int was_clipped;
@@ -412,11 +418,89 @@ void orc_sv_build_prisms(const float* xyz, const float* nrm, int V, const int32_
   }
 }
 
-int orc_sv_count(const float* prism_xyz, int PV, const int32_t* prism_idx, int PT, const float mvp[16], int W, int H,
-                 const float* scene_depth, int depth_func, int32_t* count, uint8_t* stencil) {
+/* Silhouette form (north_star (4); SURVEY F1: an optimisation of the same counts).  The two side quads that two triangles of the
+ * same orientation class extrude from a shared edge, walked in opposite directions, cover the same pixels with opposite facing:
+ * they are dropped in pairs.  Per undirected edge (vertex-index pair) and class, min(#forward, #backward) pairs go, lowest
+ * triangle indices first; what stays are the quads of silhouette edges (classes differ), boundary edges and the unpaired rest of
+ * non-manifold edges.  keep[3 t + e] = 1 if the quad of triangle t's edge e (v_e -> v_(e+1)%3) is drawn. */
+typedef struct { int64_t key; int32_t te; int32_t cls_dir; } EdgeEnt;
+static int edge_cmp(const void* a, const void* b) {
+  const EdgeEnt* x = (const EdgeEnt*)a; const EdgeEnt* y = (const EdgeEnt*)b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  if (x->cls_dir != y->cls_dir) return x->cls_dir < y->cls_dir ? -1 : 1;
+  return x->te < y->te ? -1 : (x->te > y->te ? 1 : 0);
+}
+void orc_sv_silhouette_keep(const float* nrm, const int32_t* idx, int T, const float light[3], uint8_t* keep) {
+  EdgeEnt* e = (EdgeEnt*)malloc(sizeof(EdgeEnt) * (size_t)(T > 0 ? T : 1) * 3);
+  for (int t = 0; t < T; t++) {
+    int v[3] = {idx[3 * t], idx[3 * t + 1], idx[3 * t + 2]};
+    float n[3];
+    for (int a = 0; a < 3; a++) {
+      n[a] = nrm[3 * (size_t)v[0] + a] + nrm[3 * (size_t)v[1] + a] + nrm[3 * (size_t)v[2] + a];
+      n[a] = n[a] / 3.0f;
+    }
+    float d = n[0] * light[0] + n[1] * light[1] + n[2] * light[2];
+    int cls = d >= 0.0f ? 1 : 0;                                     /* the orientation rule of ShadowVolume.cpp:55-61 */
+    for (int k = 0; k < 3; k++) {
+      int a = v[k], b = v[(k + 1) % 3];
+      EdgeEnt* q = &e[3 * (size_t)t + k];
+      q->key = a < b ? ((int64_t)a << 32) | (uint32_t)b : ((int64_t)b << 32) | (uint32_t)a;
+      q->te = 3 * t + k;
+      q->cls_dir = cls * 2 + (a < b ? 1 : 0);
+      keep[3 * (size_t)t + k] = 1;
+      if (a == b) q->key = -1 - (int64_t)q->te;                      /* a degenerate edge (its quad is degenerate too) pairs with nothing */
+    }
+  }
+  qsort(e, (size_t)T * 3, sizeof(EdgeEnt), edge_cmp);
+  size_t n = (size_t)T * 3, i = 0;
+  while (i < n) {
+    size_t j = i;
+    while (j < n && e[j].key == e[i].key) j++;
+    for (int cls = 0; cls < 2; cls++) {                              /* entries are sorted by (class, direction, triangle) */
+      size_t b0 = i; while (b0 < j && e[b0].cls_dir < cls * 2) b0++;
+      size_t f0 = b0; while (f0 < j && e[f0].cls_dir < cls * 2 + 1) f0++;
+      size_t f1 = f0; while (f1 < j && e[f1].cls_dir < cls * 2 + 2) f1++;
+      size_t nb = f0 - b0, nf = f1 - f0, k = nb < nf ? nb : nf;
+      for (size_t m = 0; m < k; m++) { keep[e[b0 + m].te] = 0; keep[e[f0 + m].te] = 0; }
+    }
+    i = j;
+  }
+  free(e);
+}
+
+/* Volumes with 6 (sides) or 8 (sides + near cap + far cap) triangles per source triangle; vertices as orc_sv_build_prisms.
+ * Quads with keep == 0 become the degenerate triangle (0,0,0), which the rasteriser discards. */
+void orc_sv_build_volumes(const float* xyz, const float* nrm, int V, const int32_t* idx, int T, const float light[3], int infinity,
+                          const uint8_t* keep, int caps, float* prism_xyz, int32_t* vol_idx) {
+  int32_t* side = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T > 0 ? T : 1) * 18);
+  orc_sv_build_prisms(xyz, nrm, V, idx, T, light, infinity, prism_xyz, side);
+  const int per = caps ? 8 : 6;
+  for (int t = 0; t < T; t++) {
+    int32_t* o = vol_idx + (size_t)t * per * 3;
+    for (int k = 0; k < 18; k++) o[k] = side[(size_t)t * 18 + k];
+    if (keep)
+      for (int q = 0; q < 3; q++)
+        if (!keep[3 * (size_t)t + q]) for (int k = 0; k < 6; k++) o[q * 6 + k] = 0;
+    if (caps) {
+      const int ordA = side[(size_t)t * 18] == t * 6 + 1;              /* ORD_A starts 1,0,3 ; ORD_B 4,3,0 */
+      const int nearA[3] = {0, 1, 2}, nearB[3] = {0, 2, 1}, farA[3] = {4, 3, 5}, farB[3] = {3, 4, 5};
+      for (int k = 0; k < 3; k++) { o[18 + k] = t * 6 + (ordA ? nearA[k] : nearB[k]); o[21 + k] = t * 6 + (ordA ? farA[k] : farB[k]); }
+    }
+  }
+  free(side);
+}
+
+/* depth-pass (zfail == 0: the reference's stencil ops, ShadowVolumes/src/main.cpp:160-172) or depth-fail counting (zfail == 1: back
+ * faces +1, front faces -1 on fragments that FAIL the depth test; far plane not clipped, depths saturate at 1).  `per` = triangles
+ * per source triangle in prism_idx; with per == 8 triangles 6 and 7 of each group are caps, whose depth test is strict (a cap
+ * fragment coplanar with the visible surface - the surface's own triangle - counts as failing). */
+int orc_sv_count_ex(const float* prism_xyz, int PV, const int32_t* prism_idx, int PT, const float mvp[16], int W, int H,
+                    const float* scene_depth, int depth_func, int zfail, int per, int32_t* count, uint8_t* stencil) {
   (void)PV;
   int64_t n;
+  g_no_far_clip = zfail ? 1 : 0;
   SubTri* rec = build_records(prism_xyz, prism_idx, PT, mvp, W, H, 0, 0.0f, 0.0f, &n);
+  g_no_far_clip = 0;
   if (!rec) return -1;
   memset(count, 0, sizeof(int32_t) * (size_t)W * H);
   int bands = H < 64 ? 1 : 64;
@@ -427,14 +511,16 @@ int orc_sv_count(const float* prism_xyz, int PV, const int32_t* prism_idx, int P
       const SubTri* s = &rec[k];
       int y0 = s->py0 > r0 ? s->py0 : r0, y1 = s->py1 < r1 ? s->py1 : r1;
       int inc = s->front ? 1 : -1;            /* GL_FRONT zpass INCR_WRAP / GL_BACK zpass DECR_WRAP */
+      int is_cap = per == 8 && ((s->prim >> 3) % 8) >= 6;
       for (int j = y0; j <= y1; j++)
         for (int i = s->px0; i <= s->px1; i++) {
           int64_t E[3];
           if (!cover(s, i, j, E)) continue;
           float z = frag_z(s, E);
           float d = scene_depth[(size_t)j * W + i];
-          int pass = depth_func == ORC_DEPTH_LESS ? (z < d) : (z <= d);
-          if (pass) count[(size_t)j * W + i] += inc;
+          int pass = (depth_func == ORC_DEPTH_LESS || is_cap) ? (z < d) : (z <= d);
+          if (!zfail) { if (pass) count[(size_t)j * W + i] += inc; }
+          else if (!pass) count[(size_t)j * W + i] -= inc;
         }
     }
   }
@@ -442,6 +528,11 @@ int orc_sv_count(const float* prism_xyz, int PV, const int32_t* prism_idx, int P
     for (size_t i = 0; i < (size_t)W * H; i++) stencil[i] = (uint8_t)((uint32_t)count[i] & 255u);
   free(rec);
   return 0;
+}
+
+int orc_sv_count(const float* prism_xyz, int PV, const int32_t* prism_idx, int PT, const float mvp[16], int W, int H,
+                 const float* scene_depth, int depth_func, int32_t* count, uint8_t* stencil) {
+  return orc_sv_count_ex(prism_xyz, PV, prism_idx, PT, mvp, W, H, scene_depth, depth_func, 0, 6, count, stencil);
 }
 
 int orc_num_threads(void) {
