@@ -92,6 +92,13 @@ def metric_name(workload, w):
     return METRIC if workload == "c2_sponza" else f"frames/sec at {w['W']}x{w['H']} ({workload}, {w['program']}/{w['technique']})"
 
 
+def bench_config(workload, w, V, T):
+    """`config` of the JSON line: the workload only, identical in both arms (what differs per run lives under `run`)."""
+    n_l = w["params"].get("numberOfSamples", 1) if w["technique"] == "montecarlo" else 1
+    return {"workload": workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,
+            "params": w["params"], "triangles": int(T), "vertices": int(V), "scene": w["scene"]}
+
+
 def algorithmic_bytes(w, V, T, L):
     """SURVEY.md §8(d) / BASELINE.md §3 per-frame algorithmic bytes of each pass."""
     px, S = w["W"] * w["H"], w["S"]
@@ -200,12 +207,75 @@ def run_reference(args, w, cfg_path):
         "impl": "reference", "metric": metric_name(args.workload, w), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "W": W, "H": H, "shadow_map": S, "technique": w["technique"], "lights": n_l, "scene": w["scene"],
-                   "steps_requested": requested},
+        "config": bench_config(args.workload, w, sc["xyz"].shape[0], sc["idx"].shape[0]), "run": {"steps_requested": requested},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full frames (depth + G-buffer + shadow pass) of the same workload, OpenMP over {cores} threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+
+
+def run_secondary(local_rank, names=("dragon_pcss", "c3_dragon", "c1_teapot", "c4_tree_sv", "c4_tree_sv_pertri"), steps=60, warmup=6):
+    """Short runs of the other configurations through the same loop as the headline (inputs resident, L2 flushed before every
+    timed step, CUDA events per step), so that the driver-run line carries them: PCSS where the filter loop really runs
+    (dragon_pcss), c3 (Dragon 4K RBSM), c1 (Teapot hard), c4 (shadow volumes: silhouette form and the reference's per-triangle
+    prisms, with prism fragments per second - the unit SURVEY 8(d) names for that pass)."""
+    import torch
+    from globalillumination_b200 import capi, hostapi, scenes
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    for name in names:
+        w = scenes.WORKLOADS[name]
+        app = hostapi.App(local_rank)
+        try:
+            if w.get("golden"):
+                app.set_scene(scenes.golden_scene(w["golden"]))
+            else:
+                app.load_scene(scenes.write_config(name))
+            app.configure(w["W"], w["H"], w["S"]); app.set_technique(w["technique"]); app.set(**w["params"])
+            sv = w["program"] == "shadow_volumes"
+            app.set(animationOn=0) if sv else app.set(animationOn=1, animation=-1800.0)
+            ctx = app.context()
+            stream = torch.cuda.Stream(device=local_rank)
+            ctx.set_stream(stream.cuda_stream)
+            with torch.cuda.stream(stream):
+                for attempt in range(6):
+                    try:
+                        for _ in range(warmup):
+                            app.display(w["program"]); app.step_animation(ANIMATION_STEP)
+                        ctx.synchronize()
+                        break
+                    except (capi.SgiError, hostapi.HostError) as e:
+                        if "overflow" not in str(e) or attempt == 5:
+                            raise
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+                for k in range(steps):
+                    flush.zero_()
+                    ev[k][0].record(stream)
+                    app.display(w["program"]); ctx.join()
+                    ev[k][1].record(stream)
+                    app.step_animation(ANIMATION_STEP)
+                ctx.synchronize()
+                ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+                rec = {"value": 1e3 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": steps, "W": w["W"], "H": w["H"], "shadow_map": w["S"],
+                       "technique": w["technique"], "params": w["params"], "scene": w["scene"]}
+                if sv:
+                    ctx.set_option("sv_count_fragments", 1)
+                    app.display(w["program"]); ctx.synchronize()
+                    frags = ctx.sv_fragments()
+                    ctx.set_option("sv_count_fragments", 0)
+                    ctx.set_option("overlap_passes", 0); ctx.enable_timing(True); ctx.reset_timing()
+                    for _ in range(5):
+                        app.display(w["program"])
+                    ctx.synchronize()
+                    t_sv = ctx.pass_time_ms("tile_sv")[0] / 5
+                    ctx.enable_timing(False)
+                    rec.update({"prism_fragments_per_frame": int(frags), "tile_sv_ms": t_sv,
+                                "prism_fragments_per_s": frags / (t_sv * 1e-3) if t_sv > 0 else None,
+                                "note": "fragments = pixel centres covered by a volume triangle (before the depth test), counted by the kernel in a separate frame"})
+            out[name] = rec
+        finally:
+            app.close()
+    return out
 
 
 SHARDED_N1_CACHE = os.path.join(ROOT, "gpurun_out", ".sharded_n1.json")
@@ -340,6 +410,7 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "lights"], help="N>1: frame-parallel, or light shards of one frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the `sharded` record (config c5 light shards, every N)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` records (short runs of the other configurations, N=1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -572,7 +643,11 @@ def main():
         for _ in range(20):
             app.display_e2e(program, result_buf, host_vis.data_ptr(), vis_bytes); app.step_animation(anim_stride)
         e2e_blocking_s = (time.perf_counter() - t0) / 20
-        lit = float((host_vis == 1.0).float().mean()) if result_buf == "visibility" else None
+        lit = None
+        if result_buf == "visibility" and not lights_mode:        # a fixed frame (the first of the animation), not whichever the loops ended on
+            app.set(animation=-1800.0)
+            app.display_e2e(program, result_buf, host_vis.data_ptr(), vis_bytes)
+            lit = float((host_vis == 1.0).float().mean())
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -637,11 +712,11 @@ def main():
         "metric": metric_name(args.workload, w), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "ms_per_step_median": med, "higher_is_better": True, "scaling": "strong" if lights_mode else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "W": w["W"], "H": w["H"], "shadow_map": w["S"], "technique": w["technique"], "lights": n_l,
-                   "params": w["params"], "triangles": T, "vertices": V, "scene": w["scene"],
-                   "l2": ("not flushed: per-frame inputs (depth maps + G-buffer) exceed L2; whole loop timed with one event pair" if lights_mode else
-                          "flushed before every timed step (256 MiB memset on the same stream, outside the event pair)"),
-                   "parallelism": (f"lights x{world} + reduce-scatter (pipelined one frame deep on a side stream)" if lights_mode else f"frames x{world}") if world > 1 else "single GPU", "lit_fraction": lit},
+        "config": bench_config(args.workload, w, V, T),
+        "run": {"l2": ("not flushed: per-frame inputs (depth maps + G-buffer) exceed L2; whole loop timed with one event pair" if lights_mode else
+                       "flushed before every timed step (256 MiB memset on the same stream, outside the event pair)"),
+                "parallelism": (f"lights x{world} + reduce-scatter (pipelined one frame deep on a side stream)" if lights_mode else f"frames x{world}") if world > 1 else "single GPU",
+                "lit_fraction": lit, "lit_fraction_frame": "animation = -1800 (the first frame of the sequence), rendered after the timed loops"},
         "clocks": clock_info, "gpu_launches": int(launches),
         "e2e": {"value": (1 if lights_mode else world) * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(V * (36 if any(l.startswith("c ") for l in w["lines"]) else 24) + T * 12),   # xyz + normals (+ colours) + indices
                 "d2h_bytes_per_step": int(vis_bytes), "steps": e2e_steps, "pipelined_frames_in_flight": 3,
@@ -652,6 +727,8 @@ def main():
         out["with_pcss_early_out"] = early
     if sharded:
         out["sharded"] = sharded
+    if world == 1 and args.workload == "c2_sponza" and not args.no_secondary:
+        out["secondary"] = run_secondary(local_rank)
     if not args.no_cpu_baseline and world == 1:
         a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup = 3, 1
         ref = run_reference(a2, w, cfg_path)
