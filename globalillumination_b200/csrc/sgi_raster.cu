@@ -1074,58 +1074,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
       es.init(X0, Y0, X1, Y1, X2, Y2);
       // No bounding-box test per pixel: a pixel outside the box cannot pass the edge tests, and pixels beyond the
       // viewport (the box is clamped to it) land in tile cells that are never flushed.
-      //
-      // Double-precision form of the three edge functions.  They are affine in the pixel position with integer coefficients;
-      // when every value over the tile stays below 2^52 in magnitude (checked below with the value at the tile origin plus the
-      // largest excursion) each one is EXACT in double arithmetic: the lane's value at its pixel of the tile's first block is
-      // formed once per work item, a block adds two fused multiply-adds per edge (block column / row times the edge's step),
-      // and coverage is one sign test of the three high words.  Same integers as EdgeSet::test, about half the instructions of
-      // the 64-bit integer form (six wide multiplies, their subtractions and two 64-bit-integer-to-float conversions per pixel);
-      // B200's FP64 pipe runs at half the FP32 rate, so this is also a B200-specific choice.
-      const int PXo = ox * SGI_SUBPIX + SGI_SUBPIX / 2, PYo = oy * SGI_SUBPIX + SGI_SUBPIX / 2;
-      const long long Eo0 = (long long)es.dx0 * (long long)(PYo - Y1) - (long long)es.dy0 * (long long)(PXo - X1);
-      const long long Eo1 = (long long)es.dx1 * (long long)(PYo - Y2) - (long long)es.dy1 * (long long)(PXo - X2);
-      const long long Eo2 = (long long)es.dx2 * (long long)(PYo - Y0) - (long long)es.dy2 * (long long)(PXo - X0);
-      const long long span = (long long)SGI_TILE * SGI_SUBPIX;
-      const long long mg0 = llabs(Eo0) + span * (llabs((long long)es.dx0) + llabs((long long)es.dy0));
-      const long long mg1 = llabs(Eo1) + span * (llabs((long long)es.dx1) + llabs((long long)es.dy1));
-      const long long mg2 = llabs(Eo2) + span * (llabs((long long)es.dx2) + llabs((long long)es.dy2));
-      if (mg0 < (1LL << 52) && mg1 < (1LL << 52) && mg2 < (1LL << 52)) {
-        // lane's pixel of block (0,0): (sub_x, sub_y); the top-left bias rides in e0..e2 (covered <=> all three >= 0)
-        const double l0 = (double)(Eo0 - es.b0 + (long long)sub_y * (256LL * es.dx0) - (long long)sub_x * (256LL * es.dy0));
-        const double l1 = (double)(Eo1 - es.b1 + (long long)sub_y * (256LL * es.dx1) - (long long)sub_x * (256LL * es.dy1));
-        const double l2 = (double)(Eo2 - es.b2 + (long long)sub_y * (256LL * es.dx2) - (long long)sub_x * (256LL * es.dy2));
-        const double sx0 = -(double)es.dy0 * (double)(SGI_BLK_W * SGI_SUBPIX), sy0 = (double)es.dx0 * (double)(SGI_BLK_H * SGI_SUBPIX);
-        const double sx1 = -(double)es.dy1 * (double)(SGI_BLK_W * SGI_SUBPIX), sy1 = (double)es.dx1 * (double)(SGI_BLK_H * SGI_SUBPIX);
-        const double sx2 = -(double)es.dy2 * (double)(SGI_BLK_W * SGI_SUBPIX), sy2 = (double)es.dx2 * (double)(SGI_BLK_H * SGI_SUBPIX);
-        const double ub1 = (double)es.b1, ub2 = (double)es.b2;
-        while (mask) {
-          const int k = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int kbx = __shfl_sync(0xffffffffu, bx, k), kby = __shfl_sync(0xffffffffu, by, k);
-          const int lx = kbx * SGI_BLK_W + sub_x, ly = kby * SGI_BLK_H + sub_y;
-          const double dkx = (double)kbx, dky = (double)kby;
-          const double e0 = __fma_rn(dkx, sx0, __fma_rn(dky, sy0, l0));
-          const double e1 = __fma_rn(dkx, sx1, __fma_rn(dky, sy1, l1));
-          const double e2 = __fma_rn(dkx, sx2, __fma_rn(dky, sy2, l2));
-          if ((__double2hiint(e0) | __double2hiint(e1) | __double2hiint(e2)) >= 0) {
-            const float b1 = (float)(e1 + ub1) * ia, b2 = (float)(e2 + ub2) * ia;
-            float z = (z0 + b1 * dz1) + b2 * dz2;
-            z = z + zoff;
-            if (!(z >= 0.0f)) z = 0.0f;
-            if (z > 1.0f) z = 1.0f;
-            sink.fragment(lx, ly, z, meta);
-          }
-          if (MODE != SGI_MODE_SVCOUNT && refresh_bounds) {
-            // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
-            const int p = ly * SGI_PITCH + lx;
-            const unsigned int cur = (MODE == SGI_MODE_DEPTH) ? zt[p] : (unsigned int)(kt[p] >> 32);
-            const unsigned int wmax = __reduce_max_sync(0xffffffffu, cur);
-            const int bi = kby * (SGI_TILE / SGI_BLK_W) + kbx;
-            if (lane == 0 && wmax < bz[bi]) atomicMin(&bz[bi], wmax);
-          }
-        }
-      } else {
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -1141,7 +1089,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
           const int bi = kby * (SGI_TILE / SGI_BLK_W) + kbx;
           if (lane == 0 && wmax < bz[bi]) atomicMin(&bz[bi], wmax);
         }
-      }
       }
     }
     __syncthreads();                                           // every warp is done with this chunk's queue
