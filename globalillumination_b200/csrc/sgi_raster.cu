@@ -680,6 +680,14 @@ __device__ __forceinline__ float frag_z(float z0, float dz1, float dz2, float ia
   return z;
 }
 
+// a * b + c with a 32 x 32 -> 64-bit product (IMAD.WIDE with the 64-bit addend).  Inline PTX so that the compiler keeps the
+// incremental form: written in C it folds the block step back into the edge function and multiplies 64-bit operands again.
+__device__ __forceinline__ long long madw(int a, int b, long long c) {
+  long long d;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+
 // Edge set-up of one triangle for repeated coverage tests.  With bias_e = (edge e owns its boundary ? 0 : 1) the
 // top-left rule `E > 0 || (E == 0 && owns)` is `E - bias >= 0`, and the bias rides for free as the addend of the
 // second wide multiply; all three tests collapse to one sign test of e0|e1|e2.  Exactly the integers cover() produces.
@@ -1074,13 +1082,26 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
       es.init(X0, Y0, X1, Y1, X2, Y2);
       // No bounding-box test per pixel: a pixel outside the box cannot pass the edge tests, and pixels beyond the
       // viewport (the box is clamped to it) land in tile cells that are never flushed.
+      //
+      // The edge functions are affine in the pixel position with integer coefficients: the lane's (biased) values at its pixel
+      // of the tile's first block are formed once per work item; a block then adds (block column) x (8 px step) and (block row) x
+      // (4 px step), which is two wide multiply-adds per edge with the 64-bit lane value as the addend - six IMAD.WIDE and one
+      // sign test per pixel instead of six wide multiplies, their operand differences and three 64-bit subtractions.
+      // Exactly the integers EdgeSet::test produces.
+      const int PXl = (ox + sub_x) * SGI_SUBPIX + SGI_SUBPIX / 2, PYl = (oy + sub_y) * SGI_SUBPIX + SGI_SUBPIX / 2;
+      const long long l0 = (long long)es.dx0 * (long long)(PYl - Y1) - ((long long)es.dy0 * (long long)(PXl - X1) + es.b0);
+      const long long l1 = (long long)es.dx1 * (long long)(PYl - Y2) - ((long long)es.dy1 * (long long)(PXl - X2) + es.b1);
+      const long long l2 = (long long)es.dx2 * (long long)(PYl - Y0) - ((long long)es.dy2 * (long long)(PXl - X0) + es.b2);
       while (mask) {
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
         const int kbx = __shfl_sync(0xffffffffu, bx, k), kby = __shfl_sync(0xffffffffu, by, k);
         const int lx = kbx * SGI_BLK_W + sub_x, ly = kby * SGI_BLK_H + sub_y;
-        long long E1, E2;
-        if (es.test(ox + lx, oy + ly, E1, E2)) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, E1, E2), meta);
+        const int cx = -(kbx * (SGI_BLK_W * SGI_SUBPIX)), cy = kby * (SGI_BLK_H * SGI_SUBPIX);
+        const long long e0 = madw(es.dy0, cx, madw(es.dx0, cy, l0));
+        const long long e1 = madw(es.dy1, cx, madw(es.dx1, cy, l1));
+        const long long e2 = madw(es.dy2, cx, madw(es.dx2, cy, l2));
+        if ((e0 | e1 | e2) >= 0) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, e1 + es.b1, e2 + es.b2), meta);
         if (MODE != SGI_MODE_SVCOUNT && refresh_bounds) {
           // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
           const int p = ly * SGI_PITCH + lx;
