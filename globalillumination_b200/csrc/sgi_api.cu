@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <cstdint>
 #include <utility>
 #include "sgi_internal.cuh"
 #include "sgi_moments.cuh"
@@ -219,6 +220,7 @@ int sgi_destroy(sgi_ctx* ctx) {
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->ev_comm_done[b]) cudaEventDestroy(ctx->ev_comm_done[b]);
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
   if (ctx->vis_spare) cudaFree(ctx->vis_spare);
+  if (ctx->d_mm) cudaFree(ctx->d_mm);
   for (void* p : {(void*)ctx->d_sv_grp_start, (void*)ctx->d_sv_grp_ent, (void*)ctx->d_sv_cls, (void*)ctx->d_sv_frags}) if (p) cudaFree(p);
   if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
   if (ctx->d_rgb) cudaFree(ctx->d_rgb);
@@ -355,7 +357,7 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t V, co
   ctx->d_xyz = ctx->d_xyz_set[s]; ctx->d_nrm = ctx->d_nrm_set[s]; ctx->d_idx = ctx->d_idx_set[s];
   ctx->V = V; ctx->T = T;
   mark_gbuffer_use(ctx);
-  ctx->gbuffer_valid = ctx->shadow_map_valid = false; ctx->ids_valid = false;
+  ctx->gbuffer_valid = ctx->shadow_map_valid = false; ctx->ids_valid = false; ctx->mm_valid = false;
   ctx->moments_tech = ctx->filtered_tech = -1;        // the moment target / filtered map describe the previous geometry
   return SGI_OK;
 }
@@ -446,7 +448,7 @@ int sgi_set_lights(sgi_ctx* ctx, int32_t N, const float* light_mvp, const float*
   memcpy(ctx->h_light_mvp_b, light_mvp_b, (size_t)N * 64);
   memcpy(ctx->light_pos, lpos, 12);
   ctx->trans_dirty = true;          // lightMVPTrans[] is uploaded lazily by the many-light pass (no sync on the single-light path)
-  ctx->shadow_map_valid = false;
+  ctx->shadow_map_valid = false; ctx->mm_valid = false;
   ctx->moments_tech = ctx->filtered_tech = -1;        // a moment target rendered for the previous light (possibly another map size) is stale
   return SGI_OK;
 }
@@ -533,10 +535,27 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
     SGI_CUDA(ctx, cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
     for (int k = 0; k < SGI_LIGHT_LANES; k++) SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[k], ctx->ev_lane_fork, 0));
   }
+  // PCF / PCSS with one light: the tile flush also records the extrema of every 32x32-texel block, dilated afterwards over the
+  // reach of the technique's tap window; the shadow pass then decides whole windows with one comparison (sgi_shadow.cu)
+  ctx->mm_valid = false;
+  const int mm_reach = (ctx->N == 1 && ctx->vis_minmax_cull) ? sgi_minmax_reach(ctx) : 0;
+  if (mm_reach > 0) {
+    const int tiles_x = (ctx->SW + SGI_TILE - 1) >> SGI_TILE_LOG2, tiles_y = (ctx->SH + SGI_TILE - 1) >> SGI_TILE_LOG2;
+    ctx->mm_w = 2 * tiles_x; ctx->mm_h = 2 * tiles_y;
+    const size_t need = (size_t)ctx->mm_w * ctx->mm_h * 4 * 6;          // min | max | two dilated (min, max) sets
+    if (ctx->mm_bytes < need) {
+      sync_all_streams(ctx);
+      if (ctx->d_mm) cudaFree(ctx->d_mm);
+      ctx->d_mm = nullptr; ctx->mm_bytes = 0;
+      SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_mm, need));
+      ctx->mm_bytes = need;
+    }
+  }
   for (int l = 0; l < ctx->N; l++) {
     SgiRasterJob job;
     memset(&job, 0, sizeof(job));
     job.mode = SGI_MODE_DEPTH;
+    if (mm_reach > 0) { job.mm_min = ctx->d_mm; job.mm_max = ctx->d_mm + (size_t)ctx->mm_w * ctx->mm_h; job.mm_w = ctx->mm_w; }
     job.xyz = ctx->d_xyz; job.nrm = ctx->d_nrm; job.idx = ctx->d_idx; job.T = ctx->T;
     memcpy(job.mvp, ctx->h_light_mvp + 16 * (size_t)l, 64);
     job.W = ctx->SW; job.H = ctx->SH;
@@ -551,6 +570,14 @@ int sgi_render_shadow_map(sgi_ctx* ctx) {
       SGI_CUDA(ctx, cudaEventRecord(ctx->ev_lane_done[k], ctx->lane_stream[k]));
       SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[k], 0));
     }
+  if (mm_reach > 0) {
+    // the dilated set belongs to the shadow-map instance just written (the previous frame's shadow pass may still read the other)
+    const int set = (ctx->alt[SGI_BUF_SHADOW_MAP] && (uintptr_t)ctx->buf[SGI_BUF_SHADOW_MAP] > (uintptr_t)ctx->alt[SGI_BUF_SHADOW_MAP]) ? 1 : 0;
+    const int R = (mm_reach + 1 + 31) / 32;
+    int rc = sgi_minmax_dilate(ctx, set, R, ctx->stream);
+    if (rc) return rc;
+    ctx->mm_valid = true; ctx->mm_set = set; ctx->mm_radius = R;
+  }
   sgi_timing_end(ctx, SGI_PASS_SHADOW_MAP, slot, ctx->stream);
   SGI_CUDA(ctx, cudaEventRecord(ctx->ev_geom_main, ctx->stream)); ctx->geom_main_recorded = true;
   ctx->shadow_map_valid = true;
@@ -915,6 +942,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
   else if (!strcmp(name, "sv_count_fragments")) ctx->sv_count_fragments = value ? 1 : 0;
+  else if (!strcmp(name, "vis_minmax_cull")) { ctx->vis_minmax_cull = value ? 1 : 0; ctx->mm_valid = false; }
   else if (!strcmp(name, "tile_threads")) {
     if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) { ctx->err = "tile_threads must be 0, 128 (depth pass only), 256, 512 or 1024"; return SGI_ERR_INVALID; }
     ctx->tile_threads = value;

@@ -496,6 +496,7 @@ struct OrderArgs {
   int32_t* tile_cnt; int n_tiles; int cap; int spill_cap;
   int32_t* counters; int32_t* snap; volatile int32_t* h_flags; int32_t* d_sticky; int size_class;
   int2* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
+  unsigned int* mm_min; unsigned int* mm_max; int mm_n;     // depth pass feeding the min-max cull: block extrema reset here (1.0 / 0.0)
 };
 #define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
 #define SGI_ORDER_REG 16        // tiles per thread held in registers (grids up to 16 384 tiles: an 8192^2 map); larger grids re-read
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nl = a.gx * a.gy;
   const bool in_regs = nl <= 1024 * SGI_ORDER_REG;
+  if (a.mm_min) for (int i = tid; i < a.mm_n; i += 1024) { a.mm_min[i] = 0x3F800000u; a.mm_max[i] = 0u; }
   int c0 = 0, c3 = 0, c5 = 0, st_long = 0, st_tot = 0;
   if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; }
   // this thread's tiles of the job rectangle, i = tid + 1024 k: tile index and cursor
@@ -648,6 +650,7 @@ struct TileArgs {
   float4* mom4; int mom_tech, z_near, z_far; float mq[16], mqt[4];      // MOMENTS
   unsigned int* ids;                                                   // IDS
   int sv_zfail, sv_caps; unsigned long long* frag_counter;             // SVCOUNT: depth-fail mode, capped volumes, optional fragment tally
+  unsigned int* mm_min; unsigned int* mm_max; int mm_w;                // DEPTH: per 32x32-texel block extrema of the map (float bits), or null
 };
 
 #define ONE_BITS 0x3F800000u
@@ -1118,6 +1121,39 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   __syncthreads();
 
   // ---- write the tile to HBM exactly once ------------------------------------------------------------------
+  if (MODE == SGI_MODE_DEPTH && a.mm_min) {
+    // Extrema of the finished depths per 32x32-texel block of the map (the shadow pass culls whole tap windows with them: a
+    // pixel nearer than the smallest depth around its footprint has no blocker, one beyond the largest has no lit tap).
+    // A warp's 32 lanes read one row segment inside ONE block: two warp reductions, then one global atomic pair per warp and row
+    // group.  Texels beyond the map edge still hold the clear value 1.0 (they only make the maximum more conservative).
+    const int bxg = (ox + qx0) >> 5, byg = (oy + qy0) >> 5;
+    if (empty) {
+      const int nb = (rs + 31) >> 5;
+      if (tid < nb * nb) {
+        const int o = (byg + tid / nb) * a.mm_w + bxg + tid % nb;
+        atomicMax(&a.mm_max[o], ONE_BITS);                    // (the minimum is already 1.0)
+      }
+    } else {
+      unsigned int mn = 0xFFFFFFFFu, mx = 0u;
+      int cur = -1;
+      for (int q = tid; q < rs * rs; q += NT) {
+        const int lxr = q & (rs - 1), lyr = q >> rs_log2;
+        const int blk = (lyr >> 5) * 2 + (lxr >> 5);          // block of the region this texel belongs to (warp-uniform)
+        if (blk != cur && cur >= 0) {
+          mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+          if (lane == 0) { const int o = (byg + (cur >> 1)) * a.mm_w + bxg + (cur & 1); atomicMin(&a.mm_min[o], mn); atomicMax(&a.mm_max[o], mx); }
+          mn = 0xFFFFFFFFu; mx = 0u;
+        }
+        cur = blk;
+        const unsigned int v = zt[(qy0 + lyr) * SGI_PITCH + qx0 + lxr];
+        mn = min(mn, v); mx = max(mx, v);
+      }
+      if (cur >= 0) {
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) { const int o = (byg + (cur >> 1)) * a.mm_w + bxg + (cur & 1); atomicMin(&a.mm_min[o], mn); atomicMax(&a.mm_max[o], mx); }
+      }
+    }
+  }
   if (MODE == SGI_MODE_DEPTH) {
     const int gx0 = ox + qx0, gy0 = oy + qy0;
     const int wv = min(rs, a.W - gx0);                          // columns of the region inside the map
@@ -1492,6 +1528,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   oa.counters = sc.d_counters; oa.snap = sc.d_snap; oa.h_flags = sc.h_flags; oa.d_sticky = sc.d_sticky; oa.size_class = size_class;
   oa.order = sc.d_tile_order; oa.tiles_x = tiles_x; oa.tx0 = tx0; oa.ty0 = ty0; oa.gx = tx1 - tx0 + 1; oa.gy = ty1 - ty0 + 1;
   oa.busiest_first = ctx->tile_order; oa.max_items = max_items; oa.split_floor = ctx->tile_split; oa.n_sm = ctx->n_sm;
+  oa.mm_min = job.mm_min; oa.mm_max = job.mm_max; oa.mm_n = job.mm_min ? job.mm_w * (2 * tiles_y) : 0;   // (mm_w = 2 * tiles_x)
 
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
   k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
@@ -1533,6 +1570,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
   ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
   ta.sv_zfail = job.sv_zfail; ta.sv_caps = job.sv_caps; ta.frag_counter = job.frag_counter;
+  ta.mm_min = job.mm_min; ta.mm_max = job.mm_max; ta.mm_w = job.mm_w;
   for (int k = 0; k < 16; k++) ta.mq[k] = job.mq[k];
   for (int k = 0; k < 4; k++) ta.mqt[k] = job.mqt[k];
   dim3 grid(max_items);
@@ -1542,6 +1580,37 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   else if (job.mode == SGI_MODE_IDS) rc = launch_tile<SGI_MODE_IDS>(ctx, ta, grid, n_rect_tiles, st);
   else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
   return rc;
+}
+
+// Dilation of the block extrema over the reach of the shadow pass's tap window: out[b] = min / max over the (2R+1)^2 blocks around
+// b, blocks outside the map counting as depth 0 for the minimum (CLAMP_TO_BORDER: a tap outside the map reads 0).  A pixel whose
+// centre texel lies in block b has its whole window (reach <= 32 R - 1 texels) inside that neighbourhood.
+namespace {
+__global__ void __launch_bounds__(256) k_mm_dilate(const unsigned int* __restrict__ mn, const unsigned int* __restrict__ mx, int w, int h, int vw, int vh, int R,
+                                                   float* __restrict__ dmin, float* __restrict__ dmax) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= w * h) return;
+  const int bx = i % w, by = i / w;
+  unsigned int lo = 0x3F800000u, hi = 0u;
+  for (int dy = -R; dy <= R; dy++)
+    for (int dx = -R; dx <= R; dx++) {
+      const int x = bx + dx, y = by + dy;
+      if (x < 0 || y < 0 || x >= vw || y >= vh) { lo = 0u; continue; }       // beyond the map: border depth 0
+      lo = min(lo, mn[y * w + x]); hi = max(hi, mx[y * w + x]);
+    }
+  dmin[i] = __uint_as_float(lo); dmax[i] = __uint_as_float(hi);
+}
+}  // namespace
+
+int sgi_minmax_dilate(sgi_ctx* ctx, int set, int R, cudaStream_t st) {
+  const int n = ctx->mm_w * ctx->mm_h;
+  unsigned int* base = ctx->d_mm;
+  // blocks that hold map texels: ceil(S / 32) per axis (the arrays are padded to whole 64x64 tiles)
+  k_mm_dilate<<<(n + 255) / 256, 256, 0, st>>>(base, base + n, ctx->mm_w, ctx->mm_h, (ctx->SW + 31) >> 5, (ctx->SH + 31) >> 5, R,
+                                               (float*)(base + (size_t)(2 + 2 * set) * n), (float*)(base + (size_t)(3 + 2 * set) * n));
+  ctx->launches++;
+  SGI_CUDA(ctx, cudaGetLastError());
+  return SGI_OK;
 }
 
 void sgi_raster_free(SgiScratch& sc) {

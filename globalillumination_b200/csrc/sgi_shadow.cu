@@ -28,6 +28,9 @@ struct VisArgs {
   float bs_q[SGI_MAX_PCF_TAPS]; int bs_w0, bs_n;              // (float(w)*blockerSearchWidth)/filterWidth      (PlausibleSoftShadow.frag:180)
   const float4* trans; int N; size_t layer;
   int pcss_early_out;      // option "pcss_early_out" (validated on the host): see pcss_t
+  // min-max cull: extrema of the depth map over the reach of the tap window, per 32x32-texel block of the window's centre texel
+  const float* dmin; const float* dmax; int mm_w; float mm_limit;     // mm_limit: largest reach (texels) the dilation covers
+  float pcf_reach, bs_reach;                                          // reach of the PCF grid / the PCSS blocker search, in texels
   // multi_fused: the camera pass's primitive ids and raster records (positions are resolved here instead of read from a G-buffer)
   const unsigned int* ids; const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
 };
@@ -103,12 +106,37 @@ __device__ __forceinline__ int keys_or(const int (&k)[N], int n) {
   return m;
 }
 
+// Min-max cull.  dmin / dmax hold, for the 32x32-texel block of the window's centre texel, the smallest / largest depth of every
+// texel a tap window of reach <= mm_limit around that texel can touch (taps beyond the map edge read 0 and are folded into the
+// minimum).  z <= dmin: every tap compares lit; z > dmax: every tap compares shadowed - the taps' values are not needed, only
+// their number, and the result is the one the tap loop would produce, bit for bit.  Returns 0 (undecided), 1 (all lit), 2 (all shadowed).
+__device__ __forceinline__ int mm_classify(const VisArgs& a, const Smap& s, float4 c, float reach) {
+  if (!a.dmin || !(reach <= a.mm_limit)) return 0;
+  const int tx = axis_texel(c.x, s.fw), ty = axis_texel(c.y, s.fh);
+  if ((tx | ty) < 0) return 0;
+  const int b = (ty >> 5) * a.mm_w + (tx >> 5);
+  if (c.z <= __ldg(&a.dmin[b])) return 1;
+  if (c.z > __ldg(&a.dmax[b])) return 2;
+  return 0;
+}
+// what `count` taps that all compare shadowed add up to, in the shaders' own order of additions
+__device__ __forceinline__ float sum_shadowed(float si, int count) {
+  float illum = 0.0f;
+  for (int i = 0; i < count; i++) illum += si;
+  return illum;
+}
+
 // ---- Shadow.frag:86-116 (tap offsets precomputed on the host with the same fp32 loop) ----
 // N = taps per axis known at compile time (0 = run-time count, columns kept in local memory)
 template <int N, bool SHARED>
 __device__ __forceinline__ float pcf_t(const VisArgs& a, const Smap& s, const TapSrc<SHARED>& src, float4 c) {
   const int n = N ? N : a.pcf_n;
   if (n <= 0) return 1.0f;
+  if (!SHARED) {
+    const int cls = mm_classify(a, s, c, a.pcf_reach);
+    if (cls == 1) return (float)(n * n) / (float)(n * n);             // n*n additions of 1.0 are exact
+    if (cls == 2) return sum_shadowed(a.p.shadow_intensity, n * n) / (float)(n * n);
+  }
   int rows[N ? N : SGI_MAX_PCF_TAPS];
 #pragma unroll
   for (int ih = 0; ih < (N ? N : SGI_MAX_PCF_TAPS); ih++)
@@ -264,11 +292,25 @@ __device__ __forceinline__ float pcss_filter(const VisArgs& a, const Smap& s, co
 template <int NB, int NK>
 __device__ __forceinline__ float pcss_t(const VisArgs& a, const Smap& s, float4 c) {
   if (a.pcss_early_out && c.z > 0.0f && c.z < SGI_PCSS_EARLY_Z) return 1.0f;
+  // no depth around the blocker-search window is nearer than the pixel: no blocker, the average is 1.0, the penumbra width
+  // ((z - 1) / 1 ...) is not positive and the program returns 1.0 (PlausibleSoftShadow.frag:189-190,386)
+  if (c.z > 0.0f && c.z <= 1.0f && a.p.light_source_radius >= 0 && a.p.z_near >= 0 && a.p.kernel_size > 0 && mm_classify(a, s, c, a.bs_reach) == 1) return 1.0f;
   const TapSrc<false> g = {s.d, s.w, 0, 0};
   const float avg = pcss_blockers<NB, false>(a, s, g, c);
   const float pw = pcss_penumbra(a.p, avg, c.z);
   const float stepSize = 2.0f * pw / (float)a.p.kernel_size;
   if (stepSize <= 0.0f || stepSize >= 1.0f) return 1.0f;
+  {
+    // the filter's window reaches |pw| (in map units) from the centre: decided as a whole where the extrema allow it
+    const int cls = mm_classify(a, s, c, fabsf(pw) * fmaxf(s.fw, s.fh) + 2.0f);
+    if (cls) {
+      const float fw2 = ((float)a.p.kernel_size - 1.0f) * 0.5f;
+      const int w0 = (int)(-fw2);
+      const int nk = NK ? NK : ((fw2 >= 0.0f) ? (int)fw2 - w0 + 1 : 0);
+      const float kk = (float)(a.p.kernel_size * a.p.kernel_size);
+      return (cls == 1 ? (float)(nk * nk) : sum_shadowed(a.p.shadow_intensity, nk * nk)) / kk;
+    }
+  }
   return pcss_filter<NK, false>(a, s, g, c, pw);
 }
 
@@ -900,6 +942,25 @@ static int moments_visibility_run(sgi_ctx* ctx, cudaStream_t st) {
   return SGI_OK;
 }
 
+// texels the current technique's fixed tap window reaches from its centre texel (PCF grid, PCSS blocker search), + margin; 0 = the
+// technique has no window the min-max cull applies to
+int sgi_minmax_reach(const sgi_ctx* ctx) {
+  const sgi_params& p = ctx->params;
+  const float smax = (float)(ctx->SW > ctx->SH ? ctx->SW : ctx->SH);
+  if (p.technique == SGI_TECH_PCF) {
+    float m = 0.0f;
+    for (int k = 0; k < ctx->pcf_n; k++) m = fmaxf(m, fabsf(ctx->pcf_off[k]));
+    const float r = m / (float)(ctx->SW < ctx->SH ? ctx->SW : ctx->SH) * smax + 3.0f;
+    return r < 4096.0f ? (int)r + 1 : 0;
+  }
+  if (p.technique == SGI_TECH_PCSS) {
+    const float bsw = ((float)ctx->SW <= 1024.0f) ? (float)p.light_source_radius / (float)ctx->SW : (float)p.light_source_radius / 1024.0f;
+    const float r = fabsf(bsw) * smax + 3.0f;             // |w| <= filterWidth: |(w * bsw) / filterWidth| <= bsw
+    return r < 4096.0f ? (int)r + 1 : 0;
+  }
+  return 0;
+}
+
 int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   if (sgi_is_moment_tech(ctx->params.technique)) return moments_visibility_run(ctx, stream);
   VisArgs a;
@@ -926,6 +987,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
   a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
   a.ids = nullptr; a.rec = nullptr; a.attr = nullptr; a.ovf_base = nullptr;
+  a.dmin = nullptr; a.dmax = nullptr; a.mm_w = 0; a.mm_limit = 0.0f; a.pcf_reach = 1.0e30f; a.bs_reach = 1.0e30f;
   a.pcss_early_out = (ctx->pcss_early_out && ctx->params.light_source_radius >= 0 && ctx->params.z_near >= 0 && ctx->params.kernel_size > 0 &&
                       ctx->params.blocker_search_size <= SGI_MAX_PCF_TAPS && !ctx->vis_staged) ? 1 : 0;
   {
@@ -947,6 +1009,16 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
     }
   }
 
+  if (ctx->mm_valid && ctx->vis_minmax_cull && !ctx->vis_staged && (ctx->params.technique == SGI_TECH_PCF || ctx->params.technique == SGI_TECH_PCSS)) {
+    const int n = ctx->mm_w * ctx->mm_h;
+    a.dmin = (const float*)(ctx->d_mm + (size_t)(2 + 2 * ctx->mm_set) * n); a.dmax = (const float*)(ctx->d_mm + (size_t)(3 + 2 * ctx->mm_set) * n);
+    a.mm_w = ctx->mm_w; a.mm_limit = (float)(32 * ctx->mm_radius - 1);
+    const float smax = (float)(ctx->SW > ctx->SH ? ctx->SW : ctx->SH);
+    float pr = 0.0f, br = 0.0f;
+    for (int k = 0; k < a.pcf_n; k++) { pr = fmaxf(pr, fabsf(a.pcf_du[k]) * smax); pr = fmaxf(pr, fabsf(a.pcf_dv[k]) * smax); }
+    for (int k = 0; k < a.bs_n; k++) br = fmaxf(br, fabsf(a.bs_q[k]) * smax);
+    a.pcf_reach = pr + 2.0f; a.bs_reach = br + 2.0f;
+  }
   int rw = a.rx1 - a.rx0, rh = a.ry1 - a.ry0;
   if (rw <= 0 || rh <= 0) return SGI_OK;
   cudaStream_t st = stream;

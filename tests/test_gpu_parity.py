@@ -684,3 +684,31 @@ def test_pcss_early_out_option_is_exact(ctx):
             fg = pos.reshape(-1, 4)[:, 0] != 0
             hit.append(float(((z > 0) & (z < 0.989))[fg].mean()))
     assert hit[0] > 0.9 and hit[2] < 0.01 and 0.05 < hit[4] < 0.95, hit
+
+
+# ---- min-max cull of the PCF / PCSS tap windows (block extrema of the depth map, dilated over the window's reach) ----------
+@pytest.mark.parametrize("name,tech,W,H,S,kw,near_light", [
+    ("teapot", "pcf", 640, 360, 512, {}, False), ("teapot", "pcss", 640, 360, 512, {}, False),
+    ("dragon", "pcss", 480, 270, 1024, {}, False), ("dragon", "pcss", 480, 270, 300, dict(kernel_size=7), False),
+    ("teapot", "pcf", 320, 180, 200, dict(kernel_order=9, penumbra_size=3), False),
+    ("teapot", "pcss", 400, 300, 256, {}, True), ("teapot", "pcf", 400, 300, 256, {}, True)])
+def test_minmax_cull_is_exact(ctx, name, tech, W, H, S, kw, near_light):
+    """With the cull on (default) and off the visibility is the same to the bit, and equal to the oracle, which runs every tap.
+    near_light: a light frustum that does not contain the scene, so tap windows cross the map border (CLAMP_TO_BORDER depth 0)."""
+    sc = dict(util.scene(name))
+    if near_light:
+        sc["light_eye"] = (np.asarray(sc["light_eye"], np.float32) * np.float32(0.25)).astype(np.float32)
+    po, pg = util.params_pair(tech, S, depth_threshold=float(sc["depth_threshold"]), **kw)
+    fm = setup_frame(ctx, sc, W, H, S, pg)
+    out = []
+    for on in (1, 0, 1):
+        ctx.set_option("vis_minmax_cull", on)
+        ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+        out.append(ctx.read("visibility"))
+    ctx.set_option("vis_minmax_cull", 1)
+    assert util.bits_equal(out[0], out[1]) and util.bits_equal(out[0], out[2]), util.describe_diff(out[0], out[1])
+    cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
+    vis_o = O.visibility(po, cam, fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
+    assert util.bits_equal(out[0], vis_o), util.describe_diff(out[0], vis_o)
+    fg = vis_o > 0
+    assert 0.02 < (vis_o[fg] == 1.0).mean() < 0.999                      # lit and shadowed regions both present
