@@ -612,31 +612,6 @@ def main():
             early = {"value": world * n_e / (ms_e / 1e3), "unit": "frames/s", "steps": n_e,
                      "note": "option pcss_early_out = 1: pixels with light-space depth in (0, 0.989) return 1.0 without taps (provably the program's result, bit-identical); not the headline"}
 
-        # ---- the same loop with the min-max cull off (option "vis_minmax_cull": every tap of every window is loaded), for comparison
-        no_cull = None
-        if w["technique"] in ("pcss", "pcf") and not lights_mode:
-            ctx.set_option("vis_minmax_cull", 0)
-            n_e = min(args.steps, 300)
-            for k in range(5):
-                frame(); app.step_animation(anim_stride)
-            ctx.synchronize()
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_e)]
-            for k in range(n_e):
-                flush.zero_()
-                evs[k][0].record(stream); frame(); evs[k][1].record(stream)
-                app.step_animation(anim_stride)
-            ctx.synchronize()
-            ms_n = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-            ctx.set_option("overlap_passes", 0); ctx.enable_timing(True); ctx.reset_timing()
-            for k in range(20):
-                frame(); app.step_animation(anim_stride)
-            ctx.synchronize()
-            vk = ctx.pass_time_ms("vis_kernel")
-            ctx.enable_timing(False); ctx.set_option("overlap_passes", 1)
-            ctx.set_option("vis_minmax_cull", 1)
-            no_cull = {"value": world * n_e / (ms_n / 1e3), "unit": "frames/s", "steps": n_e, "vis_kernel_ms": vk[0] / max(1, vk[1]),
-                       "note": "option vis_minmax_cull = 0: every tap window is loaded tap by tap (results identical); the headline runs with the cull on"}
-
         # ---- e2e: host buffers in, host buffer out, every frame ----
         vis_bytes = w["W"] * w["H"] * 4
         E2E_DEPTH = 3            # frames in flight: the host queues frame k while k-1 renders and k-2 is copied out
@@ -750,8 +725,6 @@ def main():
     }
     if early:
         out["with_pcss_early_out"] = early
-    if no_cull:
-        out["without_minmax_cull"] = no_cull
     if sharded:
         out["sharded"] = sharded
     if world == 1 and args.workload == "c2_sponza" and not args.no_secondary:

@@ -269,9 +269,11 @@ int sgi_unregister_host(void* host_ptr);
  *   "pcss_early_out"  0 (default) every PCSS pixel runs its blocker search as the shader does, 1 = pixels whose light-space depth
  *                     is in (0, 0.989) return 1.0 without a tap: provably what the program computes there (the 0.99 cut-off of
  *                     PlausibleSoftShadow.frag:368), so results stay bit-identical; off by default so that timings count the taps
- *   "vis_minmax_cull" 1 (default) PCF / PCSS with one light: the depth pass also records the extrema of every 32x32-texel block of
- *                     the map; a pixel nearer than every depth its tap window can reach (or beyond all of them) is decided
- *                     without taps - the same value the tap loop produces, bit for bit; 0 = every tap is loaded
+ *   "vis_minmax_cull" 0 (default); 1 = PCF / PCSS with one light: the depth pass also records the extrema of every 32x32-texel block
+ *                     of the map; a pixel nearer than every depth its tap window can reach (or beyond all of them) is decided
+ *                     without taps - the same value the tap loop produces, bit for bit.  Off by default: measured on the bench
+ *                     scenes it decides few windows (a surface sloped against the light blocks itself within the window's reach)
+ *                     and costs more than it saves (profiles/r2_experiments.txt)
  *   "sv_count_fragments" 0 (default); 1 = shadow-volume passes tally their fragments (sgi_sv_fragments; costs a little)
  *   "tile_bulk_flush" 1 (default) depth tiles leave shared memory by cp.async.bulk row copies, 0 = by 16-byte stores
  *   "sv_tile_cull"    1 (default) shadow volumes: (prism, tile) pairs behind the tile's farthest scene depth are not listed

@@ -11,7 +11,7 @@ d=json.loads(open("gpurun_out/${tag}_bench_c2.json").read())
 print("c2 fps %.1f e2e %.1f" % (d["value"], d["e2e"]["value"]), {k: round(v,4) for k,v in d["pass_ms"].items()})
 print("sharded ms", (d.get("sharded") or {}).get("ms_per_frame"), (d.get("sharded") or {}).get("pass_ms_rank0"))
 for k, v in (d.get("secondary") or {}).items(): print("secondary", k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items() if a in ("value", "ms_per_step", "prism_fragments_per_frame", "tile_sv_ms", "prism_fragments_per_s")})
-print("cpu_baseline", d.get("cpu_baseline"), "lit", d["run"]["lit_fraction"], "| no cull:", d.get("without_minmax_cull"), "| shadow_pass", {k: v for k, v in (d.get("shadow_pass") or {}).items() if k in ("launch_ms", "hbm_frac", "l2_taps_frac")})
+print("cpu_baseline", d.get("cpu_baseline"), "lit", d["run"]["lit_fraction"], "| shadow_pass", {k: v for k, v in (d.get("shadow_pass") or {}).items() if k in ("launch_ms", "hbm_frac", "l2_taps_frac")})
 PY
 python bench.py --workload c4_tree_sv --steps 40 --warmup 3 --no-cpu-baseline --no-sharded > gpurun_out/${tag}_bench_c4.json 2>> gpurun_out/${tag}_bench.err
 python bench.py --workload c4_tree_sv_pertri --steps 40 --warmup 3 --no-cpu-baseline --no-sharded > gpurun_out/${tag}_bench_c4p.json 2>> gpurun_out/${tag}_bench.err

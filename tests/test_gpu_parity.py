@@ -693,7 +693,7 @@ def test_pcss_early_out_option_is_exact(ctx):
     ("teapot", "pcf", 320, 180, 200, dict(kernel_order=9, penumbra_size=3), False),
     ("teapot", "pcss", 400, 300, 256, {}, True), ("teapot", "pcf", 400, 300, 256, {}, True)])
 def test_minmax_cull_is_exact(ctx, name, tech, W, H, S, kw, near_light):
-    """With the cull on (default) and off the visibility is the same to the bit, and equal to the oracle, which runs every tap.
+    """With the cull on and off (the default) the visibility is the same to the bit, and equal to the oracle, which runs every tap.
     near_light: a light frustum that does not contain the scene, so tap windows cross the map border (CLAMP_TO_BORDER depth 0)."""
     sc = dict(util.scene(name))
     if near_light:
@@ -705,7 +705,7 @@ def test_minmax_cull_is_exact(ctx, name, tech, W, H, S, kw, near_light):
         ctx.set_option("vis_minmax_cull", on)
         ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
         out.append(ctx.read("visibility"))
-    ctx.set_option("vis_minmax_cull", 1)
+    ctx.set_option("vis_minmax_cull", 0)
     assert util.bits_equal(out[0], out[1]) and util.bits_equal(out[0], out[2]), util.describe_diff(out[0], out[1])
     cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
     vis_o = O.visibility(po, cam, fm["light_mvp_b"], ctx.read("gbuf_pos"), ctx.read("gbuf_nrm"), ctx.read("shadow_map")[0])
