@@ -308,6 +308,16 @@ def run_sharded(rank, world, local_rank, steps=24, warmup=4):
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)
     n_l = w["params"]["numberOfSamples"]
+    owners, costs = None, None
+    if world > 1:
+        # the depth pass of a light costs what the light sees (here up to 1.4x apart): shards are balanced with measured costs
+        # (longest first, to the least loaded rank) instead of dealt round-robin; rank 0's measurement decides for everybody
+        from globalillumination_b200 import sharding
+        box = [[float(c) for c in app.light_costs(n_l)] if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        costs = box[0]
+        owners = sharding.balance_lights(costs, world)
+        app.set_light_owners(owners)
 
     def barrier():
         if world > 1:
@@ -366,6 +376,10 @@ def run_sharded(rank, world, local_rank, steps=24, warmup=4):
             passes[pname] = ms / n_p
     ctx.enable_timing(False)
     ctx.set_option("overlap_passes", 1)
+    all_passes = [passes]
+    if world > 1:
+        all_passes = [None] * world
+        dist.all_gather_object(all_passes, passes)
     r0, r1 = ctx.comm_strip(rank) if world > 1 else (0, w["H"])
     vis = ctx.read("visibility")[r0:r1]
     lit = float((vis == 1.0).mean())
@@ -382,6 +396,8 @@ def run_sharded(rank, world, local_rank, steps=24, warmup=4):
                        "issued by the C ABI (sgi_gather / sgi_reduce_lights)" % (px * 4 // 1000000, px * 4 // 1000000)) if world > 1 else None,
         "ms_per_frame_without_exchanges": ms_nocomm, "exposed_comm_ms": (ms_frame - ms_nocomm) if ms_nocomm is not None else 0.0,
         "pass_ms_rank0": passes, "strip_rows_rank0": [r0, r1], "lit_fraction_rank0_strip": lit,
+        "tile_depth_ms_per_rank": [round(p.get("tile_depth", 0.0), 4) for p in all_passes],
+        "light_owner": owners, "light_cost_ms": [round(c, 4) for c in costs] if costs else None,
     }
     try:
         if world == 1:

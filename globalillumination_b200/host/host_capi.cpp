@@ -123,6 +123,20 @@ int sgh_app_comm_init(sgh_app* a, const void* id128, size_t bytes, int32_t rank,
   return rc;
 }
 
+// many-light shards balanced by cost: time each light's depth pass (sgh_app_light_costs), then say which rank owns which light
+// (sgh_app_set_light_owners; every rank must be given the same table)
+int sgh_app_light_costs(sgh_app* a, float* ms, int32_t n) {
+  if (!a || !ms) return -1;
+  int rc = a->app.measureLightCosts(ms, n);
+  if (rc) g_err = a->app.error();
+  return rc;
+}
+int sgh_app_set_light_owners(sgh_app* a, const int32_t* owner, int32_t n) {
+  if (!a || n < 0 || (n > 0 && !owner)) return -1;
+  a->app.lightOwner.assign(owner, owner + n);
+  return 0;
+}
+
 // technique names = the reference's menu entries / ShadowParams flags
 int sgh_app_set_technique(sgh_app* a, const char* name) {
   if (!a || !name) return -1;

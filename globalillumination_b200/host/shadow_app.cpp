@@ -287,7 +287,7 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
   Mat4 model = modelMatrix();
   FrameMatrices f;
   for (int s = 0; s < n; s++) {
-    bool mine = (s % lightShardWorld) == lightShardRank;
+    bool mine = ((int)lightOwner.size() == n ? lightOwner[s] : s % lightShardWorld) == lightShardRank;
     if (!mine && s != n - 1) continue;
     Vec3 e = uniformSample(lightEye, shadowParams.lightSourceSize, n, s), a = uniformSample(lightAt, shadowParams.lightSourceSize, n, s);
     f = composeFrame(e, a, lightUp, cameraEye, cameraAt, cameraUp, model, windowWidth, windowHeight, shadowParams.shadowMapWidth,
@@ -308,6 +308,36 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
   if ((rc = sgi_compute_visibility(ctx))) return fail(rc, "sgi_compute_visibility");
   // partial sums of the ranks -> final visibility of this rank's strip (reduce-scatter + the division of AccurateSoftShadow.frag:127)
   if (commOn && lightShardWorld > 1 && !commSkip) { if ((rc = sgi_reduce_lights(ctx, n))) return fail(rc, "sgi_reduce_lights"); }
+  return 0;
+}
+
+// Cost of each light's depth pass (they differ with what the light sees): the caller balances the light shards with them.
+int ShadowApp::measureLightCosts(float* ms, int n) {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  if (n <= 0 || n > 1024) { err = "measureLightCosts: n must be in 1..1024"; return SGI_ERR_INVALID; }
+  int rc;
+  if (!uploaded) { if ((rc = uploadScene())) return rc; }
+  updateLight();
+  Mat4 model = modelMatrix();
+  Vec3 shading = mul3(rotate(180.0f, Vec3{0, 1, 0}), lightEye);
+  if ((rc = pushParams(SGI_TECH_HARD))) return rc;
+  for (int pass = 0; pass < 2; pass++)                 // first round: allocations and list sizing; second round: timed
+    for (int s = 0; s < n; s++) {
+      Vec3 e = uniformSample(lightEye, shadowParams.lightSourceSize, n, s), a = uniformSample(lightAt, shadowParams.lightSourceSize, n, s);
+      FrameMatrices f = composeFrame(e, a, lightUp, cameraEye, cameraAt, cameraUp, model, windowWidth, windowHeight, shadowParams.shadowMapWidth,
+                                     shadowParams.shadowMapHeight);
+      if ((rc = sgi_set_lights(ctx, 1, f.lightMVP.m, f.lightMVPBiased.m, &shading.x, shadowParams.shadowMapWidth, shadowParams.shadowMapHeight))) return fail(rc, "sgi_set_lights");
+      if (pass) { sgi_enable_timing(ctx, 1); sgi_reset_timing(ctx); }
+      if ((rc = sgi_render_shadow_map(ctx))) return fail(rc, "sgi_render_shadow_map");
+      rc = sgi_synchronize(ctx);
+      if (rc && rc != SGI_ERR_OVERFLOW) return fail(rc, "sgi_synchronize");
+      if (pass) {
+        double t = 0; int64_t calls = 0;
+        sgi_pass_time_ms(ctx, SGI_PASS_SHADOW_MAP, &t, &calls);
+        ms[s] = (float)t;
+        sgi_enable_timing(ctx, 0);
+      }
+    }
   return 0;
 }
 

@@ -101,6 +101,8 @@ class ShadowApp {
   bool svZfail = false;           // depth-fail counting over capped volumes (robust when the eye is inside a volume); false = the reference's depth-pass stencil ops
   int rect[4] = {0, 0, 0, 0};     // multi-GPU screen tile (empty = whole window)
   int lightShardRank = 0, lightShardWorld = 1;   // multi-GPU many-light: this process owns lights l = rank (mod world)
+  std::vector<int> lightOwner;    // many-light shards: rank that owns light s (empty: s mod world); set from measured per-light costs
+  int measureLightCosts(float* ms, int n);   // depth-pass time of each of the n lights of renderMonteCarlo, one at a time (CUDA events)
   bool fusedMonteCarlo = false;   // renderMonteCarlo: camera pass reduced to primitive ids (sgi_render_prim_ids), positions resolved inside
                                   // the accumulation kernel (sgi_params.multi_fused); identical visibility, no vertex map materialised
   bool commSkip = false;          // measurement aid: run the sharded frame without its exchanges (what the collectives cost = the difference)

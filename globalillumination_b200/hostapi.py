@@ -13,7 +13,7 @@ PROGRAM = {"shadow_mapping": 0, "soft_shadow_mapping": 1, "shadow_volumes": 2}
 EXPORTS = [
     "sgh_last_error", "sgh_scene_load", "sgh_scene_free", "sgh_scene_counts", "sgh_scene_copy", "sgh_scene_views",
     "sgh_scene_substitutions", "sgh_frame_matrices", "sgh_app_create", "sgh_app_destroy", "sgh_app_error", "sgh_app_context",
-    "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard", "sgh_app_comm_init",
+    "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard", "sgh_app_comm_init", "sgh_app_light_costs", "sgh_app_set_light_owners",
     "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_filter_shadow_map", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
     "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_save_image", "sgh_write_png", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
@@ -168,6 +168,16 @@ class App:
         sharded by lights with the exchanges done by ShadowApp::renderMonteCarlo."""
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         self._ck(self.L.sgh_app_comm_init(self.h, buf, 128, int(rank), int(world)))
+
+    def light_costs(self, n):
+        """Depth-pass time (ms) of each of the n lights of the many-light frame, measured one at a time."""
+        ms = np.zeros(n, np.float32)
+        self._ck(self.L.sgh_app_light_costs(self.h, _fp(ms), int(n)))
+        return ms
+
+    def set_light_owners(self, owners):
+        o = np.ascontiguousarray(owners, np.int32)
+        self._ck(self.L.sgh_app_set_light_owners(self.h, _ip(o), int(o.size)))
 
     def set_technique(self, name):
         self._ck(self.L.sgh_app_set_technique(self.h, name.encode()))

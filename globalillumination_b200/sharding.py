@@ -33,6 +33,20 @@ def light_shard(num_lights, rank, world):
     return list(range(rank, num_lights, world))
 
 
+def balance_lights(costs, world):
+    """Owner rank of every light, longest-processing-time first: lights sorted by measured cost, each given to the rank with the least
+    load so far (ties: lowest rank).  Deterministic for a given cost vector; every rank must use the same table."""
+    order = sorted(range(len(costs)), key=lambda s: (-float(costs[s]), s))
+    load = [0.0] * world
+    count = [0] * world
+    owner = [0] * len(costs)
+    for s in order:
+        r = min(range(world), key=lambda k: (load[k], count[k], k))
+        owner[s] = r
+        load[r] += float(costs[s]); count[r] += 1
+    return owner
+
+
 def frame_indices(first, count, rank, world):
     """Frames rank `rank` renders in frame-parallel mode."""
     return list(range(first + rank, first + count, world))

@@ -50,6 +50,10 @@ int sgh_app_set_light_shard(sgh_app* a, int32_t rank, int32_t world);   /* many-
 /* multi-GPU inside the library: sgi_comm_init on the app's context (id from sgi_comm_unique_id on rank 0); renderMonteCarlo then
  * shards the lights over the ranks and exchanges primitive-id strips / partial sums over NCCL itself (sgi_gather, sgi_reduce_lights) */
 int sgh_app_comm_init(sgh_app* a, const void* id128, size_t bytes, int32_t rank, int32_t world);
+/* light shards balanced by cost: the depth pass of a light costs what the light sees; ms[n] = each light's pass time (one at a time,
+ * CUDA events), owner[n] = the rank that renders light s (the same table on every rank; default s mod world) */
+int sgh_app_light_costs(sgh_app* a, float* ms, int32_t n);
+int sgh_app_set_light_owners(sgh_app* a, const int32_t* owner, int32_t n);
 int sgh_app_set_technique(sgh_app* a, const char* name);
 int sgh_app_set_int(sgh_app* a, const char* name, int32_t v);
 int sgh_app_set_float(sgh_app* a, const char* name, float v);

@@ -87,3 +87,13 @@ def test_two_rank_tile_gather_and_light_reduce_gloo():
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), "tile gather mismatch"
     assert all(r[2] for r in res), "light reduce mismatch"
+
+
+def test_balance_lights_is_deterministic_and_beats_round_robin():
+    from globalillumination_b200 import sharding
+    costs = [0.57, 0.41, 0.40, 0.52, 0.55, 0.42, 0.39, 0.50, 0.58, 0.43, 0.41, 0.51, 0.56, 0.40, 0.38, 0.49]
+    own = sharding.balance_lights(costs, 8)
+    assert own == sharding.balance_lights(list(costs), 8) and sorted(set(own)) == list(range(8))
+    load = lambda o: max(sum(c for c, r in zip(costs, o) if r == k) for k in range(8))
+    assert load(own) < load([s % 8 for s in range(16)])
+    assert sharding.balance_lights([1.0], 4) == [0]
