@@ -109,6 +109,8 @@ def main():
         uid2 = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid2, src=0)
         app.comm_init(uid2[0], rank, world)
+        if Hl == 563:                                    # a light-to-rank table other than round robin (shards balanced by cost)
+            app.set_light_owners([min(world - 1, s * world // 12) for s in range(16)])      # (unequal shares)
         for _ in range(3):                               # several frames: the exchanges of consecutive frames overlap
             app.display("soft_shadow_mapping")
         ctx = app.context()
