@@ -30,6 +30,8 @@
 // modes whose tile payload is the 64-bit (depth | primitive) key: the attribute passes that need to know the winning triangle
 #define SGI_KEYED(M) ((M) == SGI_MODE_GBUFFER || (M) == SGI_MODE_GBUFFER_RGB || (M) == SGI_MODE_MOMENTS || (M) == SGI_MODE_IDS)
 
+#define SGI_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")     // programmatic dependent launch: see launch_pdl
+
 namespace {
 
 struct CV { float x, y, z, w, b0, b1, b2; };
@@ -122,43 +124,18 @@ __device__ __forceinline__ void invalidate(SgiRec* r) {
   *r = z;
 }
 
-// Set-up of source triangle t: writes its record (slot t) and the records of the extra fan triangles clipping produced
-// (consecutive slots from `base`), valid or invalidated.  Returns the number of fan triangles (0 = rejected; `first` is then
-// invalid) and the record of slot t in registers for the binning that follows.
-__device__ __forceinline__ int setup_triangle(const SetupBinArgs& a, int t, SgiRec& first, int& base) {
-  first.prim_front = -1;
-  base = -1;
-  a.ovf_base[t] = -1;
-  int i0 = a.idx[3 * t], i1 = a.idx[3 * t + 1], i2 = a.idx[3 * t + 2];
-  CV poly[10];
-  poly[0] = xform(a.mvp, a.xyz[3 * (size_t)i0], a.xyz[3 * (size_t)i0 + 1], a.xyz[3 * (size_t)i0 + 2]);
-  poly[1] = xform(a.mvp, a.xyz[3 * (size_t)i1], a.xyz[3 * (size_t)i1 + 1], a.xyz[3 * (size_t)i1 + 2]);
-  poly[2] = xform(a.mvp, a.xyz[3 * (size_t)i2], a.xyz[3 * (size_t)i2 + 1], a.xyz[3 * (size_t)i2 + 2]);
-  poly[0].b0 = 1; poly[0].b1 = 0; poly[0].b2 = 0;
-  poly[1].b0 = 0; poly[1].b1 = 1; poly[1].b2 = 0;
-  poly[2].b0 = 0; poly[2].b1 = 0; poly[2].b2 = 1;
-  {  // trivial reject against the true frustum
-    int o0 = 0, o1 = 0, o2 = 0, o3 = 0, o4 = 0, o5 = 0;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const CV& v = poly[k];
-      if (!(v.w + v.z >= 0.0f)) o0++;
-      if (!(v.w - v.z >= 0.0f)) o1++;
-      if (!(v.w + v.x >= 0.0f)) o2++;
-      if (!(v.w - v.x >= 0.0f)) o3++;
-      if (!(v.w + v.y >= 0.0f)) o4++;
-      if (!(v.w - v.y >= 0.0f)) o5++;
-    }
-    if (a.no_far_clip) o1 = 0;
-    if (o0 == 3 || o1 == 3 || o2 == 3 || o3 == 3 || o4 == 3 || o5 == 3) { invalidate(&a.rec[t]); return 0; }
-  }
-  bool was_clipped;
-  int n = clip_polygon(poly, 3, was_clipped, a.no_far_clip);
-  if (n < 3) { invalidate(&a.rec[t]); return 0; }
+// Records of one (clipped) polygon of source triangle t: window transform, snap, fan triangulation, edge / depth-plane set-up,
+// attribute record.  NP = capacity of the polygon arrays: instantiated with 3 for triangles that need no clipping (the common
+// case: everything stays in registers) and 10 for clipped ones (local memory).  Identical arithmetic either way.
+template <int NP>
+__device__ __forceinline__ int emit_records(const SetupBinArgs& a, int t, int i0, int i1, int i2, const CV* poly, int n, bool was_clipped,
+                                            SgiRec& first, int& base) {
   float hw = (float)a.W * 0.5f, hh = (float)a.H * 0.5f;
-  int32_t X[10], Y[10];
-  float Z[10], IW[10];
-  for (int k = 0; k < n; k++) {
+  int32_t X[NP], Y[NP];
+  float Z[NP], IW[NP];
+#pragma unroll
+  for (int k = 0; k < NP; k++) {
+    if (k >= n) break;
     float nx = poly[k].x / poly[k].w, ny = poly[k].y / poly[k].w, nz = poly[k].z / poly[k].w;
     float xw = nx * hw + hw, yw = ny * hh + hh;
     Z[k] = nz * 0.5f + 0.5f;
@@ -172,7 +149,9 @@ __device__ __forceinline__ int setup_triangle(const SetupBinArgs& a, int t, SgiR
     base = a.T + atomicAdd(&a.counters[0], n - 3);
     a.ovf_base[t] = base;
   }
-  for (int f = 1; f + 1 < n; f++) {
+#pragma unroll
+  for (int f = 1; f + 1 < NP; f++) {
+    if (f + 1 >= n) break;
     int slot = (f == 1) ? t : base + (f - 2);
     int id0 = 0, id1 = f, id2 = f + 1;
     long long area2 = (long long)(X[id1] - X[id0]) * (long long)(Y[id2] - Y[id0]) -
@@ -242,6 +221,59 @@ __device__ __forceinline__ int setup_triangle(const SetupBinArgs& a, int t, SgiR
   }
   return n - 2;
 }
+
+// the clipping route of setup_triangle, kept out of line: its polygon arrays live in local memory
+__device__ __noinline__ int setup_triangle_clipped(const SetupBinArgs& a, int t, int i0, int i1, int i2, CV v0, CV v1, CV v2, SgiRec& first, int& base) {
+  CV poly[10];
+  poly[0] = v0; poly[1] = v1; poly[2] = v2;
+  bool was_clipped;
+  int n = clip_polygon(poly, 3, was_clipped, a.no_far_clip);
+  if (n < 3) { invalidate(&a.rec[t]); return 0; }
+  return emit_records<10>(a, t, i0, i1, i2, poly, n, was_clipped, first, base);
+}
+
+// Set-up of source triangle t: writes its record (slot t) and the records of the extra fan triangles clipping produced
+// (consecutive slots from `base`), valid or invalidated.  Returns the number of fan triangles (0 = rejected; `first` is then
+// invalid) and the record of slot t in registers for the binning that follows.
+__device__ __forceinline__ int setup_triangle(const SetupBinArgs& a, int t, SgiRec& first, int& base) {
+  first.prim_front = -1;
+  base = -1;
+  a.ovf_base[t] = -1;
+  int i0 = a.idx[3 * t], i1 = a.idx[3 * t + 1], i2 = a.idx[3 * t + 2];
+  CV poly[3];
+  poly[0] = xform(a.mvp, a.xyz[3 * (size_t)i0], a.xyz[3 * (size_t)i0 + 1], a.xyz[3 * (size_t)i0 + 2]);
+  poly[1] = xform(a.mvp, a.xyz[3 * (size_t)i1], a.xyz[3 * (size_t)i1 + 1], a.xyz[3 * (size_t)i1 + 2]);
+  poly[2] = xform(a.mvp, a.xyz[3 * (size_t)i2], a.xyz[3 * (size_t)i2 + 1], a.xyz[3 * (size_t)i2 + 2]);
+  poly[0].b0 = 1; poly[0].b1 = 0; poly[0].b2 = 0;
+  poly[1].b0 = 0; poly[1].b1 = 1; poly[1].b2 = 0;
+  poly[2].b0 = 0; poly[2].b1 = 0; poly[2].b2 = 1;
+  {  // trivial reject against the true frustum
+    int o0 = 0, o1 = 0, o2 = 0, o3 = 0, o4 = 0, o5 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const CV& v = poly[k];
+      if (!(v.w + v.z >= 0.0f)) o0++;
+      if (!(v.w - v.z >= 0.0f)) o1++;
+      if (!(v.w + v.x >= 0.0f)) o2++;
+      if (!(v.w - v.x >= 0.0f)) o3++;
+      if (!(v.w + v.y >= 0.0f)) o4++;
+      if (!(v.w - v.y >= 0.0f)) o5++;
+    }
+    if (a.no_far_clip) o1 = 0;
+    if (o0 == 3 || o1 == 3 || o2 == 3 || o3 == 3 || o4 == 3 || o5 == 3) { invalidate(&a.rec[t]); return 0; }
+  }
+  // all three vertices inside the near / far planes and the guard band: nothing to clip (clip_polygon would return the triangle as it is)
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const CV& v = poly[k];
+    inside = inside && (v.w + v.z >= 0.0f) && (a.no_far_clip || (v.w - v.z >= 0.0f)) && (SGI_GUARD * v.w + v.x >= 0.0f) && (SGI_GUARD * v.w - v.x >= 0.0f) &&
+             (SGI_GUARD * v.w + v.y >= 0.0f) && (SGI_GUARD * v.w - v.y >= 0.0f);
+  }
+  if (inside) return emit_records<3>(a, t, i0, i1, i2, poly, 3, false, first, base);
+  return setup_triangle_clipped(a, t, i0, i1, i2, poly[0], poly[1], poly[2], first, base);
+}
+
 
 // ---- binning -------------------------------------------------------------------------------------------------
 // conservative triangle / tile overlap: for each edge evaluate at the tile corner that maximises it
@@ -509,6 +541,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nl = a.gx * a.gy;
   const bool in_regs = nl <= 1024 * SGI_ORDER_REG;
+  for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
+  SGI_GRID_DEP_WAIT();                                 // the binner's cursors and counters from here on
   if (a.mm_min) for (int i = tid; i < a.mm_n; i += 1024) { a.mm_min[i] = 0x3F800000u; a.mm_max[i] = 0u; }
   int c0 = 0, c3 = 0, c5 = 0, st_long = 0, st_tot = 0;
   if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; }
@@ -544,7 +578,6 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); sum += min(c, a.cap); mx = max(mx, c); }
   sum = __reduce_add_sync(0xffffffffu, sum); mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) { red_sum[warp] = sum; red_max[warp] = mx; }
-  for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
   __syncthreads();
   if (warp == 0) {
     int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
@@ -814,6 +847,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   __shared__ int bucket_cnt[SGI_ZBUCKETS], bucket_pos[SGI_ZBUCKETS];
 
   const int tid = threadIdx.x, lane = tid & 31;
+  SGI_GRID_DEP_WAIT();                                           // k_order's work items (programmatic dependent launch)
   if ((int)blockIdx.x >= a.counters[4]) return;                  // the grid is an upper bound of the item count
   const int2 item2 = a.tile_order[blockIdx.x];                   // work items of k_order, busiest first: (item, list length | spill flag)
   const int item = item2.x;
@@ -1423,6 +1457,19 @@ static int list_capacity(int longest, int n_tiles) {
   return (int)cap;
 }
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream is still draining; it waits
+// (griddepcontrol.wait, first instruction that touches the predecessor's output) until that grid has completed and flushed.
+// What overlaps is the launch latency and CTA start-up of k_order / k_tile, 2-3 us each on the latency chain of every pass.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 // Per-device function attributes (the opt-in to > 48 KB of dynamic shared memory applies to the CURRENT device only): kept per
 // context, so a second context on another GPU of the same process configures its own device.
 template <int MODE, int NT>
@@ -1438,7 +1485,7 @@ static int launch_tile_nt(sgi_ctx* ctx, const TileArgs& ta, dim3 grid, cudaStrea
   }
   const int pass = (MODE == SGI_MODE_DEPTH || MODE == SGI_MODE_MOMENTS) ? SGI_PASS_TILE_DEPTH : (SGI_KEYED(MODE) ? SGI_PASS_TILE_GBUFFER : SGI_PASS_TILE_SV);
   int tslot = sgi_timing_begin(ctx, pass, stream);
-  k_tile<MODE, NT><<<grid, NT, smem, stream>>>(ta);
+  SGI_CUDA(ctx, launch_pdl(k_tile<MODE, NT>, grid, dim3(NT), smem, stream, ctx->pdl, ta));
   sgi_timing_end(ctx, pass, tslot, stream);
   ctx->launches++;
   SGI_CUDA(ctx, cudaGetLastError());
@@ -1532,7 +1579,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
   k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
-  k_order<<<1, 1024, 0, st>>>(oa);
+  SGI_CUDA(ctx, launch_pdl(k_order, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
   ctx->launches += 2;
   SGI_CUDA(ctx, cudaGetLastError());
   sc.needs_clear = false;
@@ -1550,7 +1597,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
       sa.spill = sc.d_spill; sa.spill_cap = sc.spill_cap; oa.spill_cap = sc.spill_cap;
       sc.needs_clear = true;
       k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
-      k_order<<<1, 1024, 0, st>>>(oa);
+      SGI_CUDA(ctx, launch_pdl(k_order, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
       ctx->launches += 2;
       SGI_CUDA(ctx, cudaGetLastError());
       sc.needs_clear = false;

@@ -275,6 +275,8 @@ int sgi_unregister_host(void* host_ptr);
  *                     scenes it decides few windows (a surface sloped against the light blocks itself within the window's reach)
  *                     and costs more than it saves (profiles/r2_experiments.txt)
  *   "sv_count_fragments" 0 (default); 1 = shadow-volume passes tally their fragments (sgi_sv_fragments; costs a little)
+ *   "pdl"             1 (default) k_order and the tile kernel are launched as programmatic dependents (their launch latency overlaps the
+ *                     predecessor's tail; griddepcontrol.wait in the kernels), 0 = plain stream order
  *   "tile_bulk_flush" 1 (default) depth tiles leave shared memory by cp.async.bulk row copies, 0 = by 16-byte stores
  *   "sv_tile_cull"    1 (default) shadow volumes: (prism, tile) pairs behind the tile's farthest scene depth are not listed
  *   "borrow_pinned"   0 (default) inputs are copied inside the call, 1 = page-locked inputs are read later by DMA */
