@@ -426,6 +426,7 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "lights"], help="N>1: frame-parallel, or light shards of one frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the `sharded` record (config c5 light shards, every N)")
+    ap.add_argument("--sharded-only", action="store_true", help="only the `sharded` record (its own JSON line): profiling / scaling runs")
     ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` records (short runs of the other configurations, N=1 only)")
     args = ap.parse_args()
 
@@ -458,6 +459,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from globalillumination_b200 import capi, hostapi
+    if args.sharded_only:
+        rec = run_sharded(rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps({"sharded": rec}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     app = hostapi.App(local_rank)
     if w.get("golden"):
         app.set_scene(scenes.golden_scene(w["golden"]))

@@ -58,6 +58,9 @@ int ShadowApp::loadScene(const char* config, const char* base_dir) {
 
 int ShadowApp::setScene(const float* xyz, const float* nrm, int nv, const int* idx, int nt, const float camEye[3], const float camAt_[3],
                         const float lightEyeCfg[3], const float lightAt_[3], float depthThreshold) {
+  if (nv < 0 || nt < 0 || (nv > 0 && !xyz) || (nt > 0 && !idx)) { err = "setScene: bad arguments"; return SGI_ERR_INVALID; }
+  for (long long k = 0; k < 3LL * nt; k++)                 // Mesh::computeNormals indexes the vertex arrays with these
+    if (idx[k] < 0 || idx[k] >= nv) { err = "setScene: vertex index out of range"; return SGI_ERR_INVALID; }
   unpinSceneArrays(); uploadColors.clear(); uploadColorsSrc = nullptr;
   scene = Mesh();
   scene.setGeometry(xyz, nv, idx, nt);

@@ -110,3 +110,21 @@ def test_png_writer_round_trip(tmp_path):
         hostapi.write_png(path, img)
         back = np.asarray(Image.open(path).convert("RGBA"))
         assert back.shape == img.shape and np.array_equal(back, img)
+
+
+@pytest.mark.gpu
+def test_set_scene_rejects_out_of_range_indices():
+    """ADVICE r1: ShadowApp::setScene validates the indices before Mesh::computeNormals walks the vertex arrays with them."""
+    from globalillumination_b200 import hostapi
+    app = hostapi.App(0)
+    try:
+        sc = dict(util.scene("door"))
+        bad = sc["idx"].copy(); bad[3, 1] = sc["xyz"].shape[0] + 7
+        sc["idx"] = bad
+        with pytest.raises(hostapi.HostError):
+            app.set_scene(sc)
+        sc["idx"][3, 1] = -1
+        with pytest.raises(hostapi.HostError):
+            app.set_scene(sc)
+    finally:
+        app.close()
