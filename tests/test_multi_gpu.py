@@ -132,3 +132,30 @@ def test_two_ranks_over_nccl_match_the_unsharded_frame():
            "--master-port", "29677", os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_config_c5_sandiego_full_size_against_the_oracle(ctx):
+    """c5 at full size (SanDiego geometry, 7680x4320, 16 lights x 8192^2) against the oracle itself, not only
+    through size-independent properties: every depth map, the vertex map and the 16-light visibility of the whole frame, bit for
+    bit, through the G-buffer path and through the fused primitive-id path (the one bench.py's `sharded` record runs)."""
+    sc = util.scene("sandiego")
+    W, H, S, n_l = 7680, 4320, 8192, 16
+    po, pg, fm, mvp, mvpb = _many_light_frame(ctx, sc, W, H, S, n_l)
+    ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
+    vis_a = ctx.read("visibility")
+    maps = ctx.read("shadow_map")
+    for i in range(n_l):
+        m_o = O.raster_depth(sc["xyz"], sc["idx"], mvp[i], S, S)
+        assert util.bits_equal(maps[i], m_o), f"light {i}: " + util.describe_diff(maps[i], m_o)
+    pos_o, nrm_o, dep_o = O.raster_gbuffer(sc["xyz"], sc["nrm"], sc["idx"], fm["cam_mvp"], W, H)
+    assert util.bits_equal(ctx.read("gbuf_pos"), pos_o)
+    vis_o = O.visibility_multi(po, mvpb[-1], mvpb[:, 12:16], pos_o, maps)
+    assert util.bits_equal(vis_a, vis_o), util.describe_diff(vis_a, vis_o)
+    del maps
+    _, pg_f = util.params_pair("multi_hard", S, multi_fused=1)
+    ctx.set_params(pg_f)
+    ctx.render_prim_ids(); ctx.compute_visibility()
+    vis_b = ctx.read("visibility")
+    assert util.bits_equal(vis_b, vis_o), util.describe_diff(vis_b, vis_o)
+    fg = pos_o[..., 0] != 0
+    assert fg.mean() > 0.3 and len(np.unique(vis_o[fg])) > 4
