@@ -716,6 +716,8 @@ __device__ __forceinline__ float frag_z(float z0, float dz1, float dz2, float ia
   return z;
 }
 
+__constant__ int c_rcp16[9] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192};     // ceil(2^16 / n)
+
 // a * b + c with a 32 x 32 -> 64-bit product (IMAD.WIDE with the 64-bit addend).  Inline PTX so that the compiler keeps the
 // incremental form: written in C it folds the block step back into the edge function and multiplies 64-bit operands again.
 __device__ __forceinline__ long long madw(int a, int b, long long c) {
@@ -1066,11 +1068,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     }
     // the per-block depth bounds only pay off when there is something to cull: refresh them only in busy chunks
     const bool refresh_bounds = ngroups >= 8;
-    for (;;) {
-      int item = 0;
-      if (lane == 0) item = atomicAdd(&next_item, 1);
-      item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= ngroups) break;
+    // work items are dealt to the warps round robin (they are in nearest-first order: every warp starts near the front); a shared
+    // cursor balanced them slightly better but cost an atomic and a shuffle per item, 6 % of the depth kernel's instructions
+    for (int item = tid >> 5; item < ngroups; item += NT / 32) {
       const int grp = tq.group[item];
       const int qi = grp >> 3, b0 = (grp & 7) << 5;
       const int X0 = tq.X0[qi], Y0 = tq.Y0[qi], X1 = tq.X1[qi], Y1 = tq.Y1[qi], X2 = tq.X2[qi], Y2 = tq.Y2[qi];
@@ -1080,7 +1080,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
       const int nbx = bx1 - bx0 + 1, nb = nbx * (by1 - by0 + 1);
       const int sub_x = lane & (SGI_BLK_W - 1), sub_y = lane >> 3;
       const int b = b0 + lane;
-      const int bx = bx0 + b % nbx, by = by0 + b / nbx;
+      // b / nbx and b % nbx for b < 256, nbx <= 8 without a division: (b * ceil(2^16 / nbx)) >> 16 is exact in that range
+      const int bq = (b * c_rcp16[nbx]) >> 16;
+      const int bx = bx0 + (b - bq * nbx), by = by0 + bq;
       const unsigned int zlo = tq.zlo[qi];
       bool keep = b < nb;
       const unsigned int bound = keep ? bz[by * (SGI_TILE / SGI_BLK_W) + bx] : 0u;
@@ -1138,8 +1140,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
         const long long e0 = madw(es.dy0, cx, madw(es.dx0, cy, l0));
         const long long e1 = madw(es.dy1, cx, madw(es.dx1, cy, l1));
         const long long e2 = madw(es.dy2, cx, madw(es.dx2, cy, l2));
-        if ((e0 | e1 | e2) >= 0) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, e1 + es.b1, e2 + es.b2), meta);
-        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds) {
+        const bool covered = (e0 | e1 | e2) >= 0;
+        if (covered) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, e1 + es.b1, e2 + es.b2), meta);
+        // (a block the triangle covers only in part keeps texels at their old depth: its bound would not move)
+        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds && __all_sync(0xffffffffu, covered)) {
           // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
           const int p = ly * SGI_PITCH + lx;
           const unsigned int cur = (MODE == SGI_MODE_DEPTH) ? zt[p] : (unsigned int)(kt[p] >> 32);
@@ -1149,7 +1153,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
         }
       }
     }
-    __syncthreads();                                           // every warp is done with this chunk's queue
+    if (base + NT < nitems) __syncthreads();                   // every warp is done with this chunk's queue (the last chunk runs into the flush barrier)
   }
   if (MODE == SGI_MODE_DEPTH) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was written through the generic proxy
   __syncthreads();
