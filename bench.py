@@ -615,6 +615,12 @@ def main():
             if n:
                 passes[name] = ms / n * (n / min(args.steps, 100))       # ms per frame
         ctx.enable_timing(False)
+        sv_frags = None
+        if program == "shadow_volumes":
+            ctx.set_option("sv_count_fragments", 1)
+            frame(); ctx.synchronize()
+            sv_frags = int(ctx.sv_fragments())
+            ctx.set_option("sv_count_fragments", 0)
 
         # ---- secondary figure, PCSS only: the same loop with the exact early-out of the blocker search switched on
         #      (sgi_set_option "pcss_early_out": bit-identical results, off by default so that `value` counts every tap) ----
@@ -718,6 +724,12 @@ def main():
         roof = {"bound": "hbm", "kernel": kernel_of[top][0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": kernel_of[top][1], "launch_ms": per_launch_ms, "peak_source": peak_src,
                 "share_of_step": cand[top] / (total_ms / args.steps)}
+    if roof and program == "shadow_volumes":
+        # the unit of work of the stencil pass is the prism fragment, not the byte: the HBM fraction of this kernel says
+        # nothing (it moves 8 B/pixel); fragments are tallied by the kernel itself in one extra frame (option sv_count_fragments)
+        roof["note"] = "fill-bound pass: see prism_fragments_per_s; the HBM fraction is not a measure of this kernel"
+        roof["prism_fragments_per_frame"] = sv_frags
+        roof["prism_fragments_per_s"] = sv_frags / (per_launch_ms * 1e-3) if sv_frags else None
     # the shadow pass against both of its rooflines - HBM (G-buffer in, visibility out, every map texel once)
     # and L2 (4 bytes per shadow-map tap; measured L2 read peak: profiles/r1_l2_bandwidth.txt)
     shadow_pass = None
