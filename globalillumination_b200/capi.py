@@ -43,7 +43,7 @@ EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility", "sgi_filter_shadow_map", "sgi_moment_quantization",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
-    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
+    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_set_mesh_uv", "sgi_set_texture", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -66,6 +66,7 @@ def load():
         _lib.sgi_device_ptr.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _lib.sgi_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _lib.sgi_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.sgi_set_texture.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
         _lib.sgi_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
     return _lib
 
@@ -157,6 +158,17 @@ class Context:
             self._ck(self.lib.sgi_set_mesh_colors(self.h, None))
         else:
             self._ck(self.lib.sgi_set_mesh_colors(self.h, _fp(_f32(rgb))))
+
+    def set_mesh_uv(self, uv):
+        self._ck(self.lib.sgi_set_mesh_uv(self.h, None if uv is None else _fp(_f32(uv))))
+
+    def set_texture(self, index, rgb):
+        """rgb: uint8 [h, w, 3] (row 0 = t 0) or None to unbind texture<index>."""
+        if rgb is None:
+            self._ck(self.lib.sgi_set_texture(self.h, int(index), None, 0, 0))
+        else:
+            a = np.ascontiguousarray(rgb, np.uint8)
+            self._ck(self.lib.sgi_set_texture(self.h, int(index), a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))
 
     def shade_phong(self, clear=(0.63, 0.82, 0.96, 1.0)):
         self._ck(self.lib.sgi_shade_phong(self.h, _fp(_f32(clear))))

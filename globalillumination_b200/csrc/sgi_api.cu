@@ -8,6 +8,7 @@
 #include <new>
 #include <cstdint>
 #include <utility>
+#include <vector>
 #include "sgi_internal.cuh"
 #include "sgi_moments.cuh"
 
@@ -225,6 +226,8 @@ int sgi_destroy(sgi_ctx* ctx) {
   for (void* p : {(void*)ctx->d_sv_grp_start, (void*)ctx->d_sv_grp_ent, (void*)ctx->d_sv_cls, (void*)ctx->d_sv_frags}) if (p) cudaFree(p);
   if (ctx->rbssm_buf) cudaFree(ctx->rbssm_buf);
   if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+  if (ctx->d_uv) cudaFree(ctx->d_uv);
+  for (int k = 0; k < 3; k++) if (ctx->d_tex[k]) cudaFree(ctx->d_tex[k]);
   void* ptrs[] = {ctx->d_xyz_set[0], ctx->d_nrm_set[0], ctx->d_idx_set[0], ctx->d_xyz_set[1], ctx->d_nrm_set[1], ctx->d_idx_set[1], ctx->d_light_trans};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (SgiScratch& sc : ctx->scratch) sgi_raster_free(sc);
@@ -399,6 +402,55 @@ int sgi_set_mesh_colors(sgi_ctx* ctx, const float* rgb) {
   mark_gbuffer_use(ctx);
   ctx->has_rgb = true; ctx->gbuffer_valid = false;
   return SGI_OK;
+}
+
+// Mesh::getTextureCoords(): (u, v, texture id) per vertex, the `uv` attribute of GBuffer.vert:15,20 (loadVBOs, VBOs[2])
+int sgi_set_mesh_uv(sgi_ctx* ctx, const float* uv) {
+  if (!ctx) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx);
+  if (!uv) { ctx->has_uv = false; ctx->gbuffer_valid = false; return SGI_OK; }
+  if (ctx->V <= 0) { ctx->err = "sgi_set_mesh_uv: set the mesh first"; return SGI_ERR_INVALID; }
+  if (ctx->uv_V != ctx->V) {
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SGI_CUDA(ctx, cudaStreamSynchronize(ctx->upload_stream));
+    if (ctx->d_uv) cudaFree(ctx->d_uv);
+    ctx->d_uv = nullptr;
+    SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_uv, (size_t)ctx->V * 12));
+    ctx->uv_V = ctx->V;
+  }
+  // (texture coordinates change with the mesh, not per frame: a plain ordered copy on the context's stream, after the passes queued so far)
+  sgi_join_vis(ctx);
+  SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_uv, uv, (size_t)ctx->V * 12, cudaMemcpyHostToDevice, ctx->stream));
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));        // the caller's array is borrowed for the call only
+  mark_gbuffer_use(ctx);
+  ctx->has_uv = true; ctx->gbuffer_valid = false;
+  return SGI_OK;
+}
+
+// MyGLTextureViewer::loadRGBTexture (MyGLTextureViewer.cpp:45-56; Mesh::loadTexture, `m` directive): texture<index> of GBuffer.frag,
+// RGB8, row 0 = t 0, GL_LINEAR / GL_REPEAT.  rgb == NULL unbinds.
+int sgi_set_texture(sgi_ctx* ctx, int32_t index, const uint8_t* rgb, int32_t width, int32_t height) {
+  if (!ctx || index < 0 || index > 2 || (rgb && (width <= 0 || height <= 0 || width > 16384 || height > 16384))) { if (ctx) ctx->err = "sgi_set_texture: bad arguments"; return SGI_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  sgi_join_gbuffer(ctx); sgi_join_vis(ctx);
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_tex[index]) cudaFree(ctx->d_tex[index]);
+  ctx->d_tex[index] = nullptr; ctx->tex_w[index] = ctx->tex_h[index] = 0;
+  ctx->gbuffer_valid = false;
+  if (!rgb) return SGI_OK;
+  const size_t n = (size_t)width * height;
+  std::vector<uchar4> tmp(n);
+  for (size_t i = 0; i < n; i++) tmp[i] = make_uchar4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 255);
+  SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_tex[index], n * 4));
+  SGI_CUDA(ctx, cudaMemcpy(ctx->d_tex[index], tmp.data(), n * 4, cudaMemcpyHostToDevice));
+  ctx->tex_w[index] = width; ctx->tex_h[index] = height;
+  return SGI_OK;
+}
+
+// useTextureForColoring: texture coordinates of the current mesh and at least one bound texture
+static bool textures_active(const sgi_ctx* ctx) {
+  return ctx->has_uv && ctx->uv_V == ctx->V && (ctx->d_tex[0] || ctx->d_tex[1] || ctx->d_tex[2]);
 }
 
 int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const float nm[9], int32_t W, int32_t H) {
@@ -620,8 +672,12 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   job.W = ctx->W; job.H = ctx->H;
   job.depth = (float*)ctx->buf[SGI_BUF_CAM_DEPTH];
   job.pos4 = (float4*)ctx->buf[SGI_BUF_GBUF_POS]; job.nrm4 = (float4*)ctx->buf[SGI_BUF_GBUF_NRM];
-  const bool rgb_ok = ctx->has_rgb && ctx->rgb_V == ctx->V;
-  job.rgb = rgb_ok ? ctx->d_rgb : nullptr; job.albedo4 = rgb_ok ? (float4*)ctx->buf[SGI_BUF_GBUF_ALBEDO] : nullptr;
+  const bool rgb_ok = ctx->has_rgb && ctx->rgb_V == ctx->V, tex_ok = textures_active(ctx);
+  job.rgb = rgb_ok ? ctx->d_rgb : nullptr; job.albedo4 = (rgb_ok || tex_ok) ? (float4*)ctx->buf[SGI_BUF_GBUF_ALBEDO] : nullptr;
+  if (tex_ok) {
+    job.uv = ctx->d_uv;
+    for (int k = 0; k < 3; k++) { job.tex[k].texels = ctx->d_tex[k]; job.tex[k].w = ctx->tex_w[k]; job.tex[k].h = ctx->tex_h[k]; }
+  }
   job.rx0 = ctx->params.rect_x0; job.ry0 = ctx->params.rect_y0; job.rx1 = ctx->params.rect_x1; job.ry1 = ctx->params.rect_y1;
   int rc = sgi_raster_run(ctx, job, 1, st);
   if (rc) return rc;

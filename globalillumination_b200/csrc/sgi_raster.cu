@@ -106,6 +106,7 @@ struct SetupBinArgs {
   int use_offset; float factor, units;
   int no_far_clip;                               // depth clamp (shadow volumes, depth-fail mode): the far plane does not clip, depths saturate at 1
   SgiRec* rec; SgiRecAttr* attr; int32_t* ovf_base; int32_t* counters;
+  const float* uv; SgiRecUV* uvrec;              // texture coordinates (optional)
   // binning
   int tiles_x, tx0, ty0, tx1, ty1;               // tile grid pitch and the inclusive tile range of the job rectangle
   int32_t* tile_cnt; int32_t* pairs; int cap;    // per-tile append cursor; list of tile t = pairs[t * cap .. t * cap + cap)
@@ -217,6 +218,25 @@ __device__ __forceinline__ int emit_records(const SetupBinArgs& a, int t, int i0
         }
       }
       a.attr[slot] = q;
+      if (a.uvrec) {
+        SgiRecUV w;
+        w.pad[0] = w.pad[1] = w.pad[2] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const float b0 = poly[ids[k]].b0, b1 = poly[ids[k]].b1, b2 = poly[ids[k]].b2;
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            float v;
+            if (!was_clipped) v = a.uv[3 * (size_t)src[ids[k]] + cc];
+            else {
+              const float s0 = a.uv[3 * (size_t)i0 + cc], s1 = a.uv[3 * (size_t)i1 + cc], s2 = a.uv[3 * (size_t)i2 + cc];
+              v = (b0 * s0 + b1 * s1) + b2 * s2;
+            }
+            w.U[k][cc] = v;
+          }
+        }
+        a.uvrec[slot] = w;
+      }
     }
   }
   return n - 2;
@@ -684,6 +704,7 @@ struct TileArgs {
   unsigned int* ids;                                                   // IDS
   int sv_zfail, sv_caps; unsigned long long* frag_counter;             // SVCOUNT: depth-fail mode, capped volumes, optional fragment tally
   unsigned int* mm_min; unsigned int* mm_max; int mm_w;                // DEPTH: per 32x32-texel block extrema of the map (float bits), or null
+  const SgiRecUV* uvrec; SgiTex tex[3];                                 // GBUFFER_RGB: texture select (useTextureForColoring), or null
 };
 
 #define ONE_BITS 0x3F800000u
@@ -794,6 +815,45 @@ struct TriQueue {
 #define SGI_SPLIT_EXTRA 1536      // most CTAs a pass may add by subdividing hot tiles
 #define SGI_MAX_FULL 8
 #define SGI_SMALL_TRI 8           // bbox candidates up to which one thread rasterises the triangle alone
+
+// texture2D on a scene texture: GL_LINEAR, GL_REPEAT, no mipmaps.  The filter's arithmetic is the oracle's definition
+// (oracle_raster.c tex_fetch_linear_repeat): weights fract(u*size - 0.5), texels (byte / 255, alpha 1) accumulated 00, 10, 01, 11.
+__device__ __forceinline__ float tex_wrap(float f, float size) {
+  f = f - floorf(f / size) * size;
+  if (!(f < size)) f = 0.0f;
+  return f;
+}
+__device__ __forceinline__ float4 tex_fetch_linear_repeat(const SgiTex& t, float u, float v) {
+  const float fw = (float)t.w, fh = (float)t.h;
+  const float x = u * fw - 0.5f, y = v * fh - 0.5f;
+  const float x0 = floorf(x), y0 = floorf(y), ax = x - x0, ay = y - y0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float wgt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+    const float fi = tex_wrap(x0 + (float)(k & 1), fw), fj = tex_wrap(y0 + (float)(k >> 1), fh);
+    float4 tx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fi >= 0.0f && fi < fw && fj >= 0.0f && fj < fh) {
+      const uchar4 p = __ldg(&t.texels[(size_t)(int)fj * t.w + (size_t)(int)fi]);
+      tx = make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, 1.0f);
+    }
+    acc.x = acc.x + tx.x * wgt; acc.y = acc.y + tx.y * wgt; acc.z = acc.z + tx.z * wgt; acc.w = acc.w + tx.w * wgt;
+  }
+  return acc;
+}
+// GBuffer.frag:11-30 computeFragmentColor with useTextureForColoring == 1
+__device__ __forceinline__ float4 fragment_color(const SgiTex (&tex)[3], float u, float v, float b, float r, float g, float bl) {
+  int sel = -1;
+  if (b > 0.99f && b < 1.001f) sel = 0;
+  else if (b > 1.999f && b < 2.001f) sel = 1;
+  else if (b > 2.999f && b < 3.001f) sel = 2;
+  if (sel >= 0) {
+    const SgiTex& t = tex[sel];
+    if (t.texels && t.w > 0 && t.h > 0) return tex_fetch_linear_repeat(t, u, v);
+    return make_float4(0.f, 0.f, 0.f, 0.f);              // an unbound sampler reads (0,0,0,0)
+  }
+  return make_float4(r, g, bl, 1.0f);
+}
 
 template <int MODE>
 struct TileSink {                  // where fragments go: the tile payload in shared memory
@@ -1308,6 +1368,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
         float col[3];
 #pragma unroll
         for (int cc = 0; cc < 3; cc++) col[cc] = ((q0 * at.C[0][cc] + q1 * at.C[1][cc]) + q2 * at.C[2][cc]) * iq;
+        if (a.uvrec) {                                   // useTextureForColoring: select on the interpolated (u, v, texture id)
+          SgiRecUV ur;
+          const uint4* uq = reinterpret_cast<const uint4*>(&a.uvrec[slot]);
+          uint4* ud = reinterpret_cast<uint4*>(&ur);
+          ud[0] = __ldg(uq); ud[1] = __ldg(uq + 1); ud[2] = __ldg(uq + 2);
+          float uvw[3];
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) uvw[cc] = ((q0 * ur.U[0][cc] + q1 * ur.U[1][cc]) + q2 * ur.U[2][cc]) * iq;
+          a.albedo4[o] = fragment_color(a.tex, uvw[0], uvw[1], uvw[2], col[0], col[1], col[2]);
+        } else
         a.albedo4[o] = make_float4(col[0], col[1], col[2], 1.0f);
       }
     }
@@ -1409,6 +1479,7 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
     size_t n = (size_t)max_tris * 7 + 16;
     if ((rc = grow(ctx, (void**)&sc.d_rec, n * sizeof(SgiRec)))) return rc;
     if ((rc = grow(ctx, (void**)&sc.d_attr, n * sizeof(SgiRecAttr)))) return rc;
+    if ((rc = grow(ctx, (void**)&sc.d_uvrec, n * sizeof(SgiRecUV)))) return rc;
     if ((rc = grow(ctx, (void**)&sc.d_ovf_base, (size_t)max_tris * 4 + 16))) return rc;
     if ((rc = grow(ctx, (void**)&sc.d_big, n * 4))) return rc;
     sc.rec_cap_tris = max_tris;
@@ -1560,6 +1631,8 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   SetupBinArgs sa;
   sa.xyz = job.xyz; sa.nrm = job.nrm; sa.rgb = (job.rgb && job.albedo4) ? job.rgb : nullptr; sa.idx = job.idx; sa.T = job.T;
+  const bool with_tex = job.mode == SGI_MODE_GBUFFER && job.uv && job.albedo4;
+  sa.uv = with_tex ? job.uv : nullptr; sa.uvrec = with_tex ? sc.d_uvrec : nullptr;
   for (int k = 0; k < 16; k++) sa.mvp[k] = job.mvp[k];
   sa.W = job.W; sa.H = job.H; sa.use_offset = job.use_offset; sa.factor = job.factor; sa.units = job.units;
   sa.no_far_clip = job.no_far_clip;
@@ -1622,11 +1695,13 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
   ta.sv_zfail = job.sv_zfail; ta.sv_caps = job.sv_caps; ta.frag_counter = job.frag_counter;
   ta.mm_min = job.mm_min; ta.mm_max = job.mm_max; ta.mm_w = job.mm_w;
+  ta.uvrec = with_tex ? sc.d_uvrec : nullptr;
+  for (int k = 0; k < 3; k++) ta.tex[k] = job.tex[k];
   for (int k = 0; k < 16; k++) ta.mq[k] = job.mq[k];
   for (int k = 0; k < 4; k++) ta.mqt[k] = job.mqt[k];
   dim3 grid(max_items);
   if (job.mode == SGI_MODE_DEPTH) rc = launch_tile<SGI_MODE_DEPTH>(ctx, ta, grid, n_rect_tiles, st);
-  else if (job.mode == SGI_MODE_GBUFFER) rc = (job.rgb && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, n_rect_tiles, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, n_rect_tiles, st);
+  else if (job.mode == SGI_MODE_GBUFFER) rc = ((job.rgb || with_tex) && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, n_rect_tiles, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_MOMENTS) rc = launch_tile<SGI_MODE_MOMENTS>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_IDS) rc = launch_tile<SGI_MODE_IDS>(ctx, ta, grid, n_rect_tiles, st);
   else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
@@ -1665,7 +1740,7 @@ int sgi_minmax_dilate(sgi_ctx* ctx, int set, int R, cudaStream_t st) {
 }
 
 void sgi_raster_free(SgiScratch& sc) {
-  void* ptrs[] = {sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_order, sc.d_pairs, sc.d_tile_zmax, sc.d_spill};
+  void* ptrs[] = {sc.d_uvrec, sc.d_rec, sc.d_attr, sc.d_ovf_base, sc.d_big, sc.d_counters, sc.d_tile_order, sc.d_pairs, sc.d_tile_zmax, sc.d_spill};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (sc.h_flags) cudaFreeHost(sc.h_flags);
   if (sc.d_sticky) cudaFree(sc.d_sticky);

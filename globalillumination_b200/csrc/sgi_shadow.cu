@@ -857,7 +857,8 @@ int sgi_shade_run(sgi_ctx* ctx, const float clear_rgba[4]) {
   for (int k = 0; k < 4; k++) a.clear[k] = clear_rgba[k];
   a.si = ctx->params.shadow_intensity;
   a.pos4 = (const float4*)ctx->buf[SGI_BUF_GBUF_POS]; a.nrm4 = (const float4*)ctx->buf[SGI_BUF_GBUF_NRM];
-  a.albedo4 = ctx->has_rgb ? (const float4*)ctx->buf[SGI_BUF_GBUF_ALBEDO] : nullptr;
+  const bool tex_on = ctx->has_uv && ctx->uv_V == ctx->V && (ctx->d_tex[0] || ctx->d_tex[1] || ctx->d_tex[2]);
+  a.albedo4 = (ctx->has_rgb || tex_on) ? (const float4*)ctx->buf[SGI_BUF_GBUF_ALBEDO] : nullptr;
   a.vis = (const float*)ctx->buf[SGI_BUF_VISIBILITY]; a.out = (float4*)ctx->buf[SGI_BUF_SHADED];
   a.W = ctx->W; a.H = ctx->H;
   dim3 block(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);

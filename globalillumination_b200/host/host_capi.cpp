@@ -191,6 +191,13 @@ int sgh_app_set_float(sgh_app* a, const char* name, float v) {
   return 0;
 }
 int sgh_app_upload_scene(sgh_app* a) { return a ? a->app.uploadScene() : -1; }
+// decoded pixels of the texture an `m` directive names (RGB8, row 0 = t 0): texture<index> of GBuffer.frag; NULL unbinds
+int sgh_app_set_texture(sgh_app* a, int32_t index, const uint8_t* rgb, int32_t width, int32_t height) {
+  if (!a) return -1;
+  int rc = a->app.setTexture(index, rgb, width, height);
+  if (rc) g_err = a->app.error();
+  return rc;
+}
 int sgh_app_render_shadow_map(sgh_app* a) { return a ? a->app.renderShadowMap() : -1; }
 int sgh_app_render_gbuffer(sgh_app* a) { return a ? a->app.renderGBuffer() : -1; }
 int sgh_app_filter_shadow_map(sgh_app* a) { return a ? a->app.filterShadowMap() : -1; }

@@ -52,7 +52,7 @@ int ShadowApp::loadScene(const char* config, const char* base_dir) {
   lightPositionConfig = Vec3{loader.getLightPosition()[0], loader.getLightPosition()[1], loader.getLightPosition()[2]};
   lightAt = Vec3{loader.getLightAt()[0], loader.getLightAt()[1], loader.getLightAt()[2]};
   shadowParams.depthThreshold = loader.getDepthThreshold();
-  uploaded = false; normalMatrixSet = false;
+  uploaded = false; uvUploaded = false; normalMatrixSet = false;
   return 0;
 }
 
@@ -69,7 +69,7 @@ int ShadowApp::setScene(const float* xyz, const float* nrm, int nv, const int* i
   cameraEye = Vec3{camEye[0], camEye[1], camEye[2]}; cameraAt = Vec3{camAt_[0], camAt_[1], camAt_[2]};
   lightPositionConfig = Vec3{lightEyeCfg[0], lightEyeCfg[1], lightEyeCfg[2]}; lightAt = Vec3{lightAt_[0], lightAt_[1], lightAt_[2]};
   shadowParams.depthThreshold = depthThreshold;
-  uploaded = false; normalMatrixSet = false;
+  uploaded = false; uvUploaded = false; normalMatrixSet = false;
   return 0;
 }
 
@@ -90,8 +90,22 @@ int ShadowApp::uploadScene() {
   if (scene.getColorsSize() > 0) {                 // feeds the albedo target and shadeScene()
     if ((rc = sgi_set_mesh_colors(ctx, uploadColors.data()))) return fail(rc, "sgi_set_mesh_colors");
   } else if ((rc = sgi_set_mesh_colors(ctx, nullptr))) return fail(rc, "sgi_set_mesh_colors");
+  // texture coordinates (u, v, texture id) feed the texture select of GBuffer.frag once a texture is bound (setTexture)
+  // (once per scene: they do not change from frame to frame, and the per-frame re-upload of the end-to-end loop stays asynchronous)
+  if (!uvUploaded) {
+    if (scene.getTextureCoordsSize() == scene.getPointCloudSize() && scene.getTextureCoordsSize() > 0) {
+      if ((rc = sgi_set_mesh_uv(ctx, scene.getTextureCoords()))) return fail(rc, "sgi_set_mesh_uv");
+    } else if ((rc = sgi_set_mesh_uv(ctx, nullptr))) return fail(rc, "sgi_set_mesh_uv");
+    uvUploaded = true;
+  }
   uploaded = true;
   return 0;
+}
+
+int ShadowApp::setTexture(int index, const unsigned char* rgb, int width, int height) {
+  if (!ctx) return SGI_ERR_NO_DEVICE;
+  int rc = sgi_set_texture(ctx, index, rgb, width, height);
+  return rc ? fail(rc, "sgi_set_texture") : 0;
 }
 
 // main.cpp:209-219

@@ -65,6 +65,9 @@ class ShadowApp {
                const float lightEyeCfg[3], const float lightAt_[3], float depthThreshold);
   void setWindowSize(int w, int h) { windowWidth = w; windowHeight = h; normalMatrixSet = false; }
   void setShadowMapSize(int w, int h) { shadowParams.shadowMapWidth = w; shadowParams.shadowMapHeight = h; }
+  // scene textures (Mesh::loadTexture -> loadRGBTexture): the host side has no image decoder (the reference's is OpenCV); the caller
+  // hands over decoded RGB8 pixels for texture<index> of GBuffer.frag (index = the `m` directive's running number - 1)
+  int setTexture(int index, const unsigned char* rgb, int width, int height);
   int uploadScene();              // MyGLGeometryViewer::loadVBOs (:383-405); the reference calls it on every draw
 
   // per-frame passes
@@ -118,7 +121,7 @@ class ShadowApp {
   std::string err;
   Mat3 normalMatrix;              // frozen on the first camera-view pass (MyGLGeometryViewer.cpp:114-117)
   bool normalMatrixSet = false;
-  bool uploaded = false;
+  bool uploaded = false, uvUploaded = false;
   std::vector<void*> pinned;        // scene arrays page-locked in place for DMA uploads (released before the arrays change)
   void pinSceneArrays(); void unpinSceneArrays();
   std::vector<float> uploadColors; const float* uploadColorsSrc = nullptr;   // colour array padded to the vertex count (uploadScene)

@@ -14,7 +14,7 @@ EXPORTS = [
     "sgh_last_error", "sgh_scene_load", "sgh_scene_free", "sgh_scene_counts", "sgh_scene_copy", "sgh_scene_views",
     "sgh_scene_substitutions", "sgh_frame_matrices", "sgh_app_create", "sgh_app_destroy", "sgh_app_error", "sgh_app_context",
     "sgh_app_load_scene", "sgh_app_set_scene", "sgh_app_scene_counts", "sgh_app_scene_copy", "sgh_app_configure", "sgh_app_set_rect", "sgh_app_set_light_shard", "sgh_app_comm_init", "sgh_app_light_costs", "sgh_app_set_light_owners",
-    "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_render_shadow_map",
+    "sgh_app_set_technique", "sgh_app_set_int", "sgh_app_set_float", "sgh_app_upload_scene", "sgh_app_set_texture", "sgh_app_render_shadow_map",
     "sgh_app_render_gbuffer", "sgh_app_filter_shadow_map", "sgh_app_compute_hard_shadows", "sgh_app_render_soft_shadows", "sgh_app_render_monte_carlo",
     "sgh_app_render_shadow_volumes", "sgh_app_shade_scene", "sgh_app_save_image", "sgh_write_png", "sgh_app_display", "sgh_app_display_e2e", "sgh_app_display_e2e_async", "sgh_app_e2e_wait", "sgh_app_step_animation", "sgh_procedural", "sgh_free",
 ]
@@ -38,6 +38,7 @@ def load():
         _lib.sgh_app_display_e2e_async.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
         _lib.sgh_app_e2e_wait.argtypes = [C.c_void_p, C.c_int32]
         _lib.sgh_app_save_image.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.sgh_app_set_texture.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
         _lib.sgh_app_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
     return _lib
 
@@ -188,6 +189,10 @@ class App:
                 self._ck(self.L.sgh_app_set_float(self.h, k.encode(), C.c_float(v)))
             else:
                 self._ck(self.L.sgh_app_set_int(self.h, k.encode(), int(v)))
+
+    def set_texture(self, index, rgb):
+        a = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
+        self._ck(self.L.sgh_app_set_texture(self.h, int(index), None if a is None else a.ctypes.data_as(C.c_void_p), 0 if a is None else a.shape[1], 0 if a is None else a.shape[0]))
 
     def upload_scene(self):
         self._ck(self.L.sgh_app_upload_scene(self.h))

@@ -159,6 +159,15 @@ int sgi_set_mesh(sgi_ctx* ctx, const float* xyz, const float* nrm, int32_t num_v
  * writing SGI_BUF_GBUF_ALBEDO (shading then uses white).  Call after sgi_set_mesh. */
 int sgi_set_mesh_colors(sgi_ctx* ctx, const float* rgb);
 
+/* texture coordinates and scene textures — the `uv` attribute of GBuffer.vert (Mesh::getTextureCoords: u, v and in the third component
+ * the 1-based id of the object's texture, set by the `m` directive through Mesh::loadTexture, Mesh.cpp:315-325) and the textures
+ * MyGLTextureViewer::loadRGBTexture creates (MyGLTextureViewer.cpp:45-56: RGB8, GL_LINEAR, GL_REPEAT, no mipmaps; index 0..2 =
+ * texture0..2 of GBuffer.frag; rgb rows as cv::Mat stores them, row 0 = t 0).  With both set the G-buffer pass runs the texture
+ * select of GBuffer.frag:11-30 (useTextureForColoring): SGI_BUF_GBUF_ALBEDO = bilinear texel where uv.z picks a texture, the
+ * vertex colour (or 0 without colours) elsewhere.  uv == NULL / rgb == NULL switch it off again.  Call after sgi_set_mesh. */
+int sgi_set_mesh_uv(sgi_ctx* ctx, const float* uv);
+int sgi_set_texture(sgi_ctx* ctx, int32_t index, const uint8_t* rgb, int32_t width, int32_t height);
+
 /* camera uniforms — replaces configureAmbient + configurePhong for the camera view
  * (MyGLGeometryViewer.cpp:14-19,108-134): MVP, MV, frozen normalMatrix, window size. */
 int sgi_set_camera(sgi_ctx* ctx, const float mvp[16], const float mv[16], const float normal_matrix[9],

@@ -49,6 +49,9 @@ int sgh_app_set_rect(sgh_app* a, int32_t x0, int32_t y0, int32_t x1, int32_t y1)
 int sgh_app_set_light_shard(sgh_app* a, int32_t rank, int32_t world);   /* many-light: own lights l = rank (mod world) */
 /* multi-GPU inside the library: sgi_comm_init on the app's context (id from sgi_comm_unique_id on rank 0); renderMonteCarlo then
  * shards the lights over the ranks and exchanges primitive-id strips / partial sums over NCCL itself (sgi_gather, sgi_reduce_lights) */
+/* scene texture of an `m` directive (Mesh::loadTexture): the reference decodes the image with OpenCV, which the host side here does not
+ * link; the caller supplies the decoded RGB8 pixels for texture<index> of GBuffer.frag (index = the directive's running number - 1) */
+int sgh_app_set_texture(sgh_app* a, int32_t index, const uint8_t* rgb, int32_t width, int32_t height);
 int sgh_app_comm_init(sgh_app* a, const void* id128, size_t bytes, int32_t rank, int32_t world);
 /* light shards balanced by cost: the depth pass of a light costs what the light sees; ms[n] = each light's pass time (one at a time,
  * CUDA events), owner[n] = the rank that renders light s (the same table on every rank; default s mod world) */

@@ -118,6 +118,15 @@ int  orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t
 int  orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, int V, const int32_t* idx, int T,
                            const float mvp[16], int W, int H, float* pos4, float* nrm4, float* albedo4, float* depth);
 
+/* scene textures (Mesh::loadTexture / loadRGBTexture, MyGLTextureViewer.cpp:45-56): RGB8, row 0 = t 0, GL_LINEAR, GL_REPEAT */
+typedef struct orc_texture { const uint8_t* rgb; int32_t w, h; } orc_texture;
+/* GBuffer.frag:11-30 computeFragmentColor with useTextureForColoring == 1 on one fragment (tex[3] = texture0..2) */
+void orc_fragment_color(const float uvw[3], const float rgb[3], const orc_texture tex[3], float out[4]);
+/* the G-buffer with the texture select on the (u, v, texture id) varying; uv / tex NULL = orc_raster_gbuffer_ex */
+int  orc_raster_gbuffer_tex(const float* xyz, const float* nrm, const float* rgb, const float* uv, int V, const int32_t* idx, int T,
+                            const float mvp[16], int W, int H, const orc_texture* tex, float* pos4, float* nrm4, float* albedo4,
+                            float* depth);
+
 /* ---- deferred shading: ShadowMapping/Shaders/GBuffer/PhongShading.frag:11-47 (shadeScene, main.cpp:449-457) ----
  * out4[H][W] float4; discarded (background) pixels get clear4 (0.63, 0.82, 0.96, 1). */
 void orc_shade_phong(const orc_camera* cam, float shadow_intensity, const float* pos4, const float* nrm4,

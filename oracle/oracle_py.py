@@ -209,6 +209,50 @@ def raster_gbuffer_rgb(xyz, nrm, rgb, idx, mvp, W, H):
     return pos, nr, alb, d
 
 
+class Texture(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("w", C.c_int32), ("h", C.c_int32)]
+
+
+def _textures(textures):
+    """up to three uint8 [h, w, 3] arrays (None = unbound) -> (orc_texture[3], keep-alive list)"""
+    arr = (Texture * 3)()
+    keep = []
+    for k in range(3):
+        t = textures[k] if textures is not None and k < len(textures) else None
+        if t is None:
+            arr[k] = Texture(None, 0, 0)
+        else:
+            a = np.ascontiguousarray(t, np.uint8)
+            assert a.ndim == 3 and a.shape[2] == 3
+            keep.append(a)
+            arr[k] = Texture(a.ctypes.data, a.shape[1], a.shape[0])
+    return arr, keep
+
+
+def fragment_color(uvw, rgb, textures):
+    """GBuffer.frag:11-30 with useTextureForColoring == 1 on n fragments: uvw [n,3], rgb [n,3] -> [n,4]."""
+    uvw, rgb = _f32(uvw).reshape(-1, 3), _f32(rgb).reshape(-1, 3)
+    tex, keep = _textures(textures)
+    out = np.empty((uvw.shape[0], 4), np.float32)
+    f = lib().orc_fragment_color
+    for i in range(uvw.shape[0]):
+        f(_fp(uvw[i]), _fp(rgb[i]), tex, _fp(out[i]))
+    return out
+
+
+def raster_gbuffer_tex(xyz, nrm, rgb, uv, idx, mvp, W, H, textures):
+    """G-buffer with the texture select of GBuffer.frag:11-30: rgb may be None, uv [V,3] = (u, v, texture id)."""
+    xyz, nrm, idx, mvp, uv = _f32(xyz), _f32(nrm), _i32(idx), _f32(mvp), _f32(uv)
+    rgb = None if rgb is None else _f32(rgb)
+    tex, keep = _textures(textures)
+    pos, nr, alb = (np.empty((H, W, 4), np.float32) for _ in range(3))
+    d = np.empty((H, W), np.float32)
+    rc = lib().orc_raster_gbuffer_tex(_fp(xyz), _fp(nrm), _fp(rgb) if rgb is not None else None, _fp(uv), xyz.size // 3, _ip(idx),
+                                      idx.size // 3, _fp(mvp), W, H, tex, _fp(pos), _fp(nr), _fp(alb), _fp(d))
+    assert rc == 0
+    return pos, nr, alb, d
+
+
 CLEAR_COLOR = np.array([0.63, 0.82, 0.96, 1.0], np.float32)      # shadeScene, ShadowMapping/src/main.cpp:453
 
 
@@ -477,6 +521,8 @@ def ref_run_shader(name, uniforms, W, H, rect=None):
             a = _f32(v[1])
             if len(v) >= 3 and v[2] == "linear":       # RGBA32F with GL_LINEAR (level 0)
                 s = _Sampler(a.ctypes.data, a.shape[1], a.shape[0], 4 | 0x100, 1)
+            elif len(v) >= 3 and v[2] == "linear_repeat":   # scene texture: GL_LINEAR, GL_REPEAT
+                s = _Sampler(a.ctypes.data, a.shape[1], a.shape[0], 4 | 0x100 | 0x200, 1)
             elif a.ndim == 2:
                 s = _Sampler(a.ctypes.data, a.shape[1], a.shape[0], 1, 1)
             elif a.ndim == 3 and a.shape[2] == 4 and len(v) < 3:

@@ -271,8 +271,53 @@ int orc_raster_gbuffer(const float* xyz, const float* nrm, int V, const int32_t*
 
 int orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, int V, const int32_t* idx, int T,
                           const float mvp[16], int W, int H, float* pos4, float* nrm4, float* albedo4, float* depth) {
+  return orc_raster_gbuffer_tex(xyz, nrm, rgb, NULL, V, idx, T, mvp, W, H, NULL, pos4, nrm4, albedo4, depth);
+}
+
+/* ---- GBuffer.frag:11-30 computeFragmentColor with useTextureForColoring == 1 -------------------------------------------
+ * texture2D on the scene textures of loadRGBTexture (MyGLTextureViewer.cpp:45-56): RGB8, GL_LINEAR, GL_REPEAT, no mipmaps.  GL
+ * leaves the filter's arithmetic to the implementation; DEFINED here as for the other bilinear lookups (oracle_moments_impl.h):
+ * weights fract(u*size - 0.5), texels (byte / 255.0f, alpha 1) accumulated in the order 00, 10, 01, 11, indices wrapped. */
+static inline float wrap_index(float f, float size) {
+  f = f - floorf(f / size) * size;
+  if (!(f < size)) f = 0.0f;
+  return f;
+}
+static void tex_fetch_linear_repeat(const orc_texture* t, float u, float v, float out[4]) {
+  float fw = (float)t->w, fh = (float)t->h;
+  float x = u * fw - 0.5f, y = v * fh - 0.5f;
+  float x0 = floorf(x), y0 = floorf(y), ax = x - x0, ay = y - y0;
+  out[0] = out[1] = out[2] = out[3] = 0.0f;
+  for (int k = 0; k < 4; k++) {
+    float wgt = ((k & 1) ? ax : 1.0f - ax) * ((k >> 1) ? ay : 1.0f - ay);
+    float fi = wrap_index(x0 + (float)(k & 1), fw), fj = wrap_index(y0 + (float)(k >> 1), fh);
+    float tx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (fi >= 0.0f && fi < fw && fj >= 0.0f && fj < fh) {      /* (NaN coordinates fetch the border colour 0) */
+      const uint8_t* p = t->rgb + 3 * ((size_t)(int)fj * t->w + (size_t)(int)fi);
+      tx[0] = (float)p[0] / 255.0f; tx[1] = (float)p[1] / 255.0f; tx[2] = (float)p[2] / 255.0f; tx[3] = 1.0f;
+    }
+    for (int c = 0; c < 4; c++) out[c] = out[c] + tx[c] * wgt;
+  }
+}
+void orc_fragment_color(const float uvw[3], const float rgb[3], const orc_texture tex[3], float out[4]) {
+  float b = uvw[2];
+  int sel = -1;
+  if (b > 0.99f && b < 1.001f) sel = 0;                  /* :16 */
+  else if (b > 1.999f && b < 2.001f) sel = 1;            /* :18 */
+  else if (b > 2.999f && b < 3.001f) sel = 2;            /* :20 */
+  if (sel >= 0 && tex && tex[sel].rgb && tex[sel].w > 0 && tex[sel].h > 0) { tex_fetch_linear_repeat(&tex[sel], uvw[0], uvw[1], out); return; }
+  if (sel >= 0) { out[0] = out[1] = out[2] = out[3] = 0.0f; return; }   /* an unbound sampler reads (0,0,0,0): incomplete texture */
+  out[0] = rgb[0]; out[1] = rgb[1]; out[2] = rgb[2]; out[3] = 1.0f;      /* :22-23 */
+}
+
+/* The G-buffer with the third MRT of GBuffer.frag:32-38: uv == NULL / tex == NULL: useMeshColor form (interpolated vertex colour, 1);
+ * otherwise the texture select above on the perspective-correct (u, v, texture id) varying.  rgb may be NULL (colour 0: a disabled
+ * vertex attribute).  Background (0,0,0,1). */
+int orc_raster_gbuffer_tex(const float* xyz, const float* nrm, const float* rgb, const float* uv, int V, const int32_t* idx, int T,
+                           const float mvp[16], int W, int H, const orc_texture* tex, float* pos4, float* nrm4, float* albedo4, float* depth) {
   (void)V;
-  const int with_rgb = rgb != NULL && albedo4 != NULL;
+  const int with_tex = uv != NULL && tex != NULL && albedo4 != NULL;
+  const int with_rgb = (rgb != NULL || with_tex) && albedo4 != NULL;
   int64_t n;
   SubTri* rec = build_records(xyz, idx, T, mvp, W, H, 0, 0.0f, 0.0f, &n);
   if (!rec) return -1;
@@ -294,25 +339,23 @@ int orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, 
       const int32_t* ix = idx + 3 * (size_t)t;
       /* attributes of the sub-triangle's vertices: the source vertices themselves (in the record's CCW order) when
          nothing was clipped, otherwise their barycentric combination */
-      float A[3][9];
+      float A[3][12];
+      const float* arr[4] = {xyz, nrm, rgb, with_tex ? uv : NULL};
       for (int v = 0; v < 3; v++)
-        for (int c = 0; c < 3; c++) {
-          A[v][6 + c] = 0.0f;
-          if (!s->clipped) {
-            int src = s->bary[v][0] == 1.0f ? 0 : (s->bary[v][1] == 1.0f ? 1 : 2);
-            A[v][c] = xyz[3 * (size_t)ix[src] + c];
-            A[v][3 + c] = nrm[3 * (size_t)ix[src] + c];
-            if (with_rgb) A[v][6 + c] = rgb[3 * (size_t)ix[src] + c];
-            continue;
+        for (int g = 0; g < 4; g++)
+          for (int c = 0; c < 3; c++) {
+            const float* a = arr[g];
+            float val = 0.0f;
+            if (a) {
+              if (!s->clipped) {
+                int src = s->bary[v][0] == 1.0f ? 0 : (s->bary[v][1] == 1.0f ? 1 : 2);
+                val = a[3 * (size_t)ix[src] + c];
+              } else {
+                val = (s->bary[v][0] * a[3 * (size_t)ix[0] + c] + s->bary[v][1] * a[3 * (size_t)ix[1] + c]) + s->bary[v][2] * a[3 * (size_t)ix[2] + c];
+              }
+            }
+            A[v][3 * g + c] = val;
           }
-          A[v][c] = (s->bary[v][0] * xyz[3 * (size_t)ix[0] + c] + s->bary[v][1] * xyz[3 * (size_t)ix[1] + c]) +
-                    s->bary[v][2] * xyz[3 * (size_t)ix[2] + c];
-          A[v][3 + c] = (s->bary[v][0] * nrm[3 * (size_t)ix[0] + c] + s->bary[v][1] * nrm[3 * (size_t)ix[1] + c]) +
-                        s->bary[v][2] * nrm[3 * (size_t)ix[2] + c];
-          if (with_rgb)
-            A[v][6 + c] = (s->bary[v][0] * rgb[3 * (size_t)ix[0] + c] + s->bary[v][1] * rgb[3 * (size_t)ix[1] + c]) +
-                          s->bary[v][2] * rgb[3 * (size_t)ix[2] + c];
-        }
       for (int j = y0; j <= y1; j++)
         for (int i = s->px0; i <= s->px1; i++) {
           int64_t E[3];
@@ -325,12 +368,15 @@ int orc_raster_gbuffer_ex(const float* xyz, const float* nrm, const float* rgb, 
           float q1 = ((float)E[1] * s->ia) * s->iw[1];
           float q2 = ((float)E[2] * s->ia) * s->iw[2];
           float iq = 1.0f / ((q0 + q1) + q2);
+          float col[3], uvw[3];
           for (int c = 0; c < 3; c++) {
             pos4[4 * o + c] = ((q0 * A[0][c] + q1 * A[1][c]) + q2 * A[2][c]) * iq;
             nrm4[4 * o + c] = ((q0 * A[0][3 + c] + q1 * A[1][3 + c]) + q2 * A[2][3 + c]) * iq;
-            if (with_rgb) albedo4[4 * o + c] = ((q0 * A[0][6 + c] + q1 * A[1][6 + c]) + q2 * A[2][6 + c]) * iq;
+            col[c] = ((q0 * A[0][6 + c] + q1 * A[1][6 + c]) + q2 * A[2][6 + c]) * iq;
+            uvw[c] = ((q0 * A[0][9 + c] + q1 * A[1][9 + c]) + q2 * A[2][9 + c]) * iq;
           }
-          if (with_rgb) albedo4[4 * o + 3] = 1.0f;
+          if (with_tex) orc_fragment_color(uvw, col, tex, albedo4 + 4 * o);
+          else if (with_rgb) { albedo4[4 * o] = col[0]; albedo4[4 * o + 1] = col[1]; albedo4[4 * o + 2] = col[2]; albedo4[4 * o + 3] = 1.0f; }
           pos4[4 * o + 3] = 1.0f;
           nrm4[4 * o + 3] = s->front ? 1.0f : 0.0f;
         }

@@ -34,6 +34,7 @@ SHADERS = {
     "plausible": "SoftShadowMapping/Shaders/SoftShadow/PlausibleSoftShadow.frag",
     "accurate": "SoftShadowMapping/Shaders/SoftShadow/AccurateSoftShadow.frag",
     "phong": "ShadowMapping/Shaders/GBuffer/PhongShading.frag",
+    "gbuffer": "ShadowMapping/Shaders/GBuffer/GBuffer.frag",      # computeFragmentColor: texture select / vertex colour (third MRT)
     "rbssm": "SoftShadowMapping/Shaders/SoftShadow/RBSSM.frag",
     "meanfilter": "ShadowMapping/Shaders/Filter/MeanFilter.frag",
     # moment shadow maps: the light-view fragment programs and the separable blurs
@@ -65,7 +66,10 @@ def gen_swizzles():
 
 
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
-VARYING = re.compile(r"^\s*varying\s+vec4\s+(\w+)\s*;")
+VARYING = re.compile(r"^\s*varying\s+vec[34]\s+(\w+)\s*;")
+VARYING3 = re.compile(r"^\s*varying\s+vec3\s+(\w+)\s*;")
+# which gl_FragData[] element the runner returns (default 0)
+OUT_INDEX = {"gbuffer": 2}
 UNIFORM = re.compile(r"^\s*uniform\s+(\w+)\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?\s*;")
 PLAIN_GLOBAL = re.compile(r"^(float|int|bool|vec[234]|mat[34])\s+\w+\s*;")
 
@@ -84,6 +88,7 @@ def transform(src):
     """Literal suffixes, drop #extension, thread_local file-scope variables. Returns (text, uniforms)."""
     out, uniforms, depth = [], [], 0
     varyings = []
+    vec3s = set()
     for a, b in DECL_FIXES.items():
         src = src.replace(a, b)
     for line in src.splitlines():
@@ -97,12 +102,14 @@ def transform(src):
         mv = VARYING.match(code)
         if mv:
             varyings.append(mv.group(1))
+            if VARYING3.match(code):
+                vec3s.add(mv.group(1))
         new = FLOAT_LIT.sub(lambda mm: mm.group(1) + "f", line)
         if depth == 0 and PLAIN_GLOBAL.match(code):
             new = "thread_local " + new
         depth += code.count("{") - code.count("}")
         out.append(new)
-    return "\n".join(out) + "\n", uniforms, varyings
+    return "\n".join(out) + "\n", uniforms, [(v, v in vec3s) for v in varyings]
 
 
 RUNNER = r"""
@@ -151,7 +158,7 @@ extern "C" int ref_%(NAME)s_run(const shader_%(NAME)s::RefBinding* b, int nb, in
         gl_FragData[0] = glsl::vec4(o[0], o[1], o[2], o[3]);
         shader_main();
         if (gl_discarded) continue;
-        o[0] = gl_FragData[0].x; o[1] = gl_FragData[0].y; o[2] = gl_FragData[0].z; o[3] = gl_FragData[0].w;
+        o[0] = gl_FragData[%(OUTIDX)s].x; o[1] = gl_FragData[%(OUTIDX)s].y; o[2] = gl_FragData[%(OUTIDX)s].z; o[3] = gl_FragData[%(OUTIDX)s].w;
       }
   }
   return 0;
@@ -188,14 +195,15 @@ def gen_shader_tu(name, ref_root):
         "#undef varying",
         "#undef main",
         "#undef discard",
-        RUNNER % {"NAME": name, "BINDS": "\n    ".join(binds),
+        RUNNER % {"NAME": name, "BINDS": "\n    ".join(binds), "OUTIDX": str(OUT_INDEX.get(name, 0)),
                   "TEXCOORD": "" if "f_texcoord" in text else "(void)nx; (void)ny; // no f_texcoord in this program: ",
                   "VBINDS": "\n    ".join(
                       f'if (!strcmp(b[i].name, "varying:{v}")) {{ vary_img[{k}] = (const float*)b[i].data; continue; }}'
-                      for k, v in enumerate(varyings)),
+                      for k, (v, _) in enumerate(varyings)),
                   "VSETS": "\n  ".join(
-                      f"if (vary_img[{k}]) {v} = glsl::vec4(vary_img[{k}][4 * o], vary_img[{k}][4 * o + 1], vary_img[{k}][4 * o + 2], vary_img[{k}][4 * o + 3]);"
-                      for k, v in enumerate(varyings))},
+                      (f"if (vary_img[{k}]) {v} = glsl::vec3(vary_img[{k}][4 * o], vary_img[{k}][4 * o + 1], vary_img[{k}][4 * o + 2]);" if is3 else
+                       f"if (vary_img[{k}]) {v} = glsl::vec4(vary_img[{k}][4 * o], vary_img[{k}][4 * o + 1], vary_img[{k}][4 * o + 2], vary_img[{k}][4 * o + 3]);")
+                      for k, (v, is3) in enumerate(varyings))},
     ]
     out = os.path.join(GEN, f"shader_{name}.cpp")
     with open(out, "w") as f:

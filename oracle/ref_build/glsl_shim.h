@@ -236,7 +236,8 @@ inline vec2 clamp(const vec2& v, float lo, float hi) { return vec2(clamp(v.x, lo
 struct Sampler {            // bound by the runner; plain data so it can be memcpy'd in
   const float* data;
   int32_t w, h;
-  int32_t channels;         // 1 = depth texture (returns d,d,d,1), 4 = RGBA32F; | 0x100 = GL_LINEAR (level 0) instead of GL_NEAREST
+  int32_t channels;         // 1 = depth texture (returns d,d,d,1), 4 = RGBA32F; | 0x100 = GL_LINEAR (level 0) instead of GL_NEAREST;
+                            // | 0x200 = GL_REPEAT instead of CLAMP_TO_BORDER (the scene textures of loadRGBTexture, MyGLTextureViewer.cpp:45-56)
   int32_t layers;
 };
 typedef Sampler sampler2D;
@@ -245,6 +246,7 @@ typedef Sampler sampler2DArray;
 inline vec4 sampler_texel(const Sampler& s, float fi, float fj, int layer) {     // integer texel coordinates as floats
   float fw = (float)s.w, fh = (float)s.h;
   const int ch = s.channels & 0xFF;
+  if (s.channels & 0x200) { fi = fi - std::floor(fi / fw) * fw; fj = fj - std::floor(fj / fh) * fh; if (!(fi < fw)) fi = 0.0f; if (!(fj < fh)) fj = 0.0f; }
   if (!(fi >= 0.0f && fi < fw && fj >= 0.0f && fj < fh) || layer < 0 || layer >= (s.layers > 0 ? s.layers : 1))
     return ch == 1 ? vec4(0.0f, 0.0f, 0.0f, 1.0f) : vec4(0.0f);
   size_t o = ((size_t)layer * s.h + (size_t)(int)fj) * s.w + (size_t)(int)fi;
