@@ -705,6 +705,7 @@ struct TileArgs {
   int sv_zfail, sv_caps; unsigned long long* frag_counter;             // SVCOUNT: depth-fail mode, capped volumes, optional fragment tally
   unsigned int* mm_min; unsigned int* mm_max; int mm_w;                // DEPTH: per 32x32-texel block extrema of the map (float bits), or null
   const SgiRecUV* uvrec; SgiTex tex[3];                                 // GBUFFER_RGB: texture select (useTextureForColoring), or null
+  int static_items, refresh_full_only;                                  // scheduling switches of the work-item loop (options "tile_static_items", "tile_refresh_full")
 };
 
 #define ONE_BITS 0x3F800000u
@@ -1130,7 +1131,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     const bool refresh_bounds = ngroups >= 8;
     // work items are dealt to the warps round robin (they are in nearest-first order: every warp starts near the front); a shared
     // cursor balanced them slightly better but cost an atomic and a shuffle per item, 6 % of the depth kernel's instructions
-    for (int item = tid >> 5; item < ngroups; item += NT / 32) {
+    for (int item_s = tid >> 5;; item_s += NT / 32) {
+      int item = item_s;
+      if (!a.static_items) {                                   // shared cursor: balances warps over items of very different cost
+        if (lane == 0) item = atomicAdd(&next_item, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+      }
+      if (item >= ngroups) break;
       const int grp = tq.group[item];
       const int qi = grp >> 3, b0 = (grp & 7) << 5;
       const int X0 = tq.X0[qi], Y0 = tq.Y0[qi], X1 = tq.X1[qi], Y1 = tq.Y1[qi], X2 = tq.X2[qi], Y2 = tq.Y2[qi];
@@ -1203,7 +1210,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
         const bool covered = (e0 | e1 | e2) >= 0;
         if (covered) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, e1 + es.b1, e2 + es.b2), meta);
         // (a block the triangle covers only in part keeps texels at their old depth: its bound would not move)
-        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds && __all_sync(0xffffffffu, covered)) {
+        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds && (!a.refresh_full_only || __all_sync(0xffffffffu, covered))) {
           // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
           const int p = ly * SGI_PITCH + lx;
           const unsigned int cur = (MODE == SGI_MODE_DEPTH) ? zt[p] : (unsigned int)(kt[p] >> 32);
@@ -1695,6 +1702,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
   ta.sv_zfail = job.sv_zfail; ta.sv_caps = job.sv_caps; ta.frag_counter = job.frag_counter;
   ta.mm_min = job.mm_min; ta.mm_max = job.mm_max; ta.mm_w = job.mm_w;
+  ta.static_items = ctx->tile_static_items; ta.refresh_full_only = ctx->tile_refresh_full;
   ta.uvrec = with_tex ? sc.d_uvrec : nullptr;
   for (int k = 0; k < 3; k++) ta.tex[k] = job.tex[k];
   for (int k = 0; k < 16; k++) ta.mq[k] = job.mq[k];

@@ -1,16 +1,15 @@
-"""Developer A/B helper: per-pass timings of bench workloads under different SGI_* environment switches (one context each);
-passes run one after the other (overlap off), so tile_depth / tile_gbuffer are the kernels' own durations."""
-import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from scripts.perf_probe import probe_app
-
-CONFIGS = [{}, {"SGI_TILE_BULK": "0"}, {"SGI_TILE_THREADS": "128"}, {"SGI_TILE_THREADS": "256"}, {"SGI_TILE_THREADS": "512"}]
+"""Developer A/B helper: frame rate of bench workloads under different SGI_* environment switches (one bench.py run each)."""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIGS = [{}, {"SGI_TILE_STATIC": "0"}, {"SGI_TILE_REFRESH_FULL": "0"}, {"SGI_TILE_STATIC": "0", "SGI_TILE_REFRESH_FULL": "0"}]
 if __name__ == "__main__":
-    workloads = sys.argv[1:] or ["c2_sponza", "c5_many_light"]
-    for w in workloads:
+    for w, steps in (("c2_sponza", 300), ("c3_dragon", 200), ("c5_sandiego", 30), ("c4_tree_sv", 30)):
         for cfg in CONFIGS:
-            for k in ("SGI_TILE_BULK", "SGI_TILE_THREADS"):
-                os.environ.pop(k, None)
-            os.environ.update(cfg)
-            print(cfg, end=" ", flush=True)
-            probe_app(w, 20, overlap=False)
+            env = dict(os.environ); env.update(cfg)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", w, "--steps", str(steps), "--warmup", "5", "--no-cpu-baseline",
+                                "--no-sharded", "--no-secondary"], capture_output=True, text=True, env=env)
+            try:
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                print(w, cfg, "fps %.1f" % d["value"], {k: round(v, 4) for k, v in d["pass_ms"].items() if k.startswith("tile")}, flush=True)
+            except Exception as e:
+                print(w, cfg, "FAILED", r.stderr[-300:], flush=True)
