@@ -971,6 +971,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func, a.sv_zfail, a.sv_caps, &nfrag};
   // the nearest-first order only pays where hierarchical depth has something to cull: lists of a few dozen triangles skip it
   const bool sort_items = nitems > 48;
+  // scheduling of the work-item loop, 2 = by list length (measured, profiles/r2_experiments.txt #6): long lists (the teapot's 270 per
+  // tile) want the shared cursor and a bound refresh after every block, short ones (a city's few dozen) static dealing and a refresh
+  // of fully covered blocks only; stencil counting has no bounds to refresh and prefers static dealing
+  const bool static_items = a.static_items == 2 ? (MODE == SGI_MODE_SVCOUNT || !sort_items) : a.static_items != 0;
+  const bool refresh_full_only = a.refresh_full_only == 2 ? !sort_items : a.refresh_full_only != 0;
 
   for (int base = 0; base < nitems; base += NT) {
     if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; fc_count = 0; zq_min = 0xFFFFFFFFu; zq_max = 0u; }
@@ -1133,7 +1138,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     // cursor balanced them slightly better but cost an atomic and a shuffle per item, 6 % of the depth kernel's instructions
     for (int item_s = tid >> 5;; item_s += NT / 32) {
       int item = item_s;
-      if (!a.static_items) {                                   // shared cursor: balances warps over items of very different cost
+      if (!static_items) {                                     // shared cursor: balances warps over items of very different cost
         if (lane == 0) item = atomicAdd(&next_item, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
       }
@@ -1210,7 +1215,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
         const bool covered = (e0 | e1 | e2) >= 0;
         if (covered) sink.fragment(lx, ly, frag_z(z0, dz1, dz2, ia, zoff, e1 + es.b1, e2 + es.b2), meta);
         // (a block the triangle covers only in part keeps texels at their old depth: its bound would not move)
-        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds && (!a.refresh_full_only || __all_sync(0xffffffffu, covered))) {
+        if (MODE != SGI_MODE_SVCOUNT && refresh_bounds && (!refresh_full_only || __all_sync(0xffffffffu, covered))) {
           // refresh the block's bound from what is stored now (one warp-wide max; other warps can only lower it further)
           const int p = ly * SGI_PITCH + lx;
           const unsigned int cur = (MODE == SGI_MODE_DEPTH) ? zt[p] : (unsigned int)(kt[p] >> 32);

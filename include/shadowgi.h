@@ -287,6 +287,10 @@ int sgi_unregister_host(void* host_ptr);
  *   "pdl"             1 (default) k_order and the tile kernel are launched as programmatic dependents (their launch latency overlaps the
  *                     predecessor's tail; griddepcontrol.wait in the kernels), 0 = plain stream order
  *   "tile_bulk_flush" 1 (default) depth tiles leave shared memory by cp.async.bulk row copies, 0 = by 16-byte stores
+ *   "tile_static_items" work items of a tile's triangle list are dealt to the warps round robin (1), drawn from a shared cursor (0),
+ *                       or either by the list's length (2, default: static for lists of up to 48 triangles and for stencil counting)
+ *   "tile_refresh_full" the per-block depth bound is refreshed after fully covered blocks only (1), after every block (0), or by the
+ *                       list's length (2, default).  Scheduling only: results are identical for every value of both options.
  *   "sv_tile_cull"    1 (default) shadow volumes: (prism, tile) pairs behind the tile's farthest scene depth are not listed
  *   "borrow_pinned"   0 (default) inputs are copied inside the call, 1 = page-locked inputs are read later by DMA */
 int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value);

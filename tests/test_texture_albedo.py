@@ -1,7 +1,7 @@
 """Texture albedo: the texture select of GBuffer.frag:11-30 (useTextureForColoring) on the (u, v, texture id) varying, with the scene
 textures of loadRGBTexture (RGB8, GL_LINEAR, GL_REPEAT).  CPU: the oracle's fragment colour against the unmodified GBuffer.frag
 (golden fixture tests/golden/golden_gbuffer.npz, made by make_golden_gbuffer below with the reference build; live when oracle/_ref is
-present).  GPU: the textured G-buffer and the shaded frame against the oracle, bit for bit."""
+present).  GPU: the textured G-buffer against the oracle bit for bit, the shaded frame within the powf tolerance (2e-6 relative)."""
 import os
 
 import numpy as np
@@ -84,7 +84,7 @@ def test_oracle_textured_gbuffer_reduces_to_the_colour_form_without_textures():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("with_rgb", [True, False])
-def test_textured_gbuffer_and_shading_bit_exact(with_rgb):
+def test_textured_gbuffer_bit_exact_and_shading(with_rgb):
     from globalillumination_b200 import capi
     sc, uv, tex, rgb = _textured_scene()
     W, H, S = 640, 360, 256
@@ -108,7 +108,8 @@ def test_textured_gbuffer_and_shading_bit_exact(with_rgb):
         ctx.shade_phong()
         cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
         shaded_o = O.shade_phong(cam, po.shadow_intensity, pos_o, nrm_o, alb_o, ctx.read("visibility"))
-        assert util.bits_equal(ctx.read("shaded"), shaded_o)
+        # powf is the one operation whose CPU and GPU implementations are not both correctly rounded (as in test_gpu_parity.py)
+        assert np.allclose(ctx.read("shaded"), shaded_o, rtol=2e-6, atol=1e-7)
         fg = dep_o < 1
         assert len(np.unique(alb_o[fg][:, 0])) > 500                          # filtered texels, not a handful of flat colours
         # unbinding the textures returns to the vertex-colour form
