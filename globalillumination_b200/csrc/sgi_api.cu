@@ -186,6 +186,8 @@ int sgi_create(sgi_ctx** out, int device) {
   { const char* e = getenv("SGI_TILE_THREADS"); int v = e ? atoi(e) : 0; ctx->tile_threads = (v == 128 || v == 256 || v == 512 || v == 1024) ? v : 0; }
   { const char* e = getenv("SGI_TILE_BULK"); if (e) ctx->tile_bulk_flush = e[0] != '0'; }
   { const char* e = getenv("SGI_PDL"); if (e) ctx->pdl = e[0] != '0'; }
+  { const char* e = getenv("SGI_TILE_BIN_BIG"); if (e) ctx->tile_bin_big = atoi(e); }
+  { const char* e = getenv("SGI_TILE_DIRECT"); if (e) ctx->tile_direct = atoi(e); }
   { const char* e = getenv("SGI_TILE_STATIC"); if (e) ctx->tile_static_items = e[0] - '0'; }
   { const char* e = getenv("SGI_TILE_REFRESH_FULL"); if (e) ctx->tile_refresh_full = e[0] - '0'; }
   // lowest priority: when CTAs of the next frame's raster passes and of this frame's shadow pass compete for an SM, the raster
@@ -1001,6 +1003,8 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
   else if (!strcmp(name, "pdl")) ctx->pdl = value ? 1 : 0;
+  else if (!strcmp(name, "tile_direct")) ctx->tile_direct = value;
+  else if (!strcmp(name, "tile_bin_big")) ctx->tile_bin_big = value;
   else if (!strcmp(name, "tile_static_items")) ctx->tile_static_items = value < 0 || value > 2 ? 2 : value;
   else if (!strcmp(name, "tile_refresh_full")) ctx->tile_refresh_full = value < 0 || value > 2 ? 2 : value;
   else if (!strcmp(name, "sv_count_fragments")) ctx->sv_count_fragments = value ? 1 : 0;

@@ -524,6 +524,31 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
   }
 }
 
+// The un-binned big records (floors, walls: > SGI_BIG_TILES tiles each), binned after all: with thousands of tiles per pass every
+// tile CTA testing every big record is the larger cost (a city under an 8192^2 map: 394 big records x 16384 tiles = 6.5 M record
+// tests and 25 KB of record reads per tile, where 96 % of the tiles hold nothing else).  One CTA per big record at a time, its
+// threads over the tiles of the bounding box, exact triangle / tile test as in the binner; k_order then reports no big records
+// to the tile kernel.  Launched only for passes of many tiles (option "tile_bin_big"); small passes keep the per-tile test.
+__global__ void __launch_bounds__(256) k_bin_big(const SetupBinArgs a) {
+  SGI_GRID_DEP_WAIT();                                          // the binner's big list and cursors
+  const int nbig = a.counters[3];
+  for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+    const int slot = a.big_list[b];
+    const SgiRec rr = a.rec[slot];
+    const int bx0 = max((int)rr.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)rr.py0 >> SGI_TILE_LOG2, a.ty0);
+    const int bx1 = min((int)rr.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)rr.py1 >> SGI_TILE_LOG2, a.ty1);
+    if (bx0 > bx1 || by0 > by1) continue;
+    const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
+    for (int k = threadIdx.x; k < nt; k += 256) {
+      const int ty = by0 + k / bw, tx = bx0 + k % bw;
+      if (tile_overlaps(rr, tx, ty, a.W, a.H) && !tile_behind_scene(rr, tx, ty, a.W, a.H, a.tile_zmax, a.tiles_x)) {
+        const int tile = ty * a.tiles_x + tx;
+        list_append(a, tile, atomicAdd(&a.tile_cnt[tile], 1), slot);
+      }
+    }
+  }
+}
+
 // After the binner: one CTA turns the list lengths into the work items of the tile kernel (one CTA each).
 //  * list length the tile kernel reads = min(cursor, capacity); the longest list ever wanted goes to the host-mapped flag word
 //    (the host sizes the capacity from it), a cursor beyond the capacity raises the sticky overflow flag;
@@ -549,6 +574,7 @@ struct OrderArgs {
   int32_t* counters; int32_t* snap; volatile int32_t* h_flags; int32_t* d_sticky; int size_class;
   int2* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
   unsigned int* mm_min; unsigned int* mm_max; int mm_n;     // depth pass feeding the min-max cull: block extrema reset here (1.0 / 0.0)
+  int big_binned;                                            // k_bin_big ran: the tile kernel has no big list to test
 };
 #define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
 #define SGI_ORDER_REG 16        // tiles per thread held in registers (grids up to 16 384 tiles: an 8192^2 map); larger grids re-read
@@ -602,7 +628,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   if (warp == 0) {
     int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
     if (lane == 0) {
-      a.snap[0] = c0; a.snap[3] = c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
+      a.snap[0] = c0; a.snap[3] = a.big_binned ? 0 : c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
       a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0;
       // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
       // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
@@ -705,6 +731,7 @@ struct TileArgs {
   int sv_zfail, sv_caps; unsigned long long* frag_counter;             // SVCOUNT: depth-fail mode, capped volumes, optional fragment tally
   unsigned int* mm_min; unsigned int* mm_max; int mm_w;                // DEPTH: per 32x32-texel block extrema of the map (float bits), or null
   const SgiRecUV* uvrec; SgiTex tex[3];                                 // GBUFFER_RGB: texture select (useTextureForColoring), or null
+  int direct_max;                                                       // DEPTH: lists up to this length take the register path (option "tile_direct"), 0 = never
   int static_items, refresh_full_only;                                  // scheduling switches of the work-item loop (options "tile_static_items", "tile_refresh_full")
 };
 
@@ -885,6 +912,84 @@ struct TileSink {                  // where fragments go: the tile payload in sh
   }
 };
 
+// Short lists (a city under an 8192^2 map: one to a few dozen triangles per tile, most of them larger than the tile).  The general
+// path below pays a fixed price per tile - payload clear, queue, work items, five barriers, flush from shared memory - that is most
+// of the kernel where lists are short.  Here every thread owns a patch of 4 x PH texels in registers instead: the list's set-ups
+// are parked in shared memory once (one barrier), every thread walks the list, skips triangles whose bounding box or whose edge
+// maxima miss its patch, steps the three biased edge values texel by texel (one wide multiply-add each, exact integers) and keeps
+// the minimum depth; the patch then goes straight to global memory as 16-byte stores.  No shared-memory payload, no atomics.
+// The depths are frag_z() of the same integers in the same order of operations as the general path: identical bits.
+template <int NT>
+__device__ __forceinline__ void tile_direct_depth(const TileArgs& a, TriQueue<NT>& tq, int ox, int oy, const int32_t* __restrict__ list,
+                                                  int nlisted, int nitems) {
+  constexpr int PH = SGI_TILE * SGI_TILE / NT / 4;
+  const int tid = threadIdx.x;
+  if (tid < nitems) {
+    const int slot = tid < nlisted ? __ldg(&list[tid]) : __ldg(&a.big_list[tid - nlisted]);
+    const uint4* rp = reinterpret_cast<const uint4*>(&a.rec[slot]);
+    const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+    const int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
+    const int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
+    const int lx0 = max(px0 - ox, 0), ly0 = max(py0 - oy, 0), lx1 = min(px1 - ox, SGI_TILE - 1), ly1 = min(py1 - oy, SGI_TILE - 1);
+    tq.X0[tid] = (int)q0.x; tq.Y0[tid] = (int)q0.y; tq.X1[tid] = (int)q0.z; tq.Y1[tid] = (int)q0.w; tq.X2[tid] = (int)q1.x; tq.Y2[tid] = (int)q1.y;
+    tq.z0[tid] = __uint_as_float(q1.z); tq.dz1[tid] = __uint_as_float(q1.w); tq.dz2[tid] = __uint_as_float(q2.x);
+    tq.ia[tid] = __uint_as_float(q2.y); tq.zoff[tid] = __uint_as_float(q2.z);
+    tq.box[tid] = (lx0 <= lx1 && ly0 <= ly1) ? (lx0 | (ly0 << 8) | (lx1 << 16) | (ly1 << 24)) : 0xFF;     // 0xFF: a box no patch overlaps
+  }
+  __syncthreads();
+  const int plx = (tid & 15) << 2, ply = (tid >> 4) * PH;
+  unsigned int best[PH][4];
+#pragma unroll
+  for (int j = 0; j < PH; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) best[j][i] = ONE_BITS;
+  const int PX = (ox + plx) * SGI_SUBPIX + SGI_SUBPIX / 2, PY = (oy + ply) * SGI_SUBPIX + SGI_SUBPIX / 2;
+  for (int k = 0; k < nitems; k++) {
+    const int box = tq.box[k];
+    if (plx > ((box >> 16) & 0xFF) || plx + 3 < (box & 0xFF) || ply > ((box >> 24) & 0xFF) || ply + PH - 1 < ((box >> 8) & 0xFF)) continue;
+    const int X0 = tq.X0[k], Y0 = tq.Y0[k], X1 = tq.X1[k], Y1 = tq.Y1[k], X2 = tq.X2[k], Y2 = tq.Y2[k];
+    const int dx0 = X2 - X1, dy0 = Y2 - Y1, dx1 = X0 - X2, dy1 = Y0 - Y2, dx2 = X1 - X0, dy2 = Y1 - Y0;
+    const long long b0 = (dy0 < 0 || (dy0 == 0 && dx0 < 0)) ? 0 : 1, b1 = (dy1 < 0 || (dy1 == 0 && dx1 < 0)) ? 0 : 1,
+                    b2 = (dy2 < 0 || (dy2 == 0 && dx2 < 0)) ? 0 : 1;
+    // biased edge values at the patch's first texel (EdgeSet::test): covered <=> all three >= 0
+    long long r0 = (long long)dx0 * (long long)(PY - Y1) - ((long long)dy0 * (long long)(PX - X1) + b0);
+    long long r1 = (long long)dx1 * (long long)(PY - Y2) - ((long long)dy1 * (long long)(PX - X2) + b1);
+    long long r2 = (long long)dx2 * (long long)(PY - Y0) - ((long long)dy2 * (long long)(PX - X0) + b2);
+    {  // the largest value of each edge over the patch (affine: at the corner its coefficients point to) - negative: no texel inside
+      const long long m0 = madw(dy0 < 0 ? -dy0 : 0, 3 * SGI_SUBPIX, madw(dx0 > 0 ? dx0 : 0, (PH - 1) * SGI_SUBPIX, r0));
+      const long long m1 = madw(dy1 < 0 ? -dy1 : 0, 3 * SGI_SUBPIX, madw(dx1 > 0 ? dx1 : 0, (PH - 1) * SGI_SUBPIX, r1));
+      const long long m2 = madw(dy2 < 0 ? -dy2 : 0, 3 * SGI_SUBPIX, madw(dx2 > 0 ? dx2 : 0, (PH - 1) * SGI_SUBPIX, r2));
+      if ((m0 | m1 | m2) < 0) continue;
+    }
+    const float z0 = tq.z0[k], dz1 = tq.dz1[k], dz2 = tq.dz2[k], ia = tq.ia[k], zoff = tq.zoff[k];
+#pragma unroll
+    for (int j = 0; j < PH; j++) {
+      long long c0 = r0, c1 = r1, c2 = r2;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if ((c0 | c1 | c2) >= 0) best[j][i] = min(best[j][i], __float_as_uint(frag_z(z0, dz1, dz2, ia, zoff, c1 + b1, c2 + b2)));
+        if (i < 3) { c0 = madw(dy0, -SGI_SUBPIX, c0); c1 = madw(dy1, -SGI_SUBPIX, c1); c2 = madw(dy2, -SGI_SUBPIX, c2); }
+      }
+      if (j < PH - 1) { r0 = madw(dx0, SGI_SUBPIX, r0); r1 = madw(dx1, SGI_SUBPIX, r1); r2 = madw(dx2, SGI_SUBPIX, r2); }
+    }
+  }
+  const int x = ox + plx;
+  const bool vec_ok = (a.W & 3) == 0 && x >= a.rx0 && x + 3 < a.rx1;
+  if (x + 3 < a.rx0 || x >= a.rx1) return;
+#pragma unroll
+  for (int j = 0; j < PH; j++) {
+    const int y = oy + ply + j;
+    if (y < a.ry0 || y >= a.ry1) continue;
+    float* dst = a.depth + (size_t)y * a.W + x;
+    if (vec_ok) *reinterpret_cast<uint4*>(dst) = make_uint4(best[j][0], best[j][1], best[j][2], best[j][3]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (x + i >= a.rx0 && x + i < a.rx1) dst[i] = __uint_as_float(best[j][i]);
+    }
+  }
+}
+
 // One CTA per 64x64 tile.  The tile's triangle list is consumed in chunks of 256: every thread fetches one
 // record (all loads of a chunk in flight together); triangles whose bounding box holds <= 16 pixel centres are
 // rasterised by that thread on the spot, the others are parked in shared memory and then rasterised
@@ -926,6 +1031,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   const int nspill = (tn & 0x40000000) ? a.counters[5] : 0;    // the list was full: this tile's further entries are somewhere in the spill list
   const int nitems = nlisted + nbig + nspill;                  // this tile's list, then the un-binned big triangles, then the spill list (all tiles')
   const bool empty = nitems == 0;                              // nothing can touch the tile: the flush writes the clear values
+  if (MODE == SGI_MODE_DEPTH && NT >= 256 && level == 0 && !empty && nitems <= a.direct_max && !a.mm_min) {
+    tile_direct_depth<NT>(a, tq, ox, oy, list, nlisted, nitems);        // (nitems <= NT; a spilled list is never short)
+    return;
+  }
 
   if (!empty) {
     if (MODE == SGI_MODE_DEPTH) {                              // 4 cells per store
@@ -1666,8 +1775,12 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   oa.busiest_first = ctx->tile_order; oa.max_items = max_items; oa.split_floor = ctx->tile_split; oa.n_sm = ctx->n_sm;
   oa.mm_min = job.mm_min; oa.mm_max = job.mm_max; oa.mm_n = job.mm_min ? job.mm_w * (2 * tiles_y) : 0;   // (mm_w = 2 * tiles_x)
 
+  // passes of many tiles bin their big records too (k_bin_big)
+  const bool bin_big = ctx->tile_bin_big > 0 && n_rect_tiles >= ctx->tile_bin_big;
+  oa.big_binned = bin_big ? 1 : 0;
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
   k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
+  if (bin_big) { SGI_CUDA(ctx, launch_pdl(k_bin_big, dim3(2 * ctx->n_sm), dim3(256), 0, st, ctx->pdl, sa)); ctx->launches++; }
   SGI_CUDA(ctx, launch_pdl(k_order, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
   ctx->launches += 2;
   SGI_CUDA(ctx, cudaGetLastError());
@@ -1686,6 +1799,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
       sa.spill = sc.d_spill; sa.spill_cap = sc.spill_cap; oa.spill_cap = sc.spill_cap;
       sc.needs_clear = true;
       k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
+      if (bin_big) { SGI_CUDA(ctx, launch_pdl(k_bin_big, dim3(2 * ctx->n_sm), dim3(256), 0, st, ctx->pdl, sa)); ctx->launches++; }
       SGI_CUDA(ctx, launch_pdl(k_order, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
       ctx->launches += 2;
       SGI_CUDA(ctx, cudaGetLastError());
@@ -1707,6 +1821,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
   ta.sv_zfail = job.sv_zfail; ta.sv_caps = job.sv_caps; ta.frag_counter = job.frag_counter;
   ta.mm_min = job.mm_min; ta.mm_max = job.mm_max; ta.mm_w = job.mm_w;
+  ta.direct_max = ctx->tile_direct < 0 ? 0 : (ctx->tile_direct > 128 ? 128 : ctx->tile_direct);
   ta.static_items = ctx->tile_static_items; ta.refresh_full_only = ctx->tile_refresh_full;
   ta.uvrec = with_tex ? sc.d_uvrec : nullptr;
   for (int k = 0; k < 3; k++) ta.tex[k] = job.tex[k];

@@ -287,6 +287,10 @@ int sgi_unregister_host(void* host_ptr);
  *   "pdl"             1 (default) k_order and the tile kernel are launched as programmatic dependents (their launch latency overlaps the
  *                     predecessor's tail; griddepcontrol.wait in the kernels), 0 = plain stream order
  *   "tile_bulk_flush" 1 (default) depth tiles leave shared memory by cp.async.bulk row copies, 0 = by 16-byte stores
+ *   "tile_direct"     depth tiles whose triangle list has at most this many entries (default 32, at most 128, 0 = never) are
+ *                       rasterised in registers, one 4 x 4 texel patch per thread, and stored straight to the map
+ *   "tile_bin_big"    passes of at least this many tiles (default 4096, 0 = never) bin the records that span more than 256 tiles
+ *                       as well (kernel k_bin_big); smaller passes let every tile test them
  *   "tile_static_items" work items of a tile's triangle list are dealt to the warps round robin (1), drawn from a shared cursor (0),
  *                       or either by the list's length (2, default: static for lists of up to 48 triangles and for stencil counting)
  *   "tile_refresh_full" the per-block depth bound is refreshed after fully covered blocks only (1), after every block (0), or by the

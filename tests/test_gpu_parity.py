@@ -598,11 +598,14 @@ def test_pipelined_readback_and_double_buffered_mesh(ctx):
 
 
 @pytest.mark.parametrize("option,value", [("vis_staged", 1), ("overlap_passes", 0), ("tile_threads", 256), ("tile_threads", 512), ("tile_threads", 1024),
-                                          ("tile_order", 0), ("tile_split", 0), ("tile_split", 16)])
+                                          ("tile_order", 0), ("tile_split", 0), ("tile_split", 16), ("tile_direct", 0), ("tile_direct", 128),
+                                          ("tile_bin_big", 0), ("tile_bin_big", 1), ("tile_static_items", 0), ("tile_static_items", 1),
+                                          ("tile_refresh_full", 0), ("tile_refresh_full", 1)])
 @pytest.mark.parametrize("tech,name,W,H,S", [("pcss", "teapot", 640, 360, 512), ("pcf", "raptor", 333, 217, 300), ("pcss", "dragon", 1920, 1080, 4096)])
 def test_implementation_switches_do_not_change_results(ctx, option, value, tech, name, W, H, S):
     """Shared-memory staged taps, single-stream execution, every tile-CTA size, raster-order tile launch, no / aggressive
-    hot-tile subdivision: all give the same bits as the defaults."""
+    hot-tile subdivision, the register path of short depth lists off / up to 128 entries, big records binned / tested per tile,
+    both work-item scheduling forms: all give the same bits as the defaults."""
     sc = util.scene(name)
     po, pg = util.params_pair(tech, S, kernel_size=15 if name != "raptor" else 9)
     fm = setup_frame(ctx, sc, W, H, S, pg)
@@ -613,7 +616,8 @@ def test_implementation_switches_do_not_change_results(ctx, option, value, tech,
         ctx.render_shadow_map(); ctx.render_gbuffer(); ctx.compute_visibility()
         alt = (ctx.read("visibility"), ctx.read("shadow_map"), ctx.read("gbuf_pos"))
     finally:
-        ctx.set_option(option, {"vis_staged": 0, "overlap_passes": 1, "tile_threads": 0, "tile_order": 1, "tile_split": 256}[option])
+        ctx.set_option(option, {"vis_staged": 0, "overlap_passes": 1, "tile_threads": 0, "tile_order": 1, "tile_split": 256, "tile_direct": 32,
+                                "tile_bin_big": 4096, "tile_static_items": 2, "tile_refresh_full": 2}[option])
     for a, b in zip(base, alt):
         assert util.bits_equal(a, b), (option, util.describe_diff(a, b))
     cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
@@ -712,3 +716,21 @@ def test_minmax_cull_is_exact(ctx, name, tech, W, H, S, kw, near_light):
     assert util.bits_equal(out[0], vis_o), util.describe_diff(out[0], vis_o)
     fg = vis_o > 0
     assert 0.02 < (vis_o[fg] == 1.0).mean() < 0.999                      # lit and shadowed regions both present
+
+
+@pytest.mark.parametrize("direct,bin_big", [(0, 0), (32, 0), (0, 1), (128, 1), (32, 4096)])
+def test_sparse_map_paths_match_the_oracle(ctx, direct, bin_big):
+    """The city under a 4096^2 map (4096 tiles, a few hundred records that span more than 256 of them, most tiles holding only
+    those): the register path of short lists and the binning of the big records, alone and together, against the oracle."""
+    sc = util.scene("sandiego")
+    S = 4096
+    po, pg = util.params_pair("hard", S)
+    fm = setup_frame(ctx, sc, 320, 180, S, pg)
+    ctx.set_option("tile_direct", direct); ctx.set_option("tile_bin_big", bin_big)
+    try:
+        ctx.render_shadow_map()
+        got = ctx.read("shadow_map")
+    finally:
+        ctx.set_option("tile_direct", 32); ctx.set_option("tile_bin_big", 4096)
+    want = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
+    assert util.bits_equal(got, want), util.describe_diff(got, want)
