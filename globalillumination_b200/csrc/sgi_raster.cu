@@ -924,17 +924,31 @@ __device__ __forceinline__ void tile_direct_depth(const TileArgs& a, TriQueue<NT
                                                   int nlisted, int nitems) {
   constexpr int PH = SGI_TILE * SGI_TILE / NT / 4;
   const int tid = threadIdx.x;
+  uint4 q0, q1, q2;
+  int box = 0xFF;                                              // 0xFF: a box no patch overlaps
+  unsigned int zlo = 0u;
   if (tid < nitems) {
     const int slot = tid < nlisted ? __ldg(&list[tid]) : __ldg(&a.big_list[tid - nlisted]);
     const uint4* rp = reinterpret_cast<const uint4*>(&a.rec[slot]);
-    const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+    q0 = __ldg(rp); q1 = __ldg(rp + 1); q2 = __ldg(rp + 2);
+    const uint4 q3 = __ldg(rp + 3);
     const int px0 = (int)(short)(q3.x & 0xFFFF), py0 = (int)(short)(q3.x >> 16);
     const int px1 = (int)(short)(q3.y & 0xFFFF), py1 = (int)(short)(q3.y >> 16);
     const int lx0 = max(px0 - ox, 0), ly0 = max(py0 - oy, 0), lx1 = min(px1 - ox, SGI_TILE - 1), ly1 = min(py1 - oy, SGI_TILE - 1);
-    tq.X0[tid] = (int)q0.x; tq.Y0[tid] = (int)q0.y; tq.X1[tid] = (int)q0.z; tq.Y1[tid] = (int)q0.w; tq.X2[tid] = (int)q1.x; tq.Y2[tid] = (int)q1.y;
-    tq.z0[tid] = __uint_as_float(q1.z); tq.dz1[tid] = __uint_as_float(q1.w); tq.dz2[tid] = __uint_as_float(q2.x);
-    tq.ia[tid] = __uint_as_float(q2.y); tq.zoff[tid] = __uint_as_float(q2.z);
-    tq.box[tid] = (lx0 <= lx1 && ly0 <= ly1) ? (lx0 | (ly0 << 8) | (lx1 << 16) | (ly1 << 24)) : 0xFF;     // 0xFF: a box no patch overlaps
+    if (lx0 <= lx1 && ly0 <= ly1) box = lx0 | (ly0 << 8) | (lx1 << 16) | (ly1 << 24);
+    zlo = tri_depth_lower_bound(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), __uint_as_float(q2.z));
+    tq.zlo[tid] = zlo;
+  }
+  __syncthreads();
+  if (tid < nitems) {
+    // nearest first (rank by the depth bound, ties by list position): a thread leaves the list at the first triangle that lies
+    // wholly behind everything its patch already holds
+    int rank = 0;
+    for (int j = 0; j < nitems; j++) { const unsigned int o = tq.zlo[j]; rank += (o < zlo || (o == zlo && j < tid)) ? 1 : 0; }
+    tq.X0[rank] = (int)q0.x; tq.Y0[rank] = (int)q0.y; tq.X1[rank] = (int)q0.z; tq.Y1[rank] = (int)q0.w; tq.X2[rank] = (int)q1.x; tq.Y2[rank] = (int)q1.y;
+    tq.z0[rank] = __uint_as_float(q1.z); tq.dz1[rank] = __uint_as_float(q1.w); tq.dz2[rank] = __uint_as_float(q2.x);
+    tq.ia[rank] = __uint_as_float(q2.y); tq.zoff[rank] = __uint_as_float(q2.z);
+    tq.box[rank] = box; tq.meta[rank] = (int)zlo;
   }
   __syncthreads();
   const int plx = (tid & 15) << 2, ply = (tid >> 4) * PH;
@@ -944,7 +958,9 @@ __device__ __forceinline__ void tile_direct_depth(const TileArgs& a, TriQueue<NT
 #pragma unroll
     for (int i = 0; i < 4; i++) best[j][i] = ONE_BITS;
   const int PX = (ox + plx) * SGI_SUBPIX + SGI_SUBPIX / 2, PY = (oy + ply) * SGI_SUBPIX + SGI_SUBPIX / 2;
+  unsigned int pmax = ONE_BITS;                                // largest depth the patch holds
   for (int k = 0; k < nitems; k++) {
+    if ((unsigned int)tq.meta[k] > pmax) break;                // this and every later triangle: behind the whole patch
     const int box = tq.box[k];
     if (plx > ((box >> 16) & 0xFF) || plx + 3 < (box & 0xFF) || ply > ((box >> 24) & 0xFF) || ply + PH - 1 < ((box >> 8) & 0xFF)) continue;
     const int X0 = tq.X0[k], Y0 = tq.Y0[k], X1 = tq.X1[k], Y1 = tq.Y1[k], X2 = tq.X2[k], Y2 = tq.Y2[k];
@@ -972,6 +988,11 @@ __device__ __forceinline__ void tile_direct_depth(const TileArgs& a, TriQueue<NT
       }
       if (j < PH - 1) { r0 = madw(dx0, SGI_SUBPIX, r0); r1 = madw(dx1, SGI_SUBPIX, r1); r2 = madw(dx2, SGI_SUBPIX, r2); }
     }
+    pmax = 0u;
+#pragma unroll
+    for (int j = 0; j < PH; j++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) pmax = max(pmax, best[j][i]);
   }
   const int x = ox + plx;
   const bool vec_ok = (a.W & 3) == 0 && x >= a.rx0 && x + 3 < a.rx1;

@@ -20,7 +20,8 @@ def main():
         ts = sum(v[0] for v in lines.values()) or 1
         ti = sum(v[1] for v in lines.values()) or 1
         print(f"== {fn}  ({ts} samples, {ti} warp instructions)")
-        for ln, v in sorted(lines.items(), key=lambda kv: -kv[1][0])[:top]:
+        col = 1 if "--by-inst" in sys.argv else 0
+        for ln, v in sorted(lines.items(), key=lambda kv: -kv[1][col])[:top]:
             print(f"  {ln:>5s} {100 * v[0] / ts:5.1f}% samples {100 * v[1] / ti:5.1f}% inst   {v[2][:150]}")
         print()
 

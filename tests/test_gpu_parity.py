@@ -729,7 +729,7 @@ def test_sparse_map_paths_match_the_oracle(ctx, direct, bin_big):
     ctx.set_option("tile_direct", direct); ctx.set_option("tile_bin_big", bin_big)
     try:
         ctx.render_shadow_map()
-        got = ctx.read("shadow_map")
+        got = ctx.read("shadow_map")[0]
     finally:
         ctx.set_option("tile_direct", 32); ctx.set_option("tile_bin_big", 4096)
     want = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
