@@ -43,7 +43,7 @@ EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility", "sgi_filter_shadow_map", "sgi_moment_quantization",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
-    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_set_mesh_uv", "sgi_set_texture", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
+    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_divide_selftest", "sgi_set_mesh_uv", "sgi_set_texture", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -237,6 +237,11 @@ class Context:
         n = C.c_int64()
         self._ck(self.lib.sgi_sv_fragments(self.h, C.byref(n)))
         return n.value
+
+    def divide_selftest(self, n, seed=1):
+        m = C.c_uint64()
+        self._ck(self.lib.sgi_divide_selftest(self.h, C.c_uint64(n), C.c_uint32(seed), C.byref(m)))
+        return m.value
 
     def synchronize(self):
         self._ck(self.lib.sgi_synchronize(self.h))

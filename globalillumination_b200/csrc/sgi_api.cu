@@ -889,6 +889,15 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]) {
   return SGI_OK;
 }
 
+int sgi_divide_selftest(sgi_ctx* ctx, uint64_t n, uint32_t seed, uint64_t* mismatches) {
+  if (!ctx || !mismatches) return SGI_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  unsigned long long m = 0;
+  int rc = sgi_divide_selftest_run(ctx, (unsigned long long)n, seed, &m);
+  *mismatches = (uint64_t)m;
+  return rc;
+}
+
 // option "sv_count_fragments": covered prism fragments of the last sgi_compute_shadow_volume (the unit of work SURVEY 8(d) names)
 int sgi_sv_fragments(sgi_ctx* ctx, int64_t* fragments) {
   if (!ctx || !fragments) return SGI_ERR_INVALID;

@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(256) k_mom_visibility(const MomVisArgs a) {
   if (vertex.x == 0.0f) { a.vis[o] = 0.0f; return; }
   const float4 normal = __ldg(&a.nrm4[o]);
   const float4 sc = mat4_mul(a.lmvp, vertex);
-  const float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+  float4 c;
+  sgi_div3(sc.x, sc.y, sc.z, sc.w, c.x, c.y, c.z);
+  c.w = sc.w / sc.w;
   const float si = a.shadow_intensity;
   float shadow;
   {

@@ -496,7 +496,9 @@ __global__ void __launch_bounds__(256) k_rbssm_prepare(const VisArgs a, RbssmIte
   if (vertex.x == 0.0f) { a.vis[o] = 0.0f; return; }
   const float4 normal = __ldg(&a.nrm4[o]);
   const float4 sc = mat4_mul(a.lmvp, vertex);
-  const float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+  float4 c;
+  sgi_div3(sc.x, sc.y, sc.z, sc.w, c.x, c.y, c.z);
+  c.w = sc.w / sc.w;
   float shadow = pre_evaluation(a, vertex, normal);
   if (sc.w > 0.0f && shadow == 1.0f) {                         // RBSSM.frag:1372
     const Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};

@@ -645,7 +645,9 @@ __global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
   if (vertex.x == 0.0f) { a.vis[o] = 0.0f; return; }              // discard (Shadow.frag:244): the target keeps its clear value 0
   float4 normal = __ldg(&a.nrm4[o]);
   float4 sc = mat4_mul(a.lmvp, vertex);
-  float4 c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+  float4 c;
+  sgi_div3(sc.x, sc.y, sc.z, sc.w, c.x, c.y, c.z);
+  c.w = sc.w / sc.w;
   float shadow = pre_evaluation(a, vertex, normal);
   Smap s = {a.sm, a.SW, a.SH, a.fw, a.fh};
   if (TECH == SGI_TECH_HARD || TECH == SGI_TECH_PCF || TECH == SGI_TECH_PCSS || TECH == SGI_TECH_RBSSM || TECH == SGI_TECH_PCF_TRICUBIC) {
@@ -687,7 +689,8 @@ __global__ void __launch_bounds__(256) k_visibility_staged(const VisArgs a) {
     if (vertex.x != 0.0f) {
       normal = __ldg(&a.nrm4[o]);
       sc = mat4_mul(a.lmvp, vertex);
-      c = make_float4(sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, sc.w / sc.w);
+      sgi_div3(sc.x, sc.y, sc.z, sc.w, c.x, c.y, c.z);
+      c.w = sc.w / sc.w;
       shadow = pre_evaluation(a, vertex, normal);
       need = sc.w > 0.0f && shadow == 1.0f;
     }
@@ -747,7 +750,7 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
   for (int l = 0; l < a.N; l++) {
     float4 t = __ldg(&a.trans[l]);
     float sx = cx + t.x, sy = cy + t.y, sz = cz + t.z, sw = cw + t.w;
-    sx = sx / sw; sy = sy / sw; sz = sz / sw;
+    sgi_div3(sx, sy, sz, sw, sx, sy, sz);
     Smap s = {a.sm + a.layer * l, a.SW, a.SH, a.fw, a.fh};
     float dfl = sm_fetch(s, sx, sy);
     accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
@@ -798,7 +801,7 @@ __global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a)
   for (int l = 0; l < a.N; l++) {
     float4 tr = __ldg(&a.trans[l]);
     float sx = cx + tr.x, sy = cy + tr.y, sz = cz + tr.z, sw = cw + tr.w;
-    sx = sx / sw; sy = sy / sw; sz = sz / sw;
+    sgi_div3(sx, sy, sz, sw, sx, sy, sz);
     Smap s = {a.sm + a.layer * l, a.SW, a.SH, a.fw, a.fh};
     float dfl = sm_fetch(s, sx, sy);
     accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
@@ -848,6 +851,51 @@ __global__ void __launch_bounds__(256) k_shade_phong(const ShadeArgs a) {
 }
 
 }  // namespace
+
+namespace {
+__device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// operands for the divide check: raw random bits (every exponent, denormals, infinities, NaNs), or - three draws in four - values
+// with exponents near each other, where light-space coordinates live
+__device__ __forceinline__ float test_operand(unsigned int h, unsigned int sel) {
+  if ((sel & 3u) == 0u) return __uint_as_float(h);
+  const unsigned int e = 100u + (hash_u32(h ^ 0x9e3779b9u) % 56u);             // 2^-27 .. 2^28
+  return __uint_as_float((h & 0x807FFFFFu) | (e << 23));
+}
+__global__ void __launch_bounds__(256) k_divide_selftest(unsigned long long n, unsigned int seed, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256ull) {
+    const unsigned int k = hash_u32((unsigned int)i ^ seed) + (unsigned int)(i >> 32) * 0x632be5abu;
+    const unsigned int sel = hash_u32(k + 4u);
+    const float a0 = test_operand(hash_u32(k), sel), a1 = test_operand(hash_u32(k + 1u), sel >> 2), a2 = test_operand(hash_u32(k + 2u), sel >> 4);
+    const float b = test_operand(hash_u32(k + 3u), sel >> 6);
+    float q0, q1, q2;
+    sgi_div3(a0, a1, a2, b, q0, q1, q2);
+    const float p0 = a0 / b, p1 = a1 / b, p2 = a2 / b;
+    const bool same0 = __float_as_uint(q0) == __float_as_uint(p0) || (q0 != q0 && p0 != p0);
+    const bool same1 = __float_as_uint(q1) == __float_as_uint(p1) || (q1 != q1 && p1 != p1);
+    const bool same2 = __float_as_uint(q2) == __float_as_uint(p2) || (q2 != q2 && p2 != p2);
+    bad += (same0 ? 0 : 1) + (same1 ? 0 : 1) + (same2 ? 0 : 1);
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+// sgi_divide_selftest: the shared-reciprocal divide against the plain division on n random operand quadruples
+int sgi_divide_selftest_run(sgi_ctx* ctx, unsigned long long n, unsigned int seed, unsigned long long* mismatches) {
+  unsigned long long* d = nullptr;
+  SGI_CUDA(ctx, cudaMalloc((void**)&d, 8));
+  SGI_CUDA(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+  k_divide_selftest<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(n, seed, d);
+  ctx->launches++;
+  cudaError_t e = cudaMemcpyAsync(mismatches, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  SGI_CUDA(ctx, e);
+  return SGI_OK;
+}
 
 int sgi_shade_run(sgi_ctx* ctx, const float clear_rgba[4]) {
   ShadeArgs a;

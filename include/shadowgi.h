@@ -217,6 +217,10 @@ int sgi_compute_shadow_volume(sgi_ctx* ctx, const float light_pos[3]);
 /* with the option "sv_count_fragments" = 1: how many prism fragments (pixel centres covered by a volume triangle inside the
  * rectangle, before the depth test) the last sgi_compute_shadow_volume visited - the unit of work of the stencil pass */
 int sgi_sv_fragments(sgi_ctx* ctx, int64_t* fragments);
+/* Diagnostic (no reference counterpart): the shadow pass shares one reciprocal between the three divisions of a projective
+ * divide (`shadowCoord / shadowCoord.w`, Shadow.frag:241); this runs that sequence and the plain IEEE division on n pseudo-random
+ * operand quadruples (every exponent, denormals, infinities, NaNs) and returns how many quotients differ in any bit - 0. */
+int sgi_divide_selftest(sgi_ctx* ctx, uint64_t n, uint32_t seed, uint64_t* mismatches);
 
 /* shadeScene(), ShadowMapping/src/main.cpp:449-457: deferred Phong shading of the G-buffer with the visibility buffer as
  * hardShadowMap (PhongShading.frag:11-47) into SGI_BUF_SHADED; clear_rgba = glClearColor (0.63, 0.82, 0.96, 1). */

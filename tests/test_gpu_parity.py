@@ -734,3 +734,10 @@ def test_sparse_map_paths_match_the_oracle(ctx, direct, bin_big):
         ctx.set_option("tile_direct", 32); ctx.set_option("tile_bin_big", 4096)
     want = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
     assert util.bits_equal(got, want), util.describe_diff(got, want)
+
+
+def test_shared_reciprocal_divide_has_the_bits_of_the_plain_division(ctx):
+    """The projective divides of the shadow pass share one reciprocal (sgi_internal.cuh sgi_div3): 3 x 2^30 quotients over random
+    operand bits and over exponents where light-space coordinates live - every one identical to `a / b`."""
+    for seed in (1, 2, 3, 4):
+        assert ctx.divide_selftest(1 << 28, seed) == 0
