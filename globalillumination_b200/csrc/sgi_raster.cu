@@ -111,7 +111,9 @@ struct SetupBinArgs {
   int tiles_x, tx0, ty0, tx1, ty1;               // tile grid pitch and the inclusive tile range of the job rectangle
   int32_t* tile_cnt; int32_t* pairs; int cap;    // per-tile append cursor; list of tile t = pairs[t * cap .. t * cap + cap)
   int2* spill; int spill_cap;                    // (tile, record) pairs that found their tile's list full (counters[5] = count)
-  int32_t* big_list;                             // records spanning > SGI_BIG_TILES tiles: not binned, every tile CTA tests them (counters[3] = count)
+  int32_t* big_list;                             // records spanning > big_tiles tiles: not binned by the set-up kernel (counters[3] = count); with k_bin_big
+                                                 // the ones beyond huge_tiles are listed from the far end of the buffer instead (counters[6] = count)
+  int big_tiles, huge_tiles, big_cap;            // thresholds of the two classes (huge_tiles = INT_MAX without k_bin_big), entries the buffer holds
   const unsigned int* tile_zmax;                 // shadow volumes: largest scene depth of each tile (float bits), or null
 };
 
@@ -410,8 +412,9 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
     if (bx0 > bx1 || by0 > by1) return;
     const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
     if (nt <= 4 && small_done) return;                   // appended by the aggregated path below
-    if (nt > SGI_BIG_TILES) {          // e.g. the floor: listing it in thousands of tiles costs more than letting each tile test it
-      a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
+    if (nt > a.big_tiles) {            // e.g. the floor: listing it in thousands of tiles is not this thread's job (tile kernel or k_bin_big)
+      if (nt > a.huge_tiles) a.big_list[a.big_cap - 1 - atomicAdd(&a.counters[6], 1)] = slot;
+      else a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
       return;
     }
     int k = -1;
@@ -524,28 +527,46 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
   }
 }
 
-// The un-binned big records (floors, walls: > SGI_BIG_TILES tiles each), binned after all: with thousands of tiles per pass every
-// tile CTA testing every big record is the larger cost (a city under an 8192^2 map: 394 big records x 16384 tiles = 6.5 M record
-// tests and 25 KB of record reads per tile, where 96 % of the tiles hold nothing else).  One CTA per big record at a time, its
-// threads over the tiles of the bounding box, exact triangle / tile test as in the binner; k_order then reports no big records
-// to the tile kernel.  Launched only for passes of many tiles (option "tile_bin_big"); small passes keep the per-tile test.
+// The records the set-up kernel did not bin (floors, walls, at an 8192^2 map every triangle of some size), binned after all.
+// With thousands of tiles per pass, every tile CTA testing every big record is the larger cost (a city under an 8192^2 map: 394
+// records beyond 256 tiles x 16384 tiles = 6.5 M record tests and 25 KB of record reads per tile, where 96 % of the tiles hold
+// nothing else), and the set-up kernel's own walk of the mid-sized ones leaves a few of its CTAs with most of the work.  Here the
+// work is spread over the whole GPU: records up to `huge_tiles` tiles are dealt to the warps round robin (a lane per tile of the
+// bounding box), the larger ones are walked by all CTAs together in chunks of 256 tiles.  Exact triangle / tile test as in the
+// set-up kernel; k_order then reports no big records to the tile kernel.  Launched only for passes of many tiles (option
+// "tile_bin_big"); small passes keep the per-tile test.
 __global__ void __launch_bounds__(256) k_bin_big(const SetupBinArgs a) {
-  SGI_GRID_DEP_WAIT();                                          // the binner's big list and cursors
-  const int nbig = a.counters[3];
-  for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
-    const int slot = a.big_list[b];
-    const SgiRec rr = a.rec[slot];
-    const int bx0 = max((int)rr.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)rr.py0 >> SGI_TILE_LOG2, a.ty0);
-    const int bx1 = min((int)rr.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)rr.py1 >> SGI_TILE_LOG2, a.ty1);
-    if (bx0 > bx1 || by0 > by1) continue;
-    const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
-    for (int k = threadIdx.x; k < nt; k += 256) {
+  SGI_GRID_DEP_WAIT();                                          // the set-up kernel's big lists and cursors
+  const int nmid = a.counters[3], nhuge = a.counters[6];
+  const int lane = threadIdx.x & 31, warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = gridDim.x * 8;
+  auto bin_range = [&](const SgiRec& rr, int slot, int bx0, int by0, int bw, int k0, int k1, int step, int first) {
+    for (int k = k0 + first; k < k1; k += step) {
       const int ty = by0 + k / bw, tx = bx0 + k % bw;
       if (tile_overlaps(rr, tx, ty, a.W, a.H) && !tile_behind_scene(rr, tx, ty, a.W, a.H, a.tile_zmax, a.tiles_x)) {
         const int tile = ty * a.tiles_x + tx;
         list_append(a, tile, atomicAdd(&a.tile_cnt[tile], 1), slot);
       }
     }
+  };
+  for (int b = warp; b < nmid; b += nwarps) {
+    const int slot = a.big_list[b];
+    const SgiRec rr = a.rec[slot];
+    const int bx0 = max((int)rr.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)rr.py0 >> SGI_TILE_LOG2, a.ty0);
+    const int bx1 = min((int)rr.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)rr.py1 >> SGI_TILE_LOG2, a.ty1);
+    if (bx0 > bx1 || by0 > by1) continue;
+    const int bw = bx1 - bx0 + 1;
+    bin_range(rr, slot, bx0, by0, bw, 0, bw * (by1 - by0 + 1), 32, lane);
+  }
+  for (int h = 0; h < nhuge; h++) {
+    const int slot = a.big_list[a.big_cap - 1 - h];
+    const SgiRec rr = a.rec[slot];
+    const int bx0 = max((int)rr.px0 >> SGI_TILE_LOG2, a.tx0), by0 = max((int)rr.py0 >> SGI_TILE_LOG2, a.ty0);
+    const int bx1 = min((int)rr.px1 >> SGI_TILE_LOG2, a.tx1), by1 = min((int)rr.py1 >> SGI_TILE_LOG2, a.ty1);
+    if (bx0 > bx1 || by0 > by1) continue;
+    const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
+    // chunk c of this record belongs to CTA (c + h) mod grid: the first chunks of successive records go to different CTAs
+    for (int c = (int)((blockIdx.x + gridDim.x - h % gridDim.x) % gridDim.x); c * 256 < nt; c += gridDim.x)
+      bin_range(rr, slot, bx0, by0, bw, c * 256, min(nt, c * 256 + 256), 256, threadIdx.x);
   }
 }
 
@@ -629,7 +650,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
     if (lane == 0) {
       a.snap[0] = c0; a.snap[3] = a.big_binned ? 0 : c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
-      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0;
+      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0; a.counters[6] = 0;
       // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
       // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
       // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
@@ -1799,6 +1820,9 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   // passes of many tiles bin their big records too (k_bin_big)
   const bool bin_big = ctx->tile_bin_big > 0 && n_rect_tiles >= ctx->tile_bin_big;
   oa.big_binned = bin_big ? 1 : 0;
+  // with k_bin_big the set-up kernel keeps only the records of up to 16 tiles for its own walk; 17 .. 2048 tiles: a warp each,
+  // beyond: all CTAs together.  Without it: records beyond SGI_BIG_TILES are tested by every tile CTA.
+  sa.big_tiles = bin_big ? 16 : SGI_BIG_TILES; sa.huge_tiles = bin_big ? 2048 : 0x7FFFFFFF; sa.big_cap = sc.rec_cap_tris * 7 + 16;
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
   k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
   if (bin_big) { SGI_CUDA(ctx, launch_pdl(k_bin_big, dim3(2 * ctx->n_sm), dim3(256), 0, st, ctx->pdl, sa)); ctx->launches++; }
