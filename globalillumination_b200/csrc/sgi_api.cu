@@ -187,6 +187,8 @@ int sgi_create(sgi_ctx** out, int device) {
   { const char* e = getenv("SGI_TILE_BULK"); if (e) ctx->tile_bulk_flush = e[0] != '0'; }
   { const char* e = getenv("SGI_PDL"); if (e) ctx->pdl = e[0] != '0'; }
   { const char* e = getenv("SGI_TILE_BIN_BIG"); if (e) ctx->tile_bin_big = atoi(e); }
+  { const char* e = getenv("SGI_TILE_BIN_BIG_WORK"); if (e) ctx->tile_bin_big_work = atoi(e); }
+  { const char* e = getenv("SGI_SV_SPLIT_LISTS"); if (e) ctx->sv_split_lists = e[0] != '0'; }
   { const char* e = getenv("SGI_TILE_DIRECT"); if (e) ctx->tile_direct = atoi(e); }
   { const char* e = getenv("SGI_TILE_STATIC"); if (e) ctx->tile_static_items = e[0] - '0'; }
   { const char* e = getenv("SGI_TILE_REFRESH_FULL"); if (e) ctx->tile_refresh_full = e[0] - '0'; }
@@ -1012,8 +1014,10 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
   else if (!strcmp(name, "pdl")) ctx->pdl = value ? 1 : 0;
+  else if (!strcmp(name, "sv_split_lists")) ctx->sv_split_lists = value ? 1 : 0;
   else if (!strcmp(name, "tile_direct")) ctx->tile_direct = value;
   else if (!strcmp(name, "tile_bin_big")) ctx->tile_bin_big = value;
+  else if (!strcmp(name, "tile_bin_big_work")) ctx->tile_bin_big_work = value;
   else if (!strcmp(name, "tile_static_items")) ctx->tile_static_items = value < 0 || value > 2 ? 2 : value;
   else if (!strcmp(name, "tile_refresh_full")) ctx->tile_refresh_full = value < 0 || value > 2 ? 2 : value;
   else if (!strcmp(name, "sv_count_fragments")) ctx->sv_count_fragments = value ? 1 : 0;

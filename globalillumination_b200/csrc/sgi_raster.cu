@@ -342,6 +342,14 @@ __device__ __forceinline__ bool tile_behind_scene(const SgiRec& r, int tx, int t
   return __float_as_uint(fminf(zmin, 1.0f)) > bound;
 }
 
+// stencil = count mod 256 (an 8-bit stencil buffer with GL_INCR_WRAP / GL_DECR_WRAP), after all list segments have been added
+__global__ void __launch_bounds__(256) k_sv_stencil(const int32_t* __restrict__ count, uint8_t* __restrict__ stencil, int W, int rx0, int ry0, int rx1) {
+  const int x = rx0 + blockIdx.x * 256 + threadIdx.x, y = ry0 + blockIdx.y;
+  if (x >= rx1) return;
+  const size_t o = (size_t)y * W + x;
+  stencil[o] = (uint8_t)((unsigned int)count[o] & 255u);
+}
+
 // largest scene depth of every 64x64 tile (pixels outside the viewport ignored)
 __global__ void __launch_bounds__(256) k_tile_zmax(const float* __restrict__ depth, int W, int H, int tiles_x, unsigned int* __restrict__ out) {
   const int tx = blockIdx.x, ty = blockIdx.y;
@@ -412,6 +420,7 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
     if (bx0 > bx1 || by0 > by1) return;
     const int bw = bx1 - bx0 + 1, nt = bw * (by1 - by0 + 1);
     if (nt <= 4 && small_done) return;                   // appended by the aggregated path below
+    if (nt > SGI_BIG_TILES) atomicAdd(&a.counters[7], 1);        // statistic for the host: is k_bin_big worth launching for passes like this one
     if (nt > a.big_tiles) {            // e.g. the floor: listing it in thousands of tiles is not this thread's job (tile kernel or k_bin_big)
       if (nt > a.huge_tiles) a.big_list[a.big_cap - 1 - atomicAdd(&a.counters[6], 1)] = slot;
       else a.big_list[atomicAdd(&a.counters[3], 1)] = slot;
@@ -611,8 +620,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
   SGI_GRID_DEP_WAIT();                                 // the binner's cursors and counters from here on
   if (a.mm_min) for (int i = tid; i < a.mm_n; i += 1024) { a.mm_min[i] = 0x3F800000u; a.mm_max[i] = 0u; }
-  int c0 = 0, c3 = 0, c5 = 0, st_long = 0, st_tot = 0;
-  if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; }
+  int c0 = 0, c3 = 0, c5 = 0, c7 = 0, st_long = 0, st_tot = 0, st_big = 0;
+  if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; c7 = a.counters[7]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; st_big = a.d_sticky[8 + a.size_class]; }
   // this thread's tiles of the job rectangle, i = tid + 1024 k: tile index and cursor
   int til[SGI_ORDER_REG], cnt[SGI_ORDER_REG];
   {
@@ -650,7 +659,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
     if (lane == 0) {
       a.snap[0] = c0; a.snap[3] = a.big_binned ? 0 : c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
-      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0; a.counters[6] = 0;
+      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0; a.counters[6] = 0; a.counters[7] = 0;
+      if (c7 != st_big) { a.d_sticky[8 + a.size_class] = c7; a.h_flags[8 + a.size_class] = c7; }      // records beyond SGI_BIG_TILES in this pass
       // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
       // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
       // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
@@ -750,6 +760,7 @@ struct TileArgs {
   float4* mom4; int mom_tech, z_near, z_far; float mq[16], mqt[4];      // MOMENTS
   unsigned int* ids;                                                   // IDS
   int sv_zfail, sv_caps; unsigned long long* frag_counter;             // SVCOUNT: depth-fail mode, capped volumes, optional fragment tally
+  int sv_split_lists;                                                  // SVCOUNT: hot tiles are shared by list segment, counts added atomically
   unsigned int* mm_min; unsigned int* mm_max; int mm_w;                // DEPTH: per 32x32-texel block extrema of the map (float bits), or null
   const SgiRecUV* uvrec; SgiTex tex[3];                                 // GBUFFER_RGB: texture select (useTextureForColoring), or null
   int direct_max;                                                       // DEPTH: lists up to this length take the register path (option "tile_direct"), 0 = never
@@ -1061,7 +1072,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   if ((int)blockIdx.x >= a.counters[4]) return;                  // the grid is an upper bound of the item count
   const int2 item2 = a.tile_order[blockIdx.x];                   // work items of k_order, busiest first: (item, list length | spill flag)
   const int item = item2.x;
-  const int tile = item & 0xFFFFF, level = (item >> 20) & 3, sub = item >> 22;
+  const int tile = item & 0xFFFFF, split = (item >> 20) & 3, sub = item >> 22;
+  // A hot tile is shared by 4^split CTAs.  Depth and G-buffer passes give each a quarter / a sixteenth of the tile's pixels (all
+  // of them scan the whole list).  Stencil counts are sums, so there the LIST is cut instead: every CTA counts its segment of the
+  // list over the whole tile and adds its counts to the target (option "sv_split_lists") - no record is scanned twice.
+  const bool seg_split = MODE == SGI_MODE_SVCOUNT && a.sv_split_lists && split > 0;
+  const int level = seg_split ? 0 : split;
   const int rs_log2 = SGI_TILE_LOG2 - level, rs = 1 << rs_log2;  // this CTA's region of the tile: rs x rs pixels at (qx0,qy0)
   const int qx0 = (sub & ((1 << level) - 1)) << rs_log2, qy0 = (sub >> level) << rs_log2;
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
@@ -1071,8 +1087,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   const int tn = item2.y;
   const int nlisted = tn & 0x3FFFFFFF, nbig = a.counters[3];
   const int nspill = (tn & 0x40000000) ? a.counters[5] : 0;    // the list was full: this tile's further entries are somewhere in the spill list
-  const int nitems = nlisted + nbig + nspill;                  // this tile's list, then the un-binned big triangles, then the spill list (all tiles')
-  const bool empty = nitems == 0;                              // nothing can touch the tile: the flush writes the clear values
+  const int nall = nlisted + nbig + nspill;                    // this tile's list, then the un-binned big triangles, then the spill list (all tiles')
+  int it_lo = 0, nitems = nall;                                // the CTA's share of that index space: [it_lo, nitems)
+  if (seg_split) { const int per = (nall + (1 << (2 * split)) - 1) >> (2 * split); it_lo = min(nall, sub * per); nitems = min(nall, it_lo + per); }
+  const bool empty = nitems == it_lo;                            // nothing can touch the tile: the flush writes the clear values
   if (MODE == SGI_MODE_DEPTH && NT >= 256 && level == 0 && !empty && nitems <= a.direct_max && !a.mm_min) {
     tile_direct_depth<NT>(a, tq, ox, oy, list, nlisted, nitems);        // (nitems <= NT; a spilled list is never short)
     return;
@@ -1121,14 +1139,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   int nfrag = 0;
   const TileSink<MODE> sink = {zt, kt, ct, sd, a.depth_func, a.sv_zfail, a.sv_caps, &nfrag};
   // the nearest-first order only pays where hierarchical depth has something to cull: lists of a few dozen triangles skip it
-  const bool sort_items = nitems > 48;
+  const bool sort_items = nitems - it_lo > 48;
   // scheduling of the work-item loop, 2 = by list length (measured, profiles/r2_experiments.txt #6): long lists (the teapot's 270 per
   // tile) want the shared cursor and a bound refresh after every block, short ones (a city's few dozen) static dealing and a refresh
   // of fully covered blocks only; stencil counting has no bounds to refresh and prefers static dealing
   const bool static_items = a.static_items == 2 ? (MODE == SGI_MODE_SVCOUNT || !sort_items) : a.static_items != 0;
   const bool refresh_full_only = a.refresh_full_only == 2 ? !sort_items : a.refresh_full_only != 0;
 
-  for (int base = 0; base < nitems; base += NT) {
+  for (int base = it_lo; base < nitems; base += NT) {
     if (tid == 0) { next_item = 0; q_count = 0; g_count = 0; fc_count = 0; zq_min = 0xFFFFFFFFu; zq_max = 0u; }
     if (tid < SGI_ZBUCKETS) bucket_cnt[tid] = 0;
     int my_k = -1, my_ng = 0;
@@ -1464,8 +1482,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
     const size_t o = (size_t)y * a.W + x;
     if (MODE == SGI_MODE_SVCOUNT) {
       const int c = empty ? 0 : ct[p];
-      a.count[o] = c;
-      a.stencil[o] = (uint8_t)((unsigned int)c & 255u);
+      if (a.sv_split_lists) { if (c) atomicAdd(&a.count[o], c); }       // (target zeroed before the pass; k_sv_stencil derives the stencil)
+      else { a.count[o] = c; a.stencil[o] = (uint8_t)((unsigned int)c & 255u); }
     } else {
       const unsigned long long key = empty ? 0xFFFFFFFFull : kt[p];
       const unsigned int lo32 = (unsigned int)(key & 0xFFFFFFFFull);
@@ -1784,6 +1802,11 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
     sc.needs_clear = false;
   }
 
+  // shadow volumes with list-segment splitting accumulate their counts: zero the rectangle first (ahead of the binning chain, so
+  // that the tile kernel still launches programmatically behind k_order)
+  if (job.mode == SGI_MODE_SVCOUNT && ctx->sv_split_lists)
+    SGI_CUDA(ctx, cudaMemset2DAsync(job.count + (size_t)ry0 * job.W + rx0, (size_t)job.W * 4, 0, (size_t)(rx1 - rx0) * 4, ry1 - ry0, st));
+
   // shadow volumes: per-tile farthest scene depth, so that the binner drops (prism, tile) pairs that lie behind the scene
   unsigned int* tile_zmax = nullptr;
   if (job.mode == SGI_MODE_SVCOUNT && job.scene_depth && ctx->sv_tile_cull && !job.sv_zfail) {
@@ -1818,7 +1841,9 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   oa.mm_min = job.mm_min; oa.mm_max = job.mm_max; oa.mm_n = job.mm_min ? job.mm_w * (2 * tiles_y) : 0;   // (mm_w = 2 * tiles_x)
 
   // passes of many tiles bin their big records too (k_bin_big)
-  const bool bin_big = ctx->tile_bin_big > 0 && n_rect_tiles >= ctx->tile_bin_big;
+  // (worth it where the tile CTAs would otherwise do many record tests: big records seen in the last pass of this kind x tiles)
+  const bool bin_big = ctx->tile_bin_big > 0 && n_rect_tiles >= ctx->tile_bin_big &&
+                       (long long)sc.h_flags[8 + size_class] * n_rect_tiles >= (long long)ctx->tile_bin_big_work;
   oa.big_binned = bin_big ? 1 : 0;
   // with k_bin_big the set-up kernel keeps only the records of up to 16 tiles for its own walk; 17 .. 2048 tiles: a warp each,
   // beyond: all CTAs together.  Without it: records beyond SGI_BIG_TILES are tested by every tile CTA.
@@ -1865,6 +1890,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   ta.scene_depth = job.scene_depth; ta.depth_func = job.depth_func; ta.count = job.count; ta.stencil = job.stencil;
   ta.mom4 = job.mom4; ta.mom_tech = job.mom_tech; ta.z_near = job.z_near; ta.z_far = job.z_far; ta.ids = job.ids;
   ta.sv_zfail = job.sv_zfail; ta.sv_caps = job.sv_caps; ta.frag_counter = job.frag_counter;
+  ta.sv_split_lists = (job.mode == SGI_MODE_SVCOUNT && ctx->sv_split_lists) ? 1 : 0;
   ta.mm_min = job.mm_min; ta.mm_max = job.mm_max; ta.mm_w = job.mm_w;
   ta.direct_max = ctx->tile_direct < 0 ? 0 : (ctx->tile_direct > 128 ? 128 : ctx->tile_direct);
   ta.static_items = ctx->tile_static_items; ta.refresh_full_only = ctx->tile_refresh_full;
@@ -1877,7 +1903,14 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   else if (job.mode == SGI_MODE_GBUFFER) rc = ((job.rgb || with_tex) && job.albedo4) ? launch_tile<SGI_MODE_GBUFFER_RGB>(ctx, ta, grid, n_rect_tiles, st) : launch_tile<SGI_MODE_GBUFFER>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_MOMENTS) rc = launch_tile<SGI_MODE_MOMENTS>(ctx, ta, grid, n_rect_tiles, st);
   else if (job.mode == SGI_MODE_IDS) rc = launch_tile<SGI_MODE_IDS>(ctx, ta, grid, n_rect_tiles, st);
-  else rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
+  else {
+    rc = launch_tile<SGI_MODE_SVCOUNT>(ctx, ta, grid, n_rect_tiles, st);
+    if (rc == SGI_OK && ta.sv_split_lists) {
+      k_sv_stencil<<<dim3((rx1 - rx0 + 255) / 256, ry1 - ry0), 256, 0, st>>>(job.count, job.stencil, job.W, rx0, ry0, rx1);
+      ctx->launches++;
+      SGI_CUDA(ctx, cudaGetLastError());
+    }
+  }
   return rc;
 }
 

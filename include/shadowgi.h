@@ -293,8 +293,12 @@ int sgi_unregister_host(void* host_ptr);
  *   "tile_bulk_flush" 1 (default) depth tiles leave shared memory by cp.async.bulk row copies, 0 = by 16-byte stores
  *   "tile_direct"     depth tiles whose triangle list has at most this many entries (default 32, at most 128, 0 = never) are
  *                       rasterised in registers, one 4 x 4 texel patch per thread, and stored straight to the map
- *   "tile_bin_big"    passes of at least this many tiles (default 4096, 0 = never) bin the records that span more than 256 tiles
- *                       as well (kernel k_bin_big); smaller passes let every tile test them
+ *   "tile_bin_big"    passes of at least this many tiles (default 4096, 0 = never) bin the records that span more than 16 tiles
+ *                       in a kernel of their own (k_bin_big: a warp per record, all CTAs together on the largest) when the last
+ *                       pass of the kind held enough records beyond 256 tiles - records x tiles >= "tile_bin_big_work" (default
+ *                       2^20); otherwise every tile tests those records itself
+ *   "sv_split_lists"  1 (default) hot tiles of the stencil pass are shared by list segment (every CTA counts its part of the
+ *                       list over the whole tile, counts are added atomically), 0 = by sub-region as in the depth passes
  *   "tile_static_items" work items of a tile's triangle list are dealt to the warps round robin (1), drawn from a shared cursor (0),
  *                       or either by the list's length (2, default: static for lists of up to 48 triangles and for stencil counting)
  *   "tile_refresh_full" the per-block depth bound is refreshed after fully covered blocks only (1), after every block (0), or by the

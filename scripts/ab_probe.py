@@ -1,9 +1,9 @@
 """Developer A/B helper: frame rate of bench workloads under different SGI_* environment switches (one bench.py run each)."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CONFIGS = [{}, {"SGI_TILE_BIN_BIG": "0"}]
+CONFIGS = [{}, {"SGI_SV_SPLIT_LISTS": "0"}, {"SGI_TILE_BIN_BIG": "0"}]
 if __name__ == "__main__":
-    for w, steps in (("c5_sandiego", 30), ("c3_dragon", 200)):
+    for w, steps in (("c4_tree_sv", 40), ("c4_tree_sv_1080p", 40), ("c4_tree_sv_pertri", 20), ("c3_dragon", 200), ("c5_sandiego", 30)):
         for cfg in CONFIGS:
             env = dict(os.environ); env.update(cfg)
             r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", w, "--steps", str(steps), "--warmup", "5", "--no-cpu-baseline",

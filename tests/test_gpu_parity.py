@@ -599,7 +599,7 @@ def test_pipelined_readback_and_double_buffered_mesh(ctx):
 
 @pytest.mark.parametrize("option,value", [("vis_staged", 1), ("overlap_passes", 0), ("tile_threads", 256), ("tile_threads", 512), ("tile_threads", 1024),
                                           ("tile_order", 0), ("tile_split", 0), ("tile_split", 16), ("tile_direct", 0), ("tile_direct", 128),
-                                          ("tile_bin_big", 0), ("tile_bin_big", 1), ("tile_static_items", 0), ("tile_static_items", 1),
+                                          ("tile_bin_big", 0), ("tile_bin_big_work", 0), ("sv_split_lists", 0), ("tile_static_items", 0), ("tile_static_items", 1),
                                           ("tile_refresh_full", 0), ("tile_refresh_full", 1)])
 @pytest.mark.parametrize("tech,name,W,H,S", [("pcss", "teapot", 640, 360, 512), ("pcf", "raptor", 333, 217, 300), ("pcss", "dragon", 1920, 1080, 4096)])
 def test_implementation_switches_do_not_change_results(ctx, option, value, tech, name, W, H, S):
@@ -617,7 +617,7 @@ def test_implementation_switches_do_not_change_results(ctx, option, value, tech,
         alt = (ctx.read("visibility"), ctx.read("shadow_map"), ctx.read("gbuf_pos"))
     finally:
         ctx.set_option(option, {"vis_staged": 0, "overlap_passes": 1, "tile_threads": 0, "tile_order": 1, "tile_split": 256, "tile_direct": 32,
-                                "tile_bin_big": 4096, "tile_static_items": 2, "tile_refresh_full": 2}[option])
+                                "tile_bin_big": 4096, "tile_bin_big_work": 1 << 20, "sv_split_lists": 1, "tile_static_items": 2, "tile_refresh_full": 2}[option])
     for a, b in zip(base, alt):
         assert util.bits_equal(a, b), (option, util.describe_diff(a, b))
     cam = O.make_camera(fm["cam_mv"], fm["normal_matrix"], fm["light_pos_shading"])
@@ -726,12 +726,12 @@ def test_sparse_map_paths_match_the_oracle(ctx, direct, bin_big):
     S = 4096
     po, pg = util.params_pair("hard", S)
     fm = setup_frame(ctx, sc, 320, 180, S, pg)
-    ctx.set_option("tile_direct", direct); ctx.set_option("tile_bin_big", bin_big)
+    ctx.set_option("tile_direct", direct); ctx.set_option("tile_bin_big", bin_big); ctx.set_option("tile_bin_big_work", 0 if bin_big == 1 else 1 << 20)
     try:
-        ctx.render_shadow_map()
+        ctx.render_shadow_map(); ctx.render_shadow_map()                    # (the second pass knows the first one's big-record count)
         got = ctx.read("shadow_map")[0]
     finally:
-        ctx.set_option("tile_direct", 32); ctx.set_option("tile_bin_big", 4096)
+        ctx.set_option("tile_direct", 32); ctx.set_option("tile_bin_big", 4096); ctx.set_option("tile_bin_big_work", 1 << 20)
     want = O.raster_depth(sc["xyz"], sc["idx"], fm["light_mvp"], S, S)
     assert util.bits_equal(got, want), util.describe_diff(got, want)
 

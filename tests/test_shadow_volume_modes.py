@@ -149,3 +149,19 @@ def test_c4_tree_shadow_volumes_at_1080p_bit_exact(ctx, kw):
     cnt_o, st_o = O.sv_count_ex(pxyz, pidx, fm["cam_mvp"], W, H, dep)
     assert np.array_equal(cnt, cnt_o), util.describe_diff(cnt, cnt_o)
     assert np.array_equal(st, st_o)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,W,H,kw", [("tree", 640, 480, dict(sv_silhouette=1)), ("tree", 320, 240, dict(sv_silhouette=1, sv_zfail=1)), ("raptor", 333, 217, dict())])
+def test_hot_tiles_shared_by_list_segment_or_by_region_count_the_same(ctx, name, W, H, kw):
+    """Option "sv_split_lists": hot tiles shared between CTAs by list segment (counts added atomically, the default) or by
+    sub-region: identical counts and stencil values."""
+    sc = util.scene(name)
+    _, _, cnt1, st1, *_ = _gpu_counts(ctx, sc, W, H, **kw)
+    ctx.set_option("sv_split_lists", 0)
+    try:
+        _, _, cnt0, st0, *_ = _gpu_counts(ctx, sc, W, H, **kw)
+    finally:
+        ctx.set_option("sv_split_lists", 1)
+    assert np.array_equal(cnt0, cnt1) and np.array_equal(st0, st1)
+    assert (cnt1 != 0).mean() > 0.005
