@@ -1077,9 +1077,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_tile(const TileArgs a) {
   // of them scan the whole list).  Stencil counts are sums, so there the LIST is cut instead: every CTA counts its segment of the
   // list over the whole tile and adds its counts to the target (option "sv_split_lists") - no record is scanned twice.
   const bool seg_split = MODE == SGI_MODE_SVCOUNT && a.sv_split_lists && split > 0;
-  const int level = seg_split ? 0 : split;
+  const int level = seg_split ? 0 : split, rsub = seg_split ? 0 : sub;
   const int rs_log2 = SGI_TILE_LOG2 - level, rs = 1 << rs_log2;  // this CTA's region of the tile: rs x rs pixels at (qx0,qy0)
-  const int qx0 = (sub & ((1 << level) - 1)) << rs_log2, qy0 = (sub >> level) << rs_log2;
+  const int qx0 = (rsub & ((1 << level) - 1)) << rs_log2, qy0 = (rsub >> level) << rs_log2;
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
   const int ox = tx << SGI_TILE_LOG2, oy = ty << SGI_TILE_LOG2;
 
