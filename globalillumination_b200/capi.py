@@ -16,7 +16,7 @@ TECH = {"hard": 0, "pcf": 1, "pcss": 2, "rbsm_noncons": 3, "rbsm_cons": 4, "rpcf
 MOMENT_TECHS = ("vsm", "esm", "evsm", "msm")
 BUF = {"shadow_map": 0, "gbuf_pos": 1, "gbuf_nrm": 2, "cam_depth": 3, "visibility": 4, "sv_count": 5,
        "sv_stencil": 6, "sv_prism_xyz": 7, "sv_prism_idx": 8, "gbuf_albedo": 9, "shaded": 10, "edt_nearest": 11,
-       "moments": 12, "moments_x": 13, "moments_filtered": 14, "prim_id": 15}
+       "moments": 12, "moments_x": 13, "moments_filtered": 14, "prim_id": 15, "light_mask": 16}
 PASS = {"shadow_map": 0, "gbuffer": 1, "visibility": 2, "shadow_volume": 3, "vis_kernel": 4, "tile_depth": 5,
         "tile_gbuffer": 6, "tile_sv": 7, "moment_filter": 8}
 DEPTH_LESS, DEPTH_LEQUAL = 0, 1
@@ -43,7 +43,7 @@ EXPORTS = [
     "sgi_create", "sgi_destroy", "sgi_set_stream", "sgi_set_mesh", "sgi_set_mesh_colors", "sgi_shade_phong", "sgi_set_camera", "sgi_set_lights", "sgi_set_params", "sgi_set_multi_light_common", "sgi_set_option",
     "sgi_default_params", "sgi_render_shadow_map", "sgi_render_gbuffer", "sgi_compute_visibility", "sgi_filter_shadow_map", "sgi_moment_quantization",
     "sgi_compute_shadow_volume", "sgi_read", "sgi_read_async", "sgi_read_wait", "sgi_device_ptr", "sgi_synchronize", "sgi_join", "sgi_enable_timing",
-    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_divide_selftest", "sgi_set_mesh_uv", "sgi_set_texture", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights",
+    "sgi_render_prim_ids", "sgi_sv_fragments", "sgi_divide_selftest", "sgi_set_mesh_uv", "sgi_set_texture", "sgi_comm_unique_id", "sgi_comm_init", "sgi_comm_destroy", "sgi_comm_strip", "sgi_gather", "sgi_reduce_lights", "sgi_set_light_ids",
     "sgi_pass_time_ms", "sgi_reset_timing", "sgi_alloc_host", "sgi_free_host", "sgi_register_host", "sgi_unregister_host", "sgi_kernel_launches", "sgi_last_error", "sgi_version",
 ]
 
@@ -223,6 +223,22 @@ class Context:
 
     def reduce_lights(self, total_lights):
         self._ck(self.lib.sgi_reduce_lights(self.h, int(total_lights)))
+
+    def set_light_ids(self, ids, total_lights):
+        """Light shards with lit masks (params.multi_partial = 2): index in the whole set of each light of set_lights."""
+        a = np.ascontiguousarray(ids, np.int32)
+        self._ck(self.lib.sgi_set_light_ids(self.h, int(a.size), a.ctypes.data_as(C.POINTER(C.c_int32)), int(total_lights)))
+        self.mask_total = int(total_lights)
+
+    def read_light_mask(self):
+        """SGI_BUF_LIGHT_MASK on one rank (no communicator): uint32 lit mask per pixel, assembled from the byte planes."""
+        planes = (self.mask_total + 7) // 8
+        raw = np.empty((planes, self.H, self.W), np.uint8)
+        self._ck(self.lib.sgi_read(self.h, BUF["light_mask"], raw.ctypes.data, raw.nbytes))
+        out = np.zeros((self.H, self.W), np.uint32)
+        for p in range(planes):
+            out |= raw[p].astype(np.uint32) << np.uint32(8 * p)
+        return out
 
     def filter_shadow_map(self):
         self._ck(self.lib.sgi_filter_shadow_map(self.h))

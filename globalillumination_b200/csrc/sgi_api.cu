@@ -668,6 +668,7 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   for (int b : {SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM, SGI_BUF_CAM_DEPTH, SGI_BUF_GBUF_ALBEDO}) sgi_wait_comm(ctx, b, st);
   // a fused many-light pass still resolving positions from this scratch set's records (previous frame, visibility stream)
   if (ctx->rec_reader >= 0) { SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_vis[ctx->rec_reader], 0)); ctx->rec_reader = -1; }
+  sgi_wait_comm(ctx, SGI_BUF_LIGHT_MASK, st);            // (the mask resolve of the previous frame reads the records and the ids too)
   ctx->ids_valid = false;
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
   SgiRasterJob job;
@@ -713,6 +714,7 @@ int sgi_render_prim_ids(sgi_ctx* ctx) {
   }
   // the previous frame's fused many-light pass reads this buffer and this scratch set's records on the visibility stream
   if (ctx->rec_reader >= 0) { SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_vis[ctx->rec_reader], 0)); ctx->rec_reader = -1; }
+  sgi_wait_comm(ctx, SGI_BUF_LIGHT_MASK, st);            // (the mask resolve of the previous frame reads the records and the ids too)
   sgi_wait_reads_of(ctx, SGI_BUF_PRIM_ID, st);
   sgi_wait_comm(ctx, SGI_BUF_PRIM_ID, st);
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
@@ -772,9 +774,18 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
     const bool fused = ctx->params.technique == SGI_TECH_MULTI_HARD && ctx->params.multi_fused;
     if (fused && (!ctx->ids_valid || !ctx->shadow_map_valid)) { ctx->err = "sgi_compute_visibility: multi_fused needs sgi_render_prim_ids and the shadow maps first"; return SGI_ERR_INVALID; }
     if (!fused && (!ctx->gbuffer_valid || !ctx->shadow_map_valid)) { ctx->err = "sgi_compute_visibility: render the shadow map and the G-buffer first"; return SGI_ERR_INVALID; }
+    if (ctx->params.technique == SGI_TECH_MULTI_HARD && ctx->params.multi_partial == 2) {
+      if (!fused || ctx->mask_total < 1 || (int)ctx->light_gid.size() != ctx->N) {
+        ctx->err = "sgi_compute_visibility: multi_partial = 2 needs multi_fused and sgi_set_light_ids for the current lights";
+        return SGI_ERR_INVALID;
+      }
+    }
   }
   cudaSetDevice(ctx->device);
   int rc;
+  if (ctx->params.technique == SGI_TECH_MULTI_HARD && ctx->params.multi_partial == 2) {
+    if ((rc = ensure_buf(ctx, SGI_BUF_LIGHT_MASK, sgi_padded_pixels(ctx) * (size_t)((ctx->mask_total + 7) / 8)))) return rc;
+  }
   // With pass overlap on, the shadow pass goes to the visibility stream: it waits for everything queued on the main stream
   // so far (the depth pass, uploads) and for the G-buffer pass, and the main stream does NOT wait for it - the next frame's
   // depth / G-buffer passes start right away into the other instance of their targets (prepare_target_write).
@@ -817,7 +828,8 @@ int sgi_compute_visibility(sgi_ctx* ctx) {
   }
   // collectives still running on the buffers this pass reads / overwrites (gathered primitive ids; the previous frame's exchange
   // of the visibility buffer)
-  sgi_wait_comm(ctx, SGI_BUF_PRIM_ID, vs); sgi_wait_comm(ctx, SGI_BUF_VISIBILITY, vs);
+  sgi_wait_comm(ctx, SGI_BUF_PRIM_ID, vs); sgi_wait_comm(ctx, SGI_BUF_VISIBILITY, vs); sgi_wait_comm(ctx, SGI_BUF_LIGHT_MASK, vs);
+  if (ctx->params.technique == SGI_TECH_MULTI_HARD && ctx->params.multi_partial == 2) sgi_wait_reads_of(ctx, SGI_BUF_LIGHT_MASK, vs);
   for (int b : {SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM}) sgi_wait_comm(ctx, b, vs);
   int slot = sgi_timing_begin(ctx, SGI_PASS_VISIBILITY, vs);
   rc = sgi_shadow_run(ctx, vs);

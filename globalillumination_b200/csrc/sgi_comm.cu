@@ -157,10 +157,57 @@ int sgi_gather(sgi_ctx* ctx, int32_t which) {
   return SGI_OK;
 }
 
+int sgi_set_light_ids(sgi_ctx* ctx, int32_t n, const int32_t* ids, int32_t total_lights) {
+  if (!ctx || n < 0 || n > 32 || total_lights < n || total_lights > 32 || (n > 0 && !ids)) { if (ctx) ctx->err = "sgi_set_light_ids: at most 32 lights in the whole set"; return SGI_ERR_INVALID; }
+  unsigned int seen = 0u;
+  for (int k = 0; k < n; k++) {
+    if (ids[k] < 0 || ids[k] >= total_lights || ((seen >> ids[k]) & 1u)) { ctx->err = "sgi_set_light_ids: indices must be distinct and below the total"; return SGI_ERR_INVALID; }
+    seen |= 1u << ids[k];
+  }
+  ctx->light_gid.assign(ids, ids + n);
+  ctx->mask_total = total_lights;
+  return SGI_OK;
+}
+
+// light sharding with lit masks: the planes of all ranks are summed (ncclReduceScatter on bytes, disjoint bits), then this rank
+// accumulates the visibility of its strip from the union (k_mask_resolve)
+static int reduce_light_masks(sgi_ctx* ctx, int32_t total_lights) {
+  const int which = SGI_BUF_LIGHT_MASK;
+  if (total_lights != ctx->mask_total) { ctx->err = "sgi_reduce_lights: total differs from sgi_set_light_ids"; return SGI_ERR_INVALID; }
+  if (!ctx->buf[which] || !ctx->buf[SGI_BUF_VISIBILITY]) { ctx->err = "sgi_reduce_lights: compute the lit masks first"; return SGI_ERR_INVALID; }
+  const size_t part = (size_t)sgi_strip_rows(ctx) * ctx->W * ((total_lights + 7) / 8);      // bytes per rank
+  unsigned char* base = (unsigned char*)ctx->buf[which];
+  cudaStream_t st;
+  int rc;
+  if (ctx->comm_n > 1) {
+    st = ctx->comm_stream;
+    if (ctx->buf_bytes[which] < part * ctx->comm_n) { ctx->err = "sgi_reduce_lights: mask buffer sized before sgi_comm_init"; return SGI_ERR_INVALID; }
+    if ((rc = comm_begin(ctx, which))) return rc;
+    SGI_NCCL(ctx, nccl().ReduceScatter(base, base + part * ctx->comm_rank, part, ncclUint8, ncclSum, (ncclComm_t)ctx->nccl_comm, st));
+    sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, st);              // the strip's visibility is written on this stream
+    sgi_wait_comm(ctx, SGI_BUF_VISIBILITY, st);
+  } else {
+    if ((rc = sgi_join_vis(ctx))) return rc;
+    st = ctx->stream;
+  }
+  int32_t r0 = 0, r1 = 0;
+  sgi_comm_strip(ctx, ctx->comm_rank, &r0, &r1);
+  if ((rc = sgi_mask_resolve_run(ctx, r0, r1, st))) return rc;
+  if (ctx->comm_n > 1) {
+    for (int b : {which, (int)SGI_BUF_VISIBILITY}) {
+      if (!ctx->ev_comm_done[b]) SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_done[b], cudaEventDisableTiming));
+      SGI_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done[b], ctx->comm_stream));
+      ctx->comm_pending[b] = true;
+    }
+  }
+  return SGI_OK;
+}
+
 int sgi_reduce_lights(sgi_ctx* ctx, int32_t total_lights) {
   if (!ctx || total_lights <= 0) return SGI_ERR_INVALID;
-  if (!ctx->has_camera || !ctx->buf[SGI_BUF_VISIBILITY]) { ctx->err = "sgi_reduce_lights: compute the partial visibility first"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
+  if (ctx->params.multi_partial == 2) return ctx->has_camera ? reduce_light_masks(ctx, total_lights) : SGI_ERR_INVALID;
+  if (!ctx->has_camera || !ctx->buf[SGI_BUF_VISIBILITY]) { ctx->err = "sgi_reduce_lights: compute the partial visibility first"; return SGI_ERR_INVALID; }
   const int which = SGI_BUF_VISIBILITY;
   const size_t strip = (size_t)sgi_strip_rows(ctx) * ctx->W;       // floats
   float* base = (float*)ctx->buf[which];

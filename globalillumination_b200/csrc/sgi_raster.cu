@@ -594,7 +594,10 @@ __global__ void __launch_bounds__(256) k_bin_big(const SetupBinArgs a) {
 // Histogram and scatter use one shared-memory atomic per distinct key per warp (__match_any_sync): most tiles of a pass fall
 // into two or three buckets, and same-address shared atomics serialise (the previous form of this kernel, one atomic per
 // tile, took 36 us on the 16 384 tiles of an 8192^2 map).
-__device__ __forceinline__ int split_level(int c, int w) { return c > 8 * (long long)w ? 2 : (c > 2 * (long long)w ? 1 : 0); }
+__device__ __forceinline__ int split_level(int c, int w, int max_level = 2) {
+  if (max_level >= 3 && c > 32 * (long long)w) return 3;
+  return c > 8 * (long long)w ? 2 : (c > 2 * (long long)w ? 1 : 0);
+}
 __device__ __forceinline__ int weight_bucket(int c) {
   const int l = 31 - __clz(c | 1);
   return c < 2 ? c : 2 * l + ((c >> (l - 1)) & 1);
@@ -605,6 +608,7 @@ struct OrderArgs {
   int2* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
   unsigned int* mm_min; unsigned int* mm_max; int mm_n;     // depth pass feeding the min-max cull: block extrema reset here (1.0 / 0.0)
   int big_binned;                                            // k_bin_big ran: the tile kernel has no big list to test
+  int seg_split, max_level;                                  // stencil pass: hot tiles shared by list segment, up to 4^3 per tile, against a finer even share
 };
 #define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
 #define SGI_ORDER_REG 16        // tiles per thread held in registers (grids up to 16 384 tiles: an 8192^2 map); larger grids re-read
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
       if (m2 > st_long) { a.d_sticky[a.size_class] = m2; a.h_flags[1 + a.size_class] = m2; }
       if (s2 + c5 > st_tot) { a.d_sticky[4 + a.size_class] = s2 + c5; a.h_flags[4 + a.size_class] = s2 + c5; }
       if (c5 > a.spill_cap) a.h_flags[0] = 1;                   // entries were dropped: the frame is incomplete
-      s_w = a.split_floor > 0 ? max(a.split_floor, s2 / (8 * a.n_sm)) : 0x7FFFFFF;
+      s_w = a.split_floor > 0 ? max(a.seg_split ? a.split_floor / 2 : a.split_floor, s2 / ((a.seg_split ? 32 : 8) * a.n_sm)) : 0x7FFFFFF;
     }
   }
   // list length per tile (what the tile kernel reads) | bit 30: the tile has further entries in the spill list
@@ -681,8 +685,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     const int w = s_w;
     int local = 0;
 #pragma unroll
-    for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl && til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w));
-    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(min(c, a.cap), w)); }
+    for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl && til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w, a.max_level));
+    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(min(c, a.cap), w, a.max_level)); }
     local = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0 && local) atomicAdd(&s_items, local);
     __syncthreads();
@@ -692,7 +696,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   }
   const int w = s_w;
   // ---- histogram of the items over (weight bucket, level): one shared atomic per distinct key per warp
-  auto key_of = [&](int len) -> int { const int c = len & 0x3FFFFFFF; const int lv = split_level(c, w); return (a.busiest_first ? weight_bucket(c >> lv) : 0) * 4 + lv; };
+  auto key_of = [&](int len) -> int { const int c = len & 0x3FFFFFFF; const int lv = split_level(c, w, a.max_level); return (a.busiest_first ? weight_bucket(c >> (a.seg_split ? 2 * lv : lv)) : 0) * 4 + lv; };
   auto hist_step = [&](int key) {
     const unsigned grp = __match_any_sync(0xffffffffu, key);
     if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&hist[key], __popc(grp) << (2 * (key & 3)));
@@ -873,6 +877,7 @@ struct TriQueue {
   int group[4 * NT];               // work items: queue index << 3 | group of 32 blocks (a 64x64 bbox has 128 blocks)
 };
 #define SGI_SPLIT_EXTRA 1536      // most CTAs a pass may add by subdividing hot tiles
+#define SGI_SPLIT_EXTRA_SEG 8192  // ... the stencil pass, whose hot tiles are shared by list segment (up to 64 per tile)
 #define SGI_MAX_FULL 8
 #define SGI_SMALL_TRI 8           // bbox candidates up to which one thread rasterises the triangle alone
 
@@ -1678,7 +1683,7 @@ static int sgi_raster_reserve(sgi_ctx* ctx, SgiScratch& sc, int max_tris, int W,
     if ((rc = grow(ctx, (void**)&sc.d_counters, (size_t)(32 + cap) * 4))) return rc;   // counters | snapshot | tile cursors
     sc.d_snap = sc.d_counters + 16;
     sc.d_tile_cnt = sc.d_counters + 32;
-    if ((rc = grow(ctx, (void**)&sc.d_tile_order, ((size_t)cap + SGI_SPLIT_EXTRA) * 8))) return rc;   // work items
+    if ((rc = grow(ctx, (void**)&sc.d_tile_order, ((size_t)cap + SGI_SPLIT_EXTRA_SEG) * 8))) return rc;   // work items
     if ((rc = grow(ctx, (void**)&sc.d_tile_zmax, (size_t)cap * 4))) return rc;
     sc.tile_cap = cap;
     sc.needs_clear = true;
@@ -1832,12 +1837,15 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   // grid of the tile kernel = upper bound of its work items: every tile of the rectangle + room for subdivided hot tiles
   const int n_rect_tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-  const int max_items = n_rect_tiles + (15 * n_rect_tiles < SGI_SPLIT_EXTRA ? 15 * n_rect_tiles : SGI_SPLIT_EXTRA);
+  const bool seg_split = job.mode == SGI_MODE_SVCOUNT && ctx->sv_split_lists;
+  const int max_items = seg_split ? n_rect_tiles + (63 * n_rect_tiles < SGI_SPLIT_EXTRA_SEG ? 63 * n_rect_tiles : SGI_SPLIT_EXTRA_SEG)
+                                  : n_rect_tiles + (15 * n_rect_tiles < SGI_SPLIT_EXTRA ? 15 * n_rect_tiles : SGI_SPLIT_EXTRA);
   OrderArgs oa;
   oa.tile_cnt = sc.d_tile_cnt; oa.n_tiles = n_tiles; oa.cap = cap; oa.spill_cap = sc.spill_cap;
   oa.counters = sc.d_counters; oa.snap = sc.d_snap; oa.h_flags = sc.h_flags; oa.d_sticky = sc.d_sticky; oa.size_class = size_class;
   oa.order = sc.d_tile_order; oa.tiles_x = tiles_x; oa.tx0 = tx0; oa.ty0 = ty0; oa.gx = tx1 - tx0 + 1; oa.gy = ty1 - ty0 + 1;
   oa.busiest_first = ctx->tile_order; oa.max_items = max_items; oa.split_floor = ctx->tile_split; oa.n_sm = ctx->n_sm;
+  oa.seg_split = seg_split ? 1 : 0; oa.max_level = seg_split ? 3 : 2;
   oa.mm_min = job.mm_min; oa.mm_max = job.mm_max; oa.mm_n = job.mm_min ? job.mm_w * (2 * tiles_y) : 0;   // (mm_w = 2 * tiles_x)
 
   // passes of many tiles bin their big records too (k_bin_big)

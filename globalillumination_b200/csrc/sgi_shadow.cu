@@ -8,6 +8,7 @@
 // Shadow-map taps are GL_NEAREST + CLAMP_TO_BORDER(0): texel = floor(coord*size) (MyGLTextureViewer.cpp:3-28).
 // fp32 in source order, -fmad=false: results are bit-identical to oracle/ (DESIGN.md §3).
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "sgi_internal.cuh"
 
@@ -33,6 +34,9 @@ struct VisArgs {
   float pcf_reach, bs_reach;                                          // reach of the PCF grid / the PCSS blocker search, in texels
   // multi_fused: the camera pass's primitive ids and raster records (positions are resolved here instead of read from a G-buffer)
   const unsigned int* ids; const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
+  // multi_partial == 2: the lights this rank sampled, one bit each at the light's index in the whole set, 8 lights per byte plane,
+  // laid out [rank strip][plane][strip pixels] so that every rank's part is contiguous (one in-place reduce-scatter)
+  unsigned char* mask; int mask_planes, mask_rows; size_t mask_strip; unsigned char gid[32]; int mask_total;
 };
 
 struct Smap { const float* __restrict__ d; int w, h; float fw, fh; };
@@ -762,15 +766,13 @@ __global__ void __launch_bounds__(256) k_visibility_multi(const VisArgs a) {
 // The same accumulation with the vertex map resolved on the fly: GBuffer.vert/frag's world position of the pixel's winning
 // primitive, interpolated exactly as the tile rasteriser's resolve does (perspective-correct, same expression order), so the
 // positions - and with them every tap - are identical to the materialised-G-buffer path while 16 B/pixel less is written and read.
-__global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a) {
-  int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
-  if (x >= a.rx1 || y >= a.ry1) return;
-  size_t o = (size_t)y * a.W + x;
+// world position of the pixel's winning primitive; false: the fragment is discarded (background, or vertex.x == 0)
+__device__ __forceinline__ bool fused_position(const VisArgs& a, int x, int y, size_t o, float& vx, float& vy, float& vz) {
   const unsigned int prim = __ldg(&a.ids[o]);
-  if (prim == 0xFFFFFFFFu) { a.vis[o] = 0.0f; return; }           // background: vertex map (0,0,0,1), discarded (x == 0)
+  if (prim == 0xFFFFFFFFu) return false;                         // background: vertex map (0,0,0,1), discarded (x == 0)
   const int t = (int)(prim >> 3), sub = (int)(prim & 7u);
   const int slot = (sub == 0) ? t : __ldg(&a.ovf_base[t]) + sub - 1;
-  if (slot < 0) { a.vis[o] = 0.0f; return; }                     // (an id that does not belong to this camera pass: never dereferenced)
+  if (slot < 0) return false;                                    // (an id that does not belong to this camera pass: never dereferenced)
   SgiRec r; SgiRecAttr at;
   {
     const uint4* rq = reinterpret_cast<const uint4*>(&a.rec[slot]);
@@ -787,10 +789,28 @@ __global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a)
   const float q1 = ((float)E1 * r.ia) * at.iw[1];
   const float q2 = ((float)E2 * r.ia) * at.iw[2];
   const float iq = 1.0f / ((q0 + q1) + q2);
-  const float vx = ((q0 * at.A[0][0] + q1 * at.A[1][0]) + q2 * at.A[2][0]) * iq;
-  const float vy = ((q0 * at.A[0][1] + q1 * at.A[1][1]) + q2 * at.A[2][1]) * iq;
-  const float vz = ((q0 * at.A[0][2] + q1 * at.A[1][2]) + q2 * at.A[2][2]) * iq;
-  if (vx == 0.0f) { a.vis[o] = 0.0f; return; }
+  vx = ((q0 * at.A[0][0] + q1 * at.A[1][0]) + q2 * at.A[2][0]) * iq;
+  vy = ((q0 * at.A[0][1] + q1 * at.A[1][1]) + q2 * at.A[2][1]) * iq;
+  vz = ((q0 * at.A[0][2] + q1 * at.A[1][2]) + q2 * at.A[2][2]) * iq;
+  return vx != 0.0f;
+}
+// byte of plane p of pixel (x, y) in the mask layout
+__device__ __forceinline__ size_t mask_index(const VisArgs& a, int x, int y, int p) {
+  const int rk = y / a.mask_rows;
+  return ((size_t)rk * a.mask_planes + p) * a.mask_strip + (size_t)(y - rk * a.mask_rows) * a.W + x;
+}
+
+__global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a) {
+  int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.rx1 || y >= a.ry1) return;
+  size_t o = (size_t)y * a.W + x;
+  const bool as_mask = a.p.multi_partial == 2;
+  float vx, vy, vz;
+  if (!fused_position(a, x, y, o, vx, vy, vz)) {
+    if (as_mask) { for (int p = 0; p < a.mask_planes; p++) a.mask[mask_index(a, x, y, p)] = 0; }
+    else a.vis[o] = 0.0f;
+    return;
+  }
   const float* m = a.lmvp;
   float cx = m[0] * vx + m[4] * vy + m[8] * vz;
   float cy = m[1] * vx + m[5] * vy + m[9] * vz;
@@ -798,16 +818,39 @@ __global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a)
   float cw = m[3] * vx + m[7] * vy + m[11] * vz;
   float accShadow = 0.0f, count = 0.0f;
   const float accFactor = 1.0f;
+  unsigned int lit = 0u;
   for (int l = 0; l < a.N; l++) {
     float4 tr = __ldg(&a.trans[l]);
     float sx = cx + tr.x, sy = cy + tr.y, sz = cz + tr.z, sw = cw + tr.w;
     sgi_div3(sx, sy, sz, sw, sx, sy, sz);
     Smap s = {a.sm + a.layer * l, a.SW, a.SH, a.fw, a.fh};
     float dfl = sm_fetch(s, sx, sy);
+    if (as_mask) { if (sz <= dfl) lit |= 1u << a.gid[l]; continue; }
     accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
     count += accFactor;
   }
-  a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
+  if (as_mask) { for (int p = 0; p < a.mask_planes; p++) a.mask[mask_index(a, x, y, p)] = (unsigned char)((lit >> (8 * p)) & 255u); }
+  else a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
+}
+
+// The lit masks of all ranks, summed (disjoint bits: the sum is their union), turned into the visibility of this rank's strip: the
+// accumulation loop of AccurateSoftShadow.frag:100-127 replayed over the whole light set in its own order, so the result has the
+// bits of the un-sharded frame for every shadow intensity (partial float sums would depend on how the lights were dealt).
+__global__ void __launch_bounds__(256) k_mask_resolve(const VisArgs a) {
+  int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
+  if (x >= a.rx1 || y >= a.ry1) return;
+  size_t o = (size_t)y * a.W + x;
+  float vx, vy, vz;
+  if (!fused_position(a, x, y, o, vx, vy, vz)) { a.vis[o] = 0.0f; return; }
+  unsigned int lit = 0u;
+  for (int p = 0; p < a.mask_planes; p++) lit |= (unsigned int)a.mask[mask_index(a, x, y, p)] << (8 * p);
+  float accShadow = 0.0f, count = 0.0f;
+  const float accFactor = 1.0f;
+  for (int l = 0; l < a.mask_total; l++) {
+    accShadow += (((lit >> l) & 1u) ? 1.0f : a.p.shadow_intensity) * accFactor;
+    count += accFactor;
+  }
+  a.vis[o] = accShadow / count;
 }
 
 // ShadowMapping/Shaders/GBuffer/PhongShading.frag:11-47 (shadeScene).  Note `vec3 E = normalize(-vertex)` normalises the
@@ -894,6 +937,32 @@ int sgi_divide_selftest_run(sgi_ctx* ctx, unsigned long long n, unsigned int see
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d);
   SGI_CUDA(ctx, e);
+  return SGI_OK;
+}
+
+// geometry of the lit-mask target (SGI_BUF_LIGHT_MASK): ceil(total / 8) byte planes per rank strip
+static void fill_mask_args(const sgi_ctx* ctx, VisArgs& a) {
+  a.mask = (unsigned char*)ctx->buf[SGI_BUF_LIGHT_MASK];
+  a.mask_total = ctx->mask_total; a.mask_planes = (ctx->mask_total + 7) / 8;
+  a.mask_rows = sgi_strip_rows(ctx); a.mask_strip = (size_t)a.mask_rows * ctx->W;
+  for (int l = 0; l < 32; l++) a.gid[l] = (unsigned char)(l < (int)ctx->light_gid.size() ? ctx->light_gid[l] : 0);
+}
+
+// sgi_reduce_lights in mask mode: visibility of rows [r0, r1) from the summed masks
+int sgi_mask_resolve_run(sgi_ctx* ctx, int r0, int r1, cudaStream_t st) {
+  if (r1 <= r0) return SGI_OK;
+  VisArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = ctx->params;
+  a.W = ctx->W; a.H = ctx->H; a.rx0 = 0; a.ry0 = r0; a.rx1 = ctx->W; a.ry1 = r1;
+  const SgiScratch& sc = ctx->scratch[1];
+  a.ids = (const unsigned int*)ctx->buf[SGI_BUF_PRIM_ID]; a.rec = sc.d_rec; a.attr = sc.d_attr; a.ovf_base = sc.d_ovf_base;
+  a.vis = (float*)ctx->buf[SGI_BUF_VISIBILITY];
+  fill_mask_args(ctx, a);
+  dim3 block(32, 8), grid((ctx->W + 31) / 32, (r1 - r0 + 7) / 8);
+  k_mask_resolve<<<grid, block, 0, st>>>(a);
+  ctx->launches++;
+  SGI_CUDA(ctx, cudaGetLastError());
   return SGI_OK;
 }
 
@@ -1036,6 +1105,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
   a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
   a.ids = nullptr; a.rec = nullptr; a.attr = nullptr; a.ovf_base = nullptr;
+  a.mask = nullptr; a.mask_planes = 0; a.mask_rows = 1; a.mask_strip = 0; a.mask_total = 0;
   a.dmin = nullptr; a.dmax = nullptr; a.mm_w = 0; a.mm_limit = 0.0f; a.pcf_reach = 1.0e30f; a.bs_reach = 1.0e30f;
   a.pcss_early_out = (ctx->pcss_early_out && ctx->params.light_source_radius >= 0 && ctx->params.z_near >= 0 && ctx->params.kernel_size > 0 &&
                       ctx->params.blocker_search_size <= SGI_MAX_PCF_TAPS && !ctx->vis_staged) ? 1 : 0;
@@ -1151,6 +1221,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
       if (ctx->params.multi_fused) {
         const SgiScratch& sc = ctx->scratch[1];          // the camera pass's records (sgi_render_prim_ids)
         a.ids = (const unsigned int*)ctx->buf[SGI_BUF_PRIM_ID]; a.rec = sc.d_rec; a.attr = sc.d_attr; a.ovf_base = sc.d_ovf_base;
+        if (ctx->params.multi_partial == 2) fill_mask_args(ctx, a);
         k_visibility_multi_fused<<<grid, block, 0, st>>>(a);
       } else k_visibility_multi<<<grid, block, 0, st>>>(a);
       break;

@@ -178,6 +178,7 @@ int sgh_app_set_int(sgh_app* a, const char* name, int32_t v) {
   else if (n == "animationOn") a->app.animationOn = v != 0;
   else if (n == "fusedMonteCarlo") a->app.fusedMonteCarlo = v != 0;
   else if (n == "commSkip") a->app.commSkip = v != 0;
+  else if (n == "commMasks") a->app.commMasks = v != 0;
   else { g_err = "unknown int parameter " + n; return -2; }
   return 0;
 }

@@ -185,7 +185,10 @@ int ShadowApp::pushParams(int tech) {
   q.sv_depth_func = svDepthFunc; q.sv_infinity = svInfinity;
   q.sv_silhouette = svSilhouette ? 1 : 0; q.sv_zfail = svZfail ? 1 : 0;
   q.rect_x0 = rect[0]; q.rect_y0 = rect[1]; q.rect_x1 = rect[2]; q.rect_y1 = rect[3];
-  q.multi_partial = (tech == SGI_TECH_MULTI_HARD && lightShardWorld > 1) ? 1 : 0;
+  // light shards exchange lit masks (1 bit per light and pixel) when the set has at most 32 lights and the fused pass is on,
+  // un-normalised float sums otherwise
+  const bool masks = commOn && commMasks && fusedMonteCarlo && shadowParams.numberOfSamples <= 32;
+  q.multi_partial = (tech == SGI_TECH_MULTI_HARD && lightShardWorld > 1) ? (masks ? 2 : 1) : 0;
   q.multi_fused = (tech == SGI_TECH_MULTI_HARD && fusedMonteCarlo) ? 1 : 0;
   int rc = sgi_set_params(ctx, &q);
   return rc ? fail(rc, "sgi_set_params") : 0;
@@ -301,6 +304,7 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
   // light shard: this process builds and samples only lights s = rank (mod world); the shader's common
   // term still comes from the LAST light of the whole set, as in the reference (main.cpp:790,806)
   std::vector<float> mvp, mvpb;
+  std::vector<int32_t> mine_ids;
   Mat4 model = modelMatrix();
   FrameMatrices f;
   for (int s = 0; s < n; s++) {
@@ -312,12 +316,14 @@ int ShadowApp::renderMonteCarlo() {                          // SoftShadowMappin
     if (mine) {
       mvp.insert(mvp.end(), f.lightMVP.m, f.lightMVP.m + 16);
       mvpb.insert(mvpb.end(), f.lightMVPBiased.m, f.lightMVPBiased.m + 16);
+      mine_ids.push_back(s);
     }
   }
   if (mvp.empty()) { err = "renderMonteCarlo: this rank owns no light (more ranks than lights)"; return SGI_ERR_INVALID; }
   Vec3 shading = mul3(rotate(180.0f, Vec3{0, 1, 0}), lightEye);
   rc = sgi_set_lights(ctx, (int)(mvp.size() / 16), mvp.data(), mvpb.data(), &shading.x, shadowParams.shadowMapWidth, shadowParams.shadowMapHeight);
   if (rc) return fail(rc, "sgi_set_lights");
+  if (n <= 32) { if ((rc = sgi_set_light_ids(ctx, (int32_t)mine_ids.size(), mine_ids.data(), n))) return fail(rc, "sgi_set_light_ids"); }
   rc = sgi_set_multi_light_common(ctx, lightShardWorld > 1 ? f.lightMVPBiased.m : nullptr);   // f = light n-1 here
   if (rc) return fail(rc, "sgi_set_multi_light_common");
   if ((rc = pushParams(SGI_TECH_MULTI_HARD))) return rc;

@@ -98,7 +98,12 @@ typedef struct sgi_params {
                                      sgi_compute_visibility / shadow-volume counting (multi-GPU
                                      screen tiles); an empty rectangle means the whole screen */
   int32_t multi_partial;          /* SGI_TECH_MULTI_HARD on a light shard: 1 = write the un-normalised sum
-                                     over this context's lights (ranks are summed, then divided by the total) */
+                                     over this context's lights (ranks are summed, then divided by the total);
+                                     2 (with multi_fused, at most 32 lights in the whole set) = write which of this
+                                     context's lights reach the pixel, one bit per light at its index in the whole set
+                                     (sgi_set_light_ids) into SGI_BUF_LIGHT_MASK - a quarter to a half of the bytes to
+                                     exchange, and the strip's visibility is then accumulated in the reference's light
+                                     order: the bits of the un-sharded frame for every shadow intensity */
   int32_t multi_fused;            /* SGI_TECH_MULTI_HARD: 1 = the accumulation kernel resolves each pixel's world position itself from
                                      SGI_BUF_PRIM_ID (sgi_render_prim_ids) instead of reading a materialised G-buffer: the same
                                      positions to the bit, without the 16 B/pixel write and read of the position target */
@@ -128,7 +133,8 @@ typedef enum sgi_buffer {
   SGI_BUF_MOMENTS_FILTERED = 14, /* float4 [H][W]   filterShadowMap: after the vertical pass (FILTER_Y_MAP_COLOR), what Shadow.frag samples */
   SGI_BUF_PRIM_ID = 15,     /* uint32  [H][W]       sgi_render_prim_ids: winning primitive per pixel = source triangle * 8 + fan index of its clipped
                                                     polygon; 0xFFFFFFFF = background */
-  SGI_BUF_COUNT_ = 16
+  SGI_BUF_LIGHT_MASK = 16,  /* uint8   [ranks][ceil(lights/8)][strip rows][W]  params.multi_partial == 2: lit lights per pixel, 8 per byte plane */
+  SGI_BUF_COUNT_ = 17
 } sgi_buffer;
 
 /* passes that can be timed with sgi_pass_time_ms */
@@ -251,7 +257,11 @@ int sgi_join(sgi_ctx* ctx);
  *   sgi_reduce_lights   light sharding (renderMonteCarlo, AccurateSoftShadow.frag:127): the ranks' un-normalised partial sums in
  *                       SGI_BUF_VISIBILITY (params.multi_partial) -> ncclReduceScatter in place, then divided by the number of
  *                       lights of the whole set: rank r ends with the final visibility of ITS strip (what tile-local shading
- *                       consumes); rows outside the strip are left as partial sums
+ *                       consumes); rows outside the strip are left as partial sums.  With params.multi_partial == 2 the ranks'
+ *                       lit masks (SGI_BUF_LIGHT_MASK, disjoint bits) are reduce-scattered instead - 1 B/pixel per 8 lights -
+ *                       and the strip's visibility is accumulated from the union in the light order of the whole set
+ *   sgi_set_light_ids   light sharding with masks: the index in the whole set of each light passed to sgi_set_lights, and the
+ *                       size of the whole set (<= 32)
  * The collectives run on the context's communication stream behind the passes that produce their input and ahead of the passes
  * that consume their output (device-side ordering, the host does not block). */
 int sgi_comm_unique_id(void* id128, size_t bytes);
@@ -260,6 +270,7 @@ int sgi_comm_destroy(sgi_ctx* ctx);
 int sgi_comm_strip(sgi_ctx* ctx, int32_t rank, int32_t* row0, int32_t* row1);
 int sgi_gather(sgi_ctx* ctx, int32_t which);
 int sgi_reduce_lights(sgi_ctx* ctx, int32_t total_lights);
+int sgi_set_light_ids(sgi_ctx* ctx, int32_t n, const int32_t* ids, int32_t total_lights);
 
 /* page-locked host memory for callers that want sgi_set_mesh / sgi_read to be true async DMA
  * (the reference keeps its Mesh arrays in malloc'd memory and lets the GL driver stage them) */

@@ -99,10 +99,14 @@ def main():
         print(f"C ABI tiles x{world}: sgi_gather(visibility) == un-sharded image: {same} (rows {r0}..{r1} on rank 0)", flush=True)
     app.close()
     # lights: 16 lights, fused many-light path (primitive-id strips all-gathered, partial sums reduce-scattered + divided)
-    for (Wl, Hl) in ((2048, 1152), (1000, 563)):        # the second height does not divide by the rank count: padded strips
+    # (exchange of lit masks - the default up to 32 lights - also with a shadow intensity that is not a dyadic fraction, where only
+    #  the masks reproduce the un-sharded accumulation order; and of float partial sums)
+    for (Wl, Hl, masks, si) in ((2048, 1152, 1, None), (1000, 563, 1, 0.3), (1000, 563, 0, None)):   # 563 rows do not divide by the rank count: padded strips
         app = hostapi.App(local)
         app.load_scene(scenes.write_config("c5_many_light")); app.configure(Wl, Hl, 1024); app.set_technique("montecarlo")
-        app.set(numberOfSamples=16, lightSourceSize=16)
+        app.set(numberOfSamples=16, lightSourceSize=16, commMasks=masks)
+        if si is not None:
+            app.set(shadowIntensity=si)
         app.display("soft_shadow_mapping")
         full = app.context().read("visibility")
         app.set(fusedMonteCarlo=1)
@@ -118,7 +122,7 @@ def main():
         mine = ctx.read("visibility")[r0:r1]
         same = bool(np.array_equal(mine.view(np.uint32), full[r0:r1].view(np.uint32)))
         ok &= same
-        print(f"C ABI lights x{world} {Wl}x{Hl}, rank {rank}: rows {r0}..{r1} of sgi_reduce_lights == un-sharded frame: {same}", flush=True)
+        print(f"C ABI lights x{world} {Wl}x{Hl} {'masks' if masks else 'float sums'}{'' if si is None else ' si=%g' % si}, rank {rank}: rows {r0}..{r1} of sgi_reduce_lights == un-sharded frame: {same}", flush=True)
         app.close()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -97,6 +97,64 @@ def test_comm_single_rank_strip_gather_and_reduce():
         c.close()
 
 
+@pytest.mark.parametrize("si", [0.25, 0.3])
+def test_lit_masks_single_rank_and_two_half_sets(si):
+    """params.multi_partial = 2: the many-light pass writes which lights reach each pixel (one bit per light of the whole set), the
+    exchange sums the ranks' masks and the strip's visibility is accumulated in the reference's light order.  Checked here without
+    a second GPU: (a) one rank, all lights: sgi_reduce_lights gives the un-sharded frame; (b) the lights dealt to two contexts
+    (odd / even): the union of their masks, replayed on the host in light order, gives the un-sharded frame as well - also for a
+    shadow intensity that is not a dyadic fraction, where partial float sums would depend on how the lights were dealt."""
+    from globalillumination_b200 import capi
+    sc = util.scene("teapot")
+    W, H, S, n_l = 256, 145, 128, 11
+    c = capi.Context(0)
+    try:
+        c.comm_init(capi.comm_unique_id(), 0, 1)
+        po, pg, fm, mvp, mvpb = _many_light_frame(c, sc, W, H, S, n_l, shadow_intensity=si)
+        c.render_shadow_map(); c.render_gbuffer(); c.compute_visibility()
+        full = c.read("visibility")
+        _, pg_m = util.params_pair("multi_hard", S, multi_partial=2, multi_fused=1, shadow_intensity=si)
+        c.set_params(pg_m)
+        c.set_light_ids(np.arange(n_l), n_l)
+        c.render_prim_ids(); c.gather("prim_id"); c.compute_visibility(); c.reduce_lights(n_l)
+        assert util.bits_equal(c.read("visibility"), full)
+        mask_all = c.read_light_mask()
+        fg = c.read("prim_id") != 0xFFFFFFFF
+        assert (mask_all[~fg] == 0).all() and (mask_all >> n_l == 0).all()
+        # (b) two half sets on two contexts of this device
+        union = np.zeros((H, W), np.uint32)
+        for part in (np.arange(0, n_l, 2), np.arange(1, n_l, 2)):
+            d = capi.Context(0)
+            try:
+                d.set_mesh(sc["xyz"], sc["nrm"], sc["idx"])
+                d.set_camera(fm["cam_mvp"], fm["cam_mv"], fm["normal_matrix"], W, H)
+                d.set_multi_light_common(mvpb[-1])                       # the common term comes from the last light of the WHOLE set
+                d.set_lights(mvp[part], mvpb[part], fm["light_pos_shading"], S, S)
+                d.set_params(pg_m)
+                d.set_light_ids(part, n_l)
+                d.render_shadow_map(); d.render_prim_ids(); d.compute_visibility()
+                m = d.read_light_mask()
+                assert (m & union == 0).all()                            # disjoint bits: the byte sum of the exchange is their union
+                union |= m
+            finally:
+                d.close()
+        assert np.array_equal(union, mask_all)
+        acc = np.zeros((H, W), np.float32); cnt = np.float32(0)
+        for l in range(n_l):
+            acc = (acc + np.where((union >> np.uint32(l)) & 1, np.float32(1.0), np.float32(si)).astype(np.float32)).astype(np.float32)
+            cnt = np.float32(cnt + np.float32(1.0))
+        replay = np.where(full != 0, acc / cnt, np.float32(0)).astype(np.float32)
+        assert util.bits_equal(np.where(full != 0, full, np.float32(0)), replay)
+        # a mask pass without light indices for the current lights is refused
+        c.set_lights(mvp[:3], mvpb[:3], fm["light_pos_shading"], S, S)
+        c.render_shadow_map()
+        with pytest.raises(capi.SgiError):
+            c.compute_visibility()
+        c.comm_destroy()
+    finally:
+        c.close()
+
+
 def test_two_contexts_on_one_device_and_kernel_attributes_per_context():
     """function attributes (dynamic shared memory opt-in) are per device; every context configures its own.  With one
     GPU this checks two contexts in one process side by side; with two GPUs the second context lives on device 1."""
