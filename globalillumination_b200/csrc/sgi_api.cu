@@ -14,7 +14,7 @@
 
 static void sync_all_streams(sgi_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
-  cudaStream_t others[] = {ctx->aux_stream, ctx->vis_stream, ctx->copy_stream, ctx->upload_stream, ctx->lane_stream[0], ctx->lane_stream[1], ctx->lane_stream[2], ctx->comm_stream};
+  cudaStream_t others[] = {ctx->aux_stream, ctx->vis_stream, ctx->copy_stream, ctx->upload_stream, ctx->lane_stream[0], ctx->lane_stream[1], ctx->lane_stream[2], ctx->comm_stream, ctx->comm_stream2};
   for (cudaStream_t s : others) if (s) cudaStreamSynchronize(s);
 }
 
@@ -188,6 +188,7 @@ int sgi_create(sgi_ctx** out, int device) {
   { const char* e = getenv("SGI_PDL"); if (e) ctx->pdl = e[0] != '0'; }
   { const char* e = getenv("SGI_TILE_BIN_BIG"); if (e) ctx->tile_bin_big = atoi(e); }
   { const char* e = getenv("SGI_TILE_BIN_BIG_WORK"); if (e) ctx->tile_bin_big_work = atoi(e); }
+  { const char* e = getenv("SGI_TILE_FEW_WALK"); if (e) ctx->tile_few_walk = e[0] != '0'; }
   { const char* e = getenv("SGI_SV_SPLIT_LISTS"); if (e) ctx->sv_split_lists = e[0] != '0'; }
   { const char* e = getenv("SGI_TILE_DIRECT"); if (e) ctx->tile_direct = atoi(e); }
   { const char* e = getenv("SGI_TILE_STATIC"); if (e) ctx->tile_static_items = e[0] - '0'; }
@@ -224,6 +225,8 @@ int sgi_destroy(sgi_ctx* ctx) {
   for (int b = 0; b < SGI_BUF_COUNT_; b++) { if (ctx->buf[b]) cudaFree(ctx->buf[b]); if (ctx->alt[b]) cudaFree(ctx->alt[b]); }
   sgi_comm_destroy(ctx);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->comm_stream2) cudaStreamDestroy(ctx->comm_stream2);
+  if (ctx->d_light_gid) cudaFree(ctx->d_light_gid);
   if (ctx->ev_comm_in) cudaEventDestroy(ctx->ev_comm_in);
   for (int b = 0; b < SGI_BUF_COUNT_; b++) if (ctx->ev_comm_done[b]) cudaEventDestroy(ctx->ev_comm_done[b]);
   for (int b = 0; b < SGI_EDT_NBUF; b++) if (ctx->edt_buf[b]) cudaFree(ctx->edt_buf[b]);
@@ -668,7 +671,6 @@ int sgi_render_gbuffer(sgi_ctx* ctx) {
   for (int b : {SGI_BUF_GBUF_POS, SGI_BUF_GBUF_NRM, SGI_BUF_CAM_DEPTH, SGI_BUF_GBUF_ALBEDO}) sgi_wait_comm(ctx, b, st);
   // a fused many-light pass still resolving positions from this scratch set's records (previous frame, visibility stream)
   if (ctx->rec_reader >= 0) { SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_vis[ctx->rec_reader], 0)); ctx->rec_reader = -1; }
-  sgi_wait_comm(ctx, SGI_BUF_LIGHT_MASK, st);            // (the mask resolve of the previous frame reads the records and the ids too)
   ctx->ids_valid = false;
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
   SgiRasterJob job;
@@ -714,7 +716,6 @@ int sgi_render_prim_ids(sgi_ctx* ctx) {
   }
   // the previous frame's fused many-light pass reads this buffer and this scratch set's records on the visibility stream
   if (ctx->rec_reader >= 0) { SGI_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_vis[ctx->rec_reader], 0)); ctx->rec_reader = -1; }
-  sgi_wait_comm(ctx, SGI_BUF_LIGHT_MASK, st);            // (the mask resolve of the previous frame reads the records and the ids too)
   sgi_wait_reads_of(ctx, SGI_BUF_PRIM_ID, st);
   sgi_wait_comm(ctx, SGI_BUF_PRIM_ID, st);
   int slot = sgi_timing_begin(ctx, SGI_PASS_GBUFFER, st);
@@ -941,6 +942,7 @@ int sgi_synchronize(sgi_ctx* ctx) {
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   SGI_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   if (ctx->comm_stream) SGI_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+  if (ctx->comm_stream2) SGI_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream2));
   for (int b = 0; b < SGI_BUF_COUNT_; b++) ctx->comm_pending[b] = false;
   for (int k = 0; k < 4; k++) ctx->read_pending[k] = false;
   if (ctx->timing) sgi_timing_drain(ctx);
@@ -1026,6 +1028,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
   else if (!strcmp(name, "pdl")) ctx->pdl = value ? 1 : 0;
+  else if (!strcmp(name, "tile_few_walk")) ctx->tile_few_walk = value ? 1 : 0;
   else if (!strcmp(name, "sv_split_lists")) ctx->sv_split_lists = value ? 1 : 0;
   else if (!strcmp(name, "tile_direct")) ctx->tile_direct = value;
   else if (!strcmp(name, "tile_bin_big")) ctx->tile_bin_big = value;

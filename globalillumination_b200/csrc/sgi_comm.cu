@@ -8,6 +8,7 @@
 // link-time dependency on it and loads on machines without NCCL.  The buffers that take part are padded to nranks equal strips
 // (ceil(H / nranks) rows each), so every exchange is ONE collective on the buffer itself: no packing, no staging copy.
 #include <dlfcn.h>
+#include <algorithm>
 #include <cstring>
 #include <nccl.h>
 #include "sgi_internal.cuh"
@@ -19,6 +20,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;     // NCCL >= 2.18; optional
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -34,6 +36,7 @@ NcclApi& nccl() {
       api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.dl, "ncclGetUniqueId");
       api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.dl, "ncclCommInitRank");
       api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.dl, "ncclCommDestroy");
+      api.CommSplit = (decltype(api.CommSplit))dlsym(api.dl, "ncclCommSplit");
       api.AllGather = (decltype(api.AllGather))dlsym(api.dl, "ncclAllGather");
       api.ReduceScatter = (decltype(api.ReduceScatter))dlsym(api.dl, "ncclReduceScatter");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.dl, "ncclGetErrorString");
@@ -99,6 +102,17 @@ int sgi_comm_init(sgi_ctx* ctx, const void* id128, size_t bytes, int32_t rank, i
   SGI_NCCL(ctx, nccl().CommInitRank(&comm, nranks, id, rank));
   ctx->nccl_comm = comm; ctx->comm_rank = rank; ctx->comm_n = nranks;
   if (!ctx->comm_stream) SGI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  // The reductions get a communicator and a stream of their own (ncclCommSplit, every rank in one colour): collectives of one
+  // communicator run in issue order, and a frame's id gather must not queue behind the previous frame's reduction - that chain
+  // (accumulate -> reduce -> gather -> accumulate) was the frame time at 8 GPUs.  Without ncclCommSplit: one communicator for both.
+  ctx->nccl_comm2 = nullptr;
+  if (nranks > 1 && nccl().CommSplit) {
+    ncclComm_t c2 = nullptr;
+    if (nccl().CommSplit(comm, 0, rank, &c2, nullptr) == ncclSuccess && c2) {
+      ctx->nccl_comm2 = c2;
+      if (!ctx->comm_stream2) SGI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream2, cudaStreamNonBlocking));
+    }
+  }
   if (!ctx->ev_comm_in) SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_in, cudaEventDisableTiming));
   // the strip layout depends on the rank count: targets sized before this call are re-made (padded) by the next sgi_set_camera
   ctx->W = ctx->H = 0; ctx->has_camera = false; ctx->gbuffer_valid = false; ctx->ids_valid = false;
@@ -111,6 +125,9 @@ int sgi_comm_destroy(sgi_ctx* ctx) {
     cudaSetDevice(ctx->device);
     sgi_synchronize(ctx);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->comm_stream2) cudaStreamSynchronize(ctx->comm_stream2);
+    if (ctx->nccl_comm2) nccl().CommDestroy((ncclComm_t)ctx->nccl_comm2);
+    ctx->nccl_comm2 = nullptr;
     nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
   }
@@ -130,12 +147,13 @@ int sgi_comm_strip(sgi_ctx* ctx, int32_t rank, int32_t* row0, int32_t* row1) {
 
 // Orders the communication stream behind everything that may have produced `which`: the main stream as queued so far, the
 // G-buffer / id pass on the auxiliary stream, the shadow pass on the visibility stream.
-static int comm_begin(sgi_ctx* ctx, int which) {
+static int comm_begin(sgi_ctx* ctx, int which, cudaStream_t cs) {
   SGI_CUDA(ctx, cudaEventRecord(ctx->ev_comm_in, ctx->stream));
-  SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comm_in, 0));
-  if (ctx->gbuf_in_flight) SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_gbuf_done, 0));
-  if (ctx->vis_in_flight && ctx->vis_last >= 0) SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_vis[ctx->vis_last], 0));
-  sgi_wait_reads_of(ctx, which, ctx->comm_stream);       // an asynchronous copy-out of the buffer still in flight
+  SGI_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_comm_in, 0));
+  if (ctx->gbuf_in_flight) SGI_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_gbuf_done, 0));
+  if (ctx->vis_in_flight && ctx->vis_last >= 0) SGI_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_vis[ctx->vis_last], 0));
+  sgi_wait_comm(ctx, which, cs);                         // an earlier collective on the same buffer (it may be on the other stream)
+  sgi_wait_reads_of(ctx, which, cs);                     // an asynchronous copy-out of the buffer still in flight
   if (!ctx->ev_comm_done[which]) SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_done[which], cudaEventDisableTiming));
   return SGI_OK;
 }
@@ -148,7 +166,7 @@ int sgi_gather(sgi_ctx* ctx, int32_t which) {
   const size_t strip = (size_t)sgi_strip_rows(ctx) * ctx->W * eb;
   if (!ctx->buf[which] || ctx->buf_bytes[which] < strip * ctx->comm_n) { ctx->err = "sgi_gather: buffer not produced yet (or sized before sgi_comm_init)"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
-  int rc = comm_begin(ctx, which);
+  int rc = comm_begin(ctx, which, ctx->comm_stream);
   if (rc) return rc;
   char* base = (char*)ctx->buf[which];
   SGI_NCCL(ctx, nccl().AllGather(base + strip * ctx->comm_rank, base, strip, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->comm_stream));
@@ -164,10 +182,21 @@ int sgi_set_light_ids(sgi_ctx* ctx, int32_t n, const int32_t* ids, int32_t total
     if (ids[k] < 0 || ids[k] >= total_lights || ((seen >> ids[k]) & 1u)) { ctx->err = "sgi_set_light_ids: indices must be distinct and below the total"; return SGI_ERR_INVALID; }
     seen |= 1u << ids[k];
   }
-  ctx->light_gid.assign(ids, ids + n);
   ctx->mask_total = total_lights;
+  if ((int)ctx->light_gid.size() == n && std::equal(ids, ids + n, ctx->light_gid.begin()) && ctx->d_light_gid) return SGI_OK;     // (called every frame)
+  cudaSetDevice(ctx->device);
+  if (!ctx->d_light_gid) SGI_CUDA(ctx, cudaMalloc((void**)&ctx->d_light_gid, 32 * sizeof(int)));
+  sgi_join_vis(ctx);                                             // a pass still reading the previous table
+  ctx->light_gid.assign(ids, ids + n);
+  int tmp[32] = {0};
+  for (int k = 0; k < n; k++) tmp[k] = ids[k];
+  SGI_CUDA(ctx, cudaMemcpyAsync(ctx->d_light_gid, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
+  SGI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // tmp is on the stack
   return SGI_OK;
 }
+
+static cudaStream_t reduce_stream(sgi_ctx* ctx) { return ctx->nccl_comm2 ? ctx->comm_stream2 : ctx->comm_stream; }
+static ncclComm_t reduce_comm(sgi_ctx* ctx) { return (ncclComm_t)(ctx->nccl_comm2 ? ctx->nccl_comm2 : ctx->nccl_comm); }
 
 // light sharding with lit masks: the planes of all ranks are summed (ncclReduceScatter on bytes, disjoint bits), then this rank
 // accumulates the visibility of its strip from the union (k_mask_resolve)
@@ -180,10 +209,10 @@ static int reduce_light_masks(sgi_ctx* ctx, int32_t total_lights) {
   cudaStream_t st;
   int rc;
   if (ctx->comm_n > 1) {
-    st = ctx->comm_stream;
+    st = reduce_stream(ctx);
     if (ctx->buf_bytes[which] < part * ctx->comm_n) { ctx->err = "sgi_reduce_lights: mask buffer sized before sgi_comm_init"; return SGI_ERR_INVALID; }
-    if ((rc = comm_begin(ctx, which))) return rc;
-    SGI_NCCL(ctx, nccl().ReduceScatter(base, base + part * ctx->comm_rank, part, ncclUint8, ncclSum, (ncclComm_t)ctx->nccl_comm, st));
+    if ((rc = comm_begin(ctx, which, st))) return rc;
+    SGI_NCCL(ctx, nccl().ReduceScatter(base, base + part * ctx->comm_rank, part, ncclUint8, ncclSum, reduce_comm(ctx), st));
     sgi_wait_reads_of(ctx, SGI_BUF_VISIBILITY, st);              // the strip's visibility is written on this stream
     sgi_wait_comm(ctx, SGI_BUF_VISIBILITY, st);
   } else {
@@ -196,7 +225,7 @@ static int reduce_light_masks(sgi_ctx* ctx, int32_t total_lights) {
   if (ctx->comm_n > 1) {
     for (int b : {which, (int)SGI_BUF_VISIBILITY}) {
       if (!ctx->ev_comm_done[b]) SGI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_done[b], cudaEventDisableTiming));
-      SGI_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done[b], ctx->comm_stream));
+      SGI_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done[b], st));
       ctx->comm_pending[b] = true;
     }
   }
@@ -211,12 +240,12 @@ int sgi_reduce_lights(sgi_ctx* ctx, int32_t total_lights) {
   const int which = SGI_BUF_VISIBILITY;
   const size_t strip = (size_t)sgi_strip_rows(ctx) * ctx->W;       // floats
   float* base = (float*)ctx->buf[which];
-  cudaStream_t st = ctx->comm_n > 1 ? ctx->comm_stream : nullptr;
+  cudaStream_t st = ctx->comm_n > 1 ? reduce_stream(ctx) : nullptr;
   if (ctx->comm_n > 1) {
     if (ctx->buf_bytes[which] < strip * ctx->comm_n * 4) { ctx->err = "sgi_reduce_lights: visibility buffer sized before sgi_comm_init"; return SGI_ERR_INVALID; }
-    int rc = comm_begin(ctx, which);
+    int rc = comm_begin(ctx, which, st);
     if (rc) return rc;
-    SGI_NCCL(ctx, nccl().ReduceScatter(base, base + strip * ctx->comm_rank, strip, ncclFloat, ncclSum, (ncclComm_t)ctx->nccl_comm, st));
+    SGI_NCCL(ctx, nccl().ReduceScatter(base, base + strip * ctx->comm_rank, strip, ncclFloat, ncclSum, reduce_comm(ctx), st));
   } else {
     int rc = sgi_join_vis(ctx);                                     // one rank: divide on the context's stream
     if (rc) return rc;
@@ -231,7 +260,7 @@ int sgi_reduce_lights(sgi_ctx* ctx, int32_t total_lights) {
   }
   SGI_CUDA(ctx, cudaGetLastError());
   if (ctx->comm_n > 1) {
-    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done[which], ctx->comm_stream));
+    SGI_CUDA(ctx, cudaEventRecord(ctx->ev_comm_done[which], st));
     ctx->comm_pending[which] = true;
   }
   return SGI_OK;

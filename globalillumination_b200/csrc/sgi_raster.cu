@@ -113,6 +113,7 @@ struct SetupBinArgs {
   int2* spill; int spill_cap;                    // (tile, record) pairs that found their tile's list full (counters[5] = count)
   int32_t* big_list;                             // records spanning > big_tiles tiles: not binned by the set-up kernel (counters[3] = count); with k_bin_big
                                                  // the ones beyond huge_tiles are listed from the far end of the buffer instead (counters[6] = count)
+  int few_tiles;                                 // the pass has at most 128 tiles: the CTA's larger records are walked tile-major (one atomic per warp and tile)
   int big_tiles, huge_tiles, big_cap;            // thresholds of the two classes (huge_tiles = INT_MAX without k_bin_big), entries the buffer holds
   const unsigned int* tile_zmax;                 // shadow volumes: largest scene depth of each tile (float bits), or null
 };
@@ -492,6 +493,42 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
   // ---- larger records of this CTA, flattened: inclusive prefix of their tile counts, then every thread takes pairs
   const int nq = min(q_n, SGI_SB_QCAP);
   if (nq == 0) return;
+  if (a.few_tiles) {
+    // A pass of few tiles (shadow volumes at 640x480: 80 tiles, 1.5 M pairs): the appends of the whole GPU meet on a few dozen
+    // cursors, and the pair walk below spends its time waiting for contended atomics (45 % of the kernel's stall samples).  Here
+    // the walk is tile-major - a lane per record, all lanes on the same tile - so a warp reserves its entries of a tile with ONE
+    // atomic.  More (cheap) overlap tests, a thirtieth of the atomics.  Four tiles in flight per trip.
+    const int gx = a.tx1 - a.tx0 + 1, ntile = gx * (a.ty1 - a.ty0 + 1);
+    for (int rb = (tid >> 5) * 32; rb < nq; rb += SGI_SB_THREADS) {
+      const int ri = rb + lane;
+      const bool live = ri < nq;
+      const BinRec b = q[live ? ri : 0];
+      SgiRec rr;
+      rr.X0 = b.X0; rr.Y0 = b.Y0; rr.X1 = b.X1; rr.Y1 = b.Y1; rr.X2 = b.X2; rr.Y2 = b.Y2;
+      rr.z0 = b.z0; rr.dz1 = b.dz1; rr.dz2 = b.dz2; rr.ia = b.ia; rr.zoff = b.zoff;
+      const int bx1 = b.bx0 + b.bw - 1, by1 = b.by0 + b.nt / b.bw - 1;
+      for (int t0 = 0; t0 < ntile; t0 += 4) {
+        unsigned hits[4]; int pos[4], tl[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int t = t0 + u, ty = a.ty0 + t / gx, tx = a.tx0 + t % gx;
+          const bool hit = live && t < ntile && tx >= b.bx0 && tx <= bx1 && ty >= b.by0 && ty <= by1 && tile_overlaps(rr, tx, ty, W, H) &&
+                           !tile_behind_scene(rr, tx, ty, W, H, a.tile_zmax, a.tiles_x);
+          hits[u] = __ballot_sync(0xffffffffu, hit);
+          tl[u] = ty * a.tiles_x + tx;
+          pos[u] = 0;
+          if (hits[u] && lane == __ffs(hits[u]) - 1) pos[u] = atomicAdd(&a.tile_cnt[tl[u]], __popc(hits[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (hits[u]) {
+            const int p0 = __shfl_sync(0xffffffffu, pos[u], __ffs(hits[u]) - 1);
+            if ((hits[u] >> lane) & 1u) list_append(a, tl[u], p0 + __popc(hits[u] & ((1u << lane) - 1u)), b.slot);
+          }
+      }
+    }
+    return;
+  }
   {
     const int i0 = 2 * tid, i1 = 2 * tid + 1;
     const int c0 = i0 < nq ? q[i0].nt : 0, c1 = i1 < nq ? q[i1].nt : 0;
@@ -1855,6 +1892,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   oa.big_binned = bin_big ? 1 : 0;
   // with k_bin_big the set-up kernel keeps only the records of up to 16 tiles for its own walk; 17 .. 2048 tiles: a warp each,
   // beyond: all CTAs together.  Without it: records beyond SGI_BIG_TILES are tested by every tile CTA.
+  sa.few_tiles = (ctx->tile_few_walk && n_rect_tiles <= 128) ? 1 : 0;
   sa.big_tiles = bin_big ? 16 : SGI_BIG_TILES; sa.huge_tiles = bin_big ? 2048 : 0x7FFFFFFF; sa.big_cap = sc.rec_cap_tris * 7 + 16;
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
   k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);

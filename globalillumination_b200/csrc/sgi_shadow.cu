@@ -36,7 +36,8 @@ struct VisArgs {
   const unsigned int* ids; const SgiRec* rec; const SgiRecAttr* attr; const int32_t* ovf_base;
   // multi_partial == 2: the lights this rank sampled, one bit each at the light's index in the whole set, 8 lights per byte plane,
   // laid out [rank strip][plane][strip pixels] so that every rank's part is contiguous (one in-place reduce-scatter)
-  unsigned char* mask; int mask_planes, mask_rows; size_t mask_strip; unsigned char gid[32]; int mask_total;
+  unsigned char* mask; int mask_planes, mask_rows; size_t mask_strip; const int* gid; int mask_total;
+  int own_r0, own_r1;                                                 // rows of this rank's strip (they receive the discard decision)
 };
 
 struct Smap { const float* __restrict__ d; int w, h; float fw, fh; };
@@ -800,14 +801,20 @@ __device__ __forceinline__ size_t mask_index(const VisArgs& a, int x, int y, int
   return ((size_t)rk * a.mask_planes + p) * a.mask_strip + (size_t)(y - rk * a.mask_rows) * a.W + x;
 }
 
+// MASK = false: AccurateSoftShadow.frag's accumulation (the sum, or with multi_partial = 1 the un-normalised sum).  MASK = true
+// (multi_partial = 2): which of this rank's lights reach the pixel, as bits at the lights' indices in the whole set; the rank's own
+// strip of the visibility target additionally receives the discard decision (0 = discarded, 1 = a fragment), which is all
+// k_mask_resolve needs besides the masks.
+template <bool MASK>
 __global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a) {
   int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;
-  const bool as_mask = a.p.multi_partial == 2;
   float vx, vy, vz;
-  if (!fused_position(a, x, y, o, vx, vy, vz)) {
-    if (as_mask) { for (int p = 0; p < a.mask_planes; p++) a.mask[mask_index(a, x, y, p)] = 0; }
+  const bool valid = fused_position(a, x, y, o, vx, vy, vz);
+  if (MASK && y >= a.own_r0 && y < a.own_r1) a.vis[o] = valid ? 1.0f : 0.0f;
+  if (!valid) {
+    if (MASK) { for (int p = 0; p < a.mask_planes; p++) a.mask[mask_index(a, x, y, p)] = 0; }
     else a.vis[o] = 0.0f;
     return;
   }
@@ -825,23 +832,25 @@ __global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a)
     sgi_div3(sx, sy, sz, sw, sx, sy, sz);
     Smap s = {a.sm + a.layer * l, a.SW, a.SH, a.fw, a.fh};
     float dfl = sm_fetch(s, sx, sy);
-    if (as_mask) { if (sz <= dfl) lit |= 1u << a.gid[l]; continue; }
-    accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
-    count += accFactor;
+    if (MASK) { if (sz <= dfl) lit |= 1u << __ldg(&a.gid[l]); }
+    else {
+      accShadow += ((sz <= dfl) ? 1.0f : a.p.shadow_intensity) * accFactor;
+      count += accFactor;
+    }
   }
-  if (as_mask) { for (int p = 0; p < a.mask_planes; p++) a.mask[mask_index(a, x, y, p)] = (unsigned char)((lit >> (8 * p)) & 255u); }
+  if (MASK) { for (int p = 0; p < a.mask_planes; p++) a.mask[mask_index(a, x, y, p)] = (unsigned char)((lit >> (8 * p)) & 255u); }
   else a.vis[o] = a.p.multi_partial ? accShadow : accShadow / count;
 }
 
 // The lit masks of all ranks, summed (disjoint bits: the sum is their union), turned into the visibility of this rank's strip: the
 // accumulation loop of AccurateSoftShadow.frag:100-127 replayed over the whole light set in its own order, so the result has the
 // bits of the un-sharded frame for every shadow intensity (partial float sums would depend on how the lights were dealt).
+// Reads nothing of the camera pass: the discard decision was left in the strip by this rank's own accumulation kernel.
 __global__ void __launch_bounds__(256) k_mask_resolve(const VisArgs a) {
   int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;
-  float vx, vy, vz;
-  if (!fused_position(a, x, y, o, vx, vy, vz)) { a.vis[o] = 0.0f; return; }
+  if (a.vis[o] == 0.0f) return;                                  // discarded fragment: the target keeps its 0
   unsigned int lit = 0u;
   for (int p = 0; p < a.mask_planes; p++) lit |= (unsigned int)a.mask[mask_index(a, x, y, p)] << (8 * p);
   float accShadow = 0.0f, count = 0.0f;
@@ -945,7 +954,10 @@ static void fill_mask_args(const sgi_ctx* ctx, VisArgs& a) {
   a.mask = (unsigned char*)ctx->buf[SGI_BUF_LIGHT_MASK];
   a.mask_total = ctx->mask_total; a.mask_planes = (ctx->mask_total + 7) / 8;
   a.mask_rows = sgi_strip_rows(ctx); a.mask_strip = (size_t)a.mask_rows * ctx->W;
-  for (int l = 0; l < 32; l++) a.gid[l] = (unsigned char)(l < (int)ctx->light_gid.size() ? ctx->light_gid[l] : 0);
+  a.gid = ctx->d_light_gid;
+  const int rk = ctx->comm_n > 1 ? ctx->comm_rank : 0;
+  a.own_r0 = rk * a.mask_rows < ctx->H ? rk * a.mask_rows : ctx->H;
+  a.own_r1 = (rk + 1) * a.mask_rows < ctx->H ? (rk + 1) * a.mask_rows : ctx->H;
 }
 
 // sgi_reduce_lights in mask mode: visibility of rows [r0, r1) from the summed masks
@@ -955,8 +967,6 @@ int sgi_mask_resolve_run(sgi_ctx* ctx, int r0, int r1, cudaStream_t st) {
   memset(&a, 0, sizeof(a));
   a.p = ctx->params;
   a.W = ctx->W; a.H = ctx->H; a.rx0 = 0; a.ry0 = r0; a.rx1 = ctx->W; a.ry1 = r1;
-  const SgiScratch& sc = ctx->scratch[1];
-  a.ids = (const unsigned int*)ctx->buf[SGI_BUF_PRIM_ID]; a.rec = sc.d_rec; a.attr = sc.d_attr; a.ovf_base = sc.d_ovf_base;
   a.vis = (float*)ctx->buf[SGI_BUF_VISIBILITY];
   fill_mask_args(ctx, a);
   dim3 block(32, 8), grid((ctx->W + 31) / 32, (r1 - r0 + 7) / 8);
@@ -1105,7 +1115,7 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
   for (int k = 0; k < SGI_MAX_PCF_TAPS; k++) { a.pcf_off[k] = ctx->pcf_off[k]; a.rpcf_off[k] = ctx->rpcf_off[k]; }
   a.trans = (const float4*)ctx->d_light_trans; a.N = ctx->N; a.layer = (size_t)ctx->SW * ctx->SH;
   a.ids = nullptr; a.rec = nullptr; a.attr = nullptr; a.ovf_base = nullptr;
-  a.mask = nullptr; a.mask_planes = 0; a.mask_rows = 1; a.mask_strip = 0; a.mask_total = 0;
+  a.mask = nullptr; a.mask_planes = 0; a.mask_rows = 1; a.mask_strip = 0; a.mask_total = 0; a.gid = nullptr; a.own_r0 = a.own_r1 = 0;
   a.dmin = nullptr; a.dmax = nullptr; a.mm_w = 0; a.mm_limit = 0.0f; a.pcf_reach = 1.0e30f; a.bs_reach = 1.0e30f;
   a.pcss_early_out = (ctx->pcss_early_out && ctx->params.light_source_radius >= 0 && ctx->params.z_near >= 0 && ctx->params.kernel_size > 0 &&
                       ctx->params.blocker_search_size <= SGI_MAX_PCF_TAPS && !ctx->vis_staged) ? 1 : 0;
@@ -1222,7 +1232,8 @@ int sgi_shadow_run(sgi_ctx* ctx, cudaStream_t stream) {
         const SgiScratch& sc = ctx->scratch[1];          // the camera pass's records (sgi_render_prim_ids)
         a.ids = (const unsigned int*)ctx->buf[SGI_BUF_PRIM_ID]; a.rec = sc.d_rec; a.attr = sc.d_attr; a.ovf_base = sc.d_ovf_base;
         if (ctx->params.multi_partial == 2) fill_mask_args(ctx, a);
-        k_visibility_multi_fused<<<grid, block, 0, st>>>(a);
+        if (ctx->params.multi_partial == 2) k_visibility_multi_fused<true><<<grid, block, 0, st>>>(a);
+        else k_visibility_multi_fused<false><<<grid, block, 0, st>>>(a);
       } else k_visibility_multi<<<grid, block, 0, st>>>(a);
       break;
     case SGI_TECH_RBSSM: {

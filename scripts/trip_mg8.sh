@@ -1,10 +1,10 @@
 #!/bin/bash
 # 8-GPU trip: N=1 record, then the bench at N GPUs (frame replicas headline + the `sharded` record) and the multi-GPU parity check
 # (scripts/pcie_probe.py, the host I/O probe, is run separately: profiles/r2_pcie_probe.txt)
-n=${1:-8}; tag=${2:-mg8}
+n=${1:-8}; tag=${2:-mg8}; mids=${3:-"2 4"}
 mkdir -p gpurun_out
 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
-for k in 2 4 $n; do
+for k in $mids $n; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $k --master-addr 127.0.0.1 --master-port 2961$k bench.py --gpus $k --steps 200 --warmup 5 > gpurun_out/${tag}_bench_n${k}.json 2> gpurun_out/${tag}_bench_n${k}.err
 done
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29641 scripts/multi_gpu_check.py > gpurun_out/${tag}_check.txt 2>&1

@@ -155,13 +155,15 @@ def test_c4_tree_shadow_volumes_at_1080p_bit_exact(ctx, kw):
 @pytest.mark.parametrize("name,W,H,kw", [("tree", 640, 480, dict(sv_silhouette=1)), ("tree", 320, 240, dict(sv_silhouette=1, sv_zfail=1)), ("raptor", 333, 217, dict())])
 def test_hot_tiles_shared_by_list_segment_or_by_region_count_the_same(ctx, name, W, H, kw):
     """Option "sv_split_lists": hot tiles shared between CTAs by list segment (counts added atomically, the default) or by
-    sub-region: identical counts and stencil values."""
+    sub-region; option "tile_few_walk": the binner's tile-major walk for passes of few tiles or the pair walk: identical counts
+    and stencil values."""
     sc = util.scene(name)
     _, _, cnt1, st1, *_ = _gpu_counts(ctx, sc, W, H, **kw)
-    ctx.set_option("sv_split_lists", 0)
-    try:
-        _, _, cnt0, st0, *_ = _gpu_counts(ctx, sc, W, H, **kw)
-    finally:
-        ctx.set_option("sv_split_lists", 1)
-    assert np.array_equal(cnt0, cnt1) and np.array_equal(st0, st1)
+    for option in ("sv_split_lists", "tile_few_walk"):
+        ctx.set_option(option, 0)
+        try:
+            _, _, cnt0, st0, *_ = _gpu_counts(ctx, sc, W, H, **kw)
+        finally:
+            ctx.set_option(option, 1)
+        assert np.array_equal(cnt0, cnt1) and np.array_equal(st0, st1), option
     assert (cnt1 != 0).mean() > 0.005
