@@ -642,7 +642,10 @@ namespace {
 // VA / VB: compile-time tap counts of the specialised variants (PCF: VA = taps per axis; PCSS: VA = blocker taps,
 // VB = filter taps; 0 = generic run-time loops)
 template <int TECH, int VA, int VB>
-__global__ void __launch_bounds__(256) k_visibility(const VisArgs a) {
+#ifndef SGI_VIS_MIN_CTAS
+#define SGI_VIS_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(256, SGI_VIS_MIN_CTAS) k_visibility(const VisArgs a) {
   int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;
@@ -805,8 +808,9 @@ __device__ __forceinline__ size_t mask_index(const VisArgs& a, int x, int y, int
 // (multi_partial = 2): which of this rank's lights reach the pixel, as bits at the lights' indices in the whole set; the rank's own
 // strip of the visibility target additionally receives the discard decision (0 = discarded, 1 = a fragment), which is all
 // k_mask_resolve needs besides the masks.
+// (8 CTAs per SM = 32 registers: the kernel waits on its taps, and at 34 registers - 6 CTAs - it ran 20 % longer)
 template <bool MASK>
-__global__ void __launch_bounds__(256) k_visibility_multi_fused(const VisArgs a) {
+__global__ void __launch_bounds__(256, 8) k_visibility_multi_fused(const VisArgs a) {
   int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;
