@@ -1028,6 +1028,7 @@ int sgi_set_option(sgi_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "pcss_early_out")) ctx->pcss_early_out = value ? 1 : 0;
   else if (!strcmp(name, "tile_bulk_flush")) ctx->tile_bulk_flush = value ? 1 : 0;
   else if (!strcmp(name, "pdl")) ctx->pdl = value ? 1 : 0;
+  else if (!strcmp(name, "comm_split")) ctx->comm_split = value ? 1 : 0;
   else if (!strcmp(name, "tile_few_walk")) ctx->tile_few_walk = value ? 1 : 0;
   else if (!strcmp(name, "sv_split_lists")) ctx->sv_split_lists = value ? 1 : 0;
   else if (!strcmp(name, "tile_direct")) ctx->tile_direct = value;

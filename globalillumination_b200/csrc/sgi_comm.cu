@@ -102,11 +102,11 @@ int sgi_comm_init(sgi_ctx* ctx, const void* id128, size_t bytes, int32_t rank, i
   SGI_NCCL(ctx, nccl().CommInitRank(&comm, nranks, id, rank));
   ctx->nccl_comm = comm; ctx->comm_rank = rank; ctx->comm_n = nranks;
   if (!ctx->comm_stream) SGI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
-  // The reductions get a communicator and a stream of their own (ncclCommSplit, every rank in one colour): collectives of one
-  // communicator run in issue order, and a frame's id gather must not queue behind the previous frame's reduction - that chain
-  // (accumulate -> reduce -> gather -> accumulate) was the frame time at 8 GPUs.  Without ncclCommSplit: one communicator for both.
+  // Option "comm_split" (set before this call): the reductions get a communicator and a stream of their own (ncclCommSplit, every
+  // rank in one colour), so that a frame's id gather does not queue behind the previous frame's reduction on the one stream.
+  // Measured at 8 GPUs it did not pay (the collectives' CTAs compete with the raster kernels for the SMs either way): off by default.
   ctx->nccl_comm2 = nullptr;
-  if (nranks > 1 && nccl().CommSplit) {
+  if (nranks > 1 && ctx->comm_split && nccl().CommSplit) {
     ncclComm_t c2 = nullptr;
     if (nccl().CommSplit(comm, 0, rank, &c2, nullptr) == ncclSuccess && c2) {
       ctx->nccl_comm2 = c2;

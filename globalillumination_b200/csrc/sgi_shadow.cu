@@ -641,11 +641,10 @@ namespace {
 // ================================ kernels ========================================================
 // VA / VB: compile-time tap counts of the specialised variants (PCF: VA = taps per axis; PCSS: VA = blocker taps,
 // VB = filter taps; 0 = generic run-time loops)
+// (the specialised PCF / PCSS variants wait on their taps: capped at 40 registers = 6 CTAs per SM, where they fit without spills;
+//  left to itself the compiler took 48 = 5 CTAs)
 template <int TECH, int VA, int VB>
-#ifndef SGI_VIS_MIN_CTAS
-#define SGI_VIS_MIN_CTAS 6
-#endif
-__global__ void __launch_bounds__(256, SGI_VIS_MIN_CTAS) k_visibility(const VisArgs a) {
+__global__ void __launch_bounds__(256, (VA > 0 ? 6 : 1)) k_visibility(const VisArgs a) {
   int x = a.rx0 + blockIdx.x * 32 + threadIdx.x, y = a.ry0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= a.rx1 || y >= a.ry1) return;
   size_t o = (size_t)y * a.W + x;

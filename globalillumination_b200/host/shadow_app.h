@@ -108,7 +108,8 @@ class ShadowApp {
   int measureLightCosts(float* ms, int n);   // depth-pass time of each of the n lights of renderMonteCarlo, one at a time (CUDA events)
   bool fusedMonteCarlo = false;   // renderMonteCarlo: camera pass reduced to primitive ids (sgi_render_prim_ids), positions resolved inside
                                   // the accumulation kernel (sgi_params.multi_fused); identical visibility, no vertex map materialised
-  bool commMasks = true;          // light shards of at most 32 lights exchange lit masks (1 B/pixel per 8 lights) instead of float sums
+  bool commMasks = false;         // light shards of at most 32 lights exchange lit masks (1 B/pixel per 8 lights) instead of float sums: the
+                                  // un-sharded bits for EVERY shadow intensity, but measured slower at 8 GPUs (1.13 vs 1.04 ms)
   bool commSkip = false;          // measurement aid: run the sharded frame without its exchanges (what the collectives cost = the difference)
   bool commOn = false;            // sgi_comm_init done (commInit): renderMonteCarlo exchanges id strips / partial sums over NCCL itself
   int commInit(const void* id128, size_t bytes, int rank, int world);   // joins the NCCL communicator; light shard = (rank, world)

@@ -308,6 +308,7 @@ int sgi_unregister_host(void* host_ptr);
  *                       in a kernel of their own (k_bin_big: a warp per record, all CTAs together on the largest) when the last
  *                       pass of the kind held enough records beyond 256 tiles - records x tiles >= "tile_bin_big_work" (default
  *                       2^20); otherwise every tile tests those records itself
+ *   "comm_split"      0 (default); 1 (before sgi_comm_init) = sgi_reduce_lights runs on a second communicator and stream (ncclCommSplit)
  *   "tile_few_walk"   1 (default) passes of at most 128 tiles bin their larger records tile-major, one list atomic per warp and tile
  *                       (the cursors of a few dozen tiles are contended by the whole GPU), 0 = pair by pair
  *   "sv_split_lists"  1 (default) hot tiles of the stencil pass are shared by list segment (every CTA counts its part of the

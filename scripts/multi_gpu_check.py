@@ -99,7 +99,7 @@ def main():
         print(f"C ABI tiles x{world}: sgi_gather(visibility) == un-sharded image: {same} (rows {r0}..{r1} on rank 0)", flush=True)
     app.close()
     # lights: 16 lights, fused many-light path (primitive-id strips all-gathered, partial sums reduce-scattered + divided)
-    # (exchange of lit masks - the default up to 32 lights - also with a shadow intensity that is not a dyadic fraction, where only
+    # (exchange of lit masks - host flag commMasks, up to 32 lights - also with a shadow intensity that is not a dyadic fraction, where only
     #  the masks reproduce the un-sharded accumulation order; and of float partial sums)
     for (Wl, Hl, masks, si) in ((2048, 1152, 1, None), (1000, 563, 1, 0.3), (1000, 563, 0, None)):   # 563 rows do not divide by the rank count: padded strips
         app = hostapi.App(local)
