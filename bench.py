@@ -392,9 +392,9 @@ def run_sharded(rank, world, local_rank, steps=24, warmup=4):
         "workload": name, "mode": "lights" if world > 1 else "single GPU (same code path, no exchange)", "n_gpus": world,
         "W": w["W"], "H": w["H"], "shadow_map": w["S"], "lights": n_l, "lights_per_rank": max(1, n_l // world), "triangles": int(idx.shape[0]),
         "scene": w["scene"], "frames_per_s": 1e3 / ms_frame, "ms_per_frame": ms_frame, "steps": steps, "scaling": "strong",
-        "collective": ("ncclAllGather(primitive-id strips, in place, %d MB) + ncclReduceScatter(lit masks, 1 bit per light and pixel in uint8 planes, "
-                       "in place, %d MB; %d MB as fp32 partial sums before), issued by the C ABI (sgi_gather / sgi_reduce_lights)"
-                       % (px * 4 // 1000000, px * ((n_l + 7) // 8) // 1000000, px * 4 // 1000000)) if world > 1 else None,
+        "collective": ("ncclAllGather(primitive-id strips, in place, %d MB) + ncclReduceScatter(fp32 partial visibility, in place, %d MB), "
+                       "issued by the C ABI (sgi_gather / sgi_reduce_lights); host flag commMasks exchanges lit masks (%d MB) instead"
+                       % (px * 4 // 1000000, px * 4 // 1000000, px * ((n_l + 7) // 8) // 1000000)) if world > 1 else None,
         "ms_per_frame_without_exchanges": ms_nocomm, "exposed_comm_ms": (ms_frame - ms_nocomm) if ms_nocomm is not None else 0.0,
         "pass_ms_rank0": passes, "strip_rows_rank0": [r0, r1], "lit_fraction_rank0_strip": lit,
         "tile_depth_ms_per_rank": [round(p.get("tile_depth", 0.0), 4) for p in all_passes],

@@ -263,6 +263,9 @@ __device__ __forceinline__ int setup_triangle(const SetupBinArgs& a, int t, SgiR
   base = -1;
   a.ovf_base[t] = -1;
   int i0 = a.idx[3 * t], i1 = a.idx[3 * t + 1], i2 = a.idx[3 * t + 2];
+  // a repeated index is a zero-area triangle whatever the matrix (the silhouette pass zeroes the index triples of the quads it
+  // drops: two thirds of a shadow-volume pass's slots): nothing to set up
+  if (i0 == i1 || i1 == i2 || i0 == i2) return 0;
   CV poly[3];
   poly[0] = xform(a.mvp, a.xyz[3 * (size_t)i0], a.xyz[3 * (size_t)i0 + 1], a.xyz[3 * (size_t)i0 + 2]);
   poly[1] = xform(a.mvp, a.xyz[3 * (size_t)i1], a.xyz[3 * (size_t)i1 + 1], a.xyz[3 * (size_t)i1 + 2]);
