@@ -648,6 +648,7 @@ struct OrderArgs {
   int2* order; int tiles_x, tx0, ty0, gx, gy, busiest_first, max_items, split_floor, n_sm;
   unsigned int* mm_min; unsigned int* mm_max; int mm_n;     // depth pass feeding the min-max cull: block extrema reset here (1.0 / 0.0)
   int big_binned;                                            // k_bin_big ran: the tile kernel has no big list to test
+  int big_work;                                              // records x tiles from which k_bin_big pays (option "tile_bin_big_work")
   int seg_split, max_level;                                  // stencil pass: hot tiles shared by list segment, up to 4^3 per tile, against a finer even share
 };
 #define SGI_ORDER_KEYS 256      // 64 weight buckets x 4 (3 levels used)
@@ -704,7 +705,10 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     if (lane == 0) {
       a.snap[0] = c0; a.snap[3] = a.big_binned ? 0 : c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
       a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0; a.counters[6] = 0; a.counters[7] = 0;
-      if (c7 != st_big) { a.d_sticky[8 + a.size_class] = c7; a.h_flags[8 + a.size_class] = c7; }      // records beyond SGI_BIG_TILES in this pass
+      // is k_bin_big worth launching for passes like this one (records beyond SGI_BIG_TILES x tiles)?  Only a CHANGE of the answer is
+      // written to the host-mapped word: a write across PCIe in every pass cost this kernel 4 us
+      const int want_big = ((long long)c7 * nl >= (long long)a.big_work) ? 1 : 0;
+      if (want_big != st_big) { a.d_sticky[8 + a.size_class] = want_big; a.h_flags[8 + a.size_class] = want_big; }
       // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
       // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
       // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
@@ -1890,8 +1894,8 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
 
   // passes of many tiles bin their big records too (k_bin_big)
   // (worth it where the tile CTAs would otherwise do many record tests: big records seen in the last pass of this kind x tiles)
-  const bool bin_big = ctx->tile_bin_big > 0 && n_rect_tiles >= ctx->tile_bin_big &&
-                       (long long)sc.h_flags[8 + size_class] * n_rect_tiles >= (long long)ctx->tile_bin_big_work;
+  const bool bin_big = ctx->tile_bin_big > 0 && n_rect_tiles >= ctx->tile_bin_big && (sc.h_flags[8 + size_class] != 0 || ctx->tile_bin_big_work <= 0);
+  oa.big_work = ctx->tile_bin_big_work > 0 ? ctx->tile_bin_big_work : 1;
   oa.big_binned = bin_big ? 1 : 0;
   // with k_bin_big the set-up kernel keeps only the records of up to 16 tiles for its own walk; 17 .. 2048 tiles: a warp each,
   // beyond: all CTAs together.  Without it: records beyond SGI_BIG_TILES are tested by every tile CTA.
