@@ -655,7 +655,12 @@ struct OrderArgs {
 #define SGI_ORDER_REG 16        // tiles per thread held in registers (grids up to 16 384 tiles: an 8192^2 map); larger grids re-read
 // (one global round trip on the critical path: the cursors and the binner's counters are all loaded up front; everything
 //  else happens in registers and shared memory; the work items are fire-and-forget stores)
+// SEG: the stencil pass's list-segment sharing (4^3 per tile, finer share) - a template parameter, and the big-record statistic is
+// handled by a thread of another warp: with them in the main path the kernel spilled (64 registers are all 1024 threads get) and
+// took 16 instead of 12 us on the c2 passes
+template <bool SEG>
 __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
+  constexpr int MAXLV = SEG ? 3 : 2;
   __shared__ int hist[SGI_ORDER_KEYS];
   __shared__ int red_sum[32], red_max[32];
   __shared__ int s_items, s_w;
@@ -665,8 +670,16 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   for (int k = tid; k < SGI_ORDER_KEYS; k += 1024) hist[k] = 0;
   SGI_GRID_DEP_WAIT();                                 // the binner's cursors and counters from here on
   if (a.mm_min) for (int i = tid; i < a.mm_n; i += 1024) { a.mm_min[i] = 0x3F800000u; a.mm_max[i] = 0u; }
-  int c0 = 0, c3 = 0, c5 = 0, c7 = 0, st_long = 0, st_tot = 0, st_big = 0;
-  if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; c7 = a.counters[7]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; st_big = a.d_sticky[8 + a.size_class]; }
+  int c0 = 0, c3 = 0, c5 = 0, st_long = 0, st_tot = 0;
+  if (tid == 0) { c0 = a.counters[0]; c3 = a.counters[3]; c5 = a.counters[5]; st_long = a.d_sticky[a.size_class]; st_tot = a.d_sticky[4 + a.size_class]; }
+  if (tid == 32) {
+    // is k_bin_big worth launching for passes like this one (records beyond SGI_BIG_TILES x tiles)?  Only a CHANGE of the answer is
+    // written to the host-mapped word
+    const int c7 = a.counters[7], st_big = a.d_sticky[8 + a.size_class];
+    const int want_big = ((long long)c7 * nl >= (long long)a.big_work) ? 1 : 0;
+    a.counters[7] = 0;
+    if (want_big != st_big) { a.d_sticky[8 + a.size_class] = want_big; a.h_flags[8 + a.size_class] = want_big; }
+  }
   // this thread's tiles of the job rectangle, i = tid + 1024 k: tile index and cursor
   int til[SGI_ORDER_REG], cnt[SGI_ORDER_REG];
   {
@@ -704,18 +717,14 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     int s2 = __reduce_add_sync(0xffffffffu, red_sum[lane]), m2 = __reduce_max_sync(0xffffffffu, red_max[lane]);
     if (lane == 0) {
       a.snap[0] = c0; a.snap[3] = a.big_binned ? 0 : c3; a.snap[2] = s2; a.snap[5] = min(c5, a.spill_cap);
-      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0; a.counters[6] = 0; a.counters[7] = 0;
-      // is k_bin_big worth launching for passes like this one (records beyond SGI_BIG_TILES x tiles)?  Only a CHANGE of the answer is
-      // written to the host-mapped word: a write across PCIe in every pass cost this kernel 4 us
-      const int want_big = ((long long)c7 * nl >= (long long)a.big_work) ? 1 : 0;
-      if (want_big != st_big) { a.d_sticky[8 + a.size_class] = want_big; a.h_flags[8 + a.size_class] = want_big; }
+      a.counters[0] = 0; a.counters[3] = 0; a.counters[5] = 0; a.counters[6] = 0;
       // longest list / largest pair total ever wanted (the host sizes the lists from them).  The running maxima live in device
       // memory and the host-mapped words are only ever WRITTEN: a read of host memory from this single-CTA kernel waits behind
       // whatever DMA traffic is on PCIe at the time (measured: +0.03 ms per pass while a frame is being copied out)
       if (m2 > st_long) { a.d_sticky[a.size_class] = m2; a.h_flags[1 + a.size_class] = m2; }
       if (s2 + c5 > st_tot) { a.d_sticky[4 + a.size_class] = s2 + c5; a.h_flags[4 + a.size_class] = s2 + c5; }
       if (c5 > a.spill_cap) a.h_flags[0] = 1;                   // entries were dropped: the frame is incomplete
-      s_w = a.split_floor > 0 ? max(a.seg_split ? a.split_floor / 2 : a.split_floor, s2 / ((a.seg_split ? 32 : 8) * a.n_sm)) : 0x7FFFFFF;
+      s_w = a.split_floor > 0 ? max(SEG ? a.split_floor / 2 : a.split_floor, s2 / ((SEG ? 32 : 8) * a.n_sm)) : 0x7FFFFFF;
     }
   }
   // list length per tile (what the tile kernel reads) | bit 30: the tile has further entries in the spill list
@@ -729,8 +738,8 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
     const int w = s_w;
     int local = 0;
 #pragma unroll
-    for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl && til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w, a.max_level));
-    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(min(c, a.cap), w, a.max_level)); }
+    for (int k = 0; k < SGI_ORDER_REG; k++) if (k * 1024 < nl && til[k] >= 0) local += 1 << (2 * split_level(cnt[k] & 0x3FFFFFFF, w, MAXLV));
+    if (!in_regs) for (int i = 1024 * SGI_ORDER_REG + tid; i < nl; i += 1024) { int c; tile_of(i, c); local += 1 << (2 * split_level(min(c, a.cap), w, MAXLV)); }
     local = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0 && local) atomicAdd(&s_items, local);
     __syncthreads();
@@ -740,7 +749,7 @@ __global__ void __launch_bounds__(1024) k_order(const OrderArgs a) {
   }
   const int w = s_w;
   // ---- histogram of the items over (weight bucket, level): one shared atomic per distinct key per warp
-  auto key_of = [&](int len) -> int { const int c = len & 0x3FFFFFFF; const int lv = split_level(c, w, a.max_level); return (a.busiest_first ? weight_bucket(c >> (a.seg_split ? 2 * lv : lv)) : 0) * 4 + lv; };
+  auto key_of = [&](int len) -> int { const int c = len & 0x3FFFFFFF; const int lv = split_level(c, w, MAXLV); return (a.busiest_first ? weight_bucket(c >> (SEG ? 2 * lv : lv)) : 0) * 4 + lv; };
   auto hist_step = [&](int key) {
     const unsigned grp = __match_any_sync(0xffffffffu, key);
     if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&hist[key], __popc(grp) << (2 * (key & 3)));
@@ -1904,7 +1913,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
   sc.needs_clear = true;                 // until k_order has been queued behind the binner
   k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
   if (bin_big) { SGI_CUDA(ctx, launch_pdl(k_bin_big, dim3(2 * ctx->n_sm), dim3(256), 0, st, ctx->pdl, sa)); ctx->launches++; }
-  SGI_CUDA(ctx, launch_pdl(k_order, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
+  SGI_CUDA(ctx, seg_split ? launch_pdl(k_order<true>, dim3(1), dim3(1024), 0, st, ctx->pdl, oa) : launch_pdl(k_order<false>, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
   ctx->launches += 2;
   SGI_CUDA(ctx, cudaGetLastError());
   sc.needs_clear = false;
@@ -1923,7 +1932,7 @@ int sgi_raster_run(sgi_ctx* ctx, const SgiRasterJob& job, int scratch_set, cudaS
       sc.needs_clear = true;
       k_setup_bin<<<sb_blocks, SGI_SB_THREADS, 0, st>>>(sa);
       if (bin_big) { SGI_CUDA(ctx, launch_pdl(k_bin_big, dim3(2 * ctx->n_sm), dim3(256), 0, st, ctx->pdl, sa)); ctx->launches++; }
-      SGI_CUDA(ctx, launch_pdl(k_order, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
+      SGI_CUDA(ctx, seg_split ? launch_pdl(k_order<true>, dim3(1), dim3(1024), 0, st, ctx->pdl, oa) : launch_pdl(k_order<false>, dim3(1), dim3(1024), 0, st, ctx->pdl, oa));
       ctx->launches += 2;
       SGI_CUDA(ctx, cudaGetLastError());
       sc.needs_clear = false;
