@@ -26,9 +26,10 @@ def main():
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
         name = d["Kernel Name"]
-        if name in seen:
+        key = (name, d.get("launch__grid_size", ""))          # the same kernel at another grid size is another pass (set-up of the camera / the volume pass)
+        if key in seen:
             continue
-        seen.add(name)
+        seen.add(key)
         print("----")
         print(f"  {'Kernel Name':<80s} {name}")
         for w in WANT:
