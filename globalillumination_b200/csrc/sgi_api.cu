@@ -61,19 +61,25 @@ void sgi_timing_end(sgi_ctx* ctx, int pass, int slot, cudaStream_t stream) {
   ctx->ev_n[pass] = slot + 1;
 }
 
-static int check_overflow(sgi_ctx* ctx) {
-  int rc = SGI_OK;
+// The overflow words are sticky and are looked at on every check, whatever pass raised them (they are host memory: a few loads).
+// On the pipelined path the word cannot be charged to one frame - frame k+1 is already queued when frame k's copy is waited for -
+// so a raised word condemns every read ticket issued so far (overflow_upto): each of them reports SGI_ERR_OVERFLOW at its
+// sgi_read_wait and none of them delivers a truncated frame as good.  `ticket_seq` < 0: a blocking check.
+static int check_overflow(sgi_ctx* ctx, long long ticket_seq = -1) {
   for (SgiScratch& sc : ctx->scratch) {
-    if (!sc.overflow_pending || !sc.h_flags) continue;
+    if (!sc.h_flags) continue;
     sc.overflow_pending = false;
     if (sc.h_flags[0]) {
       sc.h_flags[0] = 0;
       ctx->gbuffer_valid = false; ctx->shadow_map_valid = false;
-      ctx->err = "tile list overflow: the lists were re-sized, run the frame again";
-      rc = SGI_ERR_OVERFLOW;       // sgi_raster_run grows d_pairs from h_flags[1] on the next call
+      ctx->overflow_upto = ctx->read_seq;          // sgi_raster_run grows d_pairs from h_flags[1] on the next call
+      ctx->overflow_unreported = true;
     }
   }
-  return rc;
+  const bool bad = ticket_seq < 0 ? ctx->overflow_unreported : ticket_seq < ctx->overflow_upto;
+  if (bad || ticket_seq < 0) ctx->overflow_unreported = false;
+  if (bad) { ctx->err = "tile list overflow: the lists were re-sized, run the frame again"; return SGI_ERR_OVERFLOW; }
+  return SGI_OK;
 }
 
 // called after work that reads the G-buffer / rewrites the mesh has been queued on the main stream: the next G-buffer
@@ -966,7 +972,8 @@ int sgi_read_async(sgi_ctx* ctx, int32_t which, void* dst, size_t bytes, int32_t
   if (!ctx->buf[which] || bytes > ctx->buf_bytes[which]) { ctx->err = "sgi_read_async: buffer not produced yet or size too large"; return SGI_ERR_INVALID; }
   cudaSetDevice(ctx->device);
   sgi_join_gbuffer(ctx);
-  const int t = ctx->read_seq++ & 3;
+  const int t = ctx->read_seq & 3;
+  ctx->ticket_seq[t] = ctx->read_seq++;
   if (ctx->read_pending[t]) { SGI_CUDA(ctx, cudaEventSynchronize(ctx->read_done[t])); ctx->read_pending[t] = false; }   // back-pressure
   SGI_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->stream));                 // the buffer's producers are all on / joined into the main stream
   SGI_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
@@ -985,7 +992,7 @@ int sgi_read_wait(sgi_ctx* ctx, int32_t ticket) {
   if (!ctx || ticket < 0 || ticket > 3) return SGI_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->read_pending[ticket]) { SGI_CUDA(ctx, cudaEventSynchronize(ctx->read_done[ticket])); ctx->read_pending[ticket] = false; }
-  return check_overflow(ctx);
+  return check_overflow(ctx, ctx->ticket_seq[ticket]);
 }
 
 int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** dptr, size_t* bytes) {

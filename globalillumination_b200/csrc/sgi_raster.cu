@@ -510,11 +510,13 @@ __global__ void __launch_bounds__(SGI_SB_THREADS) k_setup_bin(const SetupBinArgs
       rr.X0 = b.X0; rr.Y0 = b.Y0; rr.X1 = b.X1; rr.Y1 = b.Y1; rr.X2 = b.X2; rr.Y2 = b.Y2;
       rr.z0 = b.z0; rr.dz1 = b.dz1; rr.dz2 = b.dz2; rr.ia = b.ia; rr.zoff = b.zoff;
       const int bx1 = b.bx0 + b.bw - 1, by1 = b.by0 + b.nt / b.bw - 1;
+      int cx = a.tx0, cy = a.ty0;                                  // the tile of step t, advanced without a division
       for (int t0 = 0; t0 < ntile; t0 += 4) {
         unsigned hits[4]; int pos[4], tl[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const int t = t0 + u, ty = a.ty0 + t / gx, tx = a.tx0 + t % gx;
+          const int t = t0 + u, ty = cy, tx = cx;
+          if (++cx > a.tx1) { cx = a.tx0; cy++; }
           const bool hit = live && t < ntile && tx >= b.bx0 && tx <= bx1 && ty >= b.by0 && ty <= by1 && tile_overlaps(rr, tx, ty, W, H) &&
                            !tile_behind_scene(rr, tx, ty, W, H, a.tile_zmax, a.tiles_x);
           hits[u] = __ballot_sync(0xffffffffu, hit);

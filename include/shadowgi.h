@@ -240,7 +240,9 @@ int sgi_device_ptr(sgi_ctx* ctx, int32_t which, void** device_ptr, size_t* bytes
  * for the copy on the device.  host_dst should be page-locked (sgi_alloc_host).  sgi_read_wait blocks the host until
  * the copy with that ticket has landed (up to 4 may be outstanding). */
 int sgi_read_async(sgi_ctx* ctx, int32_t which, void* host_dst, size_t bytes, int32_t* ticket);
-int sgi_read_wait(sgi_ctx* ctx, int32_t ticket);
+int sgi_read_wait(sgi_ctx* ctx, int32_t ticket);   /* SGI_ERR_OVERFLOW: a tile list overflowed in this frame or in one issued after it (the
+                                                      frames are pipelined): every ticket issued before the overflow was seen reports it; issue
+                                                      those frames again - the lists have been re-sized */
 int sgi_synchronize(sgi_ctx* ctx);
 /* Orders the context's stream after every pass queued so far (the G-buffer and shadow passes run on internal streams and
  * overlap the next frame's passes); does not block the host.  sgi_read*, sgi_device_ptr, sgi_shade_phong and

@@ -271,6 +271,55 @@ def test_tile_list_overflow_is_reported_and_recovered():
         c.close()
 
 
+def test_tile_list_overflow_on_the_pipelined_path():
+    """with frames pipelined (sgi_read_async, the next frame queued before the previous ticket is waited for) an overflow
+    cannot be charged to one frame; every ticket issued before the overflow was seen must report it - no truncated frame is
+    delivered as good - and re-issued frames come out right."""
+    import ctypes as C
+    from globalillumination_b200 import capi
+    c = capi.Context(0)
+    try:
+        lib = c.lib
+        W, H, S = 640, 480, 64
+        small, big = util.scene("door"), util.scene("tree")
+        po, pg = util.params_pair("hard", S)
+        fm = setup_frame(c, small, W, H, S, pg)
+        c.render_gbuffer(); c.compute_shadow_volume(small["light_eye"]); c.synchronize()      # lists sized for a few prisms
+        fm = setup_frame(c, big, W, H, S, pg)
+        ptrs, bufs = [], []
+        for _ in range(2):
+            p = C.c_void_p()
+            assert lib.sgi_alloc_host(C.byref(p), C.c_size_t(W * H * 4)) == 0
+            ptrs.append(p); bufs.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), (H, W)))
+        depth = None
+        good, reports = [], 0
+        for rnd in range(8):
+            tickets = []
+            for k in range(2):                                                               # two frames in flight
+                c.render_gbuffer(); c.compute_shadow_volume(big["light_eye"])
+                tickets.append(c.read_async("sv_count", ptrs[k].value, W * H * 4))
+            ok = []
+            for k, t in enumerate(tickets):
+                try:
+                    c.read_wait(t); ok.append(k)
+                except capi.SgiError as e:
+                    assert e.code == -4
+                    reports += 1
+            if len(ok) == 2:
+                good = [bufs[0].copy(), bufs[1].copy()]
+                break
+        assert reports >= 1 and good, (reports, len(good))
+        depth = c.read("cam_depth")
+        pxyz, pidx = O.sv_build_prisms(big["xyz"], big["nrm"], big["idx"], big["light_eye"])
+        cnt_o, _ = O.sv_count(pxyz, pidx, fm["cam_mvp"], W, H, depth)
+        assert np.array_equal(good[0], cnt_o) and np.array_equal(good[1], cnt_o)
+        c.synchronize()
+        for p in ptrs:
+            lib.sgi_free_host(p)
+    finally:
+        c.close()
+
+
 def test_empty_and_degenerate_inputs(ctx):
     from globalillumination_b200 import capi
     sc = util.scene("door")
